@@ -1,0 +1,332 @@
+"""ctypes binding of libdcb.so (include/dcb.h).  Thin: every call is a C-ABI call.
+
+The library is built in-tree by ``decombinator_b200.build``.  There is no Python or CPU fallback
+for the compute entry points: if the library is missing it is built, if that fails or no GPU is
+usable the call raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+NCOUNTERS = 20
+NTIMERS = 4
+
+RESULT_DTYPE = np.dtype([
+    ("status", "u1"), ("frame", "u1"), ("v", "u1"), ("j", "u1"),
+    ("vdel", "<u2"), ("jdel", "<u2"), ("ins_start", "<u2"), ("ins_end", "<u2"),
+    ("v_seq_start", "<u2"), ("j_seq_end", "<u2"),
+])
+assert RESULT_DTYPE.itemsize == 16
+
+
+class DcbError(RuntimeError):
+    pass
+
+
+class CPacked(ctypes.Structure):
+    _fields_ = [
+        ("n_reads", ctypes.c_uint64), ("slot_words", ctypes.c_uint32), ("uniform_len", ctypes.c_uint32),
+        ("max_len", ctypes.c_uint32), ("n_exc", ctypes.c_uint32),
+        ("words", ctypes.POINTER(ctypes.c_uint32)), ("lens", ctypes.POINTER(ctypes.c_uint16)),
+        ("flags", ctypes.POINTER(ctypes.c_uint32)), ("exc_read", ctypes.POINTER(ctypes.c_uint32)),
+        ("exc_pos", ctypes.POINTER(ctypes.c_uint16)), ("exc_kind", ctypes.POINTER(ctypes.c_uint8)),
+        ("owner", ctypes.c_void_p),
+    ]
+
+
+class CParams(ctypes.Structure):
+    _fields_ = [("both_frames", ctypes.c_int32), ("allow_ns", ctypes.c_int32), ("lenthreshold", ctypes.c_int32),
+                ("force_general", ctypes.c_int32)]
+
+
+class CSynthParams(ctypes.Structure):
+    _fields_ = [("seed", ctypes.c_uint64), ("read_len", ctypes.c_uint32), ("read2_len", ctypes.c_uint32),
+                ("sub_rate", ctypes.c_uint32), ("n_rate", ctypes.c_uint32), ("junk_rate", ctypes.c_uint32),
+                ("umi_pool", ctypes.c_uint32)]
+
+
+_lib = None
+
+
+def lib():
+    """Load (building if needed) libdcb.so and declare the prototypes of include/dcb.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.build()
+    L = ctypes.CDLL(path)
+    vp, i32, u64, u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint32
+    cpp = ctypes.POINTER(ctypes.c_char_p)
+    L.dcb_last_error.restype = ctypes.c_char_p
+    L.dcb_abi_version.restype = i32
+    L.dcb_counter_name.restype = ctypes.c_char_p
+    L.dcb_counter_name.argtypes = [i32]
+    L.dcb_tagset_build.restype = vp
+    L.dcb_tagset_build.argtypes = [cpp, ctypes.POINTER(ctypes.c_int32), cpp, i32, i32, i32]
+    L.dcb_tagset_free.argtypes = [vp]
+    L.dcb_tagset_table_bytes.restype = ctypes.c_size_t
+    L.dcb_tagset_table_bytes.argtypes = [vp]
+    L.dcb_tagset_blob.argtypes = [vp, i32, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint32)), ctypes.POINTER(ctypes.c_size_t)]
+    L.dcb_pack_reads.argtypes = [vp, vp, vp, u64, i32, i32, ctypes.POINTER(ctypes.POINTER(CPacked))]
+    L.dcb_packed_free.argtypes = [ctypes.POINTER(CPacked)]
+    L.dcb_unpack_read.argtypes = [ctypes.POINTER(CPacked), u64, ctypes.c_char_p, u32]
+    L.dcb_ctx_create.restype = vp
+    L.dcb_ctx_create.argtypes = [i32, vp, vp, ctypes.POINTER(CParams)]
+    L.dcb_ctx_destroy.argtypes = [vp]
+    L.dcb_ctx_set_stream.argtypes = [vp, vp]
+    L.dcb_decombine_batch.argtypes = [vp, ctypes.POINTER(CPacked), vp, vp]
+    L.dcb_upload.argtypes = [vp, ctypes.POINTER(CPacked)]
+    L.dcb_run_resident.argtypes = [vp]
+    L.dcb_download.argtypes = [vp, vp, vp]
+    L.dcb_timing_reset.argtypes = [vp]
+    L.dcb_timing_enable.argtypes = [vp, i32]
+    L.dcb_timing_get.argtypes = [vp, vp, vp]
+    L.dcb_last_deferred.argtypes = [vp, ctypes.POINTER(u64)]
+    L.dcb_synth_create.restype = vp
+    L.dcb_synth_create.argtypes = [ctypes.POINTER(CSynthParams), i32, ctypes.POINTER(cpp), ctypes.POINTER(ctypes.c_int),
+                                   ctypes.POINTER(cpp), ctypes.POINTER(ctypes.c_int)]
+    L.dcb_synth_destroy.argtypes = [vp]
+    L.dcb_synth_reads.argtypes = [vp, u64, u64, vp, vp, i32]
+    _lib = L
+    return L
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise DcbError("%s failed (%d): %s" % (what, rc, lib().dcb_last_error().decode()))
+
+
+def counter_names():
+    L = lib()
+    return [L.dcb_counter_name(i).decode() for i in range(NCOUNTERS)]
+
+
+def _carr(strings):
+    arr = (ctypes.c_char_p * len(strings))()
+    arr[:] = [s.encode() if isinstance(s, str) else s for s in strings]
+    return arr
+
+
+class TagTables:
+    """dcb_tagset: the flattened automaton/bitmap tables of one gene (V or J)."""
+
+    def __init__(self, tags, jumps, regions, half_split, is_v):
+        L = lib()
+        n = len(tags)
+        self._h = L.dcb_tagset_build(_carr(tags), (ctypes.c_int32 * n)(*jumps), _carr(list(regions)[:n]), n,
+                                     int(half_split), int(is_v))
+        if not self._h:
+            raise DcbError("dcb_tagset_build: " + L.dcb_last_error().decode())
+
+    @property
+    def handle(self):
+        return self._h
+
+    def table_bytes(self):
+        return lib().dcb_tagset_table_bytes(self._h)
+
+    def blob(self, which):
+        p = ctypes.POINTER(ctypes.c_uint32)()
+        n = ctypes.c_size_t()
+        _check(lib().dcb_tagset_blob(self._h, which, ctypes.byref(p), ctypes.byref(n)), "dcb_tagset_blob")
+        return np.ctypeslib.as_array(p, shape=(n.value,))
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().dcb_tagset_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class Packed:
+    """dcb_packed: 2-bit packed read slots (+ sparse non-ACGT list) in page-locked host memory."""
+
+    def __init__(self, ptr):
+        self._p = ptr
+
+    @property
+    def c(self):
+        return self._p
+
+    @property
+    def n_reads(self):
+        return int(self._p.contents.n_reads)
+
+    @property
+    def slot_words(self):
+        return int(self._p.contents.slot_words)
+
+    @property
+    def n_exc(self):
+        return int(self._p.contents.n_exc)
+
+    @property
+    def uniform_len(self):
+        return int(self._p.contents.uniform_len)
+
+    @property
+    def max_len(self):
+        return int(self._p.contents.max_len)
+
+    def words(self):
+        c = self._p.contents
+        return np.ctypeslib.as_array(c.words, shape=(max(1, self.n_reads * self.slot_words),))[: self.n_reads * self.slot_words]
+
+    def nbytes(self):
+        c = self._p.contents
+        n = self.n_reads
+        return n * self.slot_words * 4 + n * 2 + ((n + 31) // 32) * 4 + c.n_exc * 7
+
+    def unpack(self, i):
+        buf = ctypes.create_string_buffer(self.max_len + 1)
+        n = lib().dcb_unpack_read(self._p, i, buf, self.max_len + 1)
+        if n < 0:
+            raise DcbError("dcb_unpack_read")
+        return buf.raw[:n].decode()
+
+    def free(self):
+        if self._p is not None:
+            lib().dcb_packed_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def pack_arrays(buf, off, length, revcomp, n_threads=None) -> Packed:
+    """dcb_pack_reads over reads stored in one uint8 buffer (off: uint64 offsets, length: uint32)."""
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.uint64)
+    length = np.ascontiguousarray(length, dtype=np.uint32)
+    out = ctypes.POINTER(CPacked)()
+    nt = n_threads or min(32, os.cpu_count() or 1)
+    _check(lib().dcb_pack_reads(buf.ctypes.data, off.ctypes.data, length.ctypes.data, len(off), int(bool(revcomp)), nt,
+                                ctypes.byref(out)), "dcb_pack_reads")
+    return Packed(out)
+
+
+def pack_strings(reads, revcomp, n_threads=1) -> Packed:
+    bufs = [r.encode("latin-1") if isinstance(r, str) else r for r in reads]
+    length = np.array([len(b) for b in bufs], dtype=np.uint32)
+    off = np.zeros(len(bufs), dtype=np.uint64)
+    if len(bufs) > 1:
+        off[1:] = np.cumsum(length[:-1], dtype=np.uint64)
+    buf = np.frombuffer(b"".join(bufs) + b"\0", dtype=np.uint8)
+    return pack_arrays(buf, off, length, revcomp, n_threads)
+
+
+class Context:
+    """dcb_ctx: device tables + batch buffers + stream of one GPU."""
+
+    def __init__(self, vset: TagTables, jset: TagTables, device=0, both_frames=False, allow_ns=False,
+                 lenthreshold=130, force_general=False):
+        L = lib()
+        prm = CParams(int(bool(both_frames)), int(bool(allow_ns)), int(lenthreshold), int(bool(force_general)))
+        self._keep = (vset, jset)
+        self._h = L.dcb_ctx_create(int(device), vset.handle, jset.handle, ctypes.byref(prm))
+        if not self._h:
+            raise DcbError("dcb_ctx_create: " + L.dcb_last_error().decode())
+
+    def set_stream(self, cuda_stream):
+        _check(lib().dcb_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream)), "dcb_ctx_set_stream")
+
+    def decombine(self, packed: Packed, counters=None):
+        """dcb_decombine_batch: host buffers in, host buffers out."""
+        res = np.zeros(packed.n_reads, dtype=RESULT_DTYPE)
+        if counters is None:
+            counters = np.zeros(NCOUNTERS, dtype=np.uint64)
+        _check(lib().dcb_decombine_batch(self._h, packed.c, res.ctypes.data, counters.ctypes.data), "dcb_decombine_batch")
+        return res, counters
+
+    def upload(self, packed: Packed):
+        _check(lib().dcb_upload(self._h, packed.c), "dcb_upload")
+        self._n = packed.n_reads
+
+    def run_resident(self):
+        _check(lib().dcb_run_resident(self._h), "dcb_run_resident")
+
+    def download(self, counters=None, want_results=True):
+        res = np.zeros(self._n, dtype=RESULT_DTYPE) if want_results else None
+        if counters is None:
+            counters = np.zeros(NCOUNTERS, dtype=np.uint64)
+        _check(lib().dcb_download(self._h, res.ctypes.data if want_results else None, counters.ctypes.data), "dcb_download")
+        return res, counters
+
+    def timing_enable(self, on=True):
+        _check(lib().dcb_timing_enable(self._h, int(on)), "dcb_timing_enable")
+
+    def timing_reset(self):
+        _check(lib().dcb_timing_reset(self._h), "dcb_timing_reset")
+
+    def timing_get(self):
+        ms = np.zeros(NTIMERS, dtype=np.float64)
+        n = np.zeros(NTIMERS, dtype=np.uint64)
+        _check(lib().dcb_timing_get(self._h, ms.ctypes.data, n.ctypes.data), "dcb_timing_get")
+        return ms, n
+
+    def last_deferred(self):
+        n = ctypes.c_uint64()
+        _check(lib().dcb_last_deferred(self._h, ctypes.byref(n)), "dcb_last_deferred")
+        return n.value
+
+    def close(self):
+        if self._h:
+            lib().dcb_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Synth:
+    """dcb_synth: deterministic synthetic read generator."""
+
+    def __init__(self, gene_sets, seed, read_len, read2_len=0, sub_rate=0.0, n_rate=0.0, junk_rate=0.0, umi_pool=0):
+        """gene_sets: list of (v_regions, j_regions); read i is drawn from set i % len(gene_sets)."""
+        L = lib()
+        self.read_len, self.read2_len = int(read_len), int(read2_len)
+
+        def prob(x):
+            return min(0xFFFFFFFF, int(round(x * 4294967296.0)))
+
+        prm = CSynthParams(int(seed), self.read_len, self.read2_len, prob(sub_rate), prob(n_rate), prob(junk_rate),
+                           int(umi_pool))
+        n = len(gene_sets)
+        cpp = ctypes.POINTER(ctypes.c_char_p)
+        self._keep = [(_carr(v), _carr(j)) for v, j in gene_sets]
+        varr = (cpp * n)(*[ctypes.cast(k[0], cpp) for k in self._keep])
+        jarr = (cpp * n)(*[ctypes.cast(k[1], cpp) for k in self._keep])
+        nv = (ctypes.c_int * n)(*[len(v) for v, _ in gene_sets])
+        nj = (ctypes.c_int * n)(*[len(j) for _, j in gene_sets])
+        self._h = L.dcb_synth_create(ctypes.byref(prm), n, varr, nv, jarr, nj)
+        if not self._h:
+            raise DcbError("dcb_synth_create failed")
+
+    def reads(self, first, n, want_r2=False, n_threads=None):
+        r1 = np.empty(n * self.read_len, dtype=np.uint8)
+        r2 = np.empty(n * self.read2_len, dtype=np.uint8) if (want_r2 and self.read2_len) else None
+        nt = n_threads or min(32, os.cpu_count() or 1)
+        _check(lib().dcb_synth_reads(self._h, int(first), int(n), r1.ctypes.data,
+                                     r2.ctypes.data if r2 is not None else None, nt), "dcb_synth_reads")
+        return r1, r2
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().dcb_synth_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass

@@ -1,0 +1,94 @@
+// dcb_tables.h -- flattened tag tables shared by the host builder (tagset.cpp) and the kernels.
+//
+// One gene (V or J) becomes ONE blob of 32-bit words that a thread block stages in shared memory.
+// It replaces the six acora automata per chain of the reference (decombine.py:722-746):
+//
+//   * three keyword sets (full tags, half1 = tag[:split], half2 = tag[split:]), each searchable at
+//     every END position through a suffix-k-mer bitmap + a small open-addressing hash that lists the
+//     distinct keywords ending in that k-mer (longest first = findall() order at equal end);
+//   * a sampled-seed filter for the exact-tag fast path: every occurrence of a full tag of length
+//     >= Lmin contains a q-mer starting at a multiple of stride = Lmin-q+1, so only n/stride
+//     positions are looked up; a seed hit maps (hash) to the set of tag offsets that q-mer occurs
+//     at, and a candidate start is confirmed through a hash of the tags' Lmin-prefix;
+//   * per-tag records (packed tag, length, jump, first-tag-with-same-half lengths, the last / first
+//     32 germline bases for the bit-parallel deletion walk) and the 2-bit packed germline regions.
+//
+// All offsets are in 32-bit words from the start of the blob.
+#ifndef DCB_TABLES_H
+#define DCB_TABLES_H
+
+#include <stdint.h>
+
+#define DCB_MAX_TAG_LEN 32
+#define DCB_MAX_TAGS 255
+#define DCB_MAX_READ_LEN 4096
+#define DCB_HASH_EMPTY 0xFFFFFFFFu
+
+// One distinct keyword of a keyword set (16 bytes = 4 words).
+struct DcbKw {
+    uint32_t bits_lo, bits_hi;  // 2-bit packed keyword, base 0 in bits [0,2)
+    uint8_t len;                // bases
+    uint8_t first_tag;          // list.index(keyword): first tag whose full/half1/half2 equals it
+    uint8_t n_tags;             // tags sharing the keyword (ascending in the tag list)
+    uint8_t tags_off;           // offset of those tag ids in the set's byte list
+    uint32_t pad;
+};
+
+// One keyword set == one acora automaton of the reference.
+struct DcbKwSet {
+    int32_t n_kw;        // distinct keywords
+    int32_t kq;          // suffix key length in bases (min(min_len, 8))
+    int32_t bitmap_off;  // 4^kq bits
+    int32_t hash_off;    // hash_size slots: (key << 16) | (first_kw << 8) | count ; DCB_HASH_EMPTY
+    int32_t hash_mask;   // hash_size - 1
+    int32_t kw_off;      // DcbKw[n_kw] grouped by suffix key, longest first inside a group
+    int32_t taglist_off; // bytes: tag ids
+    int32_t min_len, max_len;
+};
+
+// Per-tag record (32 bytes = 8 words).
+struct DcbTag {
+    uint32_t bits_lo, bits_hi;   // packed full tag
+    uint32_t edge_lo, edge_hi;   // V: last 32 germline bases (region[m-32:m]); J: first 32 (region[0:32])
+    int16_t jump;                // jump_to_end_v / jump_to_start_j
+    int16_t region_len;          // m
+    int32_t region_off;          // packed region words
+    uint8_t len;                 // tag length
+    uint8_t h1_first_len;        // len(tags[half1 list .index(half1 of this tag)])  (length-guard quirk)
+    uint8_t h2_first_len;
+    uint8_t edge_ok;             // region_len >= 32
+    uint32_t pad;
+};
+
+struct DcbGene {
+    int32_t n_tags, split, is_v;
+    int32_t tag_off;             // DcbTag[n_tags]
+    DcbKwSet full, half1, half2;
+    // exact-tag fast path
+    int32_t lmin;                // shortest full tag
+    int32_t q, stride;           // seed length, sampling stride (lmin - q + 1)
+    int32_t seedmap_off;         // 4^q bits
+    int32_t seedhash_off;        // seedhash_size * 2 words: [key, offset mask]; key == DCB_HASH_EMPTY when free
+    int32_t seedhash_mask;
+    int32_t prefhash_off;        // prefhash_size words: tag id or DCB_HASH_EMPTY, hashed on the lmin-prefix
+    int32_t prefhash_mask;
+    int32_t n_words;             // blob size
+    int32_t general_words;       // words [0, general_words) are all the general kernel needs
+};
+
+#if defined(__CUDACC__)
+#define DCB_HD __host__ __device__ __forceinline__
+#else
+#define DCB_HD inline
+#endif
+
+DCB_HD uint32_t dcb_hash32(uint32_t k) {
+    k *= 0x9E3779B1u;
+    return k ^ (k >> 15);
+}
+DCB_HD uint32_t dcb_hash64(uint32_t lo, uint32_t hi) {
+    uint32_t k = lo * 0x9E3779B1u + hi * 0x85EBCA77u;
+    return k ^ (k >> 13);
+}
+
+#endif

@@ -1,0 +1,621 @@
+// dcr_core.cuh -- the per-read decombine logic, written once for the device.
+//
+// Every function is __host__ __device__ so that tests/sim can compile the SAME code with g++ and
+// check its logic against the oracle on a machine without a GPU.  The host build is test
+// scaffolding only: libdcb.so exports no CPU compute path.
+//
+// Behavioural spec: /root/reference/src/decombinator/decombine.py (cited per function as :line).
+// The matching itself is NOT the reference's algorithm (six byte-wise Aho-Corasick scans per read);
+// see dcb_tables.h for the table design.  What is preserved is the observable contract: the
+// findall() hit order, the candidate / guard / Hamming / deletion-walk sequence with Python's slice
+// semantics, every counter increment, and the seven values dcr() returns.
+#ifndef DCR_CORE_CUH
+#define DCR_CORE_CUH
+
+#include "dcb_tables.h"
+#include "../../include/dcb.h"
+
+#if defined(__CUDA_ARCH__)
+#define DCB_COUNT(C, id) atomicAdd(&(C)[id], 1u)
+#define DCB_POPC(x) __popc(x)
+#define DCB_FUNNEL_R(lo, hi, sh) __funnelshift_r((lo), (hi), (sh))
+#define DCB_BREV(x) __brev(x)
+#define DCB_CLZ(x) __clz(x)
+#define DCB_FFS(x) __ffs(x)
+#else
+#define DCB_COUNT(C, id) ((C)[id] += 1u)
+#define DCB_POPC(x) __builtin_popcount(x)
+static inline uint32_t dcb_funnel_r_host(uint32_t lo, uint32_t hi, int sh) {
+    sh &= 31;
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+}
+static inline uint32_t dcb_brev_host(uint32_t x) {
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+    x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+    return (x >> 16) | (x << 16);
+}
+#define DCB_FUNNEL_R(lo, hi, sh) dcb_funnel_r_host((lo), (hi), (sh))
+#define DCB_BREV(x) dcb_brev_host(x)
+#define DCB_CLZ(x) ((x) ? __builtin_clz(x) : 32)
+#define DCB_FFS(x) __builtin_ffs(x)
+#endif
+
+typedef uint32_t dcb_cnt_t;  // per-block (device) or per-call (sim) counter slots
+
+// ------------------------------------------------------------------------------------------------
+// A read as the kernels see it: 2-bit words, strided (shared memory is laid out [word][thread] so a
+// dynamic word index never causes a bank conflict), plus the sparse non-ACGT information.
+// ------------------------------------------------------------------------------------------------
+struct ReadView {
+    const uint32_t* w;      // word i at w[i * stride]
+    const uint32_t* inv;    // invalid-base bitmask (bit b of word i <-> base 32 i + b), same stride; null = none
+    int stride;
+    int n;                  // bases
+    int nw;                 // words available (reads past them yield 0)
+    // exception list of this read in the frame being analysed (positions already mapped to the frame)
+    const uint16_t* exc_pos;
+    const uint8_t* exc_kind;
+    int e0, e1;
+    int mirror;             // frame 1: position p of the frame is exception position n-1-p
+};
+
+DCB_HD uint32_t rd_word(const ReadView& r, int i) {
+    return ((unsigned)i < (unsigned)r.nw) ? r.w[i * r.stride] : 0u;
+}
+// 16 bases starting at base p (p may be negative or run past the end: missing bases read as 0)
+DCB_HD uint32_t rd_win16(const ReadView& r, int p) {
+    int wi = p >> 4;
+    return DCB_FUNNEL_R(rd_word(r, wi), rd_word(r, wi + 1), (p & 15) * 2);
+}
+DCB_HD void rd_win32(const ReadView& r, int p, uint32_t& lo, uint32_t& hi) {
+    int wi = p >> 4, sh = (p & 15) * 2;
+    uint32_t a = rd_word(r, wi), b = rd_word(r, wi + 1), c = rd_word(r, wi + 2);
+    lo = DCB_FUNNEL_R(a, b, sh);
+    hi = DCB_FUNNEL_R(b, c, sh);
+}
+DCB_HD bool rd_inv_at(const ReadView& r, int p) {
+    return r.inv && ((r.inv[(p >> 5) * r.stride] >> (p & 31)) & 1u);
+}
+// any invalid base in [a, b), 0 <= a, b <= n
+DCB_HD bool rd_inv_any(const ReadView& r, int a, int b) {
+    if (!r.inv || a >= b) return false;
+    for (int wi = a >> 5; wi <= ((b - 1) >> 5); wi++) {
+        int lo = a > wi * 32 ? a - wi * 32 : 0;
+        int hi = b < wi * 32 + 32 ? b - wi * 32 : 32;
+        uint32_t mask = (hi - lo == 32) ? 0xFFFFFFFFu : (((1u << (hi - lo)) - 1u) << lo);
+        if (r.inv[wi * r.stride] & mask) return true;
+    }
+    return false;
+}
+// "N" in read[a:b]  (only exceptions of kind 1 are the letter N)
+DCB_HD bool rd_has_N(const ReadView& r, int a, int b) {
+    for (int e = r.e0; e < r.e1; e++) {
+        if (r.exc_kind[e] != 1) continue;
+        int p = r.mirror ? r.n - 1 - (int)r.exc_pos[e] : (int)r.exc_pos[e];
+        if (p >= a && p < b) return true;
+    }
+    return false;
+}
+
+DCB_HD uint32_t mask2(int nbases) {  // low 2*nbases bits, nbases in [0,16]
+    return nbases >= 16 ? 0xFFFFFFFFu : ((1u << (2 * nbases)) - 1u);
+}
+
+// read[s:s+L] == keyword (0 <= s, s+L <= n, L <= 32); invalid bases never match
+DCB_HD bool rd_equals(const ReadView& r, int s, int L, uint32_t klo, uint32_t khi) {
+    uint32_t lo, hi;
+    rd_win32(r, s, lo, hi);
+    uint32_t mlo = mask2(L), mhi = L > 16 ? mask2(L - 16) : 0u;
+    if (((lo ^ klo) & mlo) | ((hi ^ khi) & mhi)) return false;
+    return !rd_inv_any(r, s, s + L);
+}
+
+// lev.hamming(tag, read[s:s+L]) <= 1   (decombine.py:309, 359, 436, 493)
+DCB_HD bool rd_hamming_le1(const ReadView& r, int s, int L, uint32_t klo, uint32_t khi) {
+    uint32_t lo, hi;
+    rd_win32(r, s, lo, hi);
+    uint32_t xlo = (lo ^ klo) & mask2(L), xhi = L > 16 ? ((hi ^ khi) & mask2(L - 16)) : 0u;
+    uint32_t nlo = (xlo | (xlo >> 1)) & 0x55555555u, nhi = (xhi | (xhi >> 1)) & 0x55555555u;
+    if (!r.inv || !rd_inv_any(r, s, s + L)) return DCB_POPC(nlo) + DCB_POPC(nhi) <= 1;
+    int d = 0;  // rare: the window holds non-ACGT symbols, each one is a mismatch
+    for (int i = 0; i < L; i++) {
+        uint32_t nq = i < 16 ? (nlo >> (2 * i)) & 1u : (nhi >> (2 * (i - 16))) & 1u;
+        d += (rd_inv_at(r, s + i) || nq) ? 1 : 0;
+    }
+    return d <= 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Germline regions (2-bit packed in the blob)
+// ------------------------------------------------------------------------------------------------
+DCB_HD uint32_t rg_win16(const uint32_t* blob, const DcbTag& t, int p) {
+    int nw = (t.region_len + 15) >> 4;
+    int wi = p >> 4;
+    uint32_t a = ((unsigned)wi < (unsigned)nw) ? blob[t.region_off + wi] : 0u;
+    uint32_t b = ((unsigned)(wi + 1) < (unsigned)nw) ? blob[t.region_off + wi + 1] : 0u;
+    return DCB_FUNNEL_R(a, b, (p & 15) * 2);
+}
+
+// Python s[start:stop] bounds on a sequence of length len
+struct Span { int a, b; };
+DCB_HD Span py_slice(int len, int start, int stop) {
+    if (start < 0) { start += len; if (start < 0) start = 0; } else if (start > len) start = len;
+    if (stop < 0) { stop += len; if (stop < 0) stop = 0; } else if (stop > len) stop = len;
+    if (stop < start) stop = start;
+    Span s; s.a = start; s.b = stop;
+    return s;
+}
+
+// region[a] == read[b] as Python strings (both at most 10 long here)
+DCB_HD bool slices_equal(const uint32_t* blob, const DcbTag& t, Span a, const ReadView& r, Span b) {
+    int la = a.b - a.a;
+    if (la != b.b - b.a) return false;
+    if (la == 0) return true;
+    uint32_t x = (rg_win16(blob, t, a.a) ^ rd_win16(r, b.a)) & mask2(la);
+    if (x) return false;
+    return !rd_inv_any(r, b.a, b.b);
+}
+
+DCB_HD const DcbTag& gene_tag(const uint32_t* blob, const DcbGene& g, int k) {
+    return reinterpret_cast<const DcbTag*>(blob + g.tag_off)[k];
+}
+
+// get_v_deletions (decombine.py:749-785), literal walk with Python slice semantics
+DCB_HD bool v_deletions_general(const ReadView& r, const uint32_t* blob, const DcbTag& t, int temp_end_v,
+                                int& end_v, int& dels, dcb_cnt_t* C) {
+    const int n = r.n, m = t.region_len;
+    if (temp_end_v >= n) {                                   // :760-762
+        DCB_COUNT(C, DCB_C_v_del_failed_tag_at_end);
+        return false;
+    }
+    int f = temp_end_v + 1, pos = m - 10, nd = 0;            // :754-765
+    while (0 <= f && f < n) {                                // :767
+        if (slices_equal(blob, t, py_slice(m, pos, pos + 10), r, py_slice(n, f - 10, f))) {  // :769-772
+            dels = nd;                                       // :774-775
+            end_v = temp_end_v - nd;
+            return true;
+        }
+        pos--; nd++; f--;                                    // :777-779
+    }
+    DCB_COUNT(C, DCB_C_v_del_failed);                        // :784
+    return false;
+}
+
+// get_j_deletions (decombine.py:788-817)
+DCB_HD bool j_deletions_general(const ReadView& r, const uint32_t* blob, const DcbTag& t, int temp_start_j,
+                                int end_of_v, int& start_j, int& dels, dcb_cnt_t* C) {
+    const int n = r.n, m = t.region_len;
+    int f = temp_start_j, pos = 0;
+    while (0 <= f + 2 && f + 2 < n) {                        // :795
+        if (f < end_of_v) {                                  // :798-800
+            pos++; f++;
+        } else if (slices_equal(blob, t, py_slice(m, pos, pos + 10), r, py_slice(n, f, f + 10))) {  // :802-805
+            dels = pos;                                      // :807-808
+            start_j = f;
+            return true;
+        } else {
+            pos++; f++;                                      // :810-811
+        }
+    }
+    DCB_COUNT(C, DCB_C_j_del_failed);                        // :816
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// findall() of one keyword set as a resumable generator: hits come out ordered by END position,
+// longest keyword first at equal end -- the order acora reports them in.
+// ------------------------------------------------------------------------------------------------
+struct KwScan { int e, ci, cend; };
+
+DCB_HD void kw_scan_init(KwScan& s, const DcbKwSet& ks) {
+    s.e = ks.kq - 1;
+    s.ci = s.cend = 0;
+}
+
+DCB_HD const DcbKw& kwset_kw(const uint32_t* blob, const DcbKwSet& ks, int c) {
+    return reinterpret_cast<const DcbKw*>(blob + ks.kw_off)[c];
+}
+
+DCB_HD bool kw_scan_next(const ReadView& r, const uint32_t* blob, const DcbKwSet& ks, KwScan& s, int& kw, int& start) {
+    const uint32_t kmask = mask2(ks.kq);
+    for (;;) {
+        while (s.ci < s.cend) {
+            int c = s.ci++;
+            const DcbKw& k = kwset_kw(blob, ks, c);
+            int st = s.e - (int)k.len;
+            if (st < 0) continue;
+            if (rd_equals(r, st, k.len, k.bits_lo, k.bits_hi)) { kw = c; start = st; return true; }
+        }
+        s.e++;
+        if (s.e > r.n) return false;
+        uint32_t key = rd_win16(r, s.e - ks.kq) & kmask;
+        if (!((blob[ks.bitmap_off + (key >> 5)] >> (key & 31)) & 1u)) continue;
+        uint32_t h = dcb_hash32(key) & (uint32_t)ks.hash_mask;
+        for (;;) {
+            uint32_t slot = blob[ks.hash_off + h];
+            if (slot == DCB_HASH_EMPTY) break;
+            if ((slot >> 16) == key) {
+                s.ci = (int)((slot >> 8) & 255u);
+                s.cend = s.ci + (int)(slot & 255u);
+                break;
+            }
+            h = (h + 1) & (uint32_t)ks.hash_mask;
+        }
+    }
+}
+
+struct VJ { int idx, pos, dels, seqpos; };  // (match, end_v | start_j, deletions, v_seq_start | j_seq_end)
+
+// vanalysis (decombine.py:273-394) and janalysis (decombine.py:397-531): same skeleton, mirrored arithmetic.
+template <bool IS_V>
+DCB_HD bool analyse_general(const ReadView& r, const uint32_t* blob, int end_of_v, VJ& out, dcb_cnt_t* C) {
+    const DcbGene& g = *reinterpret_cast<const DcbGene*>(blob);
+    const uint8_t* taglist;
+    KwScan sc;
+    int kw, p;
+
+    // ---- full tags: findall, >1 hit rejects (:275-290 / :399-418)
+    kw_scan_init(sc, g.full);
+    int nh = 0, kw0 = 0, p0 = 0;
+    while (nh < 2 && kw_scan_next(r, blob, g.full, sc, kw, p)) {
+        if (nh == 0) { kw0 = kw; p0 = p; }
+        nh++;
+    }
+    if (nh) {
+        if (nh > 1) { DCB_COUNT(C, IS_V ? DCB_C_multiple_v_matches : DCB_C_multiple_j_matches); return false; }
+        const DcbKw& k = kwset_kw(blob, g.full, kw0);
+        int idx = k.first_tag;
+        const DcbTag& t = gene_tag(blob, g, idx);
+        if (IS_V) {
+            int temp_end_v = p0 + t.jump - 1;
+            int end_v, dels;
+            if (!v_deletions_general(r, blob, t, temp_end_v, end_v, dels, C)) return false;
+            out.idx = idx; out.pos = end_v; out.dels = dels; out.seqpos = p0;
+        } else {
+            int temp_start_j = p0 - t.jump;
+            int start_j, dels;
+            if (!j_deletions_general(r, blob, t, temp_start_j, end_of_v, start_j, dels, C)) return false;
+            out.idx = idx; out.pos = start_j; out.dels = dels; out.seqpos = p0 + (int)k.len;
+        }
+        return true;
+    }
+
+    // ---- half1 (:294-335 / :422-470), then half2 only if half1 never hit (:339-390 / :473-527)
+    for (int half = 1; half <= 2; half++) {
+        const DcbKwSet& ks = half == 1 ? g.half1 : g.half2;
+        taglist = reinterpret_cast<const uint8_t*>(blob + ks.taglist_off);
+        kw_scan_init(sc, ks);
+        bool any = false;
+        while (kw_scan_next(r, blob, ks, sc, kw, p)) {
+            any = true;
+            const DcbKw& k = kwset_kw(blob, ks, kw);
+            const int L0 = gene_tag(blob, g, k.first_tag).len;       // len(seqs[halfN_seqs.index(hit)])
+            const int s0 = half == 1 ? p : p - g.split;              // slice start as the reference writes it
+            for (int ti = 0; ti < (int)k.n_tags; ti++) {
+                const int kk = taglist[k.tags_off + ti];             // ascending tag index
+                const DcbTag& t = gene_tag(blob, g, kk);
+                Span gs = py_slice(r.n, s0, s0 + L0);                // length guard (:302-307 etc.)
+                if ((int)t.len != gs.b - gs.a) continue;
+                Span hs = py_slice(r.n, s0, s0 + (int)t.len);        // Hamming operand (:311-314 etc.)
+                if (hs.b - hs.a != (int)t.len) continue;
+                if (!rd_hamming_le1(r, hs.a, t.len, t.bits_lo, t.bits_hi)) continue;
+                if (IS_V) {
+                    DCB_COUNT(C, half == 1 ? DCB_C_verr2 : DCB_C_verr1);          // :318 / :370
+                    int temp_end_v = half == 1 ? p + t.jump - 1 : p + t.jump - g.split - 1;
+                    int end_v, dels;
+                    if (v_deletions_general(r, blob, t, temp_end_v, end_v, dels, C)) {
+                        out.idx = kk; out.pos = end_v; out.dels = dels; out.seqpos = s0;
+                        return true;
+                    }
+                } else {
+                    DCB_COUNT(C, half == 1 ? DCB_C_jerr2 : DCB_C_jerr1);          // :445 / :504
+                    int temp_start_j = half == 1 ? p - t.jump : p - t.jump - g.split;
+                    int j_seq_end = half == 1 ? p + (int)k.len + g.split : p + (int)k.len;  // :450-454 / :511
+                    int start_j, dels;
+                    if (j_deletions_general(r, blob, t, temp_start_j, end_of_v, start_j, dels, C)) {
+                        out.idx = kk; out.pos = start_j; out.dels = dels; out.seqpos = j_seq_end;
+                        return true;
+                    }
+                }
+            }
+        }
+        if (any) {
+            // :334 / :389 / :469 / :526 -- the J half2 failure bumps foundv2notv1 in the reference; preserved
+            if (IS_V) DCB_COUNT(C, half == 1 ? DCB_C_foundv1notv2 : DCB_C_foundv2notv1);
+            else DCB_COUNT(C, half == 1 ? DCB_C_foundj1notj2 : DCB_C_foundv2notv1);
+            return false;
+        }
+    }
+    DCB_COUNT(C, IS_V ? DCB_C_no_vtags_found : DCB_C_no_j_assigned);  // :393 / :530
+    return false;
+}
+
+struct DcrParams { int allow_ns, lenthreshold; };
+
+// The four filters and the result of dcr() (decombine.py:553-581), shared by both kernels.
+// Returns -1 when the rearrangement is accepted (out filled), else the counter the reference bumps.
+DCB_HD int dcr_finish(const ReadView& r, const DcbTag& vt, const DcbTag& jt, const VJ& v, const VJ& j,
+                      const DcrParams& prm, dcb_result& out) {
+    Span it = py_slice(r.n, v.seqpos, j.seqpos);
+    if (!prm.allow_ns && r.e1 > r.e0 && rd_has_N(r, it.a, it.b)) return DCB_C_dcrfilter_intertagN;       // :553-556
+    if ((v.seqpos - j.seqpos) >= prm.lenthreshold) return DCB_C_dcrfilter_toolong_intertag;              // :557-560
+    if (v.dels > ((int)vt.jump - (int)vt.len) || j.dels > (int)jt.jump) return DCB_C_dcrfilter_imposs_deletion;  // :561-565
+    if ((v.seqpos + (int)vt.len) > (j.seqpos + (int)jt.len)) return DCB_C_dcrfilter_tag_overlap;         // :566-569
+    out.status = 1;                                                                                      // :572-581
+    out.v = (uint8_t)v.idx; out.j = (uint8_t)j.idx;
+    out.vdel = (uint16_t)v.dels; out.jdel = (uint16_t)j.dels;
+    out.ins_start = (uint16_t)(v.pos + 1); out.ins_end = (uint16_t)j.pos;
+    out.v_seq_start = (uint16_t)v.seqpos; out.j_seq_end = (uint16_t)j.seqpos;
+    return -1;
+}
+
+// dcr(read, inputargs) (decombine.py:534-585), general path: any read, any edge case.
+DCB_HD bool dcr_general(const ReadView& r, const uint32_t* vblob, const uint32_t* jblob, const DcrParams& prm,
+                        dcb_result& out, dcb_cnt_t* C) {
+    VJ v, j;
+    if (!analyse_general<true>(r, vblob, 0, v, C)) return false;                 // :542-545
+    if (!analyse_general<false>(r, jblob, v.pos + 1, j, C)) {                    // :547-548, :583-585
+        DCB_COUNT(C, DCB_C_VJ_assignment_failed);
+        return false;
+    }
+    const DcbGene& gv = *reinterpret_cast<const DcbGene*>(vblob);
+    const DcbGene& gj = *reinterpret_cast<const DcbGene*>(jblob);
+    int c = dcr_finish(r, gene_tag(vblob, gv, v.idx), gene_tag(jblob, gj, j.idx), v, j, prm, out);
+    if (c >= 0) { DCB_COUNT(C, c); return false; }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reverse complement of a packed read (replaces Bio.Seq.reverse_complement, decombine.py:182-184,
+// for the second try of `-or both`): output word ow holds bases [16 ow, 16 ow + 16) of the result.
+// ------------------------------------------------------------------------------------------------
+DCB_HD uint32_t revcomp_word(const ReadView& r, int ow) {
+    int p = r.n - 16 * ow - 16;            // source bases [p, p+16) reversed
+    uint32_t x = rd_win16(r, p);
+    uint32_t y = DCB_BREV(x);              // reverses bit order: 2-bit groups reversed, bits inside swapped
+    y = ((y & 0xAAAAAAAAu) >> 1) | ((y & 0x55555555u) << 1);
+    y = ~y;                                // complement: A<->T (0<->3), C<->G (1<->2)
+    int valid = r.n - 16 * ow;             // bases of this output word that exist
+    if (valid <= 0) return 0u;
+    return y & mask2(valid < 16 ? valid : 16);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact-tag fast path.
+// ------------------------------------------------------------------------------------------------
+// Result of the sampled-seed search for full tags: number of distinct occurrences (saturating at 2)
+// and the first one.
+struct FullHit { int count, tag, pos; };
+
+// Confirm the candidates behind one seed hit at sampled position p.
+DCB_HD void fast_verify_seed(const ReadView& r, const uint32_t* blob, const DcbGene& g, int p, FullHit& fh) {
+    uint32_t key = rd_win16(r, p) & mask2(g.q);
+    uint32_t h = dcb_hash32(key) & (uint32_t)g.seedhash_mask;
+    uint32_t offs = 0;
+    for (;;) {
+        uint32_t k = blob[g.seedhash_off + 2 * h];
+        if (k == DCB_HASH_EMPTY) break;
+        if (k == key) { offs = blob[g.seedhash_off + 2 * h + 1]; break; }
+        h = (h + 1) & (uint32_t)g.seedhash_mask;
+    }
+    while (offs) {
+        int o = DCB_FFS(offs) - 1;
+        offs &= offs - 1;
+        int P = p - o;
+        if (P < 0 || P + g.lmin > r.n) continue;
+        uint32_t lo, hi;
+        rd_win32(r, P, lo, hi);
+        uint32_t plo = lo & mask2(g.lmin), phi = g.lmin > 16 ? (hi & mask2(g.lmin - 16)) : 0u;
+        uint32_t hh = dcb_hash64(plo, phi) & (uint32_t)g.prefhash_mask;
+        for (;;) {
+            uint32_t id = blob[g.prefhash_off + hh];
+            if (id == DCB_HASH_EMPTY) break;
+            const DcbTag& t = gene_tag(blob, g, (int)id);
+            hh = (hh + 1) & (uint32_t)g.prefhash_mask;
+            int L = t.len;
+            if (P + L > r.n) continue;
+            uint32_t mlo = mask2(L), mhi = L > 16 ? mask2(L - 16) : 0u;
+            if (((lo ^ t.bits_lo) & mlo) | ((hi ^ t.bits_hi) & mhi)) continue;
+            if (fh.count && fh.tag == (int)id && fh.pos == P) continue;  // same occurrence seen via another seed
+            if (fh.count == 0) { fh.tag = (int)id; fh.pos = P; }
+            if (fh.count < 2) fh.count++;
+        }
+    }
+}
+
+// Bit-parallel "10 consecutive equal bases": x = xor of two 32-base windows; returns a word pair where
+// bit 2i is set iff bases i..i+9 are all equal (i <= 22).
+DCB_HD void run10(uint32_t xlo, uint32_t xhi, uint32_t& rlo, uint32_t& rhi) {
+    uint64_t x = ((uint64_t)xhi << 32) | xlo;
+    uint64_t eq = ~(x | (x >> 1)) & 0x5555555555555555ull;
+    uint64_t r2 = eq & (eq >> 2);
+    uint64_t r4 = r2 & (r2 >> 4);
+    uint64_t r8 = r4 & (r4 >> 8);
+    uint64_t r10 = r8 & (r2 >> 16);
+    rlo = (uint32_t)r10; rhi = (uint32_t)(r10 >> 32);
+}
+
+// Fast V: exactly the interior case of get_v_deletions (decombine.py:749-785).  Returns
+//   1 handled (out filled or a counter bumped and *fail set), 0 defer to the general kernel.
+DCB_HD int fast_v_deletions(const ReadView& r, const DcbTag& t, int temp_end_v, int& end_v, int& dels) {
+    const int f0 = temp_end_v + 1;
+    if (!t.edge_ok || f0 >= r.n || f0 < 32) return 0;
+    uint32_t lo, hi, rl, rh;
+    rd_win32(r, f0 - 32, lo, hi);
+    run10(lo ^ t.edge_lo, hi ^ t.edge_hi, rl, rh);
+    // window index i <-> deletions nd = 22 - i; want the smallest nd, i.e. the highest i <= 22
+    uint64_t r10 = (((uint64_t)rh << 32) | rl) & ((1ull << 46) - 1);  // bits 2i, i <= 22
+    if (!r10) return 0;
+    const uint32_t h32 = (uint32_t)(r10 >> 32), l32 = (uint32_t)r10;
+    const int top = h32 ? 63 - DCB_CLZ(h32) : 31 - DCB_CLZ(l32);
+    int i = top >> 1;
+    dels = 22 - i;
+    end_v = temp_end_v - dels;
+    return 1;
+}
+
+// Fast J: the interior case of get_j_deletions (decombine.py:788-817).
+DCB_HD int fast_j_deletions(const ReadView& r, const DcbTag& t, int temp_start_j, int end_of_v, int& start_j, int& dels) {
+    if (!t.edge_ok || temp_start_j < 0) return 0;
+    int pos0 = end_of_v - temp_start_j;
+    if (pos0 < 0) pos0 = 0;
+    if (pos0 > 22) return 0;
+    uint32_t lo, hi, rl, rh;
+    rd_win32(r, temp_start_j, lo, hi);
+    run10(lo ^ t.edge_lo, hi ^ t.edge_hi, rl, rh);
+    uint64_t r10 = (((uint64_t)rh << 32) | rl) & ((1ull << 46) - 1);
+    r10 &= ~((1ull << (2 * pos0)) - 1);                      // pos >= pos0
+    // the 10-mer must lie inside the read: temp_start_j + i + 10 <= n
+    int imax = r.n - 10 - temp_start_j;
+    if (imax < 0) return 0;
+    if (imax < 22) r10 &= ((1ull << (2 * imax + 2)) - 1);
+    if (!r10) return 0;
+    int low = (uint32_t)r10 ? DCB_FFS((uint32_t)r10) - 1 : 32 + DCB_FFS((uint32_t)(r10 >> 32)) - 1;
+    int i = low >> 1;
+    dels = i;
+    start_j = temp_start_j + i;
+    return 1;
+}
+
+// Sampled-seed scan of one gene over a read held in the view: probe the seed bitmap at every
+// multiple of `stride`, 32 probes at a time into a hit mask, then confirm the (rare) hits in a
+// second loop so the lanes of a warp stay converged during the probes.
+DCB_HD void fast_scan(const ReadView& r, const uint32_t* blob, const DcbGene& g, FullHit& fh) {
+    fh.count = 0; fh.tag = 0; fh.pos = 0;
+    const uint32_t qmask = mask2(g.q);
+    const int last = r.n - g.q;  // last start position of a whole q-mer
+    for (int base = 0; base <= last; base += 32 * g.stride) {
+        uint32_t hits = 0;
+        for (int i = 0; i < 32; i++) {
+            const int p = base + i * g.stride;
+            if (p > last) break;
+            const uint32_t key = rd_win16(r, p) & qmask;
+            hits |= ((blob[g.seedmap_off + (key >> 5)] >> (key & 31)) & 1u) << i;
+        }
+        while (hits) {
+            const int i = DCB_FFS(hits) - 1;
+            hits &= hits - 1;
+            fast_verify_seed(r, blob, g, base + i * g.stride, fh);
+            if (fh.count >= 2) return;
+        }
+    }
+}
+
+// Outcome of the fast path for one read.
+enum { FAST_DONE = 0, FAST_DEFER = 1 };
+
+// dcr() for the common case: read without exceptions, exactly one full V tag and one full J tag whose
+// deletion walks stay in the interior.  Anything else is deferred UNCOUNTED to the general kernel,
+// except the two outcomes that are final by themselves (multiple V / multiple J matches).
+// When both_frames is set a failed first frame must be retried, so every non-success defers.
+DCB_HD int dcr_fast_from_hits(const ReadView& r, const uint32_t* vblob, const uint32_t* jblob, const FullHit& vh,
+                              const FullHit& jh, const DcrParams& prm, int both_frames, dcb_result& out,
+                              dcb_cnt_t* C) {
+    const DcbGene& gv = *reinterpret_cast<const DcbGene*>(vblob);
+    const DcbGene& gj = *reinterpret_cast<const DcbGene*>(jblob);
+    if (vh.count == 0) return FAST_DEFER;
+    if (vh.count > 1) {
+        if (both_frames) return FAST_DEFER;
+        DCB_COUNT(C, DCB_C_multiple_v_matches);
+        return FAST_DONE;
+    }
+    const DcbTag& vt = gene_tag(vblob, gv, vh.tag);
+    VJ v, j;
+    v.idx = vh.tag; v.seqpos = vh.pos;
+    if (!fast_v_deletions(r, vt, vh.pos + vt.jump - 1, v.pos, v.dels)) return FAST_DEFER;
+    if (jh.count == 0) return FAST_DEFER;
+    if (jh.count > 1) {
+        if (both_frames) return FAST_DEFER;
+        DCB_COUNT(C, DCB_C_multiple_j_matches);
+        DCB_COUNT(C, DCB_C_VJ_assignment_failed);
+        return FAST_DONE;
+    }
+    const DcbTag& jt = gene_tag(jblob, gj, jh.tag);
+    j.idx = jh.tag; j.seqpos = jh.pos + (int)jt.len;
+    if (!fast_j_deletions(r, jt, jh.pos - jt.jump, v.pos + 1, j.pos, j.dels)) return FAST_DEFER;
+    // filters: a failed filter is final unless the other frame still has to be tried
+    int c = dcr_finish(r, vt, jt, v, j, prm, out);
+    if (c >= 0) {
+        if (both_frames) return FAST_DEFER;
+        DCB_COUNT(C, c);
+    }
+    return FAST_DONE;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-read drivers shared by the kernels (and by tests/sim): everything between "the packed words of
+// read ri are in w[]" and "here is its 16-byte record".
+// ------------------------------------------------------------------------------------------------
+struct ExcList {
+    const uint32_t* read;   // sorted read indices
+    const uint16_t* pos;
+    const uint8_t* kind;    // 1 'N', 2 other, 3 valid in the packed frame but not in its reverse complement
+    uint32_t n;
+};
+
+DCB_HD uint32_t exc_lower_bound(const ExcList& ex, uint32_t key) {
+    uint32_t lo = 0, hi = ex.n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (ex.read[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Exact-tag kernel body for one read whose words are already in r.w.  Returns FAST_DONE / FAST_DEFER.
+DCB_HD int dcr_exact_read(const ReadView& r, bool flagged, const uint32_t* vblob, const uint32_t* jblob,
+                          const DcrParams& prm, int both_frames, dcb_result& out, dcb_cnt_t* C) {
+    if (flagged) return FAST_DEFER;
+    const DcbGene& gv = *reinterpret_cast<const DcbGene*>(vblob);
+    const DcbGene& gj = *reinterpret_cast<const DcbGene*>(jblob);
+    FullHit vh, jh;
+    fast_scan(r, vblob, gv, vh);
+    jh.count = 0; jh.tag = 0; jh.pos = 0;
+    if (vh.count == 1) fast_scan(r, jblob, gj, jh);
+    return dcr_fast_from_hits(r, vblob, jblob, vh, jh, prm, both_frames, out, C);
+}
+
+// General kernel body for one read: r has w/stride/n/nw set; inv0, rd1, inv1 are this thread's scratch
+// columns (same stride as r): inv0/inv1 hold (nw+1)/2 words, rd1 holds nw words (only used with both_frames).
+DCB_HD void dcr_general_read(ReadView r, uint32_t ri, bool flagged, const ExcList& ex, uint32_t* inv0, uint32_t* rd1,
+                             uint32_t* inv1, const uint32_t* vblob, const uint32_t* jblob, const DcrParams& prm,
+                             int both_frames, dcb_result& out, dcb_cnt_t* C) {
+    const int nwi = (r.nw + 1) / 2;
+    r.inv = nullptr; r.exc_pos = ex.pos; r.exc_kind = ex.kind; r.e0 = r.e1 = 0; r.mirror = 0;
+    if (flagged) {
+        uint32_t e0 = exc_lower_bound(ex, ri), e1 = e0;
+        while (e1 < ex.n && ex.read[e1] == ri) e1++;
+        r.e0 = (int)e0; r.e1 = (int)e1;
+        bool any = false;
+        for (int k = 0; k < nwi; k++) inv0[k * r.stride] = 0;
+        for (uint32_t e = e0; e < e1; e++) {
+            if (ex.kind[e] == 3) continue;  // a real base in this frame
+            uint32_t p = ex.pos[e];
+            inv0[(p >> 5) * r.stride] |= 1u << (p & 31);
+            any = true;
+        }
+        if (any) r.inv = inv0;
+    }
+    bool ok = dcr_general(r, vblob, jblob, prm, out, C);
+    if (!ok && both_frames) {                                          // decombine.py:1005-1010
+        for (int k = 0; k < r.nw; k++) rd1[k * r.stride] = revcomp_word(r, k);
+        ReadView r1 = r;
+        r1.w = rd1; r1.inv = nullptr; r1.mirror = 1;
+        if (r.e1 > r.e0) {
+            for (int k = 0; k < nwi; k++) inv1[k * r.stride] = 0;
+            for (int e = r.e0; e < r.e1; e++) {
+                uint32_t p = (uint32_t)(r.n - 1) - ex.pos[e];
+                inv1[(p >> 5) * r.stride] |= 1u << (p & 31);
+            }
+            r1.inv = inv1;
+        }
+        dcb_result o1;
+        o1.status = 0; o1.frame = 0; o1.v = o1.j = 0; o1.vdel = o1.jdel = 0;
+        o1.ins_start = o1.ins_end = o1.v_seq_start = o1.j_seq_end = 0;
+        if (dcr_general(r1, vblob, jblob, prm, o1, C)) { o1.frame = 1; out = o1; }
+    }
+}
+
+#endif  // DCR_CORE_CUH

@@ -1,0 +1,496 @@
+// decombine.cu -- the sm_100a kernels of the decombine hot path and the context that drives them.
+//
+// Two kernels per batch, both one thread per read, 32 reads per warp:
+//
+//   dcb_exact_kernel   every read.  128-bit loads of the packed read slot, sampled-seed search for
+//                      the full V and J tags (one shared-memory bitmap probe every `stride` bases),
+//                      bit-parallel deletion walk, the four dcr() filters, one 16-byte record out.
+//                      Reads it cannot finish (no exact tag, non-ACGT symbols, a deletion walk that
+//                      leaves the interior, `-or both` retries) are appended UNCOUNTED to a queue with
+//                      one warp-aggregated atomic (ballot + popc + shuffle).
+//   dcb_general_kernel the queued reads only (compacted, so warps stay dense): the complete
+//                      vanalysis/janalysis contract incl. the half-tag fallback with Hamming <= 1 and
+//                      the literal Python-slice deletion walks.
+//
+// Tag tables are staged into shared memory once per (persistent) block with TMA bulk copies
+// (cp.async.bulk + mbarrier); reads live in shared memory as [word][thread] so data-dependent word
+// indices are bank-conflict free.
+#include "dcb_internal.h"
+#include "dcr_core.cuh"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+struct BatchDev {
+    const uint32_t* words;
+    const uint16_t* lens;
+    const uint32_t* flags;
+    const uint32_t* exc_read;
+    const uint16_t* exc_pos;
+    const uint8_t* exc_kind;
+    uint32_t n_reads, slot_words, uniform_len, n_exc;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Stage `bytes` (multiple of 16, both sides 16-byte aligned) from global into shared memory with the
+// TMA bulk-copy engine; completion is signalled on an mbarrier that all threads then wait on.
+__device__ __forceinline__ void tma_stage_begin(uint64_t* bar, uint32_t total_bytes) {
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(total_bytes)
+                     : "memory");
+    }
+}
+__device__ __forceinline__ void tma_stage_copy(uint64_t* bar, void* dst, const void* src, uint32_t bytes) {
+    if (threadIdx.x == 0) {
+        const char* s = (const char*)src;
+        char* d = (char*)dst;
+        while (bytes) {
+            uint32_t chunk = bytes > 32768u ? 32768u : bytes;
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    smem_u32(d)),
+                "l"(s), "r"(chunk), "r"(smem_u32(bar))
+                : "memory");
+            s += chunk; d += chunk; bytes -= chunk;
+        }
+    }
+}
+__device__ __forceinline__ void tma_stage_wait(uint64_t* bar) {
+    uint32_t done = 0;
+    const uint32_t addr = smem_u32(bar);
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr)
+            : "memory");
+    }
+}
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ void store_result(dcb_result* dst, const dcb_result& r) {
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(&r);
+}
+
+// first index e in [0, n) with a[e] >= key
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* a, uint32_t n, uint32_t key) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(a + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+static constexpr int kExactThreads = 256;
+static constexpr int kGeneralThreads = 128;
+
+// ------------------------------------------------------------------------------------------------
+// exact-tag kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kExactThreads)
+dcb_exact_kernel(BatchDev b, const uint32_t* __restrict__ vblob_g, const uint32_t* __restrict__ jblob_g,
+                 int vwords, int jwords, DcrParams prm, int both_frames, dcb_result* __restrict__ results,
+                 unsigned long long* __restrict__ counters, uint32_t* __restrict__ queue,
+                 uint32_t* __restrict__ queue_count) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t* vblob = smem;
+    uint32_t* jblob = vblob + vwords;
+    uint32_t* s_rd = jblob + jwords;                               // [slot_words][kExactThreads]
+    dcb_cnt_t* s_cnt = s_rd + (size_t)b.slot_words * kExactThreads;  // [DCB_NCOUNTERS]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_cnt + ((DCB_NCOUNTERS + 3) & ~3));
+
+    tma_stage_begin(bar, (uint32_t)(vwords + jwords) * 4u);
+    tma_stage_copy(bar, vblob, vblob_g, (uint32_t)vwords * 4u);
+    tma_stage_copy(bar, jblob, jblob_g, (uint32_t)jwords * 4u);
+    if (threadIdx.x < DCB_NCOUNTERS) s_cnt[threadIdx.x] = 0;
+    tma_stage_wait(bar);
+    __syncthreads();
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const uint32_t n_tiles = (b.n_reads + kExactThreads - 1) / kExactThreads;
+
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t ri = tile * kExactThreads + tid;
+        const bool live = ri < b.n_reads;
+        int action = FAST_DONE;
+        dcb_result out;
+        *reinterpret_cast<uint4*>(&out) = make_uint4(0, 0, 0, 0);
+        if (live) {
+            const uint4* src = reinterpret_cast<const uint4*>(b.words + (size_t)ri * b.slot_words);
+            for (uint32_t k = 0; k < b.slot_words / 4; k++) {
+                uint4 v = ldg_stream(src + k);
+                s_rd[(4 * k + 0) * kExactThreads + tid] = v.x;
+                s_rd[(4 * k + 1) * kExactThreads + tid] = v.y;
+                s_rd[(4 * k + 2) * kExactThreads + tid] = v.z;
+                s_rd[(4 * k + 3) * kExactThreads + tid] = v.w;
+            }
+            const bool flagged = b.n_exc && ((__ldg(b.flags + (ri >> 5)) >> (ri & 31)) & 1u);
+            ReadView r;
+            r.w = s_rd + tid; r.inv = nullptr; r.stride = kExactThreads;
+            r.n = b.uniform_len ? (int)b.uniform_len : (int)__ldg(b.lens + ri);
+            r.nw = (int)b.slot_words;
+            r.exc_pos = nullptr; r.exc_kind = nullptr; r.e0 = r.e1 = 0; r.mirror = 0;
+            action = dcr_exact_read(r, flagged, vblob, jblob, prm, both_frames, out, s_cnt);
+        }
+        // warp-aggregated append of the deferred reads
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, live && action == FAST_DEFER);
+        if (m) {
+            uint32_t base = 0;
+            if (lane == (__ffs(m) - 1)) base = atomicAdd(queue_count, (uint32_t)__popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
+            if (live && action == FAST_DEFER) queue[base + __popc(m & ((1u << lane) - 1u))] = ri;
+        }
+        if (live && action == FAST_DONE) store_result(results + ri, out);
+    }
+    __syncthreads();
+    if (threadIdx.x < DCB_NCOUNTERS && s_cnt[threadIdx.x])
+        atomicAdd(counters + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// general kernel (queued reads, or every read when queue == nullptr)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGeneralThreads)
+dcb_general_kernel(BatchDev b, const uint32_t* __restrict__ vblob_g, const uint32_t* __restrict__ jblob_g,
+                   int vwords, int jwords, DcrParams prm, int both_frames, dcb_result* __restrict__ results,
+                   unsigned long long* __restrict__ counters, const uint32_t* __restrict__ queue,
+                   const uint32_t* __restrict__ queue_count) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int T = kGeneralThreads;
+    const int nw = (int)b.slot_words, nwi = (nw + 1) / 2;
+    uint32_t* vblob = smem;
+    uint32_t* jblob = vblob + vwords;
+    uint32_t* s_rd = jblob + jwords;              // [nw][T]
+    uint32_t* s_inv = s_rd + (size_t)nw * T;      // [nwi][T]
+    uint32_t* s_rd1 = s_inv + (size_t)nwi * T;    // second frame (only when both_frames)
+    uint32_t* s_inv1 = s_rd1 + (both_frames ? (size_t)nw * T : 0);
+    dcb_cnt_t* s_cnt = s_inv1 + (both_frames ? (size_t)nwi * T : 0);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_cnt + ((DCB_NCOUNTERS + 3) & ~3));
+
+    tma_stage_begin(bar, (uint32_t)(vwords + jwords) * 4u);
+    tma_stage_copy(bar, vblob, vblob_g, (uint32_t)vwords * 4u);
+    tma_stage_copy(bar, jblob, jblob_g, (uint32_t)jwords * 4u);
+    if (threadIdx.x < DCB_NCOUNTERS) s_cnt[threadIdx.x] = 0;
+    tma_stage_wait(bar);
+    __syncthreads();
+
+    const int tid = threadIdx.x;
+    const uint32_t n_items = queue ? *queue_count : b.n_reads;
+    const uint32_t n_tiles = (n_items + T - 1) / T;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t item = tile * T + tid;
+        if (item >= n_items) continue;
+        const uint32_t ri = queue ? queue[item] : item;
+        const uint4* src = reinterpret_cast<const uint4*>(b.words + (size_t)ri * b.slot_words);
+        for (int k = 0; k < nw / 4; k++) {
+            uint4 v = __ldg(src + k);
+            s_rd[(4 * k + 0) * T + tid] = v.x;
+            s_rd[(4 * k + 1) * T + tid] = v.y;
+            s_rd[(4 * k + 2) * T + tid] = v.z;
+            s_rd[(4 * k + 3) * T + tid] = v.w;
+        }
+        ReadView r;
+        r.w = s_rd + tid; r.stride = T;
+        r.n = b.uniform_len ? (int)b.uniform_len : (int)__ldg(b.lens + ri);
+        r.nw = nw;
+        const bool flagged = b.n_exc && ((__ldg(b.flags + (ri >> 5)) >> (ri & 31)) & 1u);
+        ExcList ex;
+        ex.read = b.exc_read; ex.pos = b.exc_pos; ex.kind = b.exc_kind; ex.n = b.n_exc;
+        dcb_result out;
+        *reinterpret_cast<uint4*>(&out) = make_uint4(0, 0, 0, 0);
+        dcr_general_read(r, ri, flagged, ex, s_inv + tid, s_rd1 + tid, s_inv1 + tid, vblob, jblob, prm, both_frames,
+                         out, s_cnt);
+        store_result(results + ri, out);
+    }
+    __syncthreads();
+    if (threadIdx.x < DCB_NCOUNTERS && s_cnt[threadIdx.x])
+        atomicAdd(counters + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            dcb_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return DCB_ENOGPU;                                                                  \
+        }                                                                                       \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return DCB_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            dcb_set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(cudaGetLastError()));
+            return DCB_ENOMEM;
+        }
+        cap = want;
+        return DCB_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct dcb_ctx {
+    int device = 0;
+    int n_sms = 0;
+    dcb_params params{};
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    uint32_t *d_vgen = nullptr, *d_jgen = nullptr, *d_vfast = nullptr, *d_jfast = nullptr;
+    int vgen_words = 0, jgen_words = 0, vfast_words = 0, jfast_words = 0;
+    DevBuf words, lens, flags, exc_read, exc_pos, exc_kind, results, queue;
+    uint32_t* d_queue_count = nullptr;
+    unsigned long long* d_counters = nullptr;
+    BatchDev batch{};
+    bool have_batch = false, ran = false;
+    bool timing = false;
+    struct Ev { cudaEvent_t a, b; int slot; };
+    std::vector<Ev> events;
+    double ms[DCB_NTIMERS] = {0, 0, 0, 0};
+    uint64_t launches[DCB_NTIMERS] = {0, 0, 0, 0};
+    int exact_grid = 0, general_grid = 0;
+    size_t exact_smem = 0, general_smem = 0;
+};
+
+static int upload_blob(const std::vector<uint32_t>& v, uint32_t** d, int* words) {
+    CUDA_TRY(cudaMalloc((void**)d, v.size() * 4));
+    CUDA_TRY(cudaMemcpy(*d, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+    *words = (int)v.size();
+    return DCB_OK;
+}
+
+static int timing_begin(dcb_ctx* c, int slot) {
+    if (!c->timing) return DCB_OK;
+    dcb_ctx::Ev ev;
+    ev.slot = slot;
+    CUDA_TRY(cudaEventCreate(&ev.a));
+    CUDA_TRY(cudaEventCreate(&ev.b));
+    CUDA_TRY(cudaEventRecord(ev.a, c->stream));
+    c->events.push_back(ev);
+    return DCB_OK;
+}
+static int timing_end(dcb_ctx* c) {
+    if (!c->timing) return DCB_OK;
+    CUDA_TRY(cudaEventRecord(c->events.back().b, c->stream));
+    return DCB_OK;
+}
+static int timing_collect(dcb_ctx* c) {
+    for (auto& ev : c->events) {
+        CUDA_TRY(cudaEventSynchronize(ev.b));
+        float t = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&t, ev.a, ev.b));
+        c->ms[ev.slot] += t;
+        c->launches[ev.slot] += 1;
+        cudaEventDestroy(ev.a);
+        cudaEventDestroy(ev.b);
+    }
+    c->events.clear();
+    return DCB_OK;
+}
+
+extern "C" {
+
+dcb_ctx* dcb_ctx_create(int device, const dcb_tagset* v, const dcb_tagset* j, const dcb_params* p) {
+    if (!v || !j || !p) { dcb_set_error("dcb_ctx_create: null argument"); return nullptr; }
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        (void)cudaGetLastError();
+        dcb_set_error("dcb_ctx_create: no CUDA device available (there is no CPU fallback)");
+        return nullptr;
+    }
+    if (device < 0 || device >= n_dev) { dcb_set_error("dcb_ctx_create: device %d out of range", device); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { dcb_set_error("cudaSetDevice failed"); return nullptr; }
+    dcb_ctx* c = new dcb_ctx();
+    c->device = device;
+    c->params = *p;
+    auto fail = [&](const char* what) -> dcb_ctx* {
+        if (what) dcb_set_error("dcb_ctx_create: %s: %s", what, cudaGetErrorString(cudaGetLastError()));
+        dcb_ctx_destroy(c);
+        return nullptr;
+    };
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail("cudaGetDeviceProperties");
+    c->n_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate");
+    c->stream = c->own_stream;
+    if (upload_blob(v->general, &c->d_vgen, &c->vgen_words) || upload_blob(j->general, &c->d_jgen, &c->jgen_words) ||
+        upload_blob(v->fast, &c->d_vfast, &c->vfast_words) || upload_blob(j->fast, &c->d_jfast, &c->jfast_words))
+        return fail(nullptr);
+    if (cudaMalloc((void**)&c->d_queue_count, 16) != cudaSuccess) return fail("cudaMalloc");
+    if (cudaMalloc((void**)&c->d_counters, sizeof(unsigned long long) * DCB_NCOUNTERS) != cudaSuccess) return fail("cudaMalloc");
+    return c;
+}
+
+void dcb_ctx_destroy(dcb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    timing_collect(c);
+    if (c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
+    cudaFree(c->d_vgen); cudaFree(c->d_jgen); cudaFree(c->d_vfast); cudaFree(c->d_jfast);
+    cudaFree(c->d_queue_count); cudaFree(c->d_counters);
+    c->words.release(); c->lens.release(); c->flags.release(); c->exc_read.release(); c->exc_pos.release();
+    c->exc_kind.release(); c->results.release(); c->queue.release();
+    delete c;
+}
+
+int dcb_ctx_set_stream(dcb_ctx* c, void* cuda_stream) {
+    if (!c) return DCB_EINVAL;
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return DCB_OK;
+}
+
+int dcb_upload(dcb_ctx* c, const dcb_packed* P) {
+    if (!c || !P) { dcb_set_error("dcb_upload: null argument"); return DCB_EINVAL; }
+    if (P->n_reads >= 0xFFFFFFFFull) { dcb_set_error("dcb_upload: batch too large"); return DCB_EINVAL; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t n = P->n_reads, sw = P->slot_words;
+    int rc;
+    if ((rc = c->words.ensure(n * sw * 4 + 16)) || (rc = c->lens.ensure(n * 2 + 16)) ||
+        (rc = c->flags.ensure(((n + 31) / 32) * 4 + 16)) || (rc = c->exc_read.ensure((size_t)P->n_exc * 4 + 16)) ||
+        (rc = c->exc_pos.ensure((size_t)P->n_exc * 2 + 16)) || (rc = c->exc_kind.ensure((size_t)P->n_exc + 16)) ||
+        (rc = c->results.ensure(n * sizeof(dcb_result) + 16)) || (rc = c->queue.ensure(n * 4 + 16)))
+        return rc;
+    cudaStream_t s = c->stream;
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(c->words.p, P->words, n * sw * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c->lens.p, P->lens, n * 2, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c->flags.p, P->flags, ((n + 31) / 32) * 4, cudaMemcpyHostToDevice, s));
+    }
+    if (P->n_exc) {
+        CUDA_TRY(cudaMemcpyAsync(c->exc_read.p, P->exc_read, (size_t)P->n_exc * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c->exc_pos.p, P->exc_pos, (size_t)P->n_exc * 2, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c->exc_kind.p, P->exc_kind, (size_t)P->n_exc, cudaMemcpyHostToDevice, s));
+    }
+    BatchDev& b = c->batch;
+    b.words = (const uint32_t*)c->words.p; b.lens = (const uint16_t*)c->lens.p; b.flags = (const uint32_t*)c->flags.p;
+    b.exc_read = (const uint32_t*)c->exc_read.p; b.exc_pos = (const uint16_t*)c->exc_pos.p;
+    b.exc_kind = (const uint8_t*)c->exc_kind.p;
+    b.n_reads = (uint32_t)n; b.slot_words = (uint32_t)sw; b.uniform_len = P->uniform_len; b.n_exc = P->n_exc;
+    c->have_batch = true; c->ran = false;
+
+    // launch geometry: persistent blocks, a whole number of blocks per SM
+    const size_t tail = (((DCB_NCOUNTERS + 3) & ~3) + 4) * 4;
+    c->exact_smem = ((size_t)c->vfast_words + c->jfast_words + sw * kExactThreads) * 4 + tail;
+    const size_t nwi = (sw + 1) / 2;
+    c->general_smem = ((size_t)c->vgen_words + c->jgen_words + (sw + nwi) * kGeneralThreads * (c->params.both_frames ? 2 : 1)) * 4 + tail;
+    if (c->exact_smem > 227 * 1024 || c->general_smem > 227 * 1024) {
+        dcb_set_error("dcb_upload: tables + reads of %u nt need %zu / %zu bytes of shared memory (max 232448)",
+                      P->max_len, c->exact_smem, c->general_smem);
+        return DCB_EUNSUPPORTED;
+    }
+    CUDA_TRY(cudaFuncSetAttribute(dcb_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->exact_smem));
+    CUDA_TRY(cudaFuncSetAttribute(dcb_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->general_smem));
+    int occ_e = 0, occ_g = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, dcb_exact_kernel, kExactThreads, c->exact_smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, dcb_general_kernel, kGeneralThreads, c->general_smem));
+    if (occ_e < 1 || occ_g < 1) { dcb_set_error("dcb_upload: kernel does not fit on an SM"); return DCB_EUNSUPPORTED; }
+    const uint32_t tiles_e = (uint32_t)((n + kExactThreads - 1) / kExactThreads);
+    const uint32_t tiles_g = (uint32_t)((n + kGeneralThreads - 1) / kGeneralThreads);
+    c->exact_grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(tiles_e, (uint32_t)(c->n_sms * occ_e)));
+    c->general_grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(tiles_g, (uint32_t)(c->n_sms * occ_g)));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return DCB_OK;
+}
+
+int dcb_run_resident(dcb_ctx* c) {
+    if (!c || !c->have_batch) { dcb_set_error("dcb_run_resident: no batch uploaded"); return DCB_EINVAL; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const BatchDev& b = c->batch;
+    CUDA_TRY(cudaMemsetAsync(c->d_queue_count, 0, 16, s));
+    CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * DCB_NCOUNTERS, s));
+    if (b.n_reads == 0) { c->ran = true; return DCB_OK; }
+    DcrParams prm;
+    prm.allow_ns = c->params.allow_ns; prm.lenthreshold = c->params.lenthreshold;
+    int rc;
+    if (!c->params.force_general) {
+        if ((rc = timing_begin(c, 0))) return rc;
+        dcb_exact_kernel<<<c->exact_grid, kExactThreads, c->exact_smem, s>>>(
+            b, c->d_vfast, c->d_jfast, c->vfast_words, c->jfast_words, prm, c->params.both_frames,
+            (dcb_result*)c->results.p, c->d_counters, (uint32_t*)c->queue.p, c->d_queue_count);
+        CUDA_TRY(cudaGetLastError());
+        if ((rc = timing_end(c))) return rc;
+    }
+    if ((rc = timing_begin(c, 1))) return rc;
+    dcb_general_kernel<<<c->general_grid, kGeneralThreads, c->general_smem, s>>>(
+        b, c->d_vgen, c->d_jgen, c->vgen_words, c->jgen_words, prm, c->params.both_frames, (dcb_result*)c->results.p,
+        c->d_counters, c->params.force_general ? nullptr : (const uint32_t*)c->queue.p, c->d_queue_count);
+    CUDA_TRY(cudaGetLastError());
+    if ((rc = timing_end(c))) return rc;
+    c->ran = true;
+    return DCB_OK;
+}
+
+int dcb_download(dcb_ctx* c, dcb_result* out, uint64_t* counters) {
+    if (!c || !c->ran) { dcb_set_error("dcb_download: nothing has been run"); return DCB_EINVAL; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    if (out && c->batch.n_reads)
+        CUDA_TRY(cudaMemcpyAsync(out, c->results.p, (size_t)c->batch.n_reads * sizeof(dcb_result), cudaMemcpyDeviceToHost, s));
+    unsigned long long h[DCB_NCOUNTERS];
+    CUDA_TRY(cudaMemcpyAsync(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (counters) for (int i = 0; i < DCB_NCOUNTERS; i++) counters[i] += h[i];
+    return DCB_OK;
+}
+
+int dcb_decombine_batch(dcb_ctx* c, const dcb_packed* reads, dcb_result* out, uint64_t* counters) {
+    int rc;
+    if ((rc = dcb_upload(c, reads))) return rc;
+    if ((rc = dcb_run_resident(c))) return rc;
+    return dcb_download(c, out, counters);
+}
+
+int dcb_timing_enable(dcb_ctx* c, int on) { if (!c) return DCB_EINVAL; c->timing = on != 0; return DCB_OK; }
+int dcb_timing_reset(dcb_ctx* c) {
+    if (!c) return DCB_EINVAL;
+    int rc = timing_collect(c);
+    for (int i = 0; i < DCB_NTIMERS; i++) { c->ms[i] = 0; c->launches[i] = 0; }
+    return rc;
+}
+int dcb_timing_get(dcb_ctx* c, double ms[DCB_NTIMERS], uint64_t launches[DCB_NTIMERS]) {
+    if (!c) return DCB_EINVAL;
+    int rc = timing_collect(c);
+    for (int i = 0; i < DCB_NTIMERS; i++) { if (ms) ms[i] = c->ms[i]; if (launches) launches[i] = c->launches[i]; }
+    return rc;
+}
+int dcb_last_deferred(dcb_ctx* c, uint64_t* n) {
+    if (!c || !n || !c->ran) return DCB_EINVAL;
+    uint32_t q = 0;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy(&q, c->d_queue_count, 4, cudaMemcpyDeviceToHost));
+    *n = c->params.force_general ? c->batch.n_reads : q;
+    return DCB_OK;
+}
+
+}  // extern "C"

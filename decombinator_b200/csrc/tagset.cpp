@@ -1,0 +1,243 @@
+// tagset.cpp -- host builder of the flattened tag tables (see dcb_tables.h).
+//
+// Replaces get_v_tags/get_j_tags and the AcoraBuilder().add/.build() calls of import_tcr_info
+// (/root/reference/src/decombinator/decombine.py:698-746, 820-866).
+#include "dcb_internal.h"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace {
+
+inline int base_code(char c) {
+    switch (c) {
+        case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3;
+        default: return -1;
+    }
+}
+
+bool pack64(const std::string& s, size_t from, size_t n, uint32_t& lo, uint32_t& hi) {
+    uint64_t v = 0;
+    lo = hi = 0;
+    for (size_t i = 0; i < n; i++) {
+        int c = base_code(s[from + i]);
+        if (c < 0) return false;
+        v |= (uint64_t)c << (2 * i);
+    }
+    lo = (uint32_t)v; hi = (uint32_t)(v >> 32);
+    return true;
+}
+
+uint32_t pow2_at_least(uint32_t x) {
+    uint32_t p = 16;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+struct Blob {
+    std::vector<uint32_t> w;
+    int32_t reserve(size_t n_words) {
+        int32_t off = (int32_t)w.size();
+        w.resize(w.size() + n_words, 0u);
+        return off;
+    }
+};
+
+// One keyword set -> bitmap + hash + DcbKw array + tag list.
+void build_kwset(Blob& b, DcbKwSet& ks, const std::vector<std::string>& list) {
+    // distinct keywords in first-occurrence order, with the ascending list of tags sharing each
+    std::vector<std::string> kws;
+    std::vector<std::vector<int>> members;
+    std::map<std::string, int> seen;
+    for (size_t i = 0; i < list.size(); i++) {
+        if (list[i].empty()) continue;  // AcoraBuilder drops empty keywords
+        auto it = seen.find(list[i]);
+        if (it == seen.end()) {
+            seen[list[i]] = (int)kws.size();
+            kws.push_back(list[i]);
+            members.push_back({(int)i});
+        } else {
+            members[it->second].push_back((int)i);
+        }
+    }
+    int min_len = 1 << 30, max_len = 0;
+    for (auto& k : kws) { min_len = std::min(min_len, (int)k.size()); max_len = std::max(max_len, (int)k.size()); }
+    if (kws.empty()) { min_len = 1; max_len = 1; }
+    ks.n_kw = (int)kws.size();
+    ks.min_len = min_len; ks.max_len = max_len;
+    ks.kq = std::min(min_len, 8);
+    // group by suffix key, longest first inside a group
+    struct Ent { uint32_t key; int len; int id; };
+    std::vector<Ent> ents;
+    for (size_t i = 0; i < kws.size(); i++) {
+        uint32_t lo, hi;
+        pack64(kws[i], kws[i].size() - ks.kq, ks.kq, lo, hi);
+        ents.push_back({lo, (int)kws[i].size(), (int)i});
+    }
+    std::stable_sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& c) {
+        if (a.key != c.key) return a.key < c.key;
+        return a.len > c.len;
+    });
+    size_t bitmap_words = ((size_t)1 << (2 * ks.kq)) / 32;
+    if (bitmap_words == 0) bitmap_words = 1;
+    ks.bitmap_off = b.reserve(bitmap_words);
+    size_t n_groups = 0;
+    for (size_t i = 0; i < ents.size(); i++) if (i == 0 || ents[i].key != ents[i - 1].key) n_groups++;
+    uint32_t hsize = pow2_at_least((uint32_t)(2 * n_groups + 1));
+    ks.hash_mask = (int32_t)(hsize - 1);
+    ks.hash_off = b.reserve(hsize);
+    for (uint32_t i = 0; i < hsize; i++) b.w[ks.hash_off + i] = DCB_HASH_EMPTY;
+    ks.kw_off = b.reserve(4 * ents.size());
+    size_t total_tags = 0;
+    for (auto& m : members) total_tags += m.size();
+    ks.taglist_off = b.reserve((total_tags + 3) / 4 + 1);
+    uint8_t* taglist = reinterpret_cast<uint8_t*>(&b.w[ks.taglist_off]);
+    size_t tl = 0;
+    for (size_t i = 0; i < ents.size(); i++) {
+        const std::string& s = kws[ents[i].id];
+        DcbKw kw;
+        std::memset(&kw, 0, sizeof(kw));
+        pack64(s, 0, s.size(), kw.bits_lo, kw.bits_hi);
+        kw.len = (uint8_t)s.size();
+        kw.first_tag = (uint8_t)members[ents[i].id][0];
+        kw.n_tags = (uint8_t)members[ents[i].id].size();
+        kw.tags_off = (uint8_t)tl;
+        for (int t : members[ents[i].id]) taglist[tl++] = (uint8_t)t;
+        std::memcpy(&b.w[ks.kw_off + 4 * i], &kw, sizeof(kw));
+        b.w[ks.bitmap_off + (ents[i].key >> 5)] |= 1u << (ents[i].key & 31);
+        if (i == 0 || ents[i].key != ents[i - 1].key) {
+            size_t cnt = 1;
+            while (i + cnt < ents.size() && ents[i + cnt].key == ents[i].key) cnt++;
+            uint32_t h = dcb_hash32(ents[i].key) & (hsize - 1);
+            while (b.w[ks.hash_off + h] != DCB_HASH_EMPTY) h = (h + 1) & (hsize - 1);
+            b.w[ks.hash_off + h] = (ents[i].key << 16) | ((uint32_t)i << 8) | (uint32_t)cnt;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+dcb_tagset* dcb_tagset_build(const char* const* tags, const int32_t* jumps, const char* const* regions,
+                             int n, int half_split, int is_v) {
+    if (!tags || !jumps || !regions || n < 1) { dcb_set_error("dcb_tagset_build: null/empty input"); return nullptr; }
+    if (n > DCB_MAX_TAGS) { dcb_set_error("dcb_tagset_build: more than 255 tags"); return nullptr; }
+    if (half_split < 1 || half_split > 16) { dcb_set_error("dcb_tagset_build: half_split out of range"); return nullptr; }
+    std::vector<std::string> full, h1, h2, reg;
+    int lmin = 1 << 30;
+    for (int i = 0; i < n; i++) {
+        std::string t(tags[i]), r(regions[i]);
+        if ((int)t.size() <= half_split || t.size() > DCB_MAX_TAG_LEN || t.size() < 4) {
+            dcb_set_error("dcb_tagset_build: tag %d has unsupported length %zu (need split < len <= 32)", i, t.size());
+            return nullptr;
+        }
+        for (char c : t) if (base_code(c) < 0) { dcb_set_error("dcb_tagset_build: tag %d is not pure ACGT", i); return nullptr; }
+        for (char c : r) if (base_code(c) < 0) { dcb_set_error("dcb_tagset_build: region %d is not pure ACGT", i); return nullptr; }
+        if (r.size() > 32000 || jumps[i] > 32000 || jumps[i] < -32000) { dcb_set_error("dcb_tagset_build: region/jump too large"); return nullptr; }
+        full.push_back(t);
+        h1.push_back(t.substr(0, half_split));
+        h2.push_back(t.substr(half_split));
+        reg.push_back(r);
+        lmin = std::min(lmin, (int)t.size());
+    }
+
+    dcb_tagset* ts = new dcb_tagset();
+    ts->n_tags = n; ts->split = half_split; ts->is_v = is_v;
+    for (auto& t : full) ts->tag_len.push_back((int)t.size());
+
+    for (int which = 0; which < 2; which++) {  // 0: general blob, 1: fast blob
+        Blob b;
+        const size_t hdr_words = (sizeof(DcbGene) + 3) / 4;
+        b.reserve(hdr_words);
+        DcbGene g;
+        std::memset(&g, 0, sizeof(g));
+        g.n_tags = n; g.split = half_split; g.is_v = is_v; g.lmin = lmin;
+        g.tag_off = b.reserve(8 * (size_t)n);
+        std::vector<DcbTag> trec(n);
+        for (int i = 0; i < n; i++) {
+            DcbTag& t = trec[i];
+            std::memset(&t, 0, sizeof(t));
+            pack64(full[i], 0, full[i].size(), t.bits_lo, t.bits_hi);
+            t.len = (uint8_t)full[i].size();
+            t.jump = (int16_t)jumps[i];
+            t.region_len = (int16_t)reg[i].size();
+            t.edge_ok = reg[i].size() >= 32;
+            if (t.edge_ok) pack64(reg[i], is_v ? reg[i].size() - 32 : 0, 32, t.edge_lo, t.edge_hi);
+            int f1 = (int)(std::find(h1.begin(), h1.end(), h1[i]) - h1.begin());
+            int f2 = (int)(std::find(h2.begin(), h2.end(), h2[i]) - h2.begin());
+            t.h1_first_len = (uint8_t)full[f1].size();
+            t.h2_first_len = (uint8_t)full[f2].size();
+        }
+        if (which == 0) {
+            build_kwset(b, g.full, full);
+            build_kwset(b, g.half1, h1);
+            build_kwset(b, g.half2, h2);
+            for (int i = 0; i < n; i++) {
+                size_t nw = (reg[i].size() + 15) / 16;
+                trec[i].region_off = b.reserve(nw + 1);
+                for (size_t p = 0; p < reg[i].size(); p++)
+                    b.w[trec[i].region_off + p / 16] |= (uint32_t)base_code(reg[i][p]) << (2 * (p % 16));
+            }
+        } else {
+            g.q = lmin >= 18 ? 9 : lmin >= 12 ? 8 : lmin >= 8 ? 6 : lmin;
+            g.stride = lmin - g.q + 1;
+            size_t words = ((size_t)1 << (2 * g.q)) / 32;
+            if (words == 0) words = 1;
+            g.seedmap_off = b.reserve(words);
+            std::map<uint32_t, uint32_t> seeds;  // q-mer -> mask of offsets
+            for (int i = 0; i < n; i++) {
+                for (size_t o = 0; o + g.q <= full[i].size(); o++) {
+                    uint32_t lo, hi;
+                    pack64(full[i], o, g.q, lo, hi);
+                    seeds[lo] |= 1u << o;
+                }
+            }
+            uint32_t hsize = pow2_at_least((uint32_t)(2 * seeds.size() + 1));
+            g.seedhash_mask = (int32_t)(hsize - 1);
+            g.seedhash_off = b.reserve(2 * (size_t)hsize);
+            for (uint32_t i = 0; i < hsize; i++) b.w[g.seedhash_off + 2 * i] = DCB_HASH_EMPTY;
+            for (auto& kv : seeds) {
+                b.w[g.seedmap_off + (kv.first >> 5)] |= 1u << (kv.first & 31);
+                uint32_t h = dcb_hash32(kv.first) & (hsize - 1);
+                while (b.w[g.seedhash_off + 2 * h] != DCB_HASH_EMPTY) h = (h + 1) & (hsize - 1);
+                b.w[g.seedhash_off + 2 * h] = kv.first;
+                b.w[g.seedhash_off + 2 * h + 1] = kv.second;
+            }
+            uint32_t psize = pow2_at_least((uint32_t)(2 * n + 1));
+            g.prefhash_mask = (int32_t)(psize - 1);
+            g.prefhash_off = b.reserve(psize);
+            for (uint32_t i = 0; i < psize; i++) b.w[g.prefhash_off + i] = DCB_HASH_EMPTY;
+            for (int i = 0; i < n; i++) {
+                uint32_t lo, hi;
+                pack64(full[i], 0, lmin, lo, hi);
+                uint32_t h = dcb_hash64(lo, hi) & (psize - 1);
+                while (b.w[g.prefhash_off + h] != DCB_HASH_EMPTY) h = (h + 1) & (psize - 1);
+                b.w[g.prefhash_off + h] = (uint32_t)i;
+            }
+        }
+        while (b.w.size() % 4) b.w.push_back(0u);  // 16-byte granularity for vector copies
+        g.n_words = (int32_t)b.w.size();
+        g.general_words = which == 0 ? g.n_words : 0;
+        std::memcpy(&b.w[g.tag_off], trec.data(), sizeof(DcbTag) * n);
+        std::memcpy(&b.w[0], &g, sizeof(g));
+        (which == 0 ? ts->general : ts->fast) = std::move(b.w);
+    }
+    return ts;
+}
+
+void dcb_tagset_free(dcb_tagset* ts) { delete ts; }
+
+size_t dcb_tagset_table_bytes(const dcb_tagset* ts) { return ts ? 4 * (ts->fast.size() + ts->general.size()) : 0; }
+
+int dcb_tagset_blob(const dcb_tagset* ts, int which, const uint32_t** words, size_t* n_words) {
+    if (!ts || !words || !n_words) return DCB_EINVAL;
+    const std::vector<uint32_t>& v = which ? ts->fast : ts->general;
+    *words = v.data(); *n_words = v.size();
+    return DCB_OK;
+}
+
+}  // extern "C"

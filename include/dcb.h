@@ -1,0 +1,202 @@
+/*
+ * dcb.h -- C ABI of libdcb.so, the B200-native `decombine` hot path.
+ *
+ * The reference (innate2adaptive/decombinator, /root/reference) is pure Python and has no FFI
+ * of its own; the drop-in boundary is the stage function decombinator(inputargs)
+ * (src/decombinator/decombine.py:881) and, inside it, the per-read contract dcr(read, inputargs)
+ * (decombine.py:534).  Each entry point below names the reference interface it replaces, as
+ * file:line under /root/reference/src/decombinator/.  INTEGRATION.md shows the ctypes binding a
+ * maintainer would add to the reference to call them.
+ *
+ * Conventions: plain pointers and sizes only; every function returning int returns 0 on success
+ * and a negative DCB_E* code on failure, with text from dcb_last_error(); no exceptions cross the
+ * boundary; a context is used by one host thread at a time and launches on its own stream
+ * (or the one given with dcb_ctx_set_stream).  There is NO CPU fallback: compute entry points
+ * fail with DCB_ENOGPU when no CUDA device is usable.
+ */
+#ifndef DCB_H
+#define DCB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCB_ABI_VERSION 1
+
+enum {
+    DCB_OK = 0,
+    DCB_EINVAL = -1,   /* bad argument */
+    DCB_ENOGPU = -2,   /* no usable CUDA device / CUDA error */
+    DCB_ENOMEM = -3,
+    DCB_EUNSUPPORTED = -4, /* input outside what the tables support (e.g. tag longer than 32 nt) */
+    DCB_EIO = -5
+};
+
+const char* dcb_last_error(void);
+int dcb_abi_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Counters: the keys of the reference's `counts` Counter that dcr() and its callees bump
+ * (decombine.py:279-584; written to the summary at decombine.py:1131-1195).
+ * ------------------------------------------------------------------------------------------- */
+enum dcb_counter {
+    DCB_C_verr1 = 0,
+    DCB_C_verr2,
+    DCB_C_jerr1,
+    DCB_C_jerr2,
+    DCB_C_dcrfilter_intertagN,
+    DCB_C_dcrfilter_toolong_intertag,
+    DCB_C_dcrfilter_imposs_deletion,
+    DCB_C_dcrfilter_tag_overlap,
+    DCB_C_multiple_v_matches,
+    DCB_C_v_del_failed_tag_at_end,
+    DCB_C_v_del_failed,
+    DCB_C_foundv1notv2,
+    DCB_C_foundv2notv1,
+    DCB_C_no_vtags_found,
+    DCB_C_multiple_j_matches,
+    DCB_C_j_del_failed,
+    DCB_C_foundj1notj2,
+    DCB_C_foundj2notj1,
+    DCB_C_no_j_assigned,
+    DCB_C_VJ_assignment_failed,
+    DCB_NCOUNTERS
+};
+/* Name of counter i as spelled in the reference ("verr1", ...), or NULL. */
+const char* dcb_counter_name(int i);
+
+/* ---------------------------------------------------------------------------------------------
+ * Tag tables.  Replaces get_v_tags/get_j_tags + the six AcoraBuilder automata of
+ * import_tcr_info (decombine.py:681-746, 820-866): one call per gene.
+ *   tags[i], jumps[i] : columns 0 and 1 of the .tags file       (decombine.py:826-835)
+ *   regions[i]        : upper-cased FASTA record i               (decombine.py:690-696)
+ *   half_split        : v_half_split / j_half_split              (decombine.py:657-661)
+ * Tags and regions must be pure ACGT, 4 <= len(tag) <= 32, n <= 255 (DCB_EUNSUPPORTED otherwise).
+ * Host only; no GPU needed.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct dcb_tagset dcb_tagset;
+dcb_tagset* dcb_tagset_build(const char* const* tags, const int32_t* jumps, const char* const* regions,
+                             int n, int half_split, int is_v);
+void dcb_tagset_free(dcb_tagset*);
+/* Total bytes of the flattened table blobs (what thread blocks stage in shared memory). */
+size_t dcb_tagset_table_bytes(const dcb_tagset*);
+/* Introspection (tests): which = 0 the general-kernel blob, 1 the exact-tag-kernel blob. */
+int dcb_tagset_blob(const dcb_tagset*, int which, const uint32_t** words, size_t* n_words);
+
+/* ---------------------------------------------------------------------------------------------
+ * Packed reads: 2 bits per base (A=0 C=1 G=2 T=3, base i of a read in bits [2*(i%16), +2) of
+ * word i/16), one fixed-size slot of `slot_words` 32-bit words per read (a multiple of 4, so a
+ * slot is read with 128-bit loads).  Any other symbol is packed as 0 and listed in the sparse
+ * exception arrays (sorted by read): kind 1 = 'N', kind 2 = anything else.  `flags` has one bit
+ * per read that is set when the read has exceptions.  Buffers are page-locked when a GPU is
+ * present so they can be streamed to HBM with cudaMemcpyAsync.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct dcb_packed {
+    uint64_t n_reads;
+    uint32_t slot_words;   /* 32-bit words per read slot */
+    uint32_t uniform_len;  /* != 0: every read has this length and `lens` may be ignored */
+    uint32_t max_len;
+    uint32_t n_exc;
+    uint32_t* words;       /* n_reads * slot_words */
+    uint16_t* lens;        /* n_reads */
+    uint32_t* flags;       /* ceil(n_reads/32) */
+    uint32_t* exc_read;    /* n_exc : read index */
+    uint16_t* exc_pos;     /* n_exc : base position in the ORIENTED read */
+    uint8_t*  exc_kind;    /* n_exc : 1 = 'N', 2 = other */
+    void* owner;           /* internal */
+} dcb_packed;
+
+/* Replaces the string handling of the main loop for the V(D)J read: `vdj = record1[1]`
+ * (decombine.py:965-977) and, when revcomp != 0, revcomp(vdj) (decombine.py:182-184, 1000)
+ * with Bio.Seq's complement table.  ascii/off/len describe n reads inside one byte buffer.
+ * Allocates *out (free with dcb_packed_free).  Host only; multi-threaded. */
+int dcb_pack_reads(const char* ascii, const uint64_t* off, const uint32_t* len, uint64_t n, int revcomp,
+                   int n_threads, dcb_packed** out);
+void dcb_packed_free(dcb_packed*);
+/* Inverse of the packer for one read (tests): writes len chars, exceptions as 'N' / '?'. */
+int dcb_unpack_read(const dcb_packed*, uint64_t i, char* dst, uint32_t cap);
+
+/* ---------------------------------------------------------------------------------------------
+ * Per-read result: what dcr() returns (decombine.py:572-581) as a 16-byte record.  The insert
+ * string is oriented_read[ins_start:ins_end]; tcrseq / tcrQ are sliced with
+ * [v_seq_start:j_seq_end] on the host (decombine.py:1015-1020).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct dcb_result {
+    uint8_t status;        /* 0: dcr() returned None; 1: rearrangement found */
+    uint8_t frame;         /* 0: the packed orientation; 1: its reverse complement (-or both, 2nd try) */
+    uint8_t v, j;          /* recom[0], recom[1] */
+    uint16_t vdel, jdel;   /* recom[2], recom[3] */
+    uint16_t ins_start;    /* end_v + 1 */
+    uint16_t ins_end;      /* start_j */
+    uint16_t v_seq_start;  /* recom[5] */
+    uint16_t j_seq_end;    /* recom[6] */
+} dcb_result;
+
+typedef struct dcb_params {
+    int32_t both_frames;   /* -or both: retry the reverse complement of the packed read when the first try fails
+                              (decombine.py:1005-1010); reads are then packed in the FIRST orientation tried */
+    int32_t allow_ns;      /* inputargs["allowNs"]      (decombine.py:553-556) */
+    int32_t lenthreshold;  /* inputargs["lenthreshold"] (decombine.py:557-560) */
+    int32_t force_general; /* testing: send every read through the general (fallback) kernel */
+} dcb_params;
+
+/* ---------------------------------------------------------------------------------------------
+ * Context: one per GPU.  Owns the device copies of the tag tables, the device batch buffers and
+ * a stream.  Replaces the module globals import_tcr_info() sets up (decombine.py:593-746).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct dcb_ctx dcb_ctx;
+dcb_ctx* dcb_ctx_create(int device, const dcb_tagset* v, const dcb_tagset* j, const dcb_params* p);
+void dcb_ctx_destroy(dcb_ctx*);
+/* Launch on an externally owned cudaStream_t (e.g. torch's current stream) instead of the ctx's own. */
+int dcb_ctx_set_stream(dcb_ctx*, void* cuda_stream);
+
+/* The batched dcr(): replaces the body of the hot loop `for records in zipfqs: ... dcr(...)`
+ * (decombine.py:963-1010) for n reads.  HOST buffers in, HOST buffers out: copies the packed
+ * batch to HBM, runs the matching kernels, copies the n result records back and ADDS this
+ * batch's counter deltas to counters[DCB_NCOUNTERS].  Synchronous. */
+int dcb_decombine_batch(dcb_ctx*, const dcb_packed* reads, dcb_result* out, uint64_t* counters);
+
+/* Same work with the batch resident in HBM (bench `value`, multi-step pipelines):
+ *   dcb_upload          : host packed batch -> ctx-owned device buffers (synchronous)
+ *   dcb_run_resident    : launch the kernels on the resident batch; asynchronous on the ctx stream
+ *   dcb_download        : wait, copy results + ADD counter deltas of the last run
+ */
+int dcb_upload(dcb_ctx*, const dcb_packed* reads);
+int dcb_run_resident(dcb_ctx*);
+int dcb_download(dcb_ctx*, dcb_result* out, uint64_t* counters);
+
+/* Per-kernel device time (CUDA events on the launching stream), accumulated since the last reset.
+ * slot 0: exact-tag matching kernel, slot 1: general (half-tag fallback) kernel. */
+#define DCB_NTIMERS 4
+int dcb_timing_reset(dcb_ctx*);
+int dcb_timing_enable(dcb_ctx*, int on);
+int dcb_timing_get(dcb_ctx*, double ms[DCB_NTIMERS], uint64_t launches[DCB_NTIMERS]);
+/* Number of reads the last run sent to the general kernel. */
+int dcb_last_deferred(dcb_ctx*, uint64_t* n);
+
+/* ---------------------------------------------------------------------------------------------
+ * Synthetic workload generator: deterministic in (seed, read index).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct dcb_synth_params {
+    uint64_t seed;
+    uint32_t read_len;     /* R1 length */
+    uint32_t read2_len;    /* R2 length (barcode read); 0 = none */
+    uint32_t sub_rate;     /* per-base substitution probability * 2^32 */
+    uint32_t n_rate;       /* per-base N probability * 2^32 */
+    uint32_t junk_rate;    /* probability * 2^32 that a read is random sequence (no TCR) */
+    uint32_t umi_pool;     /* != 0: UMIs are drawn from read_index % umi_pool (copies share a UMI) */
+} dcb_synth_params;
+typedef struct dcb_synth dcb_synth;
+dcb_synth* dcb_synth_create(const dcb_synth_params* p, int n_sets, const char* const* const* v_regions,
+                            const int* n_v, const char* const* const* j_regions, const int* n_j);
+void dcb_synth_destroy(dcb_synth*);
+/* r1: n*read_len bytes; r2: n*read2_len bytes or NULL.  No terminators. */
+int dcb_synth_reads(const dcb_synth*, uint64_t first_index, uint64_t n, char* r1, char* r2, int n_threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCB_H */

@@ -1,0 +1,45 @@
+// sim_decombine.cpp -- TEST SCAFFOLDING: runs the kernels' per-read device code (dcr_core.cuh,
+// compiled for the host by g++) over a packed batch, one "thread" at a time, so that the matching
+// logic can be checked against the oracle on a machine without a GPU.  Never linked into libdcb.so
+// and never used by the product: the shipped path is the CUDA kernels in csrc/decombine.cu, which
+// call exactly the same dcr_exact_read / dcr_general_read functions.
+#include "../../decombinator_b200/csrc/dcr_core.cuh"
+
+#include <cstring>
+#include <vector>
+
+extern "C" int sim_decombine(const dcb_packed* P, const uint32_t* vgen, const uint32_t* jgen, const uint32_t* vfast,
+                             const uint32_t* jfast, int both_frames, int allow_ns, int lenthreshold, int mode,
+                             dcb_result* out, uint64_t* counters, uint64_t* n_deferred) {
+    DcrParams prm;
+    prm.allow_ns = allow_ns; prm.lenthreshold = lenthreshold;
+    const int nw = (int)P->slot_words, nwi = (nw + 1) / 2;
+    std::vector<uint32_t> inv0(nwi + 1), inv1(nwi + 1), rd1(nw + 1);
+    dcb_cnt_t cnt[DCB_NCOUNTERS];
+    std::memset(cnt, 0, sizeof(cnt));
+    ExcList ex;
+    ex.read = P->exc_read; ex.pos = P->exc_pos; ex.kind = P->exc_kind; ex.n = P->n_exc;
+    uint64_t deferred = 0;
+    for (uint64_t ri = 0; ri < P->n_reads; ri++) {
+        ReadView r;
+        std::memset(&r, 0, sizeof(r));
+        r.w = P->words + ri * P->slot_words; r.stride = 1;
+        r.n = P->uniform_len ? (int)P->uniform_len : (int)P->lens[ri];
+        r.nw = nw;
+        const bool flagged = P->n_exc && ((P->flags[ri >> 5] >> (ri & 31)) & 1u);
+        dcb_result o;
+        std::memset(&o, 0, sizeof(o));
+        int action = FAST_DEFER;
+        if (mode == 0) action = dcr_exact_read(r, flagged, vfast, jfast, prm, both_frames, o, cnt);
+        if (action == FAST_DEFER) {
+            deferred++;
+            std::memset(&o, 0, sizeof(o));
+            dcr_general_read(r, (uint32_t)ri, flagged, ex, inv0.data(), rd1.data(), inv1.data(), vgen, jgen, prm,
+                             both_frames, o, cnt);
+        }
+        out[ri] = o;
+    }
+    for (int i = 0; i < DCB_NCOUNTERS; i++) counters[i] += cnt[i];
+    if (n_deferred) *n_deferred = deferred;
+    return 0;
+}

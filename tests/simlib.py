@@ -1,0 +1,42 @@
+"""Test helper: run the kernels' device code compiled for the host (tests/sim) -- TEST SCAFFOLDING."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from decombinator_b200 import _lib
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, "sim", "sim_decombine.cpp")
+_SO = os.path.join(_HERE, "sim", "libdcbsim.so")
+_ROOT = os.path.dirname(_HERE)
+
+
+def _build():
+    deps = [_SRC, os.path.join(_ROOT, "decombinator_b200", "csrc", "dcr_core.cuh"),
+            os.path.join(_ROOT, "decombinator_b200", "csrc", "dcb_tables.h"), os.path.join(_ROOT, "include", "dcb.h")]
+    if not os.path.exists(_SO) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", "-I", os.path.join(_ROOT, "include"),
+                               _SRC, "-o", _SO])
+    return _SO
+
+
+_sim = None
+
+
+def sim_decombine(packed, vt, jt, both_frames=False, allow_ns=False, lenthreshold=130, general_only=False):
+    """-> (results, counters, n_deferred) using dcr_exact_read/dcr_general_read on the host."""
+    global _sim
+    if _sim is None:
+        _sim = ctypes.CDLL(_build())
+        _sim.sim_decombine.argtypes = [ctypes.POINTER(_lib.CPacked)] + [ctypes.c_void_p] * 4 + [ctypes.c_int] * 4 + \
+                                      [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
+    res = np.zeros(packed.n_reads, dtype=_lib.RESULT_DTYPE)
+    cnt = np.zeros(_lib.NCOUNTERS, dtype=np.uint64)
+    nd = ctypes.c_uint64()
+    blobs = [vt.blob(0), jt.blob(0), vt.blob(1), jt.blob(1)]
+    rc = _sim.sim_decombine(packed.c, *[b.ctypes.data for b in blobs], int(both_frames), int(allow_ns),
+                            int(lenthreshold), int(general_only), res.ctypes.data, cnt.ctypes.data, ctypes.byref(nd))
+    assert rc == 0
+    return res, cnt, nd.value
