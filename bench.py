@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""Benchmark of the decombine hot path on B200 (driver contract: one JSON line on stdout from rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--reads R] [--impl reference]
+
+Workload (BASELINE.json configs[1]): synthetic 10 M x 250-nt reads, human beta, extended tag set,
+-br R2 -bl 42 -ol M13.  One "step" = one pass of the decombine kernels over the whole batch of packed
+reads.  Weak scaling: every GPU gets its own 10 M-read shard of the same deterministic stream
+(contiguous index ranges, no data-path collective: reads are independent).
+
+  value     whole-job reads/s with the packed batch resident in HBM (K steps, CUDA events, max over ranks)
+  e2e       the same through the C-ABI call dcb_decombine_batch: packed reads in pinned HOST memory in,
+            result records in host memory out, copies inside the timed region
+  roofline  exact-tag kernel: algorithmic bytes (ceil(L/4)+16 per read) / its mean device time, against the
+            measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  the oracle's C port of the reference's dcr() on this box's host cores (a reported baseline)
+
+`--impl reference` times only that CPU port (the reference itself is pure Python + absent wheels and cannot be
+installed offline; its algorithm is what oracle/dcr_oracle.c restates and pins against reference fixtures).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "decombined_reads_per_sec"
+UNIT = "reads/s"
+READ_LEN = 250
+SEED = 20260002
+WORKLOAD = "synthetic 250-nt reads, human beta, extended tag set, -br R2 -bl 42 -ol M13 (BASELINE configs[1])"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_reads(info, first, n, threads):
+    from decombinator_b200 import _lib
+    syn = _lib.Synth([(info.v_regions, info.j_regions)], SEED, READ_LEN, 0, 0.0, 0.0, 0.0)
+    r1, _ = syn.reads(first, n, n_threads=threads)
+    off = np.arange(n, dtype=np.uint64) * READ_LEN
+    ln = np.full(n, READ_LEN, dtype=np.uint32)
+    return r1, off, ln
+
+
+def cpu_reference_run(r1, off, ln, threads, steps=1, warmup=0):
+    """The oracle's C port of dcr() (incl. the reverse complement) over ASCII reads in host memory."""
+    import decombine_oracle as O
+    orc = O.Oracle(O.TagSet("human", "extended", "b"))
+    for _ in range(warmup):
+        orc.decombine_arrays(r1, off, ln, "reverse", nthreads=threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = orc.decombine_arrays(r1, off, ln, "reverse", nthreads=threads)
+    dt = time.perf_counter() - t0
+    return len(off) * steps / dt, dt / steps, int(res["ok"].sum())
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for t, line in self.rows:
+            if t < t0 - 0.05 or t > t1 + 0.05:
+                continue
+            parts = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(parts[0])); mx = float(parts[1])
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:  # region shorter than the sampling period: use the nearest samples
+            for t, line in self.rows[-3:]:
+                try:
+                    parts = [x.strip() for x in line.split(",")]
+                    sm.append(float(parts[0])); mx = float(parts[1])
+                except Exception:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    host_threads = max(1, (os.cpu_count() or 1) // max(1, world if args.impl == "b200" else 1))
+
+    from decombinator_b200 import tags
+    info = tags.load("human", "extended", "b")
+    config = {"workload": WORKLOAD, "reads_per_gpu": args.reads, "read_len": READ_LEN, "seed": SEED,
+              "l2": "packed batch (64 B/read) is larger than the 126 MB L2; no flush needed",
+              "sharding": "contiguous read-index shards, one per GPU, no collective"}
+
+    # ---------------------------------------------------------------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        threads = os.cpu_count() or 1
+        n = min(args.reads, 4_000_000)
+        r1, off, ln = make_reads(info, 0, n, threads)
+        rps, sec, _ = cpu_reference_run(r1, off, ln, threads, steps=max(1, args.steps), warmup=min(1, args.warmup))
+        line = {"impl": "reference", "metric": METRIC, "value": rps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": rps, "unit": UNIT, "cores": threads, "kind": "port",
+                                 "sample": "first %d reads of the workload per step, ASCII in host memory, C port of the "
+                                           "reference's dcr() incl. revcomp, pthreads" % n},
+                "e2e": {"value": rps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "the reference is pure Python with un-installable native deps (acora, Levenshtein, biopython); "
+                        "this arm times the oracle's C restatement of the same algorithm, which is pinned against "
+                        "fixtures recorded from the unmodified reference"}
+        print(json.dumps(line))
+        return
+
+    # ---------------------------------------------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+    from decombinator_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the decombine path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n = args.reads
+    r1, off, ln = make_reads(info, rank * n, n, host_threads)
+    packed = _lib.pack_arrays(r1, off, ln, revcomp=True, n_threads=host_threads)
+    vt, jt = info.tables()
+    ctx = _lib.Context(vt, jt, device=local_rank)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.upload(packed)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident: K steps of the kernels over the batch in HBM --------------------------------------
+    with torch.cuda.stream(stream):
+        for _ in range(max(3, args.warmup)):
+            ctx.run_resident()
+        torch.cuda.synchronize()
+        res0, cnt0 = ctx.download()
+        n_deferred = ctx.last_deferred()
+        ctx.timing_enable(True)
+        ctx.timing_reset()
+        barrier()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            ctx.run_resident()
+        ev1.record(stream)
+        barrier()
+        t1 = time.perf_counter()
+        ms_total = ev0.elapsed_time(ev1)
+        kms, klaunch = ctx.timing_get()
+        ctx.timing_enable(False)
+        clocks = sampler.stop(t0, t1) if sampler else None
+
+        # ---- e2e: host packed buffers -> results in host memory through dcb_decombine_batch ------------
+        for _ in range(2):
+            ctx.decombine(packed)
+        barrier()
+        e0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 5))
+        for _ in range(e2e_steps):
+            res_e, cnt_e = ctx.decombine(packed)
+        torch.cuda.synchronize()
+        e_ms = (time.perf_counter() - e0) * 1e3
+        assert np.array_equal(res_e, res0) and np.array_equal(cnt_e, cnt0)
+
+    if world > 1:
+        t = torch.tensor([ms_total, e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e_ms = float(t[0]), float(t[1])
+        ok = torch.tensor([int(res0["status"].sum())], device="cuda", dtype=torch.int64)
+        dist.all_reduce(ok)
+        decombined = int(ok[0])
+    else:
+        decombined = int(res0["status"].sum())
+
+    if rank == 0:
+        value = world * n * args.steps / (ms_total / 1e3)
+        e2e = world * n * e2e_steps / (e_ms / 1e3)
+        bytes_per_read = (READ_LEN + 3) // 4 + 16
+        exact_ms = kms[0] / max(1, klaunch[0])
+        general_ms = kms[1] / max(1, klaunch[1])
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = bytes_per_read * n / (exact_ms / 1e3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic", "config": config,
+            "decombined_fraction": decombined / (world * n), "deferred_to_general_kernel": n_deferred / n,
+            "kernels_ms": {"dcb_exact_kernel": exact_ms, "dcb_general_kernel": general_ms},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "dcb_exact_kernel", "bytes_per_read": bytes_per_read,
+                         "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(packed.nbytes()),
+                    "d2h_bytes_per_step": int(n * 16 + 8 * _lib.NCOUNTERS), "steps": e2e_steps},
+            "gpu_launches": int(klaunch.sum()),
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sample = args.cpu_sample or min(n, 2_000_000 if threads < 16 else 10_000_000)
+            rps, sec, _ = cpu_reference_run(r1[:sample * READ_LEN], off[:sample], ln[:sample], threads)
+            line["cpu_baseline"] = {"value": rps, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "first %d reads of rank 0's shard, one pass, %.1f s" % (sample, sec)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

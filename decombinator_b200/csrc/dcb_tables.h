@@ -73,8 +73,14 @@ struct DcbGene {
     int32_t prefhash_off;        // prefhash_size words: tag id or DCB_HASH_EMPTY, hashed on the lmin-prefix
     int32_t prefhash_mask;
     int32_t n_words;             // blob size
-    int32_t general_words;       // words [0, general_words) are all the general kernel needs
+    int32_t core_words;          // exact-tag blob: words [0, core_words) exclude the seed bitmap, which comes last
+                                 // (a chain whose V and J share (q, stride) is scanned through ONE union bitmap)
 };
+
+// Seed bitmap addressing: the LOW 2q-5 bits of a q-mer key select the word, the high 5 bits the bit, so the
+// word address is a mask of the already-shifted read window and the bit index needs no masking.
+#define DCB_SEEDMAP_WORD(key, q) ((key) & ((1u << (2 * (q) - 5)) - 1u))
+#define DCB_SEEDMAP_BIT(key, q) ((key) >> (2 * (q) - 5))
 
 #if defined(__CUDACC__)
 #define DCB_HD __host__ __device__ __forceinline__

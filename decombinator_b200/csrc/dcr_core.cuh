@@ -390,8 +390,8 @@ DCB_HD uint32_t revcomp_word(const ReadView& r, int ow) {
 struct FullHit { int count, tag, pos; };
 
 // Confirm the candidates behind one seed hit at sampled position p.
-DCB_HD void fast_verify_seed(const ReadView& r, const uint32_t* blob, const DcbGene& g, int p, FullHit& fh) {
-    uint32_t key = rd_win16(r, p) & mask2(g.q);
+DCB_HD void fast_verify_seed(const ReadView& r, const uint32_t* blob, const DcbGene& g, int p, uint32_t key,
+                             FullHit& fh) {
     uint32_t h = dcb_hash32(key) & (uint32_t)g.seedhash_mask;
     uint32_t offs = 0;
     for (;;) {
@@ -492,12 +492,13 @@ DCB_HD void fast_scan(const ReadView& r, const uint32_t* blob, const DcbGene& g,
             const int p = base + i * g.stride;
             if (p > last) break;
             const uint32_t key = rd_win16(r, p) & qmask;
-            hits |= ((blob[g.seedmap_off + (key >> 5)] >> (key & 31)) & 1u) << i;
+            hits |= ((blob[g.seedmap_off + DCB_SEEDMAP_WORD(key, g.q)] >> DCB_SEEDMAP_BIT(key, g.q)) & 1u) << i;
         }
         while (hits) {
             const int i = DCB_FFS(hits) - 1;
             hits &= hits - 1;
-            fast_verify_seed(r, blob, g, base + i * g.stride, fh);
+            const int p = base + i * g.stride;
+            fast_verify_seed(r, blob, g, p, rd_win16(r, p) & qmask, fh);
             if (fh.count >= 2) return;
         }
     }

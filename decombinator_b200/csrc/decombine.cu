@@ -104,11 +104,46 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* a, uint32_t 
     return lo;
 }
 
-static constexpr int kExactThreads = 256;
+static constexpr int kExactThreads = 256;   // upper bounds; long reads launch narrower blocks (shared memory)
 static constexpr int kGeneralThreads = 128;
 
+// Shared-memory carve-up common to the kernels: [V blob][J blob][extra][per-thread columns][counters][mbarrier]
+struct SmemLayout {
+    uint32_t *vblob, *jblob, *extra, *cols;
+    dcb_cnt_t* cnt;
+    uint64_t* bar;
+};
+__device__ __forceinline__ SmemLayout carve(uint32_t* smem, int vwords, int jwords, int extra_words, size_t col_words) {
+    SmemLayout L;
+    L.vblob = smem;
+    L.jblob = L.vblob + vwords;
+    L.extra = L.jblob + jwords;
+    L.cols = L.extra + extra_words;
+    L.cnt = L.cols + col_words;
+    L.bar = reinterpret_cast<uint64_t*>(L.cnt + ((DCB_NCOUNTERS + 3) & ~3));
+    return L;
+}
+
+__device__ __forceinline__ void flush_counters(const dcb_cnt_t* s_cnt, unsigned long long* counters) {
+    __syncthreads();
+    if (threadIdx.x < DCB_NCOUNTERS && s_cnt[threadIdx.x])
+        atomicAdd(counters + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+}
+
+// Append the reads of this warp that must go to the general kernel: one atomic per warp.
+__device__ __forceinline__ void defer_reads(bool defer, uint32_t ri, uint32_t* queue, uint32_t* queue_count) {
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, defer);
+    if (m) {
+        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(queue_count, (uint32_t)__popc(m));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (defer) queue[base + __popc(m & ((1u << lane) - 1u))] = ri;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
-// exact-tag kernel
+// exact-tag kernel, generic form: any slot size / seed geometry (reads are walked from shared memory)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kExactThreads)
 dcb_exact_kernel(BatchDev b, const uint32_t* __restrict__ vblob_g, const uint32_t* __restrict__ jblob_g,
@@ -116,25 +151,21 @@ dcb_exact_kernel(BatchDev b, const uint32_t* __restrict__ vblob_g, const uint32_
                  unsigned long long* __restrict__ counters, uint32_t* __restrict__ queue,
                  uint32_t* __restrict__ queue_count) {
     extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t* vblob = smem;
-    uint32_t* jblob = vblob + vwords;
-    uint32_t* s_rd = jblob + jwords;                               // [slot_words][kExactThreads]
-    dcb_cnt_t* s_cnt = s_rd + (size_t)b.slot_words * kExactThreads;  // [DCB_NCOUNTERS]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(s_cnt + ((DCB_NCOUNTERS + 3) & ~3));
+    const int T = blockDim.x;
+    SmemLayout L = carve(smem, vwords, jwords, 0, (size_t)b.slot_words * T);
+    uint32_t* s_rd = L.cols;  // [slot_words][T]
 
-    tma_stage_begin(bar, (uint32_t)(vwords + jwords) * 4u);
-    tma_stage_copy(bar, vblob, vblob_g, (uint32_t)vwords * 4u);
-    tma_stage_copy(bar, jblob, jblob_g, (uint32_t)jwords * 4u);
-    if (threadIdx.x < DCB_NCOUNTERS) s_cnt[threadIdx.x] = 0;
-    tma_stage_wait(bar);
+    tma_stage_begin(L.bar, (uint32_t)(vwords + jwords) * 4u);
+    tma_stage_copy(L.bar, L.vblob, vblob_g, (uint32_t)vwords * 4u);
+    tma_stage_copy(L.bar, L.jblob, jblob_g, (uint32_t)jwords * 4u);
+    if (threadIdx.x < DCB_NCOUNTERS) L.cnt[threadIdx.x] = 0;
+    tma_stage_wait(L.bar);
     __syncthreads();
 
     const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const uint32_t n_tiles = (b.n_reads + kExactThreads - 1) / kExactThreads;
-
+    const uint32_t n_tiles = (b.n_reads + T - 1) / T;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint32_t ri = tile * kExactThreads + tid;
+        const uint32_t ri = tile * T + tid;
         const bool live = ri < b.n_reads;
         int action = FAST_DONE;
         dcb_result out;
@@ -143,32 +174,149 @@ dcb_exact_kernel(BatchDev b, const uint32_t* __restrict__ vblob_g, const uint32_
             const uint4* src = reinterpret_cast<const uint4*>(b.words + (size_t)ri * b.slot_words);
             for (uint32_t k = 0; k < b.slot_words / 4; k++) {
                 uint4 v = ldg_stream(src + k);
-                s_rd[(4 * k + 0) * kExactThreads + tid] = v.x;
-                s_rd[(4 * k + 1) * kExactThreads + tid] = v.y;
-                s_rd[(4 * k + 2) * kExactThreads + tid] = v.z;
-                s_rd[(4 * k + 3) * kExactThreads + tid] = v.w;
+                s_rd[(4 * k + 0) * T + tid] = v.x;
+                s_rd[(4 * k + 1) * T + tid] = v.y;
+                s_rd[(4 * k + 2) * T + tid] = v.z;
+                s_rd[(4 * k + 3) * T + tid] = v.w;
             }
             const bool flagged = b.n_exc && ((__ldg(b.flags + (ri >> 5)) >> (ri & 31)) & 1u);
             ReadView r;
-            r.w = s_rd + tid; r.inv = nullptr; r.stride = kExactThreads;
+            r.w = s_rd + tid; r.inv = nullptr; r.stride = T;
             r.n = b.uniform_len ? (int)b.uniform_len : (int)__ldg(b.lens + ri);
             r.nw = (int)b.slot_words;
             r.exc_pos = nullptr; r.exc_kind = nullptr; r.e0 = r.e1 = 0; r.mirror = 0;
-            action = dcr_exact_read(r, flagged, vblob, jblob, prm, both_frames, out, s_cnt);
+            action = dcr_exact_read(r, flagged, L.vblob, L.jblob, prm, both_frames, out, L.cnt);
         }
-        // warp-aggregated append of the deferred reads
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, live && action == FAST_DEFER);
-        if (m) {
-            uint32_t base = 0;
-            if (lane == (__ffs(m) - 1)) base = atomicAdd(queue_count, (uint32_t)__popc(m));
-            base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
-            if (live && action == FAST_DEFER) queue[base + __popc(m & ((1u << lane) - 1u))] = ri;
-        }
+        defer_reads(live && action == FAST_DEFER, ri, queue, queue_count);
         if (live && action == FAST_DONE) store_result(results + ri, out);
     }
+    flush_counters(L.cnt, counters);
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact-tag kernel, specialised: the read slot (NW words) sits in registers, every sampled seed position
+// is a compile-time constant (static funnel shifts, no index arithmetic), and when V and J share the
+// seed geometry ONE union bitmap is probed for both genes.
+//   NW      words per read slot (16 => reads up to 256 nt)
+//   QV, SV  V seed length / stride;  QJ, SJ  the same for J
+//   UNION   V and J are scanned together through one bitmap (requires QV == QJ && SV == SJ)
+// ------------------------------------------------------------------------------------------------
+template <int NW, int Q, int S>
+struct SeedScan {
+    static constexpr int NPOS = (16 * NW - Q) / S + 1;
+    static_assert(NPOS <= 64, "at most 64 sampled positions");
+    // probe the bitmap at every sampled position; bit i of (lo, hi) <-> position i * S
+    static __device__ __forceinline__ void run(const uint32_t (&w)[NW], const uint32_t* __restrict__ bitmap,
+                                               uint32_t& lo, uint32_t& hi) {
+        lo = 0; hi = 0;
+        constexpr uint32_t KMASK = (Q >= 16) ? 0xFFFFFFFFu : ((1u << (2 * Q)) - 1u);
+        constexpr int WBITS = 2 * Q - 5;
+#pragma unroll
+        for (int i = 0; i < NPOS; i++) {
+            const int p = i * S, a = p >> 4, sh = (p & 15) * 2;
+            uint32_t win;
+            if (sh == 0) win = w[a];
+            else if (sh + 2 * Q <= 32 || a + 1 >= NW) win = w[a] >> sh;
+            else win = __funnelshift_r(w[a], w[a + 1], sh);
+            const uint32_t key = win & KMASK;
+            const uint32_t word = bitmap[key & ((1u << WBITS) - 1u)];
+            const uint32_t bit = (word >> (key >> WBITS)) & 1u;
+            if (i < 32) lo |= bit << i; else hi |= bit << (i - 32);
+        }
+    }
+    // positions whose q-mer lies inside a read of n bases
+    static __device__ __forceinline__ void clip(int n, uint32_t& lo, uint32_t& hi) {
+        const int nvalid = n >= Q ? (n - Q) / S + 1 : 0;
+        if (nvalid < 32) { lo &= (1u << nvalid) - 1u; hi = 0; }
+        else if (nvalid < 64) hi &= (1u << (nvalid - 32)) - 1u;
+    }
+};
+
+template <int NW, int QV, int SV, int QJ, int SJ, bool UNION>
+__global__ void __launch_bounds__(kExactThreads)
+dcb_exact_kernel_spec(BatchDev b, const uint32_t* __restrict__ vblob_g, const uint32_t* __restrict__ jblob_g,
+                      const uint32_t* __restrict__ union_g, int vwords, int jwords, int uwords, DcrParams prm,
+                      int both_frames, dcb_result* __restrict__ results, unsigned long long* __restrict__ counters,
+                      uint32_t* __restrict__ queue, uint32_t* __restrict__ queue_count) {
+    static_assert(!UNION || (QV == QJ && SV == SJ), "union scan needs one seed geometry");
+    extern __shared__ __align__(16) uint32_t smem[];
+    constexpr int T = kExactThreads;
+    SmemLayout L = carve(smem, vwords, jwords, uwords, (size_t)NW * T);
+    uint32_t* s_rd = L.cols;
+
+    tma_stage_begin(L.bar, (uint32_t)(vwords + jwords + uwords) * 4u);
+    tma_stage_copy(L.bar, L.vblob, vblob_g, (uint32_t)vwords * 4u);
+    tma_stage_copy(L.bar, L.jblob, jblob_g, (uint32_t)jwords * 4u);
+    if (uwords) tma_stage_copy(L.bar, L.extra, union_g, (uint32_t)uwords * 4u);
+    if (threadIdx.x < DCB_NCOUNTERS) L.cnt[threadIdx.x] = 0;
+    tma_stage_wait(L.bar);
     __syncthreads();
-    if (threadIdx.x < DCB_NCOUNTERS && s_cnt[threadIdx.x])
-        atomicAdd(counters + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+
+    const DcbGene& gv = *reinterpret_cast<const DcbGene*>(L.vblob);
+    const DcbGene& gj = *reinterpret_cast<const DcbGene*>(L.jblob);
+    const uint32_t* vmap = UNION ? L.extra : L.vblob + gv.seedmap_off;
+    const uint32_t* jmap = UNION ? L.extra : L.jblob + gj.seedmap_off;
+    const int tid = threadIdx.x;
+    const uint32_t n_tiles = (b.n_reads + T - 1) / T;
+
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t ri = tile * T + tid;
+        const bool live = ri < b.n_reads;
+        int action = FAST_DONE;
+        dcb_result out;
+        *reinterpret_cast<uint4*>(&out) = make_uint4(0, 0, 0, 0);
+        if (live) {
+            uint32_t w[NW];
+            const uint4* src = reinterpret_cast<const uint4*>(b.words + (size_t)ri * NW);
+#pragma unroll
+            for (int k = 0; k < NW / 4; k++) {
+                const uint4 v = ldg_stream(src + k);
+                w[4 * k + 0] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+            }
+#pragma unroll
+            for (int k = 0; k < NW; k++) s_rd[k * T + tid] = w[k];
+            const bool flagged = b.n_exc && ((__ldg(b.flags + (ri >> 5)) >> (ri & 31)) & 1u);
+            if (flagged) {
+                action = FAST_DEFER;
+            } else {
+                ReadView r;
+                r.w = s_rd + tid; r.inv = nullptr; r.stride = T;
+                r.n = b.uniform_len ? (int)b.uniform_len : (int)__ldg(b.lens + ri);
+                r.nw = NW;
+                r.exc_pos = nullptr; r.exc_kind = nullptr; r.e0 = r.e1 = 0; r.mirror = 0;
+                FullHit vh, jh;
+                vh.count = 0; vh.tag = 0; vh.pos = 0;
+                jh.count = 0; jh.tag = 0; jh.pos = 0;
+                uint32_t lo, hi;
+                SeedScan<NW, QV, SV>::run(w, vmap, lo, hi);
+                SeedScan<NW, QV, SV>::clip(r.n, lo, hi);
+                constexpr uint32_t VMASK = (1u << (2 * QV)) - 1u;
+                while ((lo | hi) && vh.count < 2) {
+                    int i;
+                    if (lo) { i = __ffs(lo) - 1; lo &= lo - 1; } else { i = 32 + __ffs(hi) - 1; hi &= hi - 1; }
+                    const int p = i * SV;
+                    const uint32_t key = rd_win16(r, p) & VMASK;
+                    fast_verify_seed(r, L.vblob, gv, p, key, vh);
+                    if (UNION) fast_verify_seed(r, L.jblob, gj, p, key, jh);
+                }
+                if (!UNION && vh.count == 1) {
+                    SeedScan<NW, QJ, SJ>::run(w, jmap, lo, hi);
+                    SeedScan<NW, QJ, SJ>::clip(r.n, lo, hi);
+                    constexpr uint32_t JMASK = (1u << (2 * QJ)) - 1u;
+                    while ((lo | hi) && jh.count < 2) {
+                        int i;
+                        if (lo) { i = __ffs(lo) - 1; lo &= lo - 1; } else { i = 32 + __ffs(hi) - 1; hi &= hi - 1; }
+                        const int p = i * SJ;
+                        fast_verify_seed(r, L.jblob, gj, p, rd_win16(r, p) & JMASK, jh);
+                    }
+                }
+                action = dcr_fast_from_hits(r, L.vblob, L.jblob, vh, jh, prm, both_frames, out, L.cnt);
+            }
+        }
+        defer_reads(live && action == FAST_DEFER, ri, queue, queue_count);
+        if (live && action == FAST_DONE) store_result(results + ri, out);
+    }
+    flush_counters(L.cnt, counters);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -180,22 +328,19 @@ dcb_general_kernel(BatchDev b, const uint32_t* __restrict__ vblob_g, const uint3
                    unsigned long long* __restrict__ counters, const uint32_t* __restrict__ queue,
                    const uint32_t* __restrict__ queue_count) {
     extern __shared__ __align__(16) uint32_t smem[];
-    const int T = kGeneralThreads;
+    const int T = blockDim.x;
     const int nw = (int)b.slot_words, nwi = (nw + 1) / 2;
-    uint32_t* vblob = smem;
-    uint32_t* jblob = vblob + vwords;
-    uint32_t* s_rd = jblob + jwords;              // [nw][T]
+    SmemLayout L = carve(smem, vwords, jwords, 0, (size_t)(nw + nwi) * T * (both_frames ? 2 : 1));
+    uint32_t* s_rd = L.cols;                      // [nw][T]
     uint32_t* s_inv = s_rd + (size_t)nw * T;      // [nwi][T]
     uint32_t* s_rd1 = s_inv + (size_t)nwi * T;    // second frame (only when both_frames)
-    uint32_t* s_inv1 = s_rd1 + (both_frames ? (size_t)nw * T : 0);
-    dcb_cnt_t* s_cnt = s_inv1 + (both_frames ? (size_t)nwi * T : 0);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(s_cnt + ((DCB_NCOUNTERS + 3) & ~3));
+    uint32_t* s_inv1 = s_rd1 + (size_t)nw * T;
 
-    tma_stage_begin(bar, (uint32_t)(vwords + jwords) * 4u);
-    tma_stage_copy(bar, vblob, vblob_g, (uint32_t)vwords * 4u);
-    tma_stage_copy(bar, jblob, jblob_g, (uint32_t)jwords * 4u);
-    if (threadIdx.x < DCB_NCOUNTERS) s_cnt[threadIdx.x] = 0;
-    tma_stage_wait(bar);
+    tma_stage_begin(L.bar, (uint32_t)(vwords + jwords) * 4u);
+    tma_stage_copy(L.bar, L.vblob, vblob_g, (uint32_t)vwords * 4u);
+    tma_stage_copy(L.bar, L.jblob, jblob_g, (uint32_t)jwords * 4u);
+    if (threadIdx.x < DCB_NCOUNTERS) L.cnt[threadIdx.x] = 0;
+    tma_stage_wait(L.bar);
     __syncthreads();
 
     const int tid = threadIdx.x;
@@ -222,13 +367,11 @@ dcb_general_kernel(BatchDev b, const uint32_t* __restrict__ vblob_g, const uint3
         ex.read = b.exc_read; ex.pos = b.exc_pos; ex.kind = b.exc_kind; ex.n = b.n_exc;
         dcb_result out;
         *reinterpret_cast<uint4*>(&out) = make_uint4(0, 0, 0, 0);
-        dcr_general_read(r, ri, flagged, ex, s_inv + tid, s_rd1 + tid, s_inv1 + tid, vblob, jblob, prm, both_frames,
-                         out, s_cnt);
+        dcr_general_read(r, ri, flagged, ex, s_inv + tid, s_rd1 + tid, s_inv1 + tid, L.vblob, L.jblob, prm, both_frames,
+                         out, L.cnt);
         store_result(results + ri, out);
     }
-    __syncthreads();
-    if (threadIdx.x < DCB_NCOUNTERS && s_cnt[threadIdx.x])
-        atomicAdd(counters + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+    flush_counters(L.cnt, counters);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -278,9 +421,33 @@ struct dcb_ctx {
     std::vector<Ev> events;
     double ms[DCB_NTIMERS] = {0, 0, 0, 0};
     uint64_t launches[DCB_NTIMERS] = {0, 0, 0, 0};
-    int exact_grid = 0, general_grid = 0;
+    int exact_grid = 0, general_grid = 0, exact_threads = kExactThreads, general_threads = kGeneralThreads;
     size_t exact_smem = 0, general_smem = 0;
+    // seed geometry of the two genes and the union bitmap (built when they agree)
+    int qv = 0, sv = 0, qj = 0, sj = 0, vcore_words = 0, jcore_words = 0, union_words = 0;
+    uint32_t* d_union = nullptr;
+    void* spec_fn = nullptr;   // specialised exact kernel picked for the resident batch, or null
+    bool spec_union = false;
 };
+
+typedef void (*exact_spec_fn)(BatchDev, const uint32_t*, const uint32_t*, const uint32_t*, int, int, int, DcrParams, int,
+                              dcb_result*, unsigned long long*, uint32_t*, uint32_t*);
+
+// Specialisations compiled in: V seeds (q=9, stride 12) -- every shipped V tag set has 20-nt minimum tags --
+// with J either sharing that geometry (20-nt J tags: one union bitmap) or using (q=8, stride 5) (12-nt J tags).
+static exact_spec_fn pick_spec(int nw, int qv, int sv, int qj, int sj, bool* is_union) {
+    if (qv != 9 || sv != 12) return nullptr;
+    const bool uni = (qj == 9 && sj == 12), sep = (qj == 8 && sj == 5);
+    if (!uni && !sep) return nullptr;
+    *is_union = uni;
+    switch (nw) {
+        case 8:  return uni ? dcb_exact_kernel_spec<8, 9, 12, 9, 12, true> : dcb_exact_kernel_spec<8, 9, 12, 8, 5, false>;
+        case 12: return uni ? dcb_exact_kernel_spec<12, 9, 12, 9, 12, true> : dcb_exact_kernel_spec<12, 9, 12, 8, 5, false>;
+        case 16: return uni ? dcb_exact_kernel_spec<16, 9, 12, 9, 12, true> : dcb_exact_kernel_spec<16, 9, 12, 8, 5, false>;
+        case 20: return uni ? dcb_exact_kernel_spec<20, 9, 12, 9, 12, true> : dcb_exact_kernel_spec<20, 9, 12, 8, 5, false>;
+        default: return nullptr;
+    }
+}
 
 static int upload_blob(const std::vector<uint32_t>& v, uint32_t** d, int* words) {
     CUDA_TRY(cudaMalloc((void**)d, v.size() * 4));
@@ -346,6 +513,18 @@ dcb_ctx* dcb_ctx_create(int device, const dcb_tagset* v, const dcb_tagset* j, co
     if (upload_blob(v->general, &c->d_vgen, &c->vgen_words) || upload_blob(j->general, &c->d_jgen, &c->jgen_words) ||
         upload_blob(v->fast, &c->d_vfast, &c->vfast_words) || upload_blob(j->fast, &c->d_jfast, &c->jfast_words))
         return fail(nullptr);
+    {
+        const DcbGene& gv = *reinterpret_cast<const DcbGene*>(v->fast.data());
+        const DcbGene& gj = *reinterpret_cast<const DcbGene*>(j->fast.data());
+        c->qv = gv.q; c->sv = gv.stride; c->qj = gj.q; c->sj = gj.stride;
+        c->vcore_words = gv.core_words; c->jcore_words = gj.core_words;
+        if (gv.q == gj.q && gv.stride == gj.stride) {
+            const size_t words = (size_t)gv.n_words - gv.seedmap_off;
+            std::vector<uint32_t> u(words);
+            for (size_t i = 0; i < words; i++) u[i] = v->fast[gv.seedmap_off + i] | j->fast[gj.seedmap_off + i];
+            if (upload_blob(u, &c->d_union, &c->union_words)) return fail(nullptr);
+        }
+    }
     if (cudaMalloc((void**)&c->d_queue_count, 16) != cudaSuccess) return fail("cudaMalloc");
     if (cudaMalloc((void**)&c->d_counters, sizeof(unsigned long long) * DCB_NCOUNTERS) != cudaSuccess) return fail("cudaMalloc");
     return c;
@@ -357,7 +536,7 @@ void dcb_ctx_destroy(dcb_ctx* c) {
     timing_collect(c);
     if (c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
     cudaFree(c->d_vgen); cudaFree(c->d_jgen); cudaFree(c->d_vfast); cudaFree(c->d_jfast);
-    cudaFree(c->d_queue_count); cudaFree(c->d_counters);
+    cudaFree(c->d_queue_count); cudaFree(c->d_counters); cudaFree(c->d_union);
     c->words.release(); c->lens.release(); c->flags.release(); c->exc_read.release(); c->exc_pos.release();
     c->exc_kind.release(); c->results.release(); c->queue.release();
     delete c;
@@ -398,24 +577,49 @@ int dcb_upload(dcb_ctx* c, const dcb_packed* P) {
     b.n_reads = (uint32_t)n; b.slot_words = (uint32_t)sw; b.uniform_len = P->uniform_len; b.n_exc = P->n_exc;
     c->have_batch = true; c->ran = false;
 
-    // launch geometry: persistent blocks, a whole number of blocks per SM
+    // launch geometry: persistent blocks, a whole number of blocks per SM; long reads get narrower blocks
     const size_t tail = (((DCB_NCOUNTERS + 3) & ~3) + 4) * 4;
-    c->exact_smem = ((size_t)c->vfast_words + c->jfast_words + sw * kExactThreads) * 4 + tail;
+    const size_t kMaxSmem = 227 * 1024;
     const size_t nwi = (sw + 1) / 2;
-    c->general_smem = ((size_t)c->vgen_words + c->jgen_words + (sw + nwi) * kGeneralThreads * (c->params.both_frames ? 2 : 1)) * 4 + tail;
-    if (c->exact_smem > 227 * 1024 || c->general_smem > 227 * 1024) {
-        dcb_set_error("dcb_upload: tables + reads of %u nt need %zu / %zu bytes of shared memory (max 232448)",
-                      P->max_len, c->exact_smem, c->general_smem);
-        return DCB_EUNSUPPORTED;
-    }
-    CUDA_TRY(cudaFuncSetAttribute(dcb_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->exact_smem));
-    CUDA_TRY(cudaFuncSetAttribute(dcb_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->general_smem));
+    bool is_union = false;
+    exact_spec_fn spec = c->params.force_general ? nullptr : pick_spec((int)sw, c->qv, c->sv, c->qj, c->sj, &is_union);
+    c->spec_fn = (void*)spec; c->spec_union = is_union;
     int occ_e = 0, occ_g = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, dcb_exact_kernel, kExactThreads, c->exact_smem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, dcb_general_kernel, kGeneralThreads, c->general_smem));
+    if (spec) {
+        const size_t tbl = is_union ? (size_t)c->vcore_words + c->jcore_words + c->union_words
+                                    : (size_t)c->vfast_words + c->jfast_words;
+        c->exact_threads = kExactThreads;
+        c->exact_smem = (tbl + sw * kExactThreads) * 4 + tail;
+        if (c->exact_smem > kMaxSmem) { spec = nullptr; c->spec_fn = nullptr; }
+    }
+    if (spec) {
+        CUDA_TRY(cudaFuncSetAttribute(spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->exact_smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, spec, c->exact_threads, c->exact_smem));
+    } else {
+        int T = kExactThreads;
+        for (; T >= 32; T >>= 1) {
+            c->exact_smem = ((size_t)c->vfast_words + c->jfast_words + sw * T) * 4 + tail;
+            if (c->exact_smem <= kMaxSmem) break;
+        }
+        if (T < 32) { dcb_set_error("dcb_upload: tag tables + %u-nt reads do not fit in shared memory", P->max_len); return DCB_EUNSUPPORTED; }
+        c->exact_threads = T;
+        CUDA_TRY(cudaFuncSetAttribute(dcb_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->exact_smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, dcb_exact_kernel, T, c->exact_smem));
+    }
+    {
+        int T = kGeneralThreads;
+        for (; T >= 32; T >>= 1) {
+            c->general_smem = ((size_t)c->vgen_words + c->jgen_words + (sw + nwi) * T * (c->params.both_frames ? 2 : 1)) * 4 + tail;
+            if (c->general_smem <= kMaxSmem) break;
+        }
+        if (T < 32) { dcb_set_error("dcb_upload: tag tables + %u-nt reads do not fit in shared memory", P->max_len); return DCB_EUNSUPPORTED; }
+        c->general_threads = T;
+        CUDA_TRY(cudaFuncSetAttribute(dcb_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->general_smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, dcb_general_kernel, T, c->general_smem));
+    }
     if (occ_e < 1 || occ_g < 1) { dcb_set_error("dcb_upload: kernel does not fit on an SM"); return DCB_EUNSUPPORTED; }
-    const uint32_t tiles_e = (uint32_t)((n + kExactThreads - 1) / kExactThreads);
-    const uint32_t tiles_g = (uint32_t)((n + kGeneralThreads - 1) / kGeneralThreads);
+    const uint32_t tiles_e = (uint32_t)((n + c->exact_threads - 1) / c->exact_threads);
+    const uint32_t tiles_g = (uint32_t)((n + c->general_threads - 1) / c->general_threads);
     c->exact_grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(tiles_e, (uint32_t)(c->n_sms * occ_e)));
     c->general_grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(tiles_g, (uint32_t)(c->n_sms * occ_g)));
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -435,14 +639,22 @@ int dcb_run_resident(dcb_ctx* c) {
     int rc;
     if (!c->params.force_general) {
         if ((rc = timing_begin(c, 0))) return rc;
-        dcb_exact_kernel<<<c->exact_grid, kExactThreads, c->exact_smem, s>>>(
-            b, c->d_vfast, c->d_jfast, c->vfast_words, c->jfast_words, prm, c->params.both_frames,
-            (dcb_result*)c->results.p, c->d_counters, (uint32_t*)c->queue.p, c->d_queue_count);
+        if (c->spec_fn) {
+            const bool u = c->spec_union;
+            ((exact_spec_fn)c->spec_fn)<<<c->exact_grid, c->exact_threads, c->exact_smem, s>>>(
+                b, c->d_vfast, c->d_jfast, u ? c->d_union : nullptr, u ? c->vcore_words : c->vfast_words,
+                u ? c->jcore_words : c->jfast_words, u ? c->union_words : 0, prm, c->params.both_frames,
+                (dcb_result*)c->results.p, c->d_counters, (uint32_t*)c->queue.p, c->d_queue_count);
+        } else {
+            dcb_exact_kernel<<<c->exact_grid, c->exact_threads, c->exact_smem, s>>>(
+                b, c->d_vfast, c->d_jfast, c->vfast_words, c->jfast_words, prm, c->params.both_frames,
+                (dcb_result*)c->results.p, c->d_counters, (uint32_t*)c->queue.p, c->d_queue_count);
+        }
         CUDA_TRY(cudaGetLastError());
         if ((rc = timing_end(c))) return rc;
     }
     if ((rc = timing_begin(c, 1))) return rc;
-    dcb_general_kernel<<<c->general_grid, kGeneralThreads, c->general_smem, s>>>(
+    dcb_general_kernel<<<c->general_grid, c->general_threads, c->general_smem, s>>>(
         b, c->d_vgen, c->d_jgen, c->vgen_words, c->jgen_words, prm, c->params.both_frames, (dcb_result*)c->results.p,
         c->d_counters, c->params.force_general ? nullptr : (const uint32_t*)c->queue.p, c->d_queue_count);
     CUDA_TRY(cudaGetLastError());

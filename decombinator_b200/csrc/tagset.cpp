@@ -185,9 +185,6 @@ dcb_tagset* dcb_tagset_build(const char* const* tags, const int32_t* jumps, cons
         } else {
             g.q = lmin >= 18 ? 9 : lmin >= 12 ? 8 : lmin >= 8 ? 6 : lmin;
             g.stride = lmin - g.q + 1;
-            size_t words = ((size_t)1 << (2 * g.q)) / 32;
-            if (words == 0) words = 1;
-            g.seedmap_off = b.reserve(words);
             std::map<uint32_t, uint32_t> seeds;  // q-mer -> mask of offsets
             for (int i = 0; i < n; i++) {
                 for (size_t o = 0; o + g.q <= full[i].size(); o++) {
@@ -201,7 +198,6 @@ dcb_tagset* dcb_tagset_build(const char* const* tags, const int32_t* jumps, cons
             g.seedhash_off = b.reserve(2 * (size_t)hsize);
             for (uint32_t i = 0; i < hsize; i++) b.w[g.seedhash_off + 2 * i] = DCB_HASH_EMPTY;
             for (auto& kv : seeds) {
-                b.w[g.seedmap_off + (kv.first >> 5)] |= 1u << (kv.first & 31);
                 uint32_t h = dcb_hash32(kv.first) & (hsize - 1);
                 while (b.w[g.seedhash_off + 2 * h] != DCB_HASH_EMPTY) h = (h + 1) & (hsize - 1);
                 b.w[g.seedhash_off + 2 * h] = kv.first;
@@ -218,10 +214,17 @@ dcb_tagset* dcb_tagset_build(const char* const* tags, const int32_t* jumps, cons
                 while (b.w[g.prefhash_off + h] != DCB_HASH_EMPTY) h = (h + 1) & (psize - 1);
                 b.w[g.prefhash_off + h] = (uint32_t)i;
             }
+            while (b.w.size() % 4) b.w.push_back(0u);
+            g.core_words = (int32_t)b.w.size();
+            size_t words = ((size_t)1 << (2 * g.q)) / 32;  // the seed bitmap comes last
+            if (words < 4) words = 4;
+            g.seedmap_off = b.reserve(words);
+            for (auto& kv : seeds)
+                b.w[g.seedmap_off + DCB_SEEDMAP_WORD(kv.first, g.q)] |= 1u << DCB_SEEDMAP_BIT(kv.first, g.q);
         }
         while (b.w.size() % 4) b.w.push_back(0u);  // 16-byte granularity for vector copies
         g.n_words = (int32_t)b.w.size();
-        g.general_words = which == 0 ? g.n_words : 0;
+        if (which == 0) g.core_words = g.n_words;
         std::memcpy(&b.w[g.tag_off], trec.data(), sizeof(DcbTag) * n);
         std::memcpy(&b.w[0], &g, sizeof(g));
         (which == 0 ? ts->general : ts->fast) = std::move(b.w);

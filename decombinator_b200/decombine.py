@@ -1,0 +1,258 @@
+"""Drop-in for the reference's ``decombinator.decombine`` module, with the hot loop on the GPU.
+
+Same entry points and contracts as /root/reference/src/decombinator/decombine.py:
+
+* ``decombinator(inputargs) -> list[list[str]]``  (reference decombine.py:881): same argument dict,
+  same rows (``[v, j, vdel, jdel, insert, readid, tcrseq, tcrQ, bc, bcQ]``), same summary CSV, same errors;
+* ``import_tcr_info(inputargs)`` (decombine.py:593) and ``dcr(read, inputargs)`` (decombine.py:534): the
+  per-read contract, here one-read batches through the same kernels;
+* ``counts``: the module-level ``collections.Counter`` the reference exposes.
+
+What changed is the body of the read loop: all V(D)J reads are 2-bit packed (``dcb_pack_reads``), the
+batch is analysed by the CUDA kernels behind ``dcb_decombine_batch``, and only the positions come back;
+the output strings are sliced on the host from the text it already holds.  There is no CPU
+implementation of the matching here: without libdcb.so and a GPU these functions raise.
+"""
+import collections as coll
+import os
+from time import strftime, time
+
+import numpy as np
+
+from . import __version__, _lib, fastq, tags
+from .fastq import opener_check, readfq  # noqa: F401  (re-exported like the reference module)
+
+counts = coll.Counter()
+chainnams = tags.CHAINNAMS
+chain = None
+_info = None      # TcrInfo of the last import_tcr_info()
+_ctx_cache = {}   # (both_frames, allowNs, lenthreshold) -> _lib.Context
+
+_COMP = bytes.maketrans(b"ACGTUMRWSYKVHDBNacgtumrwsykvhdbn", b"TGCAAKYWSRMBDHVNtgcaakywsrmbdhvn")
+
+
+def revcomp(read):
+    """Reverse complement with Bio.Seq's table (decombine.py:182-184); used for the output strings."""
+    return read.encode("latin-1").translate(_COMP)[::-1].decode("latin-1")
+
+
+def sort_permissions(fl):
+    """decombine.py:869-873"""
+    if oct(os.stat(fl).st_mode)[4:] != "666":
+        os.chmod(fl, 0o666)
+
+
+def import_tcr_info(inputargs):
+    """Gather the TCR chain information and build the device tag tables (decombine.py:593-746)."""
+    global counts, chain, _info, _ctx_cache
+    counts = coll.Counter()
+    _info = tags.TcrInfo(inputargs)
+    chain = _info.chain
+    if _info.chain_detected:
+        counts["chain_detected"] = 1
+    for c in _ctx_cache.values():
+        c.close()
+    _ctx_cache = {}
+    g = globals()
+    for name in ("v_seqs", "j_seqs", "half1_v_seqs", "half2_v_seqs", "half1_j_seqs", "half2_j_seqs", "jump_to_end_v",
+                 "jump_to_start_j", "v_regions", "j_regions", "v_half_split", "j_half_split"):
+        g[name] = getattr(_info, name)
+    return _info
+
+
+def _context(inputargs, both_frames):
+    key = (bool(both_frames), bool(inputargs["allowNs"]), int(inputargs["lenthreshold"]))
+    ctx = _ctx_cache.get(key)
+    if ctx is None:
+        vt, jt = _info.tables()
+        device = int(os.environ.get("LOCAL_RANK", inputargs.get("device", 0) or 0))
+        ctx = _lib.Context(vt, jt, device=device, both_frames=key[0], allow_ns=key[1], lenthreshold=key[2])
+        _ctx_cache[key] = ctx
+    return ctx
+
+
+def _orientation_plan(orientation):
+    """-> (pack the reverse complement?, retry the other frame?) (decombine.py:999-1010)"""
+    if orientation == "reverse":
+        return True, False
+    if orientation == "forward":
+        return False, False
+    if orientation == "both":
+        return True, True
+    raise UnboundLocalError("orientation must be forward, reverse or both")  # reference: unbound `recom`
+
+
+def _add_device_counters(dev_counts):
+    for name, val in zip(_lib.counter_names(), dev_counts):
+        if val:
+            counts[name] += int(val)
+
+
+def dcr(read, inputargs):
+    """Check one read (in the given frame) for a rearranged TCR (decombine.py:534-585).
+
+    Returns ``[v, j, vdel, jdel, insert, v_seq_start, j_seq_end]`` or None and bumps ``counts`` like the
+    reference.  ``import_tcr_info`` must have been called first."""
+    ctx = _context(inputargs, False)
+    packed = _lib.pack_strings([read], revcomp=False)
+    res, dev_counts = ctx.decombine(packed)
+    packed.free()
+    _add_device_counters(dev_counts)
+    r = res[0]
+    if not r["status"]:
+        return None
+    return [int(r["v"]), int(r["j"]), int(r["vdel"]), int(r["jdel"]), read[int(r["ins_start"]):int(r["ins_end"])],
+            int(r["v_seq_start"]), int(r["j_seq_end"])]
+
+
+def decombine_batch(batch: fastq.ReadBatch, inputargs):
+    """GPU pass over every V(D)J read of the batch -> dcb_result array (one record per read)."""
+    pack_rc, both = _orientation_plan(inputargs["orientation"])
+    ctx = _context(inputargs, both)
+    packed = _lib.pack_arrays(batch.buf, batch.off, batch.len, revcomp=pack_rc)
+    res, dev_counts = ctx.decombine(packed)
+    packed.free()
+    _add_device_counters(dev_counts)
+    return res
+
+
+def _summary_path(inputargs, logpath, date, samplenam, number=None):
+    name = logpath + date + "_"
+    if inputargs["chain"]:
+        name += chainnams[chain] + "_"
+    name += samplenam + "_Decombinator_Summary" + ("" if number is None else str(number)) + ".csv"
+    return name
+
+
+def _open_summary(inputargs, summaryname, logpath, date, samplenam):
+    """First free name among Summary.csv, Summary2.csv, ... (decombine.py:1082-1095)."""
+    if not os.path.exists(summaryname):
+        return summaryname, open(summaryname, "wt")
+    for i in range(2, 10000):
+        cand = _summary_path(inputargs, logpath, date, samplenam, i)
+        if not os.path.exists(cand):
+            return cand, open(cand, "wt")
+    raise RuntimeError("no free summary file name")
+
+
+def decombinator(inputargs: dict) -> list:
+    """Function wrapper for decombinator (decombine.py:881-1202)."""
+    print("Running Decombinator version", __version__)
+    opener = opener_check(inputargs)
+    import_tcr_info(inputargs)
+
+    samplenam = str(inputargs["infile"].split(".")[0])
+    if os.sep in samplenam:
+        samplenam = samplenam.split(os.sep)[-1]
+
+    summaryname = logpath = None
+    date = strftime("%Y_%m_%d")
+    if inputargs["suppresssummary"] == False:  # noqa: E712
+        logpath = inputargs["outpath"] + f"Logs{os.sep}"
+        if not os.path.exists(logpath):
+            os.makedirs(logpath)
+        summaryname = _summary_path(inputargs, logpath, date, samplenam)
+
+    if inputargs["dontcheck"] == False:  # noqa: E712
+        if summaryname is None:
+            raise UnboundLocalError("cannot access local variable 'summaryname'")  # as the reference (-s without -dk)
+        if not fastq.fastq_sanity(inputargs["infile"], opener):
+            # stub summary for an empty input (decombine.py:131-161)
+            inout_name = "_".join(f"{samplenam}".split("_")[:-1]) + f"_{chainnams[chain]}"
+            summstr = "OutputFile," + inout_name + "\nNumberReadsInput," + "0"
+            summaryname, fh = _open_summary(inputargs, summaryname, logpath, date, samplenam)
+            print(summstr, file=fh)
+            fh.close()
+            sort_permissions(summaryname)
+            raise ValueError(
+                "There are fewer than four lines in this file, and thus it is not a valid FASTQ file. Please check input and try again."
+            )
+
+    counts["start_time"] = time()
+    print("Decombining FASTQ data...")
+
+    outdata = []
+    if inputargs["nobarcoding"] == False:  # noqa: E712
+        batch = fastq.load_pairs(inputargs, opener)
+        n = len(batch)
+        if inputargs["allowNs"] == False:  # noqa: E712
+            counts["dcrfilter_barcodeN"] += sum(1 for bc in batch.bc if "N" in bc)
+            if counts["dcrfilter_barcodeN"] == 0:
+                del counts["dcrfilter_barcodeN"]
+        counts["read_count"] += n
+        if inputargs["dontcount"] == False:  # noqa: E712
+            for k in range(100000, n + 1, 100000):
+                print("\t read", k)
+        res = decombine_batch(batch, inputargs) if n else np.zeros(0, dtype=_lib.RESULT_DTYPE)
+        pack_rc, _ = _orientation_plan(inputargs["orientation"])
+        hits = np.nonzero(res["status"])[0]
+        counts["vj_count"] += int(len(hits))
+        sampling = inputargs.get("sampling_analysis")
+        for i in hits:
+            r = res[i]
+            # frame "reverse" <=> the analysed string was revcomp(vdj) (decombine.py:1015-1020)
+            is_rev = pack_rc != bool(r["frame"])
+            a, b = int(r["v_seq_start"]), int(r["j_seq_end"])
+            vdj, vdjqual = batch.vdj[i], batch.vdjqual[i]
+            oriented = revcomp(vdj) if is_rev else vdj
+            tcrseq = oriented[a:b]
+            tcrQ = vdjqual[::-1][a:b] if is_rev else vdjqual[a:b]
+            row = [str(int(r["v"])), str(int(r["j"])), str(int(r["vdel"])), str(int(r["jdel"])),
+                   oriented[int(r["ins_start"]):int(r["ins_end"])], batch.ids[i], tcrseq, tcrQ, batch.bc[i], batch.bcq[i]]
+            if sampling:
+                row.append(batch.v_tail[i])
+            outdata.append(row)
+    else:
+        # the reference's read loop is nested under `nobarcoding == False` (decombine.py:950): nothing is read
+        if inputargs["extension"] == "n12":
+            print("Non-barcoding option selected, but default output file extension (n12) detected. "
+                  "Automatically changing to 'nbc'.")
+
+    counts["end_time"] = time()
+    timetaken = counts["end_time"] - counts["start_time"]
+
+    print("Analysed", "{:,}".format(counts["read_count"]), "reads, finding", "{:,}".format(counts["vj_count"]),
+          chainnams[chain], "VJ rearrangements")
+    print("Reading from", inputargs["infile"] + ", writing to variable")
+    print("Took", str(round(timetaken, 2)), "seconds")
+
+    if inputargs["suppresssummary"] == False:  # noqa: E712
+        summaryname, summaryfile = _open_summary(inputargs, summaryname, logpath, date, samplenam)
+        inout_name = "_".join(f"{samplenam}".split("_")[:-1]) + f"_{chainnams[chain]}"
+        summstr = ("Property,Value\nDirectory," + os.getcwd() + "\nInputFile," + inout_name + "\nOutputFile," + inout_name
+                   + "\nDateFinished," + date + "\nTimeFinished," + strftime("%H:%M:%S") + "\nTimeTaken(Seconds),"
+                   + str(round(timetaken, 2)) + "\n\nInputArguments:,\n")
+        for s in ["species", "chain", "extension", "tags", "dontgzip", "allowNs", "orientation", "lenthreshold", "bc_read",
+                  "bclength"]:
+            summstr = summstr + s + "," + str(inputargs[s]) + "\n"
+        counts["pc_decombined"] = counts["vj_count"] / counts["read_count"]
+        sections = [
+            ("\nNumberReadsInput,", "read_count"), ("\nNumberReadsDecombined,", "vj_count"),
+        ]
+        for label, key in sections:
+            summstr += label + str(counts[key])
+        summstr += "\nPercentReadsDecombined," + str(round(counts["pc_decombined"], 3))
+        summstr += "\n\nReadsAssignedUsingHalfTags:,"
+        for label, key in (("V1error", "verr1"), ("V2error", "verr2"), ("J1error", "jerr1"), ("J2error", "jerr2")):
+            summstr += "\n" + label + "," + str(counts[key])
+        summstr += "\n\nReadsFilteredOut:,"
+        for label, key in (("AmbiguousBaseCall(DCR)", "dcrfilter_intertagN"),
+                           ("AmbiguousBaseCall(Barcode)", "dcrfilter_barcodeN"),
+                           ("OverlongInterTagSeq", "dcrfilter_toolong_intertag"),
+                           ("ImpossibleDeletions", "dcrfilter_imposs_deletion"),
+                           ("OverlappingTagBoundaries", "dcrfilter_tag_overlap")):
+            summstr += "\n" + label + "," + str(counts[key])
+        summstr += "\n\nReadsFailedAssignment:,"
+        for label, key in (("MultipleVtagMatches", "multiple_v_matches"), ("VTagAtEndRead", "v_del_failed_tag_at_end"),
+                           ("VDeletionsUndetermined", "v_del_failed"), ("FoundV1HalfTagNotV2", "foundv1notv2"),
+                           ("FoundV2HalfTagNotV1", "foundv2notv1"), ("NoVDetected", "no_vtags_found"),
+                           ("MultipleJTagMatches", "multiple_j_matches"), ("JDeletionsUndermined", "j_del_failed"),
+                           ("FoundJ1HalfTagNotJ2", "foundj1notj2"), ("FoundJ2HalfTagNotJ1", "foundj2notj1"),
+                           ("NoJDetected", "no_j_assigned")):
+            summstr += "\n" + label + "," + str(counts[key])
+        print(summstr, file=summaryfile)
+        summaryfile.close()
+        sort_permissions(summaryname)
+
+    return outdata
+

@@ -1,0 +1,130 @@
+"""FASTQ reading for the decombine path (reference decombine.py:118-179, 228-265).
+
+``readfq`` keeps the exact record semantics of the reference's parser (Heng Li's readfq as shipped there:
+the name is the header up to the first space, sequence and quality may span lines, and the last character
+of every line is dropped unconditionally).  ``load_pairs`` materialises the records the main loop needs
+(decombine.py:950-989) as flat byte buffers that go straight to ``dcb_pack_reads``.
+"""
+import gzip
+import itertools
+
+import numpy as np
+
+
+def opener_check(inputargs):
+    """gzip.open for ``.gz`` inputs, else open (decombine.py:118-123)."""
+    return gzip.open if inputargs["infile"].endswith(".gz") else open
+
+
+def fastq_sanity(path, opener):
+    """The three checks of fastq_check (decombine.py:126-179) on the first record.
+
+    Returns False when the file holds fewer than four lines (the caller writes the stub summary and raises,
+    as the reference does); raises ValueError for a malformed first record."""
+    with opener(path, "rt") as fh:
+        if sum(1 for _ in itertools.islice(fh, 4)) < 4:
+            return False
+        # the reference keeps reading from the same handle, i.e. it inspects lines 5-8
+        rec = list(itertools.islice(fh, 0, 4))
+    if rec[0][0] != "@":
+        raise ValueError(f"Expected @ symbol at beginning of file for valid FASTQ. Found {rec[0][0]}.")
+    if rec[2][0] != "+":
+        raise ValueError(f"Expected + symbol at beginning of third line for valid FASTQ. Found {rec[2][0]}.")
+    if len(rec[1]) != len(rec[3]):
+        raise ValueError(
+            f"Length of read to match length of read quality. Found read length = {len(rec[1])} and read quality length = {len(rec[3])}"
+        )
+    return True
+
+
+def readfq(fp):
+    """Generator of (name, seq, qual) with the reference parser's behaviour (decombine.py:228-265)."""
+    pending = None
+    while True:
+        if not pending:
+            for line in fp:
+                if line[0] in ">@":
+                    pending = line[:-1]
+                    break
+        if not pending:
+            return
+        name = pending[1:].partition(" ")[0]
+        pending = None
+        chunks = []
+        for line in fp:
+            if line[0] in "@+>":
+                pending = line[:-1]
+                break
+            chunks.append(line[:-1])
+        if not pending or pending[0] != "+":
+            yield name, "".join(chunks), None
+            if not pending:
+                return
+            continue
+        seq = "".join(chunks)
+        got, quals = 0, []
+        complete = False
+        for line in fp:
+            quals.append(line[:-1])
+            got += len(line) - 1
+            if got >= len(seq):
+                complete = True
+                break
+        if complete:
+            pending = None
+            yield name, seq, "".join(quals)
+        else:
+            yield name, seq, None
+            return
+
+
+class ReadBatch:
+    """Records of one decombine run: V(D)J reads as one byte buffer + per-record Python strings for the rows."""
+
+    __slots__ = ("ids", "vdj", "vdjqual", "bc", "bcq", "v_tail", "buf", "off", "len")
+
+    def __init__(self):
+        self.ids, self.vdj, self.vdjqual, self.bc, self.bcq, self.v_tail = [], [], [], [], [], []
+        self.buf = self.off = self.len = None
+
+    def finalize(self):
+        enc = [s.encode("latin-1", "replace") for s in self.vdj]
+        self.len = np.fromiter((len(b) for b in enc), dtype=np.uint32, count=len(enc))
+        self.off = np.zeros(len(enc), dtype=np.uint64)
+        if len(enc) > 1:
+            np.cumsum(self.len[:-1], dtype=np.uint64, out=self.off[1:])
+        self.buf = np.frombuffer(b"".join(enc) + b"\0", dtype=np.uint8)
+        return self
+
+    def __len__(self):
+        return len(self.vdj)
+
+
+def load_pairs(inputargs, opener) -> ReadBatch:
+    """The record handling at the top of the hot loop (decombine.py:950-983)."""
+    bclength = inputargs["bclength"]
+    batch = ReadBatch()
+    fq1 = readfq(opener(inputargs["infile"], "rt"))
+    if inputargs["bc_read"] == "R2":
+        fq2 = readfq(opener(inputargs["infile"].replace("1.f", "2.f"), "rt"))
+    elif inputargs["bc_read"] == "R1":
+        fq2 = fq1  # the reference zips the generator with itself: two records are consumed per iteration
+    else:
+        raise UnboundLocalError("bc_read must be R1 or R2")  # the reference fails on the unbound fq1/fq2
+    sampling = inputargs.get("sampling_analysis")
+    for record1, record2 in zip(fq1, fq2):
+        if inputargs["bc_read"] == "R2":
+            batch.ids.append(record1[0])
+            batch.vdj.append(record1[1])
+            batch.vdjqual.append(record1[2])
+            batch.bc.append(record2[1][:bclength])
+            batch.bcq.append(record2[2][:bclength])
+        else:
+            batch.ids.append(record1[0])
+            batch.vdj.append(record1[1][bclength:])
+            batch.vdjqual.append(record1[2][bclength:])
+            batch.bc.append(record1[1][0:bclength])
+            batch.bcq.append(record1[2][0:bclength])
+        if sampling:
+            batch.v_tail.append(record2[1][bclength:bclength + 31])
+    return batch.finalize()

