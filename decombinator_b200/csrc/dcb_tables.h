@@ -57,7 +57,8 @@ struct DcbTag {
     uint8_t h1_first_len;        // len(tags[half1 list .index(half1 of this tag)])  (length-guard quirk)
     uint8_t h2_first_len;
     uint8_t edge_ok;             // region_len >= 32
-    uint32_t pad;
+    uint8_t next_same_prefix;    // another tag with the same lmin-prefix (chain), 0xFF = none
+    uint8_t pad8[3];
 };
 
 struct DcbGene {
@@ -68,10 +69,14 @@ struct DcbGene {
     int32_t lmin;                // shortest full tag
     int32_t q, stride;           // seed length, sampling stride (lmin - q + 1)
     int32_t seedmap_off;         // 4^q bits
-    int32_t seedhash_off;        // seedhash_size * 2 words: [key, offset mask]; key == DCB_HASH_EMPTY when free
-    int32_t seedhash_mask;
-    int32_t prefhash_off;        // prefhash_size words: tag id or DCB_HASH_EMPTY, hashed on the lmin-prefix
-    int32_t prefhash_mask;
+    // Both lookups are 2-choice cuckoo tables: a key lives in slot h1(key) or h2(key), so a lookup reads exactly
+    // two slots and never probes (no data-dependent loop for the lanes of a warp to diverge in).
+    int32_t seedhash_off;        // 2^bits slots of 2 words: [q-mer key | DCB_HASH_EMPTY, mask of tag offsets it occurs at]
+    uint32_t seed_c1, seed_c2;   // h(key) = (key * c) >> seed_shift
+    int32_t seed_shift;
+    int32_t prefhash_off;        // 2^bits slots: tag id | DCB_HASH_EMPTY, keyed on the folded lmin-prefix of the tag
+    uint32_t pref_c1, pref_c2;
+    int32_t pref_shift;
     int32_t n_words;             // blob size
     int32_t core_words;          // exact-tag blob: words [0, core_words) exclude the seed bitmap, which comes last
                                  // (a chain whose V and J share (q, stride) is scanned through ONE union bitmap)
@@ -92,7 +97,7 @@ DCB_HD uint32_t dcb_hash32(uint32_t k) {
     k *= 0x9E3779B1u;
     return k ^ (k >> 15);
 }
-DCB_HD uint32_t dcb_hash64(uint32_t lo, uint32_t hi) {
+DCB_HD uint32_t dcb_fold64(uint32_t lo, uint32_t hi) {
     uint32_t k = lo * 0x9E3779B1u + hi * 0x85EBCA77u;
     return k ^ (k >> 13);
 }

@@ -389,39 +389,43 @@ DCB_HD uint32_t revcomp_word(const ReadView& r, int ow) {
 // and the first one.
 struct FullHit { int count, tag, pos; };
 
-// Confirm the candidates behind one seed hit at sampled position p.
+// Record one confirmed full-tag occurrence (the same occurrence can be reached through two seeds).
+DCB_HD void fullhit_add(FullHit& fh, int tag, int pos) {
+    if (fh.count && fh.tag == tag && fh.pos == pos) return;
+    if (fh.count == 0) { fh.tag = tag; fh.pos = pos; }
+    if (fh.count < 2) fh.count++;
+}
+
+// All tags whose lmin-prefix chain starts at `id` against the read window (lo, hi) at position P.
+DCB_HD void fast_try_tags(const ReadView& r, const uint32_t* blob, const DcbGene& g, uint32_t id, int P, uint32_t lo,
+                          uint32_t hi, FullHit& fh) {
+    while (id < 0xFFu) {
+        const DcbTag& t = gene_tag(blob, g, (int)id);
+        const int L = t.len;
+        const uint32_t mlo = mask2(L), mhi = L > 16 ? mask2(L - 16) : 0u;
+        if (P + L <= r.n && !(((lo ^ t.bits_lo) & mlo) | ((hi ^ t.bits_hi) & mhi))) fullhit_add(fh, (int)id, P);
+        id = t.next_same_prefix;
+    }
+}
+
+// Confirm the candidates behind one seed hit at sampled position p (key = the q-mer there).
 DCB_HD void fast_verify_seed(const ReadView& r, const uint32_t* blob, const DcbGene& g, int p, uint32_t key,
                              FullHit& fh) {
-    uint32_t h = dcb_hash32(key) & (uint32_t)g.seedhash_mask;
-    uint32_t offs = 0;
-    for (;;) {
-        uint32_t k = blob[g.seedhash_off + 2 * h];
-        if (k == DCB_HASH_EMPTY) break;
-        if (k == key) { offs = blob[g.seedhash_off + 2 * h + 1]; break; }
-        h = (h + 1) & (uint32_t)g.seedhash_mask;
-    }
+    const uint32_t* sh = blob + g.seedhash_off;
+    const uint32_t s1 = (key * g.seed_c1) >> g.seed_shift, s2 = (key * g.seed_c2) >> g.seed_shift;
+    uint32_t offs = (sh[2 * s1] == key ? sh[2 * s1 + 1] : 0u) | (sh[2 * s2] == key ? sh[2 * s2 + 1] : 0u);
     while (offs) {
-        int o = DCB_FFS(offs) - 1;
+        const int o = DCB_FFS(offs) - 1;
         offs &= offs - 1;
-        int P = p - o;
+        const int P = p - o;
         if (P < 0 || P + g.lmin > r.n) continue;
         uint32_t lo, hi;
         rd_win32(r, P, lo, hi);
-        uint32_t plo = lo & mask2(g.lmin), phi = g.lmin > 16 ? (hi & mask2(g.lmin - 16)) : 0u;
-        uint32_t hh = dcb_hash64(plo, phi) & (uint32_t)g.prefhash_mask;
-        for (;;) {
-            uint32_t id = blob[g.prefhash_off + hh];
-            if (id == DCB_HASH_EMPTY) break;
-            const DcbTag& t = gene_tag(blob, g, (int)id);
-            hh = (hh + 1) & (uint32_t)g.prefhash_mask;
-            int L = t.len;
-            if (P + L > r.n) continue;
-            uint32_t mlo = mask2(L), mhi = L > 16 ? mask2(L - 16) : 0u;
-            if (((lo ^ t.bits_lo) & mlo) | ((hi ^ t.bits_hi) & mhi)) continue;
-            if (fh.count && fh.tag == (int)id && fh.pos == P) continue;  // same occurrence seen via another seed
-            if (fh.count == 0) { fh.tag = (int)id; fh.pos = P; }
-            if (fh.count < 2) fh.count++;
-        }
+        const uint32_t f = dcb_fold64(lo & mask2(g.lmin), g.lmin > 16 ? (hi & mask2(g.lmin - 16)) : 0u);
+        const uint32_t id1 = blob[g.prefhash_off + ((f * g.pref_c1) >> g.pref_shift)];
+        const uint32_t id2 = blob[g.prefhash_off + ((f * g.pref_c2) >> g.pref_shift)];
+        fast_try_tags(r, blob, g, id1, P, lo, hi, fh);
+        if (id2 != id1) fast_try_tags(r, blob, g, id2, P, lo, hi, fh);
     }
 }
 

@@ -37,6 +37,48 @@ uint32_t pow2_at_least(uint32_t x) {
     return p;
 }
 
+// 2-choice cuckoo table: returns false when the insertion walk fails (caller retries with new constants / size)
+struct Cuckoo {
+    uint32_t c1, c2;
+    int bits;
+    std::vector<uint32_t> key, val;
+    std::vector<uint8_t> used;
+    uint32_t h(uint32_t k, int which) const { return (k * (which ? c2 : c1)) >> (32 - bits); }
+    bool build(const std::vector<std::pair<uint32_t, uint32_t>>& items, int bits_, uint32_t c1_, uint32_t c2_) {
+        bits = bits_; c1 = c1_ | 1u; c2 = c2_ | 1u;
+        const size_t n = (size_t)1 << bits;
+        key.assign(n, 0); val.assign(n, 0); used.assign(n, 0);
+        for (auto it : items) {
+            uint32_t k = it.first, v = it.second;
+            int which = 0;
+            bool placed = false;
+            for (int kick = 0; kick < 500; kick++) {
+                uint32_t s = h(k, which);
+                if (!used[s]) { used[s] = 1; key[s] = k; val[s] = v; placed = true; break; }
+                uint32_t s2 = h(k, which ^ 1);
+                if (!used[s2]) { used[s2] = 1; key[s2] = k; val[s2] = v; placed = true; break; }
+                std::swap(k, key[s]); std::swap(v, val[s]);   // evict the occupant of the first choice
+                which = (h(k, 0) == s) ? 1 : 0;               // and send it to its other slot
+            }
+            if (!placed) return false;
+        }
+        return true;
+    }
+};
+
+static bool build_cuckoo(Cuckoo& ck, const std::vector<std::pair<uint32_t, uint32_t>>& items) {
+    int bits = 4;
+    while (((size_t)1 << bits) < 2 * items.size() + 2) bits++;
+    uint64_t rng = 0x2545F4914F6CDD1Dull;
+    for (int grow = 0; grow < 6; grow++, bits++) {
+        for (int attempt = 0; attempt < 64; attempt++) {
+            rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+            if (ck.build(items, bits, (uint32_t)rng, (uint32_t)(rng >> 32))) return true;
+        }
+    }
+    return false;
+}
+
 struct Blob {
     std::vector<uint32_t> w;
     int32_t reserve(size_t n_words) {
@@ -171,6 +213,7 @@ dcb_tagset* dcb_tagset_build(const char* const* tags, const int32_t* jumps, cons
             int f2 = (int)(std::find(h2.begin(), h2.end(), h2[i]) - h2.begin());
             t.h1_first_len = (uint8_t)full[f1].size();
             t.h2_first_len = (uint8_t)full[f2].size();
+            t.next_same_prefix = 0xFF;
         }
         if (which == 0) {
             build_kwset(b, g.full, full);
@@ -193,26 +236,44 @@ dcb_tagset* dcb_tagset_build(const char* const* tags, const int32_t* jumps, cons
                     seeds[lo] |= 1u << o;
                 }
             }
-            uint32_t hsize = pow2_at_least((uint32_t)(2 * seeds.size() + 1));
-            g.seedhash_mask = (int32_t)(hsize - 1);
-            g.seedhash_off = b.reserve(2 * (size_t)hsize);
-            for (uint32_t i = 0; i < hsize; i++) b.w[g.seedhash_off + 2 * i] = DCB_HASH_EMPTY;
-            for (auto& kv : seeds) {
-                uint32_t h = dcb_hash32(kv.first) & (hsize - 1);
-                while (b.w[g.seedhash_off + 2 * h] != DCB_HASH_EMPTY) h = (h + 1) & (hsize - 1);
-                b.w[g.seedhash_off + 2 * h] = kv.first;
-                b.w[g.seedhash_off + 2 * h + 1] = kv.second;
+            {
+                std::vector<std::pair<uint32_t, uint32_t>> items(seeds.begin(), seeds.end());
+                Cuckoo ck;
+                if (!build_cuckoo(ck, items)) { dcb_set_error("dcb_tagset_build: seed table construction failed"); delete ts; return nullptr; }
+                g.seed_c1 = ck.c1; g.seed_c2 = ck.c2; g.seed_shift = 32 - ck.bits;
+                const size_t slots = (size_t)1 << ck.bits;
+                g.seedhash_off = b.reserve(2 * slots);
+                for (size_t i = 0; i < slots; i++) {
+                    b.w[g.seedhash_off + 2 * i] = ck.used[i] ? ck.key[i] : DCB_HASH_EMPTY;
+                    b.w[g.seedhash_off + 2 * i + 1] = ck.used[i] ? ck.val[i] : 0u;
+                }
             }
-            uint32_t psize = pow2_at_least((uint32_t)(2 * n + 1));
-            g.prefhash_mask = (int32_t)(psize - 1);
-            g.prefhash_off = b.reserve(psize);
-            for (uint32_t i = 0; i < psize; i++) b.w[g.prefhash_off + i] = DCB_HASH_EMPTY;
-            for (int i = 0; i < n; i++) {
-                uint32_t lo, hi;
-                pack64(full[i], 0, lmin, lo, hi);
-                uint32_t h = dcb_hash64(lo, hi) & (psize - 1);
-                while (b.w[g.prefhash_off + h] != DCB_HASH_EMPTY) h = (h + 1) & (psize - 1);
-                b.w[g.prefhash_off + h] = (uint32_t)i;
+            {
+                // tags keyed on their lmin-prefix; tags sharing a prefix are chained through next_same_prefix
+                std::map<std::pair<uint32_t, uint32_t>, int> first_with_prefix;
+                std::vector<std::pair<uint32_t, uint32_t>> items;
+                std::map<uint32_t, int> folded_seen;
+                bool fold_clash = false;
+                for (int i = n - 1; i >= 0; i--) {   // descending, so each chain ends up in ascending tag order
+                    uint32_t lo, hi;
+                    pack64(full[i], 0, lmin, lo, hi);
+                    auto key = std::make_pair(lo, hi);
+                    auto it = first_with_prefix.find(key);
+                    trec[i].next_same_prefix = it == first_with_prefix.end() ? 0xFF : (uint8_t)it->second;
+                    first_with_prefix[key] = i;
+                }
+                for (auto& kv : first_with_prefix) {
+                    uint32_t f = dcb_fold64(kv.first.first, kv.first.second);
+                    if (folded_seen.count(f)) fold_clash = true;
+                    folded_seen[f] = 1;
+                    items.emplace_back(f, (uint32_t)kv.second);
+                }
+                Cuckoo ck;
+                if (fold_clash || !build_cuckoo(ck, items)) { dcb_set_error("dcb_tagset_build: prefix table construction failed"); delete ts; return nullptr; }
+                g.pref_c1 = ck.c1; g.pref_c2 = ck.c2; g.pref_shift = 32 - ck.bits;
+                const size_t slots = (size_t)1 << ck.bits;
+                g.prefhash_off = b.reserve(slots);
+                for (size_t i = 0; i < slots; i++) b.w[g.prefhash_off + i] = ck.used[i] ? ck.val[i] : DCB_HASH_EMPTY;
             }
             while (b.w.size() % 4) b.w.push_back(0u);
             g.core_words = (int32_t)b.w.size();
