@@ -7,12 +7,19 @@
 
 #include <vector>
 
+#include <string>
+
 struct dcb_tagset {
-    int n_tags = 0, split = 0, is_v = 0;
-    std::vector<int> tag_len;
-    std::vector<uint32_t> general;  // blob for the general (fallback) kernel
-    std::vector<uint32_t> fast;     // blob for the exact-tag kernel
+    int n_tags = 0, split = 0, is_v = 0, lmin = 0;
+    std::vector<std::string> tags;
+    std::vector<uint32_t> general;  // DcbGene + tags + keyword sets + germline regions (general kernel)
+    std::vector<uint32_t> core;     // DcbGene + tags only (exact-tag kernels)
+    std::vector<uint32_t> index;    // DcbSeedIndex of this gene alone
 };
+
+// Seed index over one gene (other pointer null) or over both genes of a chain (equal lmin).
+bool dcb_build_seed_index(const std::vector<std::string>* gene_v, const std::vector<std::string>* gene_j, int lmin,
+                          std::vector<uint32_t>& out);
 
 #if defined(__GNUC__)
 __attribute__((format(printf, 1, 2)))

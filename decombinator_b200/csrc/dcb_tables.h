@@ -6,10 +6,8 @@
 //   * three keyword sets (full tags, half1 = tag[:split], half2 = tag[split:]), each searchable at
 //     every END position through a suffix-k-mer bitmap + a small open-addressing hash that lists the
 //     distinct keywords ending in that k-mer (longest first = findall() order at equal end);
-//   * a sampled-seed filter for the exact-tag fast path: every occurrence of a full tag of length
-//     >= Lmin contains a q-mer starting at a multiple of stride = Lmin-q+1, so only n/stride
-//     positions are looked up; a seed hit maps (hash) to the set of tag offsets that q-mer occurs
-//     at, and a candidate start is confirmed through a hash of the tags' Lmin-prefix;
+//   * a sampled-seed index for the exact-tag fast path (DcbSeedIndex below): only every stride-th
+//     position of a read is probed;
 //   * per-tag records (packed tag, length, jump, first-tag-with-same-half lengths, the last / first
 //     32 germline bases for the bit-parallel deletion walk) and the 2-bit packed germline regions.
 //
@@ -57,29 +55,37 @@ struct DcbTag {
     uint8_t h1_first_len;        // len(tags[half1 list .index(half1 of this tag)])  (length-guard quirk)
     uint8_t h2_first_len;
     uint8_t edge_ok;             // region_len >= 32
-    uint8_t next_same_prefix;    // another tag with the same lmin-prefix (chain), 0xFF = none
-    uint8_t pad8[3];
+    uint8_t pad8[4];
 };
 
 struct DcbGene {
     int32_t n_tags, split, is_v;
     int32_t tag_off;             // DcbTag[n_tags]
-    DcbKwSet full, half1, half2;
-    // exact-tag fast path
+    DcbKwSet full, half1, half2; // general blob only
     int32_t lmin;                // shortest full tag
-    int32_t q, stride;           // seed length, sampling stride (lmin - q + 1)
-    int32_t seedmap_off;         // 4^q bits
-    // Both lookups are 2-choice cuckoo tables: a key lives in slot h1(key) or h2(key), so a lookup reads exactly
-    // two slots and never probes (no data-dependent loop for the lanes of a warp to diverge in).
-    int32_t seedhash_off;        // 2^bits slots of 2 words: [q-mer key | DCB_HASH_EMPTY, mask of tag offsets it occurs at]
-    uint32_t seed_c1, seed_c2;   // h(key) = (key * c) >> seed_shift
-    int32_t seed_shift;
-    int32_t prefhash_off;        // 2^bits slots: tag id | DCB_HASH_EMPTY, keyed on the folded lmin-prefix of the tag
-    uint32_t pref_c1, pref_c2;
-    int32_t pref_shift;
     int32_t n_words;             // blob size
-    int32_t core_words;          // exact-tag blob: words [0, core_words) exclude the seed bitmap, which comes last
-                                 // (a chain whose V and J share (q, stride) is scanned through ONE union bitmap)
+};
+
+// Seed index of the exact-tag fast path (one per gene, or ONE for both genes of a chain when their seed
+// geometry agrees).  Every occurrence of a full tag (length >= lmin) contains a q-mer that starts at a multiple
+// of stride = lmin-q+1 at tag offset o <= lmin-q, so only every stride-th position is probed:
+//   1. seed bitmap (4^q bits): is the q-mer at the sampled position p part of any tag at an offset <= lmin-q?
+//   2. on a hit, the unknown offset o falls in class c = o / span (two classes); the k-mer at [p - c*span, +k)
+//      then lies inside the tag for every o of that class, and a 2-choice cuckoo table (two slot reads, no
+//      probing loop) maps (c, k-mer) to the short list of (gene, tag, offset) candidates -- usually one;
+//   3. each candidate is confirmed by comparing the whole tag with the read window.
+struct DcbSeedIndex {
+    int32_t q, stride;
+    int32_t max_off;             // lmin - q: largest indexed tag offset
+    int32_t k, span;             // class key length (<= 15 bases) and offsets per class
+    int32_t wlead;               // the verification window starts at p - wlead (max_off + 1)
+    int32_t ck_off;              // 2^bits slots of 2 words: [class << 31 | key  (DCB_HASH_EMPTY if free), start << 4 | count]
+    uint32_t c1, c2;             // h(x) = (x * c) >> shift
+    int32_t shift;
+    int32_t pairs_off;           // 16-bit entries: gene << 15 | tag << 5 | offset   (gene 0 = V, 1 = J)
+    int32_t seedmap_off;         // the bitmap comes last
+    int32_t n_words;
+    int32_t pad;
 };
 
 // Seed bitmap addressing: the LOW 2q-5 bits of a q-mer key select the word, the high 5 bits the bit, so the
@@ -96,10 +102,6 @@ struct DcbGene {
 DCB_HD uint32_t dcb_hash32(uint32_t k) {
     k *= 0x9E3779B1u;
     return k ^ (k >> 15);
-}
-DCB_HD uint32_t dcb_fold64(uint32_t lo, uint32_t hi) {
-    uint32_t k = lo * 0x9E3779B1u + hi * 0x85EBCA77u;
-    return k ^ (k >> 13);
 }
 
 #endif

@@ -389,43 +389,57 @@ DCB_HD uint32_t revcomp_word(const ReadView& r, int ow) {
 // and the first one.
 struct FullHit { int count, tag, pos; };
 
-// Record one confirmed full-tag occurrence (the same occurrence can be reached through two seeds).
+// Record one confirmed full-tag occurrence.
 DCB_HD void fullhit_add(FullHit& fh, int tag, int pos) {
     if (fh.count && fh.tag == tag && fh.pos == pos) return;
     if (fh.count == 0) { fh.tag = tag; fh.pos = pos; }
     if (fh.count < 2) fh.count++;
 }
 
-// All tags whose lmin-prefix chain starts at `id` against the read window (lo, hi) at position P.
-DCB_HD void fast_try_tags(const ReadView& r, const uint32_t* blob, const DcbGene& g, uint32_t id, int P, uint32_t lo,
-                          uint32_t hi, FullHit& fh) {
-    while (id < 0xFFu) {
-        const DcbTag& t = gene_tag(blob, g, (int)id);
-        const int L = t.len;
-        const uint32_t mlo = mask2(L), mhi = L > 16 ? mask2(L - 16) : 0u;
-        if (P + L <= r.n && !(((lo ^ t.bits_lo) & mlo) | ((hi ^ t.bits_hi) & mhi))) fullhit_add(fh, (int)id, P);
-        id = t.next_same_prefix;
-    }
+// 64-bit window helpers (two 32-bit halves: the device has no native 64-bit shifter)
+DCB_HD uint32_t win_lo_shr(uint32_t lo, uint32_t hi, int bits) {  // low word of (hi:lo) >> bits, bits in [0, 63]
+    return bits >= 32 ? (hi >> (bits - 32)) : DCB_FUNNEL_R(lo, hi, bits);
+}
+DCB_HD uint32_t win_hi_shr(uint32_t hi, int bits) {               // high word of (hi:lo) >> bits
+    return bits >= 32 ? 0u : (hi >> bits);
 }
 
-// Confirm the candidates behind one seed hit at sampled position p (key = the q-mer there).
-DCB_HD void fast_verify_seed(const ReadView& r, const uint32_t* blob, const DcbGene& g, int p, uint32_t key,
-                             FullHit& fh) {
-    const uint32_t* sh = blob + g.seedhash_off;
-    const uint32_t s1 = (key * g.seed_c1) >> g.seed_shift, s2 = (key * g.seed_c2) >> g.seed_shift;
-    uint32_t offs = (sh[2 * s1] == key ? sh[2 * s1 + 1] : 0u) | (sh[2 * s2] == key ? sh[2 * s2 + 1] : 0u);
-    while (offs) {
-        const int o = DCB_FFS(offs) - 1;
-        offs &= offs - 1;
-        const int P = p - o;
-        if (P < 0 || P + g.lmin > r.n) continue;
-        uint32_t lo, hi;
-        rd_win32(r, P, lo, hi);
-        const uint32_t f = dcb_fold64(lo & mask2(g.lmin), g.lmin > 16 ? (hi & mask2(g.lmin - 16)) : 0u);
-        const uint32_t id1 = blob[g.prefhash_off + ((f * g.pref_c1) >> g.pref_shift)];
-        const uint32_t id2 = blob[g.prefhash_off + ((f * g.pref_c2) >> g.pref_shift)];
-        fast_try_tags(r, blob, g, id1, P, lo, hi, fh);
-        if (id2 != id1) fast_try_tags(r, blob, g, id2, P, lo, hi, fh);
+// Confirm the candidates behind one seed hit at sampled position p: two cuckoo lookups (one per offset class),
+// then a whole-tag comparison per listed (gene, tag, offset).  vcore / jcore may each be null when the index
+// only covers the other gene.
+DCB_HD void fast_verify_hit(const ReadView& r, const uint32_t* ib, int p, const uint32_t* vcore, const uint32_t* jcore,
+                            FullHit& vh, FullHit& jh) {
+    const DcbSeedIndex& ix = *reinterpret_cast<const DcbSeedIndex*>(ib);
+    uint32_t wlo, whi;                       // 32 bases starting at p - wlead
+    rd_win32(r, p - ix.wlead, wlo, whi);
+    const uint32_t kmask = mask2(ix.k);
+    const uint16_t* pairs = reinterpret_cast<const uint16_t*>(ib + ix.pairs_off);
+    for (int c = 0; c < 2; c++) {
+        const uint32_t key = ((uint32_t)c << 31) | (win_lo_shr(wlo, whi, 2 * (ix.wlead - c * ix.span)) & kmask);
+        const uint32_t s1 = (key * ix.c1) >> ix.shift, s2 = (key * ix.c2) >> ix.shift;
+        const uint32_t k1 = ib[ix.ck_off + 2 * s1], v1 = ib[ix.ck_off + 2 * s1 + 1];
+        const uint32_t k2 = ib[ix.ck_off + 2 * s2], v2 = ib[ix.ck_off + 2 * s2 + 1];
+        const uint32_t val = k1 == key ? v1 : (k2 == key ? v2 : 0u);
+        const int n_cand = (int)(val & 15u), start = (int)(val >> 4);
+        for (int i = 0; i < n_cand; i++) {
+            const uint32_t e = pairs[start + i];
+            const int o = (int)(e & 31u), tag = (int)((e >> 5) & 0x3FFu), is_j = (int)(e >> 15);
+            const uint32_t* core = is_j ? jcore : vcore;
+            const DcbTag& t = gene_tag(core, *reinterpret_cast<const DcbGene*>(core), tag);
+            const int P = p - o, L = t.len;
+            if (P < 0 || P + L > r.n) continue;
+            uint32_t lo, hi;
+            if (L - o <= 32 - ix.wlead) {    // the tag lies inside the window already in registers
+                const int sh = 2 * (ix.wlead - o);
+                lo = win_lo_shr(wlo, whi, sh);
+                hi = win_hi_shr(whi, sh);
+            } else {
+                rd_win32(r, P, lo, hi);
+            }
+            const uint32_t mlo = mask2(L), mhi = L > 16 ? mask2(L - 16) : 0u;
+            if (((lo ^ t.bits_lo) & mlo) | ((hi ^ t.bits_hi) & mhi)) continue;
+            fullhit_add(is_j ? jh : vh, tag, P);
+        }
     }
 }
 
@@ -483,27 +497,28 @@ DCB_HD int fast_j_deletions(const ReadView& r, const DcbTag& t, int temp_start_j
     return 1;
 }
 
-// Sampled-seed scan of one gene over a read held in the view: probe the seed bitmap at every
-// multiple of `stride`, 32 probes at a time into a hit mask, then confirm the (rare) hits in a
-// second loop so the lanes of a warp stay converged during the probes.
-DCB_HD void fast_scan(const ReadView& r, const uint32_t* blob, const DcbGene& g, FullHit& fh) {
-    fh.count = 0; fh.tag = 0; fh.pos = 0;
-    const uint32_t qmask = mask2(g.q);
-    const int last = r.n - g.q;  // last start position of a whole q-mer
-    for (int base = 0; base <= last; base += 32 * g.stride) {
+// Sampled-seed search through one index over a read held in the view: probe the seed bitmap at every
+// multiple of `stride`, 32 probes at a time into a hit mask, then confirm the (rare) hits in a second loop
+// so the lanes of a warp stay converged during the probes.  (The kernels have a register-resident unrolled
+// specialisation of the probing for the common slot sizes; this is the generic form.)
+DCB_HD void fast_find(const ReadView& r, const uint32_t* ib, const uint32_t* vcore, const uint32_t* jcore,
+                      FullHit& vh, FullHit& jh) {
+    const DcbSeedIndex& ix = *reinterpret_cast<const DcbSeedIndex*>(ib);
+    const uint32_t qmask = mask2(ix.q);
+    const int last = r.n - ix.q;  // last start position of a whole q-mer
+    for (int base = 0; base <= last; base += 32 * ix.stride) {
         uint32_t hits = 0;
         for (int i = 0; i < 32; i++) {
-            const int p = base + i * g.stride;
+            const int p = base + i * ix.stride;
             if (p > last) break;
             const uint32_t key = rd_win16(r, p) & qmask;
-            hits |= ((blob[g.seedmap_off + DCB_SEEDMAP_WORD(key, g.q)] >> DCB_SEEDMAP_BIT(key, g.q)) & 1u) << i;
+            hits |= ((ib[ix.seedmap_off + DCB_SEEDMAP_WORD(key, ix.q)] >> DCB_SEEDMAP_BIT(key, ix.q)) & 1u) << i;
         }
         while (hits) {
             const int i = DCB_FFS(hits) - 1;
             hits &= hits - 1;
-            const int p = base + i * g.stride;
-            fast_verify_seed(r, blob, g, p, rd_win16(r, p) & qmask, fh);
-            if (fh.count >= 2) return;
+            fast_verify_hit(r, ib, base + i * ix.stride, vcore, jcore, vh, jh);
+            if (vcore && vh.count >= 2) return;
         }
     }
 }
@@ -569,17 +584,22 @@ DCB_HD uint32_t exc_lower_bound(const ExcList& ex, uint32_t key) {
     return lo;
 }
 
-// Exact-tag kernel body for one read whose words are already in r.w.  Returns FAST_DONE / FAST_DEFER.
-DCB_HD int dcr_exact_read(const ReadView& r, bool flagged, const uint32_t* vblob, const uint32_t* jblob,
-                          const DcrParams& prm, int both_frames, dcb_result& out, dcb_cnt_t* C) {
+// Exact-tag kernel body for one read whose words are already in r.w.  vidx is the V seed index -- or the
+// union index of both genes when jidx is null.  Returns FAST_DONE / FAST_DEFER.
+DCB_HD int dcr_exact_read(const ReadView& r, bool flagged, const uint32_t* vcore, const uint32_t* jcore,
+                          const uint32_t* vidx, const uint32_t* jidx, const DcrParams& prm, int both_frames,
+                          dcb_result& out, dcb_cnt_t* C) {
     if (flagged) return FAST_DEFER;
-    const DcbGene& gv = *reinterpret_cast<const DcbGene*>(vblob);
-    const DcbGene& gj = *reinterpret_cast<const DcbGene*>(jblob);
     FullHit vh, jh;
-    fast_scan(r, vblob, gv, vh);
+    vh.count = 0; vh.tag = 0; vh.pos = 0;
     jh.count = 0; jh.tag = 0; jh.pos = 0;
-    if (vh.count == 1) fast_scan(r, jblob, gj, jh);
-    return dcr_fast_from_hits(r, vblob, jblob, vh, jh, prm, both_frames, out, C);
+    if (!jidx) {
+        fast_find(r, vidx, vcore, jcore, vh, jh);
+    } else {
+        fast_find(r, vidx, vcore, nullptr, vh, jh);
+        if (vh.count == 1) fast_find(r, jidx, nullptr, jcore, vh, jh);
+    }
+    return dcr_fast_from_hits(r, vcore, jcore, vh, jh, prm, both_frames, out, C);
 }
 
 // General kernel body for one read: r has w/stride/n/nw set; inv0, rd1, inv1 are this thread's scratch

@@ -107,21 +107,34 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* a, uint32_t 
 static constexpr int kExactThreads = 256;   // upper bounds; long reads launch narrower blocks (shared memory)
 static constexpr int kGeneralThreads = 128;
 
-// Shared-memory carve-up common to the kernels: [V blob][J blob][extra][per-thread columns][counters][mbarrier]
+// Shared-memory carve-up common to the kernels: [table 0..3][per-thread columns][counters][mbarrier]
+struct Tables4 {
+    const uint32_t* g[4];   // global pointers (null = absent)
+    int words[4];
+};
 struct SmemLayout {
-    uint32_t *vblob, *jblob, *extra, *cols;
+    uint32_t* t[4];
+    uint32_t* cols;
     dcb_cnt_t* cnt;
     uint64_t* bar;
 };
-__device__ __forceinline__ SmemLayout carve(uint32_t* smem, int vwords, int jwords, int extra_words, size_t col_words) {
+__device__ __forceinline__ SmemLayout carve(uint32_t* smem, const Tables4& tb, size_t col_words) {
     SmemLayout L;
-    L.vblob = smem;
-    L.jblob = L.vblob + vwords;
-    L.extra = L.jblob + jwords;
-    L.cols = L.extra + extra_words;
+    uint32_t* p = smem;
+    for (int i = 0; i < 4; i++) { L.t[i] = tb.words[i] ? p : nullptr; p += tb.words[i]; }
+    L.cols = p;
     L.cnt = L.cols + col_words;
     L.bar = reinterpret_cast<uint64_t*>(L.cnt + ((DCB_NCOUNTERS + 3) & ~3));
     return L;
+}
+// TMA-stage the tables, zero the block counters, wait.
+__device__ __forceinline__ void stage_tables(const SmemLayout& L, const Tables4& tb) {
+    tma_stage_begin(L.bar, (uint32_t)(tb.words[0] + tb.words[1] + tb.words[2] + tb.words[3]) * 4u);
+    for (int i = 0; i < 4; i++)
+        if (tb.words[i]) tma_stage_copy(L.bar, L.t[i], tb.g[i], (uint32_t)tb.words[i] * 4u);
+    if (threadIdx.x < DCB_NCOUNTERS) L.cnt[threadIdx.x] = 0;
+    tma_stage_wait(L.bar);
+    __syncthreads();
 }
 
 __device__ __forceinline__ void flush_counters(const dcb_cnt_t* s_cnt, unsigned long long* counters) {
@@ -143,24 +156,18 @@ __device__ __forceinline__ void defer_reads(bool defer, uint32_t ri, uint32_t* q
 }
 
 // ------------------------------------------------------------------------------------------------
-// exact-tag kernel, generic form: any slot size / seed geometry (reads are walked from shared memory)
+// exact-tag kernel, generic form: any slot size / seed geometry (reads are walked from shared memory).
+// Tables: 0 = V tag records, 1 = J tag records, 2 = V seed index (or the union index), 3 = J seed index.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kExactThreads)
-dcb_exact_kernel(BatchDev b, const uint32_t* __restrict__ vblob_g, const uint32_t* __restrict__ jblob_g,
-                 int vwords, int jwords, DcrParams prm, int both_frames, dcb_result* __restrict__ results,
+dcb_exact_kernel(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_result* __restrict__ results,
                  unsigned long long* __restrict__ counters, uint32_t* __restrict__ queue,
                  uint32_t* __restrict__ queue_count) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int T = blockDim.x;
-    SmemLayout L = carve(smem, vwords, jwords, 0, (size_t)b.slot_words * T);
+    SmemLayout L = carve(smem, tb, (size_t)b.slot_words * T);
     uint32_t* s_rd = L.cols;  // [slot_words][T]
-
-    tma_stage_begin(L.bar, (uint32_t)(vwords + jwords) * 4u);
-    tma_stage_copy(L.bar, L.vblob, vblob_g, (uint32_t)vwords * 4u);
-    tma_stage_copy(L.bar, L.jblob, jblob_g, (uint32_t)jwords * 4u);
-    if (threadIdx.x < DCB_NCOUNTERS) L.cnt[threadIdx.x] = 0;
-    tma_stage_wait(L.bar);
-    __syncthreads();
+    stage_tables(L, tb);
 
     const int tid = threadIdx.x;
     const uint32_t n_tiles = (b.n_reads + T - 1) / T;
@@ -185,7 +192,7 @@ dcb_exact_kernel(BatchDev b, const uint32_t* __restrict__ vblob_g, const uint32_
             r.n = b.uniform_len ? (int)b.uniform_len : (int)__ldg(b.lens + ri);
             r.nw = (int)b.slot_words;
             r.exc_pos = nullptr; r.exc_kind = nullptr; r.e0 = r.e1 = 0; r.mirror = 0;
-            action = dcr_exact_read(r, flagged, L.vblob, L.jblob, prm, both_frames, out, L.cnt);
+            action = dcr_exact_read(r, flagged, L.t[0], L.t[1], L.t[2], L.t[3], prm, both_frames, out, L.cnt);
         }
         defer_reads(live && action == FAST_DEFER, ri, queue, queue_count);
         if (live && action == FAST_DONE) store_result(results + ri, out);
@@ -194,12 +201,11 @@ dcb_exact_kernel(BatchDev b, const uint32_t* __restrict__ vblob_g, const uint32_
 }
 
 // ------------------------------------------------------------------------------------------------
-// exact-tag kernel, specialised: the read slot (NW words) sits in registers, every sampled seed position
-// is a compile-time constant (static funnel shifts, no index arithmetic), and when V and J share the
-// seed geometry ONE union bitmap is probed for both genes.
+// exact-tag kernel, specialised: the read slot (NW words) sits in registers and every sampled seed position
+// is a compile-time constant (static funnel shifts, no index arithmetic).
 //   NW      words per read slot (16 => reads up to 256 nt)
 //   QV, SV  V seed length / stride;  QJ, SJ  the same for J
-//   UNION   V and J are scanned together through one bitmap (requires QV == QJ && SV == SJ)
+//   UNION   V and J share the seed geometry and are found together through ONE index (table 2)
 // ------------------------------------------------------------------------------------------------
 template <int NW, int Q, int S>
 struct SeedScan {
@@ -232,30 +238,30 @@ struct SeedScan {
     }
 };
 
+__device__ __forceinline__ int pop_hit(uint32_t& lo, uint32_t& hi) {
+    int i;
+    if (lo) { i = __ffs(lo) - 1; lo &= lo - 1; } else { i = 32 + __ffs(hi) - 1; hi &= hi - 1; }
+    return i;
+}
+
 template <int NW, int QV, int SV, int QJ, int SJ, bool UNION>
 __global__ void __launch_bounds__(kExactThreads)
-dcb_exact_kernel_spec(BatchDev b, const uint32_t* __restrict__ vblob_g, const uint32_t* __restrict__ jblob_g,
-                      const uint32_t* __restrict__ union_g, int vwords, int jwords, int uwords, DcrParams prm,
-                      int both_frames, dcb_result* __restrict__ results, unsigned long long* __restrict__ counters,
-                      uint32_t* __restrict__ queue, uint32_t* __restrict__ queue_count) {
+dcb_exact_kernel_spec(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_result* __restrict__ results,
+                      unsigned long long* __restrict__ counters, uint32_t* __restrict__ queue,
+                      uint32_t* __restrict__ queue_count) {
     static_assert(!UNION || (QV == QJ && SV == SJ), "union scan needs one seed geometry");
     extern __shared__ __align__(16) uint32_t smem[];
     constexpr int T = kExactThreads;
-    SmemLayout L = carve(smem, vwords, jwords, uwords, (size_t)NW * T);
+    SmemLayout L = carve(smem, tb, (size_t)NW * T);
     uint32_t* s_rd = L.cols;
+    stage_tables(L, tb);
 
-    tma_stage_begin(L.bar, (uint32_t)(vwords + jwords + uwords) * 4u);
-    tma_stage_copy(L.bar, L.vblob, vblob_g, (uint32_t)vwords * 4u);
-    tma_stage_copy(L.bar, L.jblob, jblob_g, (uint32_t)jwords * 4u);
-    if (uwords) tma_stage_copy(L.bar, L.extra, union_g, (uint32_t)uwords * 4u);
-    if (threadIdx.x < DCB_NCOUNTERS) L.cnt[threadIdx.x] = 0;
-    tma_stage_wait(L.bar);
-    __syncthreads();
-
-    const DcbGene& gv = *reinterpret_cast<const DcbGene*>(L.vblob);
-    const DcbGene& gj = *reinterpret_cast<const DcbGene*>(L.jblob);
-    const uint32_t* vmap = UNION ? L.extra : L.vblob + gv.seedmap_off;
-    const uint32_t* jmap = UNION ? L.extra : L.jblob + gj.seedmap_off;
+    const uint32_t* vcore = L.t[0];
+    const uint32_t* jcore = L.t[1];
+    const uint32_t* vidx = L.t[2];
+    const uint32_t* jidx = UNION ? L.t[2] : L.t[3];
+    const uint32_t* vmap = vidx + reinterpret_cast<const DcbSeedIndex*>(vidx)->seedmap_off;
+    const uint32_t* jmap = jidx + reinterpret_cast<const DcbSeedIndex*>(jidx)->seedmap_off;
     const int tid = threadIdx.x;
     const uint32_t n_tiles = (b.n_reads + T - 1) / T;
 
@@ -290,27 +296,15 @@ dcb_exact_kernel_spec(BatchDev b, const uint32_t* __restrict__ vblob_g, const ui
                 uint32_t lo, hi;
                 SeedScan<NW, QV, SV>::run(w, vmap, lo, hi);
                 SeedScan<NW, QV, SV>::clip(r.n, lo, hi);
-                constexpr uint32_t VMASK = (1u << (2 * QV)) - 1u;
-                while ((lo | hi) && vh.count < 2) {
-                    int i;
-                    if (lo) { i = __ffs(lo) - 1; lo &= lo - 1; } else { i = 32 + __ffs(hi) - 1; hi &= hi - 1; }
-                    const int p = i * SV;
-                    const uint32_t key = rd_win16(r, p) & VMASK;
-                    fast_verify_seed(r, L.vblob, gv, p, key, vh);
-                    if (UNION) fast_verify_seed(r, L.jblob, gj, p, key, jh);
-                }
+                while ((lo | hi) && vh.count < 2)
+                    fast_verify_hit(r, vidx, pop_hit(lo, hi) * SV, vcore, UNION ? jcore : nullptr, vh, jh);
                 if (!UNION && vh.count == 1) {
                     SeedScan<NW, QJ, SJ>::run(w, jmap, lo, hi);
                     SeedScan<NW, QJ, SJ>::clip(r.n, lo, hi);
-                    constexpr uint32_t JMASK = (1u << (2 * QJ)) - 1u;
-                    while ((lo | hi) && jh.count < 2) {
-                        int i;
-                        if (lo) { i = __ffs(lo) - 1; lo &= lo - 1; } else { i = 32 + __ffs(hi) - 1; hi &= hi - 1; }
-                        const int p = i * SJ;
-                        fast_verify_seed(r, L.jblob, gj, p, rd_win16(r, p) & JMASK, jh);
-                    }
+                    while ((lo | hi) && jh.count < 2)
+                        fast_verify_hit(r, jidx, pop_hit(lo, hi) * SJ, nullptr, jcore, vh, jh);
                 }
-                action = dcr_fast_from_hits(r, L.vblob, L.jblob, vh, jh, prm, both_frames, out, L.cnt);
+                action = dcr_fast_from_hits(r, vcore, jcore, vh, jh, prm, both_frames, out, L.cnt);
             }
         }
         defer_reads(live && action == FAST_DEFER, ri, queue, queue_count);
@@ -323,25 +317,20 @@ dcb_exact_kernel_spec(BatchDev b, const uint32_t* __restrict__ vblob_g, const ui
 // general kernel (queued reads, or every read when queue == nullptr)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kGeneralThreads)
-dcb_general_kernel(BatchDev b, const uint32_t* __restrict__ vblob_g, const uint32_t* __restrict__ jblob_g,
-                   int vwords, int jwords, DcrParams prm, int both_frames, dcb_result* __restrict__ results,
+dcb_general_kernel(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_result* __restrict__ results,
                    unsigned long long* __restrict__ counters, const uint32_t* __restrict__ queue,
                    const uint32_t* __restrict__ queue_count) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int T = blockDim.x;
     const int nw = (int)b.slot_words, nwi = (nw + 1) / 2;
-    SmemLayout L = carve(smem, vwords, jwords, 0, (size_t)(nw + nwi) * T * (both_frames ? 2 : 1));
+    SmemLayout L = carve(smem, tb, (size_t)(nw + nwi) * T * (both_frames ? 2 : 1));
     uint32_t* s_rd = L.cols;                      // [nw][T]
     uint32_t* s_inv = s_rd + (size_t)nw * T;      // [nwi][T]
     uint32_t* s_rd1 = s_inv + (size_t)nwi * T;    // second frame (only when both_frames)
     uint32_t* s_inv1 = s_rd1 + (size_t)nw * T;
-
-    tma_stage_begin(L.bar, (uint32_t)(vwords + jwords) * 4u);
-    tma_stage_copy(L.bar, L.vblob, vblob_g, (uint32_t)vwords * 4u);
-    tma_stage_copy(L.bar, L.jblob, jblob_g, (uint32_t)jwords * 4u);
-    if (threadIdx.x < DCB_NCOUNTERS) L.cnt[threadIdx.x] = 0;
-    tma_stage_wait(L.bar);
-    __syncthreads();
+    stage_tables(L, tb);
+    const uint32_t* vblob = L.t[0];
+    const uint32_t* jblob = L.t[1];
 
     const int tid = threadIdx.x;
     const uint32_t n_items = queue ? *queue_count : b.n_reads;
@@ -367,8 +356,8 @@ dcb_general_kernel(BatchDev b, const uint32_t* __restrict__ vblob_g, const uint3
         ex.read = b.exc_read; ex.pos = b.exc_pos; ex.kind = b.exc_kind; ex.n = b.n_exc;
         dcb_result out;
         *reinterpret_cast<uint4*>(&out) = make_uint4(0, 0, 0, 0);
-        dcr_general_read(r, ri, flagged, ex, s_inv + tid, s_rd1 + tid, s_inv1 + tid, L.vblob, L.jblob, prm, both_frames,
-                         out, L.cnt);
+        dcr_general_read(r, ri, flagged, ex, s_inv + tid, s_rd1 + tid, s_inv1 + tid, vblob, jblob, prm, both_frames, out,
+                         L.cnt);
         store_result(results + ri, out);
     }
     flush_counters(L.cnt, counters);
@@ -409,8 +398,10 @@ struct dcb_ctx {
     int n_sms = 0;
     dcb_params params{};
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    uint32_t *d_vgen = nullptr, *d_jgen = nullptr, *d_vfast = nullptr, *d_jfast = nullptr;
-    int vgen_words = 0, jgen_words = 0, vfast_words = 0, jfast_words = 0;
+    // device copies of the table blobs: general (V, J), tag records (V, J), seed indexes (V, J, union of both)
+    uint32_t *d_vgen = nullptr, *d_jgen = nullptr, *d_vcore = nullptr, *d_jcore = nullptr;
+    uint32_t *d_vidx = nullptr, *d_jidx = nullptr, *d_uidx = nullptr;
+    int vgen_words = 0, jgen_words = 0, vcore_words = 0, jcore_words = 0, vidx_words = 0, jidx_words = 0, uidx_words = 0;
     DevBuf words, lens, flags, exc_read, exc_pos, exc_kind, results, queue;
     uint32_t* d_queue_count = nullptr;
     unsigned long long* d_counters = nullptr;
@@ -424,14 +415,12 @@ struct dcb_ctx {
     int exact_grid = 0, general_grid = 0, exact_threads = kExactThreads, general_threads = kGeneralThreads;
     size_t exact_smem = 0, general_smem = 0;
     // seed geometry of the two genes and the union bitmap (built when they agree)
-    int qv = 0, sv = 0, qj = 0, sj = 0, vcore_words = 0, jcore_words = 0, union_words = 0;
-    uint32_t* d_union = nullptr;
+    int qv = 0, sv = 0, qj = 0, sj = 0;
     void* spec_fn = nullptr;   // specialised exact kernel picked for the resident batch, or null
     bool spec_union = false;
 };
 
-typedef void (*exact_spec_fn)(BatchDev, const uint32_t*, const uint32_t*, const uint32_t*, int, int, int, DcrParams, int,
-                              dcb_result*, unsigned long long*, uint32_t*, uint32_t*);
+typedef void (*exact_spec_fn)(BatchDev, Tables4, DcrParams, int, dcb_result*, unsigned long long*, uint32_t*, uint32_t*);
 
 // Specialisations compiled in: V seeds (q=9, stride 12) -- every shipped V tag set has 20-nt minimum tags --
 // with J either sharing that geometry (20-nt J tags: one union bitmap) or using (q=8, stride 5) (12-nt J tags).
@@ -511,18 +500,17 @@ dcb_ctx* dcb_ctx_create(int device, const dcb_tagset* v, const dcb_tagset* j, co
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate");
     c->stream = c->own_stream;
     if (upload_blob(v->general, &c->d_vgen, &c->vgen_words) || upload_blob(j->general, &c->d_jgen, &c->jgen_words) ||
-        upload_blob(v->fast, &c->d_vfast, &c->vfast_words) || upload_blob(j->fast, &c->d_jfast, &c->jfast_words))
+        upload_blob(v->core, &c->d_vcore, &c->vcore_words) || upload_blob(j->core, &c->d_jcore, &c->jcore_words) ||
+        upload_blob(v->index, &c->d_vidx, &c->vidx_words) || upload_blob(j->index, &c->d_jidx, &c->jidx_words))
         return fail(nullptr);
     {
-        const DcbGene& gv = *reinterpret_cast<const DcbGene*>(v->fast.data());
-        const DcbGene& gj = *reinterpret_cast<const DcbGene*>(j->fast.data());
-        c->qv = gv.q; c->sv = gv.stride; c->qj = gj.q; c->sj = gj.stride;
-        c->vcore_words = gv.core_words; c->jcore_words = gj.core_words;
-        if (gv.q == gj.q && gv.stride == gj.stride) {
-            const size_t words = (size_t)gv.n_words - gv.seedmap_off;
-            std::vector<uint32_t> u(words);
-            for (size_t i = 0; i < words; i++) u[i] = v->fast[gv.seedmap_off + i] | j->fast[gj.seedmap_off + i];
-            if (upload_blob(u, &c->d_union, &c->union_words)) return fail(nullptr);
+        const DcbSeedIndex& iv = *reinterpret_cast<const DcbSeedIndex*>(v->index.data());
+        const DcbSeedIndex& ij = *reinterpret_cast<const DcbSeedIndex*>(j->index.data());
+        c->qv = iv.q; c->sv = iv.stride; c->qj = ij.q; c->sj = ij.stride;
+        if (v->lmin == j->lmin) {  // same seed geometry: one index (and one bitmap) finds both genes
+            std::vector<uint32_t> u;
+            if (!dcb_build_seed_index(&v->tags, &j->tags, v->lmin, u)) { dcb_set_error("dcb_ctx_create: union seed index failed"); return fail(nullptr); }
+            if (upload_blob(u, &c->d_uidx, &c->uidx_words)) return fail(nullptr);
         }
     }
     if (cudaMalloc((void**)&c->d_queue_count, 16) != cudaSuccess) return fail("cudaMalloc");
@@ -535,8 +523,9 @@ void dcb_ctx_destroy(dcb_ctx* c) {
     cudaSetDevice(c->device);
     timing_collect(c);
     if (c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
-    cudaFree(c->d_vgen); cudaFree(c->d_jgen); cudaFree(c->d_vfast); cudaFree(c->d_jfast);
-    cudaFree(c->d_queue_count); cudaFree(c->d_counters); cudaFree(c->d_union);
+    cudaFree(c->d_vgen); cudaFree(c->d_jgen); cudaFree(c->d_vcore); cudaFree(c->d_jcore);
+    cudaFree(c->d_vidx); cudaFree(c->d_jidx); cudaFree(c->d_uidx);
+    cudaFree(c->d_queue_count); cudaFree(c->d_counters);
     c->words.release(); c->lens.release(); c->flags.release(); c->exc_read.release(); c->exc_pos.release();
     c->exc_kind.release(); c->results.release(); c->queue.release();
     delete c;
@@ -581,15 +570,17 @@ int dcb_upload(dcb_ctx* c, const dcb_packed* P) {
     const size_t tail = (((DCB_NCOUNTERS + 3) & ~3) + 4) * 4;
     const size_t kMaxSmem = 227 * 1024;
     const size_t nwi = (sw + 1) / 2;
+    // exact-tag tables: tag records of both genes + either the union index or the two per-gene indexes
+    const bool have_union = c->d_uidx != nullptr;
+    const size_t tbl_e = (size_t)c->vcore_words + c->jcore_words + (have_union ? (size_t)c->uidx_words : (size_t)c->vidx_words + c->jidx_words);
     bool is_union = false;
     exact_spec_fn spec = c->params.force_general ? nullptr : pick_spec((int)sw, c->qv, c->sv, c->qj, c->sj, &is_union);
-    c->spec_fn = (void*)spec; c->spec_union = is_union;
+    if (spec && is_union != have_union) spec = nullptr;
+    c->spec_fn = (void*)spec; c->spec_union = have_union;
     int occ_e = 0, occ_g = 0;
     if (spec) {
-        const size_t tbl = is_union ? (size_t)c->vcore_words + c->jcore_words + c->union_words
-                                    : (size_t)c->vfast_words + c->jfast_words;
         c->exact_threads = kExactThreads;
-        c->exact_smem = (tbl + sw * kExactThreads) * 4 + tail;
+        c->exact_smem = (tbl_e + sw * kExactThreads) * 4 + tail;
         if (c->exact_smem > kMaxSmem) { spec = nullptr; c->spec_fn = nullptr; }
     }
     if (spec) {
@@ -598,7 +589,7 @@ int dcb_upload(dcb_ctx* c, const dcb_packed* P) {
     } else {
         int T = kExactThreads;
         for (; T >= 32; T >>= 1) {
-            c->exact_smem = ((size_t)c->vfast_words + c->jfast_words + sw * T) * 4 + tail;
+            c->exact_smem = (tbl_e + sw * T) * 4 + tail;
             if (c->exact_smem <= kMaxSmem) break;
         }
         if (T < 32) { dcb_set_error("dcb_upload: tag tables + %u-nt reads do not fit in shared memory", P->max_len); return DCB_EUNSUPPORTED; }
@@ -639,23 +630,29 @@ int dcb_run_resident(dcb_ctx* c) {
     int rc;
     if (!c->params.force_general) {
         if ((rc = timing_begin(c, 0))) return rc;
+        Tables4 te;
+        te.g[0] = c->d_vcore; te.words[0] = c->vcore_words;
+        te.g[1] = c->d_jcore; te.words[1] = c->jcore_words;
+        if (c->spec_union) { te.g[2] = c->d_uidx; te.words[2] = c->uidx_words; te.g[3] = nullptr; te.words[3] = 0; }
+        else { te.g[2] = c->d_vidx; te.words[2] = c->vidx_words; te.g[3] = c->d_jidx; te.words[3] = c->jidx_words; }
         if (c->spec_fn) {
-            const bool u = c->spec_union;
             ((exact_spec_fn)c->spec_fn)<<<c->exact_grid, c->exact_threads, c->exact_smem, s>>>(
-                b, c->d_vfast, c->d_jfast, u ? c->d_union : nullptr, u ? c->vcore_words : c->vfast_words,
-                u ? c->jcore_words : c->jfast_words, u ? c->union_words : 0, prm, c->params.both_frames,
-                (dcb_result*)c->results.p, c->d_counters, (uint32_t*)c->queue.p, c->d_queue_count);
+                b, te, prm, c->params.both_frames, (dcb_result*)c->results.p, c->d_counters, (uint32_t*)c->queue.p,
+                c->d_queue_count);
         } else {
             dcb_exact_kernel<<<c->exact_grid, c->exact_threads, c->exact_smem, s>>>(
-                b, c->d_vfast, c->d_jfast, c->vfast_words, c->jfast_words, prm, c->params.both_frames,
-                (dcb_result*)c->results.p, c->d_counters, (uint32_t*)c->queue.p, c->d_queue_count);
+                b, te, prm, c->params.both_frames, (dcb_result*)c->results.p, c->d_counters, (uint32_t*)c->queue.p,
+                c->d_queue_count);
         }
         CUDA_TRY(cudaGetLastError());
         if ((rc = timing_end(c))) return rc;
     }
     if ((rc = timing_begin(c, 1))) return rc;
+    Tables4 tg;
+    tg.g[0] = c->d_vgen; tg.words[0] = c->vgen_words; tg.g[1] = c->d_jgen; tg.words[1] = c->jgen_words;
+    tg.g[2] = tg.g[3] = nullptr; tg.words[2] = tg.words[3] = 0;
     dcb_general_kernel<<<c->general_grid, c->general_threads, c->general_smem, s>>>(
-        b, c->d_vgen, c->d_jgen, c->vgen_words, c->jgen_words, prm, c->params.both_frames, (dcb_result*)c->results.p,
+        b, tg, prm, c->params.both_frames, (dcb_result*)c->results.p,
         c->d_counters, c->params.force_general ? nullptr : (const uint32_t*)c->queue.p, c->d_queue_count);
     CUDA_TRY(cudaGetLastError());
     if ((rc = timing_end(c))) return rc;

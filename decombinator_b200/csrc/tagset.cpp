@@ -37,10 +37,20 @@ uint32_t pow2_at_least(uint32_t x) {
     return p;
 }
 
-// 2-choice cuckoo table: returns false when the insertion walk fails (caller retries with new constants / size)
+struct Blob {
+    std::vector<uint32_t> w;
+    int32_t reserve(size_t n_words) {
+        int32_t off = (int32_t)w.size();
+        w.resize(w.size() + n_words, 0u);
+        return off;
+    }
+    void align4() { while (w.size() % 4) w.push_back(0u); }  // 16-byte granularity for bulk copies
+};
+
+// 2-choice cuckoo table: a key lives in slot h1(key) or h2(key).
 struct Cuckoo {
-    uint32_t c1, c2;
-    int bits;
+    uint32_t c1 = 1, c2 = 1;
+    int bits = 4;
     std::vector<uint32_t> key, val;
     std::vector<uint8_t> used;
     uint32_t h(uint32_t k, int which) const { return (k * (which ? c2 : c1)) >> (32 - bits); }
@@ -57,8 +67,8 @@ struct Cuckoo {
                 if (!used[s]) { used[s] = 1; key[s] = k; val[s] = v; placed = true; break; }
                 uint32_t s2 = h(k, which ^ 1);
                 if (!used[s2]) { used[s2] = 1; key[s2] = k; val[s2] = v; placed = true; break; }
-                std::swap(k, key[s]); std::swap(v, val[s]);   // evict the occupant of the first choice
-                which = (h(k, 0) == s) ? 1 : 0;               // and send it to its other slot
+                std::swap(k, key[s]); std::swap(v, val[s]);  // evict the occupant of the first choice
+                which = (h(k, 0) == s) ? 1 : 0;              // and send it to its other slot
             }
             if (!placed) return false;
         }
@@ -66,7 +76,7 @@ struct Cuckoo {
     }
 };
 
-static bool build_cuckoo(Cuckoo& ck, const std::vector<std::pair<uint32_t, uint32_t>>& items) {
+bool build_cuckoo(Cuckoo& ck, const std::vector<std::pair<uint32_t, uint32_t>>& items) {
     int bits = 4;
     while (((size_t)1 << bits) < 2 * items.size() + 2) bits++;
     uint64_t rng = 0x2545F4914F6CDD1Dull;
@@ -79,18 +89,8 @@ static bool build_cuckoo(Cuckoo& ck, const std::vector<std::pair<uint32_t, uint3
     return false;
 }
 
-struct Blob {
-    std::vector<uint32_t> w;
-    int32_t reserve(size_t n_words) {
-        int32_t off = (int32_t)w.size();
-        w.resize(w.size() + n_words, 0u);
-        return off;
-    }
-};
-
-// One keyword set -> bitmap + hash + DcbKw array + tag list.
+// One keyword set -> bitmap + hash + DcbKw array + tag list (general kernel).
 void build_kwset(Blob& b, DcbKwSet& ks, const std::vector<std::string>& list) {
-    // distinct keywords in first-occurrence order, with the ascending list of tags sharing each
     std::vector<std::string> kws;
     std::vector<std::vector<int>> members;
     std::map<std::string, int> seen;
@@ -111,7 +111,6 @@ void build_kwset(Blob& b, DcbKwSet& ks, const std::vector<std::string>& list) {
     ks.n_kw = (int)kws.size();
     ks.min_len = min_len; ks.max_len = max_len;
     ks.kq = std::min(min_len, 8);
-    // group by suffix key, longest first inside a group
     struct Ent { uint32_t key; int len; int id; };
     std::vector<Ent> ents;
     for (size_t i = 0; i < kws.size(); i++) {
@@ -121,7 +120,7 @@ void build_kwset(Blob& b, DcbKwSet& ks, const std::vector<std::string>& list) {
     }
     std::stable_sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& c) {
         if (a.key != c.key) return a.key < c.key;
-        return a.len > c.len;
+        return a.len > c.len;  // longest first = findall() order at equal end position
     });
     size_t bitmap_words = ((size_t)1 << (2 * ks.kq)) / 32;
     if (bitmap_words == 0) bitmap_words = 1;
@@ -160,7 +159,71 @@ void build_kwset(Blob& b, DcbKwSet& ks, const std::vector<std::string>& list) {
     }
 }
 
+int seed_q(int lmin) { return lmin >= 18 ? 9 : lmin >= 12 ? 8 : lmin >= 8 ? 6 : lmin; }
+
 }  // namespace
+
+// Seed index over the tags of one gene (the other pointer null) or of both genes of a chain (same lmin).
+bool dcb_build_seed_index(const std::vector<std::string>* gene_v, const std::vector<std::string>* gene_j, int lmin,
+                          std::vector<uint32_t>& out) {
+    Blob b;
+    DcbSeedIndex idx;
+    std::memset(&idx, 0, sizeof(idx));
+    b.reserve((sizeof(DcbSeedIndex) + 3) / 4);
+    idx.q = seed_q(lmin);
+    idx.stride = lmin - idx.q + 1;
+    idx.max_off = lmin - idx.q;
+    idx.span = (idx.max_off + 2) / 2;            // two classes of offsets: [0, span) and [span, max_off]
+    idx.wlead = idx.max_off + 1;
+    idx.k = std::min(15, lmin - idx.span + 1);
+    if (idx.wlead + idx.k > 32) idx.k = 32 - idx.wlead;
+    if (idx.k < 1 || idx.wlead > 31) return false;
+    std::map<uint32_t, std::vector<uint16_t>> lists;  // class << 31 | k-mer  ->  candidates
+    std::vector<uint32_t> seeds;
+    for (int gene = 0; gene < 2; gene++) {
+        const std::vector<std::string>* tags = gene == 0 ? gene_v : gene_j;
+        if (!tags) continue;
+        for (size_t t = 0; t < tags->size(); t++) {
+            const std::string& s = (*tags)[t];
+            for (int o = 0; o <= idx.max_off; o++) {
+                uint32_t lo, hi;
+                pack64(s, o, idx.q, lo, hi);
+                seeds.push_back(lo);
+                const int c = o / idx.span, from = o - c * idx.span;
+                pack64(s, from, idx.k, lo, hi);
+                lists[((uint32_t)c << 31) | lo].push_back((uint16_t)((gene << 15) | (t << 5) | o));
+            }
+        }
+    }
+    std::vector<std::pair<uint32_t, uint32_t>> items;
+    std::vector<uint16_t> pairs;
+    for (auto& kv : lists) {
+        if (kv.second.size() > 15) return false;
+        items.emplace_back(kv.first, (uint32_t)(pairs.size() << 4) | (uint32_t)kv.second.size());
+        for (uint16_t e : kv.second) pairs.push_back(e);
+    }
+    Cuckoo ck;
+    if (!build_cuckoo(ck, items)) return false;
+    idx.c1 = ck.c1; idx.c2 = ck.c2; idx.shift = 32 - ck.bits;
+    const size_t slots = (size_t)1 << ck.bits;
+    idx.ck_off = b.reserve(2 * slots);
+    for (size_t i = 0; i < slots; i++) {
+        b.w[idx.ck_off + 2 * i] = ck.used[i] ? ck.key[i] : DCB_HASH_EMPTY;
+        b.w[idx.ck_off + 2 * i + 1] = ck.used[i] ? ck.val[i] : 0u;
+    }
+    idx.pairs_off = b.reserve((pairs.size() + 1) / 2 + 1);
+    std::memcpy(&b.w[idx.pairs_off], pairs.data(), pairs.size() * 2);
+    b.align4();
+    size_t words = ((size_t)1 << (2 * idx.q)) / 32;
+    if (words < 4) words = 4;
+    idx.seedmap_off = b.reserve(words);
+    for (uint32_t key : seeds) b.w[idx.seedmap_off + DCB_SEEDMAP_WORD(key, idx.q)] |= 1u << DCB_SEEDMAP_BIT(key, idx.q);
+    b.align4();
+    idx.n_words = (int32_t)b.w.size();
+    std::memcpy(&b.w[0], &idx, sizeof(idx));
+    out = std::move(b.w);
+    return true;
+}
 
 extern "C" {
 
@@ -188,13 +251,12 @@ dcb_tagset* dcb_tagset_build(const char* const* tags, const int32_t* jumps, cons
     }
 
     dcb_tagset* ts = new dcb_tagset();
-    ts->n_tags = n; ts->split = half_split; ts->is_v = is_v;
-    for (auto& t : full) ts->tag_len.push_back((int)t.size());
+    ts->n_tags = n; ts->split = half_split; ts->is_v = is_v; ts->lmin = lmin;
+    ts->tags = full;
 
-    for (int which = 0; which < 2; which++) {  // 0: general blob, 1: fast blob
+    for (int which = 0; which < 2; which++) {  // 0: general blob (tags + keyword sets + regions), 1: core blob (tags only)
         Blob b;
-        const size_t hdr_words = (sizeof(DcbGene) + 3) / 4;
-        b.reserve(hdr_words);
+        b.reserve((sizeof(DcbGene) + 3) / 4);
         DcbGene g;
         std::memset(&g, 0, sizeof(g));
         g.n_tags = n; g.split = half_split; g.is_v = is_v; g.lmin = lmin;
@@ -213,7 +275,6 @@ dcb_tagset* dcb_tagset_build(const char* const* tags, const int32_t* jumps, cons
             int f2 = (int)(std::find(h2.begin(), h2.end(), h2[i]) - h2.begin());
             t.h1_first_len = (uint8_t)full[f1].size();
             t.h2_first_len = (uint8_t)full[f2].size();
-            t.next_same_prefix = 0xFF;
         }
         if (which == 0) {
             build_kwset(b, g.full, full);
@@ -225,82 +286,41 @@ dcb_tagset* dcb_tagset_build(const char* const* tags, const int32_t* jumps, cons
                 for (size_t p = 0; p < reg[i].size(); p++)
                     b.w[trec[i].region_off + p / 16] |= (uint32_t)base_code(reg[i][p]) << (2 * (p % 16));
             }
-        } else {
-            g.q = lmin >= 18 ? 9 : lmin >= 12 ? 8 : lmin >= 8 ? 6 : lmin;
-            g.stride = lmin - g.q + 1;
-            std::map<uint32_t, uint32_t> seeds;  // q-mer -> mask of offsets
-            for (int i = 0; i < n; i++) {
-                for (size_t o = 0; o + g.q <= full[i].size(); o++) {
-                    uint32_t lo, hi;
-                    pack64(full[i], o, g.q, lo, hi);
-                    seeds[lo] |= 1u << o;
-                }
-            }
-            {
-                std::vector<std::pair<uint32_t, uint32_t>> items(seeds.begin(), seeds.end());
-                Cuckoo ck;
-                if (!build_cuckoo(ck, items)) { dcb_set_error("dcb_tagset_build: seed table construction failed"); delete ts; return nullptr; }
-                g.seed_c1 = ck.c1; g.seed_c2 = ck.c2; g.seed_shift = 32 - ck.bits;
-                const size_t slots = (size_t)1 << ck.bits;
-                g.seedhash_off = b.reserve(2 * slots);
-                for (size_t i = 0; i < slots; i++) {
-                    b.w[g.seedhash_off + 2 * i] = ck.used[i] ? ck.key[i] : DCB_HASH_EMPTY;
-                    b.w[g.seedhash_off + 2 * i + 1] = ck.used[i] ? ck.val[i] : 0u;
-                }
-            }
-            {
-                // tags keyed on their lmin-prefix; tags sharing a prefix are chained through next_same_prefix
-                std::map<std::pair<uint32_t, uint32_t>, int> first_with_prefix;
-                std::vector<std::pair<uint32_t, uint32_t>> items;
-                std::map<uint32_t, int> folded_seen;
-                bool fold_clash = false;
-                for (int i = n - 1; i >= 0; i--) {   // descending, so each chain ends up in ascending tag order
-                    uint32_t lo, hi;
-                    pack64(full[i], 0, lmin, lo, hi);
-                    auto key = std::make_pair(lo, hi);
-                    auto it = first_with_prefix.find(key);
-                    trec[i].next_same_prefix = it == first_with_prefix.end() ? 0xFF : (uint8_t)it->second;
-                    first_with_prefix[key] = i;
-                }
-                for (auto& kv : first_with_prefix) {
-                    uint32_t f = dcb_fold64(kv.first.first, kv.first.second);
-                    if (folded_seen.count(f)) fold_clash = true;
-                    folded_seen[f] = 1;
-                    items.emplace_back(f, (uint32_t)kv.second);
-                }
-                Cuckoo ck;
-                if (fold_clash || !build_cuckoo(ck, items)) { dcb_set_error("dcb_tagset_build: prefix table construction failed"); delete ts; return nullptr; }
-                g.pref_c1 = ck.c1; g.pref_c2 = ck.c2; g.pref_shift = 32 - ck.bits;
-                const size_t slots = (size_t)1 << ck.bits;
-                g.prefhash_off = b.reserve(slots);
-                for (size_t i = 0; i < slots; i++) b.w[g.prefhash_off + i] = ck.used[i] ? ck.val[i] : DCB_HASH_EMPTY;
-            }
-            while (b.w.size() % 4) b.w.push_back(0u);
-            g.core_words = (int32_t)b.w.size();
-            size_t words = ((size_t)1 << (2 * g.q)) / 32;  // the seed bitmap comes last
-            if (words < 4) words = 4;
-            g.seedmap_off = b.reserve(words);
-            for (auto& kv : seeds)
-                b.w[g.seedmap_off + DCB_SEEDMAP_WORD(kv.first, g.q)] |= 1u << DCB_SEEDMAP_BIT(kv.first, g.q);
         }
-        while (b.w.size() % 4) b.w.push_back(0u);  // 16-byte granularity for vector copies
+        b.align4();
         g.n_words = (int32_t)b.w.size();
-        if (which == 0) g.core_words = g.n_words;
         std::memcpy(&b.w[g.tag_off], trec.data(), sizeof(DcbTag) * n);
         std::memcpy(&b.w[0], &g, sizeof(g));
-        (which == 0 ? ts->general : ts->fast) = std::move(b.w);
+        (which == 0 ? ts->general : ts->core) = std::move(b.w);
+    }
+    if (!dcb_build_seed_index(is_v ? &ts->tags : nullptr, is_v ? nullptr : &ts->tags, lmin, ts->index)) {
+        dcb_set_error("dcb_tagset_build: seed index construction failed");
+        delete ts;
+        return nullptr;
     }
     return ts;
 }
 
 void dcb_tagset_free(dcb_tagset* ts) { delete ts; }
 
-size_t dcb_tagset_table_bytes(const dcb_tagset* ts) { return ts ? 4 * (ts->fast.size() + ts->general.size()) : 0; }
+size_t dcb_tagset_table_bytes(const dcb_tagset* ts) {
+    return ts ? 4 * (ts->core.size() + ts->index.size() + ts->general.size()) : 0;
+}
 
 int dcb_tagset_blob(const dcb_tagset* ts, int which, const uint32_t** words, size_t* n_words) {
-    if (!ts || !words || !n_words) return DCB_EINVAL;
-    const std::vector<uint32_t>& v = which ? ts->fast : ts->general;
+    if (!ts || !words || !n_words || which < 0 || which > 2) return DCB_EINVAL;
+    const std::vector<uint32_t>& v = which == 0 ? ts->general : which == 1 ? ts->core : ts->index;
     *words = v.data(); *n_words = v.size();
+    return DCB_OK;
+}
+
+int dcb_tagset_union_index(const dcb_tagset* v, const dcb_tagset* j, uint32_t* out, size_t cap, size_t* n_words) {
+    if (!v || !j || !n_words) return DCB_EINVAL;
+    if (v->lmin != j->lmin) { dcb_set_error("dcb_tagset_union_index: V and J tags have different minimum lengths"); return DCB_EUNSUPPORTED; }
+    std::vector<uint32_t> u;
+    if (!dcb_build_seed_index(&v->tags, &j->tags, v->lmin, u)) { dcb_set_error("dcb_tagset_union_index: construction failed"); return DCB_EUNSUPPORTED; }
+    *n_words = u.size();
+    if (out && cap >= u.size()) std::memcpy(out, u.data(), u.size() * 4);
     return DCB_OK;
 }
 

@@ -83,8 +83,12 @@ dcb_tagset* dcb_tagset_build(const char* const* tags, const int32_t* jumps, cons
 void dcb_tagset_free(dcb_tagset*);
 /* Total bytes of the flattened table blobs (what thread blocks stage in shared memory). */
 size_t dcb_tagset_table_bytes(const dcb_tagset*);
-/* Introspection (tests): which = 0 the general-kernel blob, 1 the exact-tag-kernel blob. */
+/* Introspection (tests): which = 0 the general-kernel blob, 1 the tag records of the exact-tag kernels,
+ * 2 this gene's seed index. */
 int dcb_tagset_blob(const dcb_tagset*, int which, const uint32_t** words, size_t* n_words);
+/* Seed index over BOTH genes of a chain (built by dcb_ctx_create when V and J share the seed geometry).
+ * Writes up to cap words; *n_words is the size needed; returns DCB_EUNSUPPORTED when the geometries differ. */
+int dcb_tagset_union_index(const dcb_tagset* v, const dcb_tagset* j, uint32_t* out, size_t cap, size_t* n_words);
 
 /* ---------------------------------------------------------------------------------------------
  * Packed reads: 2 bits per base (A=0 C=1 G=2 T=3, base i of a read in bits [2*(i%16), +2) of

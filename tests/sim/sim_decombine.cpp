@@ -8,8 +8,10 @@
 #include <cstring>
 #include <vector>
 
-extern "C" int sim_decombine(const dcb_packed* P, const uint32_t* vgen, const uint32_t* jgen, const uint32_t* vfast,
-                             const uint32_t* jfast, int both_frames, int allow_ns, int lenthreshold, int mode,
+// vidx: the V seed index, or the union index of both genes when jidx is null
+extern "C" int sim_decombine(const dcb_packed* P, const uint32_t* vgen, const uint32_t* jgen, const uint32_t* vcore,
+                             const uint32_t* jcore, const uint32_t* vidx, const uint32_t* jidx, int both_frames,
+                             int allow_ns, int lenthreshold, int mode,
                              dcb_result* out, uint64_t* counters, uint64_t* n_deferred) {
     DcrParams prm;
     prm.allow_ns = allow_ns; prm.lenthreshold = lenthreshold;
@@ -30,7 +32,7 @@ extern "C" int sim_decombine(const dcb_packed* P, const uint32_t* vgen, const ui
         dcb_result o;
         std::memset(&o, 0, sizeof(o));
         int action = FAST_DEFER;
-        if (mode == 0) action = dcr_exact_read(r, flagged, vfast, jfast, prm, both_frames, o, cnt);
+        if (mode == 0) action = dcr_exact_read(r, flagged, vcore, jcore, vidx, jidx, prm, both_frames, o, cnt);
         if (action == FAST_DEFER) {
             deferred++;
             std::memset(&o, 0, sizeof(o));

@@ -38,9 +38,13 @@ def test_tagset_build_all_shipped_sets():
             info = tags.load(species, tagset, c)
             vt, jt = info.tables()
             assert vt.table_bytes() > 0 and jt.table_bytes() > 0
-            # both blobs of both genes must fit next to a 320-nt read tile in 227 KB of shared memory
-            assert (vt.blob(1).nbytes + jt.blob(1).nbytes) + 20 * 256 * 4 < 227 * 1024
+            # the tables of both genes must fit next to a 320-nt read tile in 227 KB of shared memory
+            exact = vt.blob(1).nbytes + jt.blob(1).nbytes + vt.blob(2).nbytes + jt.blob(2).nbytes
+            assert exact + 20 * 256 * 4 < 227 * 1024
             assert (vt.blob(0).nbytes + jt.blob(0).nbytes) + 30 * 128 * 4 < 227 * 1024
+            u = _lib.union_index(vt, jt)
+            same_geometry = min(map(len, info.v_seqs)) == min(map(len, info.j_seqs))
+            assert (u is not None) == same_geometry
 
 
 def test_tagset_build_rejects_unsupported_input():

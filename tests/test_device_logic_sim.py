@@ -10,15 +10,15 @@ from decombinator_b200 import _lib, tags
 from helpers import assert_records_equal, record_to_list, synth_batch
 
 
-@pytest.mark.parametrize("general_only", [False, True])
-def test_sim_matches_reference_fixtures(dcr_cases, general_only):
+@pytest.mark.parametrize("general_only,use_union", [(False, None), (False, False), (True, None)])
+def test_sim_matches_reference_fixtures(dcr_cases, general_only, use_union):
     names = dcr_cases["counters"]
     for gi, g in enumerate(dcr_cases["groups"]):
         info = tags.load(g["species"], g["tags"], g["chain"])
         vt, jt = info.tables()
         packed = _lib.pack_strings(g["reads"], revcomp=(g["orientation"] != "forward"))
         res, cnt, _ = simlib.sim_decombine(packed, vt, jt, both_frames=(g["orientation"] == "both"), allow_ns=g["allowNs"],
-                                           lenthreshold=g["lenthreshold"], general_only=general_only)
+                                           lenthreshold=g["lenthreshold"], general_only=general_only, use_union=use_union)
         got = [record_to_list(r, rec, g["orientation"]) for r, rec in zip(g["reads"], res)]
         bad = [i for i, (a, b) in enumerate(zip(got, g["results"])) if a != b]
         assert not bad, (gi, bad[:5])
