@@ -44,18 +44,20 @@ struct DcbKwSet {
     int32_t min_len, max_len;
 };
 
-// Per-tag record (32 bytes = 8 words).
+// Per-tag record (48 bytes = 12 words; the first 16 bytes are read with one 128-bit load).
+#define DCB_TAG_WORDS 12
 struct DcbTag {
     uint32_t bits_lo, bits_hi;   // packed full tag
+    uint32_t mask_lo, mask_hi;   // 2*len low bits set
     uint32_t edge_lo, edge_hi;   // V: last 32 germline bases (region[m-32:m]); J: first 32 (region[0:32])
     int16_t jump;                // jump_to_end_v / jump_to_start_j
     int16_t region_len;          // m
-    int32_t region_off;          // packed region words
     uint8_t len;                 // tag length
-    uint8_t h1_first_len;        // len(tags[half1 list .index(half1 of this tag)])  (length-guard quirk)
-    uint8_t h2_first_len;
     uint8_t edge_ok;             // region_len >= 32
-    uint8_t pad8[4];
+    uint8_t next_same_prefix;    // next tag of the same gene sharing this tag's lmin-prefix, 0xFF = none
+    uint8_t pad8;
+    int32_t region_off;          // packed region words (general blob)
+    uint32_t pad[3];
 };
 
 struct DcbGene {
@@ -72,21 +74,33 @@ struct DcbGene {
 //   1. seed bitmap (4^q bits): is the q-mer at the sampled position p part of any tag at an offset <= lmin-q?
 //   2. on a hit, the unknown offset o falls in class c = o / span (two classes); the k-mer at [p - c*span, +k)
 //      then lies inside the tag for every o of that class, and a 2-choice cuckoo table (two slot reads, no
-//      probing loop) maps (c, k-mer) to the short list of (gene, tag, offset) candidates -- usually one;
-//   3. each candidate is confirmed by comparing the whole tag with the read window.
+//      probing loop) maps (c, k-mer) to the set of offsets it occurs at -- almost always exactly one;
+//   3. for each offset the tag would start at P = p - o: its lmin-prefix is looked up in a second cuckoo table
+//      (all tags of the index, keyed on the folded prefix) and the whole tag is compared with the read.
 struct DcbSeedIndex {
     int32_t q, stride;
     int32_t max_off;             // lmin - q: largest indexed tag offset
     int32_t k, span;             // class key length (<= 15 bases) and offsets per class
     int32_t wlead;               // the verification window starts at p - wlead (max_off + 1)
-    int32_t ck_off;              // 2^bits slots of 2 words: [class << 31 | key  (DCB_HASH_EMPTY if free), start << 4 | count]
+    int32_t ck_off;              // 2^bits slots of 2 words: [class << 31 | key  (DCB_HASH_EMPTY if free), mask of offsets]
     uint32_t c1, c2;             // h(x) = (x * c) >> shift
     int32_t shift;
-    int32_t pairs_off;           // 16-bit entries: gene << 15 | tag << 5 | offset   (gene 0 = V, 1 = J)
+    int32_t tk_off;              // 2^bits slots: fingerprint << 9 | gene << 8 | tag  (gene 0 = V, 1 = J) or DCB_HASH_EMPTY;
+                                 // fingerprint = top 23 bits of the folded prefix
+    uint32_t t1, t2;             // h(f) = (f * t) >> tshift, f = dcb_fold64(lmin-prefix)
+    int32_t tshift;
     int32_t seedmap_off;         // the bitmap comes last
     int32_t n_words;
-    int32_t pad;
 };
+
+// Geometry of a seed index as a function of (lmin, q): shared by the host builder and the kernels, whose
+// specialisations evaluate these at compile time.
+#define DCB_IDX_STRIDE(lmin, q) ((lmin) - (q) + 1)
+#define DCB_IDX_MAXOFF(lmin, q) ((lmin) - (q))
+#define DCB_IDX_SPAN(lmin, q) ((DCB_IDX_MAXOFF(lmin, q) + 2) / 2)
+#define DCB_IDX_WLEAD(lmin, q) (DCB_IDX_MAXOFF(lmin, q) + 1)
+#define DCB_IDX_K0(lmin, q) (((lmin) - DCB_IDX_SPAN(lmin, q) + 1) < 15 ? ((lmin) - DCB_IDX_SPAN(lmin, q) + 1) : 15)
+#define DCB_IDX_K(lmin, q) ((DCB_IDX_WLEAD(lmin, q) + DCB_IDX_K0(lmin, q)) > 32 ? (32 - DCB_IDX_WLEAD(lmin, q)) : DCB_IDX_K0(lmin, q))
 
 // Seed bitmap addressing: the LOW 2q-5 bits of a q-mer key select the word, the high 5 bits the bit, so the
 // word address is a mask of the already-shifted read window and the bit index needs no masking.
@@ -99,6 +113,11 @@ struct DcbSeedIndex {
 #define DCB_HD inline
 #endif
 
+DCB_HD uint32_t dcb_fold64(uint32_t lo, uint32_t hi) {
+    uint32_t k = lo * 0x9E3779B1u + hi * 0x85EBCA77u;
+    return k ^ (k >> 13);
+}
+#define DCB_TK_FP(f) ((f) & 0xFFFFFE00u)   // the fingerprint bits of a tag-prefix slot
 DCB_HD uint32_t dcb_hash32(uint32_t k) {
     k *= 0x9E3779B1u;
     return k ^ (k >> 15);

@@ -387,13 +387,18 @@ DCB_HD uint32_t revcomp_word(const ReadView& r, int ow) {
 // ------------------------------------------------------------------------------------------------
 // Result of the sampled-seed search for full tags: number of distinct occurrences (saturating at 2)
 // and the first one.
-struct FullHit { int count, tag, pos; };
+struct FullHit {
+    int count;        // distinct occurrences, saturating at 2
+    uint32_t code;    // first occurrence: tag << 16 | position
+};
+DCB_HD int fullhit_tag(const FullHit& fh) { return (int)(fh.code >> 16); }
+DCB_HD int fullhit_pos(const FullHit& fh) { return (int)(fh.code & 0xFFFFu); }
 
-// Record one confirmed full-tag occurrence.
+// Record one confirmed full-tag occurrence (the same one may be reported twice).
 DCB_HD void fullhit_add(FullHit& fh, int tag, int pos) {
-    if (fh.count && fh.tag == tag && fh.pos == pos) return;
-    if (fh.count == 0) { fh.tag = tag; fh.pos = pos; }
-    if (fh.count < 2) fh.count++;
+    const uint32_t code = ((uint32_t)tag << 16) | (uint32_t)pos;
+    if (fh.count == 0) { fh.code = code; fh.count = 1; }
+    else if (code != fh.code) fh.count = 2;
 }
 
 // 64-bit window helpers (two 32-bit halves: the device has no native 64-bit shifter)
@@ -404,42 +409,83 @@ DCB_HD uint32_t win_hi_shr(uint32_t hi, int bits) {               // high word o
     return bits >= 32 ? 0u : (hi >> bits);
 }
 
-// Confirm the candidates behind one seed hit at sampled position p: two cuckoo lookups (one per offset class),
-// then a whole-tag comparison per listed (gene, tag, offset).  vcore / jcore may each be null when the index
-// only covers the other gene.
-DCB_HD void fast_verify_hit(const ReadView& r, const uint32_t* ib, int p, const uint32_t* vcore, const uint32_t* jcore,
-                            FullHit& vh, FullHit& jh) {
+// A DcbSeedIndex with its hot fields in registers.  The specialised kernels overwrite the geometry fields with
+// compile-time constants, which the optimiser then folds through the (force-inlined) functions below.
+struct SeedIdxView {
+    const uint32_t* ck;        // class-key cuckoo slots
+    const uint32_t* tk;        // tag-prefix cuckoo slots
+    const uint32_t* seedmap;   // seed bitmap
+    uint32_t c1, c2, t1, t2;
+    int shift, tshift;
+    int q, stride, lmin, wlead, span, k;
+};
+DCB_HD SeedIdxView seed_idx_view(const uint32_t* ib) {
     const DcbSeedIndex& ix = *reinterpret_cast<const DcbSeedIndex*>(ib);
+    SeedIdxView v;
+    v.ck = ib + ix.ck_off;
+    v.tk = ib + ix.tk_off;
+    v.seedmap = ib + ix.seedmap_off;
+    v.c1 = ix.c1; v.c2 = ix.c2; v.shift = ix.shift;
+    v.t1 = ix.t1; v.t2 = ix.t2; v.tshift = ix.tshift;
+    v.q = ix.q; v.stride = ix.stride; v.lmin = ix.stride + ix.q - 1;
+    v.wlead = ix.wlead; v.span = ix.span; v.k = ix.k;
+    return v;
+}
+DCB_HD const DcbTag* gene_tags(const uint32_t* core) {
+    return core ? reinterpret_cast<const DcbTag*>(core + reinterpret_cast<const DcbGene*>(core)->tag_off) : nullptr;
+}
+
+// Confirm the candidates behind one seed hit at sampled position p: two class-key lookups give the possible tag
+// offsets (almost always one); each offset selects at most one tag through the fingerprinted tag-prefix table,
+// and that tag (plus the rare ones chained to it) is compared as a whole.
+DCB_HD void fast_verify_hit(const ReadView& r, const SeedIdxView& ix, int p, const DcbTag* vtags, const DcbTag* jtags,
+                            FullHit& vh, FullHit& jh) {
     uint32_t wlo, whi;                       // 32 bases starting at p - wlead
     rd_win32(r, p - ix.wlead, wlo, whi);
     const uint32_t kmask = mask2(ix.k);
-    const uint16_t* pairs = reinterpret_cast<const uint16_t*>(ib + ix.pairs_off);
+    uint32_t offs = 0;
     for (int c = 0; c < 2; c++) {
         const uint32_t key = ((uint32_t)c << 31) | (win_lo_shr(wlo, whi, 2 * (ix.wlead - c * ix.span)) & kmask);
         const uint32_t s1 = (key * ix.c1) >> ix.shift, s2 = (key * ix.c2) >> ix.shift;
-        const uint32_t k1 = ib[ix.ck_off + 2 * s1], v1 = ib[ix.ck_off + 2 * s1 + 1];
-        const uint32_t k2 = ib[ix.ck_off + 2 * s2], v2 = ib[ix.ck_off + 2 * s2 + 1];
-        const uint32_t val = k1 == key ? v1 : (k2 == key ? v2 : 0u);
-        const int n_cand = (int)(val & 15u), start = (int)(val >> 4);
-        for (int i = 0; i < n_cand; i++) {
-            const uint32_t e = pairs[start + i];
-            const int o = (int)(e & 31u), tag = (int)((e >> 5) & 0x3FFu), is_j = (int)(e >> 15);
-            const uint32_t* core = is_j ? jcore : vcore;
-            const DcbTag& t = gene_tag(core, *reinterpret_cast<const DcbGene*>(core), tag);
-            const int P = p - o, L = t.len;
-            if (P < 0 || P + L > r.n) continue;
-            uint32_t lo, hi;
-            if (L - o <= 32 - ix.wlead) {    // the tag lies inside the window already in registers
-                const int sh = 2 * (ix.wlead - o);
-                lo = win_lo_shr(wlo, whi, sh);
-                hi = win_hi_shr(whi, sh);
-            } else {
-                rd_win32(r, P, lo, hi);
-            }
-            const uint32_t mlo = mask2(L), mhi = L > 16 ? mask2(L - 16) : 0u;
-            if (((lo ^ t.bits_lo) & mlo) | ((hi ^ t.bits_hi) & mhi)) continue;
-            fullhit_add(is_j ? jh : vh, tag, P);
+        const uint32_t k1 = ix.ck[2 * s1], v1 = ix.ck[2 * s1 + 1];
+        const uint32_t k2 = ix.ck[2 * s2], v2 = ix.ck[2 * s2 + 1];
+        offs |= k1 == key ? v1 : (k2 == key ? v2 : 0u);
+    }
+    const uint32_t plo_mask = mask2(ix.lmin), phi_mask = ix.lmin > 16 ? mask2(ix.lmin - 16) : 0u;
+    while (offs) {
+        const int o = DCB_FFS(offs) - 1;
+        offs &= offs - 1;
+        const int P = p - o;
+        if (P < 0 || P + ix.lmin > r.n) continue;
+        uint32_t lo, hi;
+        const bool in_window = ix.lmin - o <= 32 - ix.wlead;   // the lmin-prefix lies inside the window in registers
+        if (in_window) {
+            const int sh = 2 * (ix.wlead - o);
+            lo = win_lo_shr(wlo, whi, sh);
+            hi = win_hi_shr(whi, sh);
+        } else {
+            rd_win32(r, P, lo, hi);
         }
+        const uint32_t f = dcb_fold64(lo & plo_mask, hi & phi_mask);
+        const uint32_t slot1 = ix.tk[(f * ix.t1) >> ix.tshift], slot2 = ix.tk[(f * ix.t2) >> ix.tshift];
+        // a prefix lives in at most one of its two slots: pick by fingerprint (EMPTY never matches: tag field 0xFF)
+        const uint32_t fp = DCB_TK_FP(f);
+        const uint32_t slot = DCB_TK_FP(slot1) == fp ? slot1 : slot2;
+        if (DCB_TK_FP(slot) != fp || (slot & 0xFFu) == 0xFFu) continue;
+        const int is_j = (int)((slot >> 8) & 1u);
+        const DcbTag* tags = is_j ? jtags : vtags;
+        if (!tags) continue;
+        uint32_t id = slot & 0xFFu;
+        do {
+            const DcbTag& t = tags[id];
+            const int L = t.len;
+            if (P + L <= r.n) {
+                uint32_t tlo = lo, thi = hi;
+                if (!in_window || L - o > 32 - ix.wlead) rd_win32(r, P, tlo, thi);   // long tag: past the register window
+                if (!(((tlo ^ t.bits_lo) & t.mask_lo) | ((thi ^ t.bits_hi) & t.mask_hi))) fullhit_add(is_j ? jh : vh, (int)id, P);
+            }
+            id = t.next_same_prefix;
+        } while (id != 0xFFu);
     }
 }
 
@@ -503,7 +549,9 @@ DCB_HD int fast_j_deletions(const ReadView& r, const DcbTag& t, int temp_start_j
 // specialisation of the probing for the common slot sizes; this is the generic form.)
 DCB_HD void fast_find(const ReadView& r, const uint32_t* ib, const uint32_t* vcore, const uint32_t* jcore,
                       FullHit& vh, FullHit& jh) {
-    const DcbSeedIndex& ix = *reinterpret_cast<const DcbSeedIndex*>(ib);
+    const SeedIdxView ix = seed_idx_view(ib);
+    const DcbTag* vtags = gene_tags(vcore);
+    const DcbTag* jtags = gene_tags(jcore);
     const uint32_t qmask = mask2(ix.q);
     const int last = r.n - ix.q;  // last start position of a whole q-mer
     for (int base = 0; base <= last; base += 32 * ix.stride) {
@@ -512,12 +560,12 @@ DCB_HD void fast_find(const ReadView& r, const uint32_t* ib, const uint32_t* vco
             const int p = base + i * ix.stride;
             if (p > last) break;
             const uint32_t key = rd_win16(r, p) & qmask;
-            hits |= ((ib[ix.seedmap_off + DCB_SEEDMAP_WORD(key, ix.q)] >> DCB_SEEDMAP_BIT(key, ix.q)) & 1u) << i;
+            hits |= ((ix.seedmap[DCB_SEEDMAP_WORD(key, ix.q)] >> DCB_SEEDMAP_BIT(key, ix.q)) & 1u) << i;
         }
         while (hits) {
             const int i = DCB_FFS(hits) - 1;
             hits &= hits - 1;
-            fast_verify_hit(r, ib, base + i * ix.stride, vcore, jcore, vh, jh);
+            fast_verify_hit(r, ix, base + i * ix.stride, vtags, jtags, vh, jh);
             if (vcore && vh.count >= 2) return;
         }
     }
@@ -541,10 +589,10 @@ DCB_HD int dcr_fast_from_hits(const ReadView& r, const uint32_t* vblob, const ui
         DCB_COUNT(C, DCB_C_multiple_v_matches);
         return FAST_DONE;
     }
-    const DcbTag& vt = gene_tag(vblob, gv, vh.tag);
+    const DcbTag& vt = gene_tag(vblob, gv, fullhit_tag(vh));
     VJ v, j;
-    v.idx = vh.tag; v.seqpos = vh.pos;
-    if (!fast_v_deletions(r, vt, vh.pos + vt.jump - 1, v.pos, v.dels)) return FAST_DEFER;
+    v.idx = fullhit_tag(vh); v.seqpos = fullhit_pos(vh);
+    if (!fast_v_deletions(r, vt, v.seqpos + vt.jump - 1, v.pos, v.dels)) return FAST_DEFER;
     if (jh.count == 0) return FAST_DEFER;
     if (jh.count > 1) {
         if (both_frames) return FAST_DEFER;
@@ -552,9 +600,9 @@ DCB_HD int dcr_fast_from_hits(const ReadView& r, const uint32_t* vblob, const ui
         DCB_COUNT(C, DCB_C_VJ_assignment_failed);
         return FAST_DONE;
     }
-    const DcbTag& jt = gene_tag(jblob, gj, jh.tag);
-    j.idx = jh.tag; j.seqpos = jh.pos + (int)jt.len;
-    if (!fast_j_deletions(r, jt, jh.pos - jt.jump, v.pos + 1, j.pos, j.dels)) return FAST_DEFER;
+    const DcbTag& jt = gene_tag(jblob, gj, fullhit_tag(jh));
+    j.idx = fullhit_tag(jh); j.seqpos = fullhit_pos(jh) + (int)jt.len;
+    if (!fast_j_deletions(r, jt, fullhit_pos(jh) - jt.jump, v.pos + 1, j.pos, j.dels)) return FAST_DEFER;
     // filters: a failed filter is final unless the other frame still has to be tried
     int c = dcr_finish(r, vt, jt, v, j, prm, out);
     if (c >= 0) {
@@ -591,8 +639,8 @@ DCB_HD int dcr_exact_read(const ReadView& r, bool flagged, const uint32_t* vcore
                           dcb_result& out, dcb_cnt_t* C) {
     if (flagged) return FAST_DEFER;
     FullHit vh, jh;
-    vh.count = 0; vh.tag = 0; vh.pos = 0;
-    jh.count = 0; jh.tag = 0; jh.pos = 0;
+    vh.count = 0; vh.code = 0;
+    jh.count = 0; jh.code = 0;
     if (!jidx) {
         fast_find(r, vidx, vcore, jcore, vh, jh);
     } else {

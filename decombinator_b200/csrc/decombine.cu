@@ -258,10 +258,15 @@ dcb_exact_kernel_spec(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dc
 
     const uint32_t* vcore = L.t[0];
     const uint32_t* jcore = L.t[1];
-    const uint32_t* vidx = L.t[2];
-    const uint32_t* jidx = UNION ? L.t[2] : L.t[3];
-    const uint32_t* vmap = vidx + reinterpret_cast<const DcbSeedIndex*>(vidx)->seedmap_off;
-    const uint32_t* jmap = jidx + reinterpret_cast<const DcbSeedIndex*>(jidx)->seedmap_off;
+    const DcbTag* vtags = gene_tags(vcore);
+    const DcbTag* jtags = gene_tags(jcore);
+    // index views with the geometry pinned to the template constants (lmin = S + Q - 1)
+    SeedIdxView vix = seed_idx_view(L.t[2]);
+    vix.q = QV; vix.stride = SV; vix.lmin = SV + QV - 1;
+    vix.wlead = DCB_IDX_WLEAD(SV + QV - 1, QV); vix.span = DCB_IDX_SPAN(SV + QV - 1, QV); vix.k = DCB_IDX_K(SV + QV - 1, QV);
+    SeedIdxView jix = seed_idx_view(UNION ? L.t[2] : L.t[3]);
+    jix.q = QJ; jix.stride = SJ; jix.lmin = SJ + QJ - 1;
+    jix.wlead = DCB_IDX_WLEAD(SJ + QJ - 1, QJ); jix.span = DCB_IDX_SPAN(SJ + QJ - 1, QJ); jix.k = DCB_IDX_K(SJ + QJ - 1, QJ);
     const int tid = threadIdx.x;
     const uint32_t n_tiles = (b.n_reads + T - 1) / T;
 
@@ -291,18 +296,18 @@ dcb_exact_kernel_spec(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dc
                 r.nw = NW;
                 r.exc_pos = nullptr; r.exc_kind = nullptr; r.e0 = r.e1 = 0; r.mirror = 0;
                 FullHit vh, jh;
-                vh.count = 0; vh.tag = 0; vh.pos = 0;
-                jh.count = 0; jh.tag = 0; jh.pos = 0;
+                vh.count = 0; vh.code = 0;
+                jh.count = 0; jh.code = 0;
                 uint32_t lo, hi;
-                SeedScan<NW, QV, SV>::run(w, vmap, lo, hi);
+                SeedScan<NW, QV, SV>::run(w, vix.seedmap, lo, hi);
                 SeedScan<NW, QV, SV>::clip(r.n, lo, hi);
                 while ((lo | hi) && vh.count < 2)
-                    fast_verify_hit(r, vidx, pop_hit(lo, hi) * SV, vcore, UNION ? jcore : nullptr, vh, jh);
+                    fast_verify_hit(r, vix, pop_hit(lo, hi) * SV, vtags, UNION ? jtags : nullptr, vh, jh);
                 if (!UNION && vh.count == 1) {
-                    SeedScan<NW, QJ, SJ>::run(w, jmap, lo, hi);
+                    SeedScan<NW, QJ, SJ>::run(w, jix.seedmap, lo, hi);
                     SeedScan<NW, QJ, SJ>::clip(r.n, lo, hi);
                     while ((lo | hi) && jh.count < 2)
-                        fast_verify_hit(r, jidx, pop_hit(lo, hi) * SJ, nullptr, jcore, vh, jh);
+                        fast_verify_hit(r, jix, pop_hit(lo, hi) * SJ, nullptr, jtags, vh, jh);
                 }
                 action = dcr_fast_from_hits(r, vcore, jcore, vh, jh, prm, both_frames, out, L.cnt);
             }

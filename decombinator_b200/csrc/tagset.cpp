@@ -171,48 +171,65 @@ bool dcb_build_seed_index(const std::vector<std::string>* gene_v, const std::vec
     std::memset(&idx, 0, sizeof(idx));
     b.reserve((sizeof(DcbSeedIndex) + 3) / 4);
     idx.q = seed_q(lmin);
-    idx.stride = lmin - idx.q + 1;
-    idx.max_off = lmin - idx.q;
-    idx.span = (idx.max_off + 2) / 2;            // two classes of offsets: [0, span) and [span, max_off]
-    idx.wlead = idx.max_off + 1;
-    idx.k = std::min(15, lmin - idx.span + 1);
-    if (idx.wlead + idx.k > 32) idx.k = 32 - idx.wlead;
+    idx.stride = DCB_IDX_STRIDE(lmin, idx.q);
+    idx.max_off = DCB_IDX_MAXOFF(lmin, idx.q);
+    idx.span = DCB_IDX_SPAN(lmin, idx.q);        // two classes of offsets: [0, span) and [span, max_off]
+    idx.wlead = DCB_IDX_WLEAD(lmin, idx.q);
+    idx.k = DCB_IDX_K(lmin, idx.q);
     if (idx.k < 1 || idx.wlead > 31) return false;
-    std::map<uint32_t, std::vector<uint16_t>> lists;  // class << 31 | k-mer  ->  candidates
+    std::map<uint32_t, uint32_t> classkeys;  // class << 31 | k-mer  ->  mask of offsets
+    std::map<std::pair<uint32_t, uint32_t>, uint32_t> prefixes;  // lmin-prefix -> gene << 8 | first tag
     std::vector<uint32_t> seeds;
     for (int gene = 0; gene < 2; gene++) {
         const std::vector<std::string>* tags = gene == 0 ? gene_v : gene_j;
         if (!tags) continue;
         for (size_t t = 0; t < tags->size(); t++) {
             const std::string& s = (*tags)[t];
+            uint32_t lo, hi;
             for (int o = 0; o <= idx.max_off; o++) {
-                uint32_t lo, hi;
                 pack64(s, o, idx.q, lo, hi);
                 seeds.push_back(lo);
                 const int c = o / idx.span, from = o - c * idx.span;
                 pack64(s, from, idx.k, lo, hi);
-                lists[((uint32_t)c << 31) | lo].push_back((uint16_t)((gene << 15) | (t << 5) | o));
+                classkeys[((uint32_t)c << 31) | lo] |= 1u << o;
             }
+            pack64(s, 0, lmin, lo, hi);
+            auto key = std::make_pair(lo, hi);
+            auto it = prefixes.find(key);
+            if (it == prefixes.end()) prefixes[key] = ((uint32_t)gene << 8) | (uint32_t)t;
+            else if ((it->second >> 8) != (uint32_t)gene) return false;  // a V and a J tag share a prefix: no union index
         }
     }
-    std::vector<std::pair<uint32_t, uint32_t>> items;
-    std::vector<uint16_t> pairs;
-    for (auto& kv : lists) {
-        if (kv.second.size() > 15) return false;
-        items.emplace_back(kv.first, (uint32_t)(pairs.size() << 4) | (uint32_t)kv.second.size());
-        for (uint16_t e : kv.second) pairs.push_back(e);
+    {
+        std::vector<std::pair<uint32_t, uint32_t>> items(classkeys.begin(), classkeys.end());
+        Cuckoo ck;
+        if (!build_cuckoo(ck, items)) return false;
+        idx.c1 = ck.c1; idx.c2 = ck.c2; idx.shift = 32 - ck.bits;
+        const size_t slots = (size_t)1 << ck.bits;
+        idx.ck_off = b.reserve(2 * slots);
+        for (size_t i = 0; i < slots; i++) {
+            b.w[idx.ck_off + 2 * i] = ck.used[i] ? ck.key[i] : DCB_HASH_EMPTY;
+            b.w[idx.ck_off + 2 * i + 1] = ck.used[i] ? ck.val[i] : 0u;
+        }
     }
-    Cuckoo ck;
-    if (!build_cuckoo(ck, items)) return false;
-    idx.c1 = ck.c1; idx.c2 = ck.c2; idx.shift = 32 - ck.bits;
-    const size_t slots = (size_t)1 << ck.bits;
-    idx.ck_off = b.reserve(2 * slots);
-    for (size_t i = 0; i < slots; i++) {
-        b.w[idx.ck_off + 2 * i] = ck.used[i] ? ck.key[i] : DCB_HASH_EMPTY;
-        b.w[idx.ck_off + 2 * i + 1] = ck.used[i] ? ck.val[i] : 0u;
+    {
+        std::vector<std::pair<uint32_t, uint32_t>> items;
+        std::map<uint32_t, int> folded;
+        for (auto& kv : prefixes) {
+            uint32_t f = dcb_fold64(kv.first.first, kv.first.second);
+            // lookups pick the slot by fingerprint, so the fingerprints of distinct prefixes must differ
+            if (folded.count(DCB_TK_FP(f))) return false;
+            folded[DCB_TK_FP(f)] = 1;
+            items.emplace_back(f, kv.second);
+        }
+        Cuckoo ck;
+        if (!build_cuckoo(ck, items)) return false;
+        idx.t1 = ck.c1; idx.t2 = ck.c2; idx.tshift = 32 - ck.bits;
+        const size_t slots = (size_t)1 << ck.bits;
+        idx.tk_off = b.reserve(slots);
+        for (size_t i = 0; i < slots; i++)
+            b.w[idx.tk_off + i] = ck.used[i] ? (DCB_TK_FP(ck.key[i]) | ck.val[i]) : DCB_HASH_EMPTY;
     }
-    idx.pairs_off = b.reserve((pairs.size() + 1) / 2 + 1);
-    std::memcpy(&b.w[idx.pairs_off], pairs.data(), pairs.size() * 2);
     b.align4();
     size_t words = ((size_t)1 << (2 * idx.q)) / 32;
     if (words < 4) words = 4;
@@ -260,21 +277,24 @@ dcb_tagset* dcb_tagset_build(const char* const* tags, const int32_t* jumps, cons
         DcbGene g;
         std::memset(&g, 0, sizeof(g));
         g.n_tags = n; g.split = half_split; g.is_v = is_v; g.lmin = lmin;
-        g.tag_off = b.reserve(8 * (size_t)n);
+        g.tag_off = b.reserve(DCB_TAG_WORDS * (size_t)n);
         std::vector<DcbTag> trec(n);
         for (int i = 0; i < n; i++) {
             DcbTag& t = trec[i];
             std::memset(&t, 0, sizeof(t));
             pack64(full[i], 0, full[i].size(), t.bits_lo, t.bits_hi);
             t.len = (uint8_t)full[i].size();
+            {
+                const uint64_t m = full[i].size() >= 32 ? ~0ull : ((1ull << (2 * full[i].size())) - 1ull);
+                t.mask_lo = (uint32_t)m; t.mask_hi = (uint32_t)(m >> 32);
+            }
             t.jump = (int16_t)jumps[i];
             t.region_len = (int16_t)reg[i].size();
             t.edge_ok = reg[i].size() >= 32;
             if (t.edge_ok) pack64(reg[i], is_v ? reg[i].size() - 32 : 0, 32, t.edge_lo, t.edge_hi);
-            int f1 = (int)(std::find(h1.begin(), h1.end(), h1[i]) - h1.begin());
-            int f2 = (int)(std::find(h2.begin(), h2.end(), h2[i]) - h2.begin());
-            t.h1_first_len = (uint8_t)full[f1].size();
-            t.h2_first_len = (uint8_t)full[f2].size();
+            t.next_same_prefix = 0xFF;
+            for (int k2 = i + 1; k2 < n; k2++)
+                if (full[k2].compare(0, lmin, full[i], 0, lmin) == 0) { t.next_same_prefix = (uint8_t)k2; break; }
         }
         if (which == 0) {
             build_kwset(b, g.full, full);
