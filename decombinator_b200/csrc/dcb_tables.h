@@ -102,10 +102,11 @@ struct DcbSeedIndex {
 #define DCB_IDX_K0(lmin, q) (((lmin) - DCB_IDX_SPAN(lmin, q) + 1) < 15 ? ((lmin) - DCB_IDX_SPAN(lmin, q) + 1) : 15)
 #define DCB_IDX_K(lmin, q) ((DCB_IDX_WLEAD(lmin, q) + DCB_IDX_K0(lmin, q)) > 32 ? (32 - DCB_IDX_WLEAD(lmin, q)) : DCB_IDX_K0(lmin, q))
 
-// Seed bitmap addressing: the LOW 2q-5 bits of a q-mer key select the word, the high 5 bits the bit, so the
-// word address is a mask of the already-shifted read window and the bit index needs no masking.
-#define DCB_SEEDMAP_WORD(key, q) ((key) & ((1u << (2 * (q) - 5)) - 1u))
-#define DCB_SEEDMAP_BIT(key, q) ((key) >> (2 * (q) - 5))
+// Seed bitmap addressing: the low 5 bits of a q-mer key select the bit -- stored MSB-first, so that
+// `word << (key & 31)` moves it to bit 31, from where one funnel shift appends it to a hit mask -- and the
+// remaining high bits select the word.
+#define DCB_SEEDMAP_WORD(key, q) ((key) >> 5)
+#define DCB_SEEDMAP_BIT(key, q) (31u - ((key) & 31u))
 
 #if defined(__CUDACC__)
 #define DCB_HD __host__ __device__ __forceinline__

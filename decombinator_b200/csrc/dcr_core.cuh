@@ -461,8 +461,8 @@ DCB_HD void fast_verify_hit(const ReadView& r, const SeedIdxView& ix, int p, con
         const bool in_window = ix.lmin - o <= 32 - ix.wlead;   // the lmin-prefix lies inside the window in registers
         if (in_window) {
             const int sh = 2 * (ix.wlead - o);
-            lo = win_lo_shr(wlo, whi, sh);
-            hi = win_hi_shr(whi, sh);
+            if (ix.wlead < 16) { lo = DCB_FUNNEL_R(wlo, whi, sh); hi = whi >> sh; }  // sh < 32
+            else { lo = win_lo_shr(wlo, whi, sh); hi = win_hi_shr(whi, sh); }
         } else {
             rd_win32(r, P, lo, hi);
         }

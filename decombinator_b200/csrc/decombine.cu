@@ -104,7 +104,7 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* a, uint32_t 
     return lo;
 }
 
-static constexpr int kExactThreads = 256;   // upper bounds; long reads launch narrower blocks (shared memory)
+static constexpr int kExactThreads = 512;   // upper bounds; long reads launch narrower blocks (shared memory)
 static constexpr int kGeneralThreads = 128;
 
 // Shared-memory carve-up common to the kernels: [table 0..3][per-thread columns][counters][mbarrier]
@@ -210,39 +210,39 @@ dcb_exact_kernel(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_res
 template <int NW, int Q, int S>
 struct SeedScan {
     static constexpr int NPOS = (16 * NW - Q) / S + 1;
+    static constexpr int G0 = NPOS < 32 ? NPOS : 32;   // probes collected in the first / second hit word
+    static constexpr int G1 = NPOS - G0;
     static_assert(NPOS <= 64, "at most 64 sampled positions");
-    // probe the bitmap at every sampled position; bit i of (lo, hi) <-> position i * S
+    // Probe the bitmap at every sampled position.  Probe i of a group of G lands in bit G-1-i of its hit word
+    // (each probe shifts the word left by one), so the EARLIEST position is the HIGHEST set bit.
     static __device__ __forceinline__ void run(const uint32_t (&w)[NW], const uint32_t* __restrict__ bitmap,
-                                               uint32_t& lo, uint32_t& hi) {
-        lo = 0; hi = 0;
-        constexpr uint32_t KMASK = (Q >= 16) ? 0xFFFFFFFFu : ((1u << (2 * Q)) - 1u);
-        constexpr int WBITS = 2 * Q - 5;
+                                               uint32_t& h0, uint32_t& h1) {
+        h0 = 0; h1 = 0;
+        constexpr uint32_t WMASK = (1u << (2 * Q - 5)) - 1u;
 #pragma unroll
         for (int i = 0; i < NPOS; i++) {
             const int p = i * S, a = p >> 4, sh = (p & 15) * 2;
-            uint32_t win;
+            uint32_t win;   // at least the 2Q key bits of the q-mer at p (higher bits are don't-care)
             if (sh == 0) win = w[a];
             else if (sh + 2 * Q <= 32 || a + 1 >= NW) win = w[a] >> sh;
             else win = __funnelshift_r(w[a], w[a + 1], sh);
-            const uint32_t key = win & KMASK;
-            const uint32_t word = bitmap[key & ((1u << WBITS) - 1u)];
-            const uint32_t bit = (word >> (key >> WBITS)) & 1u;
-            if (i < 32) lo |= bit << i; else hi |= bit << (i - 32);
+            const uint32_t word = bitmap[(win >> 5) & WMASK];
+            const uint32_t top = __funnelshift_l(0u, word, win);          // word << (key & 31): the key's bit -> bit 31
+            if (i < 32) h0 = __funnelshift_l(top, h0, 1); else h1 = __funnelshift_l(top, h1, 1);
         }
     }
-    // positions whose q-mer lies inside a read of n bases
-    static __device__ __forceinline__ void clip(int n, uint32_t& lo, uint32_t& hi) {
+    // keep the probes whose q-mer lies inside a read of n bases
+    static __device__ __forceinline__ void clip(int n, uint32_t& h0, uint32_t& h1) {
         const int nvalid = n >= Q ? (n - Q) / S + 1 : 0;
-        if (nvalid < 32) { lo &= (1u << nvalid) - 1u; hi = 0; }
-        else if (nvalid < 64) hi &= (1u << (nvalid - 32)) - 1u;
+        if (nvalid < G0) { h0 &= ~((1u << (G0 - nvalid)) - 1u); h1 = 0; }
+        else if (G1 > 0 && nvalid - G0 < G1) h1 &= ~((1u << (G1 - (nvalid - G0))) - 1u);
+    }
+    // earliest remaining probe index (and remove it); call only while (h0 | h1) != 0
+    static __device__ __forceinline__ int pop(uint32_t& h0, uint32_t& h1) {
+        if (h0) { const int b = 31 - __clz(h0); h0 &= ~(1u << b); return G0 - 1 - b; }
+        const int b = 31 - __clz(h1); h1 &= ~(1u << b); return G0 + G1 - 1 - b;
     }
 };
-
-__device__ __forceinline__ int pop_hit(uint32_t& lo, uint32_t& hi) {
-    int i;
-    if (lo) { i = __ffs(lo) - 1; lo &= lo - 1; } else { i = 32 + __ffs(hi) - 1; hi &= hi - 1; }
-    return i;
-}
 
 template <int NW, int QV, int SV, int QJ, int SJ, bool UNION>
 __global__ void __launch_bounds__(kExactThreads)
@@ -302,12 +302,12 @@ dcb_exact_kernel_spec(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dc
                 SeedScan<NW, QV, SV>::run(w, vix.seedmap, lo, hi);
                 SeedScan<NW, QV, SV>::clip(r.n, lo, hi);
                 while ((lo | hi) && vh.count < 2)
-                    fast_verify_hit(r, vix, pop_hit(lo, hi) * SV, vtags, UNION ? jtags : nullptr, vh, jh);
+                    fast_verify_hit(r, vix, SeedScan<NW, QV, SV>::pop(lo, hi) * SV, vtags, UNION ? jtags : nullptr, vh, jh);
                 if (!UNION && vh.count == 1) {
                     SeedScan<NW, QJ, SJ>::run(w, jix.seedmap, lo, hi);
                     SeedScan<NW, QJ, SJ>::clip(r.n, lo, hi);
                     while ((lo | hi) && jh.count < 2)
-                        fast_verify_hit(r, jix, pop_hit(lo, hi) * SJ, nullptr, jtags, vh, jh);
+                        fast_verify_hit(r, jix, SeedScan<NW, QJ, SJ>::pop(lo, hi) * SJ, nullptr, jtags, vh, jh);
                 }
                 action = dcr_fast_from_hits(r, vcore, jcore, vh, jh, prm, both_frames, out, L.cnt);
             }
