@@ -19,7 +19,7 @@ struct dcb_tagset {
 
 // Seed index over one gene (other pointer null) or over both genes of a chain (equal lmin).
 bool dcb_build_seed_index(const std::vector<std::string>* gene_v, const std::vector<std::string>* gene_j, int lmin,
-                          std::vector<uint32_t>& out);
+                          int wbits, std::vector<uint32_t>& out);
 
 #if defined(__GNUC__)
 __attribute__((format(printf, 1, 2)))

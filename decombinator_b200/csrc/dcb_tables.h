@@ -70,43 +70,74 @@ struct DcbGene {
 
 // Seed index of the exact-tag fast path (one per gene, or ONE for both genes of a chain when their seed
 // geometry agrees).  Every occurrence of a full tag (length >= lmin) contains a q-mer that starts at a multiple
-// of stride = lmin-q+1 at tag offset o <= lmin-q, so only every stride-th position is probed:
-//   1. seed bitmap (4^q bits): is the q-mer at the sampled position p part of any tag at an offset <= lmin-q?
-//   2. on a hit, the unknown offset o falls in class c = o / span (two classes); the k-mer at [p - c*span, +k)
-//      then lies inside the tag for every o of that class, and a 2-choice cuckoo table (two slot reads, no
-//      probing loop) maps (c, k-mer) to the set of offsets it occurs at -- almost always exactly one;
-//   3. for each offset the tag would start at P = p - o: its lmin-prefix is looked up in a second cuckoo table
-//      (all tags of the index, keyed on the folded prefix) and the whole tag is compared with the read.
+// of stride = max_off + 1 at a tag offset o <= max_off = min(lmin - q, 11), so only every stride-th position of
+// a read is probed:
+//   1. seed filter: a one-hash Bloom filter over the indexed q-mers (2^wbits words).  (Two bits per q-mer were
+//      measured: 3 more instructions per probe bought 7 % fewer verification trips -- no net gain -- because most
+//      extra hits are real q-mers of homologous tags, not filter noise.)  The kernels replicate it
+//      32x in shared memory, one private copy per bank, so the 32 lanes of a warp -- each probing for its own
+//      read -- never conflict: a probe is ONE shared-memory wavefront.
+//   2. on a filter hit the unknown offset o falls in class c = o / span (two classes); the k-mer at
+//      [p - c*span, +k) then lies inside the tag for every o of that class, and a 2-choice cuckoo table (two slot
+//      reads per class, no probing loop) maps (c, k-mer) to the set of offsets it occurs at -- almost always one;
+//   3. an offset o puts the tag start at P = p - o: the lmin-prefix at P is looked up in a perfect-hash table
+//      (one slot read) that names the one tag with that prefix;
+//   4. the whole tag (16-byte record: bits, mask, length) is compared with the read.
+// Tags of both genes are numbered together ("ctag"): V tags first, then J tags.
 struct DcbSeedIndex {
     int32_t q, stride;
-    int32_t max_off;             // lmin - q: largest indexed tag offset
-    int32_t k, span;             // class key length (<= 15 bases) and offsets per class
+    int32_t max_off;             // largest indexed tag offset
     int32_t wlead;               // the verification window starts at p - wlead (max_off + 1)
-    int32_t ck_off;              // 2^bits slots of 2 words: [class << 31 | key  (DCB_HASH_EMPTY if free), mask of offsets]
-    uint32_t c1, c2;             // h(x) = (x * c) >> shift
-    int32_t shift;
-    int32_t tk_off;              // 2^bits slots: fingerprint << 9 | gene << 8 | tag  (gene 0 = V, 1 = J) or DCB_HASH_EMPTY;
-                                 // fingerprint = top 23 bits of the folded prefix
-    uint32_t t1, t2;             // h(f) = (f * t) >> tshift, f = dcb_fold64(lmin-prefix)
+    int32_t lmin;                // shortest tag of the index
+    int32_t wbits;               // log2(words) of the seed filter
+    uint32_t bmul;               // word = (window * bmul) >> (32 - wbits); bmul = odd << (32 - 2q), so only the q-mer's
+                                 // own 2q bits reach the product;  bit = 31 - (q-mer & 31)  (MSB-first)
+    int32_t k, span;             // class key length (<= 15 bases) and offsets per class
+    int32_t ck_off;              // 2^cbits slots: fingerprint << 12 | offset set.  For key x = class << 30 | k-mer:
+    uint32_t c1, c2;             // slots (x * c1) >> cshift and (x * c2) >> cshift, fingerprint DCB_CK_FP(x * c1);
+    int32_t cshift;              // a free slot is 0 (empty offset set); a lookup ORs the sets of BOTH slots whose
+                                 // fingerprint matches, so a chance fingerprint match only adds offsets to try
+    int32_t tk_off;              // 2^tbits 16-bit slots of a PERFECT hash over the lmin-prefixes: the first ctag with that
+                                 // prefix, 0x1FF = free;  slot = (dcb_fold64(prefix) * t1) >> tshift.  No fingerprint: the
+    uint32_t t1;                 // tag found is compared with the read as a whole anyway.
     int32_t tshift;
-    int32_t seedmap_off;         // the bitmap comes last
+    int32_t utag_off;            // DcbUTag[n_tags]
+    int32_t n_v, n_tags;         // ctag >= n_v is J tag ctag - n_v
+    int32_t chain_off;           // 0, or uint16[n_tags]: next tag sharing this tag's lmin-prefix (0x1FF = none)
+    int32_t head_words;          // words before the filter (what the specialised kernels stage verbatim)
+    int32_t bloom_off;           // the filter comes last
     int32_t n_words;
 };
 
+#define DCB_CK_FP(prod) (((prod) >> 8) & 0xFFFFFu)               // fingerprint bits of the first-choice product
+#define DCB_CK_OFFMASK(e) ((e) & 0xFFFu)
+
+// Compact tag record of the fast path (16 bytes, one 128-bit load).
+struct alignas(16) DcbUTag {
+    uint32_t bits_lo, bits_hi;   // packed tag
+    uint32_t mask_lo;            // low word of the 2*len-bit mask
+    uint32_t mask_hi_len;        // high word of the mask (24 bits: len <= 28) | len << 24
+};
+#define DCB_FAST_MAX_TAG_LEN 28
+// filter sizes the library builds: 2^10 words when one index serves both genes, 2^9 words per gene otherwise
+// (32 private copies of all filters of a chain must fit in shared memory: 128 KB either way)
+#define DCB_WBITS_UNION 10
+#define DCB_WBITS_SINGLE 9
+
 // Geometry of a seed index as a function of (lmin, q): shared by the host builder and the kernels, whose
 // specialisations evaluate these at compile time.
-#define DCB_IDX_STRIDE(lmin, q) ((lmin) - (q) + 1)
-#define DCB_IDX_MAXOFF(lmin, q) ((lmin) - (q))
-#define DCB_IDX_SPAN(lmin, q) ((DCB_IDX_MAXOFF(lmin, q) + 2) / 2)
+#define DCB_IDX_MAXOFF(lmin, q) (((lmin) - (q)) < 11 ? ((lmin) - (q)) : 11)
+#define DCB_IDX_STRIDE(lmin, q) (DCB_IDX_MAXOFF(lmin, q) + 1)
 #define DCB_IDX_WLEAD(lmin, q) (DCB_IDX_MAXOFF(lmin, q) + 1)
+#define DCB_IDX_SPAN(lmin, q) ((DCB_IDX_MAXOFF(lmin, q) + 2) / 2)
 #define DCB_IDX_K0(lmin, q) (((lmin) - DCB_IDX_SPAN(lmin, q) + 1) < 15 ? ((lmin) - DCB_IDX_SPAN(lmin, q) + 1) : 15)
 #define DCB_IDX_K(lmin, q) ((DCB_IDX_WLEAD(lmin, q) + DCB_IDX_K0(lmin, q)) > 32 ? (32 - DCB_IDX_WLEAD(lmin, q)) : DCB_IDX_K0(lmin, q))
 
-// Seed bitmap addressing: the low 5 bits of a q-mer key select the bit -- stored MSB-first, so that
-// `word << (key & 31)` moves it to bit 31, from where one funnel shift appends it to a hit mask -- and the
-// remaining high bits select the word.
-#define DCB_SEEDMAP_WORD(key, q) ((key) >> 5)
-#define DCB_SEEDMAP_BIT(key, q) (31u - ((key) & 31u))
+// Seed filter addressing: the low 5 bits of a q-mer select the bit -- stored MSB-first, so that
+// `word << (q-mer & 31)` moves it to bit 31, from where one funnel shift appends it to a hit mask.
+#define DCB_BLOOM_MUL(q) ((0x2C1B3C6Du | 1u) << (32 - 2 * (q)))
+#define DCB_BLOOM_BIT(key) (31u - ((key) & 31u))
+#define DCB_BLOOM_WORD(win, bmul, wbits) (((uint32_t)(win) * (bmul)) >> (32 - (wbits)))
 
 #if defined(__CUDACC__)
 #define DCB_HD __host__ __device__ __forceinline__
@@ -118,7 +149,6 @@ DCB_HD uint32_t dcb_fold64(uint32_t lo, uint32_t hi) {
     uint32_t k = lo * 0x9E3779B1u + hi * 0x85EBCA77u;
     return k ^ (k >> 13);
 }
-#define DCB_TK_FP(f) ((f) & 0xFFFFFE00u)   // the fingerprint bits of a tag-prefix slot
 DCB_HD uint32_t dcb_hash32(uint32_t k) {
     k *= 0x9E3779B1u;
     return k ^ (k >> 15);

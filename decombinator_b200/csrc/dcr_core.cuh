@@ -336,14 +336,17 @@ struct DcrParams { int allow_ns, lenthreshold; };
 
 // The four filters and the result of dcr() (decombine.py:553-581), shared by both kernels.
 // Returns -1 when the rearrangement is accepted (out filled), else the counter the reference bumps.
-DCB_HD int dcr_finish(const ReadView& r, const DcbTag& vt, const DcbTag& jt, const VJ& v, const VJ& j,
+DCB_HD int dcr_finish(const ReadView& r, int vjump, int vlen, int jjump, int jlen, const VJ& v, const VJ& j,
                       const DcrParams& prm, dcb_result& out) {
-    Span it = py_slice(r.n, v.seqpos, j.seqpos);
-    if (!prm.allow_ns && r.e1 > r.e0 && rd_has_N(r, it.a, it.b)) return DCB_C_dcrfilter_intertagN;       // :553-556
+    if (!prm.allow_ns && r.e1 > r.e0) {
+        Span it = py_slice(r.n, v.seqpos, j.seqpos);
+        if (rd_has_N(r, it.a, it.b)) return DCB_C_dcrfilter_intertagN;                                   // :553-556
+    }
     if ((v.seqpos - j.seqpos) >= prm.lenthreshold) return DCB_C_dcrfilter_toolong_intertag;              // :557-560
-    if (v.dels > ((int)vt.jump - (int)vt.len) || j.dels > (int)jt.jump) return DCB_C_dcrfilter_imposs_deletion;  // :561-565
-    if ((v.seqpos + (int)vt.len) > (j.seqpos + (int)jt.len)) return DCB_C_dcrfilter_tag_overlap;         // :566-569
+    if (v.dels > (vjump - vlen) || j.dels > jjump) return DCB_C_dcrfilter_imposs_deletion;               // :561-565
+    if ((v.seqpos + vlen) > (j.seqpos + jlen)) return DCB_C_dcrfilter_tag_overlap;                       // :566-569
     out.status = 1;                                                                                      // :572-581
+    out.frame = 0;
     out.v = (uint8_t)v.idx; out.j = (uint8_t)j.idx;
     out.vdel = (uint16_t)v.dels; out.jdel = (uint16_t)j.dels;
     out.ins_start = (uint16_t)(v.pos + 1); out.ins_end = (uint16_t)j.pos;
@@ -362,7 +365,9 @@ DCB_HD bool dcr_general(const ReadView& r, const uint32_t* vblob, const uint32_t
     }
     const DcbGene& gv = *reinterpret_cast<const DcbGene*>(vblob);
     const DcbGene& gj = *reinterpret_cast<const DcbGene*>(jblob);
-    int c = dcr_finish(r, gene_tag(vblob, gv, v.idx), gene_tag(jblob, gj, j.idx), v, j, prm, out);
+    const DcbTag& vt = gene_tag(vblob, gv, v.idx);
+    const DcbTag& jt = gene_tag(jblob, gj, j.idx);
+    int c = dcr_finish(r, vt.jump, vt.len, jt.jump, jt.len, v, j, prm, out);
     if (c >= 0) { DCB_COUNT(C, c); return false; }
     return true;
 }
@@ -397,95 +402,81 @@ DCB_HD int fullhit_pos(const FullHit& fh) { return (int)(fh.code & 0xFFFFu); }
 // Record one confirmed full-tag occurrence (the same one may be reported twice).
 DCB_HD void fullhit_add(FullHit& fh, int tag, int pos) {
     const uint32_t code = ((uint32_t)tag << 16) | (uint32_t)pos;
-    if (fh.count == 0) { fh.code = code; fh.count = 1; }
-    else if (code != fh.code) fh.count = 2;
-}
-
-// 64-bit window helpers (two 32-bit halves: the device has no native 64-bit shifter)
-DCB_HD uint32_t win_lo_shr(uint32_t lo, uint32_t hi, int bits) {  // low word of (hi:lo) >> bits, bits in [0, 63]
-    return bits >= 32 ? (hi >> (bits - 32)) : DCB_FUNNEL_R(lo, hi, bits);
-}
-DCB_HD uint32_t win_hi_shr(uint32_t hi, int bits) {               // high word of (hi:lo) >> bits
-    return bits >= 32 ? 0u : (hi >> bits);
+    const bool first = fh.count == 0;
+    fh.count = first ? 1 : (code != fh.code ? 2 : fh.count);
+    fh.code = first ? code : fh.code;
 }
 
 // A DcbSeedIndex with its hot fields in registers.  The specialised kernels overwrite the geometry fields with
 // compile-time constants, which the optimiser then folds through the (force-inlined) functions below.
 struct SeedIdxView {
     const uint32_t* ck;        // class-key cuckoo slots
-    const uint32_t* tk;        // tag-prefix cuckoo slots
-    const uint32_t* seedmap;   // seed bitmap
-    uint32_t c1, c2, t1, t2;
-    int shift, tshift;
-    int q, stride, lmin, wlead, span, k;
+    const uint16_t* tk;        // tag-prefix perfect-hash slots
+    const DcbUTag* utag;       // compact tag records
+    const uint16_t* chain;     // successor of a tag among those sharing its lmin-prefix, or null
+    const uint32_t* bloom;     // compact seed filter
+    uint32_t c1, c2, t1, bmul;
+    int cshift, tshift, wbits;
+    int q, stride, lmin, wlead, span, k, n_v;
 };
 DCB_HD SeedIdxView seed_idx_view(const uint32_t* ib) {
     const DcbSeedIndex& ix = *reinterpret_cast<const DcbSeedIndex*>(ib);
     SeedIdxView v;
     v.ck = ib + ix.ck_off;
-    v.tk = ib + ix.tk_off;
-    v.seedmap = ib + ix.seedmap_off;
-    v.c1 = ix.c1; v.c2 = ix.c2; v.shift = ix.shift;
-    v.t1 = ix.t1; v.t2 = ix.t2; v.tshift = ix.tshift;
-    v.q = ix.q; v.stride = ix.stride; v.lmin = ix.stride + ix.q - 1;
-    v.wlead = ix.wlead; v.span = ix.span; v.k = ix.k;
+    v.tk = reinterpret_cast<const uint16_t*>(ib + ix.tk_off);
+    v.utag = reinterpret_cast<const DcbUTag*>(ib + ix.utag_off);
+    v.chain = ix.chain_off ? reinterpret_cast<const uint16_t*>(ib + ix.chain_off) : nullptr;
+    v.bloom = ib + ix.bloom_off;
+    v.c1 = ix.c1; v.c2 = ix.c2; v.cshift = ix.cshift;
+    v.t1 = ix.t1; v.tshift = ix.tshift;
+    v.bmul = ix.bmul; v.wbits = ix.wbits;
+    v.q = ix.q; v.stride = ix.stride; v.lmin = ix.lmin; v.wlead = ix.wlead; v.span = ix.span; v.k = ix.k; v.n_v = ix.n_v;
     return v;
 }
 DCB_HD const DcbTag* gene_tags(const uint32_t* core) {
     return core ? reinterpret_cast<const DcbTag*>(core + reinterpret_cast<const DcbGene*>(core)->tag_off) : nullptr;
 }
 
-// Confirm the candidates behind one seed hit at sampled position p: two class-key lookups give the possible tag
-// offsets (almost always one); each offset selects at most one tag through the fingerprinted tag-prefix table,
-// and that tag (plus the rare ones chained to it) is compared as a whole.
-DCB_HD void fast_verify_hit(const ReadView& r, const SeedIdxView& ix, int p, const DcbTag* vtags, const DcbTag* jtags,
-                            FullHit& vh, FullHit& jh) {
-    uint32_t wlo, whi;                       // 32 bases starting at p - wlead
-    rd_win32(r, p - ix.wlead, wlo, whi);
-    const uint32_t kmask = mask2(ix.k);
+// Class-key lookup for a filter hit at sampled position p; (wlo, whi) are the 32 bases starting at p - wlead.
+// Returns the set of candidate offsets (bit o <=> a tag may start at p - o); empty for a filter false positive.
+DCB_HD uint32_t fast_class_lookup(const SeedIdxView& ix, uint32_t wlo, uint32_t whi) {
     uint32_t offs = 0;
+    const uint32_t kmask = mask2(ix.k);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
     for (int c = 0; c < 2; c++) {
-        const uint32_t key = ((uint32_t)c << 31) | (win_lo_shr(wlo, whi, 2 * (ix.wlead - c * ix.span)) & kmask);
-        const uint32_t s1 = (key * ix.c1) >> ix.shift, s2 = (key * ix.c2) >> ix.shift;
-        const uint32_t k1 = ix.ck[2 * s1], v1 = ix.ck[2 * s1 + 1];
-        const uint32_t k2 = ix.ck[2 * s2], v2 = ix.ck[2 * s2 + 1];
-        offs |= k1 == key ? v1 : (k2 == key ? v2 : 0u);
+        const int sh = 2 * (ix.wlead - c * ix.span);   // < 32: wlead <= 12
+        const uint32_t x = ((uint32_t)c << 30) | (DCB_FUNNEL_R(wlo, whi, sh) & kmask);
+        const uint32_t prod = x * ix.c1, fp = DCB_CK_FP(prod);
+        const uint32_t e1 = ix.ck[prod >> ix.cshift], e2 = ix.ck[(x * ix.c2) >> ix.cshift];
+        offs |= ((e1 >> 12) == fp ? e1 : 0u) | ((e2 >> 12) == fp ? e2 : 0u);
     }
-    const uint32_t plo_mask = mask2(ix.lmin), phi_mask = ix.lmin > 16 ? mask2(ix.lmin - 16) : 0u;
-    while (offs) {
-        const int o = DCB_FFS(offs) - 1;
-        offs &= offs - 1;
-        const int P = p - o;
-        if (P < 0 || P + ix.lmin > r.n) continue;
-        uint32_t lo, hi;
-        const bool in_window = ix.lmin - o <= 32 - ix.wlead;   // the lmin-prefix lies inside the window in registers
-        if (in_window) {
-            const int sh = 2 * (ix.wlead - o);
-            if (ix.wlead < 16) { lo = DCB_FUNNEL_R(wlo, whi, sh); hi = whi >> sh; }  // sh < 32
-            else { lo = win_lo_shr(wlo, whi, sh); hi = win_hi_shr(whi, sh); }
-        } else {
-            rd_win32(r, P, lo, hi);
-        }
-        const uint32_t f = dcb_fold64(lo & plo_mask, hi & phi_mask);
-        const uint32_t slot1 = ix.tk[(f * ix.t1) >> ix.tshift], slot2 = ix.tk[(f * ix.t2) >> ix.tshift];
-        // a prefix lives in at most one of its two slots: pick by fingerprint (EMPTY never matches: tag field 0xFF)
-        const uint32_t fp = DCB_TK_FP(f);
-        const uint32_t slot = DCB_TK_FP(slot1) == fp ? slot1 : slot2;
-        if (DCB_TK_FP(slot) != fp || (slot & 0xFFu) == 0xFFu) continue;
-        const int is_j = (int)((slot >> 8) & 1u);
-        const DcbTag* tags = is_j ? jtags : vtags;
-        if (!tags) continue;
-        uint32_t id = slot & 0xFFu;
-        do {
-            const DcbTag& t = tags[id];
-            const int L = t.len;
-            if (P + L <= r.n) {
-                uint32_t tlo = lo, thi = hi;
-                if (!in_window || L - o > 32 - ix.wlead) rd_win32(r, P, tlo, thi);   // long tag: past the register window
-                if (!(((tlo ^ t.bits_lo) & t.mask_lo) | ((thi ^ t.bits_hi) & t.mask_hi))) fullhit_add(is_j ? jh : vh, (int)id, P);
+    return DCB_CK_OFFMASK(offs);
+}
+
+// One candidate offset o of a seed hit at p: the perfect-hash prefix table names the tag whose lmin-prefix starts at
+// P = p - o; it (and the rare tags chained to it) is compared with the read as a whole and recorded.
+DCB_HD void fast_check_offset(const ReadView& r, const SeedIdxView& ix, int p, int o, uint32_t wlo, uint32_t whi,
+                              FullHit& vh, FullHit& jh) {
+    const int P = p - o;
+    const int sh = 2 * (ix.wlead - o);                 // 2 <= sh <= 2 * wlead <= 24
+    const uint32_t lo = DCB_FUNNEL_R(wlo, whi, sh), hi = whi >> sh;   // the 32 - (wlead - o) >= 20 bases from P on
+    const uint32_t f = dcb_fold64(lo & mask2(ix.lmin), ix.lmin > 16 ? (hi & mask2(ix.lmin - 16)) : 0u);
+    uint32_t ctag = ix.tk[(f * ix.t1) >> ix.tshift];
+    if (P < 0) return;
+    while (ctag != 0x1FFu) {
+        const DcbUTag u = ix.utag[ctag];
+        const int L = (int)(u.mask_hi_len >> 24);
+        if (P + L <= r.n) {
+            uint32_t tlo = lo, thi = hi;
+            if (ix.wlead - o + L > 32) rd_win32(r, P, tlo, thi);   // long tag: past the window in registers
+            if (!(((tlo ^ u.bits_lo) & u.mask_lo) | ((thi ^ u.bits_hi) & (u.mask_hi_len & 0x00FFFFFFu)))) {
+                if ((int)ctag >= ix.n_v) fullhit_add(jh, (int)ctag - ix.n_v, P);
+                else fullhit_add(vh, (int)ctag, P);
             }
-            id = t.next_same_prefix;
-        } while (id != 0xFFu);
+        }
+        ctag = ix.chain ? ix.chain[ctag] : 0x1FFu;
     }
 }
 
@@ -501,72 +492,98 @@ DCB_HD void run10(uint32_t xlo, uint32_t xhi, uint32_t& rlo, uint32_t& rhi) {
     rlo = (uint32_t)r10; rhi = (uint32_t)(r10 >> 32);
 }
 
+// The second 16 bytes of a DcbTag: all the exact-tag path needs after the match itself, in one 128-bit load.
+struct alignas(16) DcbTagFin {
+    uint32_t edge_lo, edge_hi;
+    int16_t jump, region_len;
+    uint8_t len, edge_ok, next_same_prefix, pad8;
+};
+DCB_HD DcbTagFin tag_fin(const DcbTag* tags, int k) {
+    return *reinterpret_cast<const DcbTagFin*>(reinterpret_cast<const uint32_t*>(tags + k) + 4);
+}
+
+// 32 bases from p.  PADDED: the caller guarantees -16 <= p and (p >> 4) + 2 <= nw with a zero row before and behind the
+// read's words (the specialised kernel's shared-memory columns), so no bounds checks are needed.
+template <bool PADDED>
+DCB_HD void rd_win32x(const ReadView& r, int p, uint32_t& lo, uint32_t& hi) {
+    if (PADDED) {
+        const uint32_t* c0 = r.w + (p >> 4) * r.stride;
+        const uint32_t a = c0[0], b = c0[r.stride], c = c0[2 * r.stride];
+        const int sh = (p & 15) * 2;
+        lo = DCB_FUNNEL_R(a, b, sh);
+        hi = DCB_FUNNEL_R(b, c, sh);
+    } else {
+        rd_win32(r, p, lo, hi);
+    }
+}
+
 // Fast V: exactly the interior case of get_v_deletions (decombine.py:749-785).  Returns
-//   1 handled (out filled or a counter bumped and *fail set), 0 defer to the general kernel.
-DCB_HD int fast_v_deletions(const ReadView& r, const DcbTag& t, int temp_end_v, int& end_v, int& dels) {
+//   1 handled (end_v / dels set), 0 defer to the general kernel.
+template <bool PADDED>
+DCB_HD int fast_v_deletions(const ReadView& r, const DcbTagFin& t, int temp_end_v, int& end_v, int& dels) {
     const int f0 = temp_end_v + 1;
     if (!t.edge_ok || f0 >= r.n || f0 < 32) return 0;
     uint32_t lo, hi, rl, rh;
-    rd_win32(r, f0 - 32, lo, hi);
+    rd_win32x<PADDED>(r, f0 - 32, lo, hi);
     run10(lo ^ t.edge_lo, hi ^ t.edge_hi, rl, rh);
-    // window index i <-> deletions nd = 22 - i; want the smallest nd, i.e. the highest i <= 22
-    uint64_t r10 = (((uint64_t)rh << 32) | rl) & ((1ull << 46) - 1);  // bits 2i, i <= 22
-    if (!r10) return 0;
-    const uint32_t h32 = (uint32_t)(r10 >> 32), l32 = (uint32_t)r10;
-    const int top = h32 ? 63 - DCB_CLZ(h32) : 31 - DCB_CLZ(l32);
-    int i = top >> 1;
-    dels = 22 - i;
+    // window index i <-> deletions nd = 22 - i; want the smallest nd, i.e. the highest i <= 22 (bits 2i, i <= 22)
+    rh &= (1u << 14) - 1u;
+    if (!(rl | rh)) return 0;
+    const int top = rh ? 63 - DCB_CLZ(rh) : 31 - DCB_CLZ(rl);
+    dels = 22 - (top >> 1);
     end_v = temp_end_v - dels;
     return 1;
 }
 
 // Fast J: the interior case of get_j_deletions (decombine.py:788-817).
-DCB_HD int fast_j_deletions(const ReadView& r, const DcbTag& t, int temp_start_j, int end_of_v, int& start_j, int& dels) {
+template <bool PADDED>
+DCB_HD int fast_j_deletions(const ReadView& r, const DcbTagFin& t, int temp_start_j, int end_of_v, int& start_j, int& dels) {
     if (!t.edge_ok || temp_start_j < 0) return 0;
+    if (PADDED && temp_start_j >= 16 * (r.nw - 1)) return 0;   // the window would leave the padded columns
     int pos0 = end_of_v - temp_start_j;
     if (pos0 < 0) pos0 = 0;
-    if (pos0 > 22) return 0;
-    uint32_t lo, hi, rl, rh;
-    rd_win32(r, temp_start_j, lo, hi);
-    run10(lo ^ t.edge_lo, hi ^ t.edge_hi, rl, rh);
-    uint64_t r10 = (((uint64_t)rh << 32) | rl) & ((1ull << 46) - 1);
-    r10 &= ~((1ull << (2 * pos0)) - 1);                      // pos >= pos0
     // the 10-mer must lie inside the read: temp_start_j + i + 10 <= n
     int imax = r.n - 10 - temp_start_j;
-    if (imax < 0) return 0;
-    if (imax < 22) r10 &= ((1ull << (2 * imax + 2)) - 1);
+    if (pos0 > 22 || imax < 0) return 0;
+    if (imax > 22) imax = 22;
+    uint32_t lo, hi, rl, rh;
+    rd_win32x<PADDED>(r, temp_start_j, lo, hi);
+    run10(lo ^ t.edge_lo, hi ^ t.edge_hi, rl, rh);
+    uint64_t r10 = ((uint64_t)rh << 32) | rl;
+    r10 &= ~((1ull << (2 * pos0)) - 1);                      // pos >= pos0
+    r10 &= (1ull << (2 * imax + 2)) - 1;                     // pos <= imax (<= 22)
     if (!r10) return 0;
-    int low = (uint32_t)r10 ? DCB_FFS((uint32_t)r10) - 1 : 32 + DCB_FFS((uint32_t)(r10 >> 32)) - 1;
-    int i = low >> 1;
-    dels = i;
-    start_j = temp_start_j + i;
+    const int low = (uint32_t)r10 ? DCB_FFS((uint32_t)r10) - 1 : 32 + DCB_FFS((uint32_t)(r10 >> 32)) - 1;
+    dels = low >> 1;
+    start_j = temp_start_j + dels;
     return 1;
 }
 
-// Sampled-seed search through one index over a read held in the view: probe the seed bitmap at every
+// Sampled-seed search through one index over a read held in the view: probe the seed filter at every
 // multiple of `stride`, 32 probes at a time into a hit mask, then confirm the (rare) hits in a second loop
 // so the lanes of a warp stay converged during the probes.  (The kernels have a register-resident unrolled
-// specialisation of the probing for the common slot sizes; this is the generic form.)
-DCB_HD void fast_find(const ReadView& r, const uint32_t* ib, const uint32_t* vcore, const uint32_t* jcore,
-                      FullHit& vh, FullHit& jh) {
+// specialisation of the probing, over bank-private copies of the filter; this is the generic form.)
+DCB_HD void fast_find(const ReadView& r, const uint32_t* ib, FullHit& vh, FullHit& jh, bool stop_at_two_v) {
     const SeedIdxView ix = seed_idx_view(ib);
-    const DcbTag* vtags = gene_tags(vcore);
-    const DcbTag* jtags = gene_tags(jcore);
-    const uint32_t qmask = mask2(ix.q);
     const int last = r.n - ix.q;  // last start position of a whole q-mer
     for (int base = 0; base <= last; base += 32 * ix.stride) {
         uint32_t hits = 0;
         for (int i = 0; i < 32; i++) {
             const int p = base + i * ix.stride;
             if (p > last) break;
-            const uint32_t key = rd_win16(r, p) & qmask;
-            hits |= ((ix.seedmap[DCB_SEEDMAP_WORD(key, ix.q)] >> DCB_SEEDMAP_BIT(key, ix.q)) & 1u) << i;
+            const uint32_t win = rd_win16(r, p);
+            const uint32_t word = ix.bloom[DCB_BLOOM_WORD(win, ix.bmul, ix.wbits)];
+            hits |= ((word >> DCB_BLOOM_BIT(win)) & 1u) << i;
         }
         while (hits) {
             const int i = DCB_FFS(hits) - 1;
             hits &= hits - 1;
-            fast_verify_hit(r, ix, base + i * ix.stride, vtags, jtags, vh, jh);
-            if (vcore && vh.count >= 2) return;
+            const int p = base + i * ix.stride;
+            uint32_t wlo, whi;
+            rd_win32(r, p - ix.wlead, wlo, whi);
+            for (uint32_t offs = fast_class_lookup(ix, wlo, whi); offs; offs &= offs - 1)
+                fast_check_offset(r, ix, p, DCB_FFS(offs) - 1, wlo, whi, vh, jh);
+            if (stop_at_two_v && vh.count >= 2) return;
         }
     }
 }
@@ -578,21 +595,20 @@ enum { FAST_DONE = 0, FAST_DEFER = 1 };
 // deletion walks stay in the interior.  Anything else is deferred UNCOUNTED to the general kernel,
 // except the two outcomes that are final by themselves (multiple V / multiple J matches).
 // When both_frames is set a failed first frame must be retried, so every non-success defers.
-DCB_HD int dcr_fast_from_hits(const ReadView& r, const uint32_t* vblob, const uint32_t* jblob, const FullHit& vh,
+template <bool PADDED>
+DCB_HD int dcr_fast_from_hits(const ReadView& r, const DcbTag* vtags, const DcbTag* jtags, const FullHit& vh,
                               const FullHit& jh, const DcrParams& prm, int both_frames, dcb_result& out,
                               dcb_cnt_t* C) {
-    const DcbGene& gv = *reinterpret_cast<const DcbGene*>(vblob);
-    const DcbGene& gj = *reinterpret_cast<const DcbGene*>(jblob);
     if (vh.count == 0) return FAST_DEFER;
     if (vh.count > 1) {
         if (both_frames) return FAST_DEFER;
         DCB_COUNT(C, DCB_C_multiple_v_matches);
         return FAST_DONE;
     }
-    const DcbTag& vt = gene_tag(vblob, gv, fullhit_tag(vh));
+    const DcbTagFin vt = tag_fin(vtags, fullhit_tag(vh));
     VJ v, j;
     v.idx = fullhit_tag(vh); v.seqpos = fullhit_pos(vh);
-    if (!fast_v_deletions(r, vt, v.seqpos + vt.jump - 1, v.pos, v.dels)) return FAST_DEFER;
+    if (!fast_v_deletions<PADDED>(r, vt, v.seqpos + vt.jump - 1, v.pos, v.dels)) return FAST_DEFER;
     if (jh.count == 0) return FAST_DEFER;
     if (jh.count > 1) {
         if (both_frames) return FAST_DEFER;
@@ -600,11 +616,11 @@ DCB_HD int dcr_fast_from_hits(const ReadView& r, const uint32_t* vblob, const ui
         DCB_COUNT(C, DCB_C_VJ_assignment_failed);
         return FAST_DONE;
     }
-    const DcbTag& jt = gene_tag(jblob, gj, fullhit_tag(jh));
+    const DcbTagFin jt = tag_fin(jtags, fullhit_tag(jh));
     j.idx = fullhit_tag(jh); j.seqpos = fullhit_pos(jh) + (int)jt.len;
-    if (!fast_j_deletions(r, jt, fullhit_pos(jh) - jt.jump, v.pos + 1, j.pos, j.dels)) return FAST_DEFER;
+    if (!fast_j_deletions<PADDED>(r, jt, fullhit_pos(jh) - jt.jump, v.pos + 1, j.pos, j.dels)) return FAST_DEFER;
     // filters: a failed filter is final unless the other frame still has to be tried
-    int c = dcr_finish(r, vt, jt, v, j, prm, out);
+    int c = dcr_finish(r, vt.jump, vt.len, jt.jump, jt.len, v, j, prm, out);
     if (c >= 0) {
         if (both_frames) return FAST_DEFER;
         DCB_COUNT(C, c);
@@ -642,12 +658,12 @@ DCB_HD int dcr_exact_read(const ReadView& r, bool flagged, const uint32_t* vcore
     vh.count = 0; vh.code = 0;
     jh.count = 0; jh.code = 0;
     if (!jidx) {
-        fast_find(r, vidx, vcore, jcore, vh, jh);
+        fast_find(r, vidx, vh, jh, true);
     } else {
-        fast_find(r, vidx, vcore, nullptr, vh, jh);
-        if (vh.count == 1) fast_find(r, jidx, nullptr, jcore, vh, jh);
+        fast_find(r, vidx, vh, jh, true);
+        if (vh.count == 1) fast_find(r, jidx, vh, jh, false);
     }
-    return dcr_fast_from_hits(r, vcore, jcore, vh, jh, prm, both_frames, out, C);
+    return dcr_fast_from_hits<false>(r, gene_tags(vcore), gene_tags(jcore), vh, jh, prm, both_frames, out, C);
 }
 
 // General kernel body for one read: r has w/stride/n/nw set; inv0, rd1, inv1 are this thread's scratch

@@ -82,6 +82,19 @@ __device__ __forceinline__ void tma_stage_wait(uint64_t* bar) {
     }
 }
 
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// i * 128 + base as ONE multiply-add (the compiler otherwise rewrites the shift pair into shift + mask + add)
+__device__ __forceinline__ uint32_t mad128(uint32_t i, uint32_t base) {
+    uint32_t v;
+    asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(v) : "r"(i), "r"(base));
+    return v;
+}
+
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -201,24 +214,29 @@ dcb_exact_kernel(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_res
 }
 
 // ------------------------------------------------------------------------------------------------
-// exact-tag kernel, specialised: the read slot (NW words) sits in registers and every sampled seed position
-// is a compile-time constant (static funnel shifts, no index arithmetic).
-//   NW      words per read slot (16 => reads up to 256 nt)
-//   QV, SV  V seed length / stride;  QJ, SJ  the same for J
-//   UNION   V and J share the seed geometry and are found together through ONE index (table 2)
+// exact-tag kernel, specialised: the read slot (NW words) sits in registers, every sampled seed position is a
+// compile-time constant (static funnel shifts, no index arithmetic), and each lane probes its OWN copy of the
+// seed filter -- the filter is replicated 32x in shared memory, copy l interleaved into bank l -- so a probe
+// is one conflict-free shared-memory wavefront whatever the 32 q-mers are.
+//   NW            words per read slot (16 => reads up to 256 nt)
+//   QV, SV, WBV   V seed length / stride / log2(filter words);  QJ, SJ, WBJ the same for J
+//   UNION         V and J share the seed geometry and are found together through ONE index (table 2)
+// One block of up to 1024 threads per SM (the private filters take 128 KB).
 // ------------------------------------------------------------------------------------------------
-template <int NW, int Q, int S>
+template <int NW, int Q, int S, int WB>
 struct SeedScan {
     static constexpr int NPOS = (16 * NW - Q) / S + 1;
     static constexpr int G0 = NPOS < 32 ? NPOS : 32;   // probes collected in the first / second hit word
     static constexpr int G1 = NPOS - G0;
+    static constexpr int WLEAD = DCB_IDX_WLEAD(S + Q - 1, Q);
+    static constexpr int WMAX = ((NPOS - 1) * S - WLEAD) >> 4;   // first word of the last verification window
     static_assert(NPOS <= 64, "at most 64 sampled positions");
-    // Probe the bitmap at every sampled position.  Probe i of a group of G lands in bit G-1-i of its hit word
+    // Probe the filter at every sampled position.  Probe i of a group of G lands in bit G-1-i of its hit word
     // (each probe shifts the word left by one), so the EARLIEST position is the HIGHEST set bit.
-    static __device__ __forceinline__ void run(const uint32_t (&w)[NW], const uint32_t* __restrict__ bitmap,
-                                               uint32_t& h0, uint32_t& h1) {
+    // bl = shared-space byte address of this lane's copy of the filter: word w at bl + 128 w.
+    static __device__ __forceinline__ void run(const uint32_t (&w)[NW], uint32_t bl, uint32_t& h0, uint32_t& h1) {
         h0 = 0; h1 = 0;
-        constexpr uint32_t WMASK = (1u << (2 * Q - 5)) - 1u;
+        constexpr uint32_t BMUL = DCB_BLOOM_MUL(Q);
 #pragma unroll
         for (int i = 0; i < NPOS; i++) {
             const int p = i * S, a = p >> 4, sh = (p & 15) * 2;
@@ -226,7 +244,7 @@ struct SeedScan {
             if (sh == 0) win = w[a];
             else if (sh + 2 * Q <= 32 || a + 1 >= NW) win = w[a] >> sh;
             else win = __funnelshift_r(w[a], w[a + 1], sh);
-            const uint32_t word = bitmap[(win >> 5) & WMASK];
+            const uint32_t word = lds_u32(mad128((win * BMUL) >> (32 - WB), bl));
             const uint32_t top = __funnelshift_l(0u, word, win);          // word << (key & 31): the key's bit -> bit 31
             if (i < 32) h0 = __funnelshift_l(top, h0, 1); else h1 = __funnelshift_l(top, h1, 1);
         }
@@ -239,35 +257,89 @@ struct SeedScan {
     }
     // earliest remaining probe index (and remove it); call only while (h0 | h1) != 0
     static __device__ __forceinline__ int pop(uint32_t& h0, uint32_t& h1) {
-        if (h0) { const int b = 31 - __clz(h0); h0 &= ~(1u << b); return G0 - 1 - b; }
+        if (G1 == 0 || h0) { const int b = 31 - __clz(h0); h0 &= ~(1u << b); return G0 - 1 - b; }
         const int b = 31 - __clz(h1); h1 &= ~(1u << b); return G0 + G1 - 1 - b;
+    }
+    // the 32 bases starting at p - WLEAD, from a column that has a zero row in front and behind
+    static __device__ __forceinline__ void window(const uint32_t* col, int T, int p, uint32_t& lo, uint32_t& hi) {
+        const int W = p - WLEAD, sh = (W & 15) * 2;
+        const uint32_t* c0 = col + (W >> 4) * T;
+        const uint32_t a = c0[0], b = c0[T], c = c0[2 * T];
+        lo = __funnelshift_r(a, b, sh);
+        hi = __funnelshift_r(b, c, sh);
     }
 };
 
-template <int NW, int QV, int SV, int QJ, int SJ, bool UNION>
-__global__ void __launch_bounds__(kExactThreads)
-dcb_exact_kernel_spec(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_result* __restrict__ results,
+// Confirm the filter hits of all 32 reads of a warp.  ONE flat loop over (hit, candidate offset) pairs: on each trip a
+// lane either pops its next hit and looks the q-mer up, or -- when that q-mer stands for several tag offsets -- takes
+// the next offset, and then checks one candidate.  The warp votes on every trip, so all lanes stay in the same
+// instruction stream and the trip count is the LARGEST number of candidates any one read has (not the sum over
+// nested per-lane loops).  Must be called by all 32 lanes; `stop` is the hit counter that ends a lane's scan at 2.
+template <class Scan, int S>
+__device__ __forceinline__ void verify_hits(const ReadView& r, const SeedIdxView& ix, const uint32_t* col, int T, uint32_t lo,
+                                            uint32_t hi, FullHit& vh, FullHit& jh, const FullHit& stop) {
+    uint32_t offs = 0, wlo = 0, whi = 0;
+    int p = 0;
+    for (;;) {
+        const bool need = offs == 0 && (lo | hi) != 0 && stop.count < 2;
+        if (!__any_sync(0xFFFFFFFFu, need || offs != 0)) break;
+        if (need) {
+            p = Scan::pop(lo, hi) * S;
+            Scan::window(col, T, p, wlo, whi);
+            offs = fast_class_lookup(ix, wlo, whi);
+        }
+        __syncwarp();
+        if (offs) {
+            const int o = 31 - __clz(offs);
+            offs ^= 1u << o;
+            fast_check_offset(r, ix, p, o, wlo, whi, vh, jh);
+        }
+        __syncwarp();
+    }
+}
+
+// What the specialised kernel needs beyond Tables4: the compact filters to replicate.
+struct SpecBlooms { const uint32_t* v; const uint32_t* j; };
+
+template <int A, int B> struct StaticMax { static constexpr int value = A > B ? A : B; };
+
+template <int NW, int QV, int SV, int WBV, int QJ, int SJ, int WBJ, bool UNION>
+__global__ void __launch_bounds__(1024, 1)
+dcb_exact_kernel_spec(BatchDev b, Tables4 tb, SpecBlooms bl, DcrParams prm, int both_frames, dcb_result* __restrict__ results,
                       unsigned long long* __restrict__ counters, uint32_t* __restrict__ queue,
                       uint32_t* __restrict__ queue_count) {
-    static_assert(!UNION || (QV == QJ && SV == SJ), "union scan needs one seed geometry");
+    static_assert(!UNION || (QV == QJ && SV == SJ && WBV == WBJ), "union scan needs one seed geometry");
+    using ScanV = SeedScan<NW, QV, SV, WBV>;
+    using ScanJ = SeedScan<NW, QJ, SJ, WBJ>;
+    constexpr int WMAX = UNION ? ScanV::WMAX : StaticMax<ScanV::WMAX, ScanJ::WMAX>::value;
+    constexpr int TRAIL = WMAX + 3 - NW > 0 ? WMAX + 3 - NW : 0;   // zero rows behind the read columns
+    constexpr int ROWS = 1 + NW + TRAIL;
     extern __shared__ __align__(16) uint32_t smem[];
-    constexpr int T = kExactThreads;
-    SmemLayout L = carve(smem, tb, (size_t)NW * T);
-    uint32_t* s_rd = L.cols;
+    const int T = blockDim.x;
+    const int tid = threadIdx.x;
+    constexpr int BV = 32 << WBV, BJ = UNION ? 0 : (32 << WBJ);
+    SmemLayout L = carve(smem, tb, (size_t)BV + BJ + (size_t)ROWS * T);
+    uint32_t* s_bv = L.cols;
+    uint32_t* s_bj = s_bv + BV;
+    uint32_t* s_rd = s_bj + BJ;
+    for (int i = tid; i < BV; i += T) s_bv[i] = __ldg(bl.v + (i >> 5));
+    for (int i = tid; i < BJ; i += T) s_bj[i] = __ldg(bl.j + (i >> 5));
+    s_rd[tid] = 0u;
+    for (int k = 0; k < TRAIL; k++) s_rd[(1 + NW + k) * T + tid] = 0u;
     stage_tables(L, tb);
 
-    const uint32_t* vcore = L.t[0];
-    const uint32_t* jcore = L.t[1];
-    const DcbTag* vtags = gene_tags(vcore);
-    const DcbTag* jtags = gene_tags(jcore);
-    // index views with the geometry pinned to the template constants (lmin = S + Q - 1)
-    SeedIdxView vix = seed_idx_view(L.t[2]);
-    vix.q = QV; vix.stride = SV; vix.lmin = SV + QV - 1;
-    vix.wlead = DCB_IDX_WLEAD(SV + QV - 1, QV); vix.span = DCB_IDX_SPAN(SV + QV - 1, QV); vix.k = DCB_IDX_K(SV + QV - 1, QV);
-    SeedIdxView jix = seed_idx_view(UNION ? L.t[2] : L.t[3]);
-    jix.q = QJ; jix.stride = SJ; jix.lmin = SJ + QJ - 1;
-    jix.wlead = DCB_IDX_WLEAD(SJ + QJ - 1, QJ); jix.span = DCB_IDX_SPAN(SJ + QJ - 1, QJ); jix.k = DCB_IDX_K(SJ + QJ - 1, QJ);
-    const int tid = threadIdx.x;
+    const DcbTag* vtags = gene_tags(smem);                       // table 0 starts the dynamic shared memory
+    const DcbTag* jtags = gene_tags(smem + tb.words[0]);
+    // index views with the geometry pinned to the template constants (lmin = S + Q - 1 for the shipped sets)
+    SeedIdxView vix = seed_idx_view(smem + tb.words[0] + tb.words[1]);   // tables are laid out back to back
+    vix.q = QV; vix.stride = SV; vix.wlead = ScanV::WLEAD; vix.lmin = SV + QV - 1;
+    vix.span = DCB_IDX_SPAN(SV + QV - 1, QV); vix.k = DCB_IDX_K(SV + QV - 1, QV);
+    SeedIdxView jix = seed_idx_view(smem + tb.words[0] + tb.words[1] + (UNION ? 0 : tb.words[2]));
+    jix.q = QJ; jix.stride = SJ; jix.wlead = ScanJ::WLEAD; jix.lmin = SJ + QJ - 1;
+    jix.span = DCB_IDX_SPAN(SJ + QJ - 1, QJ); jix.k = DCB_IDX_K(SJ + QJ - 1, QJ);
+    const uint32_t* col = s_rd + T + tid;                 // word k of this thread's read at col[k * T]
+    const uint32_t my_bv = smem_u32(s_bv + (tid & 31));
+    const uint32_t my_bj = smem_u32(s_bj + (tid & 31));
     const uint32_t n_tiles = (b.n_reads + T - 1) / T;
 
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -276,42 +348,42 @@ dcb_exact_kernel_spec(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dc
         int action = FAST_DONE;
         dcb_result out;
         *reinterpret_cast<uint4*>(&out) = make_uint4(0, 0, 0, 0);
-        if (live) {
-            uint32_t w[NW];
-            const uint4* src = reinterpret_cast<const uint4*>(b.words + (size_t)ri * NW);
+        // Every lane of the warp walks the same instruction stream below (dead and flagged lanes with empty hit
+        // masks), so that the verification loop can re-converge the warp with a vote on every trip.
+        uint32_t w[NW];
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(b.words + (size_t)(live ? ri : 0) * NW);
 #pragma unroll
             for (int k = 0; k < NW / 4; k++) {
                 const uint4 v = ldg_stream(src + k);
                 w[4 * k + 0] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
             }
 #pragma unroll
-            for (int k = 0; k < NW; k++) s_rd[k * T + tid] = w[k];
-            const bool flagged = b.n_exc && ((__ldg(b.flags + (ri >> 5)) >> (ri & 31)) & 1u);
-            if (flagged) {
-                action = FAST_DEFER;
-            } else {
-                ReadView r;
-                r.w = s_rd + tid; r.inv = nullptr; r.stride = T;
-                r.n = b.uniform_len ? (int)b.uniform_len : (int)__ldg(b.lens + ri);
-                r.nw = NW;
-                r.exc_pos = nullptr; r.exc_kind = nullptr; r.e0 = r.e1 = 0; r.mirror = 0;
-                FullHit vh, jh;
-                vh.count = 0; vh.code = 0;
-                jh.count = 0; jh.code = 0;
-                uint32_t lo, hi;
-                SeedScan<NW, QV, SV>::run(w, vix.seedmap, lo, hi);
-                SeedScan<NW, QV, SV>::clip(r.n, lo, hi);
-                while ((lo | hi) && vh.count < 2)
-                    fast_verify_hit(r, vix, SeedScan<NW, QV, SV>::pop(lo, hi) * SV, vtags, UNION ? jtags : nullptr, vh, jh);
-                if (!UNION && vh.count == 1) {
-                    SeedScan<NW, QJ, SJ>::run(w, jix.seedmap, lo, hi);
-                    SeedScan<NW, QJ, SJ>::clip(r.n, lo, hi);
-                    while ((lo | hi) && jh.count < 2)
-                        fast_verify_hit(r, jix, SeedScan<NW, QJ, SJ>::pop(lo, hi) * SJ, nullptr, jtags, vh, jh);
-                }
-                action = dcr_fast_from_hits(r, vcore, jcore, vh, jh, prm, both_frames, out, L.cnt);
-            }
+            for (int k = 0; k < NW; k++) s_rd[(1 + k) * T + tid] = w[k];
         }
+        const bool flagged = live && b.n_exc && ((__ldg(b.flags + (ri >> 5)) >> (ri & 31)) & 1u);
+        const bool scan = live && !flagged;
+        ReadView r;
+        r.w = col; r.inv = nullptr; r.stride = T;
+        r.n = b.uniform_len ? (int)b.uniform_len : (live ? (int)__ldg(b.lens + ri) : 0);
+        r.nw = NW;
+        r.exc_pos = nullptr; r.exc_kind = nullptr; r.e0 = r.e1 = 0; r.mirror = 0;
+        FullHit vh, jh;
+        vh.count = 0; vh.code = 0;
+        jh.count = 0; jh.code = 0;
+        uint32_t lo, hi;
+        ScanV::run(w, my_bv, lo, hi);
+        ScanV::clip(r.n, lo, hi);
+        if (!scan) { lo = 0; hi = 0; }
+        verify_hits<ScanV, SV>(r, vix, col, T, lo, hi, vh, jh, vh);
+        if (!UNION) {
+            ScanJ::run(w, my_bj, lo, hi);
+            ScanJ::clip(r.n, lo, hi);
+            if (!scan || vh.count != 1) { lo = 0; hi = 0; }
+            verify_hits<ScanJ, SJ>(r, jix, col, T, lo, hi, vh, jh, jh);
+        }
+        if (scan) action = dcr_fast_from_hits<true>(r, vtags, jtags, vh, jh, prm, both_frames, out, L.cnt);
+        else if (live) action = FAST_DEFER;
         defer_reads(live && action == FAST_DEFER, ri, queue, queue_count);
         if (live && action == FAST_DONE) store_result(results + ri, out);
     }
@@ -420,27 +492,38 @@ struct dcb_ctx {
     int exact_grid = 0, general_grid = 0, exact_threads = kExactThreads, general_threads = kGeneralThreads;
     size_t exact_smem = 0, general_smem = 0;
     // seed geometry of the two genes and the union bitmap (built when they agree)
-    int qv = 0, sv = 0, qj = 0, sj = 0;
+    int qv = 0, sv = 0, qj = 0, sj = 0, lminv = 0, lminj = 0;
+    int vhead = 0, jhead = 0, uhead = 0, vbloom = 0, jbloom = 0, ubloom = 0;   // head_words / bloom_off of the three indexes
     void* spec_fn = nullptr;   // specialised exact kernel picked for the resident batch, or null
     bool spec_union = false;
 };
 
-typedef void (*exact_spec_fn)(BatchDev, Tables4, DcrParams, int, dcb_result*, unsigned long long*, uint32_t*, uint32_t*);
+typedef void (*exact_spec_fn)(BatchDev, Tables4, SpecBlooms, DcrParams, int, dcb_result*, unsigned long long*, uint32_t*, uint32_t*);
 
 // Specialisations compiled in: V seeds (q=9, stride 12) -- every shipped V tag set has 20-nt minimum tags --
-// with J either sharing that geometry (20-nt J tags: one union bitmap) or using (q=8, stride 5) (12-nt J tags).
-static exact_spec_fn pick_spec(int nw, int qv, int sv, int qj, int sj, bool* is_union) {
-    if (qv != 9 || sv != 12) return nullptr;
-    const bool uni = (qj == 9 && sj == 12), sep = (qj == 8 && sj == 5);
+// with J either sharing that geometry (20-nt J tags: one union index) or using (q=8, stride 5) (12-nt J tags).
+static exact_spec_fn pick_spec(int nw, int qv, int sv, int lminv, int qj, int sj, int lminj, bool* is_union) {
+    if (qv != 9 || sv != 12 || lminv != 20) return nullptr;
+    const bool uni = (qj == 9 && sj == 12 && lminj == 20), sep = (qj == 8 && sj == 5 && lminj == 12);
     if (!uni && !sep) return nullptr;
     *is_union = uni;
+#define DCB_SPEC(NW) (uni ? dcb_exact_kernel_spec<NW, 9, 12, DCB_WBITS_UNION, 9, 12, DCB_WBITS_UNION, true> \
+                          : dcb_exact_kernel_spec<NW, 9, 12, DCB_WBITS_SINGLE, 8, 5, DCB_WBITS_SINGLE, false>)
     switch (nw) {
-        case 8:  return uni ? dcb_exact_kernel_spec<8, 9, 12, 9, 12, true> : dcb_exact_kernel_spec<8, 9, 12, 8, 5, false>;
-        case 12: return uni ? dcb_exact_kernel_spec<12, 9, 12, 9, 12, true> : dcb_exact_kernel_spec<12, 9, 12, 8, 5, false>;
-        case 16: return uni ? dcb_exact_kernel_spec<16, 9, 12, 9, 12, true> : dcb_exact_kernel_spec<16, 9, 12, 8, 5, false>;
-        case 20: return uni ? dcb_exact_kernel_spec<20, 9, 12, 9, 12, true> : dcb_exact_kernel_spec<20, 9, 12, 8, 5, false>;
+        case 8:  return DCB_SPEC(8);
+        case 12: return DCB_SPEC(12);
+        case 16: return DCB_SPEC(16);
+        case 20: return DCB_SPEC(20);
         default: return nullptr;
     }
+#undef DCB_SPEC
+}
+// rows of shared memory per read column in the specialised kernel (must match the kernel's ROWS)
+static int spec_rows(int nw, bool uni) {
+    auto wmax = [&](int q, int s) { const int npos = (16 * nw - q) / s + 1; return ((npos - 1) * s - (s)) >> 4; };  // wlead == stride
+    const int wm = uni ? wmax(9, 12) : std::max(wmax(9, 12), wmax(8, 5));
+    const int trail = wm + 3 - nw > 0 ? wm + 3 - nw : 0;
+    return 1 + nw + trail;
 }
 
 static int upload_blob(const std::vector<uint32_t>& v, uint32_t** d, int* words) {
@@ -511,11 +594,15 @@ dcb_ctx* dcb_ctx_create(int device, const dcb_tagset* v, const dcb_tagset* j, co
     {
         const DcbSeedIndex& iv = *reinterpret_cast<const DcbSeedIndex*>(v->index.data());
         const DcbSeedIndex& ij = *reinterpret_cast<const DcbSeedIndex*>(j->index.data());
-        c->qv = iv.q; c->sv = iv.stride; c->qj = ij.q; c->sj = ij.stride;
-        if (v->lmin == j->lmin) {  // same seed geometry: one index (and one bitmap) finds both genes
+        c->qv = iv.q; c->sv = iv.stride; c->qj = ij.q; c->sj = ij.stride; c->lminv = iv.lmin; c->lminj = ij.lmin;
+        c->vhead = iv.head_words; c->vbloom = iv.bloom_off; c->jhead = ij.head_words; c->jbloom = ij.bloom_off;
+        if (v->lmin == j->lmin) {  // same seed geometry: one index (and one filter) finds both genes
             std::vector<uint32_t> u;
-            if (!dcb_build_seed_index(&v->tags, &j->tags, v->lmin, u)) { dcb_set_error("dcb_ctx_create: union seed index failed"); return fail(nullptr); }
-            if (upload_blob(u, &c->d_uidx, &c->uidx_words)) return fail(nullptr);
+            if (dcb_build_seed_index(&v->tags, &j->tags, v->lmin, DCB_WBITS_UNION, u)) {
+                const DcbSeedIndex& iu = *reinterpret_cast<const DcbSeedIndex*>(u.data());
+                c->uhead = iu.head_words; c->ubloom = iu.bloom_off;
+                if (upload_blob(u, &c->d_uidx, &c->uidx_words)) return fail(nullptr);
+            }
         }
     }
     if (cudaMalloc((void**)&c->d_queue_count, 16) != cudaSuccess) return fail("cudaMalloc");
@@ -579,14 +666,23 @@ int dcb_upload(dcb_ctx* c, const dcb_packed* P) {
     const bool have_union = c->d_uidx != nullptr;
     const size_t tbl_e = (size_t)c->vcore_words + c->jcore_words + (have_union ? (size_t)c->uidx_words : (size_t)c->vidx_words + c->jidx_words);
     bool is_union = false;
-    exact_spec_fn spec = c->params.force_general ? nullptr : pick_spec((int)sw, c->qv, c->sv, c->qj, c->sj, &is_union);
+    exact_spec_fn spec = c->params.force_general ? nullptr
+                                                 : pick_spec((int)sw, c->qv, c->sv, c->lminv, c->qj, c->sj, c->lminj, &is_union);
     if (spec && is_union != have_union) spec = nullptr;
     c->spec_fn = (void*)spec; c->spec_union = have_union;
     int occ_e = 0, occ_g = 0;
     if (spec) {
-        c->exact_threads = kExactThreads;
-        c->exact_smem = (tbl_e + sw * kExactThreads) * 4 + tail;
-        if (c->exact_smem > kMaxSmem) { spec = nullptr; c->spec_fn = nullptr; }
+        // tables (index heads only) + 32 private copies of the filter(s) + the read columns of as wide a block as fits
+        const size_t tbl_s = (size_t)c->vcore_words + c->jcore_words + (have_union ? (size_t)c->uhead : (size_t)c->vhead + c->jhead);
+        const size_t blooms = have_union ? ((size_t)32 << DCB_WBITS_UNION) : 2 * ((size_t)32 << DCB_WBITS_SINGLE);
+        const size_t rows = (size_t)spec_rows((int)sw, have_union);
+        int T = 1024;
+        for (; T >= 256; T -= 128) {
+            c->exact_smem = (tbl_s + blooms + rows * T) * 4 + tail;
+            if (c->exact_smem <= kMaxSmem) break;
+        }
+        if (T < 256) { spec = nullptr; c->spec_fn = nullptr; }
+        else c->exact_threads = T;
     }
     if (spec) {
         CUDA_TRY(cudaFuncSetAttribute(spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->exact_smem));
@@ -641,8 +737,11 @@ int dcb_run_resident(dcb_ctx* c) {
         if (c->spec_union) { te.g[2] = c->d_uidx; te.words[2] = c->uidx_words; te.g[3] = nullptr; te.words[3] = 0; }
         else { te.g[2] = c->d_vidx; te.words[2] = c->vidx_words; te.g[3] = c->d_jidx; te.words[3] = c->jidx_words; }
         if (c->spec_fn) {
+            SpecBlooms sb;
+            if (c->spec_union) { te.words[2] = c->uhead; sb.v = c->d_uidx + c->ubloom; sb.j = nullptr; }
+            else { te.words[2] = c->vhead; te.words[3] = c->jhead; sb.v = c->d_vidx + c->vbloom; sb.j = c->d_jidx + c->jbloom; }
             ((exact_spec_fn)c->spec_fn)<<<c->exact_grid, c->exact_threads, c->exact_smem, s>>>(
-                b, te, prm, c->params.both_frames, (dcb_result*)c->results.p, c->d_counters, (uint32_t*)c->queue.p,
+                b, te, sb, prm, c->params.both_frames, (dcb_result*)c->results.p, c->d_counters, (uint32_t*)c->queue.p,
                 c->d_queue_count);
         } else {
             dcb_exact_kernel<<<c->exact_grid, c->exact_threads, c->exact_smem, s>>>(

@@ -164,77 +164,126 @@ int seed_q(int lmin) { return lmin >= 18 ? 9 : lmin >= 12 ? 8 : lmin >= 8 ? 6 : 
 }  // namespace
 
 // Seed index over the tags of one gene (the other pointer null) or of both genes of a chain (same lmin).
+// wbits: log2(words) of the seed filter.
 bool dcb_build_seed_index(const std::vector<std::string>* gene_v, const std::vector<std::string>* gene_j, int lmin,
-                          std::vector<uint32_t>& out) {
+                          int wbits, std::vector<uint32_t>& out) {
     Blob b;
     DcbSeedIndex idx;
     std::memset(&idx, 0, sizeof(idx));
     b.reserve((sizeof(DcbSeedIndex) + 3) / 4);
+    b.align4();
     idx.q = seed_q(lmin);
-    idx.stride = DCB_IDX_STRIDE(lmin, idx.q);
+    idx.lmin = lmin;
     idx.max_off = DCB_IDX_MAXOFF(lmin, idx.q);
-    idx.span = DCB_IDX_SPAN(lmin, idx.q);        // two classes of offsets: [0, span) and [span, max_off]
+    idx.stride = DCB_IDX_STRIDE(lmin, idx.q);
     idx.wlead = DCB_IDX_WLEAD(lmin, idx.q);
+    idx.wbits = wbits;
+    idx.span = DCB_IDX_SPAN(lmin, idx.q);            // two classes of offsets: [0, span) and [span, max_off]
     idx.k = DCB_IDX_K(lmin, idx.q);
-    if (idx.k < 1 || idx.wlead > 31) return false;
-    std::map<uint32_t, uint32_t> classkeys;  // class << 31 | k-mer  ->  mask of offsets
-    std::map<std::pair<uint32_t, uint32_t>, uint32_t> prefixes;  // lmin-prefix -> gene << 8 | first tag
-    std::vector<uint32_t> seeds;
-    for (int gene = 0; gene < 2; gene++) {
-        const std::vector<std::string>* tags = gene == 0 ? gene_v : gene_j;
-        if (!tags) continue;
-        for (size_t t = 0; t < tags->size(); t++) {
-            const std::string& s = (*tags)[t];
-            uint32_t lo, hi;
-            for (int o = 0; o <= idx.max_off; o++) {
-                pack64(s, o, idx.q, lo, hi);
-                seeds.push_back(lo);
-                const int c = o / idx.span, from = o - c * idx.span;
-                pack64(s, from, idx.k, lo, hi);
-                classkeys[((uint32_t)c << 31) | lo] |= 1u << o;
-            }
-            pack64(s, 0, lmin, lo, hi);
-            auto key = std::make_pair(lo, hi);
-            auto it = prefixes.find(key);
-            if (it == prefixes.end()) prefixes[key] = ((uint32_t)gene << 8) | (uint32_t)t;
-            else if ((it->second >> 8) != (uint32_t)gene) return false;  // a V and a J tag share a prefix: no union index
+    if (idx.k < 1 || idx.k > 15) return false;
+    if (idx.q < 3 || idx.q > 9 || lmin > 32 || wbits < 2 || wbits > 2 * idx.q - 5 || wbits > 27) return false;
+    idx.bmul = DCB_BLOOM_MUL(idx.q);
+
+    // combined tag list: V first
+    std::vector<const std::string*> all;
+    idx.n_v = gene_v ? (int32_t)gene_v->size() : 0;
+    if (gene_v) for (auto& s : *gene_v) all.push_back(&s);
+    if (gene_j) for (auto& s : *gene_j) all.push_back(&s);
+    idx.n_tags = (int32_t)all.size();
+    if (all.empty() || all.size() > 510) return false;
+
+    std::map<uint32_t, uint32_t> seeds;                           // indexed q-mers (the filter's keys)
+    std::map<uint32_t, uint32_t> classkeys;                       // class << 30 | k-mer -> set of offsets
+    std::map<std::pair<uint32_t, uint32_t>, int> prefixes;        // lmin-prefix -> first ctag
+    std::vector<int> next_same(all.size(), 0x1FF);
+    for (size_t t = 0; t < all.size(); t++) {
+        const std::string& s = *all[t];
+        if ((int)s.size() < lmin || s.size() > DCB_FAST_MAX_TAG_LEN) return false;
+        uint32_t lo, hi;
+        for (int o = 0; o <= idx.max_off; o++) {
+            if (!pack64(s, o, idx.q, lo, hi)) return false;
+            seeds[lo] |= 1u << o;
+            const int c = o / idx.span;
+            pack64(s, o - c * idx.span, idx.k, lo, hi);               // the k-mer starts c*span before the seed
+            classkeys[((uint32_t)c << 30) | lo] |= 1u << o;
+        }
+        pack64(s, 0, lmin, lo, hi);
+        auto key = std::make_pair(lo, hi);
+        auto it = prefixes.find(key);
+        if (it == prefixes.end()) prefixes[key] = (int)t;
+        else {                                                    // chain the tags that share a prefix, ascending
+            int k = it->second;
+            while (next_same[k] != 0x1FF) k = next_same[k];
+            next_same[k] = (int)t;
         }
     }
-    {
+    {   // class keys
         std::vector<std::pair<uint32_t, uint32_t>> items(classkeys.begin(), classkeys.end());
         Cuckoo ck;
         if (!build_cuckoo(ck, items)) return false;
-        idx.c1 = ck.c1; idx.c2 = ck.c2; idx.shift = 32 - ck.bits;
+        idx.c1 = ck.c1; idx.c2 = ck.c2; idx.cshift = 32 - ck.bits;
         const size_t slots = (size_t)1 << ck.bits;
-        idx.ck_off = b.reserve(2 * slots);
-        for (size_t i = 0; i < slots; i++) {
-            b.w[idx.ck_off + 2 * i] = ck.used[i] ? ck.key[i] : DCB_HASH_EMPTY;
-            b.w[idx.ck_off + 2 * i + 1] = ck.used[i] ? ck.val[i] : 0u;
-        }
-    }
-    {
-        std::vector<std::pair<uint32_t, uint32_t>> items;
-        std::map<uint32_t, int> folded;
-        for (auto& kv : prefixes) {
-            uint32_t f = dcb_fold64(kv.first.first, kv.first.second);
-            // lookups pick the slot by fingerprint, so the fingerprints of distinct prefixes must differ
-            if (folded.count(DCB_TK_FP(f))) return false;
-            folded[DCB_TK_FP(f)] = 1;
-            items.emplace_back(f, kv.second);
-        }
-        Cuckoo ck;
-        if (!build_cuckoo(ck, items)) return false;
-        idx.t1 = ck.c1; idx.t2 = ck.c2; idx.tshift = 32 - ck.bits;
-        const size_t slots = (size_t)1 << ck.bits;
-        idx.tk_off = b.reserve(slots);
+        idx.ck_off = b.reserve(slots);
         for (size_t i = 0; i < slots; i++)
-            b.w[idx.tk_off + i] = ck.used[i] ? (DCB_TK_FP(ck.key[i]) | ck.val[i]) : DCB_HASH_EMPTY;
+            b.w[idx.ck_off + i] = ck.used[i] ? ((DCB_CK_FP(ck.key[i] * ck.c1) << 12) | ck.val[i]) : 0u;
+    }
+    {   // lmin-prefixes: search a multiplier that spreads them over the slots without a collision
+        std::vector<std::pair<uint32_t, int>> items;
+        for (auto& kv : prefixes) items.emplace_back(dcb_fold64(kv.first.first, kv.first.second), kv.second);
+        for (size_t i = 0; i < items.size(); i++)
+            for (size_t k = i + 1; k < items.size(); k++)
+                if (items[i].first == items[k].first) return false;   // two prefixes fold to the same word
+        uint64_t rng = 0x9E3779B97F4A7C15ull;
+        bool done = false;
+        for (int bits = 9; bits <= 14 && !done; bits++) {
+            if (((size_t)1 << bits) < 2 * items.size()) continue;
+            std::vector<int> slot((size_t)1 << bits);
+            for (int attempt = 0; attempt < 20000 && !done; attempt++) {
+                rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+                const uint32_t m = (uint32_t)rng | 1u;
+                std::fill(slot.begin(), slot.end(), -1);
+                bool ok = true;
+                for (auto& it : items) {
+                    int& sl = slot[(it.first * m) >> (32 - bits)];
+                    if (sl >= 0) { ok = false; break; }
+                    sl = it.second;
+                }
+                if (!ok) continue;
+                idx.t1 = m; idx.tshift = 32 - bits;
+                idx.tk_off = b.reserve(((size_t)1 << bits) / 2);
+                uint16_t* tk = reinterpret_cast<uint16_t*>(&b.w[idx.tk_off]);
+                for (size_t i = 0; i < slot.size(); i++) tk[i] = slot[i] >= 0 ? (uint16_t)slot[i] : (uint16_t)0x1FF;
+                done = true;
+            }
+        }
+        if (!done) return false;
     }
     b.align4();
-    size_t words = ((size_t)1 << (2 * idx.q)) / 32;
-    if (words < 4) words = 4;
-    idx.seedmap_off = b.reserve(words);
-    for (uint32_t key : seeds) b.w[idx.seedmap_off + DCB_SEEDMAP_WORD(key, idx.q)] |= 1u << DCB_SEEDMAP_BIT(key, idx.q);
+    idx.utag_off = b.reserve(4 * all.size());
+    bool any_chain = false;
+    for (size_t t = 0; t < all.size(); t++) {
+        const std::string& s = *all[t];
+        DcbUTag u;
+        pack64(s, 0, s.size(), u.bits_lo, u.bits_hi);
+        const uint64_t m = (1ull << (2 * s.size())) - 1ull;
+        u.mask_lo = (uint32_t)m;
+        u.mask_hi_len = (uint32_t)(m >> 32) | ((uint32_t)s.size() << 24);
+        std::memcpy(&b.w[idx.utag_off + 4 * t], &u, sizeof(u));
+        if (next_same[t] != 0x1FF) any_chain = true;
+    }
+    // chains of tags sharing an lmin-prefix (rare): one 16-bit successor per tag, 0x1FF = none
+    idx.chain_off = 0;
+    if (any_chain) {
+        idx.chain_off = b.reserve((all.size() + 1) / 2);
+        uint16_t* ch = reinterpret_cast<uint16_t*>(&b.w[idx.chain_off]);
+        for (size_t t = 0; t < all.size(); t++) ch[t] = (uint16_t)next_same[t];
+    }
+    b.align4();
+    idx.head_words = (int32_t)b.w.size();
+    const size_t words = (size_t)1 << wbits;
+    idx.bloom_off = b.reserve(words);
+    for (auto& kv : seeds)
+        b.w[idx.bloom_off + DCB_BLOOM_WORD(kv.first, idx.bmul, wbits)] |= 1u << DCB_BLOOM_BIT(kv.first);
     b.align4();
     idx.n_words = (int32_t)b.w.size();
     std::memcpy(&b.w[0], &idx, sizeof(idx));
@@ -277,6 +326,7 @@ dcb_tagset* dcb_tagset_build(const char* const* tags, const int32_t* jumps, cons
         DcbGene g;
         std::memset(&g, 0, sizeof(g));
         g.n_tags = n; g.split = half_split; g.is_v = is_v; g.lmin = lmin;
+        b.align4();                                   // tag records are read with 128-bit loads
         g.tag_off = b.reserve(DCB_TAG_WORDS * (size_t)n);
         std::vector<DcbTag> trec(n);
         for (int i = 0; i < n; i++) {
@@ -313,7 +363,7 @@ dcb_tagset* dcb_tagset_build(const char* const* tags, const int32_t* jumps, cons
         std::memcpy(&b.w[0], &g, sizeof(g));
         (which == 0 ? ts->general : ts->core) = std::move(b.w);
     }
-    if (!dcb_build_seed_index(is_v ? &ts->tags : nullptr, is_v ? nullptr : &ts->tags, lmin, ts->index)) {
+    if (!dcb_build_seed_index(is_v ? &ts->tags : nullptr, is_v ? nullptr : &ts->tags, lmin, DCB_WBITS_SINGLE, ts->index)) {
         dcb_set_error("dcb_tagset_build: seed index construction failed");
         delete ts;
         return nullptr;
@@ -338,7 +388,7 @@ int dcb_tagset_union_index(const dcb_tagset* v, const dcb_tagset* j, uint32_t* o
     if (!v || !j || !n_words) return DCB_EINVAL;
     if (v->lmin != j->lmin) { dcb_set_error("dcb_tagset_union_index: V and J tags have different minimum lengths"); return DCB_EUNSUPPORTED; }
     std::vector<uint32_t> u;
-    if (!dcb_build_seed_index(&v->tags, &j->tags, v->lmin, u)) { dcb_set_error("dcb_tagset_union_index: construction failed"); return DCB_EUNSUPPORTED; }
+    if (!dcb_build_seed_index(&v->tags, &j->tags, v->lmin, DCB_WBITS_UNION, u)) { dcb_set_error("dcb_tagset_union_index: construction failed"); return DCB_EUNSUPPORTED; }
     *n_words = u.size();
     if (out && cap >= u.size()) std::memcpy(out, u.data(), u.size() * 4);
     return DCB_OK;
