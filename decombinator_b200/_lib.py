@@ -47,7 +47,7 @@ class CParams(ctypes.Structure):
 class CSynthParams(ctypes.Structure):
     _fields_ = [("seed", ctypes.c_uint64), ("read_len", ctypes.c_uint32), ("read2_len", ctypes.c_uint32),
                 ("sub_rate", ctypes.c_uint32), ("n_rate", ctypes.c_uint32), ("junk_rate", ctypes.c_uint32),
-                ("umi_pool", ctypes.c_uint32)]
+                ("umi_pool", ctypes.c_uint32), ("sub_rate2", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
 _lib = None
@@ -88,6 +88,12 @@ def lib():
     L.dcb_timing_enable.argtypes = [vp, i32]
     L.dcb_timing_get.argtypes = [vp, vp, vp]
     L.dcb_last_deferred.argtypes = [vp, ctypes.POINTER(u64)]
+    L.dcb_dist_create.restype = vp
+    L.dcb_dist_create.argtypes = [i32]
+    L.dcb_dist_destroy.argtypes = [vp]
+    L.dcb_umi_pairs.argtypes = [vp, vp, u32, i32, vp, u64, ctypes.POINTER(u64)]
+    L.dcb_lev_leq.argtypes = [vp, vp, vp, vp, u32, vp, vp, u64, ctypes.c_double, vp]
+    L.dcb_dist_last_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     L.dcb_synth_create.restype = vp
     L.dcb_synth_create.argtypes = [ctypes.POINTER(CSynthParams), i32, ctypes.POINTER(cpp), ctypes.POINTER(ctypes.c_int),
                                    ctypes.POINTER(cpp), ctypes.POINTER(ctypes.c_int)]
@@ -305,7 +311,8 @@ class Context:
 class Synth:
     """dcb_synth: deterministic synthetic read generator."""
 
-    def __init__(self, gene_sets, seed, read_len, read2_len=0, sub_rate=0.0, n_rate=0.0, junk_rate=0.0, umi_pool=0):
+    def __init__(self, gene_sets, seed, read_len, read2_len=0, sub_rate=0.0, n_rate=0.0, junk_rate=0.0, umi_pool=0,
+                 sub_rate2=0.0):
         """gene_sets: list of (v_regions, j_regions); read i is drawn from set i % len(gene_sets)."""
         L = lib()
         self.read_len, self.read2_len = int(read_len), int(read2_len)
@@ -314,7 +321,7 @@ class Synth:
             return min(0xFFFFFFFF, int(round(x * 4294967296.0)))
 
         prm = CSynthParams(int(seed), self.read_len, self.read2_len, prob(sub_rate), prob(n_rate), prob(junk_rate),
-                           int(umi_pool))
+                           int(umi_pool), prob(sub_rate2), 0)
         n = len(gene_sets)
         cpp = ctypes.POINTER(ctypes.c_char_p)
         self._keep = [(_carr(v), _carr(j)) for v, j in gene_sets]
@@ -339,5 +346,100 @@ class Synth:
             if self._h:
                 lib().dcb_synth_destroy(self._h)
                 self._h = None
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------------------------------
+# collapse distance primitives
+# ---------------------------------------------------------------------------------------------------------
+UMI_MAX_LEN = 19
+_BASE_ALPHABET = "ACGTNSL"
+
+
+def _alphabet(strings, limit=8):
+    """Symbol codes for the characters that occur: A C G T N S L first (fixed codes), then whatever else shows up."""
+    codes = {c: i for i, c in enumerate(_BASE_ALPHABET)}
+    extra = sorted(set("".join(strings)) - set(codes))
+    if len(extra) > limit - len(_BASE_ALPHABET):
+        raise DcbError("more than %d distinct symbols: %r" % (limit, "".join(extra)))
+    for c in extra:
+        codes[c] = len(codes)
+    return codes
+
+
+def encode_umis(umis):
+    """list[str] -> uint64 codes for dcb_umi_pairs (3 bits per symbol, length in the top 6 bits)."""
+    codes = _alphabet(umis)
+    out = np.zeros(len(umis), dtype=np.uint64)
+    for i, u in enumerate(umis):
+        if len(u) > UMI_MAX_LEN:
+            raise DcbError("UMI %r is longer than %d symbols" % (u, UMI_MAX_LEN))
+        v = len(u) << 58
+        for k, ch in enumerate(u):
+            v |= codes[ch] << (3 * k)
+        out[i] = v
+    return out
+
+
+def encode_seqs(seqs):
+    """list[str] -> (symbols uint8, off uint64, len uint32) for dcb_lev_leq."""
+    codes = _alphabet(seqs)
+    table = np.zeros(256, dtype=np.uint8)
+    for ch, v in codes.items():
+        table[ord(ch)] = v
+    length = np.array([len(x) for x in seqs], dtype=np.uint32)
+    off = np.zeros(len(seqs), dtype=np.uint64)
+    if len(seqs) > 1:
+        off[1:] = np.cumsum(length[:-1], dtype=np.uint64)
+    raw = np.frombuffer("".join(seqs).encode("latin-1"), dtype=np.uint8)
+    return table[raw], off, length
+
+
+class Dist:
+    """dcb_dist: the GPU distance primitives of collapse (UMI neighbour pairs, bounded Levenshtein verdicts)."""
+
+    def __init__(self, device=0):
+        L = lib()
+        self._h = L.dcb_dist_create(int(device))
+        if not self._h:
+            raise DcbError("dcb_dist_create: " + L.dcb_last_error().decode())
+
+    def umi_pairs(self, codes, max_edits):
+        """-> (row, col) int64 arrays: every pair row < col within max_edits, ascending (row, col)."""
+        codes = np.ascontiguousarray(codes, dtype=np.uint64)
+        n = ctypes.c_uint64()
+        _check(lib().dcb_umi_pairs(self._h, codes.ctypes.data, len(codes), int(max_edits), None, 0, ctypes.byref(n)),
+               "dcb_umi_pairs")
+        keys = np.zeros(n.value, dtype=np.uint64)
+        if n.value:
+            _check(lib().dcb_umi_pairs(self._h, None, 0, 0, keys.ctypes.data, n.value, ctypes.byref(n)), "dcb_umi_pairs")
+        return (keys >> np.uint64(32)).astype(np.int64), (keys & np.uint64(0xFFFFFFFF)).astype(np.int64)
+
+    def lev_leq(self, symbols, off, length, a, b, frac):
+        """-> bool array: levenshtein(seq a[t], seq b[t]) <= len(shorter) * frac."""
+        a = np.ascontiguousarray(a, dtype=np.uint32)
+        b = np.ascontiguousarray(b, dtype=np.uint32)
+        symbols = np.ascontiguousarray(symbols, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        length = np.ascontiguousarray(length, dtype=np.uint32)
+        out = np.zeros(len(a), dtype=np.uint8)
+        _check(lib().dcb_lev_leq(self._h, symbols.ctypes.data, off.ctypes.data, length.ctypes.data, len(length),
+                                 a.ctypes.data, b.ctypes.data, len(a), float(frac), out.ctypes.data), "dcb_lev_leq")
+        return out.astype(bool)
+
+    def last_ms(self):
+        ms = ctypes.c_double()
+        _check(lib().dcb_dist_last_ms(self._h, ctypes.byref(ms)), "dcb_dist_last_ms")
+        return ms.value
+
+    def close(self):
+        if self._h:
+            lib().dcb_dist_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
         except Exception:
             pass

@@ -57,22 +57,26 @@ struct Synth {
 void make_read(const Synth& S, uint64_t index, char* r1, char* r2) {
     const dcb_synth_params& p = S.p;
     Rng rng(p.seed ^ (index * 0x9E3779B97F4A7C15ull));
+    // with a UMI pool, read `index` is a copy of molecule index % umi_pool: the rearrangement comes from the molecule's
+    // own stream, sequencing errors from the read's
+    Rng pool_rng((p.seed + 0x5DEECE66Dull) ^ ((index % (p.umi_pool ? p.umi_pool : 1)) * 0xC2B2AE3D27D4EB4Full));
+    Rng& mrng = p.umi_pool ? pool_rng : rng;
     const int L = (int)p.read_len;
-    bool junk = p.junk_rate && (uint32_t)(rng.next() >> 32) < p.junk_rate;
+    bool junk = p.junk_rate && (uint32_t)(mrng.next() >> 32) < p.junk_rate;
     std::string mol;
     int e = 0;
     if (!junk) {
         const GeneSet& g = S.sets[index % S.sets.size()];
-        const std::string& V = g.v[rng.below((uint32_t)g.v.size())];
-        const std::string& J = g.j[rng.below((uint32_t)g.j.size())];
-        int vdel = kVdel[rng.below(10)], jdel = kJdel[rng.below(9)], nins = kIns[rng.below(11)];
+        const std::string& V = g.v[mrng.below((uint32_t)g.v.size())];
+        const std::string& J = g.j[mrng.below((uint32_t)g.j.size())];
+        int vdel = kVdel[mrng.below(10)], jdel = kJdel[mrng.below(9)], nins = kIns[mrng.below(11)];
         if (vdel > (int)V.size()) vdel = (int)V.size();
         if (jdel > (int)J.size()) jdel = (int)J.size();
         mol.reserve(V.size() + J.size() + 512);
         mol.append(V, 0, V.size() - vdel);
-        for (int i = 0; i < nins; i++) mol.push_back(kBases[rng.below(4)]);
+        for (int i = 0; i < nins; i++) mol.push_back(kBases[mrng.below(4)]);
         mol.append(J, jdel, std::string::npos);
-        e = (int)mol.size() + 20 + (int)rng.below(41);
+        e = (int)mol.size() + 20 + (int)mrng.below(41);
         mol.append(S.constant);
     }
     // window = mol[e-L : e], left-padded with random bases when the molecule is short
@@ -105,6 +109,15 @@ void make_read(const Synth& S, uint64_t index, char* r1, char* r2) {
         for (const char* s = kSpacer2; *s; s++) put(*s);
         for (int i = 0; i < 6; i++) put(kBases[urng.below(4)]);
         while (k < L2) put(kBases[rng.below(4)]);
+        if (p.sub_rate2) {   // sequencing errors in the barcode read (fuzzy spacers, UMI neighbours)
+            for (int i = 0; i < L2; i++) {
+                uint64_t r = rng.next();
+                if ((uint32_t)(r >> 32) < p.sub_rate2) {
+                    int cur = r2[i] == 'A' ? 0 : r2[i] == 'C' ? 1 : r2[i] == 'G' ? 2 : 3;
+                    r2[i] = kBases[(cur + 1 + ((uint32_t)r % 3)) & 3];
+                }
+            }
+        }
     }
 }
 

@@ -182,6 +182,34 @@ int dcb_timing_get(dcb_ctx*, double ms[DCB_NTIMERS], uint64_t launches[DCB_NTIME
 int dcb_last_deferred(dcb_ctx*, uint64_t* n);
 
 /* ---------------------------------------------------------------------------------------------
+ * Distance primitives of the collapse step (no tag tables needed: their own light context).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct dcb_dist dcb_dist;
+dcb_dist* dcb_dist_create(int device);
+void dcb_dist_destroy(dcb_dist*);
+
+/* UMI neighbour search.  Replaces
+ *     matches = prsnn.symdel(umi_list, max_edits=barcode_threshold, output_type="coo_matrix")
+ *     matches = sparse.triu(matches); matches.sum_duplicates()                 (collapse.py:735-742)
+ * codes[i]: UMI i, 3 bits per symbol (symbol k in bits [3k, 3k+3); the caller picks the alphabet, <= 8 symbols),
+ *           length (<= 19) in bits [58, 64).
+ * With codes != NULL the sorted list of pairs (row < col, Levenshtein(codes[row], codes[col]) <= max_edits,
+ * ascending (row, col) = the order make_clusters walks the COO matrix in, collapse.py:773) is computed on the GPU
+ * and kept; *n_pairs is its length.  With keys != NULL the kept list is copied out as row << 32 | col
+ * (DCB_ENOMEM when cap is too small).  Typical use: one call with keys == NULL to size, one with codes == NULL. */
+int dcb_umi_pairs(dcb_dist*, const uint64_t* codes, uint32_t n, int max_edits, uint64_t* keys, uint64_t cap,
+                  uint64_t* n_pairs);
+
+/* Batch of are_seqs_equivalent(seq1, seq2, lev_threshold_fraction) (collapse.py:355-360; called at :601, :778):
+ *     verdict[t] = polyleven.levenshtein(A, B) <= len(shorter of A, B) * frac        (compared in double)
+ * for A = sequence a[t], B = sequence b[t].  Sequences: one byte per symbol (codes 0..7, the caller picks the
+ * alphabet), sequence i at symbols[off[i] .. off[i] + len[i]), len <= 512. */
+int dcb_lev_leq(dcb_dist*, const uint8_t* symbols, const uint64_t* off, const uint32_t* len, uint32_t n_seqs,
+                const uint32_t* a, const uint32_t* b, uint64_t n_pairs, double frac, uint8_t* verdict);
+/* Device time of the pair-search kernel of the last dcb_umi_pairs (CUDA events). */
+int dcb_dist_last_ms(dcb_dist*, double* ms);
+
+/* ---------------------------------------------------------------------------------------------
  * Synthetic workload generator: deterministic in (seed, read index).
  * ------------------------------------------------------------------------------------------- */
 typedef struct dcb_synth_params {
@@ -191,7 +219,9 @@ typedef struct dcb_synth_params {
     uint32_t sub_rate;     /* per-base substitution probability * 2^32 */
     uint32_t n_rate;       /* per-base N probability * 2^32 */
     uint32_t junk_rate;    /* probability * 2^32 that a read is random sequence (no TCR) */
-    uint32_t umi_pool;     /* != 0: UMIs are drawn from read_index % umi_pool (copies share a UMI) */
+    uint32_t umi_pool;     /* != 0: read i is a copy of molecule i % umi_pool (same rearrangement, same UMI) */
+    uint32_t sub_rate2;    /* per-base substitution probability * 2^32 in R2 (the barcode read) */
+    uint32_t reserved;
 } dcb_synth_params;
 typedef struct dcb_synth dcb_synth;
 dcb_synth* dcb_synth_create(const dcb_synth_params* p, int n_sets, const char* const* const* v_regions,

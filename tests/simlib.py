@@ -46,3 +46,22 @@ def sim_decombine(packed, vt, jt, both_frames=False, allow_ns=False, lenthreshol
                             int(lenthreshold), int(general_only), res.ctypes.data, cnt.ctypes.data, ctypes.byref(nd))
     assert rc == 0
     return res, cnt, nd.value
+
+
+_LEV_SRC = os.path.join(_HERE, "sim", "sim_lev.cpp")
+_LEV_SO = os.path.join(_HERE, "sim", "liblevsim.so")
+_lev = None
+
+
+def lev_sim():
+    """ctypes handle on csrc/lev_core.cuh compiled for the host (sim_umi_distance, sim_umi_may_be_within, sim_seq_distance)."""
+    global _lev
+    if _lev is None:
+        deps = [_LEV_SRC, os.path.join(_ROOT, "decombinator_b200", "csrc", "lev_core.cuh")]
+        if not os.path.exists(_LEV_SO) or any(os.path.getmtime(d) > os.path.getmtime(_LEV_SO) for d in deps):
+            subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", _LEV_SRC, "-o", _LEV_SO])
+        _lev = ctypes.CDLL(_LEV_SO)
+        _lev.sim_umi_distance.argtypes = [ctypes.c_uint64, ctypes.c_uint64]
+        _lev.sim_umi_may_be_within.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int]
+        _lev.sim_seq_distance.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    return _lev

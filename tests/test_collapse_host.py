@@ -1,0 +1,121 @@
+"""CPU-only: (1) the collapse oracle against fixtures recorded from the unmodified reference, (2) the bit-parallel
+Levenshtein code the kernels run (csrc/lev_core.cuh, compiled for the host by tests/sim) against the oracle, (3) the
+HOST logic of decombinator_b200.collapse -- grouping order, component order, counting -- with the distances supplied
+by the oracle in place of the GPU context.  The GPU suite (test_gpu_collapse.py) repeats (3) on the CUDA kernels."""
+import collections as coll
+import gzip
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import collapse_checks
+import collapse_oracle as CO
+import simlib
+from decombinator_b200 import _lib, collapse
+
+
+@pytest.fixture(scope="module")
+def collapse_cases(golden_dir):
+    with gzip.open(os.path.join(golden_dir, "collapse_cases.json.gz"), "rt") as fh:
+        return json.load(fh)
+
+
+@pytest.fixture
+def oracle_distances(monkeypatch):
+    """Install the oracle where decombinator_b200.collapse expects its GPU context (tests only)."""
+    monkeypatch.setattr(collapse, "_dist", CO.OracleDist())
+
+
+def test_collapse_oracle_matches_recorded_distances(collapse_cases):
+    for a, b, d in collapse_cases["distances"]:
+        assert CO.levenshtein(a, b) == d
+
+
+def test_collapse_oracle_matches_recorded_pairs_and_verdicts(collapse_cases):
+    for case in collapse_cases["cases"]:
+        row, col = CO.umi_pairs(case["umis"], case["args"]["bcthreshold"])
+        assert [[int(i), int(j)] for i, j in zip(row, col)] == case["pairs"]
+        protos = [k.split("|")[2] for k in case["group_keys"]]
+        frac = case["args"]["percentlevdist"] / 100
+        assert [CO.seqs_equivalent(protos[i], protos[j], frac) for i, j in case["pairs"]] == case["verdicts"]
+
+
+def test_device_levenshtein_code_matches_oracle(collapse_cases):
+    sim = simlib.lev_sim()
+    for a, b, d in collapse_cases["distances"]:
+        sa, _, _ = _lib.encode_seqs([a, b])
+        x, y = np.ascontiguousarray(sa[:len(a)]), np.ascontiguousarray(sa[len(a):])
+        assert sim.sim_seq_distance(x.ctypes.data, len(a), y.ctypes.data, len(b)) == d, (len(a), len(b))
+    rng = random.Random(3)
+    for _ in range(3000):
+        L = rng.choice((4, 8, 11, 12, 13, 17, 19))
+        a = "".join(rng.choice("ACGTNSL") for _ in range(L))
+        b = list(a)
+        for _ in range(rng.randrange(0, 4)):
+            op = rng.randrange(3)
+            if op == 0 and b:
+                b[rng.randrange(len(b))] = rng.choice("ACGT")
+            elif op == 1 and b:
+                del b[rng.randrange(len(b))]
+            elif len(b) < 19:
+                b.insert(rng.randrange(len(b) + 1), rng.choice("ACGT"))
+        b = "".join(b)
+        ca, cb = (int(x) for x in _lib.encode_umis([a, b]))
+        d = CO.levenshtein(a, b)
+        assert sim.sim_umi_distance(ca, cb) == d
+        for k in (0, 1, 2, 3):
+            if d <= k:  # the prefilter may never reject a pair that is within k edits
+                assert sim.sim_umi_may_be_within(ca, cb, k) == 1, (a, b, k)
+
+
+def test_host_logic_matches_reference_runs(collapse_cases, oracle_distances):
+    for case in collapse_cases["cases"]:
+        collapse_checks.check_case(case)
+
+
+@pytest.mark.parametrize("chain,name", [("a", "alpha"), ("b", "beta")])
+def test_host_logic_reproduces_golden_freq(golden_dir, tmp_path, oracle_distances, chain, name):
+    collapse_checks.check_tiny_freq(golden_dir, tmp_path, chain, name)
+
+
+def test_reference_unit_answers(oracle_distances):
+    collapse_checks.check_reference_unit_answers()
+
+
+def test_barcode_positions_known_answers():
+    """reference tests/test_collapse.py:55-195"""
+    c = coll.Counter()
+    m13, i8 = "GTCGTGACTGGGAAAACCCTGG", "GTCGTGAT"
+    f = collapse.get_barcode_positions
+    assert f("GTCGTGACTGGGAAAACCCTGGTTTCCGGTCGTGATAAAGTG", {"oligo": "m13", "allowNs": False}, c) == \
+        [len(m13), len(m13) + 6, len(m13) + 6 + len(i8), len(m13) + 6 + len(i8) + 6]
+    assert f("GTCGTGATTTTCCGGTCGTGATAAAGTG", {"oligo": "i8", "allowNs": False}, c) == [8, 14, 22, 28]
+    assert f("GAAGCTATCACGACATCACTAC", {"oligo": "i8_single", "allowNs": False}, c) == [0, 6, 14, 20]
+    assert f("CGGGCTTGGTATCGGCCGATCTACGGG", {"oligo": "nebio", "allowNs": False}, c) == [0, 17]
+    assert f("CTCGTTAGGTTCGTACGGGGATTGCA", {"oligo": "takara", "allowNs": False}, c) == [0, 12]
+    assert f("GTCGTGACTGGGAAAACCCTGGTTNCCGGTCGTGATAAAGTG", {"oligo": "m13", "allowNs": False}, c) is None
+    assert c["getbarcode_fail_N"] == 1
+    with pytest.raises(ValueError):
+        f("ACGT", {"oligo": "nope", "allowNs": False}, c)
+    for spacer, seq, lo, hi in (("GTCGTGACTGGGAAAACCCTGG", "GTCGTGACTGGGAAAACCCTGGTTTCCGGTCGTGATAAAGTG", 0, 32),
+                                ("GTCGTGAT", "GTCGTGATTTTCCGGTCGTGATAAAGTG", 0, 18), ("ATCACGAC", "GAAGCTATCACGACATCACTAC", 0, 18),
+                                ("TACGGG", "CGGGCTTGGTATCGGCCGATCTACGGG", 18, 28), ("GTACGGG", "CTCGTTAGGTTCGTACGGGGATTGCA", 0, 19)):
+        assert collapse.findFirstSpacer({"spcr1": spacer}, seq, lo, hi) == [spacer]
+
+
+def test_empty_n12_raises(tmp_path):
+    p = tmp_path / "empty.n12"
+    p.write_text("")
+    with pytest.raises(ValueError):
+        collapse.check_dcr_file(str(p), open)
+
+
+def test_distances_fail_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.DcbError):
+        _lib.Dist(0)

@@ -1,0 +1,143 @@
+"""Parity tests of the collapse distance kernels (csrc/collapse.cu) through the C ABI: dcb_umi_pairs and dcb_lev_leq
+against the oracle and against fixtures recorded from the unmodified reference; the collapse stage end to end with the
+distances on the GPU against the recorded runs and the reference's golden .freq files.  Bit-exact everywhere."""
+import gzip
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import collapse_checks
+import collapse_oracle as CO
+from decombinator_b200 import _lib, collapse
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def collapse_cases(golden_dir):
+    with gzip.open(os.path.join(golden_dir, "collapse_cases.json.gz"), "rt") as fh:
+        return json.load(fh)
+
+
+@pytest.fixture(scope="module")
+def dist():
+    d = _lib.Dist(0)
+    yield d
+    d.close()
+
+
+@pytest.fixture(autouse=True)
+def real_gpu_context():
+    collapse._dist = None   # whatever an earlier (CPU) test installed: the product path builds its own dcb_dist
+    yield
+
+
+def test_lev_leq_matches_recorded_distances(dist, collapse_cases):
+    pairs = collapse_cases["distances"]
+    seqs = [p[0] for p in pairs] + [p[1] for p in pairs]
+    sym, off, ln = _lib.encode_seqs(seqs)
+    n = len(pairs)
+    a, b = np.arange(n, dtype=np.uint32), np.arange(n, 2 * n, dtype=np.uint32)
+    for frac in (0.0, 0.05, 0.1, 0.13, 0.25, 1.0):
+        got = dist.lev_leq(sym, off, ln, a, b, frac)
+        want = [d <= min(len(x), len(y)) * frac for x, y, d in pairs]
+        assert got.tolist() == want, frac
+
+
+def test_lev_leq_random_pairs_vs_oracle(dist):
+    rng = random.Random(11)
+    seqs = []
+    for _ in range(600):
+        L = rng.choice((0, 1, 20, 63, 64, 65, 90, 128, 129, 130, 191, 193, 256, 257, 400, 512))
+        a = [rng.choice("ACGTN") for _ in range(L)]
+        b = list(a)
+        for _ in range(rng.randrange(0, 30)):
+            op = rng.randrange(3)
+            if op == 0 and b:
+                b[rng.randrange(len(b))] = rng.choice("ACGTRY")
+            elif op == 1 and b:
+                del b[rng.randrange(len(b))]
+            elif len(b) < 512:
+                b.insert(rng.randrange(len(b) + 1), rng.choice("ACGT"))
+        seqs += ["".join(a), "".join(b)]
+    sym, off, ln = _lib.encode_seqs(seqs)
+    a = np.arange(0, len(seqs), 2, dtype=np.uint32)
+    b = a + 1
+    for frac in (0.02, 0.1):
+        got = dist.lev_leq(sym, off, ln, a, b, frac)
+        want = [CO.seqs_equivalent(seqs[i], seqs[j], frac) for i, j in zip(a, b)]
+        assert got.tolist() == want
+
+
+def test_lev_leq_rejects_bad_input(dist):
+    sym, off, ln = _lib.encode_seqs(["A" * 513, "ACGT"])
+    with pytest.raises(_lib.DcbError):
+        dist.lev_leq(sym, off, ln, [0], [1], 0.1)
+    with pytest.raises(_lib.DcbError):
+        _lib.encode_umis(["A" * 20])
+
+
+@pytest.mark.parametrize("n,alphabet,length,k", [(0, "ACGT", 12, 2), (1, "ACGT", 12, 2), (2500, "ACGT", 6, 2), (3000, "AC", 12, 2),
+                                                  (2000, "ACGTNSL", 12, 1), (1500, "ACG", 17, 3), (700, "ACGT", 5, 0)])
+def test_umi_pairs_vs_oracle(dist, n, alphabet, length, k):
+    rng = random.Random(n + k)
+    umis = []
+    for _ in range(n):
+        L = length if rng.random() < 0.8 else max(1, length - rng.randrange(0, 3))
+        umis.append("".join(rng.choice(alphabet) for _ in range(L)))
+    row, col = dist.umi_pairs(_lib.encode_umis(umis), k)
+    wrow, wcol = CO.umi_pairs(umis, k)
+    assert np.array_equal(row, wrow) and np.array_equal(col, wcol)
+    assert np.all(row < col)
+    key = row * (1 << 32) + col
+    assert np.all(np.diff(key) > 0)   # sorted row-major, no duplicates
+
+
+def test_umi_pairs_matches_recorded_runs(dist, collapse_cases):
+    for case in collapse_cases["cases"]:
+        row, col = dist.umi_pairs(_lib.encode_umis(case["umis"]), case["args"]["bcthreshold"])
+        assert [[int(i), int(j)] for i, j in zip(row, col)] == case["pairs"]
+
+
+def test_umi_pairs_large_properties(dist):
+    """200 k UMIs (2e10 pair tests on the GPU): size-independent properties instead of the brute-force oracle."""
+    rng = np.random.default_rng(5)
+    n = 200_000
+    base = rng.integers(0, 4, size=(n, 12), dtype=np.uint64)
+    codes = np.full(n, 12 << 58, dtype=np.uint64)
+    for k in range(12):
+        codes |= base[:, k] << np.uint64(3 * k)
+    row, col = dist.umi_pairs(codes, 1)
+    assert np.all(row < col)
+    # every reported pair is really within one edit (sampled), and planted neighbours are all found
+    letters = np.array(list("ACGT"))
+    def s(i):
+        return "".join(letters[base[i].astype(int)])
+    for t in rng.integers(0, len(row), size=300):
+        assert CO.levenshtein(s(int(row[t])), s(int(col[t]))) <= 1
+    planted = base[:1000].copy()
+    planted[:, 5] = (planted[:, 5] + 1) % 4
+    codes2 = codes.copy()
+    extra = np.full(1000, 12 << 58, dtype=np.uint64)
+    for k in range(12):
+        extra |= planted[:, k] << np.uint64(3 * k)
+    row2, col2 = dist.umi_pairs(np.concatenate([codes2, extra]), 1)
+    found = set(zip(row2.tolist(), col2.tolist()))
+    assert all((i, n + i) in found for i in range(1000))
+
+
+def test_collapse_stage_matches_reference_runs(collapse_cases):
+    for case in collapse_cases["cases"]:
+        collapse_checks.check_case(case)
+
+
+@pytest.mark.parametrize("chain,name", [("a", "alpha"), ("b", "beta")])
+def test_collapse_reproduces_golden_freq(golden_dir, tmp_path, chain, name):
+    collapse_checks.check_tiny_freq(golden_dir, tmp_path, chain, name)
+
+
+def test_reference_unit_answers_on_gpu():
+    collapse_checks.check_reference_unit_answers()
