@@ -358,14 +358,12 @@ _BASE_ALPHABET = "ACGTNSL"
 
 
 def _alphabet(strings, limit=8):
-    """Symbol codes for the characters that occur: A C G T N S L first (fixed codes), then whatever else shows up."""
-    codes = {c: i for i, c in enumerate(_BASE_ALPHABET)}
-    extra = sorted(set("".join(strings)) - set(codes))
-    if len(extra) > limit - len(_BASE_ALPHABET):
-        raise DcbError("more than %d distinct symbols: %r" % (limit, "".join(extra)))
-    for c in extra:
-        codes[c] = len(codes)
-    return codes
+    """Symbol codes for the characters that occur (at most 8): A C G T N S L in that order, then whatever else."""
+    present = set("".join(strings))
+    order = [c for c in _BASE_ALPHABET if c in present] + sorted(present - set(_BASE_ALPHABET))
+    if len(order) > limit:
+        raise DcbError("more than %d distinct symbols: %r" % (limit, "".join(order)))
+    return {c: i for i, c in enumerate(order)}
 
 
 def encode_umis(umis):
