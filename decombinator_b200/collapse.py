@@ -357,24 +357,13 @@ class _BarcodeMachine:
         return None
 
 
-def read_in_data(data, inputargs, barcode_quality_parameters, lev_threshold_fraction, dont_count, opener):
-    """Filter the decombined rows, extract their barcodes and sort them into initial groups (collapse.py:482-701).
+def _filter_rows(data, inputargs, barcode_quality_parameters, dont_count, from_file, first_index=0):
+    """The per-row part of read_in_data (collapse.py:523-593): barcode location, quality and length filters.
 
-    Returns ``{"barcode|0|protoseq": [dcretc, ...]}`` in the reference's dict order."""
-    if inputargs["command"] == "collapse":
-        if not inputargs["dontcheckinput"]:
-            if not check_dcr_file(data, opener):
-                print("Please check that file contains suitable Decombinator output for collapsing.")
-                print("Alternatively, disable the input file sanity check by changing the 'dontcheckinput' flag, i.e. '-di True'")
-                sys.exit()
-        data = opener(data, "rt")
-    if not data:
-        raise ValueError("No reads found in input file. Check .n12 and log files for errors.")
-
-    print("Reading data in...")
+    -> ([(global row index, barcode, seq, dcretc), ...] for the rows that survive, Counter of str(dcr), rows seen).
+    Rows are independent here, so a multi-GPU run calls this on each rank's shard (parallel.py)."""
     t0 = time.time()
-    from_file = inputargs["command"] == "collapse"
-    machines = {}
+    kept = []
     input_dcr_counts = coll.Counter()
     lcount = -1
     for lcount, line in enumerate(data):
@@ -401,14 +390,22 @@ def read_in_data(data, inputargs, barcode_quality_parameters, lev_threshold_frac
         parts = [str(dcr), seq, line[7], line[5]]
         if inputargs["sampling_analysis"]:
             parts += [barcode, barcode_qualstring, line[8], line[10]]
+        kept.append((first_index + lcount, barcode, seq, "|".join(parts)))
+    return kept, input_dcr_counts, lcount + 1
+
+
+def _group_rows(kept, lev_threshold_fraction):
+    """Order-dependent grouping by exact barcode (collapse.py:595-682) of rows given in global input order.
+
+    -> list of finished _BarcodeMachine.  Only rows with the SAME barcode interact, so any partition of the barcodes
+    (parallel.py: hash(barcode) % world) can be grouped independently and merged by ``tick`` afterwards."""
+    machines = {}
+    for idx, barcode, seq, dcretc in kept:
         m = machines.get(barcode)
         if m is None:
             m = machines[barcode] = _BarcodeMachine(barcode)
-        m.rows.append((lcount, seq, "|".join(parts)))
-    if from_file:
-        data.close()
-
-    # run the per-barcode machines; each round resolves, in one GPU batch, every verdict some machine waits for
+        m.rows.append((idx, seq, dcretc))
+    # each round resolves, in one GPU batch, every verdict some machine waits for
     cache, waiting = {}, list(machines.values())
     while waiting:
         need, blocked = {}, []
@@ -422,21 +419,48 @@ def read_in_data(data, inputargs, barcode_quality_parameters, lev_threshold_frac
             for key, verdict in zip(keys, _verdicts(keys, lev_threshold_fraction)):
                 cache[key] = verdict
         waiting = blocked
+    return list(machines.values())
 
-    groups = sorted((m for m in machines.values() if m.members is not None), key=lambda m: m.tick)
+
+def _groups_to_dict(groups, input_dcr_counts, dropped, dead):
+    """[(tick, barcode, proto, members)] -> the reference's ``barcode_dcretc`` dict (in its insertion order) + counters."""
     barcode_dcretc = coll.defaultdict(list)
-    for m in groups:
-        barcode_dcretc["|".join([m.barcode, "0", m.proto])] = m.members
-    counts["multi_tcr_barcode_reads"] += sum(m.dropped for m in machines.values())
-    if counts["multi_tcr_barcode_reads"] == 0:
-        del counts["multi_tcr_barcode_reads"]
+    for _, barcode, proto, members in sorted(groups, key=lambda g: g[0]):
+        barcode_dcretc["|".join([barcode, "0", proto])] = members
+    if dropped:
+        counts["multi_tcr_barcode_reads"] += dropped
     counts["readdata_barcode_dcretc_keys"] = len(barcode_dcretc)
     counts["number_input_unique_dcrs"] = len(input_dcr_counts)
     counts["number_input_total_dcrs"] = sum(input_dcr_counts.values())
-    counts["multi_tcr_barcodes"] = sum(1 for m in machines.values() if m.dead)
+    counts["multi_tcr_barcodes"] = dead
+    return barcode_dcretc
 
+
+def read_in_data(data, inputargs, barcode_quality_parameters, lev_threshold_fraction, dont_count, opener):
+    """Filter the decombined rows, extract their barcodes and sort them into initial groups (collapse.py:482-701).
+
+    Returns ``{"barcode|0|protoseq": [dcretc, ...]}`` in the reference's dict order."""
+    if inputargs["command"] == "collapse":
+        if not inputargs["dontcheckinput"]:
+            if not check_dcr_file(data, opener):
+                print("Please check that file contains suitable Decombinator output for collapsing.")
+                print("Alternatively, disable the input file sanity check by changing the 'dontcheckinput' flag, i.e. '-di True'")
+                sys.exit()
+        data = opener(data, "rt")
+    if not data:
+        raise ValueError("No reads found in input file. Check .n12 and log files for errors.")
+
+    print("Reading data in...")
+    t0 = time.time()
+    from_file = inputargs["command"] == "collapse"
+    kept, input_dcr_counts, n_lines = _filter_rows(data, inputargs, barcode_quality_parameters, dont_count, from_file)
+    if from_file:
+        data.close()
+    machines = _group_rows(kept, lev_threshold_fraction)
+    barcode_dcretc = _groups_to_dict([(m.tick, m.barcode, m.proto, m.members) for m in machines if m.members is not None],
+                                     input_dcr_counts, sum(m.dropped for m in machines), sum(1 for m in machines if m.dead))
     t1 = time.time()
-    print("   Read in total of", lcount + 1, "lines")
+    print("   Read in total of", n_lines, "lines")
     print("  ", counts["readdata_success"], "reads sorted into", len(barcode_dcretc), "initial groups")
     print("  ", round(t1 - t0, 2), "seconds")
     counts["time_readdata_s"] = t1
@@ -560,10 +584,8 @@ def cluster_UMIs(barcode_dcretc, inputargs, barcode_threshold, lev_threshold_fra
     return clusters
 
 
-def collapsinate(data, inputargs, barcode_quality_parameters, lev_threshold_fraction, barcode_distance_threshold, outpath,
-                 file_id, dont_count, opener=None):
-    """read in -> cluster -> count (collapse.py:897-976)."""
-    barcode_dcretc = read_in_data(data, inputargs, barcode_quality_parameters, lev_threshold_fraction, dont_count, opener)
+def _count_clusters(barcode_dcretc, inputargs, barcode_distance_threshold, lev_threshold_fraction, dont_count, outpath, file_id):
+    """cluster -> count (collapse.py:919-976), from the initial groups on."""
     clusters = cluster_UMIs(barcode_dcretc, inputargs, barcode_distance_threshold, lev_threshold_fraction, dont_count)
 
     print("Collapsing clusters...")
@@ -598,6 +620,82 @@ def collapsinate(data, inputargs, barcode_quality_parameters, lev_threshold_frac
     return out_data, collapsed, average_cluster_size_counter
 
 
+def collapsinate(data, inputargs, barcode_quality_parameters, lev_threshold_fraction, barcode_distance_threshold, outpath,
+                 file_id, dont_count, opener=None):
+    """read in -> cluster -> count (collapse.py:897-976)."""
+    barcode_dcretc = read_in_data(data, inputargs, barcode_quality_parameters, lev_threshold_fraction, dont_count, opener)
+    return _count_clusters(barcode_dcretc, inputargs, barcode_distance_threshold, lev_threshold_fraction, dont_count, outpath,
+                           file_id)
+
+
+def _write_summary(inputargs, file_id, average_cluster_size_counter):
+    """Collapsing summary CSV (+ optional UMI histogram), collapse.py:1040-1224."""
+    chainnams = {"a": "alpha", "b": "beta", "g": "gamma", "d": "delta"}
+    chain_name = chainnams[inputargs["chain"].lower()]
+    logpath = inputargs["outpath"] + f"Logs{os.sep}"
+    sample_name = file_id.split(os.sep)[-1]
+    if not os.path.exists(logpath):
+        os.makedirs(logpath)
+    date = time.strftime("%Y_%m_%d")
+    stem = logpath + date + "_" + "dcr_" + sample_name + f"_{chain_name}" + "_Collapsing_Summary"
+    summaryname = stem + ".csv"
+    if os.path.exists(summaryname):
+        for i in range(2, 10000):
+            summaryname = stem + str(i) + ".csv"
+            if not os.path.exists(summaryname):
+                break
+    inout_name = "_".join(f"{file_id}".split("_")[:-1]) + f"_{chain_name}"
+    out = ["Property,Value", "Version," + str(__version__), "Directory," + os.getcwd(), "InputFile," + inout_name,
+           "OutputFile," + inout_name, "DateFinished," + date, "TimeFinished," + time.strftime("%H:%M:%S"),
+           "TimeTaken(Seconds)," + str(round(counts["time_taken_total_s"], 2)), ""]
+    for s in ["extension", "dontgzip", "allowNs", "dontcheckinput", "barcodeduplication", "minbcQ", "bcQbelowmin",
+              "bcthreshold", "lenthreshold", "percentlevdist", "avgQthreshold", "positionalbarcodes", "oligo"]:
+        out.append(s + "," + str(inputargs[s]))
+    counts["pc_input_dcrs"] = counts["number_input_total_dcrs"] / counts["readdata_input_dcrs"]
+    counts["pc_uniq_dcr_kept"] = counts["number_output_unique_dcrs"] / counts["number_input_unique_dcrs"]
+    counts["pc_total_dcr_kept"] = counts["number_output_total_dcrs"] / counts["number_input_total_dcrs"]
+    counts["avg_input_tcr_size"] = counts["number_input_total_dcrs"] / counts["number_input_unique_dcrs"]
+    counts["avg_output_tcr_size"] = counts["number_output_total_dcrs"] / counts["number_output_unique_dcrs"]
+    counts["avg_RNA_duplication"] = 1 / counts["pc_total_dcr_kept"]
+    out.append("")
+    for label, key, nd in (("InputUncollapsedDCRLines", "readdata_input_dcrs", None),
+                           ("UniqueDCRsPassingFilters", "number_input_unique_dcrs", None),
+                           ("TotalDCRsPassingFilters", "number_input_total_dcrs", None),
+                           ("PercentDCRPassingFilters(withbarcode)", "pc_input_dcrs", 3),
+                           ("UniqueDCRsPostCollapsing", "number_output_unique_dcrs", None),
+                           ("TotalDCRsPostCollapsing", "number_output_total_dcrs", None),
+                           ("PercentUniqueDCRsKept", "pc_uniq_dcr_kept", 3),
+                           ("PercentTotalDCRsKept", "pc_total_dcr_kept", 3),
+                           ("AverageInputTCRAbundance", "avg_input_tcr_size", 3),
+                           ("AverageOutputTCRAbundance", "avg_output_tcr_size", 3),
+                           ("AverageRNAduplication", "avg_RNA_duplication", 3)):
+        out.append(label + "," + str(counts[key] if nd is None else round(counts[key], nd)))
+    out.append("")
+    for label, key in (("BarcodeFail_ContainedNs", "getbarcode_fail_N"),
+                       ("BarcodeFail_SpacersNotFound", "readdata_fail_no_bclocs"),
+                       ("BarcodeFail_LowQuality", "readdata_fail_low_barcode_quality"),
+                       ("NumberMultiTCRBarcodes", "multi_tcr_barcodes"),
+                       ("NumberMultiTCRBarcodeReads", "multi_tcr_barcode_reads"),
+                       ("MedianUMIsPerTCR", "median_barcodes_per_tcr")):
+        out.append(label + "," + str(counts[key]))
+    with open(summaryname, "w") as fh:
+        print("\n".join(out), file=fh)
+
+    if inputargs["UMIhistogram"]:
+        hfileprefix = "_".join(summaryname.split("_")[:-2] + ["UMIhistogram"])
+        if os.path.exists(hfileprefix + ".csv"):
+            i = 1
+            while os.path.exists(hfileprefix + str(i) + ".csv"):
+                i += 1
+            hfileprefix += str(i)
+        hfilename = hfileprefix + ".csv"
+        with open(hfilename, "w") as hfile:
+            for av, count in sorted(average_cluster_size_counter.items()):
+                print(str(av) + "," + str(count), file=hfile)
+        print("\nAverage UMI cluster size histogram data saved to", hfilename)
+
+
+
 def collapsinator(inputargs: dict, data: list = None) -> list:
     """Function wrapper for Collapsinator (collapse.py:979-1226)."""
     global counts
@@ -623,67 +721,5 @@ def collapsinator(inputargs: dict, data: list = None) -> list:
     counts["time_taken_total_s"] = counts["end_time"] - counts["start_time"]
 
     if inputargs["suppresssummary"] == False:  # noqa: E712
-        chainnams = {"a": "alpha", "b": "beta", "g": "gamma", "d": "delta"}
-        chain_name = chainnams[inputargs["chain"].lower()]
-        logpath = inputargs["outpath"] + f"Logs{os.sep}"
-        sample_name = file_id.split(os.sep)[-1]
-        if not os.path.exists(logpath):
-            os.makedirs(logpath)
-        date = time.strftime("%Y_%m_%d")
-        stem = logpath + date + "_" + "dcr_" + sample_name + f"_{chain_name}" + "_Collapsing_Summary"
-        summaryname = stem + ".csv"
-        if os.path.exists(summaryname):
-            for i in range(2, 10000):
-                summaryname = stem + str(i) + ".csv"
-                if not os.path.exists(summaryname):
-                    break
-        inout_name = "_".join(f"{file_id}".split("_")[:-1]) + f"_{chain_name}"
-        out = ["Property,Value", "Version," + str(__version__), "Directory," + os.getcwd(), "InputFile," + inout_name,
-               "OutputFile," + inout_name, "DateFinished," + date, "TimeFinished," + time.strftime("%H:%M:%S"),
-               "TimeTaken(Seconds)," + str(round(counts["time_taken_total_s"], 2)), ""]
-        for s in ["extension", "dontgzip", "allowNs", "dontcheckinput", "barcodeduplication", "minbcQ", "bcQbelowmin",
-                  "bcthreshold", "lenthreshold", "percentlevdist", "avgQthreshold", "positionalbarcodes", "oligo"]:
-            out.append(s + "," + str(inputargs[s]))
-        counts["pc_input_dcrs"] = counts["number_input_total_dcrs"] / counts["readdata_input_dcrs"]
-        counts["pc_uniq_dcr_kept"] = counts["number_output_unique_dcrs"] / counts["number_input_unique_dcrs"]
-        counts["pc_total_dcr_kept"] = counts["number_output_total_dcrs"] / counts["number_input_total_dcrs"]
-        counts["avg_input_tcr_size"] = counts["number_input_total_dcrs"] / counts["number_input_unique_dcrs"]
-        counts["avg_output_tcr_size"] = counts["number_output_total_dcrs"] / counts["number_output_unique_dcrs"]
-        counts["avg_RNA_duplication"] = 1 / counts["pc_total_dcr_kept"]
-        out.append("")
-        for label, key, nd in (("InputUncollapsedDCRLines", "readdata_input_dcrs", None),
-                               ("UniqueDCRsPassingFilters", "number_input_unique_dcrs", None),
-                               ("TotalDCRsPassingFilters", "number_input_total_dcrs", None),
-                               ("PercentDCRPassingFilters(withbarcode)", "pc_input_dcrs", 3),
-                               ("UniqueDCRsPostCollapsing", "number_output_unique_dcrs", None),
-                               ("TotalDCRsPostCollapsing", "number_output_total_dcrs", None),
-                               ("PercentUniqueDCRsKept", "pc_uniq_dcr_kept", 3),
-                               ("PercentTotalDCRsKept", "pc_total_dcr_kept", 3),
-                               ("AverageInputTCRAbundance", "avg_input_tcr_size", 3),
-                               ("AverageOutputTCRAbundance", "avg_output_tcr_size", 3),
-                               ("AverageRNAduplication", "avg_RNA_duplication", 3)):
-            out.append(label + "," + str(counts[key] if nd is None else round(counts[key], nd)))
-        out.append("")
-        for label, key in (("BarcodeFail_ContainedNs", "getbarcode_fail_N"),
-                           ("BarcodeFail_SpacersNotFound", "readdata_fail_no_bclocs"),
-                           ("BarcodeFail_LowQuality", "readdata_fail_low_barcode_quality"),
-                           ("NumberMultiTCRBarcodes", "multi_tcr_barcodes"),
-                           ("NumberMultiTCRBarcodeReads", "multi_tcr_barcode_reads"),
-                           ("MedianUMIsPerTCR", "median_barcodes_per_tcr")):
-            out.append(label + "," + str(counts[key]))
-        with open(summaryname, "w") as fh:
-            print("\n".join(out), file=fh)
-
-        if inputargs["UMIhistogram"]:
-            hfileprefix = "_".join(summaryname.split("_")[:-2] + ["UMIhistogram"])
-            if os.path.exists(hfileprefix + ".csv"):
-                i = 1
-                while os.path.exists(hfileprefix + str(i) + ".csv"):
-                    i += 1
-                hfileprefix += str(i)
-            hfilename = hfileprefix + ".csv"
-            with open(hfilename, "w") as hfile:
-                for av, count in sorted(average_cluster_size_counter.items()):
-                    print(str(av) + "," + str(count), file=hfile)
-            print("\nAverage UMI cluster size histogram data saved to", hfilename)
+        _write_summary(inputargs, file_id, average_cluster_size_counter)
     return out_data

@@ -174,6 +174,9 @@ def decombinator(inputargs: dict) -> list:
     outdata = []
     if inputargs["nobarcoding"] == False:  # noqa: E712
         batch = fastq.load_pairs(inputargs, opener)
+        if inputargs.get("shard"):   # multi-GPU run (parallel.py): this rank analyses one contiguous shard of the reads
+            from .parallel import shard_bounds
+            batch = batch.shard(*shard_bounds(len(batch), *inputargs["shard"]))
         n = len(batch)
         if inputargs["allowNs"] == False:  # noqa: E712
             counts["dcrfilter_barcodeN"] += sum(1 for bc in batch.bc if "N" in bc)

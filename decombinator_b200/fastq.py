@@ -99,6 +99,13 @@ class ReadBatch:
     def __len__(self):
         return len(self.vdj)
 
+    def shard(self, lo, hi):
+        """The records [lo, hi) as a batch of their own (multi-GPU runs: one contiguous shard per rank)."""
+        part = ReadBatch()
+        for name in ("ids", "vdj", "vdjqual", "bc", "bcq", "v_tail"):
+            setattr(part, name, getattr(self, name)[lo:hi])
+        return part.finalize()
+
 
 def load_pairs(inputargs, opener) -> ReadBatch:
     """The record handling at the top of the hot loop (decombine.py:950-983)."""

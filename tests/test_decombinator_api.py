@@ -86,3 +86,52 @@ def test_readfq_matches_reference_parser_quirks(tmp_path):
     import decombine_oracle as O
     assert got == list(O.readfq(_io.StringIO(text)))
     assert got[0] == ("r1", "ACGTAC", "FFFFFF") and got[2] == ("fa", "ACGT", None)
+
+
+def _sharded_worker(rank, world, port, tmp, out_path):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "oracle"), os.path.join(root, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    # two ranks share the one GPU of the test box: LOCAL_RANK stays 0, the rendezvous is gloo
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK="0", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import json
+    import torch.distributed as dist
+    from decombinator_b200 import collapse as C, decombine as D, parallel
+    parallel.init_from_env("gloo")
+    args = _args(os.path.join(tmp, "TINY_1.fq"), "b", tmp, suppresssummary=True, oligo="M13", command="pipeline")
+    rows = parallel.decombinator_sharded(args)
+    # every rank keeps its own shard for the collapse all-to-all
+    lo, hi = parallel.shard_bounds(106, rank, world)
+    args2 = dict(args, shard=(rank, world))
+    mine = D.decombinator(args2)
+    n_before = [None] * world
+    dist.all_gather_object(n_before, len(mine))
+    freq = parallel.collapsinator_sharded(args, data=mine, first_index=sum(n_before[:rank]))
+    if rank == 0:
+        json.dump({"rows": rows, "vj": int(D.counts["vj_count"]), "freq": freq}, open(out_path, "w"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@gpu
+def test_two_rank_pipeline_equals_golden(golden_dir, tmp_path):
+    """decombine sharded over two ranks (contiguous shards, no collective) + collapse with the barcode-hash all-to-all
+    reproduces the single-process goldens: .n12 rows in input order and the .freq rows."""
+    import json
+    import socket
+    import torch.multiprocessing as mp
+    for f in ("TINY_1.fq", "TINY_2.fq"):
+        shutil.copy(os.path.join(golden_dir, f), tmp_path / f)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out_path = str(tmp_path / "out.json")
+    mp.spawn(_sharded_worker, args=(2, port, str(tmp_path), out_path), nprocs=2, join=True)
+    got = json.load(open(out_path))
+    want_n12 = open(os.path.join(golden_dir, "dcr_TINY_1_beta.n12")).read()
+    assert "".join(", ".join(map(str, r)) + "\n" for r in got["rows"]) == want_n12
+    assert got["vj"] == 48
+    want_freq = open(os.path.join(golden_dir, "dcr_TINY_1_beta.freq")).read()
+    assert "".join(", ".join(map(str, r)) + "\n" for r in got["freq"]) == want_freq
