@@ -208,14 +208,13 @@ def main():
         clocks = sampler.stop(t0, t1) if sampler else None
 
         # ---- e2e: host packed buffers -> results in host memory through dcb_decombine_batch ------------
-        for _ in range(2):
-            ctx.decombine(packed)
+        for _ in range(3):
+            ctx.decombine(packed, pinned=True)
         barrier()
         e0 = time.perf_counter()
-        e2e_steps = max(1, min(args.steps, 5))
+        e2e_steps = max(1, min(args.steps, 10))
         for _ in range(e2e_steps):
-            res_e, cnt_e = ctx.decombine(packed)
-        torch.cuda.synchronize()
+            res_e, cnt_e = ctx.decombine(packed, pinned=True)   # synchronous: results are in host memory on return
         e_ms = (time.perf_counter() - e0) * 1e3
         assert np.array_equal(res_e, res0) and np.array_equal(cnt_e, cnt0)
 
@@ -242,6 +241,12 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = bytes_per_read * n / (exact_ms / 1e3) / 1e9
+        traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of one exact-kernel launch (ncu --set full), per read
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = float(t["dram_bytes_per_read"]) * n
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -249,9 +254,9 @@ def main():
             "decombined_fraction": decombined / (world * n), "deferred_to_general_kernel": n_deferred / n,
             "kernels_ms": {"dcb_exact_kernel": exact_ms, "dcb_general_kernel": general_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "dcb_exact_kernel", "bytes_per_read": bytes_per_read,
+                         "traffic": traffic, "kernel": "dcb_exact_kernel_spec", "bytes_per_read": bytes_per_read,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650"},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(packed.nbytes()),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(packed.h2d_bytes()),
                     "d2h_bytes_per_step": int(n * 16 + 8 * _lib.NCOUNTERS), "steps": e2e_steps},
             "gpu_launches": int(klaunch.sum()),
             "clocks": clocks,

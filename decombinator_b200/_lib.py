@@ -81,6 +81,9 @@ def lib():
     L.dcb_ctx_destroy.argtypes = [vp]
     L.dcb_ctx_set_stream.argtypes = [vp, vp]
     L.dcb_decombine_batch.argtypes = [vp, ctypes.POINTER(CPacked), vp, vp]
+    L.dcb_pinned_alloc.restype = vp
+    L.dcb_pinned_alloc.argtypes = [ctypes.c_size_t]
+    L.dcb_pinned_free.argtypes = [vp]
     L.dcb_upload.argtypes = [vp, ctypes.POINTER(CPacked)]
     L.dcb_run_resident.argtypes = [vp]
     L.dcb_download.argtypes = [vp, vp, vp]
@@ -201,6 +204,12 @@ class Packed:
         n = self.n_reads
         return n * self.slot_words * 4 + n * 2 + ((n + 31) // 32) * 4 + c.n_exc * 7
 
+    def h2d_bytes(self):
+        """Bytes dcb_decombine_batch copies to the device for this batch."""
+        c = self._p.contents
+        n = self.n_reads
+        return n * self.slot_words * 4 + (0 if c.uniform_len else n * 2) + ((((n + 31) // 32) * 4 + c.n_exc * 7) if c.n_exc else 0)
+
     def unpack(self, i):
         buf = ctypes.create_string_buffer(self.max_len + 1)
         n = lib().dcb_unpack_read(self._p, i, buf, self.max_len + 1)
@@ -257,9 +266,22 @@ class Context:
     def set_stream(self, cuda_stream):
         _check(lib().dcb_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream)), "dcb_ctx_set_stream")
 
-    def decombine(self, packed: Packed, counters=None):
-        """dcb_decombine_batch: host buffers in, host buffers out."""
-        res = np.zeros(packed.n_reads, dtype=RESULT_DTYPE)
+    def _pinned_results(self, n):
+        """A page-locked result array of n records (dcb_pinned_alloc), kept and reused while it is large enough."""
+        if getattr(self, "_pin_cap", 0) < n:
+            if getattr(self, "_pin_ptr", None):
+                lib().dcb_pinned_free(self._pin_ptr)
+            self._pin_cap = max(n, 1)
+            self._pin_ptr = lib().dcb_pinned_alloc(self._pin_cap * RESULT_DTYPE.itemsize)
+            if not self._pin_ptr:
+                raise DcbError("dcb_pinned_alloc: " + lib().dcb_last_error().decode())
+        buf = (ctypes.c_uint8 * (n * RESULT_DTYPE.itemsize)).from_address(self._pin_ptr)
+        return np.frombuffer(buf, dtype=RESULT_DTYPE, count=n)
+
+    def decombine(self, packed: Packed, counters=None, pinned=False):
+        """dcb_decombine_batch: host buffers in, host buffers out.  pinned=True returns a view of a page-locked buffer
+        owned by this context (valid until the next pinned call) instead of a fresh array."""
+        res = self._pinned_results(packed.n_reads) if pinned else np.zeros(packed.n_reads, dtype=RESULT_DTYPE)
         if counters is None:
             counters = np.zeros(NCOUNTERS, dtype=np.uint64)
         _check(lib().dcb_decombine_batch(self._h, packed.c, res.ctypes.data, counters.ctypes.data), "dcb_decombine_batch")
@@ -300,6 +322,10 @@ class Context:
         if self._h:
             lib().dcb_ctx_destroy(self._h)
             self._h = None
+        if getattr(self, "_pin_ptr", None):
+            lib().dcb_pinned_free(self._pin_ptr)
+            self._pin_ptr = None
+            self._pin_cap = 0
 
     def __del__(self):
         try:

@@ -36,6 +36,7 @@ struct BatchDev {
     const uint16_t* exc_pos;
     const uint8_t* exc_kind;
     uint32_t n_reads, slot_words, uniform_len, n_exc;
+    uint32_t first;   // the launch covers reads [first, first + n_reads); every array is indexed by the global read index
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -119,6 +120,8 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* a, uint32_t 
 
 static constexpr int kExactThreads = 512;   // upper bounds; long reads launch narrower blocks (shared memory)
 static constexpr int kGeneralThreads = 128;
+static constexpr int kMaxChunks = 256;             // queue counters per context
+static constexpr uint32_t kChunkReads = 1u << 20;  // reads per chunk of the pipelined host-to-host path
 
 // Shared-memory carve-up common to the kernels: [table 0..3][per-thread columns][counters][mbarrier]
 struct Tables4 {
@@ -185,8 +188,8 @@ dcb_exact_kernel(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_res
     const int tid = threadIdx.x;
     const uint32_t n_tiles = (b.n_reads + T - 1) / T;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint32_t ri = tile * T + tid;
-        const bool live = ri < b.n_reads;
+        const uint32_t ri = b.first + tile * T + tid;
+        const bool live = tile * T + tid < b.n_reads;
         int action = FAST_DONE;
         dcb_result out;
         *reinterpret_cast<uint4*>(&out) = make_uint4(0, 0, 0, 0);
@@ -343,8 +346,8 @@ dcb_exact_kernel_spec(BatchDev b, Tables4 tb, SpecBlooms bl, DcrParams prm, int 
     const uint32_t n_tiles = (b.n_reads + T - 1) / T;
 
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint32_t ri = tile * T + tid;
-        const bool live = ri < b.n_reads;
+        const uint32_t ri = b.first + tile * T + tid;
+        const bool live = tile * T + tid < b.n_reads;
         int action = FAST_DONE;
         dcb_result out;
         *reinterpret_cast<uint4*>(&out) = make_uint4(0, 0, 0, 0);
@@ -415,7 +418,7 @@ dcb_general_kernel(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_r
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t item = tile * T + tid;
         if (item >= n_items) continue;
-        const uint32_t ri = queue ? queue[item] : item;
+        const uint32_t ri = queue ? queue[item] : b.first + item;
         const uint4* src = reinterpret_cast<const uint4*>(b.words + (size_t)ri * b.slot_words);
         for (int k = 0; k < nw / 4; k++) {
             uint4 v = __ldg(src + k);
@@ -474,7 +477,8 @@ struct dcb_ctx {
     int device = 0;
     int n_sms = 0;
     dcb_params params{};
-    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
     // device copies of the table blobs: general (V, J), tag records (V, J), seed indexes (V, J, union of both)
     uint32_t *d_vgen = nullptr, *d_jgen = nullptr, *d_vcore = nullptr, *d_jcore = nullptr;
     uint32_t *d_vidx = nullptr, *d_jidx = nullptr, *d_uidx = nullptr;
@@ -587,6 +591,9 @@ dcb_ctx* dcb_ctx_create(int device, const dcb_tagset* v, const dcb_tagset* j, co
     c->n_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate");
     c->stream = c->own_stream;
+    if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate");
+    if (cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming) != cudaSuccess) return fail("cudaEventCreate");
     if (upload_blob(v->general, &c->d_vgen, &c->vgen_words) || upload_blob(j->general, &c->d_jgen, &c->jgen_words) ||
         upload_blob(v->core, &c->d_vcore, &c->vcore_words) || upload_blob(j->core, &c->d_jcore, &c->jcore_words) ||
         upload_blob(v->index, &c->d_vidx, &c->vidx_words) || upload_blob(j->index, &c->d_jidx, &c->jidx_words))
@@ -605,7 +612,7 @@ dcb_ctx* dcb_ctx_create(int device, const dcb_tagset* v, const dcb_tagset* j, co
             }
         }
     }
-    if (cudaMalloc((void**)&c->d_queue_count, 16) != cudaSuccess) return fail("cudaMalloc");
+    if (cudaMalloc((void**)&c->d_queue_count, sizeof(uint32_t) * kMaxChunks) != cudaSuccess) return fail("cudaMalloc");
     if (cudaMalloc((void**)&c->d_counters, sizeof(unsigned long long) * DCB_NCOUNTERS) != cudaSuccess) return fail("cudaMalloc");
     return c;
 }
@@ -615,6 +622,9 @@ void dcb_ctx_destroy(dcb_ctx* c) {
     cudaSetDevice(c->device);
     timing_collect(c);
     if (c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
+    if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+    if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+    if (c->ev_done) cudaEventDestroy(c->ev_done);
     cudaFree(c->d_vgen); cudaFree(c->d_jgen); cudaFree(c->d_vcore); cudaFree(c->d_jcore);
     cudaFree(c->d_vidx); cudaFree(c->d_jidx); cudaFree(c->d_uidx);
     cudaFree(c->d_queue_count); cudaFree(c->d_counters);
@@ -629,33 +639,23 @@ int dcb_ctx_set_stream(dcb_ctx* c, void* cuda_stream) {
     return DCB_OK;
 }
 
-int dcb_upload(dcb_ctx* c, const dcb_packed* P) {
-    if (!c || !P) { dcb_set_error("dcb_upload: null argument"); return DCB_EINVAL; }
-    if (P->n_reads >= 0xFFFFFFFFull) { dcb_set_error("dcb_upload: batch too large"); return DCB_EINVAL; }
-    CUDA_TRY(cudaSetDevice(c->device));
+// Size the device buffers for batch P, point the BatchDev at them and pick the launch geometry.  No copies.
+static int prepare_batch(dcb_ctx* c, const dcb_packed* P) {
+    if (P->n_reads >= 0xFFFFFFFFull) { dcb_set_error("batch too large"); return DCB_EINVAL; }
     const size_t n = P->n_reads, sw = P->slot_words;
+    if (sw == 0 || sw % 4) { dcb_set_error("slot_words must be a positive multiple of 4"); return DCB_EINVAL; }
     int rc;
     if ((rc = c->words.ensure(n * sw * 4 + 16)) || (rc = c->lens.ensure(n * 2 + 16)) ||
         (rc = c->flags.ensure(((n + 31) / 32) * 4 + 16)) || (rc = c->exc_read.ensure((size_t)P->n_exc * 4 + 16)) ||
         (rc = c->exc_pos.ensure((size_t)P->n_exc * 2 + 16)) || (rc = c->exc_kind.ensure((size_t)P->n_exc + 16)) ||
         (rc = c->results.ensure(n * sizeof(dcb_result) + 16)) || (rc = c->queue.ensure(n * 4 + 16)))
         return rc;
-    cudaStream_t s = c->stream;
-    if (n) {
-        CUDA_TRY(cudaMemcpyAsync(c->words.p, P->words, n * sw * 4, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(c->lens.p, P->lens, n * 2, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(c->flags.p, P->flags, ((n + 31) / 32) * 4, cudaMemcpyHostToDevice, s));
-    }
-    if (P->n_exc) {
-        CUDA_TRY(cudaMemcpyAsync(c->exc_read.p, P->exc_read, (size_t)P->n_exc * 4, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(c->exc_pos.p, P->exc_pos, (size_t)P->n_exc * 2, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(c->exc_kind.p, P->exc_kind, (size_t)P->n_exc, cudaMemcpyHostToDevice, s));
-    }
     BatchDev& b = c->batch;
     b.words = (const uint32_t*)c->words.p; b.lens = (const uint16_t*)c->lens.p; b.flags = (const uint32_t*)c->flags.p;
     b.exc_read = (const uint32_t*)c->exc_read.p; b.exc_pos = (const uint16_t*)c->exc_pos.p;
     b.exc_kind = (const uint8_t*)c->exc_kind.p;
     b.n_reads = (uint32_t)n; b.slot_words = (uint32_t)sw; b.uniform_len = P->uniform_len; b.n_exc = P->n_exc;
+    b.first = 0;
     c->have_batch = true; c->ran = false;
 
     // launch geometry: persistent blocks, a whole number of blocks per SM; long reads get narrower blocks
@@ -693,7 +693,7 @@ int dcb_upload(dcb_ctx* c, const dcb_packed* P) {
             c->exact_smem = (tbl_e + sw * T) * 4 + tail;
             if (c->exact_smem <= kMaxSmem) break;
         }
-        if (T < 32) { dcb_set_error("dcb_upload: tag tables + %u-nt reads do not fit in shared memory", P->max_len); return DCB_EUNSUPPORTED; }
+        if (T < 32) { dcb_set_error("tag tables + %u-nt reads do not fit in shared memory", P->max_len); return DCB_EUNSUPPORTED; }
         c->exact_threads = T;
         CUDA_TRY(cudaFuncSetAttribute(dcb_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->exact_smem));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, dcb_exact_kernel, T, c->exact_smem));
@@ -704,33 +704,48 @@ int dcb_upload(dcb_ctx* c, const dcb_packed* P) {
             c->general_smem = ((size_t)c->vgen_words + c->jgen_words + (sw + nwi) * T * (c->params.both_frames ? 2 : 1)) * 4 + tail;
             if (c->general_smem <= kMaxSmem) break;
         }
-        if (T < 32) { dcb_set_error("dcb_upload: tag tables + %u-nt reads do not fit in shared memory", P->max_len); return DCB_EUNSUPPORTED; }
+        if (T < 32) { dcb_set_error("tag tables + %u-nt reads do not fit in shared memory", P->max_len); return DCB_EUNSUPPORTED; }
         c->general_threads = T;
         CUDA_TRY(cudaFuncSetAttribute(dcb_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->general_smem));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, dcb_general_kernel, T, c->general_smem));
     }
-    if (occ_e < 1 || occ_g < 1) { dcb_set_error("dcb_upload: kernel does not fit on an SM"); return DCB_EUNSUPPORTED; }
+    if (occ_e < 1 || occ_g < 1) { dcb_set_error("kernel does not fit on an SM"); return DCB_EUNSUPPORTED; }
     const uint32_t tiles_e = (uint32_t)((n + c->exact_threads - 1) / c->exact_threads);
     const uint32_t tiles_g = (uint32_t)((n + c->general_threads - 1) / c->general_threads);
     c->exact_grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(tiles_e, (uint32_t)(c->n_sms * occ_e)));
     c->general_grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(tiles_g, (uint32_t)(c->n_sms * occ_g)));
-    CUDA_TRY(cudaStreamSynchronize(s));
     return DCB_OK;
 }
 
-int dcb_run_resident(dcb_ctx* c) {
-    if (!c || !c->have_batch) { dcb_set_error("dcb_run_resident: no batch uploaded"); return DCB_EINVAL; }
-    CUDA_TRY(cudaSetDevice(c->device));
-    cudaStream_t s = c->stream;
-    const BatchDev& b = c->batch;
-    CUDA_TRY(cudaMemsetAsync(c->d_queue_count, 0, 16, s));
-    CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * DCB_NCOUNTERS, s));
-    if (b.n_reads == 0) { c->ran = true; return DCB_OK; }
+// lens (unless every read has the same length), flag bits and the sparse exception list: everything but the words
+static int copy_side_arrays(dcb_ctx* c, const dcb_packed* P, cudaStream_t s) {
+    const size_t n = P->n_reads;
+    if (n && !P->uniform_len) CUDA_TRY(cudaMemcpyAsync(c->lens.p, P->lens, n * 2, cudaMemcpyHostToDevice, s));
+    if (n && P->n_exc) CUDA_TRY(cudaMemcpyAsync(c->flags.p, P->flags, ((n + 31) / 32) * 4, cudaMemcpyHostToDevice, s));
+    if (P->n_exc) {
+        CUDA_TRY(cudaMemcpyAsync(c->exc_read.p, P->exc_read, (size_t)P->n_exc * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c->exc_pos.p, P->exc_pos, (size_t)P->n_exc * 2, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c->exc_kind.p, P->exc_kind, (size_t)P->n_exc, cudaMemcpyHostToDevice, s));
+    }
+    return DCB_OK;
+}
+
+// Both kernels over reads [first, first + count) of the resident batch, on stream s.  slot: which queue counter.
+static int launch_range(dcb_ctx* c, cudaStream_t s, uint32_t first, uint32_t count, int slot, bool timed) {
+    if (count == 0) return DCB_OK;
+    BatchDev b = c->batch;
+    b.first = first; b.n_reads = count;
+    uint32_t* qcount = c->d_queue_count + slot;
+    uint32_t* queue = (uint32_t*)c->queue.p + first;
     DcrParams prm;
     prm.allow_ns = c->params.allow_ns; prm.lenthreshold = c->params.lenthreshold;
+    const uint32_t tiles_e = (count + c->exact_threads - 1) / c->exact_threads;
+    const uint32_t tiles_g = (count + c->general_threads - 1) / c->general_threads;
+    const int grid_e = (int)std::max<uint32_t>(1, std::min<uint32_t>(tiles_e, (uint32_t)c->exact_grid));
+    const int grid_g = (int)std::max<uint32_t>(1, std::min<uint32_t>(tiles_g, (uint32_t)c->general_grid));
     int rc;
     if (!c->params.force_general) {
-        if ((rc = timing_begin(c, 0))) return rc;
+        if (timed && (rc = timing_begin(c, 0))) return rc;
         Tables4 te;
         te.g[0] = c->d_vcore; te.words[0] = c->vcore_words;
         te.g[1] = c->d_jcore; te.words[1] = c->jcore_words;
@@ -740,26 +755,55 @@ int dcb_run_resident(dcb_ctx* c) {
             SpecBlooms sb;
             if (c->spec_union) { te.words[2] = c->uhead; sb.v = c->d_uidx + c->ubloom; sb.j = nullptr; }
             else { te.words[2] = c->vhead; te.words[3] = c->jhead; sb.v = c->d_vidx + c->vbloom; sb.j = c->d_jidx + c->jbloom; }
-            ((exact_spec_fn)c->spec_fn)<<<c->exact_grid, c->exact_threads, c->exact_smem, s>>>(
-                b, te, sb, prm, c->params.both_frames, (dcb_result*)c->results.p, c->d_counters, (uint32_t*)c->queue.p,
-                c->d_queue_count);
+            ((exact_spec_fn)c->spec_fn)<<<grid_e, c->exact_threads, c->exact_smem, s>>>(
+                b, te, sb, prm, c->params.both_frames, (dcb_result*)c->results.p, c->d_counters, queue, qcount);
         } else {
-            dcb_exact_kernel<<<c->exact_grid, c->exact_threads, c->exact_smem, s>>>(
-                b, te, prm, c->params.both_frames, (dcb_result*)c->results.p, c->d_counters, (uint32_t*)c->queue.p,
-                c->d_queue_count);
+            dcb_exact_kernel<<<grid_e, c->exact_threads, c->exact_smem, s>>>(
+                b, te, prm, c->params.both_frames, (dcb_result*)c->results.p, c->d_counters, queue, qcount);
         }
         CUDA_TRY(cudaGetLastError());
-        if ((rc = timing_end(c))) return rc;
+        if (timed && (rc = timing_end(c))) return rc;
     }
-    if ((rc = timing_begin(c, 1))) return rc;
+    if (timed && (rc = timing_begin(c, 1))) return rc;
     Tables4 tg;
     tg.g[0] = c->d_vgen; tg.words[0] = c->vgen_words; tg.g[1] = c->d_jgen; tg.words[1] = c->jgen_words;
     tg.g[2] = tg.g[3] = nullptr; tg.words[2] = tg.words[3] = 0;
-    dcb_general_kernel<<<c->general_grid, c->general_threads, c->general_smem, s>>>(
-        b, tg, prm, c->params.both_frames, (dcb_result*)c->results.p,
-        c->d_counters, c->params.force_general ? nullptr : (const uint32_t*)c->queue.p, c->d_queue_count);
+    dcb_general_kernel<<<grid_g, c->general_threads, c->general_smem, s>>>(
+        b, tg, prm, c->params.both_frames, (dcb_result*)c->results.p, c->d_counters,
+        c->params.force_general ? nullptr : (const uint32_t*)queue, qcount);
     CUDA_TRY(cudaGetLastError());
-    if ((rc = timing_end(c))) return rc;
+    if (timed && (rc = timing_end(c))) return rc;
+    return DCB_OK;
+}
+
+static int read_counters(dcb_ctx* c, cudaStream_t s, uint64_t* counters) {
+    unsigned long long h[DCB_NCOUNTERS];
+    CUDA_TRY(cudaMemcpyAsync(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (counters) for (int i = 0; i < DCB_NCOUNTERS; i++) counters[i] += h[i];
+    return DCB_OK;
+}
+
+int dcb_upload(dcb_ctx* c, const dcb_packed* P) {
+    if (!c || !P) { dcb_set_error("dcb_upload: null argument"); return DCB_EINVAL; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = prepare_batch(c, P))) return rc;
+    cudaStream_t s = c->stream;
+    if (P->n_reads) CUDA_TRY(cudaMemcpyAsync(c->words.p, P->words, (size_t)P->n_reads * P->slot_words * 4, cudaMemcpyHostToDevice, s));
+    if ((rc = copy_side_arrays(c, P, s))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return DCB_OK;
+}
+
+int dcb_run_resident(dcb_ctx* c) {
+    if (!c || !c->have_batch) { dcb_set_error("dcb_run_resident: no batch uploaded"); return DCB_EINVAL; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    CUDA_TRY(cudaMemsetAsync(c->d_queue_count, 0, sizeof(uint32_t) * kMaxChunks, s));
+    CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * DCB_NCOUNTERS, s));
+    int rc;
+    if ((rc = launch_range(c, s, 0, c->batch.n_reads, 0, true))) return rc;
     c->ran = true;
     return DCB_OK;
 }
@@ -770,19 +814,53 @@ int dcb_download(dcb_ctx* c, dcb_result* out, uint64_t* counters) {
     cudaStream_t s = c->stream;
     if (out && c->batch.n_reads)
         CUDA_TRY(cudaMemcpyAsync(out, c->results.p, (size_t)c->batch.n_reads * sizeof(dcb_result), cudaMemcpyDeviceToHost, s));
-    unsigned long long h[DCB_NCOUNTERS];
-    CUDA_TRY(cudaMemcpyAsync(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    if (counters) for (int i = 0; i < DCB_NCOUNTERS; i++) counters[i] += h[i];
-    return DCB_OK;
+    return read_counters(c, s, counters);
 }
 
-int dcb_decombine_batch(dcb_ctx* c, const dcb_packed* reads, dcb_result* out, uint64_t* counters) {
+// Host buffers in, host buffers out.  The batch is cut into chunks that alternate between two streams, so the upload of
+// one chunk, the kernels of another and the download of a third overlap (the copy engines and the SMs run side by
+// side); with page-locked buffers (dcb_pack_reads / dcb_pinned_alloc) the step is bound by the host->device copy.
+int dcb_decombine_batch(dcb_ctx* c, const dcb_packed* P, dcb_result* out, uint64_t* counters) {
+    if (!c || !P) { dcb_set_error("dcb_decombine_batch: null argument"); return DCB_EINVAL; }
+    CUDA_TRY(cudaSetDevice(c->device));
     int rc;
-    if ((rc = dcb_upload(c, reads))) return rc;
-    if ((rc = dcb_run_resident(c))) return rc;
-    return dcb_download(c, out, counters);
+    if ((rc = prepare_batch(c, P))) return rc;
+    const uint32_t n = (uint32_t)P->n_reads;
+    const size_t sw = P->slot_words;
+    cudaStream_t st[2] = {c->stream, c->stream2};
+    CUDA_TRY(cudaMemsetAsync(c->d_queue_count, 0, sizeof(uint32_t) * kMaxChunks, st[0]));
+    CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * DCB_NCOUNTERS, st[0]));
+    if ((rc = copy_side_arrays(c, P, st[0]))) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev_ready, st[0]));
+    CUDA_TRY(cudaStreamWaitEvent(st[1], c->ev_ready, 0));
+    uint32_t chunk = std::max<uint32_t>(kChunkReads, (n + kMaxChunks - 1) / kMaxChunks);
+    chunk = (chunk + 1023u) & ~1023u;
+    int k = 0;
+    for (uint32_t first = 0; first < n; first += chunk, k++) {
+        const uint32_t count = std::min<uint32_t>(chunk, n - first);
+        cudaStream_t s = st[k & 1];
+        CUDA_TRY(cudaMemcpyAsync((uint32_t*)c->words.p + (size_t)first * sw, P->words + (size_t)first * sw, (size_t)count * sw * 4,
+                                 cudaMemcpyHostToDevice, s));
+        if ((rc = launch_range(c, s, first, count, k, false))) return rc;
+        if (out)
+            CUDA_TRY(cudaMemcpyAsync(out + first, (dcb_result*)c->results.p + first, (size_t)count * sizeof(dcb_result),
+                                     cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(cudaEventRecord(c->ev_done, st[1]));
+    CUDA_TRY(cudaStreamWaitEvent(st[0], c->ev_done, 0));
+    c->ran = true;
+    return read_counters(c, st[0], counters);
 }
+
+void* dcb_pinned_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) {
+        dcb_set_error("dcb_pinned_alloc(%zu): %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+void dcb_pinned_free(void* p) { if (p) cudaFreeHost(p); }
 
 int dcb_timing_enable(dcb_ctx* c, int on) { if (!c) return DCB_EINVAL; c->timing = on != 0; return DCB_OK; }
 int dcb_timing_reset(dcb_ctx* c) {
@@ -799,10 +877,12 @@ int dcb_timing_get(dcb_ctx* c, double ms[DCB_NTIMERS], uint64_t launches[DCB_NTI
 }
 int dcb_last_deferred(dcb_ctx* c, uint64_t* n) {
     if (!c || !n || !c->ran) return DCB_EINVAL;
-    uint32_t q = 0;
+    uint32_t q[kMaxChunks];
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    CUDA_TRY(cudaMemcpy(&q, c->d_queue_count, 4, cudaMemcpyDeviceToHost));
-    *n = c->params.force_general ? c->batch.n_reads : q;
+    CUDA_TRY(cudaMemcpy(q, c->d_queue_count, sizeof(q), cudaMemcpyDeviceToHost));
+    uint64_t total = 0;
+    for (int i = 0; i < kMaxChunks; i++) total += q[i];
+    *n = c->params.force_general ? c->batch.n_reads : total;
     return DCB_OK;
 }
 

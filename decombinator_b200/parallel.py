@@ -99,23 +99,43 @@ def _sum_counters(local):
     return total
 
 
-def decombinator_sharded(inputargs):
-    """``decombinator(inputargs)`` over all ranks: rank 0 returns every row in input order (and owns ``counts`` with the
-    whole-job totals), the other ranks return [].  Each rank packs and analyses only its own shard of the reads."""
+def decombinator_shard(inputargs):
+    """This rank's part of ``decombinator(inputargs)``: -> (rows of its shard, global row index of the first one).
+    ``decombine.counts`` ends up holding the whole-job totals on every rank."""
     rank, world = _rank_world()
-    if world == 1:
-        return D.decombinator(inputargs)
     args = dict(inputargs)
-    args["shard"] = (rank, world)
-    args["suppresssummary"] = True if rank else inputargs["suppresssummary"]
+    if world > 1:
+        args["shard"] = (rank, world)
+        if rank:   # rank 0 checks the FASTQ and writes the summary
+            args["suppresssummary"] = True
+            args["dontcheck"] = True
     rows = D.decombinator(args)
-    parts = [None] * world if rank == 0 else None
-    dist.gather_object(rows, parts, dst=0)
+    if world == 1:
+        return rows, 0
+    sizes = [None] * world
+    dist.all_gather_object(sizes, len(rows))
     skip = ("start_time", "end_time", "pc_decombined", "chain_detected")
     total = _sum_counters({k: v for k, v in D.counts.items() if k not in skip})
     for k, v in total.items():
         D.counts[k] = v
+    return rows, sum(sizes[:rank])
+
+
+def gather_rows(rows):
+    """Rank 0 gets the rows of all ranks concatenated in rank order (= input order); the others get []."""
+    rank, world = _rank_world()
+    if world == 1:
+        return rows
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(rows, parts, dst=0)
     return [r for p in parts for r in p] if rank == 0 else []
+
+
+def decombinator_sharded(inputargs):
+    """``decombinator(inputargs)`` over all ranks: rank 0 returns every row in input order (and ``counts`` holds the
+    whole-job totals), the other ranks return [].  Each rank packs and analyses only its own shard of the reads."""
+    rows, _ = decombinator_shard(inputargs)
+    return gather_rows(rows)
 
 
 def collapsinator_sharded(inputargs, data=None, first_index=0, n_total=None):

@@ -158,10 +158,16 @@ void dcb_ctx_destroy(dcb_ctx*);
 int dcb_ctx_set_stream(dcb_ctx*, void* cuda_stream);
 
 /* The batched dcr(): replaces the body of the hot loop `for records in zipfqs: ... dcr(...)`
- * (decombine.py:963-1010) for n reads.  HOST buffers in, HOST buffers out: copies the packed
- * batch to HBM, runs the matching kernels, copies the n result records back and ADDS this
- * batch's counter deltas to counters[DCB_NCOUNTERS].  Synchronous. */
+ * (decombine.py:963-1010) for n reads.  HOST buffers in, HOST buffers out: streams the packed
+ * batch to HBM in chunks on two streams (upload, kernels and download of different chunks
+ * overlap), copies the n result records back and ADDS this batch's counter deltas to
+ * counters[DCB_NCOUNTERS].  Synchronous on return. */
 int dcb_decombine_batch(dcb_ctx*, const dcb_packed* reads, dcb_result* out, uint64_t* counters);
+
+/* Page-locked host memory for result records (so that the device->host copies of dcb_decombine_batch run
+ * asynchronously, overlapped with the uploads); NULL when no GPU is usable. */
+void* dcb_pinned_alloc(size_t bytes);
+void dcb_pinned_free(void*);
 
 /* Same work with the batch resident in HBM (bench `value`, multi-step pipelines):
  *   dcb_upload          : host packed batch -> ctx-owned device buffers (synchronous)

@@ -100,15 +100,10 @@ def _sharded_worker(rank, world, port, tmp, out_path):
     import torch.distributed as dist
     from decombinator_b200 import collapse as C, decombine as D, parallel
     parallel.init_from_env("gloo")
-    args = _args(os.path.join(tmp, "TINY_1.fq"), "b", tmp, suppresssummary=True, oligo="M13", command="pipeline")
-    rows = parallel.decombinator_sharded(args)
-    # every rank keeps its own shard for the collapse all-to-all
-    lo, hi = parallel.shard_bounds(106, rank, world)
-    args2 = dict(args, shard=(rank, world))
-    mine = D.decombinator(args2)
-    n_before = [None] * world
-    dist.all_gather_object(n_before, len(mine))
-    freq = parallel.collapsinator_sharded(args, data=mine, first_index=sum(n_before[:rank]))
+    args = _args(os.path.join(tmp, "TINY_1.fq"), "b", tmp, suppresssummary=True, dontcheck=True, oligo="M13", command="pipeline")
+    mine, first = parallel.decombinator_shard(args)     # every rank keeps its own shard for the collapse all-to-all
+    rows = parallel.gather_rows(mine)
+    freq = parallel.collapsinator_sharded(args, data=mine, first_index=first)
     if rank == 0:
         json.dump({"rows": rows, "vj": int(D.counts["vj_count"]), "freq": freq}, open(out_path, "w"))
     dist.barrier()
