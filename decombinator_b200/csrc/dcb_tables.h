@@ -93,10 +93,12 @@ struct DcbSeedIndex {
     uint32_t bmul;               // word = (window * bmul) >> (32 - wbits); bmul = odd << (32 - 2q), so only the q-mer's
                                  // own 2q bits reach the product;  bit = 31 - (q-mer & 31)  (MSB-first)
     int32_t k, span;             // class key length (<= 15 bases) and offsets per class
-    int32_t ck_off;              // 2^cbits slots: fingerprint << 12 | offset set.  For key x = class << 30 | k-mer:
-    uint32_t c1, c2;             // slots (x * c1) >> cshift and (x * c2) >> cshift, fingerprint DCB_CK_FP(x * c1);
-    int32_t cshift;              // a free slot is 0 (empty offset set); a lookup ORs the sets of BOTH slots whose
-                                 // fingerprint matches, so a chance fingerprint match only adds offsets to try
+    int32_t ck_off;              // 2^cbits slots: fingerprint << 12 | offset set.  For key x = class << 30 | k-mer the
+    uint32_t c1, c2;             // two candidate slots are (x * c1) >> cshift and (x * c2) >> cshift; an entry sitting in
+    int32_t cshift;              // its c1-slot carries the top 20 bits of x * c2 as fingerprint and vice versa (the slot
+                                 // index already pins the top bits of its own product).  A free slot is 0 (empty offset
+                                 // set); a lookup ORs the sets of BOTH slots whose fingerprint matches, so a chance
+                                 // fingerprint match only adds offsets to try
     int32_t tk_off;              // 2^tbits 16-bit slots of a PERFECT hash over the lmin-prefixes: the first ctag with that
                                  // prefix, 0x1FF = free;  slot = (dcb_fold64(prefix) * t1) >> tshift.  No fingerprint: the
     uint32_t t1;                 // tag found is compared with the read as a whole anyway.
@@ -109,7 +111,7 @@ struct DcbSeedIndex {
     int32_t n_words;
 };
 
-#define DCB_CK_FP(prod) (((prod) >> 8) & 0xFFFFFu)               // fingerprint bits of the first-choice product
+#define DCB_CK_FPMASK 0xFFFFF000u                               // fingerprint bits of a slot / of a product
 #define DCB_CK_OFFMASK(e) ((e) & 0xFFFu)
 
 // Compact tag record of the fast path (16 bytes, one 128-bit load).

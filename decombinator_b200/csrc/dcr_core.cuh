@@ -448,9 +448,9 @@ DCB_HD uint32_t fast_class_lookup(const SeedIdxView& ix, uint32_t wlo, uint32_t 
     for (int c = 0; c < 2; c++) {
         const int sh = 2 * (ix.wlead - c * ix.span);   // < 32: wlead <= 12
         const uint32_t x = ((uint32_t)c << 30) | (DCB_FUNNEL_R(wlo, whi, sh) & kmask);
-        const uint32_t prod = x * ix.c1, fp = DCB_CK_FP(prod);
-        const uint32_t e1 = ix.ck[prod >> ix.cshift], e2 = ix.ck[(x * ix.c2) >> ix.cshift];
-        offs |= ((e1 >> 12) == fp ? e1 : 0u) | ((e2 >> 12) == fp ? e2 : 0u);
+        const uint32_t p1 = x * ix.c1, p2 = x * ix.c2;
+        const uint32_t e1 = ix.ck[p1 >> ix.cshift], e2 = ix.ck[p2 >> ix.cshift];
+        offs |= (((e1 ^ p2) & DCB_CK_FPMASK) == 0 ? e1 : 0u) | (((e2 ^ p1) & DCB_CK_FPMASK) == 0 ? e2 : 0u);
     }
     return DCB_CK_OFFMASK(offs);
 }

@@ -224,8 +224,12 @@ bool dcb_build_seed_index(const std::vector<std::string>* gene_v, const std::vec
         idx.c1 = ck.c1; idx.c2 = ck.c2; idx.cshift = 32 - ck.bits;
         const size_t slots = (size_t)1 << ck.bits;
         idx.ck_off = b.reserve(slots);
-        for (size_t i = 0; i < slots; i++)
-            b.w[idx.ck_off + i] = ck.used[i] ? ((DCB_CK_FP(ck.key[i] * ck.c1) << 12) | ck.val[i]) : 0u;
+        for (size_t i = 0; i < slots; i++) {
+            if (!ck.used[i]) { b.w[idx.ck_off + i] = 0u; continue; }
+            // the fingerprint comes from the product that did NOT choose this slot
+            const uint32_t other = ck.h(ck.key[i], 0) == i ? ck.key[i] * ck.c2 : ck.key[i] * ck.c1;
+            b.w[idx.ck_off + i] = (other & DCB_CK_FPMASK) | ck.val[i];
+        }
     }
     {   // lmin-prefixes: search a multiplier that spreads them over the slots without a collision
         std::vector<std::pair<uint32_t, int>> items;
