@@ -121,10 +121,14 @@ struct alignas(16) DcbUTag {
     uint32_t mask_hi_len;        // high word of the mask (24 bits: len <= 28) | len << 24
 };
 #define DCB_FAST_MAX_TAG_LEN 28
-// filter sizes the library builds: 2^10 words when one index serves both genes, 2^9 words per gene otherwise
-// (32 private copies of all filters of a chain must fit in shared memory: 128 KB either way)
-#define DCB_WBITS_UNION 10
-#define DCB_WBITS_SINGLE 9
+// filter sizes the library builds: 2^12 words when one index serves both genes, 2^11 words per gene otherwise
+// (DCB_BLOOM_COPIES private copies of all filters of a chain must fit in shared memory: 128 KB either way)
+#define DCB_WBITS_UNION 12
+#define DCB_WBITS_SINGLE 11
+// private copies of a filter in shared memory: lane l probes copy l % DCB_BLOOM_COPIES; word i of copy c sits at word
+// i * DCB_BLOOM_COPIES + c, i.e. in bank 8 * (i % 4) + c, so lanes of different copies never conflict and the four
+// lanes that share a copy conflict only when their words fall in the same quarter (measured in profiles/)
+#define DCB_BLOOM_COPIES 8
 
 // Geometry of a seed index as a function of (lmin, q): shared by the host builder and the kernels, whose
 // specialisations evaluate these at compile time.

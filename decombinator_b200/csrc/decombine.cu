@@ -89,10 +89,11 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     return v;
 }
 
-// i * 128 + base as ONE multiply-add (the compiler otherwise rewrites the shift pair into shift + mask + add)
-__device__ __forceinline__ uint32_t mad128(uint32_t i, uint32_t base) {
+// i * (4 * DCB_BLOOM_COPIES) + base as ONE multiply-add (the compiler otherwise rewrites the shift pair into
+// shift + mask + add): the byte address of word i of this lane's filter copy
+__device__ __forceinline__ uint32_t mad_copy(uint32_t i, uint32_t base) {
     uint32_t v;
-    asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(v) : "r"(i), "r"(base));
+    asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(v) : "r"(i), "r"(base), "n"(4 * DCB_BLOOM_COPIES));
     return v;
 }
 
@@ -218,9 +219,10 @@ dcb_exact_kernel(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_res
 
 // ------------------------------------------------------------------------------------------------
 // exact-tag kernel, specialised: the read slot (NW words) sits in registers, every sampled seed position is a
-// compile-time constant (static funnel shifts, no index arithmetic), and each lane probes its OWN copy of the
-// seed filter -- the filter is replicated 32x in shared memory, copy l interleaved into bank l -- so a probe
-// is one conflict-free shared-memory wavefront whatever the 32 q-mers are.
+// compile-time constant (static funnel shifts, no index arithmetic), and the lanes probe DCB_BLOOM_COPIES private
+// copies of the seed filter, interleaved word by word in shared memory (copy c only ever touches banks c, c + 8,
+// c + 16, c + 24), so a probe costs one or two shared-memory wavefronts whatever the 32 q-mers are.  (32 copies of a
+// 4x smaller filter were conflict-free but let 0.5 false hits per read through to the verification loop.)
 //   NW            words per read slot (16 => reads up to 256 nt)
 //   QV, SV, WBV   V seed length / stride / log2(filter words);  QJ, SJ, WBJ the same for J
 //   UNION         V and J share the seed geometry and are found together through ONE index (table 2)
@@ -236,7 +238,7 @@ struct SeedScan {
     static_assert(NPOS <= 64, "at most 64 sampled positions");
     // Probe the filter at every sampled position.  Probe i of a group of G lands in bit G-1-i of its hit word
     // (each probe shifts the word left by one), so the EARLIEST position is the HIGHEST set bit.
-    // bl = shared-space byte address of this lane's copy of the filter: word w at bl + 128 w.
+    // bl = shared-space byte address of this lane's copy of the filter: word w at bl + 4 * DCB_BLOOM_COPIES * w.
     static __device__ __forceinline__ void run(const uint32_t (&w)[NW], uint32_t bl, uint32_t& h0, uint32_t& h1) {
         h0 = 0; h1 = 0;
         constexpr uint32_t BMUL = DCB_BLOOM_MUL(Q);
@@ -247,7 +249,7 @@ struct SeedScan {
             if (sh == 0) win = w[a];
             else if (sh + 2 * Q <= 32 || a + 1 >= NW) win = w[a] >> sh;
             else win = __funnelshift_r(w[a], w[a + 1], sh);
-            const uint32_t word = lds_u32(mad128((win * BMUL) >> (32 - WB), bl));
+            const uint32_t word = lds_u32(mad_copy((win * BMUL) >> (32 - WB), bl));
             const uint32_t top = __funnelshift_l(0u, word, win);          // word << (key & 31): the key's bit -> bit 31
             if (i < 32) h0 = __funnelshift_l(top, h0, 1); else h1 = __funnelshift_l(top, h1, 1);
         }
@@ -320,13 +322,13 @@ dcb_exact_kernel_spec(BatchDev b, Tables4 tb, SpecBlooms bl, DcrParams prm, int 
     extern __shared__ __align__(16) uint32_t smem[];
     const int T = blockDim.x;
     const int tid = threadIdx.x;
-    constexpr int BV = 32 << WBV, BJ = UNION ? 0 : (32 << WBJ);
+    constexpr int BV = DCB_BLOOM_COPIES << WBV, BJ = UNION ? 0 : (DCB_BLOOM_COPIES << WBJ);
     SmemLayout L = carve(smem, tb, (size_t)BV + BJ + (size_t)ROWS * T);
     uint32_t* s_bv = L.cols;
     uint32_t* s_bj = s_bv + BV;
     uint32_t* s_rd = s_bj + BJ;
-    for (int i = tid; i < BV; i += T) s_bv[i] = __ldg(bl.v + (i >> 5));
-    for (int i = tid; i < BJ; i += T) s_bj[i] = __ldg(bl.j + (i >> 5));
+    for (int i = tid; i < BV; i += T) s_bv[i] = __ldg(bl.v + i / DCB_BLOOM_COPIES);
+    for (int i = tid; i < BJ; i += T) s_bj[i] = __ldg(bl.j + i / DCB_BLOOM_COPIES);
     s_rd[tid] = 0u;
     for (int k = 0; k < TRAIL; k++) s_rd[(1 + NW + k) * T + tid] = 0u;
     stage_tables(L, tb);
@@ -341,8 +343,8 @@ dcb_exact_kernel_spec(BatchDev b, Tables4 tb, SpecBlooms bl, DcrParams prm, int 
     jix.q = QJ; jix.stride = SJ; jix.wlead = ScanJ::WLEAD; jix.lmin = SJ + QJ - 1;
     jix.span = DCB_IDX_SPAN(SJ + QJ - 1, QJ); jix.k = DCB_IDX_K(SJ + QJ - 1, QJ);
     const uint32_t* col = s_rd + T + tid;                 // word k of this thread's read at col[k * T]
-    const uint32_t my_bv = smem_u32(s_bv + (tid & 31));
-    const uint32_t my_bj = smem_u32(s_bj + (tid & 31));
+    const uint32_t my_bv = smem_u32(s_bv + (tid % DCB_BLOOM_COPIES));
+    const uint32_t my_bj = smem_u32(s_bj + (tid % DCB_BLOOM_COPIES));
     const uint32_t n_tiles = (b.n_reads + T - 1) / T;
 
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -672,9 +674,9 @@ static int prepare_batch(dcb_ctx* c, const dcb_packed* P) {
     c->spec_fn = (void*)spec; c->spec_union = have_union;
     int occ_e = 0, occ_g = 0;
     if (spec) {
-        // tables (index heads only) + 32 private copies of the filter(s) + the read columns of as wide a block as fits
+        // tables (index heads only) + the private copies of the filter(s) + the read columns of as wide a block as fits
         const size_t tbl_s = (size_t)c->vcore_words + c->jcore_words + (have_union ? (size_t)c->uhead : (size_t)c->vhead + c->jhead);
-        const size_t blooms = have_union ? ((size_t)32 << DCB_WBITS_UNION) : 2 * ((size_t)32 << DCB_WBITS_SINGLE);
+        const size_t blooms = have_union ? ((size_t)DCB_BLOOM_COPIES << DCB_WBITS_UNION) : 2 * ((size_t)DCB_BLOOM_COPIES << DCB_WBITS_SINGLE);
         const size_t rows = (size_t)spec_rows((int)sw, have_union);
         int T = 1024;
         for (; T >= 256; T -= 128) {
