@@ -254,7 +254,7 @@ def main():
             "decombined_fraction": decombined / (world * n), "deferred_to_general_kernel": n_deferred / n,
             "kernels_ms": {"dcb_exact_kernel": exact_ms, "dcb_general_kernel": general_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "dcb_exact_kernel_spec", "bytes_per_read": bytes_per_read,
+                         "traffic": traffic, "kernel": ctx.exact_kernel_name(), "bytes_per_read": bytes_per_read,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(packed.h2d_bytes()),
                     "d2h_bytes_per_step": int(n * 16 + 8 * _lib.NCOUNTERS), "steps": e2e_steps},

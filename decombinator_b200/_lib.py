@@ -91,6 +91,8 @@ def lib():
     L.dcb_timing_enable.argtypes = [vp, i32]
     L.dcb_timing_get.argtypes = [vp, vp, vp]
     L.dcb_last_deferred.argtypes = [vp, ctypes.POINTER(u64)]
+    L.dcb_exact_kernel_name.argtypes = [vp]
+    L.dcb_exact_kernel_name.restype = ctypes.c_char_p
     L.dcb_dist_create.restype = vp
     L.dcb_dist_create.argtypes = [i32]
     L.dcb_dist_destroy.argtypes = [vp]
@@ -257,7 +259,7 @@ class Context:
     def __init__(self, vset: TagTables, jset: TagTables, device=0, both_frames=False, allow_ns=False,
                  lenthreshold=130, force_general=False):
         L = lib()
-        prm = CParams(int(bool(both_frames)), int(bool(allow_ns)), int(lenthreshold), int(bool(force_general)))
+        prm = CParams(int(bool(both_frames)), int(bool(allow_ns)), int(lenthreshold), int(force_general))
         self._keep = (vset, jset)
         self._h = L.dcb_ctx_create(int(device), vset.handle, jset.handle, ctypes.byref(prm))
         if not self._h:
@@ -317,6 +319,9 @@ class Context:
         n = ctypes.c_uint64()
         _check(lib().dcb_last_deferred(self._h, ctypes.byref(n)), "dcb_last_deferred")
         return n.value
+
+    def exact_kernel_name(self):
+        return lib().dcb_exact_kernel_name(self._h).decode()
 
     def close(self):
         if self._h:

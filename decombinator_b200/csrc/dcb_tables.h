@@ -107,9 +107,26 @@ struct DcbSeedIndex {
     int32_t n_v, n_tags;         // ctag >= n_v is J tag ctag - n_v
     int32_t chain_off;           // 0, or uint16[n_tags]: next tag sharing this tag's lmin-prefix (0x1FF = none)
     int32_t head_words;          // words before the filter (what the specialised kernels stage verbatim)
-    int32_t bloom_off;           // the filter comes last
+    int32_t bloom_off;           // the bit filter follows the head
     int32_t n_words;
+    // --- tables of the queue kernel (dcb_exact_kernel_q), stored behind the bit filter -------------------------------
+    //   * byte filter: ONE byte per slot (1 = an indexed q-mer hashes here), slot = (window * fmul) >> (32 - fbits).
+    //     A probe is IMAD, SHF, LDS.U8 and one IMAD that appends the byte to the hit mask: no bit extraction, and half
+    //     of the probe's instructions run on the FMA pipe instead of the (saturated) ALU pipe;
+    //   * q-mer -> offset set, hash-and-displace (CHD): bucket = (x * m1) >> (32 - b1), slot = (((x * m2) >> (32 - b2))
+    //     + disp[bucket]) & (2^b2 - 1); the 16-bit slot holds the set of tag offsets the q-mer occurs at (bit o).  No
+    //     fingerprint: every candidate is compared with the read as a whole, a filter false positive just finds nothing.
+    //     m1, m2 and fmul are odd << (32 - 2q), so only the q-mer's own bits of a wider window reach the products.
+    int32_t legacy_words;        // words up to the end of the bit filter (what the other exact kernels stage)
+    int32_t fbits;
+    uint32_t fmul;
+    uint32_t m1, m2;
+    int32_t b1, b2;
+    int32_t qtab_off;            // uint16 disp[2^b1] then uint16 offsets[2^b2]
+    int32_t qtab_words;
+    int32_t bfilter_off;         // 2^fbits bytes
 };
+#define DCB_FBITS 16             // byte filter of the queue kernel: 64 KB
 
 #define DCB_CK_FPMASK 0xFFFFF000u                               // fingerprint bits of a slot / of a product
 #define DCB_CK_OFFMASK(e) ((e) & 0xFFFu)

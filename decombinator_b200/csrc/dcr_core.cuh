@@ -588,6 +588,101 @@ DCB_HD void fast_find(const ReadView& r, const uint32_t* ib, FullHit& vh, FullHi
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Queue kernel (dcb_exact_kernel_q): byte filter + hash-and-displace offset table (DcbSeedIndex, second half).
+// A full-tag occurrence is kept as ONE word per gene: 0 = none, DCB_HIT_MULTI = two or more distinct occurrences,
+// else DCB_HIT_ONE | tag << 16 | position.
+// ------------------------------------------------------------------------------------------------
+#define DCB_HIT_ONE 0x80000000u
+#define DCB_HIT_MULTI 0xFFFFFFFFu
+// add an occurrence (or merge the state another lane collected) into a hit word
+DCB_HD uint32_t hit_merge(uint32_t cur, uint32_t c) {
+    return cur == 0u ? c : ((c == 0u || c == cur) ? cur : DCB_HIT_MULTI);
+}
+DCB_HD FullHit hit_decode(uint32_t h) {
+    FullHit fh;
+    fh.count = h == 0u ? 0 : (h == DCB_HIT_MULTI ? 2 : 1);
+    fh.code = h & 0x7FFFFFFFu;
+    return fh;
+}
+
+struct QIdxView {
+    const uint16_t* disp;      // 2^b1 displacements
+    const uint16_t* offs;      // 2^b2 offset sets
+    const uint16_t* tk;        // tag-prefix perfect-hash slots
+    const DcbUTag* utag;
+    const uint16_t* chain;
+    uint32_t m1, m2, t1, mask2;
+    int s1, s2, tshift;
+    int q, stride, lmin, wlead, n_v;
+};
+// ib: the index blob; qtab: where its qtab_words were staged (ib + qtab_off when the blob is used in place)
+DCB_HD QIdxView q_idx_view(const uint32_t* ib, const uint32_t* qtab) {
+    const DcbSeedIndex& ix = *reinterpret_cast<const DcbSeedIndex*>(ib);
+    QIdxView v;
+    v.disp = reinterpret_cast<const uint16_t*>(qtab);
+    v.offs = v.disp + ((size_t)1 << ix.b1);
+    v.tk = reinterpret_cast<const uint16_t*>(ib + ix.tk_off);
+    v.utag = reinterpret_cast<const DcbUTag*>(ib + ix.utag_off);
+    v.chain = ix.chain_off ? reinterpret_cast<const uint16_t*>(ib + ix.chain_off) : nullptr;
+    v.m1 = ix.m1; v.m2 = ix.m2; v.t1 = ix.t1; v.mask2 = (1u << ix.b2) - 1u;
+    v.s1 = 32 - ix.b1; v.s2 = 32 - ix.b2; v.tshift = ix.tshift;
+    v.q = ix.q; v.stride = ix.stride; v.lmin = ix.lmin; v.wlead = ix.wlead; v.n_v = ix.n_v;
+    return v;
+}
+// Offsets the q-mer in the low 2q bits of x occurs at in some tag (bit o); anything for a q-mer that is not indexed.
+DCB_HD uint32_t q_offsets(const QIdxView& ix, uint32_t x) {
+    const uint32_t d = ix.disp[(x * ix.m1) >> ix.s1];
+    return ix.offs[(((x * ix.m2) >> ix.s2) + d) & ix.mask2];
+}
+// One candidate: a tag starting at P = p - o, where (wlo, whi) are the 32 bases from p - wlead.  Calls
+// sink(ctag, P) for every tag found there (one, unless tags share their lmin-prefix).
+template <bool PADDED, class Sink>
+DCB_HD void q_check_offset(const ReadView& r, const QIdxView& ix, int p, int o, uint32_t wlo, uint32_t whi, Sink& sink) {
+    const int P = p - o;
+    const int sh = 2 * (ix.wlead - o);                 // 2 <= sh <= 2 * wlead <= 24
+    const uint32_t lo = DCB_FUNNEL_R(wlo, whi, sh), hi = whi >> sh;   // the 32 - (wlead - o) >= lmin bases from P on
+    const uint32_t f = dcb_fold64(lo & mask2(ix.lmin), ix.lmin > 16 ? (hi & mask2(ix.lmin - 16)) : 0u);
+    uint32_t ctag = ix.tk[(f * ix.t1) >> ix.tshift];
+    if (P < 0) return;
+    while (ctag != 0x1FFu) {
+        const DcbUTag u = ix.utag[ctag];
+        const int L = (int)(u.mask_hi_len >> 24);
+        if (P + L <= r.n) {
+            uint32_t tlo = lo, thi = hi;
+            if (ix.wlead - o + L > 32) rd_win32x<PADDED>(r, P, tlo, thi);   // long tag: past the window in registers
+            if (!(((tlo ^ u.bits_lo) & u.mask_lo) | ((thi ^ u.bits_hi) & (u.mask_hi_len & 0x00FFFFFFu)))) sink(ctag, P);
+        }
+        ctag = ix.chain ? ix.chain[ctag] : 0x1FFu;
+    }
+}
+// Collects occurrences into two hit words (V, J).
+struct HitWords {
+    uint32_t v, j;
+    int n_v;
+    DCB_HD void operator()(uint32_t ctag, int P) {
+        if ((int)ctag >= n_v) j = hit_merge(j, DCB_HIT_ONE | ((ctag - (uint32_t)n_v) << 16) | (uint32_t)P);
+        else v = hit_merge(v, DCB_HIT_ONE | (ctag << 16) | (uint32_t)P);
+    }
+};
+// The whole search for one read, serially (tests/sim and nothing else: the kernel spreads this work over a warp).
+DCB_HD void q_find(const ReadView& r, const uint32_t* ib, FullHit& vh, FullHit& jh) {
+    const DcbSeedIndex& hd = *reinterpret_cast<const DcbSeedIndex*>(ib);
+    const QIdxView ix = q_idx_view(ib, ib + hd.qtab_off);
+    const uint8_t* filt = reinterpret_cast<const uint8_t*>(ib + hd.bfilter_off);
+    HitWords hw;
+    hw.v = 0; hw.j = 0; hw.n_v = ix.n_v;
+    for (int p = 0; p + ix.q <= r.n; p += ix.stride) {
+        const uint32_t win = rd_win16(r, p);
+        if (!filt[(win * hd.fmul) >> (32 - hd.fbits)]) continue;
+        uint32_t wlo, whi;
+        rd_win32(r, p - ix.wlead, wlo, whi);
+        for (uint32_t offs = q_offsets(ix, DCB_FUNNEL_R(wlo, whi, 2 * ix.wlead)); offs; offs &= offs - 1)
+            q_check_offset<false>(r, ix, p, DCB_FFS(offs) - 1, wlo, whi, hw);
+    }
+    vh = hit_decode(hw.v); jh = hit_decode(hw.j);
+}
+
 // Outcome of the fast path for one read.
 enum { FAST_DONE = 0, FAST_DEFER = 1 };
 
@@ -652,12 +747,14 @@ DCB_HD uint32_t exc_lower_bound(const ExcList& ex, uint32_t key) {
 // union index of both genes when jidx is null.  Returns FAST_DONE / FAST_DEFER.
 DCB_HD int dcr_exact_read(const ReadView& r, bool flagged, const uint32_t* vcore, const uint32_t* jcore,
                           const uint32_t* vidx, const uint32_t* jidx, const DcrParams& prm, int both_frames,
-                          dcb_result& out, dcb_cnt_t* C) {
+                          dcb_result& out, dcb_cnt_t* C, bool use_q = false) {
     if (flagged) return FAST_DEFER;
     FullHit vh, jh;
     vh.count = 0; vh.code = 0;
     jh.count = 0; jh.code = 0;
-    if (!jidx) {
+    if (use_q) {          // the queue kernel's tables (union index only)
+        q_find(r, vidx, vh, jh);
+    } else if (!jidx) {
         fast_find(r, vidx, vh, jh, true);
     } else {
         fast_find(r, vidx, vh, jh, true);

@@ -396,6 +396,249 @@ dcb_exact_kernel_spec(BatchDev b, Tables4 tb, SpecBlooms bl, DcrParams prm, int 
 }
 
 // ------------------------------------------------------------------------------------------------
+// exact-tag kernel, queue form (chains whose V and J tags share one seed geometry: every `extended` set).
+// Same contract as dcb_exact_kernel_spec -- the read slot in registers, compile-time seed positions, the same finish --
+// with the search reorganised so that the lanes of a warp do equal amounts of work:
+//   1. probe: ONE byte filter (64 KB, one byte per slot).  A probe is SHF (window), IMAD (hash), SHF (slot), LDS.U8
+//      and an IMAD that appends the byte to the hit mask; no bit extraction, half the instructions on the FMA pipe.
+//   2. the first two hits of a read (a clean read has exactly two: its V and its J tag) are confirmed by the lane that
+//      owns the read: q-mer -> offset set (hash-and-displace, two 16-bit reads) -> perfect-hash prefix table -> whole-tag
+//      compare.  Its first offset is checked on the spot.
+//   3. everything beyond that -- third and later hits (filter noise, homologous q-mers), second and later offsets --
+//      goes to two small per-warp queues in shared memory and is confirmed by WHICHEVER lane is free, 32 items per
+//      trip; results travel back through one slot per read and gene (compare-and-swap keeps "none / one / several").
+//      A queue that overflows marks the owning read as deferred (the general kernel redoes it), so capacity is never
+//      a correctness matter.
+// No block-wide barrier inside the tile loop: a warp only ever reads the read columns of its own lanes.
+// ------------------------------------------------------------------------------------------------
+struct QTables {
+    const uint32_t* vcore; const uint32_t* jcore; const uint32_t* head; const uint32_t* qtab; const uint32_t* bfilter;
+    int vcore_words, jcore_words, head_words, qtab_words;
+};
+static constexpr int kQCapA = 64;     // queued hits per warp and tile
+static constexpr int kQCapB = 192;    // queued (hit, offset) candidates per warp and tile
+// per-warp scratch, in words: 64 result slots, queue A (u16), queue B (u16), counters (nA, nB, defer mask, pad)
+static constexpr int kQWarpWords = 64 + kQCapA / 2 + kQCapB / 2 + 4;
+
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t mad2(uint32_t h, uint32_t bit) {   // 2 * h + bit on the FMA pipe
+    uint32_t v;
+    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(v) : "r"(h), "r"(bit));
+    return v;
+}
+// results of queued candidates: one slot per (owner lane, gene)
+struct SlotSink {
+    uint32_t* slots;   // this warp's 64 slots
+    int owner, n_v;
+    __device__ __forceinline__ void operator()(uint32_t ctag, int P) {
+        const bool is_j = (int)ctag >= n_v;
+        const uint32_t c = DCB_HIT_ONE | ((is_j ? ctag - (uint32_t)n_v : ctag) << 16) | (uint32_t)P;
+        uint32_t* s = slots + 2 * owner + (is_j ? 1 : 0);
+        const uint32_t old = atomicCAS(s, 0u, c);
+        if (old != 0u && old != c) atomicExch(s, DCB_HIT_MULTI);
+    }
+};
+__device__ __forceinline__ void q_push(uint32_t* count, uint16_t* q, int cap, uint32_t item, uint32_t* defer_mask, int owner) {
+    const uint32_t pos = atomicAdd(count, 1u);
+    if (pos < (uint32_t)cap) q[pos] = (uint16_t)item;
+    else atomicOr(defer_mask, 1u << owner);
+}
+
+template <int NW, int Q, int S, int T>
+__global__ void __launch_bounds__(T, 1)
+dcb_exact_kernel_q(BatchDev b, QTables qt, DcrParams prm, int both_frames, dcb_result* __restrict__ results,
+                   unsigned long long* __restrict__ counters, uint32_t* __restrict__ queue,
+                   uint32_t* __restrict__ queue_count) {
+    constexpr int NPOS = (16 * NW - Q) / S + 1;
+    static_assert(NPOS <= 32, "one hit word");
+    constexpr int WLEAD = DCB_IDX_WLEAD(S + Q - 1, Q);
+    static_assert(WLEAD == S, "the verification window starts one stride before the seed");
+    constexpr int WMAX = ((NPOS - 1) * S - WLEAD) >> 4;
+    constexpr int TRAIL = WMAX + 3 - NW > 1 ? WMAX + 3 - NW : 1;    // zero rows behind the read columns
+    constexpr int ROWS = 1 + NW + TRAIL;
+    constexpr uint32_t FMUL = DCB_BLOOM_MUL(Q);
+    constexpr int FBYTES = 1 << DCB_FBITS;
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // layout: [byte filter][read columns][per-warp scratch][V tags][J tags][index head][offset table][counters][mbarrier]
+    uint32_t* s_rd = smem + FBYTES / 4;
+    uint32_t* s_ws = s_rd + ROWS * T;
+    uint32_t* s_vcore = s_ws + (T / 32) * kQWarpWords;
+    uint32_t* s_jcore = s_vcore + qt.vcore_words;
+    uint32_t* s_head = s_jcore + qt.jcore_words;
+    uint32_t* s_qtab = s_head + qt.head_words;
+    dcb_cnt_t* s_cnt = s_qtab + qt.qtab_words;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_cnt + ((DCB_NCOUNTERS + 3) & ~3));
+
+    s_rd[tid] = 0u;
+    for (int k = 0; k < TRAIL; k++) s_rd[(1 + NW + k) * T + tid] = 0u;
+    for (int i = tid; i < (T / 32) * kQWarpWords; i += T) s_ws[i] = 0u;
+    tma_stage_begin(bar, (uint32_t)(FBYTES + 4 * (qt.vcore_words + qt.jcore_words + qt.head_words + qt.qtab_words)));
+    tma_stage_copy(bar, smem, qt.bfilter, FBYTES);
+    tma_stage_copy(bar, s_vcore, qt.vcore, 4u * qt.vcore_words);
+    tma_stage_copy(bar, s_jcore, qt.jcore, 4u * qt.jcore_words);
+    tma_stage_copy(bar, s_head, qt.head, 4u * qt.head_words);
+    tma_stage_copy(bar, s_qtab, qt.qtab, 4u * qt.qtab_words);
+    if (tid < DCB_NCOUNTERS) s_cnt[tid] = 0;
+    tma_stage_wait(bar);
+    __syncthreads();
+
+    const DcbTag* vtags = gene_tags(s_vcore);
+    const DcbTag* jtags = gene_tags(s_jcore);
+    QIdxView ix = q_idx_view(s_head, s_qtab);
+    ix.q = Q; ix.stride = S; ix.wlead = WLEAD; ix.lmin = S + Q - 1;       // geometry pinned to the template constants
+    const uint32_t* col = s_rd + T + tid;                 // word k of this thread's read at col[k * T]
+    const uint32_t* wcol = s_rd + T + (tid - lane);       // ... of lane l of this warp at wcol[l + k * T]
+    uint32_t* slots = s_ws + warp * kQWarpWords;
+    uint16_t* qa = reinterpret_cast<uint16_t*>(slots + 64);
+    uint16_t* qb = qa + kQCapA;
+    uint32_t* qn = slots + 64 + kQCapA / 2 + kQCapB / 2;  // [0] queued hits, [1] queued candidates, [2] defer mask
+    const uint32_t filt = smem_u32(smem);
+    const uint32_t n_tiles = (b.n_reads + T - 1) / T;
+
+    // the 32 bases from (i - 1) * S of the read in column c (the seed of probe i sits WLEAD = S bases into the window)
+    auto window = [&](const uint32_t* c, int i, uint32_t& lo, uint32_t& hi) {
+        const int W = (i - 1) * S, sh = (W & 15) * 2;
+        const uint32_t* c0 = c + (W >> 4) * T;
+        const uint32_t x = c0[0], y = c0[T], z = c0[2 * T];
+        lo = __funnelshift_r(x, y, sh);
+        hi = __funnelshift_r(y, z, sh);
+    };
+
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t ri = b.first + tile * T + tid;
+        const bool live = tile * T + tid < b.n_reads;
+        int action = FAST_DONE;
+        dcb_result out;
+        *reinterpret_cast<uint4*>(&out) = make_uint4(0, 0, 0, 0);
+        uint32_t w[NW];
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(b.words + (size_t)(live ? ri : 0) * NW);
+#pragma unroll
+            for (int k = 0; k < NW / 4; k++) {
+                const uint4 v = ldg_stream(src + k);
+                w[4 * k + 0] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+            }
+#pragma unroll
+            for (int k = 0; k < NW; k++) s_rd[(1 + k) * T + tid] = w[k];
+        }
+        const bool flagged = live && b.n_exc && ((__ldg(b.flags + (ri >> 5)) >> (ri & 31)) & 1u);
+        const bool scan = live && !flagged;
+        ReadView r;
+        r.w = col; r.inv = nullptr; r.stride = T;
+        r.n = b.uniform_len ? (int)b.uniform_len : (live ? (int)__ldg(b.lens + ri) : 0);
+        r.nw = NW;
+        r.exc_pos = nullptr; r.exc_kind = nullptr; r.e0 = r.e1 = 0; r.mirror = 0;
+
+        // 1. probe: bit NPOS-1-i of h <=> the q-mer at i * S may be indexed
+        uint32_t h = 0;
+#pragma unroll
+        for (int i = 0; i < NPOS; i++) {
+            const int p = i * S, a = p >> 4, sh = (p & 15) * 2;
+            uint32_t win;   // at least the 2Q key bits of the q-mer at p (higher bits never reach the product)
+            if (sh == 0) win = w[a];
+            else if (sh + 2 * Q <= 32 || a + 1 >= NW) win = w[a] >> sh;
+            else win = __funnelshift_r(w[a], w[a + 1], sh);
+            h = mad2(h, lds_u8(filt + ((win * FMUL) >> (32 - DCB_FBITS))));
+        }
+        {
+            const int nvalid = r.n >= Q ? (r.n - Q) / S + 1 : 0;     // probes whose q-mer lies inside the read
+            if (nvalid < NPOS) h &= ~((1u << (NPOS - nvalid)) - 1u);
+            if (!scan) h = 0;
+        }
+        __syncwarp();                                                 // the warp's columns are written
+
+        // 2. the owner confirms its first two hits
+        HitWords hw;
+        hw.v = 0; hw.j = 0; hw.n_v = ix.n_v;
+#pragma unroll
+        for (int round = 0; round < 2; round++) {
+            if (h) {
+                const int bit = 31 - __clz(h);
+                h ^= 1u << bit;
+                const int i = NPOS - 1 - bit;
+                uint32_t wlo, whi;
+                window(col, i, wlo, whi);
+                uint32_t offs = q_offsets(ix, __funnelshift_r(wlo, whi, 2 * WLEAD));
+                if (offs) {
+                    const int o = 31 - __clz(offs);
+                    offs ^= 1u << o;
+                    q_check_offset<true>(r, ix, i * S, o, wlo, whi, hw);
+                    while (offs) {
+                        const int o2 = 31 - __clz(offs);
+                        offs ^= 1u << o2;
+                        q_push(qn + 1, qb, kQCapB, (uint32_t)lane | ((uint32_t)i << 5) | ((uint32_t)o2 << 10), qn + 2, lane);
+                    }
+                }
+            }
+        }
+        while (h) {
+            const int bit = 31 - __clz(h);
+            h ^= 1u << bit;
+            q_push(qn, qa, kQCapA, (uint32_t)lane | ((uint32_t)(NPOS - 1 - bit) << 5), qn + 2, lane);
+        }
+        __syncwarp();
+
+        // 3. the queues, 32 items per trip, any lane for any read of the warp
+        const uint32_t n_a = min(qn[0], (uint32_t)kQCapA);
+        if (n_a | qn[1]) {                                            // warp-uniform
+            for (uint32_t base = 0; base < n_a; base += 32) {         // whole-warp trips
+                const uint32_t t = base + lane;
+                if (t < n_a) {
+                    const uint32_t e = qa[t];
+                    const int owner = e & 31, i = e >> 5;
+                    uint32_t wlo, whi;
+                    window(wcol + owner, i, wlo, whi);
+                    uint32_t offs = q_offsets(ix, __funnelshift_r(wlo, whi, 2 * WLEAD));
+                    while (offs) {
+                        const int o = 31 - __clz(offs);
+                        offs ^= 1u << o;
+                        q_push(qn + 1, qb, kQCapB, (uint32_t)owner | ((uint32_t)i << 5) | ((uint32_t)o << 10), qn + 2, owner);
+                    }
+                }
+            }
+            __syncwarp();
+            const uint32_t n_b = min(qn[1], (uint32_t)kQCapB);
+            for (uint32_t base = 0; base < n_b; base += 32) {
+                const uint32_t t = base + lane;
+                const bool valid = t < n_b;
+                const uint32_t e = valid ? qb[t] : 0u;
+                const int owner = e & 31, i = (e >> 5) & 31, o = e >> 10;
+                const int n_owner = __shfl_sync(0xFFFFFFFFu, r.n, owner);
+                if (valid) {
+                    uint32_t wlo, whi;
+                    window(wcol + owner, i, wlo, whi);
+                    ReadView ro = r;
+                    ro.w = wcol + owner;
+                    ro.n = n_owner;
+                    SlotSink sink;
+                    sink.slots = slots; sink.owner = owner; sink.n_v = ix.n_v;
+                    q_check_offset<true>(ro, ix, i * S, o, wlo, whi, sink);
+                }
+            }
+            __syncwarp();
+            hw.v = hit_merge(hw.v, slots[2 * lane]);
+            hw.j = hit_merge(hw.j, slots[2 * lane + 1]);
+            const bool overflow = (qn[2] >> lane) & 1u;
+            __syncwarp();
+            slots[2 * lane] = 0u; slots[2 * lane + 1] = 0u;
+            if (lane < 3) qn[lane] = 0u;
+            if (overflow) hw.v = hw.j = 0u;                            // incomplete search: nothing found => deferred below
+        }
+        const FullHit vh = hit_decode(hw.v), jh = hit_decode(hw.j);
+        if (scan) action = dcr_fast_from_hits<true>(r, vtags, jtags, vh, jh, prm, both_frames, out, s_cnt);
+        else if (live) action = FAST_DEFER;
+        defer_reads(live && action == FAST_DEFER, ri, queue, queue_count);
+        if (live && action == FAST_DONE) store_result(results + ri, out);
+    }
+    flush_counters(s_cnt, counters);
+}
+
+// ------------------------------------------------------------------------------------------------
 // general kernel (queued reads, or every read when queue == nullptr)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kGeneralThreads)
@@ -501,6 +744,9 @@ struct dcb_ctx {
     int qv = 0, sv = 0, qj = 0, sj = 0, lminv = 0, lminj = 0;
     int vhead = 0, jhead = 0, uhead = 0, vbloom = 0, jbloom = 0, ubloom = 0;   // head_words / bloom_off of the three indexes
     void* spec_fn = nullptr;   // specialised exact kernel picked for the resident batch, or null
+    void* q_fn = nullptr;      // queue kernel picked for the resident batch, or null (then spec_fn / the generic kernel run)
+    int ulegacy = 0, uqtab_off = 0, uqtab_words = 0, ubfilter_off = 0, ufbits = 0;
+    int vlegacy = 0, jlegacy = 0;
     bool spec_union = false;
 };
 
@@ -524,6 +770,25 @@ static exact_spec_fn pick_spec(int nw, int qv, int sv, int lminv, int qj, int sj
     }
 #undef DCB_SPEC
 }
+// Queue kernel: chains whose V and J tags share the (q=9, stride 12) geometry, read slots up to 24 words.
+typedef void (*exact_q_fn)(BatchDev, QTables, DcrParams, int, dcb_result*, unsigned long long*, uint32_t*, uint32_t*);
+static constexpr int kQThreads = 1024;
+static exact_q_fn pick_q(int nw, int q, int s, int lmin) {
+    if (q != 9 || s != 12 || lmin != 20) return nullptr;
+    switch (nw) {
+        case 8:  return dcb_exact_kernel_q<8, 9, 12, kQThreads>;
+        case 12: return dcb_exact_kernel_q<12, 9, 12, kQThreads>;
+        case 16: return dcb_exact_kernel_q<16, 9, 12, kQThreads>;
+        case 20: return dcb_exact_kernel_q<20, 9, 12, kQThreads>;
+        default: return nullptr;
+    }
+}
+static int q_rows(int nw) {   // must match the kernel's ROWS
+    const int npos = (16 * nw - 9) / 12 + 1, wmax = ((npos - 1) * 12 - 12) >> 4;
+    const int trail = wmax + 3 - nw > 1 ? wmax + 3 - nw : 1;
+    return 1 + nw + trail;
+}
+
 // rows of shared memory per read column in the specialised kernel (must match the kernel's ROWS)
 static int spec_rows(int nw, bool uni) {
     auto wmax = [&](int q, int s) { const int npos = (16 * nw - q) / s + 1; return ((npos - 1) * s - (s)) >> 4; };  // wlead == stride
@@ -605,11 +870,13 @@ dcb_ctx* dcb_ctx_create(int device, const dcb_tagset* v, const dcb_tagset* j, co
         const DcbSeedIndex& ij = *reinterpret_cast<const DcbSeedIndex*>(j->index.data());
         c->qv = iv.q; c->sv = iv.stride; c->qj = ij.q; c->sj = ij.stride; c->lminv = iv.lmin; c->lminj = ij.lmin;
         c->vhead = iv.head_words; c->vbloom = iv.bloom_off; c->jhead = ij.head_words; c->jbloom = ij.bloom_off;
+        c->vlegacy = iv.legacy_words; c->jlegacy = ij.legacy_words;
         if (v->lmin == j->lmin) {  // same seed geometry: one index (and one filter) finds both genes
             std::vector<uint32_t> u;
             if (dcb_build_seed_index(&v->tags, &j->tags, v->lmin, DCB_WBITS_UNION, u)) {
                 const DcbSeedIndex& iu = *reinterpret_cast<const DcbSeedIndex*>(u.data());
-                c->uhead = iu.head_words; c->ubloom = iu.bloom_off;
+                c->uhead = iu.head_words; c->ubloom = iu.bloom_off; c->ulegacy = iu.legacy_words;
+                c->uqtab_off = iu.qtab_off; c->uqtab_words = iu.qtab_words; c->ubfilter_off = iu.bfilter_off; c->ufbits = iu.fbits;
                 if (upload_blob(u, &c->d_uidx, &c->uidx_words)) return fail(nullptr);
             }
         }
@@ -666,14 +933,28 @@ static int prepare_batch(dcb_ctx* c, const dcb_packed* P) {
     const size_t nwi = (sw + 1) / 2;
     // exact-tag tables: tag records of both genes + either the union index or the two per-gene indexes
     const bool have_union = c->d_uidx != nullptr;
-    const size_t tbl_e = (size_t)c->vcore_words + c->jcore_words + (have_union ? (size_t)c->uidx_words : (size_t)c->vidx_words + c->jidx_words);
+    const size_t tbl_e = (size_t)c->vcore_words + c->jcore_words + (have_union ? (size_t)c->ulegacy : (size_t)c->vlegacy + c->jlegacy);
     bool is_union = false;
-    exact_spec_fn spec = c->params.force_general ? nullptr
+    exact_spec_fn spec = c->params.force_general == 1 ? nullptr
                                                  : pick_spec((int)sw, c->qv, c->sv, c->lminv, c->qj, c->sj, c->lminj, &is_union);
     if (spec && is_union != have_union) spec = nullptr;
     c->spec_fn = (void*)spec; c->spec_union = have_union;
     int occ_e = 0, occ_g = 0;
-    if (spec) {
+    exact_q_fn qfn = nullptr;
+    if (have_union && c->params.force_general == 0 && c->ufbits == DCB_FBITS)
+        qfn = pick_q((int)sw, c->qv, c->sv, c->lminv);
+    if (qfn) {
+        c->exact_smem = ((size_t)1 << DCB_FBITS) + ((size_t)q_rows((int)sw) * kQThreads + (size_t)(kQThreads / 32) * kQWarpWords +
+                         c->vcore_words + c->jcore_words + c->uhead + c->uqtab_words) * 4 + tail;
+        if (c->exact_smem > kMaxSmem) qfn = nullptr;
+    }
+    c->q_fn = (void*)qfn;
+    if (qfn) {
+        spec = nullptr; c->spec_fn = nullptr;
+        c->exact_threads = kQThreads;
+        CUDA_TRY(cudaFuncSetAttribute(qfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->exact_smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, qfn, c->exact_threads, c->exact_smem));
+    } else if (spec) {
         // tables (index heads only) + the private copies of the filter(s) + the read columns of as wide a block as fits
         const size_t tbl_s = (size_t)c->vcore_words + c->jcore_words + (have_union ? (size_t)c->uhead : (size_t)c->vhead + c->jhead);
         const size_t blooms = have_union ? ((size_t)DCB_BLOOM_COPIES << DCB_WBITS_UNION) : 2 * ((size_t)DCB_BLOOM_COPIES << DCB_WBITS_SINGLE);
@@ -686,7 +967,8 @@ static int prepare_batch(dcb_ctx* c, const dcb_packed* P) {
         if (T < 256) { spec = nullptr; c->spec_fn = nullptr; }
         else c->exact_threads = T;
     }
-    if (spec) {
+    if (qfn) {
+    } else if (spec) {
         CUDA_TRY(cudaFuncSetAttribute(spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->exact_smem));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, spec, c->exact_threads, c->exact_smem));
     } else {
@@ -746,14 +1028,21 @@ static int launch_range(dcb_ctx* c, cudaStream_t s, uint32_t first, uint32_t cou
     const int grid_e = (int)std::max<uint32_t>(1, std::min<uint32_t>(tiles_e, (uint32_t)c->exact_grid));
     const int grid_g = (int)std::max<uint32_t>(1, std::min<uint32_t>(tiles_g, (uint32_t)c->general_grid));
     int rc;
-    if (!c->params.force_general) {
+    if (c->params.force_general != 1) {
         if (timed && (rc = timing_begin(c, 0))) return rc;
         Tables4 te;
         te.g[0] = c->d_vcore; te.words[0] = c->vcore_words;
         te.g[1] = c->d_jcore; te.words[1] = c->jcore_words;
-        if (c->spec_union) { te.g[2] = c->d_uidx; te.words[2] = c->uidx_words; te.g[3] = nullptr; te.words[3] = 0; }
-        else { te.g[2] = c->d_vidx; te.words[2] = c->vidx_words; te.g[3] = c->d_jidx; te.words[3] = c->jidx_words; }
-        if (c->spec_fn) {
+        if (c->spec_union) { te.g[2] = c->d_uidx; te.words[2] = c->ulegacy; te.g[3] = nullptr; te.words[3] = 0; }
+        else { te.g[2] = c->d_vidx; te.words[2] = c->vlegacy; te.g[3] = c->d_jidx; te.words[3] = c->jlegacy; }
+        if (c->q_fn) {
+            QTables qt;
+            qt.vcore = c->d_vcore; qt.jcore = c->d_jcore; qt.head = c->d_uidx; qt.qtab = c->d_uidx + c->uqtab_off;
+            qt.bfilter = c->d_uidx + c->ubfilter_off;
+            qt.vcore_words = c->vcore_words; qt.jcore_words = c->jcore_words; qt.head_words = c->uhead; qt.qtab_words = c->uqtab_words;
+            ((exact_q_fn)c->q_fn)<<<grid_e, c->exact_threads, c->exact_smem, s>>>(
+                b, qt, prm, c->params.both_frames, (dcb_result*)c->results.p, c->d_counters, queue, qcount);
+        } else if (c->spec_fn) {
             SpecBlooms sb;
             if (c->spec_union) { te.words[2] = c->uhead; sb.v = c->d_uidx + c->ubloom; sb.j = nullptr; }
             else { te.words[2] = c->vhead; te.words[3] = c->jhead; sb.v = c->d_vidx + c->vbloom; sb.j = c->d_jidx + c->jbloom; }
@@ -772,7 +1061,7 @@ static int launch_range(dcb_ctx* c, cudaStream_t s, uint32_t first, uint32_t cou
     tg.g[2] = tg.g[3] = nullptr; tg.words[2] = tg.words[3] = 0;
     dcb_general_kernel<<<grid_g, c->general_threads, c->general_smem, s>>>(
         b, tg, prm, c->params.both_frames, (dcb_result*)c->results.p, c->d_counters,
-        c->params.force_general ? nullptr : (const uint32_t*)queue, qcount);
+        c->params.force_general == 1 ? nullptr : (const uint32_t*)queue, qcount);
     CUDA_TRY(cudaGetLastError());
     if (timed && (rc = timing_end(c))) return rc;
     return DCB_OK;
@@ -877,6 +1166,10 @@ int dcb_timing_get(dcb_ctx* c, double ms[DCB_NTIMERS], uint64_t launches[DCB_NTI
     for (int i = 0; i < DCB_NTIMERS; i++) { if (ms) ms[i] = c->ms[i]; if (launches) launches[i] = c->launches[i]; }
     return rc;
 }
+const char* dcb_exact_kernel_name(const dcb_ctx* c) {
+    if (!c || !c->have_batch) return "";
+    return c->q_fn ? "dcb_exact_kernel_q" : c->spec_fn ? "dcb_exact_kernel_spec" : "dcb_exact_kernel";
+}
 int dcb_last_deferred(dcb_ctx* c, uint64_t* n) {
     if (!c || !n || !c->ran) return DCB_EINVAL;
     uint32_t q[kMaxChunks];
@@ -884,7 +1177,7 @@ int dcb_last_deferred(dcb_ctx* c, uint64_t* n) {
     CUDA_TRY(cudaMemcpy(q, c->d_queue_count, sizeof(q), cudaMemcpyDeviceToHost));
     uint64_t total = 0;
     for (int i = 0; i < kMaxChunks; i++) total += q[i];
-    *n = c->params.force_general ? c->batch.n_reads : total;
+    *n = c->params.force_general == 1 ? c->batch.n_reads : total;
     return DCB_OK;
 }
 

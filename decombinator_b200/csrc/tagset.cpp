@@ -159,6 +159,64 @@ void build_kwset(Blob& b, DcbKwSet& ks, const std::vector<std::string>& list) {
     }
 }
 
+// Hash-and-displace table over the indexed q-mers (see DcbSeedIndex): buckets are placed largest first, each with the
+// smallest displacement that drops all its keys into free slots.
+struct Chd {
+    uint32_t m1 = 1, m2 = 1;
+    int b1 = 1, b2 = 1;
+    std::vector<uint16_t> disp, slot;
+    bool build(const std::vector<std::pair<uint32_t, uint32_t>>& items, int b1_, int b2_, uint32_t m1_, uint32_t m2_) {
+        b1 = b1_; b2 = b2_; m1 = m1_; m2 = m2_;
+        const size_t n1 = (size_t)1 << b1, n2 = (size_t)1 << b2;
+        std::vector<std::vector<size_t>> bucket(n1);
+        for (size_t i = 0; i < items.size(); i++) bucket[(items[i].first * m1) >> (32 - b1)].push_back(i);
+        std::vector<size_t> order(n1);
+        for (size_t i = 0; i < n1; i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t c) { return bucket[a].size() > bucket[c].size(); });
+        disp.assign(n1, 0); slot.assign(n2, 0);
+        std::vector<uint8_t> used(n2, 0);
+        std::vector<uint32_t> base, at;
+        for (size_t bi : order) {
+            const auto& bk = bucket[bi];
+            if (bk.empty()) break;
+            base.clear();
+            for (size_t i : bk) base.push_back((items[i].first * m2) >> (32 - b2));
+            for (size_t i = 0; i < base.size(); i++)
+                for (size_t k = i + 1; k < base.size(); k++)
+                    if (base[i] == base[k]) return false;           // collide under every displacement
+            bool placed = false;
+            for (uint32_t d = 0; d < n2 && d < 65536u && !placed; d++) {
+                bool ok = true;
+                for (uint32_t x : base) if (used[(x + d) & (n2 - 1)]) { ok = false; break; }
+                if (!ok) continue;
+                for (size_t i = 0; i < bk.size(); i++) {
+                    const uint32_t s = (base[i] + d) & (uint32_t)(n2 - 1);
+                    used[s] = 1; slot[s] = (uint16_t)items[bk[i]].second;
+                }
+                disp[bi] = (uint16_t)d;
+                placed = true;
+            }
+            if (!placed) return false;
+        }
+        return true;
+    }
+};
+
+bool build_chd(Chd& chd, const std::vector<std::pair<uint32_t, uint32_t>>& items, int q) {
+    if (2 * q > 30) return false;
+    int b2 = 4;
+    while (((size_t)1 << b2) < 2 * items.size() + 2) b2++;
+    int b1 = b2 > 4 ? b2 - 3 : 1;                                   // ~2 keys per bucket on average at load <= 0.5
+    if (b2 > 2 * q) return false;
+    uint64_t rng = 0xD1B54A32D192ED03ull;
+    for (int attempt = 0; attempt < 4096; attempt++) {
+        rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+        const uint32_t m1 = ((uint32_t)rng | 1u) << (32 - 2 * q), m2 = ((uint32_t)(rng >> 32) | 1u) << (32 - 2 * q);
+        if (chd.build(items, b1, b2, m1, m2)) return true;
+    }
+    return false;
+}
+
 int seed_q(int lmin) { return lmin >= 18 ? 9 : lmin >= 12 ? 8 : lmin >= 8 ? 6 : lmin; }
 
 }  // namespace
@@ -288,6 +346,27 @@ bool dcb_build_seed_index(const std::vector<std::string>* gene_v, const std::vec
     idx.bloom_off = b.reserve(words);
     for (auto& kv : seeds)
         b.w[idx.bloom_off + DCB_BLOOM_WORD(kv.first, idx.bmul, wbits)] |= 1u << DCB_BLOOM_BIT(kv.first);
+    b.align4();
+    idx.legacy_words = (int32_t)b.w.size();
+    {   // queue kernel: q-mer -> offset set by hash-and-displace, and the byte filter
+        std::vector<std::pair<uint32_t, uint32_t>> items(seeds.begin(), seeds.end());
+        Chd chd;
+        if (!build_chd(chd, items, idx.q)) return false;
+        idx.m1 = chd.m1; idx.m2 = chd.m2; idx.b1 = chd.b1; idx.b2 = chd.b2;
+        const size_t n1 = (size_t)1 << chd.b1, n2 = (size_t)1 << chd.b2;
+        idx.qtab_off = b.reserve((n1 + n2 + 1) / 2);
+        uint16_t* t16 = reinterpret_cast<uint16_t*>(&b.w[idx.qtab_off]);
+        for (size_t i = 0; i < n1; i++) t16[i] = chd.disp[i];
+        for (size_t i = 0; i < n2; i++) t16[n1 + i] = chd.slot[i];
+        b.align4();
+        idx.qtab_words = (int32_t)b.w.size() - idx.qtab_off;
+        idx.fbits = DCB_FBITS;
+        idx.fmul = DCB_BLOOM_MUL(idx.q);
+        if (idx.fbits > 2 * idx.q) idx.fbits = 2 * idx.q;
+        idx.bfilter_off = b.reserve(((size_t)1 << idx.fbits) / 4);
+        uint8_t* f8 = reinterpret_cast<uint8_t*>(&b.w[idx.bfilter_off]);
+        for (auto& kv : seeds) f8[(kv.first * idx.fmul) >> (32 - idx.fbits)] = 1;
+    }
     b.align4();
     idx.n_words = (int32_t)b.w.size();
     std::memcpy(&b.w[0], &idx, sizeof(idx));

@@ -32,7 +32,7 @@ extern "C" int sim_decombine(const dcb_packed* P, const uint32_t* vgen, const ui
         dcb_result o;
         std::memset(&o, 0, sizeof(o));
         int action = FAST_DEFER;
-        if (mode == 0) action = dcr_exact_read(r, flagged, vcore, jcore, vidx, jidx, prm, both_frames, o, cnt);
+        if (mode == 0 || mode == 2) action = dcr_exact_read(r, flagged, vcore, jcore, vidx, jidx, prm, both_frames, o, cnt, mode == 2);
         if (action == FAST_DEFER) {
             deferred++;
             std::memset(&o, 0, sizeof(o));

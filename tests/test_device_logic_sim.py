@@ -10,15 +10,19 @@ from decombinator_b200 import _lib, tags
 from helpers import assert_records_equal, record_to_list, synth_batch
 
 
-@pytest.mark.parametrize("general_only,use_union", [(False, None), (False, False), (True, None)])
-def test_sim_matches_reference_fixtures(dcr_cases, general_only, use_union):
+@pytest.mark.parametrize("general_only,use_union,use_q", [(False, None, False), (False, False, False), (True, None, False),
+                                                          (False, None, True)])
+def test_sim_matches_reference_fixtures(dcr_cases, general_only, use_union, use_q):
     names = dcr_cases["counters"]
     for gi, g in enumerate(dcr_cases["groups"]):
         info = tags.load(g["species"], g["tags"], g["chain"])
         vt, jt = info.tables()
+        if use_q and _lib.union_index(vt, jt) is None:
+            continue   # the queue kernel's tables exist for chains whose V and J tags share the seed geometry
         packed = _lib.pack_strings(g["reads"], revcomp=(g["orientation"] != "forward"))
         res, cnt, _ = simlib.sim_decombine(packed, vt, jt, both_frames=(g["orientation"] == "both"), allow_ns=g["allowNs"],
-                                           lenthreshold=g["lenthreshold"], general_only=general_only, use_union=use_union)
+                                           lenthreshold=g["lenthreshold"], general_only=general_only, use_union=use_union,
+                                           use_q=use_q)
         got = [record_to_list(r, rec, g["orientation"]) for r, rec in zip(g["reads"], res)]
         bad = [i for i, (a, b) in enumerate(zip(got, g["results"])) if a != b]
         assert not bad, (gi, bad[:5])
@@ -47,4 +51,7 @@ def test_sim_matches_oracle_on_synthetic(species, tagset, chain, orientation, L,
     assert np.array_equal(cnt, orc.counts)
     if sub == 0.0:
         assert deferred < 0.1 * n  # the exact-tag path must carry clean data on its own
+    if _lib.union_index(vt, jt) is not None:   # the queue kernel's tables find exactly the same tags
+        res_q, cnt_q, deferred_q = simlib.sim_decombine(packed, vt, jt, both_frames=(orientation == "both"), use_q=True)
+        assert np.array_equal(res_q, res) and np.array_equal(cnt_q, cnt) and deferred_q == deferred
     packed.free()

@@ -21,7 +21,9 @@ def _ctx(info, **kw):
     return _lib.Context(vt, jt, device=0, **kw)
 
 
-@pytest.mark.parametrize("force_general", [False, True])
+# force_general: 0 = the shipped path (queue kernel where the chain has one seed geometry, else the per-lane exact
+# kernels), 1 = general kernel only, 2 = per-lane exact kernels only
+@pytest.mark.parametrize("force_general", [0, 1, 2])
 def test_cuda_matches_reference_fixtures(dcr_cases, force_general):
     names = dcr_cases["counters"]
     for gi, g in enumerate(dcr_cases["groups"]):
@@ -61,7 +63,7 @@ def test_cuda_matches_oracle_on_synthetic(species, tagset, chain, orientation, L
     orc = O.Oracle(O.TagSet(species, tagset, chain))
     want = orc.decombine_arrays(r1, off, ln, orientation, nthreads=os.cpu_count() or 4)
     packed = _lib.pack_arrays(r1, off, ln, revcomp=(orientation != "forward"))
-    for force_general in (False, True):
+    for force_general in (0, 1, 2):
         ctx = _ctx(info, both_frames=(orientation == "both"), force_general=force_general)
         res, cnt = ctx.decombine(packed)
         assert_records_equal(res, want, orientation, "force_general=%s" % force_general)
@@ -102,7 +104,7 @@ def test_ragged_empty_and_extreme_inputs():
     want = orc.decombine_reads(ragged, "both")
     packed = _lib.pack_strings(ragged, revcomp=True)
     assert packed.uniform_len == 0 and packed.max_len == 4000
-    for fg in (False, True):
+    for fg in (0, 1, 2):
         ctx = _ctx(info, both_frames=True, force_general=fg)
         res, cnt = ctx.decombine(packed)
         assert_records_equal(res, want, "both", "ragged fg=%s" % fg)
@@ -115,6 +117,36 @@ def test_ragged_empty_and_extreme_inputs():
     res, cnt = ctx.decombine(p0)
     assert len(res) == 0 and not cnt.any()
     ctx.close()
+
+
+def _revcomp(s):
+    return s[::-1].translate(str.maketrans("ACGT", "TGCA"))
+
+
+@pytest.mark.parametrize("L", [128, 250, 320])
+def test_tag_dense_reads_overflow_the_warp_queues(L):
+    """Reads made of back-to-back tags give every lane of a warp ~10 seed hits: far more than the per-warp queues of
+    the queue kernel hold.  Overflowing reads must be handed to the general kernel, results unchanged."""
+    info = tags.load("human", "extended", "b")
+    rng = np.random.default_rng(7)
+    vs, js = list(info.v_seqs), list(info.j_seqs)
+    r1, off, ln = synth_batch(info, 4000, L, 0.0, 0.0, 0.0, seed=3)
+    reads = [bytes(r1[i * L:(i + 1) * L]).decode() for i in range(4000)]
+    for i in range(0, 4000, 2):          # every other read, and one solid block of them
+        parts = [(vs if rng.random() < 0.8 else js)[rng.integers(0, 14)] for _ in range(L // 20 + 1)]
+        reads[i] = _revcomp("".join(parts)[:L])
+    for i in range(1000, 1200):
+        reads[i] = _revcomp("".join(vs[(i + k) % len(vs)] for k in range(L // 20 + 1))[:L])
+    orc = O.Oracle(O.TagSet("human", "extended", "b"))
+    want = orc.decombine_reads(reads, "reverse")
+    packed = _lib.pack_strings(reads, revcomp=True)
+    for fg in (0, 2):
+        ctx = _ctx(info, force_general=fg)
+        res, cnt = ctx.decombine(packed)
+        assert_records_equal(res, want, "reverse", "dense fg=%s" % fg)
+        assert np.array_equal(cnt, orc.counts)
+        ctx.close()
+    packed.free()
 
 
 def _digest(res):
@@ -133,10 +165,11 @@ def test_full_size_properties_config2():
     res, cnt = ctx.decombine(packed)
     res2, cnt2 = ctx.decombine(packed)
     assert _digest(res) == _digest(res2) and np.array_equal(cnt, cnt2)          # deterministic
-    ctxg = _ctx(info, force_general=True)
-    resg, cntg = ctxg.decombine(packed)
-    assert _digest(res) == _digest(resg) and np.array_equal(cnt, cntg)          # exact-tag path == general path
-    ctxg.close()
+    for fg in (1, 2):
+        ctxg = _ctx(info, force_general=fg)
+        resg, cntg = ctxg.decombine(packed)
+        assert _digest(res) == _digest(resg) and np.array_equal(cnt, cntg)      # three independent kernels agree
+        ctxg.close()
     # shard invariance: 8 contiguous shards (what 8 GPUs would each see) concatenate to the whole
     parts, csum = [], np.zeros_like(cnt)
     for s in range(8):
