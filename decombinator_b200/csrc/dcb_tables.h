@@ -109,7 +109,7 @@ struct DcbSeedIndex {
     int32_t head_words;          // words before the filter (what the specialised kernels stage verbatim)
     int32_t bloom_off;           // the bit filter follows the head
     int32_t n_words;
-    // --- tables of the queue kernel (dcb_exact_kernel_q), stored behind the bit filter -------------------------------
+    // --- tables of the flat kernel (dcb_exact_kernel_flat), stored behind the bit filter -------------------------------
     //   * byte filter: ONE byte per slot (1 = an indexed q-mer hashes here), slot = (window * fmul) >> (32 - fbits).
     //     A probe is IMAD, SHF, LDS.U8 and one IMAD that appends the byte to the hit mask: no bit extraction, and half
     //     of the probe's instructions run on the FMA pipe instead of the (saturated) ALU pipe;
@@ -117,7 +117,10 @@ struct DcbSeedIndex {
     //     + disp[bucket]) & (2^b2 - 1); the 16-bit slot holds the set of tag offsets the q-mer occurs at (bit o).  No
     //     fingerprint: every candidate is compared with the read as a whole, a filter false positive just finds nothing.
     //     m1, m2 and fmul are odd << (32 - 2q), so only the q-mer's own bits of a wider window reach the products.
+    //     The flat kernel's tables have their OWN seed geometry (qq, qstride): longer seeds sampled more densely
+    //     (20-nt tags: 13-mers at every 8th position) hit fewer homologous tags, which is what its trip count pays for.
     int32_t legacy_words;        // words up to the end of the bit filter (what the other exact kernels stage)
+    int32_t qq, qstride;         // seed length / sampling stride of the tables below (qstride = lmin - qq + 1 = their wlead)
     int32_t fbits;
     uint32_t fmul;
     uint32_t m1, m2;
@@ -125,8 +128,27 @@ struct DcbSeedIndex {
     int32_t qtab_off;            // uint16 disp[2^b1] then uint16 offsets[2^b2]
     int32_t qtab_words;
     int32_t bfilter_off;         // 2^fbits bytes
+    //   * tag slots: a PERFECT hash over the lmin-prefixes straight to 8-byte records (inside the qtab block):
+    //     slot = (prefix_lo * ta + prefix_hi * tb) >> (32 - tq_bits); a record is {prefix_lo, DCB_TQ_META(...)} so a 20-nt
+    //     tag is confirmed by ONE 64-bit read and two compares.  DCB_TQ_MORE marks tags longer than lmin or sharing their
+    //     prefix with another tag: those go on to the whole-tag compare / chain walk of the other kernels.  A free slot
+    //     has length 255 (never fits a read).
+    int32_t tq_off, tq_bits;
+    uint32_t ta, tb;
+    int32_t qwlead;              // the flat kernel's verification window starts at p - qwlead (= qstride - 1)
 };
-#define DCB_FBITS 16             // byte filter of the queue kernel: 64 KB
+// meta word of a tag slot: prefix bits 32.. (2 * lmin - 32 <= 14 of them) and one guard bit above them that only a free
+// slot sets (so a free slot equals no read) | ctag << 16 (8 bits) | DCB_TQ_MORE | length << 25
+#define DCB_TQ_MORE (1u << 24)
+#define DCB_TQ_META(prefix_hi, ctag, len, more) ((uint32_t)(prefix_hi) | ((uint32_t)(ctag) << 16) | ((more) ? DCB_TQ_MORE : 0u) | ((uint32_t)(len) << 25))
+#define DCB_TQ_LEN(meta) ((meta) >> 25)
+#define DCB_TQ_CTAG(meta) (((meta) >> 16) & 0xFFu)
+#define DCB_TQ_HIBITS(lmin) (2 * (lmin) - 32)                       // prefix bits held in the meta word
+#define DCB_TQ_CMPMASK(lmin) ((2u << DCB_TQ_HIBITS(lmin)) - 1u)     // those bits and the guard bit
+#define DCB_TQ_FREE(lmin) DCB_TQ_META(1u << DCB_TQ_HIBITS(lmin), 0xFF, 127, 0)
+#define DCB_FBITS 16             // byte filter of the flat kernel: 64 KB
+// seed length of the flat kernel's tables: stride 8 where the tags allow it (2 * qq <= 30 bits of key)
+#define DCB_QQ(lmin, q) (((lmin) >= 20 && (lmin) <= 22) ? (lmin) - 7 : (q))
 
 #define DCB_CK_FPMASK 0xFFFFF000u                               // fingerprint bits of a slot / of a product
 #define DCB_CK_OFFMASK(e) ((e) & 0xFFFu)

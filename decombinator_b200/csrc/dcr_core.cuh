@@ -589,7 +589,7 @@ DCB_HD void fast_find(const ReadView& r, const uint32_t* ib, FullHit& vh, FullHi
 }
 
 // ------------------------------------------------------------------------------------------------
-// Queue kernel (dcb_exact_kernel_q): byte filter + hash-and-displace offset table (DcbSeedIndex, second half).
+// Flat kernel (dcb_exact_kernel_flat): byte filter + hash-and-displace offset table (DcbSeedIndex, second half).
 // A full-tag occurrence is kept as ONE word per gene: 0 = none, DCB_HIT_MULTI = two or more distinct occurrences,
 // else DCB_HIT_ONE | tag << 16 | position.
 // ------------------------------------------------------------------------------------------------
@@ -606,14 +606,15 @@ DCB_HD FullHit hit_decode(uint32_t h) {
     return fh;
 }
 
+struct alignas(8) DcbTq { uint32_t x, y; };   // one tag slot: prefix_lo, meta
 struct QIdxView {
     const uint16_t* disp;      // 2^b1 displacements
     const uint16_t* offs;      // 2^b2 offset sets
-    const uint16_t* tk;        // tag-prefix perfect-hash slots
+    const DcbTq* tq;           // tag slots: {prefix_lo, meta}
     const DcbUTag* utag;
     const uint16_t* chain;
-    uint32_t m1, m2, t1, mask2;
-    int s1, s2, tshift;
+    uint32_t m1, m2, ta, tb, mask2;
+    int s1, s2, tqshift;
     int q, stride, lmin, wlead, n_v;
 };
 // ib: the index blob; qtab: where its qtab_words were staged (ib + qtab_off when the blob is used in place)
@@ -622,12 +623,12 @@ DCB_HD QIdxView q_idx_view(const uint32_t* ib, const uint32_t* qtab) {
     QIdxView v;
     v.disp = reinterpret_cast<const uint16_t*>(qtab);
     v.offs = v.disp + ((size_t)1 << ix.b1);
-    v.tk = reinterpret_cast<const uint16_t*>(ib + ix.tk_off);
+    v.tq = reinterpret_cast<const DcbTq*>(qtab + (ix.tq_off - ix.qtab_off));
     v.utag = reinterpret_cast<const DcbUTag*>(ib + ix.utag_off);
     v.chain = ix.chain_off ? reinterpret_cast<const uint16_t*>(ib + ix.chain_off) : nullptr;
-    v.m1 = ix.m1; v.m2 = ix.m2; v.t1 = ix.t1; v.mask2 = (1u << ix.b2) - 1u;
-    v.s1 = 32 - ix.b1; v.s2 = 32 - ix.b2; v.tshift = ix.tshift;
-    v.q = ix.q; v.stride = ix.stride; v.lmin = ix.lmin; v.wlead = ix.wlead; v.n_v = ix.n_v;
+    v.m1 = ix.m1; v.m2 = ix.m2; v.ta = ix.ta; v.tb = ix.tb; v.mask2 = (1u << ix.b2) - 1u;
+    v.s1 = 32 - ix.b1; v.s2 = 32 - ix.b2; v.tqshift = 32 - ix.tq_bits;
+    v.q = ix.qq; v.stride = ix.qstride; v.lmin = ix.lmin; v.wlead = ix.qwlead; v.n_v = ix.n_v;
     return v;
 }
 // Offsets the q-mer in the low 2q bits of x occurs at in some tag (bit o); anything for a q-mer that is not indexed.
@@ -636,15 +637,22 @@ DCB_HD uint32_t q_offsets(const QIdxView& ix, uint32_t x) {
     return ix.offs[(((x * ix.m2) >> ix.s2) + d) & ix.mask2];
 }
 // One candidate: a tag starting at P = p - o, where (wlo, whi) are the 32 bases from p - wlead.  Calls
-// sink(ctag, P) for every tag found there (one, unless tags share their lmin-prefix).
+// sink(ctag, P) for every tag found there (one, unless tags share their lmin-prefix).  The lmin-prefix is looked up in
+// the tag slots: one 64-bit read confirms a tag of minimum length; longer tags and tags sharing a prefix (DCB_TQ_MORE)
+// go on to the whole-tag compare.
 template <bool PADDED, class Sink>
 DCB_HD void q_check_offset(const ReadView& r, const QIdxView& ix, int p, int o, uint32_t wlo, uint32_t whi, Sink& sink) {
     const int P = p - o;
-    const int sh = 2 * (ix.wlead - o);                 // 2 <= sh <= 2 * wlead <= 24
-    const uint32_t lo = DCB_FUNNEL_R(wlo, whi, sh), hi = whi >> sh;   // the 32 - (wlead - o) >= lmin bases from P on
-    const uint32_t f = dcb_fold64(lo & mask2(ix.lmin), ix.lmin > 16 ? (hi & mask2(ix.lmin - 16)) : 0u);
-    uint32_t ctag = ix.tk[(f * ix.t1) >> ix.tshift];
-    if (P < 0) return;
+    const int sh = 2 * (ix.wlead - o);                 // 0 <= sh <= 2 * wlead <= 22
+    const uint32_t lo = DCB_FUNNEL_R(wlo, whi, sh), hi = whi >> sh;   // the 32 - (wlead - o) >= lmin + 5 bases from P on
+    const uint32_t hp = hi & ((1u << DCB_TQ_HIBITS(ix.lmin)) - 1u);
+    const DcbTq e = ix.tq[(lo * ix.ta + hp * ix.tb) >> ix.tqshift];
+    if (e.x != lo || ((hp ^ e.y) & DCB_TQ_CMPMASK(ix.lmin)) != 0u || P < 0) return;
+    uint32_t ctag = DCB_TQ_CTAG(e.y);
+    if (!(e.y & DCB_TQ_MORE)) {
+        if (P + (int)DCB_TQ_LEN(e.y) <= r.n) sink(ctag, P);
+        return;
+    }
     while (ctag != 0x1FFu) {
         const DcbUTag u = ix.utag[ctag];
         const int L = (int)(u.mask_hi_len >> 24);
@@ -661,8 +669,11 @@ struct HitWords {
     uint32_t v, j;
     int n_v;
     DCB_HD void operator()(uint32_t ctag, int P) {
-        if ((int)ctag >= n_v) j = hit_merge(j, DCB_HIT_ONE | ((ctag - (uint32_t)n_v) << 16) | (uint32_t)P);
-        else v = hit_merge(v, DCB_HIT_ONE | (ctag << 16) | (uint32_t)P);
+        const bool is_j = (int)ctag >= n_v;
+        const uint32_t c = DCB_HIT_ONE | ((is_j ? ctag - (uint32_t)n_v : ctag) << 16) | (uint32_t)P;
+        const uint32_t m = hit_merge(is_j ? j : v, c);
+        v = is_j ? v : m;
+        j = is_j ? m : j;
     }
 };
 // The whole search for one read, serially (tests/sim and nothing else: the kernel spreads this work over a warp).

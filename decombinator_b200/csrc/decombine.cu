@@ -396,29 +396,23 @@ dcb_exact_kernel_spec(BatchDev b, Tables4 tb, SpecBlooms bl, DcrParams prm, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// exact-tag kernel, queue form (chains whose V and J tags share one seed geometry: every `extended` set).
+// exact-tag kernel, flat form (chains whose V and J tags share one seed geometry: every `extended` set).
 // Same contract as dcb_exact_kernel_spec -- the read slot in registers, compile-time seed positions, the same finish --
-// with the search reorganised so that the lanes of a warp do equal amounts of work:
-//   1. probe: ONE byte filter (64 KB, one byte per slot).  A probe is SHF (window), IMAD (hash), SHF (slot), LDS.U8
-//      and an IMAD that appends the byte to the hit mask; no bit extraction, half the instructions on the FMA pipe.
-//   2. the first two hits of a read (a clean read has exactly two: its V and its J tag) are confirmed by the lane that
-//      owns the read: q-mer -> offset set (hash-and-displace, two 16-bit reads) -> perfect-hash prefix table -> whole-tag
-//      compare.  Its first offset is checked on the spot.
-//   3. everything beyond that -- third and later hits (filter noise, homologous q-mers), second and later offsets --
-//      goes to two small per-warp queues in shared memory and is confirmed by WHICHEVER lane is free, 32 items per
-//      trip; results travel back through one slot per read and gene (compare-and-swap keeps "none / one / several").
-//      A queue that overflows marks the owning read as deferred (the general kernel redoes it), so capacity is never
-//      a correctness matter.
-// No block-wide barrier inside the tile loop: a warp only ever reads the read columns of its own lanes.
+// with a leaner search:
+//   1. probe: ONE byte filter (64 KB, one byte per slot) over 13-mers sampled at every 8th base.  A probe is (SHF for
+//      the odd positions; the even ones are word-aligned), IMAD (hash), SHF (slot), LDS.U8 and an IMAD that appends the
+//      byte to the hit mask: no bit extraction, half the instructions on the FMA pipe.
+//   2. confirm: one warp-voted loop; a trip pops a hit (window of 32 bases from shared memory, 13-mer -> offset set by
+//      hash-and-displace: two 16-bit reads) and checks ONE offset (perfect-hash prefix table -> whole-tag compare).
+//      13-mers are specific enough that the offset set is almost always one offset of one tag, so the trip count of a
+//      warp is close to its largest per-read hit count.  A read that already has two distinct V tags is final
+//      (multiple_v_matches) and drops its remaining hits.
+// No block-wide barrier inside the tile loop: a lane only ever reads the read column it wrote itself.
 // ------------------------------------------------------------------------------------------------
 struct QTables {
     const uint32_t* vcore; const uint32_t* jcore; const uint32_t* head; const uint32_t* qtab; const uint32_t* bfilter;
     int vcore_words, jcore_words, head_words, qtab_words;
 };
-static constexpr int kQCapA = 64;     // queued hits per warp and tile
-static constexpr int kQCapB = 192;    // queued (hit, offset) candidates per warp and tile
-// per-warp scratch, in words: 64 result slots, queue A (u16), queue B (u16), counters (nA, nB, defer mask, pad)
-static constexpr int kQWarpWords = 64 + kQCapA / 2 + kQCapB / 2 + 4;
 
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
     uint32_t v;
@@ -430,44 +424,27 @@ __device__ __forceinline__ uint32_t mad2(uint32_t h, uint32_t bit) {   // 2 * h 
     asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(v) : "r"(h), "r"(bit));
     return v;
 }
-// results of queued candidates: one slot per (owner lane, gene)
-struct SlotSink {
-    uint32_t* slots;   // this warp's 64 slots
-    int owner, n_v;
-    __device__ __forceinline__ void operator()(uint32_t ctag, int P) {
-        const bool is_j = (int)ctag >= n_v;
-        const uint32_t c = DCB_HIT_ONE | ((is_j ? ctag - (uint32_t)n_v : ctag) << 16) | (uint32_t)P;
-        uint32_t* s = slots + 2 * owner + (is_j ? 1 : 0);
-        const uint32_t old = atomicCAS(s, 0u, c);
-        if (old != 0u && old != c) atomicExch(s, DCB_HIT_MULTI);
-    }
-};
-__device__ __forceinline__ void q_push(uint32_t* count, uint16_t* q, int cap, uint32_t item, uint32_t* defer_mask, int owner) {
-    const uint32_t pos = atomicAdd(count, 1u);
-    if (pos < (uint32_t)cap) q[pos] = (uint16_t)item;
-    else atomicOr(defer_mask, 1u << owner);
-}
 
+#define WLEAD_OF(S) ((S) - 1)
 template <int NW, int Q, int S, int T>
 __global__ void __launch_bounds__(T, 1)
-dcb_exact_kernel_q(BatchDev b, QTables qt, DcrParams prm, int both_frames, dcb_result* __restrict__ results,
-                   unsigned long long* __restrict__ counters, uint32_t* __restrict__ queue,
-                   uint32_t* __restrict__ queue_count) {
+dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dcb_result* __restrict__ results,
+                      unsigned long long* __restrict__ counters, uint32_t* __restrict__ queue,
+                      uint32_t* __restrict__ queue_count) {
     constexpr int NPOS = (16 * NW - Q) / S + 1;
     static_assert(NPOS <= 32, "one hit word");
-    constexpr int WLEAD = DCB_IDX_WLEAD(S + Q - 1, Q);
-    static_assert(WLEAD == S, "the verification window starts one stride before the seed");
+    static_assert(S + Q - 1 <= 32 - WLEAD_OF(S), "the lmin-prefix at every candidate offset lies inside the window");
+    constexpr int WLEAD = S - 1;                                     // the verification window starts at the earliest possible tag start
     constexpr int WMAX = ((NPOS - 1) * S - WLEAD) >> 4;
     constexpr int TRAIL = WMAX + 3 - NW > 1 ? WMAX + 3 - NW : 1;    // zero rows behind the read columns
     constexpr int ROWS = 1 + NW + TRAIL;
     constexpr uint32_t FMUL = DCB_BLOOM_MUL(Q);
     constexpr int FBYTES = 1 << DCB_FBITS;
     extern __shared__ __align__(16) uint32_t smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // layout: [byte filter][read columns][per-warp scratch][V tags][J tags][index head][offset table][counters][mbarrier]
+    const int tid = threadIdx.x;
+    // layout: [byte filter][read columns][V tags][J tags][index head][offset table][counters][mbarrier]
     uint32_t* s_rd = smem + FBYTES / 4;
-    uint32_t* s_ws = s_rd + ROWS * T;
-    uint32_t* s_vcore = s_ws + (T / 32) * kQWarpWords;
+    uint32_t* s_vcore = s_rd + ROWS * T;
     uint32_t* s_jcore = s_vcore + qt.vcore_words;
     uint32_t* s_head = s_jcore + qt.jcore_words;
     uint32_t* s_qtab = s_head + qt.head_words;
@@ -476,7 +453,6 @@ dcb_exact_kernel_q(BatchDev b, QTables qt, DcrParams prm, int both_frames, dcb_r
 
     s_rd[tid] = 0u;
     for (int k = 0; k < TRAIL; k++) s_rd[(1 + NW + k) * T + tid] = 0u;
-    for (int i = tid; i < (T / 32) * kQWarpWords; i += T) s_ws[i] = 0u;
     tma_stage_begin(bar, (uint32_t)(FBYTES + 4 * (qt.vcore_words + qt.jcore_words + qt.head_words + qt.qtab_words)));
     tma_stage_copy(bar, smem, qt.bfilter, FBYTES);
     tma_stage_copy(bar, s_vcore, qt.vcore, 4u * qt.vcore_words);
@@ -492,22 +468,8 @@ dcb_exact_kernel_q(BatchDev b, QTables qt, DcrParams prm, int both_frames, dcb_r
     QIdxView ix = q_idx_view(s_head, s_qtab);
     ix.q = Q; ix.stride = S; ix.wlead = WLEAD; ix.lmin = S + Q - 1;       // geometry pinned to the template constants
     const uint32_t* col = s_rd + T + tid;                 // word k of this thread's read at col[k * T]
-    const uint32_t* wcol = s_rd + T + (tid - lane);       // ... of lane l of this warp at wcol[l + k * T]
-    uint32_t* slots = s_ws + warp * kQWarpWords;
-    uint16_t* qa = reinterpret_cast<uint16_t*>(slots + 64);
-    uint16_t* qb = qa + kQCapA;
-    uint32_t* qn = slots + 64 + kQCapA / 2 + kQCapB / 2;  // [0] queued hits, [1] queued candidates, [2] defer mask
     const uint32_t filt = smem_u32(smem);
     const uint32_t n_tiles = (b.n_reads + T - 1) / T;
-
-    // the 32 bases from (i - 1) * S of the read in column c (the seed of probe i sits WLEAD = S bases into the window)
-    auto window = [&](const uint32_t* c, int i, uint32_t& lo, uint32_t& hi) {
-        const int W = (i - 1) * S, sh = (W & 15) * 2;
-        const uint32_t* c0 = c + (W >> 4) * T;
-        const uint32_t x = c0[0], y = c0[T], z = c0[2 * T];
-        lo = __funnelshift_r(x, y, sh);
-        hi = __funnelshift_r(y, z, sh);
-    };
 
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t ri = b.first + tile * T + tid;
@@ -550,84 +512,34 @@ dcb_exact_kernel_q(BatchDev b, QTables qt, DcrParams prm, int both_frames, dcb_r
             if (nvalid < NPOS) h &= ~((1u << (NPOS - nvalid)) - 1u);
             if (!scan) h = 0;
         }
-        __syncwarp();                                                 // the warp's columns are written
+        // this lane's column is read back below by this lane only: program order suffices, no barrier
 
-        // 2. the owner confirms its first two hits
+        // 2. confirm, one (hit, offset) candidate per trip
         HitWords hw;
         hw.v = 0; hw.j = 0; hw.n_v = ix.n_v;
-#pragma unroll
-        for (int round = 0; round < 2; round++) {
-            if (h) {
+        uint32_t offs = 0, wlo = 0, whi = 0;
+        int p = 0;
+        for (;;) {
+            const bool need = offs == 0u && h != 0u;
+            if (!__any_sync(0xFFFFFFFFu, need || offs != 0u)) break;
+            if (need) {
                 const int bit = 31 - __clz(h);
                 h ^= 1u << bit;
-                const int i = NPOS - 1 - bit;
-                uint32_t wlo, whi;
-                window(col, i, wlo, whi);
-                uint32_t offs = q_offsets(ix, __funnelshift_r(wlo, whi, 2 * WLEAD));
-                if (offs) {
-                    const int o = 31 - __clz(offs);
-                    offs ^= 1u << o;
-                    q_check_offset<true>(r, ix, i * S, o, wlo, whi, hw);
-                    while (offs) {
-                        const int o2 = 31 - __clz(offs);
-                        offs ^= 1u << o2;
-                        q_push(qn + 1, qb, kQCapB, (uint32_t)lane | ((uint32_t)i << 5) | ((uint32_t)o2 << 10), qn + 2, lane);
-                    }
-                }
+                // bit position of the window start i * S - WLEAD, i = NPOS - 1 - bit, as ONE multiply-add
+                const int wb = 2 * (S * (NPOS - 1) - WLEAD) - 2 * S * bit;
+                p = (wb >> 1) + WLEAD;
+                const uint32_t* c0 = col + (wb >> 5) * T;
+                const uint32_t x = c0[0], y = c0[T], z = c0[2 * T];
+                wlo = __funnelshift_r(x, y, wb);                     // the shift wraps modulo 32
+                whi = __funnelshift_r(y, z, wb);
+                offs = q_offsets(ix, __funnelshift_r(wlo, whi, 2 * WLEAD));
             }
-        }
-        while (h) {
-            const int bit = 31 - __clz(h);
-            h ^= 1u << bit;
-            q_push(qn, qa, kQCapA, (uint32_t)lane | ((uint32_t)(NPOS - 1 - bit) << 5), qn + 2, lane);
-        }
-        __syncwarp();
-
-        // 3. the queues, 32 items per trip, any lane for any read of the warp
-        const uint32_t n_a = min(qn[0], (uint32_t)kQCapA);
-        if (n_a | qn[1]) {                                            // warp-uniform
-            for (uint32_t base = 0; base < n_a; base += 32) {         // whole-warp trips
-                const uint32_t t = base + lane;
-                if (t < n_a) {
-                    const uint32_t e = qa[t];
-                    const int owner = e & 31, i = e >> 5;
-                    uint32_t wlo, whi;
-                    window(wcol + owner, i, wlo, whi);
-                    uint32_t offs = q_offsets(ix, __funnelshift_r(wlo, whi, 2 * WLEAD));
-                    while (offs) {
-                        const int o = 31 - __clz(offs);
-                        offs ^= 1u << o;
-                        q_push(qn + 1, qb, kQCapB, (uint32_t)owner | ((uint32_t)i << 5) | ((uint32_t)o << 10), qn + 2, owner);
-                    }
-                }
+            if (offs) {
+                const int o = 31 - __clz(offs);
+                offs ^= 1u << o;
+                q_check_offset<true>(r, ix, p, o, wlo, whi, hw);
+                if (hw.v == DCB_HIT_MULTI) { h = 0u; offs = 0u; }    // final whatever else is found (decombine.py:278-280)
             }
-            __syncwarp();
-            const uint32_t n_b = min(qn[1], (uint32_t)kQCapB);
-            for (uint32_t base = 0; base < n_b; base += 32) {
-                const uint32_t t = base + lane;
-                const bool valid = t < n_b;
-                const uint32_t e = valid ? qb[t] : 0u;
-                const int owner = e & 31, i = (e >> 5) & 31, o = e >> 10;
-                const int n_owner = __shfl_sync(0xFFFFFFFFu, r.n, owner);
-                if (valid) {
-                    uint32_t wlo, whi;
-                    window(wcol + owner, i, wlo, whi);
-                    ReadView ro = r;
-                    ro.w = wcol + owner;
-                    ro.n = n_owner;
-                    SlotSink sink;
-                    sink.slots = slots; sink.owner = owner; sink.n_v = ix.n_v;
-                    q_check_offset<true>(ro, ix, i * S, o, wlo, whi, sink);
-                }
-            }
-            __syncwarp();
-            hw.v = hit_merge(hw.v, slots[2 * lane]);
-            hw.j = hit_merge(hw.j, slots[2 * lane + 1]);
-            const bool overflow = (qn[2] >> lane) & 1u;
-            __syncwarp();
-            slots[2 * lane] = 0u; slots[2 * lane + 1] = 0u;
-            if (lane < 3) qn[lane] = 0u;
-            if (overflow) hw.v = hw.j = 0u;                            // incomplete search: nothing found => deferred below
         }
         const FullHit vh = hit_decode(hw.v), jh = hit_decode(hw.j);
         if (scan) action = dcr_fast_from_hits<true>(r, vtags, jtags, vh, jh, prm, both_frames, out, s_cnt);
@@ -744,8 +656,8 @@ struct dcb_ctx {
     int qv = 0, sv = 0, qj = 0, sj = 0, lminv = 0, lminj = 0;
     int vhead = 0, jhead = 0, uhead = 0, vbloom = 0, jbloom = 0, ubloom = 0;   // head_words / bloom_off of the three indexes
     void* spec_fn = nullptr;   // specialised exact kernel picked for the resident batch, or null
-    void* q_fn = nullptr;      // queue kernel picked for the resident batch, or null (then spec_fn / the generic kernel run)
-    int ulegacy = 0, uqtab_off = 0, uqtab_words = 0, ubfilter_off = 0, ufbits = 0;
+    void* q_fn = nullptr;      // flat kernel picked for the resident batch, or null (then spec_fn / the generic kernel run)
+    int ulegacy = 0, uqtab_off = 0, uqtab_words = 0, ubfilter_off = 0, ufbits = 0, uqq = 0, uqs = 0, utqbits = 0;
     int vlegacy = 0, jlegacy = 0;
     bool spec_union = false;
 };
@@ -770,21 +682,21 @@ static exact_spec_fn pick_spec(int nw, int qv, int sv, int lminv, int qj, int sj
     }
 #undef DCB_SPEC
 }
-// Queue kernel: chains whose V and J tags share the (q=9, stride 12) geometry, read slots up to 24 words.
+// Flat kernel: chains whose V and J tags share one index with 20-nt minimum tags (13-mer seeds at stride 8), read slots
+// up to 16 words (its hit mask is one word).
 typedef void (*exact_q_fn)(BatchDev, QTables, DcrParams, int, dcb_result*, unsigned long long*, uint32_t*, uint32_t*);
 static constexpr int kQThreads = 1024;
-static exact_q_fn pick_q(int nw, int q, int s, int lmin) {
-    if (q != 9 || s != 12 || lmin != 20) return nullptr;
+static exact_q_fn pick_q(int nw, int qq, int qs, int lmin) {
+    if (qq != 13 || qs != 8 || lmin != 20) return nullptr;
     switch (nw) {
-        case 8:  return dcb_exact_kernel_q<8, 9, 12, kQThreads>;
-        case 12: return dcb_exact_kernel_q<12, 9, 12, kQThreads>;
-        case 16: return dcb_exact_kernel_q<16, 9, 12, kQThreads>;
-        case 20: return dcb_exact_kernel_q<20, 9, 12, kQThreads>;
+        case 8:  return dcb_exact_kernel_flat<8, 13, 8, kQThreads>;
+        case 12: return dcb_exact_kernel_flat<12, 13, 8, kQThreads>;
+        case 16: return dcb_exact_kernel_flat<16, 13, 8, kQThreads>;
         default: return nullptr;
     }
 }
 static int q_rows(int nw) {   // must match the kernel's ROWS
-    const int npos = (16 * nw - 9) / 12 + 1, wmax = ((npos - 1) * 12 - 12) >> 4;
+    const int npos = (16 * nw - 13) / 8 + 1, wmax = ((npos - 1) * 8 - 7) >> 4;
     const int trail = wmax + 3 - nw > 1 ? wmax + 3 - nw : 1;
     return 1 + nw + trail;
 }
@@ -877,6 +789,7 @@ dcb_ctx* dcb_ctx_create(int device, const dcb_tagset* v, const dcb_tagset* j, co
                 const DcbSeedIndex& iu = *reinterpret_cast<const DcbSeedIndex*>(u.data());
                 c->uhead = iu.head_words; c->ubloom = iu.bloom_off; c->ulegacy = iu.legacy_words;
                 c->uqtab_off = iu.qtab_off; c->uqtab_words = iu.qtab_words; c->ubfilter_off = iu.bfilter_off; c->ufbits = iu.fbits;
+                c->uqq = iu.qq; c->uqs = iu.qstride; c->utqbits = iu.tq_bits;
                 if (upload_blob(u, &c->d_uidx, &c->uidx_words)) return fail(nullptr);
             }
         }
@@ -941,10 +854,10 @@ static int prepare_batch(dcb_ctx* c, const dcb_packed* P) {
     c->spec_fn = (void*)spec; c->spec_union = have_union;
     int occ_e = 0, occ_g = 0;
     exact_q_fn qfn = nullptr;
-    if (have_union && c->params.force_general == 0 && c->ufbits == DCB_FBITS)
-        qfn = pick_q((int)sw, c->qv, c->sv, c->lminv);
+    if (have_union && c->params.force_general == 0 && c->ufbits == DCB_FBITS && c->utqbits > 0)
+        qfn = pick_q((int)sw, c->uqq, c->uqs, c->lminv);
     if (qfn) {
-        c->exact_smem = ((size_t)1 << DCB_FBITS) + ((size_t)q_rows((int)sw) * kQThreads + (size_t)(kQThreads / 32) * kQWarpWords +
+        c->exact_smem = ((size_t)1 << DCB_FBITS) + ((size_t)q_rows((int)sw) * kQThreads +
                          c->vcore_words + c->jcore_words + c->uhead + c->uqtab_words) * 4 + tail;
         if (c->exact_smem > kMaxSmem) qfn = nullptr;
     }
@@ -1168,7 +1081,7 @@ int dcb_timing_get(dcb_ctx* c, double ms[DCB_NTIMERS], uint64_t launches[DCB_NTI
 }
 const char* dcb_exact_kernel_name(const dcb_ctx* c) {
     if (!c || !c->have_batch) return "";
-    return c->q_fn ? "dcb_exact_kernel_q" : c->spec_fn ? "dcb_exact_kernel_spec" : "dcb_exact_kernel";
+    return c->q_fn ? "dcb_exact_kernel_flat" : c->spec_fn ? "dcb_exact_kernel_spec" : "dcb_exact_kernel";
 }
 int dcb_last_deferred(dcb_ctx* c, uint64_t* n) {
     if (!c || !n || !c->ran) return DCB_EINVAL;

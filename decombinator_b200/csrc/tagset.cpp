@@ -348,10 +348,21 @@ bool dcb_build_seed_index(const std::vector<std::string>* gene_v, const std::vec
         b.w[idx.bloom_off + DCB_BLOOM_WORD(kv.first, idx.bmul, wbits)] |= 1u << DCB_BLOOM_BIT(kv.first);
     b.align4();
     idx.legacy_words = (int32_t)b.w.size();
-    {   // queue kernel: q-mer -> offset set by hash-and-displace, and the byte filter
-        std::vector<std::pair<uint32_t, uint32_t>> items(seeds.begin(), seeds.end());
+    {   // flat kernel: qq-mer -> offset set by hash-and-displace, and the byte filter
+        idx.qq = DCB_QQ(lmin, idx.q);
+        idx.qstride = lmin - idx.qq + 1;
+        if (idx.qstride > 12) { idx.qq = idx.q; idx.qstride = idx.stride; }
+        std::map<uint32_t, uint32_t> seeds2;
+        for (size_t t = 0; t < all.size(); t++) {
+            uint32_t lo, hi;
+            for (int o = 0; o < idx.qstride; o++) {
+                if (!pack64(*all[t], o, idx.qq, lo, hi)) return false;
+                seeds2[lo] |= 1u << o;
+            }
+        }
+        std::vector<std::pair<uint32_t, uint32_t>> items(seeds2.begin(), seeds2.end());
         Chd chd;
-        if (!build_chd(chd, items, idx.q)) return false;
+        if (!build_chd(chd, items, idx.qq)) return false;
         idx.m1 = chd.m1; idx.m2 = chd.m2; idx.b1 = chd.b1; idx.b2 = chd.b2;
         const size_t n1 = (size_t)1 << chd.b1, n2 = (size_t)1 << chd.b2;
         idx.qtab_off = b.reserve((n1 + n2 + 1) / 2);
@@ -359,13 +370,51 @@ bool dcb_build_seed_index(const std::vector<std::string>* gene_v, const std::vec
         for (size_t i = 0; i < n1; i++) t16[i] = chd.disp[i];
         for (size_t i = 0; i < n2; i++) t16[n1 + i] = chd.slot[i];
         b.align4();
+        // tag slots: perfect hash over the lmin-prefixes straight to {prefix_lo, meta} records
+        idx.tq_off = 0; idx.tq_bits = 0; idx.ta = idx.tb = 1;
+        if (lmin >= 17 && lmin <= 23 && all.size() <= 255) {
+            const uint32_t himask = (1u << DCB_TQ_HIBITS(lmin)) - 1u;
+            uint64_t rng2 = 0xA0761D6478BD642Full;
+            bool done = false;
+            for (int bits = 8; bits <= 12 && !done; bits++) {
+                if (((size_t)1 << bits) < 4 * prefixes.size()) continue;
+                std::vector<int> slot((size_t)1 << bits);
+                for (int attempt = 0; attempt < 4000 && !done; attempt++) {
+                    rng2 ^= rng2 << 13; rng2 ^= rng2 >> 7; rng2 ^= rng2 << 17;
+                    const uint32_t ta = (uint32_t)rng2 | 1u, tb = (uint32_t)(rng2 >> 32) | 1u;
+                    std::fill(slot.begin(), slot.end(), -1);
+                    bool ok = true;
+                    for (auto& kv : prefixes) {
+                        int& sl = slot[(kv.first.first * ta + (kv.first.second & himask) * tb) >> (32 - bits)];
+                        if (sl >= 0) { ok = false; break; }
+                        sl = kv.second;
+                    }
+                    if (!ok) continue;
+                    idx.ta = ta; idx.tb = tb; idx.tq_bits = bits;
+                    idx.tq_off = b.reserve((size_t)2 << bits);
+                    for (size_t i = 0; i < slot.size(); i++) {
+                        uint32_t lo = 0, meta = DCB_TQ_FREE(lmin);
+                        if (slot[i] >= 0) {
+                            const std::string& t = *all[slot[i]];
+                            uint32_t hi;
+                            pack64(t, 0, lmin, lo, hi);
+                            meta = DCB_TQ_META(hi & himask, slot[i], t.size(), (int)t.size() > lmin || next_same[slot[i]] != 0x1FF);
+                        }
+                        b.w[idx.tq_off + 2 * i] = lo; b.w[idx.tq_off + 2 * i + 1] = meta;
+                    }
+                    done = true;
+                }
+            }
+        }
+        b.align4();
+        idx.qwlead = idx.qstride - 1;
         idx.qtab_words = (int32_t)b.w.size() - idx.qtab_off;
         idx.fbits = DCB_FBITS;
-        idx.fmul = DCB_BLOOM_MUL(idx.q);
-        if (idx.fbits > 2 * idx.q) idx.fbits = 2 * idx.q;
+        idx.fmul = DCB_BLOOM_MUL(idx.qq);
+        if (idx.fbits > 2 * idx.qq) idx.fbits = 2 * idx.qq;
         idx.bfilter_off = b.reserve(((size_t)1 << idx.fbits) / 4);
         uint8_t* f8 = reinterpret_cast<uint8_t*>(&b.w[idx.bfilter_off]);
-        for (auto& kv : seeds) f8[(kv.first * idx.fmul) >> (32 - idx.fbits)] = 1;
+        for (auto& kv : seeds2) f8[(kv.first * idx.fmul) >> (32 - idx.fbits)] = 1;
     }
     b.align4();
     idx.n_words = (int32_t)b.w.size();

@@ -145,7 +145,7 @@ typedef struct dcb_params {
     int32_t allow_ns;      /* inputargs["allowNs"]      (decombine.py:553-556) */
     int32_t lenthreshold;  /* inputargs["lenthreshold"] (decombine.py:557-560) */
     int32_t force_general; /* testing: 1 = send every read through the general (fallback) kernel;
-                              2 = exact-tag search without the queue kernel (the per-lane kernels only) */
+                              2 = exact-tag search without the flat kernel (the bit-filter kernels only) */
 } dcb_params;
 
 /* ---------------------------------------------------------------------------------------------
@@ -187,7 +187,7 @@ int dcb_timing_enable(dcb_ctx*, int on);
 int dcb_timing_get(dcb_ctx*, double ms[DCB_NTIMERS], uint64_t launches[DCB_NTIMERS]);
 /* Number of reads the last run sent to the general kernel. */
 int dcb_last_deferred(dcb_ctx*, uint64_t* n);
-/* Name of the exact-tag kernel chosen for the resident batch ("dcb_exact_kernel_q", "dcb_exact_kernel_spec" or
+/* Name of the exact-tag kernel chosen for the resident batch ("dcb_exact_kernel_flat", "dcb_exact_kernel_spec" or
    "dcb_exact_kernel"); a static string, "" before any batch. */
 const char* dcb_exact_kernel_name(const dcb_ctx*);
 
