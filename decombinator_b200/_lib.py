@@ -58,7 +58,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build()
+    path = os.environ.get("DCB_LIB") or _build.build()   # DCB_LIB: a tuning build of the same sources (tools/variants.sh)
     L = ctypes.CDLL(path)
     vp, i32, u64, u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint32
     cpp = ctypes.POINTER(ctypes.c_char_p)

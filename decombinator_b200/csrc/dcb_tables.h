@@ -110,13 +110,13 @@ struct DcbSeedIndex {
     int32_t bloom_off;           // the bit filter follows the head
     int32_t n_words;
     // --- tables of the flat kernel (dcb_exact_kernel_flat), stored behind the bit filter -------------------------------
-    //   * byte filter: ONE byte per slot (1 = an indexed q-mer hashes here), slot = (window * fmul) >> (32 - fbits).
-    //     A probe is IMAD, SHF, LDS.U8 and one IMAD that appends the byte to the hit mask: no bit extraction, and half
-    //     of the probe's instructions run on the FMA pipe instead of the (saturated) ALU pipe;
+    //   * byte filter: ONE byte per slot (1 = an indexed seed hashes here), slot = DCB_FSLOT(seed).  A probe is IMAD (hash),
+    //     LEA.HI (slot + the filter's fixed shared-memory address), LDS.U8 and one IMAD that appends the byte to the hit
+    //     mask: no bit extraction, half of the probe's instructions on the FMA pipe;
     //   * q-mer -> offset set, hash-and-displace (CHD): bucket = (x * m1) >> (32 - b1), slot = (((x * m2) >> (32 - b2))
     //     + disp[bucket]) & (2^b2 - 1); the 16-bit slot holds the set of tag offsets the q-mer occurs at (bit o).  No
     //     fingerprint: every candidate is compared with the read as a whole, a filter false positive just finds nothing.
-    //     m1, m2 and fmul are odd << (32 - 2q), so only the q-mer's own bits of a wider window reach the products.
+    //     m1 and m2 are odd << (32 - 2q), so only the q-mer's own bits of a wider window reach the products.
     //     The flat kernel's tables have their OWN seed geometry (qq, qstride): longer seeds sampled more densely
     //     (20-nt tags: 13-mers at every 8th position) hit fewer homologous tags, which is what its trip count pays for.
     int32_t legacy_words;        // words up to the end of the bit filter (what the other exact kernels stage)
@@ -142,11 +142,18 @@ struct DcbSeedIndex {
 #define DCB_TQ_MORE (1u << 24)
 #define DCB_TQ_META(prefix_hi, ctag, len, more) ((uint32_t)(prefix_hi) | ((uint32_t)(ctag) << 16) | ((more) ? DCB_TQ_MORE : 0u) | ((uint32_t)(len) << 25))
 #define DCB_TQ_LEN(meta) ((meta) >> 25)
+#if defined(__CUDA_ARCH__)
+#define DCB_TQ_CTAG(meta) __byte_perm((meta), 0u, 0x4442)           // byte 2, one PRMT
+#else
 #define DCB_TQ_CTAG(meta) (((meta) >> 16) & 0xFFu)
+#endif
 #define DCB_TQ_HIBITS(lmin) (2 * (lmin) - 32)                       // prefix bits held in the meta word
 #define DCB_TQ_CMPMASK(lmin) ((2u << DCB_TQ_HIBITS(lmin)) - 1u)     // those bits and the guard bit
 #define DCB_TQ_FREE(lmin) DCB_TQ_META(1u << DCB_TQ_HIBITS(lmin), 0xFF, 127, 0)
+#ifndef DCB_FBITS
 #define DCB_FBITS 16             // byte filter of the flat kernel: 64 KB
+#endif
+#define DCB_FSLOT(key, fmul, fbits) (((uint32_t)(key) * (fmul)) >> (32 - (fbits)))
 // seed length of the flat kernel's tables: stride 8 where the tags allow it (2 * qq <= 30 bits of key)
 #define DCB_QQ(lmin, q) (((lmin) >= 20 && (lmin) <= 22) ? (lmin) - 7 : (q))
 

@@ -666,14 +666,19 @@ DCB_HD void q_check_offset(const ReadView& r, const QIdxView& ix, int p, int o, 
 }
 // Collects occurrences into two hit words (V, J).
 struct HitWords {
-    uint32_t v, j;
+    uint32_t v, j;             // hit words over the combined tag numbering (J tags still carry + n_v)
     int n_v;
     DCB_HD void operator()(uint32_t ctag, int P) {
         const bool is_j = (int)ctag >= n_v;
-        const uint32_t c = DCB_HIT_ONE | ((is_j ? ctag - (uint32_t)n_v : ctag) << 16) | (uint32_t)P;
+        const uint32_t c = DCB_HIT_ONE | (ctag << 16) | (uint32_t)P;
         const uint32_t m = hit_merge(is_j ? j : v, c);
         v = is_j ? v : m;
         j = is_j ? m : j;
+    }
+    DCB_HD void decode(FullHit& vh, FullHit& jh) const {
+        vh = hit_decode(v);
+        jh = hit_decode(j);
+        jh.code -= (uint32_t)n_v << 16;          // meaningful only when jh.count == 1
     }
 };
 // The whole search for one read, serially (tests/sim and nothing else: the kernel spreads this work over a warp).
@@ -685,13 +690,13 @@ DCB_HD void q_find(const ReadView& r, const uint32_t* ib, FullHit& vh, FullHit& 
     hw.v = 0; hw.j = 0; hw.n_v = ix.n_v;
     for (int p = 0; p + ix.q <= r.n; p += ix.stride) {
         const uint32_t win = rd_win16(r, p);
-        if (!filt[(win * hd.fmul) >> (32 - hd.fbits)]) continue;
+        if (!filt[DCB_FSLOT(win, hd.fmul, hd.fbits)]) continue;
         uint32_t wlo, whi;
         rd_win32(r, p - ix.wlead, wlo, whi);
         for (uint32_t offs = q_offsets(ix, DCB_FUNNEL_R(wlo, whi, 2 * ix.wlead)); offs; offs &= offs - 1)
             q_check_offset<false>(r, ix, p, DCB_FFS(offs) - 1, wlo, whi, hw);
     }
-    vh = hit_decode(hw.v); jh = hit_decode(hw.j);
+    hw.decode(vh, jh);
 }
 
 // Outcome of the fast path for one read.

@@ -99,7 +99,16 @@ __device__ __forceinline__ uint32_t mad_copy(uint32_t i, uint32_t base) {
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
     uint4 r;
+#ifndef DCB_VAR_LDG
+#define DCB_VAR_LDG 1   // measured: L1-allocating loads 4 % faster than no_allocate (the four loads of a slot share two sectors)
+#endif
+#if DCB_VAR_LDG == 0
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+#elif DCB_VAR_LDG == 1
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+#else
+    asm volatile("ld.global.nc.L1::evict_first.v4.u32 {%0, %1, %2, %3}, [%4];"
+#endif
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
     return r;
@@ -419,6 +428,12 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
     asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+template <int OFF>
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
 __device__ __forceinline__ uint32_t mad2(uint32_t h, uint32_t bit) {   // 2 * h + bit on the FMA pipe
     uint32_t v;
     asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(v) : "r"(h), "r"(bit));
@@ -431,6 +446,7 @@ __global__ void __launch_bounds__(T, 1)
 dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dcb_result* __restrict__ results,
                       unsigned long long* __restrict__ counters, uint32_t* __restrict__ queue,
                       uint32_t* __restrict__ queue_count) {
+    static_assert(S == 8, "seeds start at half-word boundaries");
     constexpr int NPOS = (16 * NW - Q) / S + 1;
     static_assert(NPOS <= 32, "one hit word");
     static_assert(S + Q - 1 <= 32 - WLEAD_OF(S), "the lmin-prefix at every candidate offset lies inside the window");
@@ -438,12 +454,15 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
     constexpr int WMAX = ((NPOS - 1) * S - WLEAD) >> 4;
     constexpr int TRAIL = WMAX + 3 - NW > 1 ? WMAX + 3 - NW : 1;    // zero rows behind the read columns
     constexpr int ROWS = 1 + NW + TRAIL;
-    constexpr uint32_t FMUL = DCB_BLOOM_MUL(Q);
     constexpr int FBYTES = 1 << DCB_FBITS;
+    constexpr uint32_t FMUL = DCB_BLOOM_MUL(Q);
     extern __shared__ __align__(16) uint32_t smem[];
     const int tid = threadIdx.x;
-    // layout: [byte filter][read columns][V tags][J tags][index head][offset table][counters][mbarrier]
-    uint32_t* s_rd = smem + FBYTES / 4;
+    // layout: [byte filter][read columns][V tags][J tags][index head][offset table + tag slots][counters][mbarrier]
+    // (kept as small as it is: shared memory is carved out of the L1, and a 204 KB layout measured 20 % slower in the
+    // phases that touch global memory than this 160 KB one)
+    uint32_t* s_filt = smem;
+    uint32_t* s_rd = s_filt + FBYTES / 4;
     uint32_t* s_vcore = s_rd + ROWS * T;
     uint32_t* s_jcore = s_vcore + qt.vcore_words;
     uint32_t* s_head = s_jcore + qt.jcore_words;
@@ -454,7 +473,7 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
     s_rd[tid] = 0u;
     for (int k = 0; k < TRAIL; k++) s_rd[(1 + NW + k) * T + tid] = 0u;
     tma_stage_begin(bar, (uint32_t)(FBYTES + 4 * (qt.vcore_words + qt.jcore_words + qt.head_words + qt.qtab_words)));
-    tma_stage_copy(bar, smem, qt.bfilter, FBYTES);
+    tma_stage_copy(bar, s_filt, qt.bfilter, FBYTES);
     tma_stage_copy(bar, s_vcore, qt.vcore, 4u * qt.vcore_words);
     tma_stage_copy(bar, s_jcore, qt.jcore, 4u * qt.jcore_words);
     tma_stage_copy(bar, s_head, qt.head, 4u * qt.head_words);
@@ -468,7 +487,8 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
     QIdxView ix = q_idx_view(s_head, s_qtab);
     ix.q = Q; ix.stride = S; ix.wlead = WLEAD; ix.lmin = S + Q - 1;       // geometry pinned to the template constants
     const uint32_t* col = s_rd + T + tid;                 // word k of this thread's read at col[k * T]
-    const uint32_t filt = smem_u32(smem);
+    const uint32_t col_addr = smem_u32(col);
+    const uint32_t filt = smem_u32(s_filt);
     const uint32_t n_tiles = (b.n_reads + T - 1) / T;
 
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -496,23 +516,35 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
         r.nw = NW;
         r.exc_pos = nullptr; r.exc_kind = nullptr; r.e0 = r.e1 = 0; r.mirror = 0;
 
-        // 1. probe: bit NPOS-1-i of h <=> the q-mer at i * S may be indexed
+        // 1. probe: bit NPOS-1-i of h <=> the seed at i * S may be indexed.  The slot must hash the WHOLE seed: reads are
+        //    full of 8-mers that homologous genes share with a tag (measured: slot = the seed's first 8 bases costs 0.8
+        //    trips more than it saves in probe instructions).  Even probes are word-aligned (no extraction).
         uint32_t h = 0;
 #pragma unroll
         for (int i = 0; i < NPOS; i++) {
-            const int p = i * S, a = p >> 4, sh = (p & 15) * 2;
-            uint32_t win;   // at least the 2Q key bits of the q-mer at p (higher bits never reach the product)
-            if (sh == 0) win = w[a];
-            else if (sh + 2 * Q <= 32 || a + 1 >= NW) win = w[a] >> sh;
-            else win = __funnelshift_r(w[a], w[a + 1], sh);
+            const uint32_t win = (i & 1) ? __funnelshift_r(w[i >> 1], (i >> 1) + 1 < NW ? w[(i >> 1) + 1] : 0u, 16) : w[i >> 1];
             h = mad2(h, lds_u8(filt + ((win * FMUL) >> (32 - DCB_FBITS))));
         }
         {
-            const int nvalid = r.n >= Q ? (r.n - Q) / S + 1 : 0;     // probes whose q-mer lies inside the read
+            const int nvalid = r.n >= Q ? (r.n - Q) / S + 1 : 0;     // probes whose seed lies inside the read
             if (nvalid < NPOS) h &= ~((1u << (NPOS - nvalid)) - 1u);
             if (!scan) h = 0;
         }
         // this lane's column is read back below by this lane only: program order suffices, no barrier
+#ifdef DCB_VAR_PREFETCH
+        {   // the next tile's slot of this lane: in flight while this tile is confirmed and finished
+            const uint32_t nt = tile + gridDim.x;
+            if (nt < n_tiles) {
+                const uint32_t* nx = b.words + (size_t)min(b.first + nt * T + tid, b.first + b.n_reads - 1) * NW;
+#if DCB_VAR_PREFETCH == 1
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+                if (NW > 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + 32));
+#else
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+#endif
+            }
+        }
+#endif
 
         // 2. confirm, one (hit, offset) candidate per trip
         HitWords hw;
@@ -523,15 +555,15 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
             const bool need = offs == 0u && h != 0u;
             if (!__any_sync(0xFFFFFFFFu, need || offs != 0u)) break;
             if (need) {
-                const int bit = 31 - __clz(h);
+                const int bit = 31 - __clz(h);                       // probe i = NPOS - 1 - bit
                 h ^= 1u << bit;
-                // bit position of the window start i * S - WLEAD, i = NPOS - 1 - bit, as ONE multiply-add
+                // bit position of the window start i * S - WLEAD as ONE multiply-add; its word row is (i - 1) >> 1
                 const int wb = 2 * (S * (NPOS - 1) - WLEAD) - 2 * S * bit;
                 p = (wb >> 1) + WLEAD;
-                const uint32_t* c0 = col + (wb >> 5) * T;
-                const uint32_t x = c0[0], y = c0[T], z = c0[2 * T];
+                const uint32_t a0 = col_addr - (T * 4) + (uint32_t)(((NPOS - bit) >> 1) * (T * 4));
+                const uint32_t x = lds_u32<0>(a0), y = lds_u32<T * 4>(a0), zz = lds_u32<2 * T * 4>(a0);
                 wlo = __funnelshift_r(x, y, wb);                     // the shift wraps modulo 32
-                whi = __funnelshift_r(y, z, wb);
+                whi = __funnelshift_r(y, zz, wb);
                 offs = q_offsets(ix, __funnelshift_r(wlo, whi, 2 * WLEAD));
             }
             if (offs) {
@@ -541,7 +573,8 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
                 if (hw.v == DCB_HIT_MULTI) { h = 0u; offs = 0u; }    // final whatever else is found (decombine.py:278-280)
             }
         }
-        const FullHit vh = hit_decode(hw.v), jh = hit_decode(hw.j);
+        FullHit vh, jh;
+        hw.decode(vh, jh);
         if (scan) action = dcr_fast_from_hits<true>(r, vtags, jtags, vh, jh, prm, both_frames, out, s_cnt);
         else if (live) action = FAST_DEFER;
         defer_reads(live && action == FAST_DEFER, ri, queue, queue_count);

@@ -414,7 +414,7 @@ bool dcb_build_seed_index(const std::vector<std::string>* gene_v, const std::vec
         if (idx.fbits > 2 * idx.qq) idx.fbits = 2 * idx.qq;
         idx.bfilter_off = b.reserve(((size_t)1 << idx.fbits) / 4);
         uint8_t* f8 = reinterpret_cast<uint8_t*>(&b.w[idx.bfilter_off]);
-        for (auto& kv : seeds2) f8[(kv.first * idx.fmul) >> (32 - idx.fbits)] = 1;
+        for (auto& kv : seeds2) f8[DCB_FSLOT(kv.first, idx.fmul, idx.fbits)] = 1;
     }
     b.align4();
     idx.n_words = (int32_t)b.w.size();
