@@ -33,6 +33,10 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 
 import numpy as np  # noqa: E402
 
+# stdout carries ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION in some images) off it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 METRIC = "decombined_reads_per_sec"
 UNIT = "reads/s"
 READ_LEN = 250
