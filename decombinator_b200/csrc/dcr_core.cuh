@@ -768,7 +768,7 @@ DCB_HD int dcr_exact_read(const ReadView& r, bool flagged, const uint32_t* vcore
     FullHit vh, jh;
     vh.count = 0; vh.code = 0;
     jh.count = 0; jh.code = 0;
-    if (use_q) {          // the queue kernel's tables (union index only)
+    if (use_q) {          // the flat kernel's tables (union index only)
         q_find(r, vidx, vh, jh);
     } else if (!jidx) {
         fast_find(r, vidx, vh, jh, true);

@@ -428,6 +428,21 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
     asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int bfind_u32(uint32_t x) {               // index of the highest set bit, as FLO delivers it
+    int v;
+    asm("bfind.u32 %0, %1;" : "=r"(v) : "r"(x));
+    return v;
+}
 template <int OFF>
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t v;
@@ -599,6 +614,54 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
                         q_check_offset<true>(r, ix, p, o, wlo, whi, hw);   // whole-tag compare / chain walk
                     }
                     if (hw.v == DCB_HIT_MULTI) { h = 0u; offs = 0u; noffs = 0u; }
+                }
+            }
+        }
+#elif defined(DCB_VAR_TRIM)
+        // hand-trimmed form of the loop below: FLO results used as they come (bfind), separate table bases, the
+        // prefix compare folded into two logic ops, the hit words updated by predicated moves inside the match branch
+        uint32_t offs = 0, wlo = 0, whi = 0;
+        int p = 0;
+        const uint32_t disp_addr = smem_u32(ix.disp), offs_addr = smem_u32(ix.offs), tq_addr = smem_u32(ix.tq);
+        for (;;) {
+            const bool need = offs == 0u && h != 0u;
+            if (!__any_sync(0xFFFFFFFFu, need || offs != 0u)) break;
+            if (need) {
+                const int bit = bfind_u32(h);                        // probe i = NPOS - 1 - bit
+                h ^= 1u << bit;
+                const int wb = 2 * (S * (NPOS - 1) - WLEAD) - 2 * S * bit;
+                p = (S * (NPOS - 1)) - S * bit;
+                const uint32_t a0 = col_addr - (T * 4) + (uint32_t)(((NPOS - bit) >> 1) * (T * 4));
+                const uint32_t x = lds_u32<0>(a0), y = lds_u32<T * 4>(a0), zz = lds_u32<2 * T * 4>(a0);
+                wlo = __funnelshift_r(x, y, wb);                     // the shift wraps modulo 32
+                whi = __funnelshift_r(y, zz, wb);
+                const uint32_t key = __funnelshift_r(wlo, whi, 2 * WLEAD);
+                const uint32_t d = lds_u16(disp_addr + 2u * ((key * ix.m1) >> ix.s1));
+                offs = lds_u16(offs_addr + 2u * ((((key * ix.m2) >> ix.s2) + d) & ix.mask2));
+            }
+            if (offs) {
+                const int o = bfind_u32(offs);
+                offs ^= 1u << o;
+                const int P = p - o;
+                const int sh = 2 * WLEAD - 2 * o;
+                const uint32_t lo = __funnelshift_r(wlo, whi, sh), hi = whi >> sh;
+                const uint32_t hp = hi & ((1u << DCB_TQ_HIBITS(S + Q - 1)) - 1u);
+                const uint2 e = lds_u64(tq_addr + 8u * ((lo * ix.ta + hp * ix.tb) >> ix.tqshift));
+                if (((((hp ^ e.y) & DCB_TQ_CMPMASK(S + Q - 1)) | (lo ^ e.x)) == 0u) && P >= 0) {
+                    if (!(e.y & DCB_TQ_MORE)) {
+                        if (P + (int)DCB_TQ_LEN(e.y) <= r.n) {
+                            const uint32_t ctag = DCB_TQ_CTAG(e.y);
+                            const uint32_t c = ctag * 65536u + ((uint32_t)P + DCB_HIT_ONE);
+                            if ((int)ctag >= ix.n_v) hw.j = hit_merge(hw.j, c);
+                            else {
+                                hw.v = hit_merge(hw.v, c);
+                                if (hw.v == DCB_HIT_MULTI) { h = 0u; offs = 0u; }   // final (decombine.py:278-280)
+                            }
+                        }
+                    } else {
+                        q_check_offset<true>(r, ix, p, o, wlo, whi, hw);   // whole-tag compare / chain walk
+                        if (hw.v == DCB_HIT_MULTI) { h = 0u; offs = 0u; }
+                    }
                 }
             }
         }

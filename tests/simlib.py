@@ -30,7 +30,7 @@ def sim_decombine(packed, vt, jt, both_frames=False, allow_ns=False, lenthreshol
     """-> (results, counters, n_deferred) using dcr_exact_read/dcr_general_read on the host.
 
     use_union: None = what dcb_ctx_create does (union index when V and J share the seed geometry).
-    use_q: search through the queue kernel's tables (byte filter + offset table of the union index)."""
+    use_q: search through the flat kernel's tables (byte filter + offset table of the union index)."""
     global _sim
     if _sim is None:
         _sim = ctypes.CDLL(_build())

@@ -18,7 +18,7 @@ def test_sim_matches_reference_fixtures(dcr_cases, general_only, use_union, use_
         info = tags.load(g["species"], g["tags"], g["chain"])
         vt, jt = info.tables()
         if use_q and _lib.union_index(vt, jt) is None:
-            continue   # the queue kernel's tables exist for chains whose V and J tags share the seed geometry
+            continue   # the flat kernel's tables exist for chains whose V and J tags share the seed geometry
         packed = _lib.pack_strings(g["reads"], revcomp=(g["orientation"] != "forward"))
         res, cnt, _ = simlib.sim_decombine(packed, vt, jt, both_frames=(g["orientation"] == "both"), allow_ns=g["allowNs"],
                                            lenthreshold=g["lenthreshold"], general_only=general_only, use_union=use_union,
@@ -51,7 +51,46 @@ def test_sim_matches_oracle_on_synthetic(species, tagset, chain, orientation, L,
     assert np.array_equal(cnt, orc.counts)
     if sub == 0.0:
         assert deferred < 0.1 * n  # the exact-tag path must carry clean data on its own
-    if _lib.union_index(vt, jt) is not None:   # the queue kernel's tables find exactly the same tags
+    if _lib.union_index(vt, jt) is not None:   # the flat kernel's tables find exactly the same tags
         res_q, cnt_q, deferred_q = simlib.sim_decombine(packed, vt, jt, both_frames=(orientation == "both"), use_q=True)
         assert np.array_equal(res_q, res) and np.array_equal(cnt_q, cnt) and deferred_q == deferred
+    packed.free()
+
+
+def sweep_reads(info, L, seed=5):
+    """Every tag of the chain at every start position modulo the seed stride and at both read ends: one V tag and one
+    J tag per read (in the oriented frame), random bases elsewhere.  Exercises every sampling phase of the seed index,
+    tags cut off by the read ends, and windows that reach into the padding around a packed read."""
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    reads = []
+    vs, js = list(info.v_seqs), list(info.j_seqs)
+    for k, vtag in enumerate(vs):
+        for pv in list(range(0, 17)) + [L // 2 - 40 + d for d in range(9)]:
+            jtag = js[(k + pv) % len(js)]
+            for pj in (pv + len(vtag) + 30 + (pv % 9), L - len(jtag) - (pv % 4), L - len(jtag) + 1 + (pv % 3)):
+                body = bytearray(acgt[rng.integers(0, 4, L)].tobytes())
+                body[pv:pv + len(vtag)] = vtag.encode()
+                if pj + len(jtag) <= L:
+                    body[pj:pj + len(jtag)] = jtag.encode()
+                else:                                  # J tag cut off by the read end
+                    body[pj:L] = jtag.encode()[:L - pj]
+                reads.append(bytes(body[:L]).translate(comp)[::-1].decode())   # stored as the reverse complement
+    return reads
+
+
+@pytest.mark.parametrize("tagset,chain,L", [("extended", "b", 250), ("extended", "a", 150), ("original", "a", 128)])
+def test_sim_tag_position_sweep(tagset, chain, L):
+    info = tags.load("human", tagset, chain)
+    vt, jt = info.tables()
+    reads = sweep_reads(info, L)
+    orc = O.Oracle(O.TagSet("human", tagset, chain))
+    want = orc.decombine_reads(reads, "reverse")
+    assert want["ok"].sum() > 0.3 * len(reads)
+    packed = _lib.pack_strings(reads, revcomp=True)
+    for use_q in (False, True):
+        res, cnt, _ = simlib.sim_decombine(packed, vt, jt, use_q=use_q)
+        assert_records_equal(res, want, "reverse", "sweep use_q=%s" % use_q)
+        assert np.array_equal(cnt, orc.counts)
     packed.free()

@@ -21,8 +21,8 @@ def _ctx(info, **kw):
     return _lib.Context(vt, jt, device=0, **kw)
 
 
-# force_general: 0 = the shipped path (queue kernel where the chain has one seed geometry, else the per-lane exact
-# kernels), 1 = general kernel only, 2 = per-lane exact kernels only
+# force_general: 0 = the shipped path (flat kernel where the chain has one seed geometry, else the bit-filter exact
+# kernels), 1 = general kernel only, 2 = bit-filter exact kernels only
 @pytest.mark.parametrize("force_general", [0, 1, 2])
 def test_cuda_matches_reference_fixtures(dcr_cases, force_general):
     names = dcr_cases["counters"]
@@ -124,9 +124,10 @@ def _revcomp(s):
 
 
 @pytest.mark.parametrize("L", [128, 250, 320])
-def test_tag_dense_reads_overflow_the_warp_queues(L):
-    """Reads made of back-to-back tags give every lane of a warp ~10 seed hits: far more than the per-warp queues of
-    the queue kernel hold.  Overflowing reads must be handed to the general kernel, results unchanged."""
+def test_tag_dense_reads(L):
+    """Reads made of back-to-back tags give every lane of a warp ~10 seed hits (and every hit word its 'several
+    occurrences' state): the confirmation loop of the exact-tag kernels must find them all, results unchanged.
+    L = 320 does not fit the flat kernel's one-word hit mask and runs the bit-filter kernel."""
     info = tags.load("human", "extended", "b")
     rng = np.random.default_rng(7)
     vs, js = list(info.v_seqs), list(info.j_seqs)
@@ -194,3 +195,23 @@ def test_full_size_properties_config2():
     assert_records_equal(res[lo:lo + w], want, "reverse", "window")
     assert ok + filt <= n
     ctx.close(); packed.free()
+
+
+@pytest.mark.parametrize("tagset,chain,L", [("extended", "b", 250), ("extended", "a", 150), ("original", "a", 128),
+                                            ("original", "b", 250)])
+def test_tag_position_sweep(tagset, chain, L):
+    """Every tag at every start position modulo the seed stride and at both read ends (see sweep_reads), through every
+    exact-tag kernel and the general kernel."""
+    from test_device_logic_sim import sweep_reads
+    info = tags.load("human", tagset, chain)
+    reads = sweep_reads(info, L)
+    orc = O.Oracle(O.TagSet("human", tagset, chain))
+    want = orc.decombine_reads(reads, "reverse")
+    packed = _lib.pack_strings(reads, revcomp=True)
+    for fg in (0, 1, 2):
+        ctx = _ctx(info, force_general=fg)
+        res, cnt = ctx.decombine(packed)
+        assert_records_equal(res, want, "reverse", "sweep fg=%s" % fg)
+        assert np.array_equal(cnt, orc.counts)
+        ctx.close()
+    packed.free()

@@ -3,8 +3,8 @@
 # usage: tools/gpu_cycle.sh [noprof] [quick]   quick = only the parity tests that exercise the exact kernels
 mkdir -p gpurun_out
 SEL=""
-if [[ "$*" == *quick* ]]; then SEL="-k fixtures or synthetic or ragged or dense"; fi
-timeout 1200 python -m pytest tests -m gpu -x -q ${SEL:+-k "fixtures or synthetic or ragged or dense"} > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log
+if [[ "$*" == *quick* ]]; then SEL="quick"; fi
+timeout 1200 python -m pytest tests -m gpu -x -q ${SEL:+-k "fixtures or synthetic or ragged or dense or sweep"} > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log
 timeout 400 python bench.py > gpurun_out/bench1.json 2> gpurun_out/bench1.err; cat gpurun_out/bench1.json; tail -3 gpurun_out/bench1.err
 if [[ "$*" != *noprof* ]]; then
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --reads 4000000 --no-cpu-baseline > gpurun_out/b_ncu.log 2>&1
