@@ -53,12 +53,14 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sub-rate", type=float, default=0.0, help="per-base substitution rate of the synthetic reads (default: the headline workload, 0)")
+    ap.add_argument("--n-rate", type=float, default=0.0, help="per-base N rate")
     return ap.parse_args()
 
 
-def make_reads(info, first, n, threads):
+def make_reads(info, first, n, threads, sub_rate=0.0, n_rate=0.0):
     from decombinator_b200 import _lib
-    syn = _lib.Synth([(info.v_regions, info.j_regions)], SEED, READ_LEN, 0, 0.0, 0.0, 0.0)
+    syn = _lib.Synth([(info.v_regions, info.j_regions)], SEED, READ_LEN, 0, sub_rate, n_rate, 0.0)
     r1, _ = syn.reads(first, n, n_threads=threads)
     off = np.arange(n, dtype=np.uint64) * READ_LEN
     ln = np.full(n, READ_LEN, dtype=np.uint32)
@@ -142,13 +144,15 @@ def main():
               "spin_up": "0.5 s of untimed passes before the W warm-up steps (clock ramp)",
               "sharding": "contiguous read-index shards, one per GPU, no collective"}
 
+    if args.sub_rate or args.n_rate:
+        config["workload"] += " + %.3g substitutions, %.3g N per base (NOT the headline workload)" % (args.sub_rate, args.n_rate)
     # ---------------------------------------------------------------------------------------------
     if args.impl == "reference":
         if rank != 0:
             return
         threads = os.cpu_count() or 1
         n = min(args.reads, 4_000_000)
-        r1, off, ln = make_reads(info, 0, n, threads)
+        r1, off, ln = make_reads(info, 0, n, threads, args.sub_rate, args.n_rate)
         rps, sec, _ = cpu_reference_run(r1, off, ln, threads, steps=max(1, args.steps), warmup=min(1, args.warmup))
         line = {"impl": "reference", "metric": METRIC, "value": rps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -175,7 +179,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     n = args.reads
-    r1, off, ln = make_reads(info, rank * n, n, host_threads)
+    r1, off, ln = make_reads(info, rank * n, n, host_threads, args.sub_rate, args.n_rate)
     packed = _lib.pack_arrays(r1, off, ln, revcomp=True, n_threads=host_threads)
     vt, jt = info.tables()
     ctx = _lib.Context(vt, jt, device=local_rank)

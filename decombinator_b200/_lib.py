@@ -73,6 +73,7 @@ def lib():
     L.dcb_tagset_table_bytes.argtypes = [vp]
     L.dcb_tagset_blob.argtypes = [vp, i32, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint32)), ctypes.POINTER(ctypes.c_size_t)]
     L.dcb_tagset_union_index.argtypes = [vp, vp, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+    L.dcb_tagset_suffix_filter.argtypes = [vp, vp, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
     L.dcb_pack_reads.argtypes = [vp, vp, vp, u64, i32, i32, ctypes.POINTER(ctypes.POINTER(CPacked))]
     L.dcb_packed_free.argtypes = [ctypes.POINTER(CPacked)]
     L.dcb_unpack_read.argtypes = [ctypes.POINTER(CPacked), u64, ctypes.c_char_p, u32]
@@ -164,6 +165,15 @@ def union_index(vt: "TagTables", jt: "TagTables"):
         return None
     out = np.zeros(n.value, dtype=np.uint32)
     _check(lib().dcb_tagset_union_index(vt.handle, jt.handle, out.ctypes.data, n.value, ctypes.byref(n)), "dcb_tagset_union_index")
+    return out
+
+
+def suffix_filter(vt: "TagTables", jt: "TagTables"):
+    """Union suffix filter of the chain's six keyword sets (what the general kernel marks candidate positions with)."""
+    n = ctypes.c_size_t()
+    _check(lib().dcb_tagset_suffix_filter(vt.handle, jt.handle, None, 0, ctypes.byref(n)), "dcb_tagset_suffix_filter")
+    out = np.zeros(n.value, dtype=np.uint32)
+    _check(lib().dcb_tagset_suffix_filter(vt.handle, jt.handle, out.ctypes.data, n.value, ctypes.byref(n)), "dcb_tagset_suffix_filter")
     return out
 
 

@@ -191,6 +191,19 @@ struct alignas(16) DcbUTag {
 #define DCB_BLOOM_BIT(key) (31u - ((key) & 31u))
 #define DCB_BLOOM_WORD(win, bmul, wbits) (((uint32_t)(win) * (bmul)) >> (32 - (wbits)))
 
+// Union suffix filter of the general kernel: one bit per slot over the last `kq` bases of EVERY keyword of the six
+// keyword sets of a chain (full tags, first halves, second halves of both genes), kq = the shortest keyword.  A keyword
+// can only end where the kq-mer in front of that position is in the filter, so the general kernel marks those
+// positions once per read (one probe per base) and its six findall scans then visit only the marked ones.
+// slot = DCB_SFSLOT(kq-mer); fmul = odd << (32 - 2 kq) (or 1 << (32 - 2 kq) when 2 kq <= fbits: the kq-mer itself).
+struct DcbSuffixFilter {
+    int32_t kq, fbits;
+    uint32_t fmul;
+    int32_t n_words;             // header + 2^fbits / 32 filter words
+};
+#define DCB_SFILTER_HEAD 4       // words in front of the bits
+#define DCB_SFSLOT(key, fmul, fbits) (((uint32_t)(key) * (fmul)) >> (32 - (fbits)))
+
 #if defined(__CUDACC__)
 #define DCB_HD __host__ __device__ __forceinline__
 #else

@@ -59,6 +59,10 @@ struct ReadView {
     const uint8_t* exc_kind;
     int e0, e1;
     int mirror;             // frame 1: position p of the frame is exception position n-1-p
+    // candidate keyword positions (general kernel): bit b of word i <-> the cand_kq-mer that STARTS at base 32 i + b may
+    // be the tail of a keyword (union suffix filter); same stride; null = not marked, scans visit every position
+    const uint32_t* cand;
+    int cand_kq;
 };
 
 DCB_HD uint32_t rd_word(const ReadView& r, int i) {
@@ -125,6 +129,50 @@ DCB_HD bool rd_hamming_le1(const ReadView& r, int s, int L, uint32_t klo, uint32
         d += (rd_inv_at(r, s + i) || nq) ? 1 : 0;
     }
     return d <= 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Candidate keyword positions: one probe of the union suffix filter (DcbSuffixFilter) per base of the read, 32 start
+// positions per output word.  Non-ACGT symbols are packed as base 0 and probed as such: a keyword needs valid bases, so
+// marking by the packed bits can only mark too much, never too little.  cand_col: this read's words, stride r.stride.
+// ------------------------------------------------------------------------------------------------
+DCB_HD void cand_build(ReadView& r, const uint32_t* sf, uint32_t* cand_col) {
+    const DcbSuffixFilter& h = *reinterpret_cast<const DcbSuffixFilter*>(sf);
+    const uint32_t* bits = sf + DCB_SFILTER_HEAD;
+    const uint32_t kmask = h.kq >= 16 ? 0xFFFFFFFFu : ((1u << (2 * h.kq)) - 1u);
+    const int sh = 32 - h.fbits;
+    const int nout = (r.nw + 1) / 2;
+    for (int m = 0; m < nout; m++) {
+        uint32_t acc = 0;
+        for (int half = 0; half < 2; half++) {
+            const int wi = 2 * m + half;
+            const uint32_t a = rd_word(r, wi), b = rd_word(r, wi + 1);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int j = 0; j < 16; j++) {
+                const uint32_t key = DCB_FUNNEL_R(a, b, 2 * j) & kmask;
+                const uint32_t sl = (key * h.fmul) >> sh;
+                acc |= ((bits[sl >> 5] >> (sl & 31)) & 1u) << (16 * half + j);
+            }
+        }
+        cand_col[m * r.stride] = acc;
+    }
+    r.cand = cand_col;
+    r.cand_kq = h.kq;
+}
+// Smallest marked start position >= p, or a value >= 32 * words when there is none.
+DCB_HD int cand_next(const ReadView& r, int p) {
+    const int nout = (r.nw + 1) / 2;
+    if (p < 0) p = 0;
+    int m = p >> 5;
+    if (m >= nout) return 32 * nout;
+    uint32_t wv = r.cand[m * r.stride] & (0xFFFFFFFFu << (p & 31));
+    while (!wv) {
+        if (++m >= nout) return 32 * nout;
+        wv = r.cand[m * r.stride];
+    }
+    return 32 * m + DCB_FFS(wv) - 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -229,6 +277,10 @@ DCB_HD bool kw_scan_next(const ReadView& r, const uint32_t* blob, const DcbKwSet
             if (rd_equals(r, st, k.len, k.bits_lo, k.bits_hi)) { kw = c; start = st; return true; }
         }
         s.e++;
+        if (r.cand) {   // skip to the next end position whose cand_kq-mer tail is in the union suffix filter
+            const int pmin = s.e - r.cand_kq;
+            s.e = cand_next(r, pmin) + r.cand_kq;
+        }
         if (s.e > r.n) return false;
         uint32_t key = rd_win16(r, s.e - ks.kq) & kmask;
         if (!((blob[ks.bitmap_off + (key >> 5)] >> (key & 31)) & 1u)) continue;
@@ -781,11 +833,16 @@ DCB_HD int dcr_exact_read(const ReadView& r, bool flagged, const uint32_t* vcore
 
 // General kernel body for one read: r has w/stride/n/nw set; inv0, rd1, inv1 are this thread's scratch
 // columns (same stride as r): inv0/inv1 hold (nw+1)/2 words, rd1 holds nw words (only used with both_frames).
+// sf / cand0: the chain's union suffix filter and (nw+1)/2 scratch words for the candidate positions, or null (every
+// position is scanned).
 DCB_HD void dcr_general_read(ReadView r, uint32_t ri, bool flagged, const ExcList& ex, uint32_t* inv0, uint32_t* rd1,
                              uint32_t* inv1, const uint32_t* vblob, const uint32_t* jblob, const DcrParams& prm,
-                             int both_frames, dcb_result& out, dcb_cnt_t* C) {
+                             int both_frames, dcb_result& out, dcb_cnt_t* C, const uint32_t* sf = nullptr,
+                             uint32_t* cand0 = nullptr) {
     const int nwi = (r.nw + 1) / 2;
     r.inv = nullptr; r.exc_pos = ex.pos; r.exc_kind = ex.kind; r.e0 = r.e1 = 0; r.mirror = 0;
+    r.cand = nullptr; r.cand_kq = 0;
+    if (sf && cand0) cand_build(r, sf, cand0);
     if (flagged) {
         uint32_t e0 = exc_lower_bound(ex, ri), e1 = e0;
         while (e1 < ex.n && ex.read[e1] == ri) e1++;
@@ -805,6 +862,7 @@ DCB_HD void dcr_general_read(ReadView r, uint32_t ri, bool flagged, const ExcLis
         for (int k = 0; k < r.nw; k++) rd1[k * r.stride] = revcomp_word(r, k);
         ReadView r1 = r;
         r1.w = rd1; r1.inv = nullptr; r1.mirror = 1;
+        if (sf && cand0) cand_build(r1, sf, cand0);          // the first frame is done with its marks
         if (r.e1 > r.e0) {
             for (int k = 0; k < nwi; k++) inv1[k * r.stride] = 0;
             for (int e = r.e0; e < r.e1; e++) {

@@ -217,7 +217,7 @@ dcb_exact_kernel(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_res
             r.w = s_rd + tid; r.inv = nullptr; r.stride = T;
             r.n = b.uniform_len ? (int)b.uniform_len : (int)__ldg(b.lens + ri);
             r.nw = (int)b.slot_words;
-            r.exc_pos = nullptr; r.exc_kind = nullptr; r.e0 = r.e1 = 0; r.mirror = 0;
+            r.exc_pos = nullptr; r.exc_kind = nullptr; r.e0 = r.e1 = 0; r.mirror = 0; r.cand = nullptr; r.cand_kq = 0;
             action = dcr_exact_read(r, flagged, L.t[0], L.t[1], L.t[2], L.t[3], prm, both_frames, out, L.cnt);
         }
         defer_reads(live && action == FAST_DEFER, ri, queue, queue_count);
@@ -381,7 +381,7 @@ dcb_exact_kernel_spec(BatchDev b, Tables4 tb, SpecBlooms bl, DcrParams prm, int 
         r.w = col; r.inv = nullptr; r.stride = T;
         r.n = b.uniform_len ? (int)b.uniform_len : (live ? (int)__ldg(b.lens + ri) : 0);
         r.nw = NW;
-        r.exc_pos = nullptr; r.exc_kind = nullptr; r.e0 = r.e1 = 0; r.mirror = 0;
+        r.exc_pos = nullptr; r.exc_kind = nullptr; r.e0 = r.e1 = 0; r.mirror = 0; r.cand = nullptr; r.cand_kq = 0;
         FullHit vh, jh;
         vh.count = 0; vh.code = 0;
         jh.count = 0; jh.code = 0;
@@ -529,7 +529,7 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
         r.w = col; r.inv = nullptr; r.stride = T;
         r.n = b.uniform_len ? (int)b.uniform_len : (live ? (int)__ldg(b.lens + ri) : 0);
         r.nw = NW;
-        r.exc_pos = nullptr; r.exc_kind = nullptr; r.e0 = r.e1 = 0; r.mirror = 0;
+        r.exc_pos = nullptr; r.exc_kind = nullptr; r.e0 = r.e1 = 0; r.mirror = 0; r.cand = nullptr; r.cand_kq = 0;
 
         // 1. probe: bit NPOS-1-i of h <=> the seed at i * S may be indexed.  The slot must hash the WHOLE seed: reads are
         //    full of 8-mers that homologous genes share with a tag (measured: slot = the seed's first 8 bases costs 0.8
@@ -711,14 +711,16 @@ dcb_general_kernel(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_r
     extern __shared__ __align__(16) uint32_t smem[];
     const int T = blockDim.x;
     const int nw = (int)b.slot_words, nwi = (nw + 1) / 2;
-    SmemLayout L = carve(smem, tb, (size_t)(nw + nwi) * T * (both_frames ? 2 : 1));
+    SmemLayout L = carve(smem, tb, (size_t)(nw + nwi) * T * (both_frames ? 2 : 1) + (size_t)nwi * T);
     uint32_t* s_rd = L.cols;                      // [nw][T]
     uint32_t* s_inv = s_rd + (size_t)nw * T;      // [nwi][T]
-    uint32_t* s_rd1 = s_inv + (size_t)nwi * T;    // second frame (only when both_frames)
+    uint32_t* s_cand = s_inv + (size_t)nwi * T;   // [nwi][T] candidate keyword positions
+    uint32_t* s_rd1 = s_cand + (size_t)nwi * T;   // second frame (only when both_frames)
     uint32_t* s_inv1 = s_rd1 + (size_t)nw * T;
     stage_tables(L, tb);
     const uint32_t* vblob = L.t[0];
     const uint32_t* jblob = L.t[1];
+    const uint32_t* sfilt = tb.words[2] ? L.t[2] : nullptr;      // union suffix filter
 
     const int tid = threadIdx.x;
     const uint32_t n_items = queue ? *queue_count : b.n_reads;
@@ -745,7 +747,7 @@ dcb_general_kernel(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_r
         dcb_result out;
         *reinterpret_cast<uint4*>(&out) = make_uint4(0, 0, 0, 0);
         dcr_general_read(r, ri, flagged, ex, s_inv + tid, s_rd1 + tid, s_inv1 + tid, vblob, jblob, prm, both_frames, out,
-                         L.cnt);
+                         L.cnt, sfilt, s_cand + tid);
         store_result(results + ri, out);
     }
     flush_counters(L.cnt, counters);
@@ -790,6 +792,8 @@ struct dcb_ctx {
     // device copies of the table blobs: general (V, J), tag records (V, J), seed indexes (V, J, union of both)
     uint32_t *d_vgen = nullptr, *d_jgen = nullptr, *d_vcore = nullptr, *d_jcore = nullptr;
     uint32_t *d_vidx = nullptr, *d_jidx = nullptr, *d_uidx = nullptr;
+    uint32_t* d_sfilt = nullptr;   // union suffix filter of the general kernel
+    int sfilt_words = 0;
     int vgen_words = 0, jgen_words = 0, vcore_words = 0, jcore_words = 0, vidx_words = 0, jidx_words = 0, uidx_words = 0;
     DevBuf words, lens, flags, exc_read, exc_pos, exc_kind, results, queue;
     uint32_t* d_queue_count = nullptr;
@@ -945,6 +949,14 @@ dcb_ctx* dcb_ctx_create(int device, const dcb_tagset* v, const dcb_tagset* j, co
             }
         }
     }
+    {   // union suffix filter: the general kernel marks candidate keyword positions with it
+        size_t nwf = 0;
+        if (dcb_tagset_suffix_filter(v, j, nullptr, 0, &nwf) == DCB_OK) {
+            std::vector<uint32_t> sf(nwf);
+            if (dcb_tagset_suffix_filter(v, j, sf.data(), sf.size(), &nwf) == DCB_OK)
+                if (upload_blob(sf, &c->d_sfilt, &c->sfilt_words)) return fail(nullptr);
+        }
+    }
     if (cudaMalloc((void**)&c->d_queue_count, sizeof(uint32_t) * kMaxChunks) != cudaSuccess) return fail("cudaMalloc");
     if (cudaMalloc((void**)&c->d_counters, sizeof(unsigned long long) * DCB_NCOUNTERS) != cudaSuccess) return fail("cudaMalloc");
     return c;
@@ -959,7 +971,7 @@ void dcb_ctx_destroy(dcb_ctx* c) {
     if (c->ev_ready) cudaEventDestroy(c->ev_ready);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
     cudaFree(c->d_vgen); cudaFree(c->d_jgen); cudaFree(c->d_vcore); cudaFree(c->d_jcore);
-    cudaFree(c->d_vidx); cudaFree(c->d_jidx); cudaFree(c->d_uidx);
+    cudaFree(c->d_vidx); cudaFree(c->d_jidx); cudaFree(c->d_uidx); cudaFree(c->d_sfilt);
     cudaFree(c->d_queue_count); cudaFree(c->d_counters);
     c->words.release(); c->lens.release(); c->flags.release(); c->exc_read.release(); c->exc_pos.release();
     c->exc_kind.release(); c->results.release(); c->queue.release();
@@ -1049,7 +1061,7 @@ static int prepare_batch(dcb_ctx* c, const dcb_packed* P) {
     {
         int T = kGeneralThreads;
         for (; T >= 32; T >>= 1) {
-            c->general_smem = ((size_t)c->vgen_words + c->jgen_words + (sw + nwi) * T * (c->params.both_frames ? 2 : 1)) * 4 + tail;
+            c->general_smem = ((size_t)c->vgen_words + c->jgen_words + c->sfilt_words + (sw + nwi) * T * (c->params.both_frames ? 2 : 1) + nwi * T) * 4 + tail;
             if (c->general_smem <= kMaxSmem) break;
         }
         if (T < 32) { dcb_set_error("tag tables + %u-nt reads do not fit in shared memory", P->max_len); return DCB_EUNSUPPORTED; }
@@ -1122,7 +1134,7 @@ static int launch_range(dcb_ctx* c, cudaStream_t s, uint32_t first, uint32_t cou
     if (timed && (rc = timing_begin(c, 1))) return rc;
     Tables4 tg;
     tg.g[0] = c->d_vgen; tg.words[0] = c->vgen_words; tg.g[1] = c->d_jgen; tg.words[1] = c->jgen_words;
-    tg.g[2] = tg.g[3] = nullptr; tg.words[2] = tg.words[3] = 0;
+    tg.g[2] = c->d_sfilt; tg.words[2] = c->sfilt_words; tg.g[3] = nullptr; tg.words[3] = 0;
     dcb_general_kernel<<<grid_g, c->general_threads, c->general_smem, s>>>(
         b, tg, prm, c->params.both_frames, (dcb_result*)c->results.p, c->d_counters,
         c->params.force_general == 1 ? nullptr : (const uint32_t*)queue, qcount);

@@ -516,6 +516,40 @@ int dcb_tagset_blob(const dcb_tagset* ts, int which, const uint32_t** words, siz
     return DCB_OK;
 }
 
+int dcb_tagset_suffix_filter(const dcb_tagset* v, const dcb_tagset* j, uint32_t* out, size_t cap, size_t* n_words) {
+    if (!v || !j || !n_words) return DCB_EINVAL;
+    std::vector<std::string> kws;
+    int kq = 1 << 30;
+    for (const dcb_tagset* ts : {v, j})
+        for (const std::string& t : ts->tags) {
+            kws.push_back(t);
+            kws.push_back(t.substr(0, ts->split));
+            kws.push_back(t.substr(ts->split));
+        }
+    for (auto& k : kws) kq = std::min(kq, (int)k.size());
+    if (kq < 1) { dcb_set_error("dcb_tagset_suffix_filter: empty keyword"); return DCB_EUNSUPPORTED; }
+    if (kq > 16) kq = 16;
+    DcbSuffixFilter h;
+    h.kq = kq;
+    h.fbits = 2 * kq < 16 ? (2 * kq < 5 ? 5 : 2 * kq) : 16;
+    // short keywords index the filter directly (exact membership), longer ones through a multiplicative hash; the
+    // prober masks the window to the kq-mer's own 2 kq bits first
+    h.fmul = 2 * kq <= h.fbits ? (1u << (32 - h.fbits)) : ((0x2C1B3C6Du | 1u) << (32 - 2 * kq));
+    const size_t words = ((size_t)1 << h.fbits) / 32;
+    h.n_words = (int32_t)(DCB_SFILTER_HEAD + words);
+    std::vector<uint32_t> blob(((size_t)h.n_words + 3) & ~(size_t)3, 0u);
+    std::memcpy(blob.data(), &h, sizeof(h));
+    for (auto& k : kws) {
+        uint32_t lo, hi;
+        if (!pack64(k, k.size() - kq, kq, lo, hi)) { dcb_set_error("dcb_tagset_suffix_filter: non-ACGT keyword"); return DCB_EUNSUPPORTED; }
+        const uint32_t sl = DCB_SFSLOT(lo, h.fmul, h.fbits);
+        blob[DCB_SFILTER_HEAD + (sl >> 5)] |= 1u << (sl & 31);
+    }
+    *n_words = blob.size();
+    if (out && cap >= blob.size()) std::memcpy(out, blob.data(), blob.size() * 4);
+    return DCB_OK;
+}
+
 int dcb_tagset_union_index(const dcb_tagset* v, const dcb_tagset* j, uint32_t* out, size_t cap, size_t* n_words) {
     if (!v || !j || !n_words) return DCB_EINVAL;
     if (v->lmin != j->lmin) { dcb_set_error("dcb_tagset_union_index: V and J tags have different minimum lengths"); return DCB_EUNSUPPORTED; }

@@ -89,6 +89,9 @@ int dcb_tagset_blob(const dcb_tagset*, int which, const uint32_t** words, size_t
 /* Seed index over BOTH genes of a chain (built by dcb_ctx_create when V and J share the seed geometry).
  * Writes up to cap words; *n_words is the size needed; returns DCB_EUNSUPPORTED when the geometries differ. */
 int dcb_tagset_union_index(const dcb_tagset* v, const dcb_tagset* j, uint32_t* out, size_t cap, size_t* n_words);
+/* Union suffix filter of the six keyword sets of a chain (csrc/dcb_tables.h, DcbSuffixFilter): what the general kernel
+   marks candidate keyword positions with.  Same calling convention as dcb_tagset_union_index. */
+int dcb_tagset_suffix_filter(const dcb_tagset* v, const dcb_tagset* j, uint32_t* out, size_t cap, size_t* n_words);
 
 /* ---------------------------------------------------------------------------------------------
  * Packed reads: 2 bits per base (A=0 C=1 G=2 T=3, base i of a read in bits [2*(i%16), +2) of

@@ -12,11 +12,11 @@
 extern "C" int sim_decombine(const dcb_packed* P, const uint32_t* vgen, const uint32_t* jgen, const uint32_t* vcore,
                              const uint32_t* jcore, const uint32_t* vidx, const uint32_t* jidx, int both_frames,
                              int allow_ns, int lenthreshold, int mode,
-                             dcb_result* out, uint64_t* counters, uint64_t* n_deferred) {
+                             dcb_result* out, uint64_t* counters, uint64_t* n_deferred, const uint32_t* sfilt) {
     DcrParams prm;
     prm.allow_ns = allow_ns; prm.lenthreshold = lenthreshold;
     const int nw = (int)P->slot_words, nwi = (nw + 1) / 2;
-    std::vector<uint32_t> inv0(nwi + 1), inv1(nwi + 1), rd1(nw + 1);
+    std::vector<uint32_t> inv0(nwi + 1), inv1(nwi + 1), rd1(nw + 1), cand(nwi + 1);
     dcb_cnt_t cnt[DCB_NCOUNTERS];
     std::memset(cnt, 0, sizeof(cnt));
     ExcList ex;
@@ -37,7 +37,7 @@ extern "C" int sim_decombine(const dcb_packed* P, const uint32_t* vgen, const ui
             deferred++;
             std::memset(&o, 0, sizeof(o));
             dcr_general_read(r, (uint32_t)ri, flagged, ex, inv0.data(), rd1.data(), inv1.data(), vgen, jgen, prm,
-                             both_frames, o, cnt);
+                             both_frames, o, cnt, sfilt, sfilt ? cand.data() : nullptr);
         }
         out[ri] = o;
     }
