@@ -42,6 +42,7 @@ struct DcbKwSet {
     int32_t kw_off;      // DcbKw[n_kw] grouped by suffix key, longest first inside a group
     int32_t taglist_off; // bytes: tag ids
     int32_t min_len, max_len;
+    int32_t set_id;      // 0 full, 1 first halves, 2 second halves; + 3 for the J gene (tags the entries of a hit list)
 };
 
 // Per-tag record (48 bytes = 12 words; the first 16 bytes are read with one 128-bit load).

@@ -63,7 +63,13 @@ struct ReadView {
     // be the tail of a keyword (union suffix filter); same stride; null = not marked, scans visit every position
     const uint32_t* cand;
     int cand_kq;
+    // hit list (general kernel): every keyword occurrence of all six sets, found in ONE pass over the marked positions
+    // (hits_build) in findall order; entry = start | keyword << 16 | set_id << 24, same stride; null = not built, each
+    // findall scans by itself
+    const uint32_t* hits;
+    int n_hits;
 };
+#define DCB_HITS_CAP 24
 
 DCB_HD uint32_t rd_word(const ReadView& r, int i) {
     return ((unsigned)i < (unsigned)r.nw) ? r.w[i * r.stride] : 0u;
@@ -210,6 +216,27 @@ DCB_HD const DcbTag& gene_tag(const uint32_t* blob, const DcbGene& g, int k) {
     return reinterpret_cast<const DcbTag*>(blob + g.tag_off)[k];
 }
 
+// Bit-parallel "10 consecutive equal bases": x = xor of two 32-base windows; returns a word pair where
+// bit 2i is set iff bases i..i+9 are all equal (i <= 22).
+DCB_HD void run10(uint32_t xlo, uint32_t xhi, uint32_t& rlo, uint32_t& rhi) {
+    uint64_t x = ((uint64_t)xhi << 32) | xlo;
+    uint64_t eq = ~(x | (x >> 1)) & 0x5555555555555555ull;
+    uint64_t r2 = eq & (eq >> 2);
+    uint64_t r4 = r2 & (r2 >> 4);
+    uint64_t r8 = r4 & (r4 >> 8);
+    uint64_t r10 = r8 & (r2 >> 16);
+    rlo = (uint32_t)r10; rhi = (uint32_t)(r10 >> 32);
+}
+
+// 32 germline bases from p (0 <= p, p + 32 <= region_len)
+DCB_HD void rg_win32(const uint32_t* blob, const DcbTag& t, int p, uint32_t& lo, uint32_t& hi) {
+    const int wi = p >> 4, sh = (p & 15) * 2;
+    const uint32_t a = blob[t.region_off + wi], b = blob[t.region_off + wi + 1];
+    const uint32_t c = sh ? blob[t.region_off + wi + 2] : 0u;      // the packer leaves one zero word behind every region
+    lo = DCB_FUNNEL_R(a, b, sh);
+    hi = DCB_FUNNEL_R(b, c, sh);
+}
+
 // get_v_deletions (decombine.py:749-785), literal walk with Python slice semantics
 DCB_HD bool v_deletions_general(const ReadView& r, const uint32_t* blob, const DcbTag& t, int temp_end_v,
                                 int& end_v, int& dels, dcb_cnt_t* C) {
@@ -219,6 +246,25 @@ DCB_HD bool v_deletions_general(const ReadView& r, const uint32_t* blob, const D
         return false;
     }
     int f = temp_end_v + 1, pos = m - 10, nd = 0;            // :754-765
+    // Interior fast-forward: while the next 23 steps compare plain 10-base slices (no wrap, no truncation, no non-ACGT
+    // symbol), they are 23 alignments of ONE 32-base window of the read against one of the region -- a run of 10 equal
+    // bases found bit-parallel.  A substitution in the true junction makes this walk run to the start of the read
+    // (v_del_failed); stepping it base by base was 80 % of the general kernel's time.
+    while (f < n && f >= 32 && pos >= 22 && pos + 10 <= m && !rd_inv_any(r, f - 32, f)) {
+        uint32_t lo, hi, glo, ghi, rl, rh;
+        rd_win32(r, f - 32, lo, hi);
+        rg_win32(blob, t, pos - 22, glo, ghi);
+        run10(lo ^ glo, hi ^ ghi, rl, rh);
+        rh &= (1u << 14) - 1u;                               // window index i <= 22 <-> step 22 - i
+        if (rl | rh) {
+            const int top = rh ? 63 - DCB_CLZ(rh) : 31 - DCB_CLZ(rl);
+            nd += 22 - (top >> 1);
+            dels = nd;
+            end_v = temp_end_v - nd;
+            return true;
+        }
+        f -= 23; pos -= 23; nd += 23;
+    }
     while (0 <= f && f < n) {                                // :767
         if (slices_equal(blob, t, py_slice(m, pos, pos + 10), r, py_slice(n, f - 10, f))) {  // :769-772
             dels = nd;                                       // :774-775
@@ -236,6 +282,22 @@ DCB_HD bool j_deletions_general(const ReadView& r, const uint32_t* blob, const D
                                 int end_of_v, int& start_j, int& dels, dcb_cnt_t* C) {
     const int n = r.n, m = t.region_len;
     int f = temp_start_j, pos = 0;
+    // Interior fast-forward, as in v_deletions_general: past end_of_v, 23 steps at a time.
+    if (f >= 0 && f < end_of_v && end_of_v + 2 < n) { pos += end_of_v - f; f = end_of_v; }   // :798-800, junction bases
+    while (f >= 0 && f >= end_of_v && f + 32 <= n && pos + 32 <= m && !rd_inv_any(r, f, f + 32)) {
+        uint32_t lo, hi, glo, ghi, rl, rh;
+        rd_win32(r, f, lo, hi);
+        rg_win32(blob, t, pos, glo, ghi);
+        run10(lo ^ glo, hi ^ ghi, rl, rh);
+        rh &= (1u << 14) - 1u;                               // window index i <= 22 <-> step i
+        if (rl | rh) {
+            const int low = rl ? DCB_FFS(rl) - 1 : 32 + DCB_FFS(rh) - 1;
+            dels = pos + (low >> 1);
+            start_j = f + (low >> 1);
+            return true;
+        }
+        f += 23; pos += 23;
+    }
     while (0 <= f + 2 && f + 2 < n) {                        // :795
         if (f < end_of_v) {                                  // :798-800
             pos++; f++;
@@ -255,11 +317,12 @@ DCB_HD bool j_deletions_general(const ReadView& r, const uint32_t* blob, const D
 // findall() of one keyword set as a resumable generator: hits come out ordered by END position,
 // longest keyword first at equal end -- the order acora reports them in.
 // ------------------------------------------------------------------------------------------------
-struct KwScan { int e, ci, cend; };
+struct KwScan { int e, ci, cend, hi; };
 
 DCB_HD void kw_scan_init(KwScan& s, const DcbKwSet& ks) {
     s.e = ks.kq - 1;
     s.ci = s.cend = 0;
+    s.hi = 0;
 }
 
 DCB_HD const DcbKw& kwset_kw(const uint32_t* blob, const DcbKwSet& ks, int c) {
@@ -267,6 +330,13 @@ DCB_HD const DcbKw& kwset_kw(const uint32_t* blob, const DcbKwSet& ks, int c) {
 }
 
 DCB_HD bool kw_scan_next(const ReadView& r, const uint32_t* blob, const DcbKwSet& ks, KwScan& s, int& kw, int& start) {
+    if (r.hits) {            // the occurrences are already listed, in this order
+        while (s.hi < r.n_hits) {
+            const uint32_t e = r.hits[s.hi++ * r.stride];
+            if ((int)(e >> 24) == ks.set_id) { kw = (int)((e >> 16) & 255u); start = (int)(e & 0xFFFFu); return true; }
+        }
+        return false;
+    }
     const uint32_t kmask = mask2(ks.kq);
     for (;;) {
         while (s.ci < s.cend) {
@@ -296,6 +366,48 @@ DCB_HD bool kw_scan_next(const ReadView& r, const uint32_t* blob, const DcbKwSet
             h = (h + 1) & (uint32_t)ks.hash_mask;
         }
     }
+}
+
+// All keyword occurrences of the six sets of a chain in one pass over the marked positions (cand_build), appended per
+// set in exactly the order kw_scan_next reports them.  One converged loop per warp instead of up to six scans that
+// every lane enters and leaves at its own time (measured: 4.6 of 32 lanes active in the scans).  More than
+// DCB_HITS_CAP occurrences: the list is dropped and the scans run as before.
+DCB_HD void hits_build(ReadView& r, const uint32_t* vblob, const uint32_t* jblob, uint32_t* hits_col) {
+    const DcbGene& gv = *reinterpret_cast<const DcbGene*>(vblob);
+    const DcbGene& gj = *reinterpret_cast<const DcbGene*>(jblob);
+    int n = 0;
+    bool ok = true;
+    r.hits = nullptr; r.n_hits = 0;
+    const int limit = 32 * ((r.nw + 1) / 2);
+    for (int p = cand_next(r, 0); p < limit; p = cand_next(r, p + 1)) {
+        const int e = p + r.cand_kq;                     // candidate end position (exclusive)
+        if (e > r.n) break;
+        for (int si = 0; si < 6; si++) {
+            const uint32_t* blob = si < 3 ? vblob : jblob;
+            const DcbGene& g = si < 3 ? gv : gj;
+            const DcbKwSet& ks = (si % 3) == 0 ? g.full : (si % 3) == 1 ? g.half1 : g.half2;
+            if (e < ks.kq) continue;
+            const uint32_t key = rd_win16(r, e - ks.kq) & mask2(ks.kq);
+            if (!((blob[ks.bitmap_off + (key >> 5)] >> (key & 31)) & 1u)) continue;
+            uint32_t h = dcb_hash32(key) & (uint32_t)ks.hash_mask;
+            int ci = 0, cend = 0;
+            for (;;) {
+                const uint32_t slot = blob[ks.hash_off + h];
+                if (slot == DCB_HASH_EMPTY) break;
+                if ((slot >> 16) == key) { ci = (int)((slot >> 8) & 255u); cend = ci + (int)(slot & 255u); break; }
+                h = (h + 1) & (uint32_t)ks.hash_mask;
+            }
+            for (int c = ci; c < cend; c++) {
+                const DcbKw& k = kwset_kw(blob, ks, c);
+                const int st = e - (int)k.len;
+                if (st < 0 || !rd_equals(r, st, k.len, k.bits_lo, k.bits_hi)) continue;
+                if (n < DCB_HITS_CAP) hits_col[n * r.stride] = (uint32_t)st | ((uint32_t)c << 16) | ((uint32_t)si << 24);
+                else ok = false;
+                n++;
+            }
+        }
+    }
+    if (ok) { r.hits = hits_col; r.n_hits = n; }
 }
 
 struct VJ { int idx, pos, dels, seqpos; };  // (match, end_v | start_j, deletions, v_seq_start | j_seq_end)
@@ -530,18 +642,6 @@ DCB_HD void fast_check_offset(const ReadView& r, const SeedIdxView& ix, int p, i
         }
         ctag = ix.chain ? ix.chain[ctag] : 0x1FFu;
     }
-}
-
-// Bit-parallel "10 consecutive equal bases": x = xor of two 32-base windows; returns a word pair where
-// bit 2i is set iff bases i..i+9 are all equal (i <= 22).
-DCB_HD void run10(uint32_t xlo, uint32_t xhi, uint32_t& rlo, uint32_t& rhi) {
-    uint64_t x = ((uint64_t)xhi << 32) | xlo;
-    uint64_t eq = ~(x | (x >> 1)) & 0x5555555555555555ull;
-    uint64_t r2 = eq & (eq >> 2);
-    uint64_t r4 = r2 & (r2 >> 4);
-    uint64_t r8 = r4 & (r4 >> 8);
-    uint64_t r10 = r8 & (r2 >> 16);
-    rlo = (uint32_t)r10; rhi = (uint32_t)(r10 >> 32);
 }
 
 // The second 16 bytes of a DcbTag: all the exact-tag path needs after the match itself, in one 128-bit load.
@@ -838,10 +938,10 @@ DCB_HD int dcr_exact_read(const ReadView& r, bool flagged, const uint32_t* vcore
 DCB_HD void dcr_general_read(ReadView r, uint32_t ri, bool flagged, const ExcList& ex, uint32_t* inv0, uint32_t* rd1,
                              uint32_t* inv1, const uint32_t* vblob, const uint32_t* jblob, const DcrParams& prm,
                              int both_frames, dcb_result& out, dcb_cnt_t* C, const uint32_t* sf = nullptr,
-                             uint32_t* cand0 = nullptr) {
+                             uint32_t* cand0 = nullptr, uint32_t* hits0 = nullptr) {
     const int nwi = (r.nw + 1) / 2;
     r.inv = nullptr; r.exc_pos = ex.pos; r.exc_kind = ex.kind; r.e0 = r.e1 = 0; r.mirror = 0;
-    r.cand = nullptr; r.cand_kq = 0;
+    r.cand = nullptr; r.cand_kq = 0; r.hits = nullptr; r.n_hits = 0;
     if (sf && cand0) cand_build(r, sf, cand0);
     if (flagged) {
         uint32_t e0 = exc_lower_bound(ex, ri), e1 = e0;
@@ -857,6 +957,7 @@ DCB_HD void dcr_general_read(ReadView r, uint32_t ri, bool flagged, const ExcLis
         }
         if (any) r.inv = inv0;
     }
+    if (r.cand && hits0) hits_build(r, vblob, jblob, hits0);      // after r.inv: an occurrence needs valid bases
     bool ok = dcr_general(r, vblob, jblob, prm, out, C);
     if (!ok && both_frames) {                                          // decombine.py:1005-1010
         for (int k = 0; k < r.nw; k++) rd1[k * r.stride] = revcomp_word(r, k);
@@ -871,6 +972,8 @@ DCB_HD void dcr_general_read(ReadView r, uint32_t ri, bool flagged, const ExcLis
             }
             r1.inv = inv1;
         }
+        r1.hits = nullptr; r1.n_hits = 0;
+        if (r1.cand && hits0) hits_build(r1, vblob, jblob, hits0);
         dcb_result o1;
         o1.status = 0; o1.frame = 0; o1.v = o1.j = 0; o1.vdel = o1.jdel = 0;
         o1.ins_start = o1.ins_end = o1.v_seq_start = o1.j_seq_end = 0;

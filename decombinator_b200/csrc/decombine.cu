@@ -217,7 +217,7 @@ dcb_exact_kernel(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_res
             r.w = s_rd + tid; r.inv = nullptr; r.stride = T;
             r.n = b.uniform_len ? (int)b.uniform_len : (int)__ldg(b.lens + ri);
             r.nw = (int)b.slot_words;
-            r.exc_pos = nullptr; r.exc_kind = nullptr; r.e0 = r.e1 = 0; r.mirror = 0; r.cand = nullptr; r.cand_kq = 0;
+            r.exc_pos = nullptr; r.exc_kind = nullptr; r.e0 = r.e1 = 0; r.mirror = 0; r.cand = nullptr; r.cand_kq = 0; r.hits = nullptr; r.n_hits = 0;
             action = dcr_exact_read(r, flagged, L.t[0], L.t[1], L.t[2], L.t[3], prm, both_frames, out, L.cnt);
         }
         defer_reads(live && action == FAST_DEFER, ri, queue, queue_count);
@@ -381,7 +381,7 @@ dcb_exact_kernel_spec(BatchDev b, Tables4 tb, SpecBlooms bl, DcrParams prm, int 
         r.w = col; r.inv = nullptr; r.stride = T;
         r.n = b.uniform_len ? (int)b.uniform_len : (live ? (int)__ldg(b.lens + ri) : 0);
         r.nw = NW;
-        r.exc_pos = nullptr; r.exc_kind = nullptr; r.e0 = r.e1 = 0; r.mirror = 0; r.cand = nullptr; r.cand_kq = 0;
+        r.exc_pos = nullptr; r.exc_kind = nullptr; r.e0 = r.e1 = 0; r.mirror = 0; r.cand = nullptr; r.cand_kq = 0; r.hits = nullptr; r.n_hits = 0;
         FullHit vh, jh;
         vh.count = 0; vh.code = 0;
         jh.count = 0; jh.code = 0;
@@ -529,7 +529,7 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
         r.w = col; r.inv = nullptr; r.stride = T;
         r.n = b.uniform_len ? (int)b.uniform_len : (live ? (int)__ldg(b.lens + ri) : 0);
         r.nw = NW;
-        r.exc_pos = nullptr; r.exc_kind = nullptr; r.e0 = r.e1 = 0; r.mirror = 0; r.cand = nullptr; r.cand_kq = 0;
+        r.exc_pos = nullptr; r.exc_kind = nullptr; r.e0 = r.e1 = 0; r.mirror = 0; r.cand = nullptr; r.cand_kq = 0; r.hits = nullptr; r.n_hits = 0;
 
         // 1. probe: bit NPOS-1-i of h <=> the seed at i * S may be indexed.  The slot must hash the WHOLE seed: reads are
         //    full of 8-mers that homologous genes share with a tag (measured: slot = the seed's first 8 bases costs 0.8
@@ -711,11 +711,12 @@ dcb_general_kernel(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_r
     extern __shared__ __align__(16) uint32_t smem[];
     const int T = blockDim.x;
     const int nw = (int)b.slot_words, nwi = (nw + 1) / 2;
-    SmemLayout L = carve(smem, tb, (size_t)(nw + nwi) * T * (both_frames ? 2 : 1) + (size_t)nwi * T);
+    SmemLayout L = carve(smem, tb, (size_t)(nw + nwi) * T * (both_frames ? 2 : 1) + (size_t)(nwi + DCB_HITS_CAP) * T);
     uint32_t* s_rd = L.cols;                      // [nw][T]
     uint32_t* s_inv = s_rd + (size_t)nw * T;      // [nwi][T]
     uint32_t* s_cand = s_inv + (size_t)nwi * T;   // [nwi][T] candidate keyword positions
-    uint32_t* s_rd1 = s_cand + (size_t)nwi * T;   // second frame (only when both_frames)
+    uint32_t* s_hits = s_cand + (size_t)nwi * T;  // [DCB_HITS_CAP][T] keyword occurrences
+    uint32_t* s_rd1 = s_hits + (size_t)DCB_HITS_CAP * T;   // second frame (only when both_frames)
     uint32_t* s_inv1 = s_rd1 + (size_t)nw * T;
     stage_tables(L, tb);
     const uint32_t* vblob = L.t[0];
@@ -747,7 +748,7 @@ dcb_general_kernel(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_r
         dcb_result out;
         *reinterpret_cast<uint4*>(&out) = make_uint4(0, 0, 0, 0);
         dcr_general_read(r, ri, flagged, ex, s_inv + tid, s_rd1 + tid, s_inv1 + tid, vblob, jblob, prm, both_frames, out,
-                         L.cnt, sfilt, s_cand + tid);
+                         L.cnt, sfilt, s_cand + tid, s_hits + tid);
         store_result(results + ri, out);
     }
     flush_counters(L.cnt, counters);
@@ -1061,7 +1062,7 @@ static int prepare_batch(dcb_ctx* c, const dcb_packed* P) {
     {
         int T = kGeneralThreads;
         for (; T >= 32; T >>= 1) {
-            c->general_smem = ((size_t)c->vgen_words + c->jgen_words + c->sfilt_words + (sw + nwi) * T * (c->params.both_frames ? 2 : 1) + nwi * T) * 4 + tail;
+            c->general_smem = ((size_t)c->vgen_words + c->jgen_words + c->sfilt_words + (sw + nwi) * T * (c->params.both_frames ? 2 : 1) + (nwi + DCB_HITS_CAP) * T) * 4 + tail;
             if (c->general_smem <= kMaxSmem) break;
         }
         if (T < 32) { dcb_set_error("tag tables + %u-nt reads do not fit in shared memory", P->max_len); return DCB_EUNSUPPORTED; }

@@ -482,6 +482,7 @@ dcb_tagset* dcb_tagset_build(const char* const* tags, const int32_t* jumps, cons
             build_kwset(b, g.full, full);
             build_kwset(b, g.half1, h1);
             build_kwset(b, g.half2, h2);
+            g.full.set_id = is_v ? 0 : 3; g.half1.set_id = is_v ? 1 : 4; g.half2.set_id = is_v ? 2 : 5;
             for (int i = 0; i < n; i++) {
                 size_t nw = (reg[i].size() + 15) / 16;
                 trec[i].region_off = b.reserve(nw + 1);

@@ -16,7 +16,7 @@ extern "C" int sim_decombine(const dcb_packed* P, const uint32_t* vgen, const ui
     DcrParams prm;
     prm.allow_ns = allow_ns; prm.lenthreshold = lenthreshold;
     const int nw = (int)P->slot_words, nwi = (nw + 1) / 2;
-    std::vector<uint32_t> inv0(nwi + 1), inv1(nwi + 1), rd1(nw + 1), cand(nwi + 1);
+    std::vector<uint32_t> inv0(nwi + 1), inv1(nwi + 1), rd1(nw + 1), cand(nwi + 1), hits(DCB_HITS_CAP);
     dcb_cnt_t cnt[DCB_NCOUNTERS];
     std::memset(cnt, 0, sizeof(cnt));
     ExcList ex;
@@ -37,7 +37,7 @@ extern "C" int sim_decombine(const dcb_packed* P, const uint32_t* vgen, const ui
             deferred++;
             std::memset(&o, 0, sizeof(o));
             dcr_general_read(r, (uint32_t)ri, flagged, ex, inv0.data(), rd1.data(), inv1.data(), vgen, jgen, prm,
-                             both_frames, o, cnt, sfilt, sfilt ? cand.data() : nullptr);
+                             both_frames, o, cnt, sfilt, sfilt ? cand.data() : nullptr, sfilt ? hits.data() : nullptr);
         }
         out[ri] = o;
     }
