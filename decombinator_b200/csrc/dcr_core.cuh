@@ -69,7 +69,7 @@ struct ReadView {
     const uint32_t* hits;
     int n_hits;
 };
-#define DCB_HITS_CAP 24
+#define DCB_HITS_CAP 16
 
 DCB_HD uint32_t rd_word(const ReadView& r, int i) {
     return ((unsigned)i < (unsigned)r.nw) ? r.w[i * r.stride] : 0u;
@@ -91,6 +91,12 @@ DCB_HD bool rd_inv_at(const ReadView& r, int p) {
 // any invalid base in [a, b), 0 <= a, b <= n
 DCB_HD bool rd_inv_any(const ReadView& r, int a, int b) {
     if (!r.inv || a >= b) return false;
+    if (b - a <= 32) {                        // one funnel shift over two mask words (every caller but the N filter)
+        const int wi = a >> 5, nwm = (r.nw + 1) / 2;
+        const uint32_t w0 = r.inv[wi * r.stride], w1 = wi + 1 < nwm ? r.inv[(wi + 1) * r.stride] : 0u;
+        const uint32_t x = DCB_FUNNEL_R(w0, w1, a & 31);
+        return (x & (b - a == 32 ? 0xFFFFFFFFu : ((1u << (b - a)) - 1u))) != 0u;
+    }
     for (int wi = a >> 5; wi <= ((b - 1) >> 5); wi++) {
         int lo = a > wi * 32 ? a - wi * 32 : 0;
         int hi = b < wi * 32 + 32 ? b - wi * 32 : 32;

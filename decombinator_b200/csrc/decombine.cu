@@ -129,7 +129,7 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* a, uint32_t 
 }
 
 static constexpr int kExactThreads = 512;   // upper bounds; long reads launch narrower blocks (shared memory)
-static constexpr int kGeneralThreads = 128;
+static constexpr int kGeneralThreads = 768;   // one wide block per SM: the 72 KB of tables are staged once, 24 warps hide the latency
 static constexpr int kMaxChunks = 256;             // queue counters per context
 static constexpr uint32_t kChunkReads = 1u << 20;  // reads per chunk of the pipelined host-to-host path
 
@@ -1061,7 +1061,7 @@ static int prepare_batch(dcb_ctx* c, const dcb_packed* P) {
     }
     {
         int T = kGeneralThreads;
-        for (; T >= 32; T >>= 1) {
+        for (; T >= 32; T -= (T > 64 ? 64 : 32)) {
             c->general_smem = ((size_t)c->vgen_words + c->jgen_words + c->sfilt_words + (sw + nwi) * T * (c->params.both_frames ? 2 : 1) + (nwi + DCB_HITS_CAP) * T) * 4 + tail;
             if (c->general_smem <= kMaxSmem) break;
         }
