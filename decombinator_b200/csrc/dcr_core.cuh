@@ -963,27 +963,32 @@ DCB_HD void dcr_general_read(ReadView r, uint32_t ri, bool flagged, const ExcLis
         }
         if (any) r.inv = inv0;
     }
-    if (r.cand && hits0) hits_build(r, vblob, jblob, hits0);      // after r.inv: an occurrence needs valid bases
-    bool ok = dcr_general(r, vblob, jblob, prm, out, C);
-    if (!ok && both_frames) {                                          // decombine.py:1005-1010
-        for (int k = 0; k < r.nw; k++) rd1[k * r.stride] = revcomp_word(r, k);
-        ReadView r1 = r;
-        r1.w = rd1; r1.inv = nullptr; r1.mirror = 1;
-        if (sf && cand0) cand_build(r1, sf, cand0);          // the first frame is done with its marks
-        if (r.e1 > r.e0) {
-            for (int k = 0; k < nwi; k++) inv1[k * r.stride] = 0;
-            for (int e = r.e0; e < r.e1; e++) {
-                uint32_t p = (uint32_t)(r.n - 1) - ex.pos[e];
-                inv1[(p >> 5) * r.stride] |= 1u << (p & 31);
+    // One copy of the analysis code for both frames (the general kernel is instruction-cache bound: 24 warps at
+    // different places of ~100 KB of code): frame 1 re-enters the same loop body with the mirrored read.
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int frame = 0; frame < (both_frames ? 2 : 1); frame++) {
+        if (frame == 1) {                                                  // decombine.py:1005-1010
+            for (int k = 0; k < r.nw; k++) rd1[k * r.stride] = revcomp_word(r, k);
+            const ReadView r0 = r;
+            r.w = rd1; r.inv = nullptr; r.mirror = 1;
+            if (r0.e1 > r0.e0) {
+                for (int k = 0; k < nwi; k++) inv1[k * r.stride] = 0;
+                for (int e = r0.e0; e < r0.e1; e++) {
+                    uint32_t p = (uint32_t)(r.n - 1) - ex.pos[e];
+                    inv1[(p >> 5) * r.stride] |= 1u << (p & 31);
+                }
+                r.inv = inv1;
             }
-            r1.inv = inv1;
+            r.hits = nullptr; r.n_hits = 0;
+            if (sf && cand0) cand_build(r, sf, cand0);                    // the first frame is done with its marks
         }
-        r1.hits = nullptr; r1.n_hits = 0;
-        if (r1.cand && hits0) hits_build(r1, vblob, jblob, hits0);
-        dcb_result o1;
-        o1.status = 0; o1.frame = 0; o1.v = o1.j = 0; o1.vdel = o1.jdel = 0;
-        o1.ins_start = o1.ins_end = o1.v_seq_start = o1.j_seq_end = 0;
-        if (dcr_general(r1, vblob, jblob, prm, o1, C)) { o1.frame = 1; out = o1; }
+        if (r.cand && hits0) hits_build(r, vblob, jblob, hits0);          // after r.inv: an occurrence needs valid bases
+        dcb_result o;
+        o.status = 0; o.frame = 0; o.v = o.j = 0; o.vdel = o.jdel = 0;
+        o.ins_start = o.ins_end = o.v_seq_start = o.j_seq_end = 0;
+        if (dcr_general(r, vblob, jblob, prm, o, C)) { o.frame = (uint8_t)frame; out = o; break; }
     }
 }
 
