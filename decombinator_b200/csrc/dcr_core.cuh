@@ -939,12 +939,15 @@ DCB_HD int dcr_exact_read(const ReadView& r, bool flagged, const uint32_t* vcore
 
 // General kernel body for one read: r has w/stride/n/nw set; inv0, rd1, inv1 are this thread's scratch
 // columns (same stride as r): inv0/inv1 hold (nw+1)/2 words, rd1 holds nw words (only used with both_frames).
-// sf / cand0: the chain's union suffix filter and (nw+1)/2 scratch words for the candidate positions, or null (every
-// position is scanned).
-DCB_HD void dcr_general_read(ReadView r, uint32_t ri, bool flagged, const ExcList& ex, uint32_t* inv0, uint32_t* rd1,
-                             uint32_t* inv1, const uint32_t* vblob, const uint32_t* jblob, const DcrParams& prm,
-                             int both_frames, dcb_result& out, dcb_cnt_t* C, const uint32_t* sf = nullptr,
-                             uint32_t* cand0 = nullptr, uint32_t* hits0 = nullptr) {
+// The general path in two steps, so that a thread block can regroup its reads in between (the kernel sorts them by what
+// dcr_general_prepare found, then every warp runs mostly one path of the analysis):
+//   dcr_general_prepare  candidate marks, invalid-base mask, hit list of the first frame; returns the read's class
+//   dcr_general_run      the analysis of both frames on a prepared view
+// sf / cand0 / hits0: the chain's union suffix filter, (nw+1)/2 words for the marks and DCB_HITS_CAP words for the hit
+// list -- or null: the scans visit every position.
+DCB_HD int dcr_general_prepare(ReadView& r, uint32_t ri, bool flagged, const ExcList& ex, uint32_t* inv0,
+                               const uint32_t* vblob, const uint32_t* jblob, const uint32_t* sf, uint32_t* cand0,
+                               uint32_t* hits0) {
     const int nwi = (r.nw + 1) / 2;
     r.inv = nullptr; r.exc_pos = ex.pos; r.exc_kind = ex.kind; r.e0 = r.e1 = 0; r.mirror = 0;
     r.cand = nullptr; r.cand_kq = 0; r.hits = nullptr; r.n_hits = 0;
@@ -963,8 +966,23 @@ DCB_HD void dcr_general_read(ReadView r, uint32_t ri, bool flagged, const ExcLis
         }
         if (any) r.inv = inv0;
     }
-    // One copy of the analysis code for both frames (the general kernel is instruction-cache bound: 24 warps at
-    // different places of ~100 KB of code): frame 1 re-enters the same loop body with the mirrored read.
+    if (r.cand && hits0) hits_build(r, vblob, jblob, hits0);      // after r.inv: an occurrence needs valid bases
+    // class: which paths of the analysis the read will take (full V tag found? full J tag found? non-ACGT symbols?)
+    int nv = 0, nj = 0;
+    if (r.hits)
+        for (int i = 0; i < r.n_hits; i++) {
+            const uint32_t set = r.hits[i * r.stride] >> 24;
+            nv += set == 0u; nj += set == 3u;
+        }
+    return (r.hits ? 0 : 8) | (nv == 0 ? 1 : 0) | (nj == 0 ? 2 : 0) | (r.inv ? 4 : 0);
+}
+
+DCB_HD void dcr_general_run(ReadView r, const ExcList& ex, uint32_t* rd1, uint32_t* inv1, const uint32_t* vblob,
+                            const uint32_t* jblob, const DcrParams& prm, int both_frames, dcb_result& out, dcb_cnt_t* C,
+                            const uint32_t* sf, uint32_t* cand0, uint32_t* hits0) {
+    const int nwi = (r.nw + 1) / 2;
+    // One copy of the analysis code for both frames (the general kernel is instruction-fetch bound: 24 warps at
+    // different places of ~90 KB of code): frame 1 re-enters the same loop body with the mirrored read.
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -983,13 +1001,22 @@ DCB_HD void dcr_general_read(ReadView r, uint32_t ri, bool flagged, const ExcLis
             }
             r.hits = nullptr; r.n_hits = 0;
             if (sf && cand0) cand_build(r, sf, cand0);                    // the first frame is done with its marks
+            if (r.cand && hits0) hits_build(r, vblob, jblob, hits0);
         }
-        if (r.cand && hits0) hits_build(r, vblob, jblob, hits0);          // after r.inv: an occurrence needs valid bases
         dcb_result o;
         o.status = 0; o.frame = 0; o.v = o.j = 0; o.vdel = o.jdel = 0;
         o.ins_start = o.ins_end = o.v_seq_start = o.j_seq_end = 0;
         if (dcr_general(r, vblob, jblob, prm, o, C)) { o.frame = (uint8_t)frame; out = o; break; }
     }
+}
+
+// Both steps on one thread (tests/sim; the kernel regroups in between).
+DCB_HD void dcr_general_read(ReadView r, uint32_t ri, bool flagged, const ExcList& ex, uint32_t* inv0, uint32_t* rd1,
+                             uint32_t* inv1, const uint32_t* vblob, const uint32_t* jblob, const DcrParams& prm,
+                             int both_frames, dcb_result& out, dcb_cnt_t* C, const uint32_t* sf = nullptr,
+                             uint32_t* cand0 = nullptr, uint32_t* hits0 = nullptr) {
+    dcr_general_prepare(r, ri, flagged, ex, inv0, vblob, jblob, sf, cand0, hits0);
+    dcr_general_run(r, ex, rd1, inv1, vblob, jblob, prm, both_frames, out, C, sf, cand0, hits0);
 }
 
 #endif  // DCR_CORE_CUH

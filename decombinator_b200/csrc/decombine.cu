@@ -711,12 +711,15 @@ dcb_general_kernel(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_r
     extern __shared__ __align__(16) uint32_t smem[];
     const int T = blockDim.x;
     const int nw = (int)b.slot_words, nwi = (nw + 1) / 2;
-    SmemLayout L = carve(smem, tb, (size_t)(nw + nwi) * T * (both_frames ? 2 : 1) + (size_t)(nwi + DCB_HITS_CAP) * T);
+    SmemLayout L = carve(smem, tb, (size_t)(nw + nwi) * T * (both_frames ? 2 : 1) + (size_t)(nwi + DCB_HITS_CAP + 6) * T + 20);
     uint32_t* s_rd = L.cols;                      // [nw][T]
     uint32_t* s_inv = s_rd + (size_t)nw * T;      // [nwi][T]
     uint32_t* s_cand = s_inv + (size_t)nwi * T;   // [nwi][T] candidate keyword positions
     uint32_t* s_hits = s_cand + (size_t)nwi * T;  // [DCB_HITS_CAP][T] keyword occurrences
-    uint32_t* s_rd1 = s_hits + (size_t)DCB_HITS_CAP * T;   // second frame (only when both_frames)
+    uint32_t* s_meta = s_hits + (size_t)DCB_HITS_CAP * T;  // [5][T] read index, length, exception range, view flags
+    uint16_t* s_perm = reinterpret_cast<uint16_t*>(s_meta + (size_t)5 * T);   // [T] column of the t-th read after regrouping
+    uint32_t* s_cls = s_meta + (size_t)5 * T + (T + 1) / 2;        // [18] class counters / offsets
+    uint32_t* s_rd1 = s_cls + 20;                 // second frame (only when both_frames)
     uint32_t* s_inv1 = s_rd1 + (size_t)nw * T;
     stage_tables(L, tb);
     const uint32_t* vblob = L.t[0];
@@ -726,30 +729,65 @@ dcb_general_kernel(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_r
     const int tid = threadIdx.x;
     const uint32_t n_items = queue ? *queue_count : b.n_reads;
     const uint32_t n_tiles = (n_items + T - 1) / T;
+    ExcList ex;
+    ex.read = b.exc_read; ex.pos = b.exc_pos; ex.kind = b.exc_kind; ex.n = b.n_exc;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // ---- step 1: thread t prepares the read in column t (marks, invalid-base mask, hit list) and classifies it
         const uint32_t item = tile * T + tid;
-        if (item >= n_items) continue;
-        const uint32_t ri = queue ? queue[item] : b.first + item;
-        const uint4* src = reinterpret_cast<const uint4*>(b.words + (size_t)ri * b.slot_words);
-        for (int k = 0; k < nw / 4; k++) {
-            uint4 v = __ldg(src + k);
-            s_rd[(4 * k + 0) * T + tid] = v.x;
-            s_rd[(4 * k + 1) * T + tid] = v.y;
-            s_rd[(4 * k + 2) * T + tid] = v.z;
-            s_rd[(4 * k + 3) * T + tid] = v.w;
+        const bool live = item < n_items;
+        int cls = 16;                                      // dead column (past the end of the queue)
+        __syncthreads();                                   // the previous tile is done with the columns and s_cls
+        if (tid < 18) s_cls[tid] = 0u;
+        __syncthreads();
+        if (live) {
+            const uint32_t ri = queue ? queue[item] : b.first + item;
+            const uint4* src = reinterpret_cast<const uint4*>(b.words + (size_t)ri * b.slot_words);
+            for (int k = 0; k < nw / 4; k++) {
+                uint4 v = __ldg(src + k);
+                s_rd[(4 * k + 0) * T + tid] = v.x;
+                s_rd[(4 * k + 1) * T + tid] = v.y;
+                s_rd[(4 * k + 2) * T + tid] = v.z;
+                s_rd[(4 * k + 3) * T + tid] = v.w;
+            }
+            ReadView r;
+            r.w = s_rd + tid; r.stride = T;
+            r.n = b.uniform_len ? (int)b.uniform_len : (int)__ldg(b.lens + ri);
+            r.nw = nw;
+            const bool flagged = b.n_exc && ((__ldg(b.flags + (ri >> 5)) >> (ri & 31)) & 1u);
+            cls = dcr_general_prepare(r, ri, flagged, ex, s_inv + tid, vblob, jblob, sfilt, s_cand + tid, s_hits + tid);
+            uint32_t* m = s_meta + tid;                    // what step 2 needs to rebuild the view of this column
+            m[0] = ri; m[T] = (uint32_t)r.n; m[2 * T] = (uint32_t)r.e0; m[3 * T] = (uint32_t)r.e1;
+            m[4 * T] = (uint32_t)r.n_hits | (r.hits ? 0x100u : 0u) | (r.inv ? 0x200u : 0u) | (r.cand ? 0x400u : 0u) |
+                       ((uint32_t)r.cand_kq << 16);
         }
-        ReadView r;
-        r.w = s_rd + tid; r.stride = T;
-        r.n = b.uniform_len ? (int)b.uniform_len : (int)__ldg(b.lens + ri);
-        r.nw = nw;
-        const bool flagged = b.n_exc && ((__ldg(b.flags + (ri >> 5)) >> (ri & 31)) & 1u);
-        ExcList ex;
-        ex.read = b.exc_read; ex.pos = b.exc_pos; ex.kind = b.exc_kind; ex.n = b.n_exc;
-        dcb_result out;
-        *reinterpret_cast<uint4*>(&out) = make_uint4(0, 0, 0, 0);
-        dcr_general_read(r, ri, flagged, ex, s_inv + tid, s_rd1 + tid, s_inv1 + tid, vblob, jblob, prm, both_frames, out,
-                         L.cnt, sfilt, s_cand + tid, s_hits + tid);
-        store_result(results + ri, out);
+        // ---- regroup: counting sort of the columns by class, so that a warp of step 2 runs mostly one path
+        const uint32_t rank = atomicAdd(&s_cls[cls], 1u);  // shared-memory atomics, 17 counters
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t acc = 0;
+            for (int k = 0; k < 17; k++) { const uint32_t c = s_cls[k]; s_cls[k] = acc; acc += c; }
+            s_cls[17] = acc;
+        }
+        __syncthreads();
+        s_perm[s_cls[cls] + rank] = (uint16_t)tid;
+        __syncthreads();
+        // ---- step 2: thread t analyses column s_perm[t] (dead columns sort last)
+        const int col = s_perm[tid];
+        if ((uint32_t)tid < s_cls[16]) {                   // live columns: classes 0..15
+            const uint32_t* m = s_meta + col;
+            const uint32_t ri = m[0], fl = m[4 * T];
+            ReadView r;
+            r.w = s_rd + col; r.stride = T; r.n = (int)m[T]; r.nw = nw;
+            r.exc_pos = ex.pos; r.exc_kind = ex.kind; r.e0 = (int)m[2 * T]; r.e1 = (int)m[3 * T]; r.mirror = 0;
+            r.inv = (fl & 0x200u) ? s_inv + col : nullptr;
+            r.cand = (fl & 0x400u) ? s_cand + col : nullptr; r.cand_kq = (int)(fl >> 16);
+            r.hits = (fl & 0x100u) ? s_hits + col : nullptr; r.n_hits = (int)(fl & 0xFFu);
+            dcb_result out;
+            *reinterpret_cast<uint4*>(&out) = make_uint4(0, 0, 0, 0);
+            dcr_general_run(r, ex, s_rd1 + col, s_inv1 + col, vblob, jblob, prm, both_frames, out, L.cnt, sfilt,
+                            s_cand + col, s_hits + col);
+            store_result(results + ri, out);
+        }
     }
     flush_counters(L.cnt, counters);
 }
@@ -1062,7 +1100,7 @@ static int prepare_batch(dcb_ctx* c, const dcb_packed* P) {
     {
         int T = kGeneralThreads;
         for (; T >= 32; T -= (T > 64 ? 64 : 32)) {
-            c->general_smem = ((size_t)c->vgen_words + c->jgen_words + c->sfilt_words + (sw + nwi) * T * (c->params.both_frames ? 2 : 1) + (nwi + DCB_HITS_CAP) * T) * 4 + tail;
+            c->general_smem = ((size_t)c->vgen_words + c->jgen_words + c->sfilt_words + (sw + nwi) * T * (c->params.both_frames ? 2 : 1) + (nwi + DCB_HITS_CAP + 6) * T + 20) * 4 + tail;
             if (c->general_smem <= kMaxSmem) break;
         }
         if (T < 32) { dcb_set_error("tag tables + %u-nt reads do not fit in shared memory", P->max_len); return DCB_EUNSUPPORTED; }
