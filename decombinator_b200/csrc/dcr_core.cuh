@@ -388,13 +388,24 @@ DCB_HD void hits_build(ReadView& r, const uint32_t* vblob, const uint32_t* jblob
     for (int p = cand_next(r, 0); p < limit; p = cand_next(r, p + 1)) {
         const int e = p + r.cand_kq;                     // candidate end position (exclusive)
         if (e > r.n) break;
+        // first the six cheap bitmap tests, then the (few) sets that passed: lanes walk their own set bits together,
+        // whichever sets they are, instead of all waiting while one lane confirms a keyword of one set
+        uint32_t pass = 0;
         for (int si = 0; si < 6; si++) {
             const uint32_t* blob = si < 3 ? vblob : jblob;
             const DcbGene& g = si < 3 ? gv : gj;
             const DcbKwSet& ks = (si % 3) == 0 ? g.full : (si % 3) == 1 ? g.half1 : g.half2;
             if (e < ks.kq) continue;
             const uint32_t key = rd_win16(r, e - ks.kq) & mask2(ks.kq);
-            if (!((blob[ks.bitmap_off + (key >> 5)] >> (key & 31)) & 1u)) continue;
+            pass |= ((blob[ks.bitmap_off + (key >> 5)] >> (key & 31)) & 1u) << si;
+        }
+        while (pass) {
+            const int si = DCB_FFS(pass) - 1;
+            pass &= pass - 1;
+            const uint32_t* blob = si < 3 ? vblob : jblob;
+            const DcbGene& g = si < 3 ? gv : gj;
+            const DcbKwSet& ks = (si % 3) == 0 ? g.full : (si % 3) == 1 ? g.half1 : g.half2;
+            const uint32_t key = rd_win16(r, e - ks.kq) & mask2(ks.kq);
             uint32_t h = dcb_hash32(key) & (uint32_t)ks.hash_mask;
             int ci = 0, cend = 0;
             for (;;) {
