@@ -74,6 +74,11 @@ def lib():
     L.dcb_tagset_blob.argtypes = [vp, i32, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint32)), ctypes.POINTER(ctypes.c_size_t)]
     L.dcb_tagset_union_index.argtypes = [vp, vp, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
     L.dcb_tagset_suffix_filter.argtypes = [vp, vp, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+    L.dcb_fastq_index_build.argtypes = [vp, u64, i32, ctypes.POINTER(ctypes.POINTER(CFastqIndex))]
+    L.dcb_fastq_index_free.argtypes = [ctypes.POINTER(CFastqIndex)]
+    L.dcb_fastq_index_free.restype = None
+    L.dcb_count_ranges_with.argtypes = [vp, vp, vp, u64, i32, i32]
+    L.dcb_count_ranges_with.restype = u64
     L.dcb_pack_reads.argtypes = [vp, vp, vp, u64, i32, i32, ctypes.POINTER(ctypes.POINTER(CPacked))]
     L.dcb_packed_free.argtypes = [ctypes.POINTER(CPacked)]
     L.dcb_unpack_read.argtypes = [ctypes.POINTER(CPacked), u64, ctypes.c_char_p, u32]
@@ -239,6 +244,50 @@ class Packed:
             self.free()
         except Exception:
             pass
+
+
+class CFastqIndex(ctypes.Structure):
+    _fields_ = [("n_records", ctypes.c_uint64),
+                ("name_off", ctypes.POINTER(ctypes.c_uint64)), ("name_len", ctypes.POINTER(ctypes.c_uint32)),
+                ("seq_off", ctypes.POINTER(ctypes.c_uint64)), ("seq_len", ctypes.POINTER(ctypes.c_uint32)),
+                ("qual_off", ctypes.POINTER(ctypes.c_uint64)), ("qual_len", ctypes.POINTER(ctypes.c_uint32)),
+                ("strict", ctypes.c_int32)]
+
+
+def fastq_index(data, n_threads=None):
+    """dcb_fastq_index_build over FASTQ text in memory (bytes / uint8 array).
+
+    -> dict of numpy arrays (name_off, name_len, seq_off, seq_len, qual_off, qual_len), or None when the text is not in
+    the strict four-line layout (the caller then uses the general parser)."""
+    buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+    out = ctypes.POINTER(CFastqIndex)()
+    nt = n_threads or min(32, os.cpu_count() or 1)
+    _check(lib().dcb_fastq_index_build(buf.ctypes.data if len(buf) else None, len(buf), nt, ctypes.byref(out)),
+           "dcb_fastq_index_build")
+    try:
+        ix = out.contents
+        if not ix.strict:
+            return None
+        n = int(ix.n_records)
+        res = {}
+        for name, ctype, dt in (("name_off", ctypes.c_uint64, np.uint64), ("name_len", ctypes.c_uint32, np.uint32),
+                                ("seq_off", ctypes.c_uint64, np.uint64), ("seq_len", ctypes.c_uint32, np.uint32),
+                                ("qual_off", ctypes.c_uint64, np.uint64), ("qual_len", ctypes.c_uint32, np.uint32)):
+            res[name] = np.ctypeslib.as_array(getattr(ix, name), shape=(n,)).astype(dt, copy=True) if n else np.zeros(0, dt)
+        return res
+    finally:
+        lib().dcb_fastq_index_free(out)
+
+
+def count_ranges_with(buf, off, length, symbol, n_threads=None):
+    """How many of the byte ranges (off[i], length[i]) of buf contain `symbol` (one character)."""
+    buf = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf
+    off = np.ascontiguousarray(off, dtype=np.uint64)
+    length = np.ascontiguousarray(length, dtype=np.uint32)
+    if len(off) == 0:
+        return 0
+    nt = n_threads or min(32, os.cpu_count() or 1)
+    return int(lib().dcb_count_ranges_with(buf.ctypes.data, off.ctypes.data, length.ctypes.data, len(off), ord(symbol), nt))
 
 
 def pack_arrays(buf, off, length, revcomp, n_threads=None) -> Packed:

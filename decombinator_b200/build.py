@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdcb.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-SOURCES = ["decombine.cu", "collapse.cu", "tagset.cpp", "pack.cpp", "synth.cpp", "error.cpp"]
+SOURCES = ["decombine.cu", "collapse.cu", "tagset.cpp", "pack.cpp", "fastq.cpp", "synth.cpp", "error.cpp"]
 
 FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

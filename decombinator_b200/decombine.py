@@ -179,7 +179,7 @@ def decombinator(inputargs: dict) -> list:
             batch = batch.shard(*shard_bounds(len(batch), *inputargs["shard"]))
         n = len(batch)
         if inputargs["allowNs"] == False:  # noqa: E712
-            counts["dcrfilter_barcodeN"] += sum(1 for bc in batch.bc if "N" in bc)
+            counts["dcrfilter_barcodeN"] += fastq.count_containing(batch.bc, "N")
             if counts["dcrfilter_barcodeN"] == 0:
                 del counts["dcrfilter_barcodeN"]
         counts["read_count"] += n

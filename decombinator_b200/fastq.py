@@ -78,6 +78,43 @@ def readfq(fp):
             return
 
 
+class TextColumn:
+    """One string per record, kept as (offset, length) into the raw FASTQ bytes and decoded on demand.
+
+    Behaves like the list of str the general parser builds (len, integer index, slice, iteration); the rows of the
+    result only ever need the strings of the reads that decombined."""
+
+    __slots__ = ("buf", "off", "len")
+
+    def __init__(self, buf, off, length):
+        self.buf, self.off, self.len = buf, off, length
+
+    def __len__(self):
+        return len(self.off)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return TextColumn(self.buf, self.off[i], self.len[i])
+        o = int(self.off[i])
+        return self.buf[o:o + int(self.len[i])].decode("ascii")
+
+    def __iter__(self):
+        buf = self.buf
+        for o, n in zip(self.off.tolist(), self.len.tolist()):
+            yield buf[o:o + n].decode("ascii")
+
+    def count_containing(self, symbol):
+        from . import _lib
+        return _lib.count_ranges_with(self.buf, self.off, self.len, symbol)
+
+
+def count_containing(column, symbol):
+    """Records of a column (list of str or TextColumn) that contain `symbol`."""
+    if isinstance(column, TextColumn):
+        return column.count_containing(symbol)
+    return sum(1 for s in column if symbol in s)
+
+
 class ReadBatch:
     """Records of one decombine run: V(D)J reads as one byte buffer + per-record Python strings for the rows."""
 
@@ -88,6 +125,11 @@ class ReadBatch:
         self.buf = self.off = self.len = None
 
     def finalize(self):
+        if isinstance(self.vdj, TextColumn):     # native index: the reads are packed straight from the file's bytes
+            self.buf = np.frombuffer(self.vdj.buf, dtype=np.uint8)
+            self.off = np.ascontiguousarray(self.vdj.off, dtype=np.uint64)
+            self.len = np.ascontiguousarray(self.vdj.len, dtype=np.uint32)
+            return self
         enc = [s.encode("latin-1", "replace") for s in self.vdj]
         self.len = np.fromiter((len(b) for b in enc), dtype=np.uint32, count=len(enc))
         self.off = np.zeros(len(enc), dtype=np.uint64)
@@ -107,8 +149,64 @@ class ReadBatch:
         return part.finalize()
 
 
+def _clip(off, length, start, stop=None):
+    """(offset, length) of s[start:stop] for every record s = (off, length); start, stop >= 0."""
+    n = length.astype(np.int64)
+    a = np.minimum(n, start)
+    b = n if stop is None else np.minimum(n, stop)
+    return off + a.astype(np.uint64), np.maximum(b - a, 0).astype(np.uint32)
+
+
+def load_pairs_native(inputargs, opener):
+    """load_pairs through the native record index (dcb_fastq_index_build); None when a file is not in the strict
+    four-line layout (the general parser then reproduces the reference's handling of everything else)."""
+    from . import _lib
+    bclength = inputargs["bclength"]
+    if not isinstance(bclength, int) or bclength < 0 or inputargs["bc_read"] not in ("R1", "R2"):
+        return None
+    with opener(inputargs["infile"], "rb") as fh:
+        data1 = fh.read()
+    ix1 = _lib.fastq_index(data1)
+    if ix1 is None:
+        return None
+    sampling = inputargs.get("sampling_analysis")
+    batch = ReadBatch()
+    if inputargs["bc_read"] == "R2":
+        with opener(inputargs["infile"].replace("1.f", "2.f"), "rb") as fh:
+            data2 = fh.read()
+        ix2 = _lib.fastq_index(data2)
+        if ix2 is None:
+            return None
+        n = min(len(ix1["seq_off"]), len(ix2["seq_off"]))            # zip() stops at the shorter file
+        one = {k: v[:n] for k, v in ix1.items()}
+        two = {k: v[:n] for k, v in ix2.items()}
+        batch.ids = TextColumn(data1, one["name_off"], one["name_len"])
+        batch.vdj = TextColumn(data1, one["seq_off"], one["seq_len"])
+        batch.vdjqual = TextColumn(data1, one["qual_off"], one["qual_len"])
+        batch.bc = TextColumn(data2, *_clip(two["seq_off"], two["seq_len"], 0, bclength))
+        batch.bcq = TextColumn(data2, *_clip(two["qual_off"], two["qual_len"], 0, bclength))
+        batch.v_tail = TextColumn(data2, *_clip(two["seq_off"], two["seq_len"], bclength, bclength + 31)) if sampling else []
+    else:
+        # the reference zips the generator with itself: records 2k and 2k+1 are consumed together, the second only
+        # feeds the sampling column
+        n = len(ix1["seq_off"]) // 2
+        one = {k: v[0:2 * n:2] for k, v in ix1.items()}
+        two = {k: v[1:2 * n:2] for k, v in ix1.items()}
+        batch.ids = TextColumn(data1, one["name_off"], one["name_len"])
+        batch.vdj = TextColumn(data1, *_clip(one["seq_off"], one["seq_len"], bclength))
+        batch.vdjqual = TextColumn(data1, *_clip(one["qual_off"], one["qual_len"], bclength))
+        batch.bc = TextColumn(data1, *_clip(one["seq_off"], one["seq_len"], 0, bclength))
+        batch.bcq = TextColumn(data1, *_clip(one["qual_off"], one["qual_len"], 0, bclength))
+        batch.v_tail = TextColumn(data1, *_clip(two["seq_off"], two["seq_len"], bclength, bclength + 31)) if sampling else []
+    return batch.finalize()
+
+
 def load_pairs(inputargs, opener) -> ReadBatch:
     """The record handling at the top of the hot loop (decombine.py:950-983)."""
+    if not inputargs.get("python_fastq"):
+        native = load_pairs_native(inputargs, opener)
+        if native is not None:
+            return native
     bclength = inputargs["bclength"]
     batch = ReadBatch()
     fq1 = readfq(opener(inputargs["infile"], "rt"))

@@ -123,6 +123,28 @@ typedef struct dcb_packed {
 int dcb_pack_reads(const char* ascii, const uint64_t* off, const uint32_t* len, uint64_t n, int revcomp,
                    int n_threads, dcb_packed** out);
 void dcb_packed_free(dcb_packed*);
+/* ---------------------------------------------------------------------------------------------
+ * FASTQ ingest (host): the record index of a FASTQ text held in memory.  Replaces the reference's
+ * parser readfq (decombine.py:228-265) for files in the strict layout (four lines per record, '\n'
+ * line ends, ASCII, quality at least as long as its sequence): name = header after '@' up to the
+ * first space, sequence / quality = the second / fourth line, all as (offset, length) into `text`,
+ * so sequences go to dcb_pack_reads without a copy.  strict == 0 (and n_records == 0): the text is
+ * not in that layout and the caller must use the general parser.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct dcb_fastq_index {
+    uint64_t n_records;
+    uint64_t* name_off; uint32_t* name_len;
+    uint64_t* seq_off;  uint32_t* seq_len;
+    uint64_t* qual_off; uint32_t* qual_len;
+    int32_t strict;
+} dcb_fastq_index;
+int dcb_fastq_index_build(const char* text, uint64_t n_bytes, int n_threads, dcb_fastq_index** out);
+void dcb_fastq_index_free(dcb_fastq_index*);
+/* Number of the n byte ranges (off[i], len[i]) of text that contain `symbol` (the barcode "N" count,
+   decombine.py:985-989). */
+uint64_t dcb_count_ranges_with(const char* text, const uint64_t* off, const uint32_t* len, uint64_t n, int symbol,
+                               int n_threads);
+
 /* Inverse of the packer for one read (tests): writes len chars, exceptions as 'N' / '?'. */
 int dcb_unpack_read(const dcb_packed*, uint64_t i, char* dst, uint32_t cap);
 

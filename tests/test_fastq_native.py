@@ -1,0 +1,95 @@
+"""CPU-only: the native FASTQ record index (csrc/fastq.cpp, dcb_fastq_index_build) against the general parser, which
+keeps the reference's readfq semantics (decombine.py:228-265): same records on strict four-line files, and a clean
+hand-over ("not strict") for everything whose handling depends on readfq's quirks."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from decombinator_b200 import _lib, fastq
+
+
+def _args(path, bc_read="R2", bclength=42, sampling=False, python_fastq=False):
+    return {"infile": str(path), "bc_read": bc_read, "bclength": bclength, "sampling_analysis": sampling,
+            "python_fastq": python_fastq}
+
+
+def _write_pair(tmp_path, recs1, recs2, gz=False, tail="\n"):
+    def text(recs):
+        return "".join("@%s\n%s\n+\n%s%s" % (n, s, q, "\n") for n, s, q in recs)[:-1] + tail
+    p1, p2 = tmp_path / ("s_1.fq" + (".gz" if gz else "")), tmp_path / ("s_2.fq" + (".gz" if gz else ""))
+    op = gzip.open if gz else open
+    with op(p1, "wt") as fh:
+        fh.write(text(recs1))
+    with op(p2, "wt") as fh:
+        fh.write(text(recs2))
+    return p1
+
+
+def _columns(batch):
+    return {k: list(getattr(batch, k)) for k in ("ids", "vdj", "vdjqual", "bc", "bcq", "v_tail")}
+
+
+def _random_records(rng, n, lo=30, hi=80, names=None):
+    out = []
+    for i in range(n):
+        L = int(rng.integers(lo, hi))
+        seq = "".join(rng.choice(list("ACGTN"), L, p=[0.24, 0.24, 0.24, 0.24, 0.04]))
+        qual = "".join(rng.choice(list("#,:F@+>I"), L))          # quality lines may start with '@', '+', '>'
+        name = (names[i] if names else "SYN:%d extra words 1:N:0" % i)
+        out.append((name, seq, qual))
+    return out
+
+
+@pytest.mark.parametrize("bc_read,gz,sampling", [("R2", False, False), ("R2", True, True), ("R1", False, True), ("R1", True, False)])
+def test_native_index_matches_general_parser(tmp_path, bc_read, gz, sampling):
+    rng = np.random.default_rng(3)
+    recs1 = _random_records(rng, 501)
+    recs2 = _random_records(rng, 480)                             # the shorter file ends the zip
+    recs1[7] = ("", "ACGT", "FFFF")                               # empty name
+    recs1[9] = ("name_without_space", "", "")                     # empty read
+    recs2[11] = ("x y", "ACG", "FFFFFF")                          # quality longer than the sequence
+    p1 = _write_pair(tmp_path, recs1, recs2, gz=gz)
+    opener = gzip.open if gz else open
+    for bl in (0, 6, 42, 100):
+        native = fastq.load_pairs_native(_args(p1, bc_read, bl, sampling), opener)
+        assert native is not None
+        general = fastq.load_pairs(_args(p1, bc_read, bl, sampling, python_fastq=True), opener)
+        assert _columns(native) == _columns(general)
+        assert np.array_equal(native.len, general.len)
+        got = [bytes(native.buf[o:o + n]) for o, n in zip(native.off.tolist(), native.len.tolist())]
+        want = [bytes(general.buf[o:o + n]) for o, n in zip(general.off.tolist(), general.len.tolist())]
+        assert got == want
+        assert fastq.count_containing(native.bc, "N") == fastq.count_containing(general.bc, "N")
+        part = native.shard(100, 150)
+        assert list(part.vdj) == list(general.vdj)[100:150] and len(part) == 50
+
+
+@pytest.mark.parametrize("text", [
+    "",                                                           # empty
+    "@a\nACGT\n+\nFFFF",                                          # last line not terminated (readfq drops its last char)
+    "@a\r\nACGT\r\n+\r\nFFFF\r\n",                                # CRLF
+    "@a\nAC\nGT\n+\nFFFF\n",                                      # multi-line sequence
+    "@a\nACGT\n+\nFF\nFF\n",                                      # multi-line quality
+    ">a\nACGT\n>b\nACGT\n",                                       # FASTA records
+    "@a\nACGT\n+\nFFFF\n@b\nACGT\n+\n",                           # partial last record
+    "@a\n+CGT\n+\nFFFF\n",                                        # sequence line that readfq takes for a marker
+    "@a\nACGT\n+\nFFFF\n\n@b\nACGT\n+\nFFFF\n",                   # blank line between records
+    "@a\nAC\xc3\xa9T\n+\nFFFFF\n",                                # non-ASCII
+])
+def test_non_strict_layouts_are_handed_over(text):
+    assert _lib.fastq_index(text.encode("latin-1")) is None
+
+
+def test_tiny_files_of_the_reference(tmp_path):
+    """The reference's own test files (bundled copy used by the golden tests) are strict and index identically."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    cands = [os.path.join(here, "golden", "TINY_1.fq"), os.path.join(here, "golden", "TINY_1.fq.gz")]
+    path = next((c for c in cands if os.path.exists(c)), None)
+    if path is None:
+        pytest.skip("TINY_1.fq not bundled")
+    opener = gzip.open if path.endswith(".gz") else open
+    native = fastq.load_pairs_native(_args(path), opener)
+    general = fastq.load_pairs(_args(path, python_fastq=True), opener)
+    assert native is not None and _columns(native) == _columns(general)

@@ -9,7 +9,7 @@ if [ "$1" == "build" ]; then
   shift; mkdir -p build
   while [ $# -ge 2 ]; do
     /usr/local/cuda/bin/nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-O3 -shared $2 \
-      -I include -o build/var_$1.so $CS/decombine.cu $CS/collapse.cu $CS/tagset.cpp $CS/pack.cpp $CS/synth.cpp $CS/error.cpp -lpthread &
+      -I include -o build/var_$1.so $CS/decombine.cu $CS/collapse.cu $CS/tagset.cpp $CS/pack.cpp $CS/fastq.cpp $CS/synth.cpp $CS/error.cpp -lpthread &
     shift 2
   done
   wait; ls -la build/
