@@ -79,6 +79,10 @@ def lib():
     L.dcb_fastq_index_free.restype = None
     L.dcb_count_ranges_with.argtypes = [vp, vp, vp, u64, i32, i32]
     L.dcb_count_ranges_with.restype = u64
+    L.dcb_format_rows.argtypes = [vp, u64, i32] + [ctypes.POINTER(CColumn)] * 6 + [ctypes.c_char_p, i32,
+                                  ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(u64), ctypes.POINTER(u64)]
+    L.dcb_buffer_free.argtypes = [ctypes.c_void_p]
+    L.dcb_buffer_free.restype = None
     L.dcb_pack_reads.argtypes = [vp, vp, vp, u64, i32, i32, ctypes.POINTER(ctypes.POINTER(CPacked))]
     L.dcb_packed_free.argtypes = [ctypes.POINTER(CPacked)]
     L.dcb_unpack_read.argtypes = [ctypes.POINTER(CPacked), u64, ctypes.c_char_p, u32]
@@ -244,6 +248,36 @@ class Packed:
             self.free()
         except Exception:
             pass
+
+
+class CColumn(ctypes.Structure):
+    _fields_ = [("text", ctypes.c_void_p), ("off", ctypes.c_void_p), ("len", ctypes.c_void_p)]
+
+
+def format_rows(res, packed_revcomp, columns, sep, n_threads=None):
+    """dcb_format_rows: the rows of every decombined read as one text buffer (fields joined by sep, one row per line).
+
+    columns: (ids, vdj, vdjqual, bc, bcq, v_tail-or-None), each an object with .buf (bytes), .off (uint64), .len (uint32).
+    -> (bytes, number of rows)"""
+    keep, cols = [], []
+    for col in columns:
+        if col is None:
+            cols.append(None)
+            continue
+        buf = np.frombuffer(col.buf, dtype=np.uint8)
+        off = np.ascontiguousarray(col.off, dtype=np.uint64)
+        ln = np.ascontiguousarray(col.len, dtype=np.uint32)
+        keep.append((buf, off, ln))
+        cols.append(ctypes.pointer(CColumn(buf.ctypes.data, off.ctypes.data, ln.ctypes.data)))
+    res = np.ascontiguousarray(res)
+    out, nbytes, nrows = ctypes.c_void_p(), ctypes.c_uint64(), ctypes.c_uint64()
+    nt = n_threads or min(32, os.cpu_count() or 1)
+    _check(lib().dcb_format_rows(res.ctypes.data, len(res), int(bool(packed_revcomp)), *cols, sep.encode("ascii"), nt,
+                                 ctypes.byref(out), ctypes.byref(nbytes), ctypes.byref(nrows)), "dcb_format_rows")
+    try:
+        return ctypes.string_at(out.value, nbytes.value), int(nrows.value)
+    finally:
+        lib().dcb_buffer_free(out)
 
 
 class CFastqIndex(ctypes.Structure):

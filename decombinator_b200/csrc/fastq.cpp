@@ -128,3 +128,130 @@ uint64_t dcb_count_ranges_with(const char* text, const uint64_t* off, const uint
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Row assembly: the ten strings the reference builds per decombined read
+// (decombine.py:1015-1039) -- v, j, vdel, jdel, insert, read id, tcrseq, tcrQ, barcode, barcode quality
+// (+ the sampling column) -- formatted for ALL hits of a batch into one text buffer, fields joined by `sep`,
+// one row per line.  With sep = ", " the buffer IS the .n12 text of write_out_intermediate (io.py:480-513);
+// with a separator that cannot occur in the data, Python splits it into the list of rows at C speed.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Comp {
+    unsigned char t[256];
+    Comp() {   // Bio.Seq.reverse_complement's table (decombine.py:182-184), as in pack.cpp
+        const char* from = "ACGTUMRWSYKVHDBNacgtumrwsykvhdbn";
+        const char* to = "TGCAAKYWSRMBDHVNtgcaakywsrmbdhvn";
+        for (int i = 0; i < 256; i++) t[i] = (unsigned char)i;
+        for (int i = 0; from[i]; i++) t[(unsigned char)from[i]] = (unsigned char)to[i];
+    }
+};
+const Comp kComp;
+
+inline void clip(int64_t len, int64_t& a, int64_t& b) {          // Python s[a:b] for a, b >= 0
+    if (a > len) a = len;
+    if (b > len) b = len;
+    if (b < a) b = a;
+}
+inline int dec_len(unsigned v) { return v >= 10000 ? 5 : v >= 1000 ? 4 : v >= 100 ? 3 : v >= 10 ? 2 : 1; }
+inline char* put_dec(char* p, unsigned v) {
+    const int n = dec_len(v);
+    for (int i = n - 1; i >= 0; i--) { p[i] = (char)('0' + v % 10); v /= 10; }
+    return p + n;
+}
+
+struct RowCtx {
+    const dcb_result* res; int packed_rc;
+    const dcb_column *ids, *vdj, *qual, *bc, *bcq, *tail;
+    const char* sep; size_t sep_len;
+};
+
+// length of the row of read i (it decombined), or its bytes when dst != nullptr
+inline size_t row_emit(const RowCtx& c, uint64_t i, char* dst) {
+    const dcb_result& r = c.res[i];
+    const bool rev = (c.packed_rc != 0) != (r.frame != 0);
+    const int64_t n = c.vdj->len[i], nq = c.qual->len[i];
+    int64_t ia = r.ins_start, ib = r.ins_end, sa = r.v_seq_start, sb = r.j_seq_end, qa = r.v_seq_start, qb = r.j_seq_end;
+    clip(n, ia, ib); clip(n, sa, sb); clip(nq, qa, qb);
+    const size_t fixed = (size_t)dec_len(r.v) + dec_len(r.j) + dec_len(r.vdel) + dec_len(r.jdel);
+    const int nf = c.tail ? 11 : 10;
+    const size_t total = fixed + (size_t)(ib - ia) + c.ids->len[i] + (size_t)(sb - sa) + (size_t)(qb - qa) + c.bc->len[i] +
+                         c.bcq->len[i] + (c.tail ? c.tail->len[i] : 0) + (size_t)(nf - 1) * c.sep_len + 1;
+    if (!dst) return total;
+    char* p = dst;
+    auto sep = [&] { std::memcpy(p, c.sep, c.sep_len); p += c.sep_len; };
+    auto raw = [&](const dcb_column* col) { std::memcpy(p, col->text + col->off[i], col->len[i]); p += col->len[i]; };
+    const unsigned char* s = (const unsigned char*)c.vdj->text + c.vdj->off[i];
+    const char* q = c.qual->text + c.qual->off[i];
+    auto seq = [&](int64_t a, int64_t b) {                       // oriented[a:b]
+        if (rev) for (int64_t k = a; k < b; k++) *p++ = (char)kComp.t[s[n - 1 - k]];
+        else { std::memcpy(p, s + a, (size_t)(b - a)); p += b - a; }
+    };
+    p = put_dec(p, r.v); sep(); p = put_dec(p, r.j); sep(); p = put_dec(p, r.vdel); sep(); p = put_dec(p, r.jdel); sep();
+    seq(ia, ib); sep();
+    raw(c.ids); sep();
+    seq(sa, sb); sep();
+    if (rev) for (int64_t k = qa; k < qb; k++) *p++ = q[nq - 1 - k];
+    else { std::memcpy(p, q + qa, (size_t)(qb - qa)); p += qb - qa; }
+    sep();
+    raw(c.bc); sep();
+    raw(c.bcq);
+    if (c.tail) { sep(); raw(c.tail); }
+    *p++ = '\n';
+    return (size_t)(p - dst);
+}
+
+}  // namespace
+
+extern "C" {
+
+int dcb_format_rows(const dcb_result* res, uint64_t n, int packed_revcomp, const dcb_column* ids, const dcb_column* vdj,
+                    const dcb_column* vdjqual, const dcb_column* bc, const dcb_column* bcq, const dcb_column* v_tail,
+                    const char* sep, int n_threads, char** out, uint64_t* out_bytes, uint64_t* n_rows) {
+    if (!out || !out_bytes || !n_rows || !sep || (n && (!res || !ids || !vdj || !vdjqual || !bc || !bcq))) {
+        dcb_set_error("dcb_format_rows: null argument");
+        return DCB_EINVAL;
+    }
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 64) n_threads = 64;
+    RowCtx c;
+    c.res = res; c.packed_rc = packed_revcomp; c.ids = ids; c.vdj = vdj; c.qual = vdjqual; c.bc = bc; c.bcq = bcq; c.tail = v_tail;
+    c.sep = sep; c.sep_len = std::strlen(sep);
+    // contiguous read ranges per thread: sizes, then bytes, rows staying in read order
+    std::vector<uint64_t> bytes(n_threads + 1, 0), rows(n_threads + 1, 0);
+    const int nt = (n < 4096) ? 1 : n_threads;
+    auto range = [&](int t, uint64_t& a, uint64_t& b) { a = n * (uint64_t)t / nt; b = n * (uint64_t)(t + 1) / nt; };
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++)
+            th.emplace_back([&, t] {
+                uint64_t a, b, sz = 0, nr = 0;
+                range(t, a, b);
+                for (uint64_t i = a; i < b; i++) if (res[i].status) { sz += row_emit(c, i, nullptr); nr++; }
+                bytes[t + 1] = sz; rows[t + 1] = nr;
+            });
+        for (auto& x : th) x.join();
+    }
+    for (int t = 0; t < nt; t++) { bytes[t + 1] += bytes[t]; rows[t + 1] += rows[t]; }
+    char* buf = (char*)std::malloc(bytes[nt] + 1);
+    if (!buf) { dcb_set_error("dcb_format_rows: out of memory"); return DCB_ENOMEM; }
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++)
+            th.emplace_back([&, t] {
+                uint64_t a, b;
+                range(t, a, b);
+                char* p = buf + bytes[t];
+                for (uint64_t i = a; i < b; i++) if (res[i].status) p += row_emit(c, i, p);
+            });
+        for (auto& x : th) x.join();
+    }
+    buf[bytes[nt]] = 0;
+    *out = buf; *out_bytes = bytes[nt]; *n_rows = rows[nt];
+    return DCB_OK;
+}
+
+void dcb_buffer_free(char* p) { std::free(p); }
+
+}  // extern "C"

@@ -105,6 +105,22 @@ def dcr(read, inputargs):
             int(r["v_seq_start"]), int(r["j_seq_end"])]
 
 
+class RowsText:
+    """The rows of a run as the text write_out_intermediate would produce from them (", " between fields, one row per
+    line): what `decombinator decombine` hands to the writer instead of a list of lists when nothing else reads them."""
+
+    __slots__ = ("text", "n_rows")
+
+    def __init__(self, text: bytes, n_rows: int):
+        self.text, self.n_rows = text, n_rows
+
+    def __len__(self):
+        return self.n_rows
+
+    def rows(self):
+        return [line.split(", ") for line in self.text.decode("ascii").split("\n")[:-1]]
+
+
 def decombine_batch(batch: fastq.ReadBatch, inputargs):
     """GPU pass over every V(D)J read of the batch -> dcb_result array (one record per read)."""
     pack_rc, both = _orientation_plan(inputargs["orientation"])
@@ -191,6 +207,22 @@ def decombinator(inputargs: dict) -> list:
         hits = np.nonzero(res["status"])[0]
         counts["vj_count"] += int(len(hits))
         sampling = inputargs.get("sampling_analysis")
+        if isinstance(batch.vdj, fastq.TextColumn) and len(hits):
+            # native ingest: the rows are formatted by dcb_format_rows (all hits, multi-threaded) into one buffer whose
+            # field separator cannot occur in the data, and split here at C speed
+            sep = "\x1f"
+            cols = (batch.ids, batch.vdj, batch.vdjqual, batch.bc, batch.bcq, batch.v_tail if sampling else None)
+            if inputargs.get("rows_as_text"):
+                # the `decombine` command only writes the rows: with the .n12 separator the buffer IS the file's text
+                blob, nrows = _lib.format_rows(res, pack_rc, cols, ", ")
+                assert nrows == len(hits)
+                outdata = RowsText(blob, nrows)
+                hits = ()
+            elif not any(sep.encode() in c.buf for c in {id(c.buf): c for c in cols if c is not None}.values()):
+                blob, nrows = _lib.format_rows(res, pack_rc, cols, sep)
+                outdata = [line.split(sep) for line in blob.decode("ascii").split("\n")[:-1]]
+                assert len(outdata) == nrows == len(hits)
+                hits = ()
         for i in hits:
             r = res[i]
             # frame "reverse" <=> the analysed string was revcomp(vdj) (decombine.py:1015-1020)

@@ -130,8 +130,12 @@ def intermediate_filename(inputargs: dict, suffix: str) -> str:
 def write_out_intermediate(data: list, inputargs: dict, suffix: str):
     """``.n12`` / ``.freq`` writer: ``", ".join(map(str, row)) + "\\n"`` per row, gzip unless -dz (io.py:480-513)."""
     outfilename = intermediate_filename(inputargs, suffix)
-    with open(outfilename, "w") as outfile:
-        outfile.writelines(", ".join(map(str, line)) + "\n" for line in data)
+    if hasattr(data, "text"):     # decombine.RowsText: the rows already formatted natively (dcb_format_rows)
+        with open(outfilename, "wb") as outfile:
+            outfile.write(data.text)
+    else:
+        with open(outfilename, "w") as outfile:
+            outfile.writelines(", ".join(map(str, line)) + "\n" for line in data)
     if not inputargs["dontgzip"]:
         print("Compressing intermediate output file to", outfilename + ".gz")
         with open(outfilename) as infile, gzip.open(outfilename + ".gz", "wt") as outfile:

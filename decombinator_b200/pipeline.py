@@ -59,6 +59,7 @@ def main():
         if multi:
             data = parallel.decombinator_sharded(inputargs)
         else:
+            inputargs["rows_as_text"] = True      # nothing reads the rows but the .n12 writer
             data = decombinator(inputargs)
         if rank == 0:
             write_out_intermediate(data, inputargs, ".n12")

@@ -164,6 +164,20 @@ typedef struct dcb_result {
     uint16_t j_seq_end;    /* recom[6] */
 } dcb_result;
 
+/* One string per read as (offset, length) into a text buffer (a column of the FASTQ index above). */
+typedef struct dcb_column { const char* text; const uint64_t* off; const uint32_t* len; } dcb_column;
+
+/* Row assembly of the reference's main loop (decombine.py:1015-1039) for every read with status 1, in read
+ * order: v, j, vdel, jdel, insert, read id, tcrseq, tcrQ, barcode, barcode quality (+ v_tail when given), fields
+ * joined by `sep`, one row per line, into ONE malloc'ed buffer (free with dcb_buffer_free).  packed_revcomp:
+ * the batch was packed as the reverse complement (-or reverse / both); a result of frame 1 is the other strand.
+ * With sep = ", " the buffer is the .n12 text of write_out_intermediate (io.py:480-513). */
+int dcb_format_rows(const dcb_result* res, uint64_t n, int packed_revcomp, const dcb_column* ids, const dcb_column* vdj,
+                    const dcb_column* vdjqual, const dcb_column* bc, const dcb_column* bcq, const dcb_column* v_tail,
+                    const char* sep, int n_threads, char** out, uint64_t* out_bytes, uint64_t* n_rows);
+void dcb_buffer_free(char*);
+
+
 typedef struct dcb_params {
     int32_t both_frames;   /* -or both: retry the reverse complement of the packed read when the first try fails
                               (decombine.py:1005-1010); reads are then packed in the FIRST orientation tried */

@@ -18,13 +18,19 @@ def _args(infile, chain, outdir, **kw):
 
 
 @gpu
+@pytest.mark.parametrize("mode", ["native", "rows_as_text", "python_fastq"])
 @pytest.mark.parametrize("chain,name", [("a", "alpha"), ("b", "beta")])
-def test_tiny_golden_n12_bytes(golden_dir, tmp_path, chain, name):
-    """reference tests/test_pipeline.py:63-84 / test_subparsers.py:27-47: the .n12 must be byte-identical."""
+def test_tiny_golden_n12_bytes(golden_dir, tmp_path, chain, name, mode):
+    """reference tests/test_pipeline.py:63-84 / test_subparsers.py:27-47: the .n12 must be byte-identical -- through
+    the native ingest + row formatter (list of rows), through the text hand-over of the `decombine` command, and
+    through the general (Python) parser and row assembly."""
     for f in ("TINY_1.fq", "TINY_2.fq"):
         shutil.copy(os.path.join(golden_dir, f), tmp_path / f)
     args = _args(str(tmp_path / "TINY_1.fq"), chain, tmp_path)
+    if mode != "native":
+        args[mode] = True
     rows = decombine.decombinator(args)
+    assert isinstance(rows, decombine.RowsText) == (mode == "rows_as_text")
     io.write_out_intermediate(rows, args, ".n12")
     out = tmp_path / ("dcr_TINY_1_%s.n12" % name)
     assert out.read_bytes() == open(os.path.join(golden_dir, "dcr_TINY_1_%s.n12" % name), "rb").read()
@@ -46,10 +52,16 @@ def test_recorded_reference_runs(decombinator_runs, tmp_path):
         (tmp_path / os.path.basename(a["infile"]).replace("1.f", "2.f")).write_text(run["fastq2"])
         a["infile"] = str(f1)
         a["tagfastadir"] = "Decombinator-Tags-FASTAs"
-        rows = decombine.decombinator(a)
-        assert rows == run["rows"], ri
-        got = {k: int(v) for k, v in decombine.counts.items() if k not in ("start_time", "end_time")}
-        assert got == run["counts"], (ri, got, run["counts"])
+        for mode in ("native", "python_fastq", "rows_as_text"):   # the three host paths around the same kernels
+            b = dict(a)
+            if mode != "native":
+                b[mode] = True
+            rows = decombine.decombinator(b)
+            if mode == "rows_as_text" and not isinstance(rows, list):
+                rows = rows.rows()
+            assert rows == run["rows"], (ri, mode)
+            got = {k: int(v) for k, v in decombine.counts.items() if k not in ("start_time", "end_time")}
+            assert got == run["counts"], (ri, mode, got, run["counts"])
 
 
 @gpu

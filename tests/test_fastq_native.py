@@ -93,3 +93,60 @@ def test_tiny_files_of_the_reference(tmp_path):
     native = fastq.load_pairs_native(_args(path), opener)
     general = fastq.load_pairs(_args(path, python_fastq=True), opener)
     assert native is not None and _columns(native) == _columns(general)
+
+
+@pytest.mark.parametrize("pack_rc", [True, False])
+@pytest.mark.parametrize("with_tail", [True, False])
+def test_format_rows_matches_the_reference_row_assembly(pack_rc, with_tail):
+    """dcb_format_rows against the literal row assembly of the main loop (decombine.py:1015-1039): both strands,
+    IUPAC / lower-case symbols through the reverse complement, quality lines longer than their read, slices that run
+    past the end."""
+    from decombinator_b200.decombine import revcomp
+    rng = np.random.default_rng(1)
+    n = 3000
+    text = bytearray()
+    cols = {k: ([], []) for k in ("ids", "vdj", "q", "bc", "bcq", "tail")}
+
+    def add(col, s):
+        cols[col][0].append(len(text)); cols[col][1].append(len(s))
+        text.extend(s.encode()); text.extend(b"\n")
+
+    for i in range(n):
+        L = int(rng.integers(20, 120))
+        add("ids", "R%d" % i)
+        add("vdj", "".join(rng.choice(list("ACGTNacgtRYKMbdhv"), L)))
+        add("q", "".join(rng.choice(list("FI#,:"), L + int(rng.integers(0, 3)))))
+        add("bc", "".join(rng.choice(list("ACGTN"), 12)))
+        add("bcq", "F" * 12)
+        add("tail", "".join(rng.choice(list("ACGT"), int(rng.integers(0, 31)))))
+    data = bytes(text)
+    C = {k: fastq.TextColumn(data, np.array(v[0], np.uint64), np.array(v[1], np.uint32)) for k, v in cols.items()}
+    res = np.zeros(n, dtype=_lib.RESULT_DTYPE)
+    for i in range(n):
+        L = int(C["vdj"].len[i])
+        a = int(rng.integers(0, L)); b = int(rng.integers(a, L + 5))
+        ia = int(rng.integers(a, max(a + 1, b)))
+        res[i] = (rng.random() < 0.7, rng.integers(0, 2), rng.integers(0, 200), rng.integers(0, 99), 0, rng.integers(0, 30000),
+                  rng.integers(0, 12), ia, int(rng.integers(ia, b + 1)) if b >= ia else ia, a, b)[:len(res.dtype.names)] \
+            if False else res[i]
+        res[i]["status"] = rng.random() < 0.7; res[i]["frame"] = rng.integers(0, 2)
+        res[i]["v"] = rng.integers(0, 200); res[i]["j"] = rng.integers(0, 99)
+        res[i]["vdel"] = rng.integers(0, 30000); res[i]["jdel"] = rng.integers(0, 12)
+        res[i]["v_seq_start"] = a; res[i]["j_seq_end"] = b
+        res[i]["ins_start"] = ia; res[i]["ins_end"] = int(rng.integers(ia, b + 1)) if b >= ia else ia
+    blob, nrows = _lib.format_rows(res, pack_rc, (C["ids"], C["vdj"], C["q"], C["bc"], C["bcq"], C["tail"] if with_tail else None), ", ")
+    want = []
+    for i in np.nonzero(res["status"])[0]:
+        r = res[i]
+        is_rev = pack_rc != bool(r["frame"])
+        a, b = int(r["v_seq_start"]), int(r["j_seq_end"])
+        vdj, q = C["vdj"][i], C["q"][i]
+        o = revcomp(vdj) if is_rev else vdj
+        row = [str(int(r["v"])), str(int(r["j"])), str(int(r["vdel"])), str(int(r["jdel"])),
+               o[int(r["ins_start"]):int(r["ins_end"])], C["ids"][i], o[a:b], (q[::-1][a:b] if is_rev else q[a:b]),
+               C["bc"][i], C["bcq"][i]]
+        if with_tail:
+            row.append(C["tail"][i])
+        want.append(", ".join(row) + "\n")
+    assert blob.decode() == "".join(want)
+    assert nrows == len(want)
