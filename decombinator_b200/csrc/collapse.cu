@@ -250,10 +250,21 @@ int dcb_lev_leq(dcb_dist* d, const uint8_t* symbols, const uint64_t* off, const 
     CUDA_TRY(cudaMemcpyAsync(d_a, a, n_pairs * 4, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(d_b, b, n_pairs * 4, cudaMemcpyHostToDevice, s));
     const unsigned long long blocks = (n_pairs + 127) / 128;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaEventRecord(e0, s));
     dcb_lev_leq_kernel<<<(unsigned)blocks, 128, 0, s>>>(d_sym, d_off, d_len, d_a, d_b, n_pairs, frac, d_ver);
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(e1, s));
     CUDA_TRY(cudaMemcpyAsync(verdict, d_ver, n_pairs, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
+    {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) d->last_ms = ms;   // kernel time of this call (dcb_dist_last_ms)
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
     cudaFree(d_sym); cudaFree(d_off); cudaFree(d_len); cudaFree(d_a); cudaFree(d_b); cudaFree(d_ver);
     return DCB_OK;
 }
