@@ -428,21 +428,6 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
     asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
-    uint32_t v;
-    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
-    uint2 v;
-    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ int bfind_u32(uint32_t x) {               // index of the highest set bit, as FLO delivers it
-    int v;
-    asm("bfind.u32 %0, %1;" : "=r"(v) : "r"(x));
-    return v;
-}
 template <int OFF>
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t v;
@@ -463,7 +448,8 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
                       uint32_t* __restrict__ queue_count) {
     static_assert(S == 8, "seeds start at half-word boundaries");
     constexpr int NPOS = (16 * NW - Q) / S + 1;
-    static_assert(NPOS <= 32, "one hit word");
+    constexpr int NA = NPOS < 32 ? NPOS : 32, NB = NPOS - NA;        // probes in the first / second hit word
+    static_assert(NB <= 32, "two hit words");
     static_assert(S + Q - 1 <= 32 - WLEAD_OF(S), "the lmin-prefix at every candidate offset lies inside the window");
     constexpr int WLEAD = S - 1;                                     // the verification window starts at the earliest possible tag start
     constexpr int WMAX = ((NPOS - 1) * S - WLEAD) >> 4;
@@ -534,16 +520,23 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
         // 1. probe: bit NPOS-1-i of h <=> the seed at i * S may be indexed.  The slot must hash the WHOLE seed: reads are
         //    full of 8-mers that homologous genes share with a tag (measured: slot = the seed's first 8 bases costs 0.8
         //    trips more than it saves in probe instructions).  Even probes are word-aligned (no extraction).
-        uint32_t h = 0;
+        //    Probe i < NA is bit NA-1-i of h, probe i >= NA (reads longer than 256 nt) bit NPOS-1-i of hb.
+        uint32_t h = 0, hb = 0;
 #pragma unroll
         for (int i = 0; i < NPOS; i++) {
             const uint32_t win = (i & 1) ? __funnelshift_r(w[i >> 1], (i >> 1) + 1 < NW ? w[(i >> 1) + 1] : 0u, 16) : w[i >> 1];
-            h = mad2(h, lds_u8(filt + ((win * FMUL) >> (32 - DCB_FBITS))));
+            const uint32_t byte = lds_u8(filt + ((win * FMUL) >> (32 - DCB_FBITS)));
+            if (i < NA) h = mad2(h, byte);
+            else hb = mad2(hb, byte);
         }
         {
             const int nvalid = r.n >= Q ? (r.n - Q) / S + 1 : 0;     // probes whose seed lies inside the read
-            if (nvalid < NPOS) h &= ~((1u << (NPOS - nvalid)) - 1u);
-            if (!scan) h = 0;
+            if (nvalid < NA) h &= ~((1u << (NA - nvalid)) - 1u);
+            if (NB > 0) {
+                const int nvb = nvalid > NA ? nvalid - NA : 0;
+                if (nvb < NB) hb &= ~((1u << (NB - nvb)) - 1u);
+            }
+            if (!scan) { h = 0; hb = 0; }
         }
         // this lane's column is read back below by this lane only: program order suffices, no barrier
 #ifndef DCB_VAR_PREFETCH
@@ -567,117 +560,19 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
         // 2. confirm, one (hit, offset) candidate per trip
         HitWords hw;
         hw.v = 0; hw.j = 0; hw.n_v = ix.n_v;
-#ifdef DCB_VAR_PIPE
-        // Software-pipelined and branch-free on its main path: a trip checks one offset of the CURRENT hit while the NEXT
-        // hit is popped (window + offset set), two independent dependency chains for the scheduler to interleave.  Lanes
-        // without work run the same instructions on harmless inputs (every shared-memory index stays in range; a match
-        // is only ever recorded for real read bases at a real position, and only when the lane had an offset to check).
-        uint32_t offs = 0, wlo = 0, whi = 0, noffs = 0, nwlo = 0, nwhi = 0;
-        int p = 0, np = 0;
-        auto pop = [&](uint32_t hh, uint32_t& o_, uint32_t& lo_, uint32_t& hi_, int& p_, uint32_t& hnew) {
-            const int bit = 31 - __clz(hh);
-            const int wb = 2 * (S * (NPOS - 1) - WLEAD) - 2 * S * bit;
-            const uint32_t a0 = col_addr - (T * 4) + (uint32_t)(((NPOS - bit) >> 1) * (T * 4));
-            const uint32_t x = lds_u32<0>(a0), y = lds_u32<T * 4>(a0), zz = lds_u32<2 * T * 4>(a0);
-            lo_ = __funnelshift_r(x, y, wb);
-            hi_ = __funnelshift_r(y, zz, wb);
-            p_ = (wb >> 1) + WLEAD;
-            o_ = q_offsets(ix, __funnelshift_r(lo_, hi_, 2 * WLEAD));
-            hnew = hh & ~(1u << (bit & 31));
-        };
-        if (h) { uint32_t hn; pop(h, noffs, nwlo, nwhi, np, hn); h = hn; }
-        for (;;) {
-            if (offs == 0u) { offs = noffs; wlo = nwlo; whi = nwhi; p = np; noffs = 0u; }
-            if (!__any_sync(0xFFFFFFFFu, (offs | h) != 0u)) break;
-            // next hit
-            {
-                uint32_t o2, lo2, hi2, hn; int p2;
-                pop(h, o2, lo2, hi2, p2, hn);
-                const bool need = noffs == 0u && h != 0u;
-                noffs = need ? o2 : noffs; nwlo = need ? lo2 : nwlo; nwhi = need ? hi2 : nwhi; np = need ? p2 : np;
-                h = need ? hn : h;
-            }
-            // one offset of the current hit
-            {
-                const bool have = offs != 0u;
-                const int o = 31 - __clz(offs);
-                offs = have ? offs ^ (1u << (o & 31)) : 0u;
-                const int P = p - o;
-                const int sh = 2 * (WLEAD - o);
-                const uint32_t lo = __funnelshift_r(wlo, whi, sh), hi = whi >> (sh & 31);
-                const uint32_t hp = hi & ((1u << DCB_TQ_HIBITS(S + Q - 1)) - 1u);
-                const DcbTq e = ix.tq[(lo * ix.ta + hp * ix.tb) >> ix.tqshift];
-                if (have && e.x == lo && ((hp ^ e.y) & DCB_TQ_CMPMASK(S + Q - 1)) == 0u && P >= 0) {
-                    if (!(e.y & DCB_TQ_MORE)) {
-                        if (P + (int)DCB_TQ_LEN(e.y) <= r.n) hw(DCB_TQ_CTAG(e.y), P);
-                    } else {
-                        q_check_offset<true>(r, ix, p, o, wlo, whi, hw);   // whole-tag compare / chain walk
-                    }
-                    if (hw.v == DCB_HIT_MULTI) { h = 0u; offs = 0u; noffs = 0u; }
-                }
-            }
-        }
-#elif defined(DCB_VAR_TRIM)
-        // hand-trimmed form of the loop below: FLO results used as they come (bfind), separate table bases, the
-        // prefix compare folded into two logic ops, the hit words updated by predicated moves inside the match branch
-        uint32_t offs = 0, wlo = 0, whi = 0;
-        int p = 0;
-        const uint32_t disp_addr = smem_u32(ix.disp), offs_addr = smem_u32(ix.offs), tq_addr = smem_u32(ix.tq);
-        for (;;) {
-            const bool need = offs == 0u && h != 0u;
-            if (!__any_sync(0xFFFFFFFFu, need || offs != 0u)) break;
-            if (need) {
-                const int bit = bfind_u32(h);                        // probe i = NPOS - 1 - bit
-                h ^= 1u << bit;
-                const int wb = 2 * (S * (NPOS - 1) - WLEAD) - 2 * S * bit;
-                p = (S * (NPOS - 1)) - S * bit;
-                const uint32_t a0 = col_addr - (T * 4) + (uint32_t)(((NPOS - bit) >> 1) * (T * 4));
-                const uint32_t x = lds_u32<0>(a0), y = lds_u32<T * 4>(a0), zz = lds_u32<2 * T * 4>(a0);
-                wlo = __funnelshift_r(x, y, wb);                     // the shift wraps modulo 32
-                whi = __funnelshift_r(y, zz, wb);
-                const uint32_t key = __funnelshift_r(wlo, whi, 2 * WLEAD);
-                const uint32_t d = lds_u16(disp_addr + 2u * ((key * ix.m1) >> ix.s1));
-                offs = lds_u16(offs_addr + 2u * ((((key * ix.m2) >> ix.s2) + d) & ix.mask2));
-            }
-            if (offs) {
-                const int o = bfind_u32(offs);
-                offs ^= 1u << o;
-                const int P = p - o;
-                const int sh = 2 * WLEAD - 2 * o;
-                const uint32_t lo = __funnelshift_r(wlo, whi, sh), hi = whi >> sh;
-                const uint32_t hp = hi & ((1u << DCB_TQ_HIBITS(S + Q - 1)) - 1u);
-                const uint2 e = lds_u64(tq_addr + 8u * ((lo * ix.ta + hp * ix.tb) >> ix.tqshift));
-                if (((((hp ^ e.y) & DCB_TQ_CMPMASK(S + Q - 1)) | (lo ^ e.x)) == 0u) && P >= 0) {
-                    if (!(e.y & DCB_TQ_MORE)) {
-                        if (P + (int)DCB_TQ_LEN(e.y) <= r.n) {
-                            const uint32_t ctag = DCB_TQ_CTAG(e.y);
-                            const uint32_t c = ctag * 65536u + ((uint32_t)P + DCB_HIT_ONE);
-                            if ((int)ctag >= ix.n_v) hw.j = hit_merge(hw.j, c);
-                            else {
-                                hw.v = hit_merge(hw.v, c);
-                                if (hw.v == DCB_HIT_MULTI) { h = 0u; offs = 0u; }   // final (decombine.py:278-280)
-                            }
-                        }
-                    } else {
-                        q_check_offset<true>(r, ix, p, o, wlo, whi, hw);   // whole-tag compare / chain walk
-                        if (hw.v == DCB_HIT_MULTI) { h = 0u; offs = 0u; }
-                    }
-                }
-            }
-        }
-#else
         uint32_t offs = 0, wlo = 0, whi = 0;
         int p = 0;
         for (;;) {
-            const bool need = offs == 0u && h != 0u;
+            const bool need = offs == 0u && (h | hb) != 0u;
             if (!__any_sync(0xFFFFFFFFu, need || offs != 0u)) break;
             if (need) {
-                const int bit = 31 - __clz(h);                       // probe i = NPOS - 1 - bit
-                h ^= 1u << bit;
-                // bit position of the window start i * S - WLEAD as ONE multiply-add; its word row is (i - 1) >> 1
-                const int wb = 2 * (S * (NPOS - 1) - WLEAD) - 2 * S * bit;
-                p = (wb >> 1) + WLEAD;
-                const uint32_t a0 = col_addr - (T * 4) + (uint32_t)(((NPOS - bit) >> 1) * (T * 4));
+                int i;                                               // the probe popped: lowest position first
+                if (NB == 0 || h) { const int bit = 31 - __clz(h); h ^= 1u << bit; i = NA - 1 - bit; }
+                else { const int bit = 31 - __clz(hb); hb ^= 1u << bit; i = NPOS - 1 - bit; }
+                // bit position of the window start i * S - WLEAD; its word row is (i - 1) >> 1
+                const int wb = 2 * (S * i - WLEAD);
+                p = S * i;
+                const uint32_t a0 = col_addr - (T * 4) + (uint32_t)(((i + 1) >> 1) * (T * 4));
                 const uint32_t x = lds_u32<0>(a0), y = lds_u32<T * 4>(a0), zz = lds_u32<2 * T * 4>(a0);
                 wlo = __funnelshift_r(x, y, wb);                     // the shift wraps modulo 32
                 whi = __funnelshift_r(y, zz, wb);
@@ -687,10 +582,9 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
                 const int o = 31 - __clz(offs);
                 offs ^= 1u << o;
                 q_check_offset<true>(r, ix, p, o, wlo, whi, hw);
-                if (hw.v == DCB_HIT_MULTI) { h = 0u; offs = 0u; }    // final whatever else is found (decombine.py:278-280)
+                if (hw.v == DCB_HIT_MULTI) { h = 0u; hb = 0u; offs = 0u; }   // final whatever else is found (decombine.py:278-280)
             }
         }
-#endif
         FullHit vh, jh;
         hw.decode(vh, jh);
         if (scan) action = dcr_fast_from_hits<true>(r, vtags, jtags, vh, jh, prm, both_frames, out, s_cnt);
@@ -877,7 +771,7 @@ static exact_spec_fn pick_spec(int nw, int qv, int sv, int lminv, int qj, int sj
 #undef DCB_SPEC
 }
 // Flat kernel: chains whose V and J tags share one index with 20-nt minimum tags (13-mer seeds at stride 8), read slots
-// up to 16 words (its hit mask is one word).
+// up to 20 words (320 nt: two hit words).
 typedef void (*exact_q_fn)(BatchDev, QTables, DcrParams, int, dcb_result*, unsigned long long*, uint32_t*, uint32_t*);
 static constexpr int kQThreads = 1024;
 static exact_q_fn pick_q(int nw, int qq, int qs, int lmin) {
@@ -886,6 +780,7 @@ static exact_q_fn pick_q(int nw, int qq, int qs, int lmin) {
         case 8:  return dcb_exact_kernel_flat<8, 13, 8, kQThreads>;
         case 12: return dcb_exact_kernel_flat<12, 13, 8, kQThreads>;
         case 16: return dcb_exact_kernel_flat<16, 13, 8, kQThreads>;
+        case 20: return dcb_exact_kernel_flat<20, 13, 8, kQThreads>;
         default: return nullptr;
     }
 }

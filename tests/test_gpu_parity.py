@@ -44,6 +44,8 @@ def test_cuda_matches_reference_fixtures(dcr_cases, force_general):
     ("human", "extended", "b", "reverse", 250, 0.01, 0.001, 0.05),   # configs[2] shape (beta half)
     ("human", "extended", "a", "reverse", 250, 0.01, 0.001, 0.05),   # configs[2] shape (alpha half)
     ("human", "extended", "a", "both", 150, 0.01, 0.001, 0.05),
+    ("human", "extended", "b", "reverse", 300, 0.005, 0.0005, 0.05),  # 20-word slots: the flat kernel's two hit words
+    ("human", "extended", "a", "both", 310, 0.0, 0.0, 0.02),
     ("human", "original", "b", "forward", 300, 0.02, 0.002, 0.05),
     ("human", "original", "a", "reverse", 100, 0.01, 0.0, 0.0),
     ("mouse", "original", "g", "reverse", 250, 0.005, 0.0, 0.02),    # configs[4] shape
@@ -127,7 +129,7 @@ def _revcomp(s):
 def test_tag_dense_reads(L):
     """Reads made of back-to-back tags give every lane of a warp ~10 seed hits (and every hit word its 'several
     occurrences' state): the confirmation loop of the exact-tag kernels must find them all, results unchanged.
-    L = 320 does not fit the flat kernel's one-word hit mask and runs the bit-filter kernel."""
+    L = 320 needs the flat kernel's second hit word."""
     info = tags.load("human", "extended", "b")
     rng = np.random.default_rng(7)
     vs, js = list(info.v_seqs), list(info.j_seqs)
@@ -198,7 +200,7 @@ def test_full_size_properties_config2():
 
 
 @pytest.mark.parametrize("tagset,chain,L", [("extended", "b", 250), ("extended", "a", 150), ("original", "a", 128),
-                                            ("original", "b", 250)])
+                                            ("original", "b", 250), ("extended", "b", 318)])
 def test_tag_position_sweep(tagset, chain, L):
     """Every tag at every start position modulo the seed stride and at both read ends (see sweep_reads), through every
     exact-tag kernel and the general kernel."""
