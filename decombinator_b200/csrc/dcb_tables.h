@@ -35,7 +35,7 @@ struct DcbKw {
 // One keyword set == one acora automaton of the reference.
 struct DcbKwSet {
     int32_t n_kw;        // distinct keywords
-    int32_t kq;          // suffix key length in bases (min(min_len, 8))
+    int32_t kq;          // suffix key length in bases (min(min_len, 6))
     int32_t bitmap_off;  // 4^kq bits
     int32_t hash_off;    // hash_size slots: (key << 16) | (first_kw << 8) | count ; DCB_HASH_EMPTY
     int32_t hash_mask;   // hash_size - 1

@@ -129,7 +129,11 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* a, uint32_t 
 }
 
 static constexpr int kExactThreads = 512;   // upper bounds; long reads launch narrower blocks (shared memory)
-static constexpr int kGeneralThreads = 768;   // one wide block per SM: the 72 KB of tables are staged once, 24 warps hide the latency
+#ifndef DCB_GENERAL_THREADS
+#define DCB_GENERAL_THREADS 768
+#define DCB_GENERAL_BLOCKS 1
+#endif
+static constexpr int kGeneralThreads = DCB_GENERAL_THREADS;   // one wide block per SM: the 72 KB of tables are staged once, 24 warps hide the latency
 static constexpr int kMaxChunks = 256;             // queue counters per context
 static constexpr uint32_t kChunkReads = 1u << 20;  // reads per chunk of the pipelined host-to-host path
 
@@ -598,7 +602,7 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
 // ------------------------------------------------------------------------------------------------
 // general kernel (queued reads, or every read when queue == nullptr)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kGeneralThreads)
+__global__ void __launch_bounds__(kGeneralThreads, DCB_GENERAL_BLOCKS)
 dcb_general_kernel(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_result* __restrict__ results,
                    unsigned long long* __restrict__ counters, const uint32_t* __restrict__ queue,
                    const uint32_t* __restrict__ queue_count) {

@@ -110,7 +110,7 @@ void build_kwset(Blob& b, DcbKwSet& ks, const std::vector<std::string>& list) {
     if (kws.empty()) { min_len = 1; max_len = 1; }
     ks.n_kw = (int)kws.size();
     ks.min_len = min_len; ks.max_len = max_len;
-    ks.kq = std::min(min_len, 8);
+    ks.kq = std::min(min_len, 6);   // 4^6 bits = 512 B per set: the scans only visit marked positions, a sharper bitmap buys nothing
     struct Ent { uint32_t key; int len; int id; };
     std::vector<Ent> ents;
     for (size_t i = 0; i < kws.size(); i++) {

@@ -20,7 +20,7 @@ else
     for rep in 1 2; do
       DCB_LIB=$PWD/$f timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline "$@" 2>/dev/null | python -c "
 import sys,json
-d=json.loads(sys.stdin.readline()); print('$f', '%.2f G reads/s  exact %.4f ms  e2e %.3f G' % (d['value']/1e9, d['kernels_ms']['dcb_exact_kernel'], d['e2e']['value']/1e9))" >> gpurun_out/variants.txt || echo "$f FAILED" >> gpurun_out/variants.txt
+d=json.loads(sys.stdin.readline()); print('$f', '%.2f G reads/s  exact %.4f ms  general %.3f ms  e2e %.3f G' % (d['value']/1e9, d['kernels_ms']['dcb_exact_kernel'], d['kernels_ms']['dcb_general_kernel'], d['e2e']['value']/1e9))" >> gpurun_out/variants.txt || echo "$f FAILED" >> gpurun_out/variants.txt
     done
   done
   cat gpurun_out/variants.txt
