@@ -218,7 +218,7 @@ def decombinator(inputargs: dict) -> list:
                 assert nrows == len(hits)
                 outdata = RowsText(blob, nrows)
                 hits = ()
-            elif not any(sep.encode() in c.buf for c in {id(c.buf): c for c in cols if c is not None}.values()):
+            elif not any(c.buf.find(sep.encode()) != -1 for c in {id(c.buf): c for c in cols if c is not None}.values()):
                 blob, nrows = _lib.format_rows(res, pack_rc, cols, sep)
                 outdata = [line.split(sep) for line in blob.decode("ascii").split("\n")[:-1]]
                 assert len(outdata) == nrows == len(hits)

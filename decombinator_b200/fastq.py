@@ -7,6 +7,7 @@ of every line is dropped unconditionally).  ``load_pairs`` materialises the reco
 """
 import gzip
 import itertools
+import mmap
 
 import numpy as np
 
@@ -157,6 +158,19 @@ def _clip(off, length, start, stop=None):
     return off + a.astype(np.uint64), np.maximum(b - a, 0).astype(np.uint32)
 
 
+def _file_bytes(path, opener):
+    """The file's text as a bytes-like object: a read-only memory map for plain files (no copy out of the page cache),
+    the decompressed bytes for .gz."""
+    if opener is open:
+        try:
+            with open(path, "rb") as fh:
+                return mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+        except (ValueError, OSError):      # empty file, or a file system without mmap
+            pass
+    with opener(path, "rb") as fh:
+        return fh.read()
+
+
 def load_pairs_native(inputargs, opener):
     """load_pairs through the native record index (dcb_fastq_index_build); None when a file is not in the strict
     four-line layout (the general parser then reproduces the reference's handling of everything else)."""
@@ -164,16 +178,14 @@ def load_pairs_native(inputargs, opener):
     bclength = inputargs["bclength"]
     if not isinstance(bclength, int) or bclength < 0 or inputargs["bc_read"] not in ("R1", "R2"):
         return None
-    with opener(inputargs["infile"], "rb") as fh:
-        data1 = fh.read()
+    data1 = _file_bytes(inputargs["infile"], opener)
     ix1 = _lib.fastq_index(data1)
     if ix1 is None:
         return None
     sampling = inputargs.get("sampling_analysis")
     batch = ReadBatch()
     if inputargs["bc_read"] == "R2":
-        with opener(inputargs["infile"].replace("1.f", "2.f"), "rb") as fh:
-            data2 = fh.read()
+        data2 = _file_bytes(inputargs["infile"].replace("1.f", "2.f"), opener)
         ix2 = _lib.fastq_index(data2)
         if ix2 is None:
             return None
