@@ -33,9 +33,8 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 
 import numpy as np  # noqa: E402
 
-# stdout carries ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION in some images) off it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries ONE JSON line: NCCL's debug output (the version banner at NCCL_DEBUG=VERSION/WARN/INFO) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "decombined_reads_per_sec"
 UNIT = "reads/s"
