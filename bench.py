@@ -33,8 +33,10 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 
 import numpy as np  # noqa: E402
 
-# stdout carries ONE JSON line: NCCL's debug output (the version banner at NCCL_DEBUG=VERSION/WARN/INFO) goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries ONE JSON line: keep a private handle on it and point file descriptor 1 at stderr, so that whatever a
+# library prints there (NCCL's version banner at NCCL_DEBUG=VERSION/WARN/INFO, for one) cannot end up beside the line
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 
 METRIC = "decombined_reads_per_sec"
 UNIT = "reads/s"
@@ -163,7 +165,7 @@ def main():
                 "note": "the reference is pure Python with un-installable native deps (acora, Levenshtein, biopython); "
                         "this arm times the oracle's C restatement of the same algorithm, which is pinned against "
                         "fixtures recorded from the unmodified reference"}
-        print(json.dumps(line))
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
         return
 
     # ---------------------------------------------------------------------------------------------
@@ -282,7 +284,7 @@ def main():
             rps, sec, _ = cpu_reference_run(r1[:sample * READ_LEN], off[:sample], ln[:sample], threads)
             line["cpu_baseline"] = {"value": rps, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "first %d reads of rank 0's shard, one pass, %.1f s" % (sample, sec)}
-        print(json.dumps(line))
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
