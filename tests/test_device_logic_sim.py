@@ -94,3 +94,23 @@ def test_sim_tag_position_sweep(tagset, chain, L):
         assert_records_equal(res, want, "reverse", "sweep use_q=%s" % use_q)
         assert np.array_equal(cnt, orc.counts)
     packed.free()
+
+
+@pytest.mark.parametrize("species,tagset,chain,orientation", [("human", "extended", "b", "reverse"), ("human", "original", "b", "both"),
+                                                              ("mouse", "original", "g", "reverse")])
+def test_sim_marks_and_hit_list_change_nothing(species, tagset, chain, orientation):
+    """The general path with the union suffix filter (candidate marks + hit list) against the same code scanning every
+    position: identical records and counters on reads with substitutions, N and junk -- the marks may only skip
+    positions where no keyword of any of the six sets can end (6-mer keywords of the `original` J sets included)."""
+    info = tags.load(species, tagset, chain)
+    vt, jt = info.tables()
+    r1, off, ln = synth_batch(info, 6000, 200, 0.02, 0.004, 0.1, seed=23)
+    packed = _lib.pack_arrays(r1, off, ln, revcomp=(orientation != "forward"))
+    both = orientation == "both"
+    a = simlib.sim_decombine(packed, vt, jt, both_frames=both, general_only=True, use_marks=True)
+    b = simlib.sim_decombine(packed, vt, jt, both_frames=both, general_only=True, use_marks=False)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    sf = _lib.suffix_filter(vt, jt)
+    assert sf[0] == min(min(len(t), len(t) - s, s) for ts, s in ((info.v_seqs, info.v_half_split), (info.j_seqs, info.j_half_split))
+                        for t in ts)      # kq = the shortest keyword of the six sets
+    packed.free()
