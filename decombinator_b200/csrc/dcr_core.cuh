@@ -875,11 +875,32 @@ enum { FAST_DONE = 0, FAST_DEFER = 1 };
 // deletion walks stay in the interior.  Anything else is deferred UNCOUNTED to the general kernel,
 // except the two outcomes that are final by themselves (multiple V / multiple J matches).
 // When both_frames is set a failed first frame must be retried, so every non-success defers.
+// Reads with non-ACGT symbols (packed as base 0, which can fake an 'A'): the exact-tag search can only find too many
+// occurrences, never too few, so its outcome stands whenever it found exactly one V and one J tag and no symbol lies in
+// anything the reference looks at for this read -- the two tags, the two deletion windows, the inter-tag span.  xp names
+// the read's entries of the sparse exception list; anything else about such a read is deferred.
+struct ExcProbe {
+    const uint32_t* read; const uint16_t* pos; const uint8_t* kind;
+    const uint32_t* index;      // index[k] = first entry whose read is >= 32 k; the list ends with read = 0xFFFFFFFF
+    uint32_t ri;
+};
+DCB_HD bool exc_in_span(const ExcProbe& x, int lo, int hi) {
+    uint32_t e = x.index[x.ri >> 5];
+    while (x.read[e] < x.ri) e++;
+    for (; x.read[e] == x.ri; e++) {
+        if (x.kind[e] == 3) continue;               // a real base in this frame
+        const int p = (int)x.pos[e];
+        if (p >= lo && p < hi) return true;
+    }
+    return false;
+}
+
 template <bool PADDED>
 DCB_HD int dcr_fast_from_hits(const ReadView& r, const DcbTag* vtags, const DcbTag* jtags, const FullHit& vh,
                               const FullHit& jh, const DcrParams& prm, int both_frames, dcb_result& out,
-                              dcb_cnt_t* C) {
+                              dcb_cnt_t* C, const bool use_xp = false, const ExcProbe xp = ExcProbe()) {
     if (vh.count == 0) return FAST_DEFER;
+    if (use_xp && (vh.count > 1 || jh.count != 1)) return FAST_DEFER;      // an occurrence may be a fake
     if (vh.count > 1) {
         if (both_frames) return FAST_DEFER;
         DCB_COUNT(C, DCB_C_multiple_v_matches);
@@ -899,6 +920,13 @@ DCB_HD int dcr_fast_from_hits(const ReadView& r, const DcbTag* vtags, const DcbT
     const DcbTagFin jt = tag_fin(jtags, fullhit_tag(jh));
     j.idx = fullhit_tag(jh); j.seqpos = fullhit_pos(jh) + (int)jt.len;
     if (!fast_j_deletions<PADDED>(r, jt, fullhit_pos(jh) - jt.jump, v.pos + 1, j.pos, j.dels)) return FAST_DEFER;
+    if (use_xp) {
+        const int f0 = v.seqpos + vt.jump, tsj = fullhit_pos(jh) - jt.jump;       // V window [f0 - 32, f0), J window [tsj, tsj + 32)
+        const int lo = v.seqpos < f0 - 32 ? v.seqpos : f0 - 32;
+        int hi = j.seqpos > tsj + 32 ? j.seqpos : tsj + 32;
+        if (f0 > hi) hi = f0;
+        if (exc_in_span(xp, lo, hi)) return FAST_DEFER;
+    }
     // filters: a failed filter is final unless the other frame still has to be tried
     int c = dcr_finish(r, vt.jump, vt.len, jt.jump, jt.len, v, j, prm, out);
     if (c >= 0) {
@@ -932,8 +960,9 @@ DCB_HD uint32_t exc_lower_bound(const ExcList& ex, uint32_t key) {
 // union index of both genes when jidx is null.  Returns FAST_DONE / FAST_DEFER.
 DCB_HD int dcr_exact_read(const ReadView& r, bool flagged, const uint32_t* vcore, const uint32_t* jcore,
                           const uint32_t* vidx, const uint32_t* jidx, const DcrParams& prm, int both_frames,
-                          dcb_result& out, dcb_cnt_t* C, bool use_q = false) {
-    if (flagged) return FAST_DEFER;
+                          dcb_result& out, dcb_cnt_t* C, bool use_q = false, const ExcProbe* xp = nullptr) {
+    if (flagged && !xp) return FAST_DEFER;
+    if (!flagged) xp = nullptr;
     FullHit vh, jh;
     vh.count = 0; vh.code = 0;
     jh.count = 0; jh.code = 0;
@@ -945,7 +974,8 @@ DCB_HD int dcr_exact_read(const ReadView& r, bool flagged, const uint32_t* vcore
         fast_find(r, vidx, vh, jh, true);
         if (vh.count == 1) fast_find(r, jidx, vh, jh, false);
     }
-    return dcr_fast_from_hits<false>(r, gene_tags(vcore), gene_tags(jcore), vh, jh, prm, both_frames, out, C);
+    return dcr_fast_from_hits<false>(r, gene_tags(vcore), gene_tags(jcore), vh, jh, prm, both_frames, out, C, xp != nullptr,
+                                     xp ? *xp : ExcProbe());
 }
 
 // General kernel body for one read: r has w/stride/n/nw set; inv0, rd1, inv1 are this thread's scratch

@@ -35,6 +35,7 @@ struct BatchDev {
     const uint32_t* exc_read;
     const uint16_t* exc_pos;
     const uint8_t* exc_kind;
+    const uint32_t* exc_index;   // exc_index[k] = first exception entry whose read is >= 32 k (n_exc > 0 only)
     uint32_t n_reads, slot_words, uniform_len, n_exc;
     uint32_t first;   // the launch covers reads [first, first + n_reads); every array is indexed by the global read index
 };
@@ -445,7 +446,7 @@ __device__ __forceinline__ uint32_t mad2(uint32_t h, uint32_t bit) {   // 2 * h 
 }
 
 #define WLEAD_OF(S) ((S) - 1)
-template <int NW, int Q, int S, int T>
+template <int NW, int Q, int S, int T, bool EXC>
 __global__ void __launch_bounds__(T, 1)
 dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dcb_result* __restrict__ results,
                       unsigned long long* __restrict__ counters, uint32_t* __restrict__ queue,
@@ -513,8 +514,9 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
 #pragma unroll
             for (int k = 0; k < NW; k++) s_rd[(1 + k) * T + tid] = w[k];
         }
+        // EXC: the batch has reads with non-ACGT symbols (its own instantiation, so that the clean path carries none of it)
         const bool flagged = live && b.n_exc && ((__ldg(b.flags + (ri >> 5)) >> (ri & 31)) & 1u);
-        const bool scan = live && !flagged;
+        const bool scan = EXC ? live : (live && !flagged);   // EXC: reads with non-ACGT symbols too, see ExcProbe
         ReadView r;
         r.w = col; r.inv = nullptr; r.stride = T;
         r.n = b.uniform_len ? (int)b.uniform_len : (live ? (int)__ldg(b.lens + ri) : 0);
@@ -591,8 +593,14 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
         }
         FullHit vh, jh;
         hw.decode(vh, jh);
-        if (scan) action = dcr_fast_from_hits<true>(r, vtags, jtags, vh, jh, prm, both_frames, out, s_cnt);
-        else if (live) action = FAST_DEFER;
+        if (EXC) {
+            ExcProbe xp;
+            xp.read = b.exc_read; xp.pos = b.exc_pos; xp.kind = b.exc_kind; xp.index = b.exc_index; xp.ri = ri;
+            if (scan) action = dcr_fast_from_hits<true>(r, vtags, jtags, vh, jh, prm, both_frames, out, s_cnt, flagged, xp);
+        } else {
+            if (scan) action = dcr_fast_from_hits<true>(r, vtags, jtags, vh, jh, prm, both_frames, out, s_cnt);
+            else if (live) action = FAST_DEFER;
+        }
         defer_reads(live && action == FAST_DEFER, ri, queue, queue_count);
         if (live && action == FAST_DONE) store_result(results + ri, out);
     }
@@ -732,7 +740,8 @@ struct dcb_ctx {
     uint32_t* d_sfilt = nullptr;   // union suffix filter of the general kernel
     int sfilt_words = 0;
     int vgen_words = 0, jgen_words = 0, vcore_words = 0, jcore_words = 0, vidx_words = 0, jidx_words = 0, uidx_words = 0;
-    DevBuf words, lens, flags, exc_read, exc_pos, exc_kind, results, queue;
+    DevBuf words, lens, flags, exc_read, exc_pos, exc_kind, exc_index, results, queue;
+    std::vector<uint32_t> h_exc_index;   // host copy of exc_index while its upload is in flight
     uint32_t* d_queue_count = nullptr;
     unsigned long long* d_counters = nullptr;
     BatchDev batch{};
@@ -778,15 +787,17 @@ static exact_spec_fn pick_spec(int nw, int qv, int sv, int lminv, int qj, int sj
 // up to 20 words (320 nt: two hit words).
 typedef void (*exact_q_fn)(BatchDev, QTables, DcrParams, int, dcb_result*, unsigned long long*, uint32_t*, uint32_t*);
 static constexpr int kQThreads = 1024;
-static exact_q_fn pick_q(int nw, int qq, int qs, int lmin) {
+static exact_q_fn pick_q(int nw, int qq, int qs, int lmin, bool exc) {
     if (qq != 13 || qs != 8 || lmin != 20) return nullptr;
+#define DCB_FLAT(NW) (exc ? dcb_exact_kernel_flat<NW, 13, 8, kQThreads, true> : dcb_exact_kernel_flat<NW, 13, 8, kQThreads, false>)
     switch (nw) {
-        case 8:  return dcb_exact_kernel_flat<8, 13, 8, kQThreads>;
-        case 12: return dcb_exact_kernel_flat<12, 13, 8, kQThreads>;
-        case 16: return dcb_exact_kernel_flat<16, 13, 8, kQThreads>;
-        case 20: return dcb_exact_kernel_flat<20, 13, 8, kQThreads>;
+        case 8:  return DCB_FLAT(8);
+        case 12: return DCB_FLAT(12);
+        case 16: return DCB_FLAT(16);
+        case 20: return DCB_FLAT(20);
         default: return nullptr;
     }
+#undef DCB_FLAT
 }
 static int q_rows(int nw) {   // must match the kernel's ROWS
     const int npos = (16 * nw - 13) / 8 + 1, wmax = ((npos - 1) * 8 - 7) >> 4;
@@ -911,7 +922,7 @@ void dcb_ctx_destroy(dcb_ctx* c) {
     cudaFree(c->d_vgen); cudaFree(c->d_jgen); cudaFree(c->d_vcore); cudaFree(c->d_jcore);
     cudaFree(c->d_vidx); cudaFree(c->d_jidx); cudaFree(c->d_uidx); cudaFree(c->d_sfilt);
     cudaFree(c->d_queue_count); cudaFree(c->d_counters);
-    c->words.release(); c->lens.release(); c->flags.release(); c->exc_read.release(); c->exc_pos.release();
+    c->words.release(); c->lens.release(); c->flags.release(); c->exc_read.release(); c->exc_pos.release(); c->exc_index.release();
     c->exc_kind.release(); c->results.release(); c->queue.release();
     delete c;
 }
@@ -931,12 +942,13 @@ static int prepare_batch(dcb_ctx* c, const dcb_packed* P) {
     if ((rc = c->words.ensure(n * sw * 4 + 16)) || (rc = c->lens.ensure(n * 2 + 16)) ||
         (rc = c->flags.ensure(((n + 31) / 32) * 4 + 16)) || (rc = c->exc_read.ensure((size_t)P->n_exc * 4 + 16)) ||
         (rc = c->exc_pos.ensure((size_t)P->n_exc * 2 + 16)) || (rc = c->exc_kind.ensure((size_t)P->n_exc + 16)) ||
+        (rc = c->exc_index.ensure(((n + 31) / 32 + 2) * 4 + 16)) ||
         (rc = c->results.ensure(n * sizeof(dcb_result) + 16)) || (rc = c->queue.ensure(n * 4 + 16)))
         return rc;
     BatchDev& b = c->batch;
     b.words = (const uint32_t*)c->words.p; b.lens = (const uint16_t*)c->lens.p; b.flags = (const uint32_t*)c->flags.p;
     b.exc_read = (const uint32_t*)c->exc_read.p; b.exc_pos = (const uint16_t*)c->exc_pos.p;
-    b.exc_kind = (const uint8_t*)c->exc_kind.p;
+    b.exc_kind = (const uint8_t*)c->exc_kind.p; b.exc_index = (const uint32_t*)c->exc_index.p;
     b.n_reads = (uint32_t)n; b.slot_words = (uint32_t)sw; b.uniform_len = P->uniform_len; b.n_exc = P->n_exc;
     b.first = 0;
     c->have_batch = true; c->ran = false;
@@ -956,7 +968,7 @@ static int prepare_batch(dcb_ctx* c, const dcb_packed* P) {
     int occ_e = 0, occ_g = 0;
     exact_q_fn qfn = nullptr;
     if (have_union && c->params.force_general == 0 && c->ufbits == DCB_FBITS && c->utqbits > 0)
-        qfn = pick_q((int)sw, c->uqq, c->uqs, c->lminv);
+        qfn = pick_q((int)sw, c->uqq, c->uqs, c->lminv, P->n_exc != 0);
     if (qfn) {
         c->exact_smem = ((size_t)1 << DCB_FBITS) + ((size_t)q_rows((int)sw) * kQThreads +
                          c->vcore_words + c->jcore_words + c->uhead + c->uqtab_words) * 4 + tail;
@@ -1024,6 +1036,16 @@ static int copy_side_arrays(dcb_ctx* c, const dcb_packed* P, cudaStream_t s) {
         CUDA_TRY(cudaMemcpyAsync(c->exc_read.p, P->exc_read, (size_t)P->n_exc * 4, cudaMemcpyHostToDevice, s));
         CUDA_TRY(cudaMemcpyAsync(c->exc_pos.p, P->exc_pos, (size_t)P->n_exc * 2, cudaMemcpyHostToDevice, s));
         CUDA_TRY(cudaMemcpyAsync(c->exc_kind.p, P->exc_kind, (size_t)P->n_exc, cudaMemcpyHostToDevice, s));
+        // the list's end marker and the per-32-reads index the exact kernel enters the list through
+        CUDA_TRY(cudaMemsetAsync((char*)c->exc_read.p + (size_t)P->n_exc * 4, 0xFF, 4, s));
+        const size_t nb = (n + 31) / 32 + 1;
+        c->h_exc_index.assign(nb, P->n_exc);
+        uint32_t e = 0;
+        for (size_t k = 0; k < nb; k++) {
+            while (e < P->n_exc && P->exc_read[e] < 32 * k) e++;
+            c->h_exc_index[k] = e;
+        }
+        CUDA_TRY(cudaMemcpyAsync(c->exc_index.p, c->h_exc_index.data(), nb * 4, cudaMemcpyHostToDevice, s));
     }
     return DCB_OK;
 }

@@ -22,6 +22,16 @@ extern "C" int sim_decombine(const dcb_packed* P, const uint32_t* vgen, const ui
     ExcList ex;
     ex.read = P->exc_read; ex.pos = P->exc_pos; ex.kind = P->exc_kind; ex.n = P->n_exc;
     uint64_t deferred = 0;
+    // what the context uploads beside the exception list: its end marker and the per-32-reads entry index (flat kernel)
+    std::vector<uint32_t> xread(P->exc_read, P->exc_read + P->n_exc), xindex((P->n_reads + 31) / 32 + 1, P->n_exc);
+    xread.push_back(0xFFFFFFFFu);
+    {
+        uint32_t e = 0;
+        for (size_t k = 0; k < xindex.size(); k++) {
+            while (e < P->n_exc && P->exc_read[e] < 32 * k) e++;
+            xindex[k] = e;
+        }
+    }
     for (uint64_t ri = 0; ri < P->n_reads; ri++) {
         ReadView r;
         std::memset(&r, 0, sizeof(r));
@@ -32,7 +42,11 @@ extern "C" int sim_decombine(const dcb_packed* P, const uint32_t* vgen, const ui
         dcb_result o;
         std::memset(&o, 0, sizeof(o));
         int action = FAST_DEFER;
-        if (mode == 0 || mode == 2) action = dcr_exact_read(r, flagged, vcore, jcore, vidx, jidx, prm, both_frames, o, cnt, mode == 2);
+        ExcProbe xp;
+        xp.read = xread.data(); xp.pos = P->exc_pos; xp.kind = P->exc_kind; xp.index = xindex.data(); xp.ri = (uint32_t)ri;
+        if (mode == 0 || mode == 2)
+            action = dcr_exact_read(r, flagged, vcore, jcore, vidx, jidx, prm, both_frames, o, cnt, mode == 2,
+                                    mode == 2 && P->n_exc ? &xp : nullptr);   // the flat kernel also takes reads with non-ACGT symbols
         if (action == FAST_DEFER) {
             deferred++;
             std::memset(&o, 0, sizeof(o));

@@ -53,7 +53,10 @@ def test_sim_matches_oracle_on_synthetic(species, tagset, chain, orientation, L,
         assert deferred < 0.1 * n  # the exact-tag path must carry clean data on its own
     if _lib.union_index(vt, jt) is not None:   # the flat kernel's tables find exactly the same tags
         res_q, cnt_q, deferred_q = simlib.sim_decombine(packed, vt, jt, both_frames=(orientation == "both"), use_q=True)
-        assert np.array_equal(res_q, res) and np.array_equal(cnt_q, cnt) and deferred_q == deferred
+        assert np.array_equal(res_q, res) and np.array_equal(cnt_q, cnt)
+        assert deferred_q <= deferred          # the flat kernel also finishes reads whose non-ACGT symbols lie outside the V-J span
+        if nrate > 0:
+            assert deferred_q < deferred
     packed.free()
 
 
