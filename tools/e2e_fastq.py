@@ -23,11 +23,13 @@ def main():
     ap.add_argument("--reads", type=int, default=2_000_000)
     ap.add_argument("--python-fastq", action="store_true", help="use the general (Python) parser instead of the native index")
     ap.add_argument("--rows-as-text", action="store_true", help="what the `decombine` command does: rows handed over as .n12 text")
+    ap.add_argument("--pipeline", action="store_true", help="decombine + collapse (pipeline.run) on reads with repeated UMIs")
     args = ap.parse_args()
     from decombinator_b200 import _lib, decombine, fastq, io, tags
     info = tags.load("human", "extended", "b")
     L, n = 250, args.reads
-    syn = _lib.Synth([(info.v_regions, info.j_regions)], 20260002, L, 42 + 20, 0.0, 0.0, 0.0)
+    syn = _lib.Synth([(info.v_regions, info.j_regions)], 20260002, L, 42 + 20, 0.0, 0.0, 0.0,
+                     umi_pool=(max(1000, n // 20) if args.pipeline else 0))
     r1, r2 = syn.reads(0, n, want_r2=True)
     os.makedirs("/tmp/e2e", exist_ok=True)
     p1, p2 = "/tmp/e2e/syn_1.fq", "/tmp/e2e/syn_2.fq"
@@ -45,6 +47,18 @@ def main():
                              outpath="/tmp/e2e/")
     ia["python_fastq"] = args.python_fastq
     ia["rows_as_text"] = args.rows_as_text
+    if args.pipeline:
+        from decombinator_b200 import pipeline
+        ia.update(dontsave=True, oligo="M13", command="pipeline")
+        t0 = time.perf_counter()
+        rows = decombine.decombinator(dict(ia))
+        t_dec = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        out = pipeline.run(dict(ia))
+        t_pipe = time.perf_counter() - t0
+        print(json.dumps({"reads": n, "decombinator_s": round(t_dec, 2), "pipeline_s": round(t_pipe, 2), "rows": len(rows),
+                          "collapsed": len(out), "pipeline_reads_per_s": round(n / t_pipe)}))
+        return
     # warm-up: tables, context, CUDA
     small = dict(ia)
     decombine.import_tcr_info(small)
