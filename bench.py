@@ -278,7 +278,7 @@ def main():
             "gpu_launches": int(klaunch.sum()),
             "clocks": clocks,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only
             threads = os.cpu_count() or 1
             sample = args.cpu_sample or min(n, 2_000_000 if threads < 16 else 10_000_000)
             rps, sec, _ = cpu_reference_run(r1[:sample * READ_LEN], off[:sample], ln[:sample], threads)
