@@ -2,15 +2,20 @@
 //
 // Two kernels per batch, both one thread per read, 32 reads per warp:
 //
-//   dcb_exact_kernel   every read.  128-bit loads of the packed read slot, sampled-seed search for
-//                      the full V and J tags (one shared-memory bitmap probe every `stride` bases),
-//                      bit-parallel deletion walk, the four dcr() filters, one 16-byte record out.
-//                      Reads it cannot finish (no exact tag, non-ACGT symbols, a deletion walk that
-//                      leaves the interior, `-or both` retries) are appended UNCOUNTED to a queue with
-//                      one warp-aggregated atomic (ballot + popc + shuffle).
-//   dcb_general_kernel the queued reads only (compacted, so warps stay dense): the complete
-//                      vanalysis/janalysis contract incl. the half-tag fallback with Hamming <= 1 and
-//                      the literal Python-slice deletion walks.
+//   exact-tag kernel   every read.  128-bit loads of the packed read slot, sampled-seed search for the full V and J
+//                      tags, bit-parallel deletion walk, the four dcr() filters, one 16-byte record out.  Reads it
+//                      cannot finish (no exact tag, a non-ACGT symbol where the reference looks, a deletion walk that
+//                      leaves the interior, `-or both` retries) are appended UNCOUNTED to a queue with one
+//                      warp-aggregated atomic (ballot + popc + shuffle).  Three forms, picked per batch:
+//                        dcb_exact_kernel_flat   chains with one seed geometry, reads up to 320 nt: 13-mer seeds at
+//                                                stride 8, byte filter, hash-and-displace offsets, 8-byte tag slots
+//                        dcb_exact_kernel_spec   V (9-mers, stride 12) + J (8-mers, stride 5) bit filters in private
+//                                                copies, class-key cuckoo + prefix table (12-nt J tags, long reads)
+//                        dcb_exact_kernel        the generic form of the latter (any slot size / geometry)
+//   dcb_general_kernel the queued reads only (compacted, so warps stay dense): the complete vanalysis/janalysis
+//                      contract incl. the half-tag fallback with Hamming <= 1 and the literal Python-slice deletion
+//                      walks; candidate keyword positions marked by a union suffix filter, one hit list per read,
+//                      reads regrouped by class between preparation and analysis.
 //
 // Tag tables are staged into shared memory once per (persistent) block with TMA bulk copies
 // (cp.async.bulk + mbarrier); reads live in shared memory as [word][thread] so data-dependent word
