@@ -296,9 +296,9 @@ def fastq_index(data, n_threads=None):
     buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
     out = ctypes.POINTER(CFastqIndex)()
     nt = n_threads or min(32, os.cpu_count() or 1)
-    _check(lib().dcb_fastq_index_build(buf.ctypes.data if len(buf) else None, len(buf), nt, ctypes.byref(out)),
-           "dcb_fastq_index_build")
+    rc = lib().dcb_fastq_index_build(buf.ctypes.data if len(buf) else None, len(buf), nt, ctypes.byref(out))
     try:
+        _check(rc, "dcb_fastq_index_build")
         ix = out.contents
         if not ix.strict:
             return None
@@ -310,7 +310,8 @@ def fastq_index(data, n_threads=None):
             res[name] = np.ctypeslib.as_array(getattr(ix, name), shape=(n,)).astype(dt, copy=True) if n else np.zeros(0, dt)
         return res
     finally:
-        lib().dcb_fastq_index_free(out)
+        if out:
+            lib().dcb_fastq_index_free(out)
 
 
 def count_ranges_with(buf, off, length, symbol, n_threads=None):
