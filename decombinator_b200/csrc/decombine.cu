@@ -141,6 +141,7 @@ static constexpr int kExactThreads = 512;   // upper bounds; long reads launch n
 #endif
 static constexpr int kGeneralThreads = DCB_GENERAL_THREADS;   // one wide block per SM: the 72 KB of tables are staged once, 24 warps hide the latency
 static constexpr int kMaxChunks = 256;             // queue counters per context
+static constexpr size_t kZeroBlockBytes = sizeof(uint32_t) * kMaxChunks + sizeof(unsigned long long) * DCB_NCOUNTERS;
 static constexpr uint32_t kChunkReads = 1u << 20;  // reads per chunk of the pipelined host-to-host path
 
 // Shared-memory carve-up common to the kernels: [table 0..3][per-thread columns][counters][mbarrier]
@@ -911,8 +912,9 @@ dcb_ctx* dcb_ctx_create(int device, const dcb_tagset* v, const dcb_tagset* j, co
                 if (upload_blob(sf, &c->d_sfilt, &c->sfilt_words)) return fail(nullptr);
         }
     }
-    if (cudaMalloc((void**)&c->d_queue_count, sizeof(uint32_t) * kMaxChunks) != cudaSuccess) return fail("cudaMalloc");
-    if (cudaMalloc((void**)&c->d_counters, sizeof(unsigned long long) * DCB_NCOUNTERS) != cudaSuccess) return fail("cudaMalloc");
+    // queue counters and reference counters in ONE block: a step clears both with one memset
+    if (cudaMalloc((void**)&c->d_queue_count, kZeroBlockBytes) != cudaSuccess) return fail("cudaMalloc");
+    c->d_counters = reinterpret_cast<unsigned long long*>(c->d_queue_count + kMaxChunks);
     return c;
 }
 
@@ -926,7 +928,7 @@ void dcb_ctx_destroy(dcb_ctx* c) {
     if (c->ev_done) cudaEventDestroy(c->ev_done);
     cudaFree(c->d_vgen); cudaFree(c->d_jgen); cudaFree(c->d_vcore); cudaFree(c->d_jcore);
     cudaFree(c->d_vidx); cudaFree(c->d_jidx); cudaFree(c->d_uidx); cudaFree(c->d_sfilt);
-    cudaFree(c->d_queue_count); cudaFree(c->d_counters);
+    cudaFree(c->d_queue_count);   // d_counters lives in the same block
     c->words.release(); c->lens.release(); c->flags.release(); c->exc_read.release(); c->exc_pos.release(); c->exc_index.release();
     c->exc_kind.release(); c->results.release(); c->queue.release();
     delete c;
@@ -1132,8 +1134,7 @@ int dcb_run_resident(dcb_ctx* c) {
     if (!c || !c->have_batch) { dcb_set_error("dcb_run_resident: no batch uploaded"); return DCB_EINVAL; }
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
-    CUDA_TRY(cudaMemsetAsync(c->d_queue_count, 0, sizeof(uint32_t) * kMaxChunks, s));
-    CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * DCB_NCOUNTERS, s));
+    CUDA_TRY(cudaMemsetAsync(c->d_queue_count, 0, kZeroBlockBytes, s));
     int rc;
     if ((rc = launch_range(c, s, 0, c->batch.n_reads, 0, true))) return rc;
     c->ran = true;
@@ -1160,8 +1161,7 @@ int dcb_decombine_batch(dcb_ctx* c, const dcb_packed* P, dcb_result* out, uint64
     const uint32_t n = (uint32_t)P->n_reads;
     const size_t sw = P->slot_words;
     cudaStream_t st[2] = {c->stream, c->stream2};
-    CUDA_TRY(cudaMemsetAsync(c->d_queue_count, 0, sizeof(uint32_t) * kMaxChunks, st[0]));
-    CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * DCB_NCOUNTERS, st[0]));
+    CUDA_TRY(cudaMemsetAsync(c->d_queue_count, 0, kZeroBlockBytes, st[0]));
     if ((rc = copy_side_arrays(c, P, st[0]))) return rc;
     CUDA_TRY(cudaEventRecord(c->ev_ready, st[0]));
     CUDA_TRY(cudaStreamWaitEvent(st[1], c->ev_ready, 0));
