@@ -97,6 +97,27 @@ int dcb_pack_reads(const char* ascii, const uint64_t* off, const uint32_t* len, 
             bool flagged = false;
             uint32_t acc = 0;
             uint32_t i = 0;
+            // eight bases at a time while they are all A/C/G/T (SWAR): code = ((c >> 1) ^ (c >> 2)) & 3 maps
+            // A,C,G,T -> 0,1,2,3; the reverse complement reads the bytes from the end (byte swap) and flips the code.
+            // Any other symbol in a group hands the rest of the read to the byte loop below.
+            for (; i + 8 <= L; i += 8) {
+                uint64_t x;
+                if (revcomp) { std::memcpy(&x, s + (L - 8 - i), 8); x = __builtin_bswap64(x); }
+                else std::memcpy(&x, s + i, 8);
+                const uint64_t k01 = 0x0101010101010101ull, k7f = 0x7F7F7F7F7F7F7F7Full, k80 = 0x8080808080808080ull;
+                // 0x80 in exactly the bytes of v that are 0 (no carry crosses a byte: exact per byte)
+                auto zero_bytes = [&](uint64_t v) { return ~(((v & k7f) + k7f) | v | k7f); };
+                const uint64_t ok = zero_bytes(x ^ (k01 * 'A')) | zero_bytes(x ^ (k01 * 'C')) | zero_bytes(x ^ (k01 * 'G')) |
+                                    zero_bytes(x ^ (k01 * 'T'));
+                if (ok != k80) break;        // another symbol in this group: the byte loop below takes over
+                uint64_t v = ((x >> 1) ^ (x >> 2)) & (k01 * 3);
+                if (revcomp) v ^= k01 * 3;
+                v = (v | (v >> 6)) & 0x000F000F000F000Full;
+                v = (v | (v >> 12)) & 0x000000FF000000FFull;
+                v = (v | (v >> 24)) & 0xFFFFull;
+                acc |= (uint32_t)v << (2 * (i & 15));
+                if ((i & 15) == 8) { w[i >> 4] = acc; acc = 0; }
+            }
             for (; i < L; i++) {
                 unsigned char c = revcomp ? kT.comp[s[L - 1 - i]] : s[i];
                 int code = kT.code[c];
