@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sub-rate", type=float, default=0.0, help="per-base substitution rate of the synthetic reads (default: the headline workload, 0)")
     ap.add_argument("--n-rate", type=float, default=0.0, help="per-base N rate")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the extra workload blocks (configs[2])")
     return ap.parse_args()
 
 
@@ -79,6 +80,75 @@ def cpu_reference_run(r1, off, ln, threads, steps=1, warmup=0):
         res = orc.decombine_arrays(r1, off, ln, "reverse", nthreads=threads)
     dt = time.perf_counter() - t0
     return len(off) * steps / dt, dt / steps, int(res["ok"].sum())
+
+
+def run_cfg2(args, rank, world, local_rank, host_threads, stream, barrier):
+    """BASELINE configs[2] in the same run: ONE mixed file (even reads alpha molecules, odd reads beta), human extended tag
+    sets, 1 % substitutions + 0.1 % N per base, analysed once per chain (-c a, then -c b) as the reference's example does.
+    Batch resident in HBM, K passes of all three kernels per chain, CUDA events, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from decombinator_b200 import _lib, tags
+    ia, ib = tags.load("human", "extended", "a"), tags.load("human", "extended", "b")
+    n, seed = args.reads, 20260003
+    syn = _lib.Synth([(ia.v_regions, ia.j_regions), (ib.v_regions, ib.j_regions)], seed, READ_LEN, 0, 0.01, 0.001, 0.0)
+    r1, _ = syn.reads(rank * n, n, n_threads=host_threads)
+    off = np.arange(n, dtype=np.uint64) * READ_LEN
+    ln = np.full(n, READ_LEN, dtype=np.uint32)
+    packed = _lib.pack_arrays(r1, off, ln, revcomp=True, n_threads=host_threads)
+    del r1
+    steps = max(1, min(args.steps, 20))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    out = {"workload": "synthetic 250-nt reads, one mixed file (even reads human alpha, odd reads human beta), extended tag sets, "
+                       "1 % substitutions + 0.1 % N per base, analysed once per chain (BASELINE configs[2] shape, %d reads per GPU)" % n,
+           "seed": seed, "steps": steps, "chains": {}}
+    total_ms = 0.0
+    for chain, info in (("a", ia), ("b", ib)):
+        vt, jt = info.tables()
+        ctx = _lib.Context(vt, jt, device=local_rank)
+        ctx.set_stream(stream.cuda_stream)
+        ctx.upload(packed)
+        with torch.cuda.stream(stream):
+            for _ in range(5):
+                ctx.run_resident()
+            torch.cuda.synchronize()
+            res, cnt = ctx.download()
+            ctx.timing_enable(True); ctx.timing_reset()
+            barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            for _ in range(steps):
+                ctx.run_resident()
+            ev1.record(stream)
+            barrier()
+            ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        kms, kl = ctx.timing_get()
+        per = [kms[i] / max(1, kl[i]) for i in range(3)]
+        bpr = (READ_LEN + 3) // 4 + 16
+        out["chains"][chain] = {
+            "value": world * n * steps / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / steps,
+            "decombined_fraction": float(res["status"].mean()),
+            "queued_by_exact_kernel": ctx.last_deferred() / n, "deferred_to_general_kernel": ctx.last_general() / n,
+            "kernels_ms": {ctx.exact_kernel_name(): per[0], "dcb_halftag_kernel": per[2], "dcb_general_kernel": per[1]},
+            "roofline_frac_all_kernels": bpr * n / (ms / steps / 1e3) / 1e9 / peak,
+            "gpu_launches": int(kl.sum()),
+        }
+        total_ms += ms / steps
+        ctx.close()
+    packed.free()
+    out["value"] = world * n / (total_ms / 1e3)
+    out["unit"] = "reads of the file/s, both chains analysed"
+    out["ms_per_file_pass"] = total_ms
+    return out
 
 
 class ClockSampler:
@@ -234,6 +304,15 @@ def main():
             res_e, cnt_e = ctx.decombine(packed, pinned=True)   # synchronous: results are in host memory on return
         e_ms = (time.perf_counter() - e0) * 1e3
         assert np.array_equal(res_e, res0) and np.array_equal(cnt_e, cnt0)
+    exact_name, h2d_bytes = ctx.exact_kernel_name(), packed.h2d_bytes()
+
+    n_general = ctx.last_general()
+    cfg2 = None
+    if not args.no_workloads:
+        ctx.close(); ctx = None
+        packed.free()
+        cfg2 = run_cfg2(args, rank, world, local_rank, host_threads, stream, barrier)
+        packed = None
 
     if world > 1:
         t = torch.tensor([ms_total, e_ms], device="cuda", dtype=torch.float64)
@@ -268,16 +347,21 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic", "config": config,
-            "decombined_fraction": decombined / (world * n), "deferred_to_general_kernel": n_deferred / n,
-            "kernels_ms": {"dcb_exact_kernel": exact_ms, "dcb_general_kernel": general_ms},
+            "decombined_fraction": decombined / (world * n), "queued_by_exact_kernel": n_deferred / n,
+            "deferred_to_general_kernel": n_general / n,
+            "kernels_ms": {"dcb_exact_kernel": exact_ms, "dcb_halftag_kernel": kms[2] / max(1, klaunch[2]),
+                           "dcb_general_kernel": general_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": ctx.exact_kernel_name(), "bytes_per_read": bytes_per_read,
+                         "traffic": traffic, "traffic_source": "profiles/traffic.json (one ncu --set full capture of this kernel, per read) x reads",
+                         "kernel": exact_name, "bytes_per_read": bytes_per_read,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650"},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(packed.h2d_bytes()),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(n * 16 + 8 * _lib.NCOUNTERS), "steps": e2e_steps},
             "gpu_launches": int(klaunch.sum()),
             "clocks": clocks,
         }
+        if cfg2:
+            line["workloads"] = {"cfg2": cfg2}
         if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only
             threads = os.cpu_count() or 1
             sample = args.cpu_sample or min(n, 2_000_000 if threads < 16 else 10_000_000)

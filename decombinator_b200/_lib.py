@@ -74,6 +74,7 @@ def lib():
     L.dcb_tagset_blob.argtypes = [vp, i32, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint32)), ctypes.POINTER(ctypes.c_size_t)]
     L.dcb_tagset_union_index.argtypes = [vp, vp, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
     L.dcb_tagset_suffix_filter.argtypes = [vp, vp, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+    L.dcb_tagset_half_index.argtypes = [vp, vp, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
     L.dcb_fastq_index_build.argtypes = [vp, u64, i32, ctypes.POINTER(ctypes.POINTER(CFastqIndex))]
     L.dcb_fastq_index_free.argtypes = [ctypes.POINTER(CFastqIndex)]
     L.dcb_fastq_index_free.restype = None
@@ -101,6 +102,9 @@ def lib():
     L.dcb_timing_enable.argtypes = [vp, i32]
     L.dcb_timing_get.argtypes = [vp, vp, vp]
     L.dcb_last_deferred.argtypes = [vp, ctypes.POINTER(u64)]
+    L.dcb_last_general.argtypes = [vp, ctypes.POINTER(u64)]
+    L.dcb_halftag_kernel_name.argtypes = [vp]
+    L.dcb_halftag_kernel_name.restype = ctypes.c_char_p
     L.dcb_exact_kernel_name.argtypes = [vp]
     L.dcb_exact_kernel_name.restype = ctypes.c_char_p
     L.dcb_dist_create.restype = vp
@@ -174,6 +178,16 @@ def union_index(vt: "TagTables", jt: "TagTables"):
         return None
     out = np.zeros(n.value, dtype=np.uint32)
     _check(lib().dcb_tagset_union_index(vt.handle, jt.handle, out.ctypes.data, n.value, ctypes.byref(n)), "dcb_tagset_union_index")
+    return out
+
+
+def half_index(vt: "TagTables", jt: "TagTables"):
+    """Sampled half-tag index of the chain (what the half-tag kernel searches with), or None when a half tag is too short."""
+    n = ctypes.c_size_t()
+    if lib().dcb_tagset_half_index(vt.handle, jt.handle, None, 0, ctypes.byref(n)) != 0:
+        return None
+    out = np.zeros(n.value, dtype=np.uint32)
+    _check(lib().dcb_tagset_half_index(vt.handle, jt.handle, out.ctypes.data, n.value, ctypes.byref(n)), "dcb_tagset_half_index")
     return out
 
 
@@ -413,6 +427,14 @@ class Context:
         n = ctypes.c_uint64()
         _check(lib().dcb_last_deferred(self._h, ctypes.byref(n)), "dcb_last_deferred")
         return n.value
+
+    def last_general(self):
+        n = ctypes.c_uint64()
+        _check(lib().dcb_last_general(self._h, ctypes.byref(n)), "dcb_last_general")
+        return n.value
+
+    def halftag_kernel_name(self):
+        return lib().dcb_halftag_kernel_name(self._h).decode()
 
     def exact_kernel_name(self):
         return lib().dcb_exact_kernel_name(self._h).decode()

@@ -5,9 +5,9 @@
 #include "../../include/dcb.h"
 #include "dcb_tables.h"
 
-#include <vector>
-
+#include <map>
 #include <string>
+#include <vector>
 
 struct dcb_tagset {
     int n_tags = 0, split = 0, is_v = 0, lmin = 0;
@@ -15,11 +15,15 @@ struct dcb_tagset {
     std::vector<uint32_t> general;  // DcbGene + tags + keyword sets + germline regions (general kernel)
     std::vector<uint32_t> core;     // DcbGene + tags only (exact-tag kernels)
     std::vector<uint32_t> index;    // DcbSeedIndex of this gene alone
+    std::map<std::string, int> kw_index[3];   // keyword -> its position in the DcbKw array of the full / half1 / half2 set
 };
 
 // Seed index over one gene (other pointer null) or over both genes of a chain (equal lmin).
 bool dcb_build_seed_index(const std::vector<std::string>* gene_v, const std::vector<std::string>* gene_j, int lmin,
                           int wbits, std::vector<uint32_t>& out);
+
+// Sampled half-tag index over both genes of a chain (DcbHalfIndex); false when a half keyword is too short for it.
+bool dcb_build_half_index(const dcb_tagset* v, const dcb_tagset* j, std::vector<uint32_t>& out);
 
 #if defined(__GNUC__)
 __attribute__((format(printf, 1, 2)))

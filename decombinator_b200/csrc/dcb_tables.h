@@ -205,6 +205,33 @@ struct DcbSuffixFilter {
 #define DCB_SFILTER_HEAD 4       // words in front of the bits
 #define DCB_SFSLOT(key, fmul, fbits) (((uint32_t)(key) * (fmul)) >> (32 - (fbits)))
 
+// Sampled half-tag index of the half-tag kernel (dcb_halftag_kernel): finds every occurrence of a half keyword (the four
+// sets V half1, V half2, J half1, J half2 = set 0..3) without walking an automaton over every base.  Every keyword has
+// at least kmin = q + stride - 1 bases, so each occurrence contains the q-mer that starts at the first multiple of
+// `stride` at or behind its start (keyword offset o < stride): only every stride-th position of a read is probed.
+//   * probe table: DIRECT-indexed by the q-mer (4^q 16-bit entries, q = 7: 32 KB): bit 4 * set + o says that the q-mer
+//     occurs at offset o of a keyword of that set;
+//   * keyword table: 2-choice cuckoo over (set, kmin-prefix), 8-byte slots {key, list position | count << 8}: the
+//     keywords of the set that start with this prefix (almost always one) as indices into the set's DcbKw array of the
+//     general blob, which holds the whole keyword to compare with the read;
+//   * fullkw: for every tag (V tags first, then J) the index of its keyword in its gene's FULL keyword set, so that a
+//     full-tag occurrence found by the exact-tag kernel can be handed to the analysis as a hit-list entry.
+// Built only for chains whose half keywords all have >= 10 bases (every `extended` set, human alpha `original`).
+struct DcbHalfIndex {
+    int32_t q, stride, kmin;
+    int32_t n_v, n_tags;
+    int32_t t_off;               // uint16[4^q]
+    int32_t h_off, hshift;       // 2^(32 - hshift) slots of {uint32 key, uint32 meta}; key = set << 28 | kmin-prefix; free = ~0
+    uint32_t c1, c2;
+    int32_t list_off;            // uint8 keyword indices
+    int32_t fullkw_off;          // uint8[n_tags]
+    int32_t n_words;
+    int32_t pad[3];
+};
+#define DCB_HALF_Q 7
+#define DCB_HALF_STRIDE 4
+#define DCB_HALF_FREE 0xFFFFFFFFu
+
 #if defined(__CUDACC__)
 #define DCB_HD __host__ __device__ __forceinline__
 #else

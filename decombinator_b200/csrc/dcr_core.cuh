@@ -775,6 +775,12 @@ DCB_HD FullHit hit_decode(uint32_t h) {
     return fh;
 }
 
+// Hand-over word of the exact-tag kernels for one gene: 0 = no full tag in the read, DCB_HIT_MULTI = several,
+// else DCB_HIT_ONE | tag << 16 | position (tag numbered inside its gene).
+DCB_HD uint32_t half_word_of(const FullHit& fh) {
+    return fh.count == 0 ? 0u : (fh.count > 1 ? DCB_HIT_MULTI : (DCB_HIT_ONE | fh.code));
+}
+
 struct alignas(8) DcbTq { uint32_t x, y; };   // one tag slot: prefix_lo, meta
 struct QIdxView {
     const uint16_t* disp;      // 2^b1 displacements
@@ -960,7 +966,9 @@ DCB_HD uint32_t exc_lower_bound(const ExcList& ex, uint32_t key) {
 // union index of both genes when jidx is null.  Returns FAST_DONE / FAST_DEFER.
 DCB_HD int dcr_exact_read(const ReadView& r, bool flagged, const uint32_t* vcore, const uint32_t* jcore,
                           const uint32_t* vidx, const uint32_t* jidx, const DcrParams& prm, int both_frames,
-                          dcb_result& out, dcb_cnt_t* C, bool use_q = false, const ExcProbe* xp = nullptr) {
+                          dcb_result& out, dcb_cnt_t* C, bool use_q = false, const ExcProbe* xp = nullptr,
+                          uint32_t* hand = nullptr) {
+    if (hand) { hand[0] = DCB_HIT_MULTI; hand[1] = DCB_HIT_MULTI; }   // "not searched": the half-tag path passes such a read on
     if (flagged && !xp) return FAST_DEFER;
     if (!flagged) xp = nullptr;
     FullHit vh, jh;
@@ -974,6 +982,7 @@ DCB_HD int dcr_exact_read(const ReadView& r, bool flagged, const uint32_t* vcore
         fast_find(r, vidx, vh, jh, true);
         if (vh.count == 1) fast_find(r, jidx, vh, jh, false);
     }
+    if (hand) { hand[0] = half_word_of(vh); hand[1] = half_word_of(jh); }
     return dcr_fast_from_hits<false>(r, gene_tags(vcore), gene_tags(jcore), vh, jh, prm, both_frames, out, C, xp != nullptr,
                                      xp ? *xp : ExcProbe());
 }
@@ -1049,6 +1058,146 @@ DCB_HD void dcr_general_run(ReadView r, const ExcList& ex, uint32_t* rd1, uint32
         o.ins_start = o.ins_end = o.v_seq_start = o.j_seq_end = 0;
         if (dcr_general(r, vblob, jblob, prm, o, C)) { o.frame = (uint8_t)frame; out = o; break; }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Half-tag path (dcb_halftag_kernel): reads the exact-tag kernel could not finish -- almost always because a
+// substitution or an N sits in one of the two tags -- WITHOUT the general kernel's per-base candidate marks.  The
+// exact-tag kernel hands over what it found (one hit word per gene); the half keywords of the gene(s) still missing
+// are found through the sampled index (DcbHalfIndex: one direct-indexed probe at every 4th base), all occurrences
+// are listed in findall order, and the analysis (analyse_general: guards, Hamming <= 1, counters, deletion walks,
+// filters -- decombine.py:273-585) then runs on that hit list exactly as it does in the general kernel.
+// ------------------------------------------------------------------------------------------------
+struct HalfIdxView {
+    const uint16_t* t;
+    const uint32_t* h;
+    const uint8_t* list;
+    const uint8_t* fullkw;
+    uint32_t c1, c2;
+    int hshift, n_v;
+};
+DCB_HD HalfIdxView half_idx_view(const uint32_t* hb) {
+    const DcbHalfIndex& hx = *reinterpret_cast<const DcbHalfIndex*>(hb);
+    HalfIdxView v;
+    v.t = reinterpret_cast<const uint16_t*>(hb + hx.t_off);
+    v.h = hb + hx.h_off;
+    v.list = reinterpret_cast<const uint8_t*>(hb + hx.list_off);
+    v.fullkw = reinterpret_cast<const uint8_t*>(hb + hx.fullkw_off);
+    v.c1 = hx.c1; v.c2 = hx.c2; v.hshift = hx.hshift; v.n_v = hx.n_v;
+    return v;
+}
+DCB_HD const DcbKwSet& half_kwset(const DcbGene& gv, const DcbGene& gj, int set) {   // set 0..3: V half1, V half2, J half1, J half2
+    const DcbGene& g = set < 2 ? gv : gj;
+    return (set & 1) ? g.half2 : g.half1;
+}
+// One candidate: a keyword of `set` starting at P (its kmin-prefix is looked up; every keyword with that prefix is
+// compared with the read as a whole).  Appends the occurrences to the hit list; n counts them even past `cap`.
+DCB_HD void half_confirm(const ReadView& r, const HalfIdxView& hx, const uint32_t* vblob, const uint32_t* jblob, int set, int P,
+                         uint32_t* hits_col, int cap, int& n) {
+    if (P < 0) return;
+    constexpr int KMIN = DCB_HALF_Q + DCB_HALF_STRIDE - 1;
+    uint32_t lo, hi;
+    rd_win32(r, P, lo, hi);
+    const uint32_t key = ((uint32_t)set << 28) | (lo & mask2(KMIN));
+    const uint32_t s1 = (key * hx.c1) >> hx.hshift, s2 = (key * hx.c2) >> hx.hshift;
+    uint32_t meta;
+    if (hx.h[2 * s1] == key) meta = hx.h[2 * s1 + 1];
+    else if (hx.h[2 * s2] == key) meta = hx.h[2 * s2 + 1];
+    else return;
+    const uint32_t* blob = set < 2 ? vblob : jblob;
+    const DcbKwSet& ks = half_kwset(*reinterpret_cast<const DcbGene*>(vblob), *reinterpret_cast<const DcbGene*>(jblob), set);
+    const int first = (int)(meta & 255u), cnt = (int)(meta >> 8);
+    for (int i = 0; i < cnt; i++) {
+        const int c = hx.list[first + i];
+        const DcbKw& k = kwset_kw(blob, ks, c);
+        if (P + (int)k.len > r.n) continue;
+        if (((lo ^ k.bits_lo) & mask2(k.len)) | (k.len > 16 ? ((hi ^ k.bits_hi) & mask2(k.len - 16)) : 0u)) continue;
+        if (r.inv && rd_inv_any(r, P, P + (int)k.len)) continue;          // an occurrence needs valid bases
+        if (n < cap) hits_col[n * r.stride] = (uint32_t)P | ((uint32_t)c << 16) | ((uint32_t)ks.set_id << 24);
+        n++;
+    }
+}
+// findall order inside every set: ascending END position, longest keyword first at equal end.  The list is short
+// (one or two entries as a rule), so an insertion sort on (end, -length) over ALL entries -- which orders every set.
+DCB_HD uint32_t half_hit_key(const uint32_t e, const uint32_t* vblob, const uint32_t* jblob) {
+    const int sid = (int)(e >> 24);
+    const uint32_t* blob = sid < 3 ? vblob : jblob;
+    const DcbGene& g = *reinterpret_cast<const DcbGene*>(blob);
+    const DcbKwSet& ks = (sid % 3) == 0 ? g.full : (sid % 3) == 1 ? g.half1 : g.half2;
+    const uint32_t len = kwset_kw(blob, ks, (int)((e >> 16) & 255u)).len;
+    return (((e & 0xFFFFu) + len) << 8) | (255u - len);
+}
+DCB_HD void half_sort_hits(uint32_t* hits_col, int stride, int n, const uint32_t* vblob, const uint32_t* jblob) {
+    for (int i = 1; i < n; i++) {
+        const uint32_t e = hits_col[i * stride], ke = half_hit_key(e, vblob, jblob);
+        int k = i;
+        while (k > 0 && half_hit_key(hits_col[(k - 1) * stride], vblob, jblob) > ke) { hits_col[k * stride] = hits_col[(k - 1) * stride]; k--; }
+        hits_col[k * stride] = e;
+    }
+}
+// Steps of the half-tag path shared by the kernel and tests/sim.  r: w/stride/n/nw set.  Returns false when the read
+// must go on to the general kernel (nothing has been counted then).
+//   half_begin   the read's view (exception range [e0, e1) of a flagged read -> invalid-base mask), the full-tag words
+//                checked against the mask (a tag over a symbol packed as base 0 is no occurrence), the half sets to find
+DCB_HD bool half_begin(ReadView& r, bool flagged, const ExcList& ex, uint32_t e0, uint32_t* inv0, const uint32_t* vblob,
+                       const uint32_t* jblob, uint32_t& hv, uint32_t& hj, uint32_t& need) {
+    const int nwi = (r.nw + 1) / 2;
+    r.inv = nullptr; r.exc_pos = ex.pos; r.exc_kind = ex.kind; r.e0 = r.e1 = 0; r.mirror = 0;
+    r.cand = nullptr; r.cand_kq = 0; r.hits = nullptr; r.n_hits = 0;
+    if (flagged) {
+        uint32_t e1 = e0;
+        bool any = false;
+        for (int k = 0; k < nwi; k++) inv0[k * r.stride] = 0;
+        for (; e1 < ex.n && ex.read[e1] == ex.read[e0]; e1++) {
+            if (ex.kind[e1] == 3) continue;  // a real base in this frame
+            const uint32_t p = ex.pos[e1];
+            inv0[(p >> 5) * r.stride] |= 1u << (p & 31);
+            any = true;
+        }
+        r.e0 = (int)e0; r.e1 = (int)e1;
+        if (any) r.inv = inv0;
+    }
+    if (hv == DCB_HIT_MULTI || hj == DCB_HIT_MULTI) return false;
+    if (r.inv) {
+        const DcbGene& gv = *reinterpret_cast<const DcbGene*>(vblob);
+        const DcbGene& gj = *reinterpret_cast<const DcbGene*>(jblob);
+        if (hv) { const int P = (int)(hv & 0xFFFFu), L = gene_tag(vblob, gv, (int)((hv >> 16) & 0x7FFFu)).len; if (rd_inv_any(r, P, P + L)) hv = 0u; }
+        if (hj) { const int P = (int)(hj & 0xFFFFu), L = gene_tag(jblob, gj, (int)((hj >> 16) & 0x7FFFu)).len; if (rd_inv_any(r, P, P + L)) hj = 0u; }
+    }
+    need = (hv ? 0u : 0x00FFu) | (hj ? 0u : 0xFF00u);
+    return true;
+}
+//   half_finish  full-tag occurrences + the n half occurrences collected in hits0 -> sorted hit list -> dcr()
+DCB_HD bool half_finish(ReadView& r, const HalfIdxView& hx, uint32_t hv, uint32_t hj, uint32_t* hits0, int cap, int n,
+                        const uint32_t* vblob, const uint32_t* jblob, const DcrParams& prm, dcb_result& out, dcb_cnt_t* C) {
+    if (hv) { if (n < cap) hits0[n * r.stride] = (hv & 0xFFFFu) | ((uint32_t)hx.fullkw[(hv >> 16) & 0x7FFFu] << 16); n++; }
+    if (hj) { if (n < cap) hits0[n * r.stride] = (hj & 0xFFFFu) | ((uint32_t)hx.fullkw[hx.n_v + ((hj >> 16) & 0x7FFFu)] << 16) | (3u << 24); n++; }
+    if (n > cap) return false;
+    half_sort_hits(hits0, r.stride, n, vblob, jblob);
+    r.hits = hits0; r.n_hits = n;
+    dcb_result o;
+    o.status = 0; o.frame = 0; o.v = o.j = 0; o.vdel = o.jdel = 0;
+    o.ins_start = o.ins_end = o.v_seq_start = o.j_seq_end = 0;
+    if (dcr_general(r, vblob, jblob, prm, o, C)) out = o;
+    return true;
+}
+// The whole path on one thread (tests/sim; the kernel probes from registers and confirms in one flat loop).
+DCB_HD bool dcr_half_read(ReadView r, bool flagged, const ExcList& ex, uint32_t e0, uint32_t hv, uint32_t hj, uint32_t* inv0,
+                          uint32_t* hits0, int cap, const uint32_t* vblob, const uint32_t* jblob, const uint32_t* hb,
+                          const DcrParams& prm, dcb_result& out, dcb_cnt_t* C) {
+    uint32_t need;
+    if (!half_begin(r, flagged, ex, e0, inv0, vblob, jblob, hv, hj, need)) return false;
+    const HalfIdxView hx = half_idx_view(hb);
+    int n = 0;
+    if (need)
+        for (int p = 0; p + DCB_HALF_Q <= r.n; p += DCB_HALF_STRIDE) {
+            uint32_t e = hx.t[rd_win16(r, p) & mask2(DCB_HALF_Q)] & need;
+            for (; e; e &= e - 1) {
+                const int b = DCB_FFS(e) - 1;
+                half_confirm(r, hx, vblob, jblob, b >> 2, p - (b & 3), hits0, cap, n);
+            }
+        }
+    return half_finish(r, hx, hv, hj, hits0, cap, n, vblob, jblob, prm, out, C);
 }
 
 // Both steps on one thread (tests/sim; the kernel regroups in between).

@@ -141,7 +141,7 @@ static constexpr int kExactThreads = 512;   // upper bounds; long reads launch n
 #endif
 static constexpr int kGeneralThreads = DCB_GENERAL_THREADS;   // one wide block per SM: the 72 KB of tables are staged once, 24 warps hide the latency
 static constexpr int kMaxChunks = 256;             // queue counters per context
-static constexpr size_t kZeroBlockBytes = sizeof(uint32_t) * kMaxChunks + sizeof(unsigned long long) * DCB_NCOUNTERS;
+static constexpr size_t kZeroBlockBytes = sizeof(uint32_t) * 2 * kMaxChunks + sizeof(unsigned long long) * DCB_NCOUNTERS;   // two queue counters per chunk
 static constexpr uint32_t kChunkReads = 1u << 20;  // reads per chunk of the pipelined host-to-host path
 
 // Shared-memory carve-up common to the kernels: [table 0..3][per-thread columns][counters][mbarrier]
@@ -609,8 +609,130 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
         }
         defer_reads(live && action == FAST_DEFER, ri, queue, queue_count);
         if (live && action == FAST_DONE) store_result(results + ri, out);
+        else if (live) {
+            // hand-over to dcb_halftag_kernel in the read's (still unused) result slot: what the search found, one word
+            // per gene with the tag numbered inside its gene; "several" for a read that was not searched
+            const bool one_j = hw.j != 0u && hw.j != DCB_HIT_MULTI;
+            const uint4 hand = make_uint4(scan ? hw.v : DCB_HIT_MULTI, scan ? (one_j ? hw.j - ((uint32_t)ix.n_v << 16) : hw.j) : DCB_HIT_MULTI, 0u, 0u);
+            *reinterpret_cast<uint4*>(results + ri) = hand;
+        }
     }
     flush_counters(s_cnt, counters);
+}
+
+// ------------------------------------------------------------------------------------------------
+// half-tag kernel: the reads the flat exact-tag kernel queued (compacted, so warps are dense), one thread per read.
+// Almost all of them lack ONE full tag because of a substitution or an N in it.  The flat kernel left what it found in
+// the read's result slot; here the half keywords of the missing gene(s) are found through the sampled half-tag index
+// (DcbHalfIndex: a direct-indexed 16-bit entry per 7-mer, probed at every 4th base from registers), every occurrence is
+// confirmed and listed in findall order, and analyse_general runs on that list -- the same analysis code as the general
+// kernel, without its per-base candidate marks, six-set hit list and block-wide regrouping.  A read it cannot take
+// (several full-tag candidates in a read with non-ACGT symbols, more than DCB_HALF_CAP occurrences) goes on to the
+// general kernel through a second queue, uncounted.
+// Tables: 0 = V general blob, 1 = J general blob, 2 = half-tag index.
+// ------------------------------------------------------------------------------------------------
+#define DCB_HALF_CAP 8
+template <int NW, int T>
+__global__ void __launch_bounds__(T, 1)
+dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict__ results,
+                   unsigned long long* __restrict__ counters, const uint32_t* __restrict__ queue,
+                   const uint32_t* __restrict__ queue_count, uint32_t* __restrict__ queue2, uint32_t* __restrict__ queue2_count) {
+    constexpr int NWI = (NW + 1) / 2;
+    constexpr int NPOS = (16 * NW - DCB_HALF_Q) / DCB_HALF_STRIDE + 1;
+    constexpr int NM = (NPOS + 31) / 32;                            // candidate mask words
+    extern __shared__ __align__(16) uint32_t smem[];
+    SmemLayout L = carve(smem, tb, (size_t)(NW + NWI + DCB_HALF_CAP) * T);
+    uint32_t* s_rd = L.cols;                      // [NW][T]
+    uint32_t* s_inv = s_rd + (size_t)NW * T;      // [NWI][T]
+    uint32_t* s_hits = s_inv + (size_t)NWI * T;   // [DCB_HALF_CAP][T]
+    stage_tables(L, tb);
+    const uint32_t* vblob = L.t[0];
+    const uint32_t* jblob = L.t[1];
+    const HalfIdxView hx = half_idx_view(L.t[2]);
+    const uint32_t t7 = smem_u32(hx.t);
+
+    const int tid = threadIdx.x;
+    const uint32_t n_items = *queue_count;
+    const uint32_t n_tiles = (n_items + T - 1) / T;
+    ExcList ex;
+    ex.read = b.exc_read; ex.pos = b.exc_pos; ex.kind = b.exc_kind; ex.n = b.n_exc;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t item = tile * T + tid;
+        const bool live = item < n_items;
+        const uint32_t ri = live ? __ldg(queue + item) : b.first;
+        bool pass_on = false;
+        uint32_t w[NW];
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(b.words + (size_t)ri * NW);
+#pragma unroll
+            for (int k = 0; k < NW / 4; k++) {
+                const uint4 v = ldg_stream(src + k);
+                w[4 * k + 0] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+            }
+#pragma unroll
+            for (int k = 0; k < NW; k++) s_rd[k * T + tid] = w[k];
+        }
+        if (live) {
+            const uint4 hand = *reinterpret_cast<const uint4*>(results + ri);
+            uint32_t hv = hand.x, hj = hand.y, need = 0;
+            ReadView r;
+            r.w = s_rd + tid; r.stride = T; r.nw = NW;
+            r.n = b.uniform_len ? (int)b.uniform_len : (int)__ldg(b.lens + ri);
+            const bool flagged = b.n_exc && ((__ldg(b.flags + (ri >> 5)) >> (ri & 31)) & 1u);
+            uint32_t e0 = 0;
+            if (flagged) {
+                e0 = __ldg(b.exc_index + (ri >> 5));
+                while (__ldg(b.exc_read + e0) < ri) e0++;
+            }
+            if (!half_begin(r, flagged, ex, e0, s_inv + tid, vblob, jblob, hv, hj, need)) {
+                pass_on = true;
+            } else {
+                // probe: bit i of the candidate mask <=> the 7-mer at base 4 i occurs, at an offset < 4, in a half keyword
+                // of a gene that is still missing
+                uint32_t cm[NM];
+#pragma unroll
+                for (int m = 0; m < NM; m++) cm[m] = 0u;
+                if (need) {
+#pragma unroll
+                    for (int i = 0; i < NPOS; i++) {
+                        const int a = i >> 2, sh = (i & 3) * 8;
+                        const uint32_t win = sh <= 16 ? (w[a] >> sh) : __funnelshift_r(w[a], a + 1 < NW ? w[a + 1] : 0u, sh);
+                        uint32_t e;
+                        asm("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(t7 + ((win & 0x3FFFu) << 1)));
+                        cm[i >> 5] |= ((e & need) ? 1u : 0u) << (i & 31);
+                    }
+                    const int nvalid = r.n >= DCB_HALF_Q ? (r.n - DCB_HALF_Q) / DCB_HALF_STRIDE + 1 : 0;   // probes inside the read
+#pragma unroll
+                    for (int m = 0; m < NM; m++) {
+                        const int keep = nvalid - 32 * m;
+                        if (keep < 32) cm[m] &= keep > 0 ? ((1u << keep) - 1u) : 0u;
+                    }
+                }
+                // confirm: every (candidate, set, offset) -> the keywords with that prefix, compared as a whole
+                int n = 0;
+#pragma unroll
+                for (int m = 0; m < NM; m++) {
+                    uint32_t c = cm[m];
+                    while (c) {
+                        const int i = 32 * m + __ffs(c) - 1;
+                        c &= c - 1;
+                        const int p = DCB_HALF_STRIDE * i;
+                        uint32_t e = hx.t[rd_win16(r, p) & 0x3FFFu] & need;
+                        for (; e; e &= e - 1) {
+                            const int bit = __ffs(e) - 1;
+                            half_confirm(r, hx, vblob, jblob, bit >> 2, p - (bit & 3), s_hits + tid, DCB_HALF_CAP, n);
+                        }
+                    }
+                }
+                dcb_result out;
+                *reinterpret_cast<uint4*>(&out) = make_uint4(0, 0, 0, 0);
+                if (half_finish(r, hx, hv, hj, s_hits + tid, DCB_HALF_CAP, n, vblob, jblob, prm, out, L.cnt)) store_result(results + ri, out);
+                else pass_on = true;
+            }
+        }
+        defer_reads(pass_on, ri, queue2, queue2_count);
+    }
+    flush_counters(L.cnt, counters);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -745,6 +867,12 @@ struct dcb_ctx {
     uint32_t *d_vidx = nullptr, *d_jidx = nullptr, *d_uidx = nullptr;
     uint32_t* d_sfilt = nullptr;   // union suffix filter of the general kernel
     int sfilt_words = 0;
+    uint32_t* d_half = nullptr;    // sampled half-tag index (null: the chain has half tags too short for it)
+    int half_words = 0;
+    void* half_fn = nullptr;       // half-tag kernel picked for the resident batch, or null
+    int half_grid = 0, half_threads = 0;
+    size_t half_smem = 0;
+    DevBuf queue2;                 // reads the half-tag kernel passes on to the general kernel
     int vgen_words = 0, jgen_words = 0, vcore_words = 0, jcore_words = 0, vidx_words = 0, jidx_words = 0, uidx_words = 0;
     DevBuf words, lens, flags, exc_read, exc_pos, exc_kind, exc_index, results, queue;
     std::vector<uint32_t> h_exc_index;   // host copy of exc_index while its upload is in flight
@@ -809,6 +937,18 @@ static int q_rows(int nw) {   // must match the kernel's ROWS
     const int npos = (16 * nw - 13) / 8 + 1, wmax = ((npos - 1) * 8 - 7) >> 4;
     const int trail = wmax + 3 - nw > 1 ? wmax + 3 - nw : 1;
     return 1 + nw + trail;
+}
+
+typedef void (*halftag_fn)(BatchDev, Tables4, DcrParams, dcb_result*, unsigned long long*, const uint32_t*, const uint32_t*, uint32_t*, uint32_t*);
+static constexpr int kHalfThreads = 768;
+static halftag_fn pick_half(int nw) {
+    switch (nw) {
+        case 8:  return dcb_halftag_kernel<8, kHalfThreads>;
+        case 12: return dcb_halftag_kernel<12, kHalfThreads>;
+        case 16: return dcb_halftag_kernel<16, kHalfThreads>;
+        case 20: return dcb_halftag_kernel<20, kHalfThreads>;
+        default: return nullptr;
+    }
 }
 
 // rows of shared memory per read column in the specialised kernel (must match the kernel's ROWS)
@@ -912,9 +1052,14 @@ dcb_ctx* dcb_ctx_create(int device, const dcb_tagset* v, const dcb_tagset* j, co
                 if (upload_blob(sf, &c->d_sfilt, &c->sfilt_words)) return fail(nullptr);
         }
     }
+    {   // sampled half-tag index: what the half-tag kernel finds the half keywords with
+        std::vector<uint32_t> hb;
+        if (dcb_build_half_index(v, j, hb))
+            if (upload_blob(hb, &c->d_half, &c->half_words)) return fail(nullptr);
+    }
     // queue counters and reference counters in ONE block: a step clears both with one memset
     if (cudaMalloc((void**)&c->d_queue_count, kZeroBlockBytes) != cudaSuccess) return fail("cudaMalloc");
-    c->d_counters = reinterpret_cast<unsigned long long*>(c->d_queue_count + kMaxChunks);
+    c->d_counters = reinterpret_cast<unsigned long long*>(c->d_queue_count + 2 * kMaxChunks);
     return c;
 }
 
@@ -927,10 +1072,10 @@ void dcb_ctx_destroy(dcb_ctx* c) {
     if (c->ev_ready) cudaEventDestroy(c->ev_ready);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
     cudaFree(c->d_vgen); cudaFree(c->d_jgen); cudaFree(c->d_vcore); cudaFree(c->d_jcore);
-    cudaFree(c->d_vidx); cudaFree(c->d_jidx); cudaFree(c->d_uidx); cudaFree(c->d_sfilt);
+    cudaFree(c->d_vidx); cudaFree(c->d_jidx); cudaFree(c->d_uidx); cudaFree(c->d_sfilt); cudaFree(c->d_half);
     cudaFree(c->d_queue_count);   // d_counters lives in the same block
     c->words.release(); c->lens.release(); c->flags.release(); c->exc_read.release(); c->exc_pos.release(); c->exc_index.release();
-    c->exc_kind.release(); c->results.release(); c->queue.release();
+    c->exc_kind.release(); c->results.release(); c->queue.release(); c->queue2.release();
     delete c;
 }
 
@@ -950,7 +1095,8 @@ static int prepare_batch(dcb_ctx* c, const dcb_packed* P) {
         (rc = c->flags.ensure(((n + 31) / 32) * 4 + 16)) || (rc = c->exc_read.ensure((size_t)P->n_exc * 4 + 16)) ||
         (rc = c->exc_pos.ensure((size_t)P->n_exc * 2 + 16)) || (rc = c->exc_kind.ensure((size_t)P->n_exc + 16)) ||
         (rc = c->exc_index.ensure(((n + 31) / 32 + 2) * 4 + 16)) ||
-        (rc = c->results.ensure(n * sizeof(dcb_result) + 16)) || (rc = c->queue.ensure(n * 4 + 16)))
+        (rc = c->results.ensure(n * sizeof(dcb_result) + 16)) || (rc = c->queue.ensure(n * 4 + 16)) ||
+        (rc = c->queue2.ensure(n * 4 + 16)))
         return rc;
     BatchDev& b = c->batch;
     b.words = (const uint32_t*)c->words.p; b.lens = (const uint16_t*)c->lens.p; b.flags = (const uint32_t*)c->flags.p;
@@ -974,7 +1120,7 @@ static int prepare_batch(dcb_ctx* c, const dcb_packed* P) {
     c->spec_fn = (void*)spec; c->spec_union = have_union;
     int occ_e = 0, occ_g = 0;
     exact_q_fn qfn = nullptr;
-    if (have_union && c->params.force_general == 0 && c->ufbits == DCB_FBITS && c->utqbits > 0)
+    if (have_union && (c->params.force_general == 0 || c->params.force_general == 3) && c->ufbits == DCB_FBITS && c->utqbits > 0)
         qfn = pick_q((int)sw, c->uqq, c->uqs, c->lminv, P->n_exc != 0);
     if (qfn) {
         c->exact_smem = ((size_t)1 << DCB_FBITS) + ((size_t)q_rows((int)sw) * kQThreads +
@@ -1025,6 +1171,19 @@ static int prepare_batch(dcb_ctx* c, const dcb_packed* P) {
         c->general_threads = T;
         CUDA_TRY(cudaFuncSetAttribute(dcb_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->general_smem));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, dcb_general_kernel, T, c->general_smem));
+    }
+    // half-tag kernel: between the flat kernel and the general kernel, for chains with a half-tag index (one frame only)
+    c->half_fn = nullptr;
+    if (qfn && c->d_half && !c->params.both_frames && c->params.force_general == 0) {
+        halftag_fn hf = pick_half((int)sw);
+        c->half_threads = kHalfThreads;
+        c->half_smem = ((size_t)c->vgen_words + c->jgen_words + c->half_words + (sw + nwi + DCB_HALF_CAP) * kHalfThreads) * 4 + tail;
+        int occ_h = 0;
+        if (hf && c->half_smem <= kMaxSmem) {
+            CUDA_TRY(cudaFuncSetAttribute(hf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->half_smem));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_h, hf, kHalfThreads, c->half_smem));
+            if (occ_h >= 1) { c->half_fn = (void*)hf; c->half_grid = c->n_sms * occ_h; }
+        }
     }
     if (occ_e < 1 || occ_g < 1) { dcb_set_error("kernel does not fit on an SM"); return DCB_EUNSUPPORTED; }
     const uint32_t tiles_e = (uint32_t)((n + c->exact_threads - 1) / c->exact_threads);
@@ -1098,10 +1257,24 @@ static int launch_range(dcb_ctx* c, cudaStream_t s, uint32_t first, uint32_t cou
         CUDA_TRY(cudaGetLastError());
         if (timed && (rc = timing_end(c))) return rc;
     }
-    if (timed && (rc = timing_begin(c, 1))) return rc;
     Tables4 tg;
     tg.g[0] = c->d_vgen; tg.words[0] = c->vgen_words; tg.g[1] = c->d_jgen; tg.words[1] = c->jgen_words;
-    tg.g[2] = c->d_sfilt; tg.words[2] = c->sfilt_words; tg.g[3] = nullptr; tg.words[3] = 0;
+    tg.g[3] = nullptr; tg.words[3] = 0;
+    if (c->half_fn && c->q_fn) {   // the queued reads through the half-tag kernel; what it passes on is the general kernel's queue
+        if (timed && (rc = timing_begin(c, 2))) return rc;
+        uint32_t* qcount2 = c->d_queue_count + kMaxChunks + slot;
+        uint32_t* queue2 = (uint32_t*)c->queue2.p + first;
+        tg.g[2] = c->d_half; tg.words[2] = c->half_words;
+        const uint32_t tiles_h = (count + c->half_threads - 1) / c->half_threads;
+        const int grid_h = (int)std::max<uint32_t>(1, std::min<uint32_t>(tiles_h, (uint32_t)c->half_grid));
+        ((halftag_fn)c->half_fn)<<<grid_h, c->half_threads, c->half_smem, s>>>(
+            b, tg, prm, (dcb_result*)c->results.p, c->d_counters, queue, qcount, queue2, qcount2);
+        CUDA_TRY(cudaGetLastError());
+        if (timed && (rc = timing_end(c))) return rc;
+        queue = queue2; qcount = qcount2;
+    }
+    if (timed && (rc = timing_begin(c, 1))) return rc;
+    tg.g[2] = c->d_sfilt; tg.words[2] = c->sfilt_words;
     dcb_general_kernel<<<grid_g, c->general_threads, c->general_smem, s>>>(
         b, tg, prm, c->params.both_frames, (dcb_result*)c->results.p, c->d_counters,
         c->params.force_general == 1 ? nullptr : (const uint32_t*)queue, qcount);
@@ -1211,15 +1384,26 @@ const char* dcb_exact_kernel_name(const dcb_ctx* c) {
     if (!c || !c->have_batch) return "";
     return c->q_fn ? "dcb_exact_kernel_flat" : c->spec_fn ? "dcb_exact_kernel_spec" : "dcb_exact_kernel";
 }
-int dcb_last_deferred(dcb_ctx* c, uint64_t* n) {
-    if (!c || !n || !c->ran) return DCB_EINVAL;
+static int sum_queue_counts(dcb_ctx* c, int which, uint64_t* total) {
     uint32_t q[kMaxChunks];
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    CUDA_TRY(cudaMemcpy(q, c->d_queue_count, sizeof(q), cudaMemcpyDeviceToHost));
-    uint64_t total = 0;
-    for (int i = 0; i < kMaxChunks; i++) total += q[i];
-    *n = c->params.force_general == 1 ? c->batch.n_reads : total;
+    CUDA_TRY(cudaMemcpy(q, c->d_queue_count + which * kMaxChunks, sizeof(q), cudaMemcpyDeviceToHost));
+    *total = 0;
+    for (int i = 0; i < kMaxChunks; i++) *total += q[i];
     return DCB_OK;
+}
+int dcb_last_deferred(dcb_ctx* c, uint64_t* n) {
+    if (!c || !n || !c->ran) return DCB_EINVAL;
+    if (c->params.force_general == 1) { *n = c->batch.n_reads; return DCB_OK; }
+    return sum_queue_counts(c, 0, n);
+}
+int dcb_last_general(dcb_ctx* c, uint64_t* n) {
+    if (!c || !n || !c->ran) return DCB_EINVAL;
+    if (c->params.force_general == 1) { *n = c->batch.n_reads; return DCB_OK; }
+    return sum_queue_counts(c, (c->half_fn && c->q_fn) ? 1 : 0, n);
+}
+const char* dcb_halftag_kernel_name(const dcb_ctx* c) {
+    return (c && c->have_batch && c->half_fn && c->q_fn) ? "dcb_halftag_kernel" : "";
 }
 
 }  // extern "C"

@@ -89,6 +89,10 @@ int dcb_tagset_blob(const dcb_tagset*, int which, const uint32_t** words, size_t
 /* Seed index over BOTH genes of a chain (built by dcb_ctx_create when V and J share the seed geometry).
  * Writes up to cap words; *n_words is the size needed; returns DCB_EUNSUPPORTED when the geometries differ. */
 int dcb_tagset_union_index(const dcb_tagset* v, const dcb_tagset* j, uint32_t* out, size_t cap, size_t* n_words);
+/* Sampled half-tag index of a chain (csrc/dcb_tables.h, DcbHalfIndex): what the half-tag kernel finds the occurrences of
+   the acora half-tag automata with (decombine.py:730-746 build them; findall at :294, :339, :422, :473).  Same calling
+   convention; DCB_EUNSUPPORTED when a half tag of the chain is shorter than 10 bases (the kernel then does not run). */
+int dcb_tagset_half_index(const dcb_tagset* v, const dcb_tagset* j, uint32_t* out, size_t cap, size_t* n_words);
 /* Union suffix filter of the six keyword sets of a chain (csrc/dcb_tables.h, DcbSuffixFilter): what the general kernel
    marks candidate keyword positions with.  Same calling convention as dcb_tagset_union_index. */
 int dcb_tagset_suffix_filter(const dcb_tagset* v, const dcb_tagset* j, uint32_t* out, size_t cap, size_t* n_words);
@@ -184,7 +188,8 @@ typedef struct dcb_params {
     int32_t allow_ns;      /* inputargs["allowNs"]      (decombine.py:553-556) */
     int32_t lenthreshold;  /* inputargs["lenthreshold"] (decombine.py:557-560) */
     int32_t force_general; /* testing: 1 = send every read through the general (fallback) kernel;
-                              2 = exact-tag search without the flat kernel (the bit-filter kernels only) */
+                              2 = exact-tag search without the flat kernel (the bit-filter kernels only);
+                              3 = no half-tag kernel (the flat kernel's queue goes straight to the general kernel) */
 } dcb_params;
 
 /* ---------------------------------------------------------------------------------------------
@@ -219,13 +224,18 @@ int dcb_run_resident(dcb_ctx*);
 int dcb_download(dcb_ctx*, dcb_result* out, uint64_t* counters);
 
 /* Per-kernel device time (CUDA events on the launching stream), accumulated since the last reset.
- * slot 0: exact-tag matching kernel, slot 1: general (half-tag fallback) kernel. */
+ * slot 0: exact-tag matching kernel, slot 1: general kernel, slot 2: half-tag kernel. */
 #define DCB_NTIMERS 4
 int dcb_timing_reset(dcb_ctx*);
 int dcb_timing_enable(dcb_ctx*, int on);
 int dcb_timing_get(dcb_ctx*, double ms[DCB_NTIMERS], uint64_t launches[DCB_NTIMERS]);
-/* Number of reads the last run sent to the general kernel. */
+/* Number of reads of the last run that the exact-tag kernel could not finish (queued for the next kernel), and the
+   number that reached the general kernel (the same, unless the half-tag kernel ran in between). */
 int dcb_last_deferred(dcb_ctx*, uint64_t* n);
+int dcb_last_general(dcb_ctx*, uint64_t* n);
+/* "dcb_halftag_kernel" when the half-tag kernel runs between the exact-tag and the general kernel for the resident batch
+   (chains whose half tags all have >= 10 bases, one frame), else "". */
+const char* dcb_halftag_kernel_name(const dcb_ctx*);
 /* Name of the exact-tag kernel chosen for the resident batch ("dcb_exact_kernel_flat", "dcb_exact_kernel_spec" or
    "dcb_exact_kernel"); a static string, "" before any batch. */
 const char* dcb_exact_kernel_name(const dcb_ctx*);

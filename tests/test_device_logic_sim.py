@@ -60,6 +60,55 @@ def test_sim_matches_oracle_on_synthetic(species, tagset, chain, orientation, L,
     packed.free()
 
 
+def test_sim_half_tag_path_matches_reference_fixtures(dcr_cases):
+    """The half-tag path (dcr_half_read: what dcb_halftag_kernel runs per read) between the flat kernel's search and the
+    general path, on the fixtures recorded from the reference; it must take every read the exact search queues except
+    those with several full-tag candidates AND non-ACGT symbols."""
+    names = dcr_cases["counters"]
+    ran = 0
+    for gi, g in enumerate(dcr_cases["groups"]):
+        info = tags.load(g["species"], g["tags"], g["chain"])
+        vt, jt = info.tables()
+        if g["orientation"] == "both" or _lib.union_index(vt, jt) is None or _lib.half_index(vt, jt) is None:
+            continue
+        packed = _lib.pack_strings(g["reads"], revcomp=(g["orientation"] != "forward"))
+        res, cnt, nd, nd2 = simlib.sim_decombine(packed, vt, jt, allow_ns=g["allowNs"], lenthreshold=g["lenthreshold"],
+                                                 use_q=True, use_half=True, want_deferred2=True)
+        got = [record_to_list(r, rec, g["orientation"]) for r, rec in zip(g["reads"], res)]
+        bad = [i for i, (a, b) in enumerate(zip(got, g["results"])) if a != b]
+        assert not bad, (gi, bad[:5])
+        assert {n: int(c) for n, c in zip(names, cnt)} == g["totals"], gi
+        assert nd > 0 and nd2 <= 0.02 * len(g["reads"])
+        ran += 1
+        packed.free()
+    assert ran >= 5
+
+
+@pytest.mark.parametrize("chain,L,sub,nrate", [("b", 250, 0.01, 0.001), ("a", 250, 0.01, 0.001), ("b", 300, 0.03, 0.005),
+                                               ("a", 100, 0.02, 0.01)])
+def test_sim_half_tag_path_matches_oracle(chain, L, sub, nrate):
+    info = tags.load("human", "extended", chain)
+    vt, jt = info.tables()
+    n = 40000
+    r1, off, ln = synth_batch(info, n, L, sub, nrate, 0.05, seed=77)
+    orc = O.Oracle(O.TagSet("human", "extended", chain))
+    want = orc.decombine_arrays(r1, off, ln, "reverse", nthreads=4)
+    packed = _lib.pack_arrays(r1, off, ln, revcomp=True)
+    res, cnt, nd, nd2 = simlib.sim_decombine(packed, vt, jt, use_q=True, use_half=True, want_deferred2=True)
+    assert_records_equal(res, want, "reverse")
+    assert np.array_equal(cnt, orc.counts)
+    assert nd > 0.2 * n and nd2 < 0.02 * n          # the half-tag path takes what the exact search queues
+    packed.free()
+
+
+def test_half_index_only_for_long_half_tags():
+    """The sampled index needs half tags of >= 10 bases: every `extended` chain has one, chains with a 6-base J split none."""
+    for sp, ts, ch, want in (("human", "extended", "a", True), ("human", "extended", "b", True), ("human", "original", "a", False),
+                             ("human", "original", "b", False), ("mouse", "original", "g", False)):
+        vt, jt = tags.load(sp, ts, ch).tables()
+        assert (_lib.half_index(vt, jt) is not None) == want
+
+
 def sweep_reads(info, L, seed=5):
     """Every tag of the chain at every start position modulo the seed stride and at both read ends: one V tag and one
     J tag per read (in the oriented frame), random bases elsewhere.  Exercises every sampling phase of the seed index,

@@ -56,7 +56,8 @@ def test_shard_bounds_cover_in_order():
 
 def test_barcode_owner_is_stable():
     from decombinator_b200.parallel import barcode_owner
-    assert [barcode_owner("ACGTACGTACGT", w) for w in (1, 2, 4, 8)] == [0, 1, 1, 5] or True  # values are an implementation detail
+    assert barcode_owner("ACGTACGTACGT", 1) == 0
+    assert all(0 <= barcode_owner("ACGTACGTACGT", w) < w for w in (2, 3, 4, 8))
     assert barcode_owner("ACGTACGTACGT", 8) == barcode_owner("ACGTACGTACGT", 8)
     owners = {barcode_owner("".join("ACGT"[(i >> (2 * k)) & 3] for k in range(6)), 4) for i in range(4096)}
     assert owners == {0, 1, 2, 3}
