@@ -105,7 +105,7 @@ def run_cfg2(args, rank, world, local_rank, host_threads, stream, barrier):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     out = {"workload": "synthetic 250-nt reads, one mixed file (even reads human alpha, odd reads human beta), extended tag sets, "
-                       "1 % substitutions + 0.1 % N per base, analysed once per chain (BASELINE configs[2] shape, %d reads per GPU)" % n,
+                       "1 %% substitutions + 0.1 %% N per base, analysed once per chain (BASELINE configs[2] shape, %d reads per GPU)" % n,
            "seed": seed, "steps": steps, "chains": {}}
     total_ms = 0.0
     for chain, info in (("a", ia), ("b", ib)):

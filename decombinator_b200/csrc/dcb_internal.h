@@ -15,7 +15,6 @@ struct dcb_tagset {
     std::vector<uint32_t> general;  // DcbGene + tags + keyword sets + germline regions (general kernel)
     std::vector<uint32_t> core;     // DcbGene + tags only (exact-tag kernels)
     std::vector<uint32_t> index;    // DcbSeedIndex of this gene alone
-    std::map<std::string, int> kw_index[3];   // keyword -> its position in the DcbKw array of the full / half1 / half2 set
 };
 
 // Seed index over one gene (other pointer null) or over both genes of a chain (equal lmin).

@@ -211,20 +211,26 @@ struct DcbSuffixFilter {
 // `stride` at or behind its start (keyword offset o < stride): only every stride-th position of a read is probed.
 //   * probe table: DIRECT-indexed by the q-mer (4^q 16-bit entries, q = 7: 32 KB): bit 4 * set + o says that the q-mer
 //     occurs at offset o of a keyword of that set;
-//   * keyword table: 2-choice cuckoo over (set, kmin-prefix), 8-byte slots {key, list position | count << 8}: the
-//     keywords of the set that start with this prefix (almost always one) as indices into the set's DcbKw array of the
-//     general blob, which holds the whole keyword to compare with the read;
-//   * fullkw: for every tag (V tags first, then J) the index of its keyword in its gene's FULL keyword set, so that a
-//     full-tag occurrence found by the exact-tag kernel can be handed to the analysis as a hit-list entry.
-// Built only for chains whose half keywords all have >= 10 bases (every `extended` set, human alpha `original`).
+//   * keyword table: 2-choice cuckoo over (set, kmin-prefix), 8-byte slots {key, position | count << 8}: the keywords
+//     of the set that start with this prefix (almost always one), as a run of `ids`, each naming a DcbHalfKw record:
+//     the whole keyword to compare with the read, the length of the FIRST tag that has this half (the reference's
+//     length guard, decombine.py:302-307) and the tags that share it, ascending.
+// Built only for chains whose half keywords all have >= 10 bases (every `extended` set).
+struct alignas(16) DcbHalfKw {
+    uint32_t bits_lo, bits_hi;   // packed keyword
+    uint8_t len, first_len, n_tags, set;
+    uint16_t tags_off, pad;      // tag ids (inside the gene) in the tag-id list
+};
 struct DcbHalfIndex {
     int32_t q, stride, kmin;
     int32_t n_v, n_tags;
+    int32_t v_split, j_split;
     int32_t t_off;               // uint16[4^q]
     int32_t h_off, hshift;       // 2^(32 - hshift) slots of {uint32 key, uint32 meta}; key = set << 28 | kmin-prefix; free = ~0
     uint32_t c1, c2;
-    int32_t list_off;            // uint8 keyword indices
-    int32_t fullkw_off;          // uint8[n_tags]
+    int32_t ids_off;             // uint8: keyword record numbers, grouped by (set, prefix)
+    int32_t kw_off, n_kw;        // DcbHalfKw[n_kw]
+    int32_t tags_off;            // uint8 tag ids
     int32_t n_words;
     int32_t pad[3];
 };

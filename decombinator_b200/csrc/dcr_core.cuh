@@ -688,13 +688,16 @@ DCB_HD void rd_win32x(const ReadView& r, int p, uint32_t& lo, uint32_t& hi) {
 
 // Fast V: exactly the interior case of get_v_deletions (decombine.py:749-785).  Returns
 //   1 handled (end_v / dels set), 0 defer to the general kernel.
+// ri: the read's invalid-base column (01 per non-ACGT symbol, the read's own layout) or null: an invalid base never matches.
 template <bool PADDED>
-DCB_HD int fast_v_deletions(const ReadView& r, const DcbTagFin& t, int temp_end_v, int& end_v, int& dels) {
+DCB_HD int fast_v_deletions(const ReadView& r, const DcbTagFin& t, int temp_end_v, int& end_v, int& dels, const ReadView* ri = nullptr) {
     const int f0 = temp_end_v + 1;
     if (!t.edge_ok || f0 >= r.n || f0 < 32) return 0;
     uint32_t lo, hi, rl, rh;
     rd_win32x<PADDED>(r, f0 - 32, lo, hi);
-    run10(lo ^ t.edge_lo, hi ^ t.edge_hi, rl, rh);
+    lo ^= t.edge_lo; hi ^= t.edge_hi;
+    if (ri) { uint32_t ilo, ihi; rd_win32x<PADDED>(*ri, f0 - 32, ilo, ihi); lo |= ilo; hi |= ihi; }
+    run10(lo, hi, rl, rh);
     // window index i <-> deletions nd = 22 - i; want the smallest nd, i.e. the highest i <= 22 (bits 2i, i <= 22)
     rh &= (1u << 14) - 1u;
     if (!(rl | rh)) return 0;
@@ -706,7 +709,8 @@ DCB_HD int fast_v_deletions(const ReadView& r, const DcbTagFin& t, int temp_end_
 
 // Fast J: the interior case of get_j_deletions (decombine.py:788-817).
 template <bool PADDED>
-DCB_HD int fast_j_deletions(const ReadView& r, const DcbTagFin& t, int temp_start_j, int end_of_v, int& start_j, int& dels) {
+DCB_HD int fast_j_deletions(const ReadView& r, const DcbTagFin& t, int temp_start_j, int end_of_v, int& start_j, int& dels,
+                            const ReadView* ri = nullptr) {
     if (!t.edge_ok || temp_start_j < 0) return 0;
     if (PADDED && temp_start_j >= 16 * (r.nw - 1)) return 0;   // the window would leave the padded columns
     int pos0 = end_of_v - temp_start_j;
@@ -717,7 +721,9 @@ DCB_HD int fast_j_deletions(const ReadView& r, const DcbTagFin& t, int temp_star
     if (imax > 22) imax = 22;
     uint32_t lo, hi, rl, rh;
     rd_win32x<PADDED>(r, temp_start_j, lo, hi);
-    run10(lo ^ t.edge_lo, hi ^ t.edge_hi, rl, rh);
+    lo ^= t.edge_lo; hi ^= t.edge_hi;
+    if (ri) { uint32_t ilo, ihi; rd_win32x<PADDED>(*ri, temp_start_j, ilo, ihi); lo |= ilo; hi |= ihi; }
+    run10(lo, hi, rl, rh);
     uint64_t r10 = ((uint64_t)rh << 32) | rl;
     r10 &= ~((1ull << (2 * pos0)) - 1);                      // pos >= pos0
     r10 &= (1ull << (2 * imax + 2)) - 1;                     // pos <= imax (<= 22)
@@ -1062,142 +1068,241 @@ DCB_HD void dcr_general_run(ReadView r, const ExcList& ex, uint32_t* rd1, uint32
 
 // ------------------------------------------------------------------------------------------------
 // Half-tag path (dcb_halftag_kernel): reads the exact-tag kernel could not finish -- almost always because a
-// substitution or an N sits in one of the two tags -- WITHOUT the general kernel's per-base candidate marks.  The
-// exact-tag kernel hands over what it found (one hit word per gene); the half keywords of the gene(s) still missing
-// are found through the sampled index (DcbHalfIndex: one direct-indexed probe at every 4th base), all occurrences
-// are listed in findall order, and the analysis (analyse_general: guards, Hamming <= 1, counters, deletion walks,
-// filters -- decombine.py:273-585) then runs on that hit list exactly as it does in the general kernel.
+// substitution or an N sits in one of the two tags.  The exact-tag kernel hands over what it found (one hit word per
+// gene); the half keywords of the gene(s) still missing are found through the sampled index (DcbHalfIndex), every
+// occurrence is expanded into its (tag, start) candidates, kept sorted in the order the reference tries them
+// (decombine.py:294-390, 422-527: half1 hits in findall order, each with its tags ascending; half2 only when half1
+// never hit), and the candidates are then tried one by one: length guard, Hamming <= 1, counter, deletion walk.
+// Only the INTERIOR case is decided here (tag windows inside the read, deletion walks that end inside one 32-base
+// window); everything else -- and nothing has been counted by then: counters are kept pending in a bit mask -- is
+// passed on to the general kernel.  Non-ACGT symbols (packed as base 0) are honoured through a second column in the
+// read's own layout (01 per invalid base) that is OR-ed into every comparison: an invalid base never matches.
 // ------------------------------------------------------------------------------------------------
-struct HalfIdxView {
+struct HalfView {
     const uint16_t* t;
     const uint32_t* h;
-    const uint8_t* list;
-    const uint8_t* fullkw;
+    const uint8_t* ids;
+    const DcbHalfKw* kw;
+    const uint8_t* tags;
     uint32_t c1, c2;
-    int hshift, n_v;
+    int hshift, v_split, j_split;
 };
-DCB_HD HalfIdxView half_idx_view(const uint32_t* hb) {
+DCB_HD HalfView half_view(const uint32_t* hb) {
     const DcbHalfIndex& hx = *reinterpret_cast<const DcbHalfIndex*>(hb);
-    HalfIdxView v;
+    HalfView v;
     v.t = reinterpret_cast<const uint16_t*>(hb + hx.t_off);
     v.h = hb + hx.h_off;
-    v.list = reinterpret_cast<const uint8_t*>(hb + hx.list_off);
-    v.fullkw = reinterpret_cast<const uint8_t*>(hb + hx.fullkw_off);
-    v.c1 = hx.c1; v.c2 = hx.c2; v.hshift = hx.hshift; v.n_v = hx.n_v;
+    v.ids = reinterpret_cast<const uint8_t*>(hb + hx.ids_off);
+    v.kw = reinterpret_cast<const DcbHalfKw*>(hb + hx.kw_off);
+    v.tags = reinterpret_cast<const uint8_t*>(hb + hx.tags_off);
+    v.c1 = hx.c1; v.c2 = hx.c2; v.hshift = hx.hshift; v.v_split = hx.v_split; v.j_split = hx.j_split;
     return v;
 }
-DCB_HD const DcbKwSet& half_kwset(const DcbGene& gv, const DcbGene& gj, int set) {   // set 0..3: V half1, V half2, J half1, J half2
-    const DcbGene& g = set < 2 ? gv : gj;
-    return (set & 1) ? g.half2 : g.half1;
+// A candidate: gene << 31 | kind << 29 (0 full tag, 1 half1, 2 half2) | end of the keyword occurrence << 19 |
+// (31 - keyword length) << 14 | tag << 6 | guard failed << 5.  Ascending integer order = V before J, full tag, then
+// half1 hits by (end, longest first) with their tags ascending, then half2 hits likewise: the reference's order.
+#define DCB_HC_GENE(e) ((e) >> 31)
+#define DCB_HC_KIND(e) (((e) >> 29) & 3u)
+#define DCB_HC_END(e) (((e) >> 19) & 1023u)
+#define DCB_HC_KWLEN(e) (31u - (((e) >> 14) & 31u))
+#define DCB_HC_TAG(e) (((e) >> 6) & 255u)
+#define DCB_HC_GUARDFAIL(e) (((e) >> 5) & 1u)
+#define DCB_HC_MAKE(gene, kind, end, kwlen, tag, gf) \
+    (((uint32_t)(gene) << 31) | ((uint32_t)(kind) << 29) | ((uint32_t)(end) << 19) | ((31u - (uint32_t)(kwlen)) << 14) | ((uint32_t)(tag) << 6) | ((uint32_t)(gf) << 5))
+#define DCB_HALF_MAX_READ 1008     // `end` has 10 bits
+DCB_HD void half_insert(uint32_t* cand, int stride, int cap, int& n, uint32_t e) {
+    if (n < cap) {
+        int k = n;
+        while (k > 0 && cand[(k - 1) * stride] > e) { cand[k * stride] = cand[(k - 1) * stride]; k--; }
+        cand[k * stride] = e;
+    }
+    n++;
 }
-// One candidate: a keyword of `set` starting at P (its kmin-prefix is looked up; every keyword with that prefix is
-// compared with the read as a whole).  Appends the occurrences to the hit list; n counts them even past `cap`.
-DCB_HD void half_confirm(const ReadView& r, const HalfIdxView& hx, const uint32_t* vblob, const uint32_t* jblob, int set, int P,
-                         uint32_t* hits_col, int cap, int& n) {
+// The view of the invalid-base column: same geometry as the read.
+DCB_HD ReadView half_inv_view(const ReadView& r, const uint32_t* inv2) {
+    ReadView ri = r;
+    ri.w = inv2;
+    return ri;
+}
+// One probe hit: a keyword of `set` may start at P.  Its kmin-prefix is looked up; every keyword with that prefix is
+// compared with the read as a whole and an occurrence expanded into one candidate per tag that has this half.
+// bail: a candidate whose tag window is not inside the read (the reference's slices then wrap or truncate).
+template <bool PADDED>
+DCB_HD void half_expand(const ReadView& r, const uint32_t* inv2, const HalfView& hx, const DcbTag* vtags, const DcbTag* jtags,
+                        int set, int P, uint32_t* cand, int cap, int& n, bool& bail) {
     if (P < 0) return;
     constexpr int KMIN = DCB_HALF_Q + DCB_HALF_STRIDE - 1;
     uint32_t lo, hi;
-    rd_win32(r, P, lo, hi);
+    rd_win32x<PADDED>(r, P, lo, hi);
     const uint32_t key = ((uint32_t)set << 28) | (lo & mask2(KMIN));
     const uint32_t s1 = (key * hx.c1) >> hx.hshift, s2 = (key * hx.c2) >> hx.hshift;
-    uint32_t meta;
-    if (hx.h[2 * s1] == key) meta = hx.h[2 * s1 + 1];
-    else if (hx.h[2 * s2] == key) meta = hx.h[2 * s2 + 1];
-    else return;
-    const uint32_t* blob = set < 2 ? vblob : jblob;
-    const DcbKwSet& ks = half_kwset(*reinterpret_cast<const DcbGene*>(vblob), *reinterpret_cast<const DcbGene*>(jblob), set);
+    const uint32_t k1 = hx.h[2 * s1], k2 = hx.h[2 * s2];
+    if (k1 != key && k2 != key) return;
+    const uint32_t meta = hx.h[2 * (k1 == key ? s1 : s2) + 1];
     const int first = (int)(meta & 255u), cnt = (int)(meta >> 8);
+    const int gene = set >> 1, half2 = set & 1;
+    const DcbTag* tags = gene ? jtags : vtags;
+    const int split = gene ? hx.j_split : hx.v_split;
     for (int i = 0; i < cnt; i++) {
-        const int c = hx.list[first + i];
-        const DcbKw& k = kwset_kw(blob, ks, c);
-        if (P + (int)k.len > r.n) continue;
-        if (((lo ^ k.bits_lo) & mask2(k.len)) | (k.len > 16 ? ((hi ^ k.bits_hi) & mask2(k.len - 16)) : 0u)) continue;
-        if (r.inv && rd_inv_any(r, P, P + (int)k.len)) continue;          // an occurrence needs valid bases
-        if (n < cap) hits_col[n * r.stride] = (uint32_t)P | ((uint32_t)c << 16) | ((uint32_t)ks.set_id << 24);
-        n++;
+        const DcbHalfKw k = hx.kw[hx.ids[first + i]];
+        const int len = k.len;
+        if (P + len > r.n) continue;
+        uint32_t xlo = lo ^ k.bits_lo, xhi = hi ^ k.bits_hi;
+        if (inv2) {
+            uint32_t ilo, ihi;
+            rd_win32x<PADDED>(half_inv_view(r, inv2), P, ilo, ihi);
+            xlo |= ilo; xhi |= ihi;                                    // an occurrence needs valid bases
+        }
+        if ((xlo & mask2(len)) | (len > 16 ? (xhi & mask2(len - 16)) : 0u)) continue;
+        const int s0 = half2 ? P - split : P;                          // where the whole tag would start (decombine.py:311, 361)
+        for (int ti = 0; ti < (int)k.n_tags; ti++) {
+            const int kk = hx.tags[k.tags_off + ti];
+            const int tlen = tags[kk].len;
+            const int span = tlen > (int)k.first_len ? tlen : (int)k.first_len;
+            if (s0 < 0 || s0 + span > r.n) bail = true;
+            half_insert(cand, r.stride, cap, n, DCB_HC_MAKE(gene, 1 + half2, P + len, len, kk, tlen != (int)k.first_len));
+        }
     }
 }
-// findall order inside every set: ascending END position, longest keyword first at equal end.  The list is short
-// (one or two entries as a rule), so an insertion sort on (end, -length) over ALL entries -- which orders every set.
-DCB_HD uint32_t half_hit_key(const uint32_t e, const uint32_t* vblob, const uint32_t* jblob) {
-    const int sid = (int)(e >> 24);
-    const uint32_t* blob = sid < 3 ? vblob : jblob;
-    const DcbGene& g = *reinterpret_cast<const DcbGene*>(blob);
-    const DcbKwSet& ks = (sid % 3) == 0 ? g.full : (sid % 3) == 1 ? g.half1 : g.half2;
-    const uint32_t len = kwset_kw(blob, ks, (int)((e >> 16) & 255u)).len;
-    return (((e & 0xFFFFu) + len) << 8) | (255u - len);
-}
-DCB_HD void half_sort_hits(uint32_t* hits_col, int stride, int n, const uint32_t* vblob, const uint32_t* jblob) {
-    for (int i = 1; i < n; i++) {
-        const uint32_t e = hits_col[i * stride], ke = half_hit_key(e, vblob, jblob);
-        int k = i;
-        while (k > 0 && half_hit_key(hits_col[(k - 1) * stride], vblob, jblob) > ke) { hits_col[k * stride] = hits_col[(k - 1) * stride]; k--; }
-        hits_col[k * stride] = e;
-    }
-}
-// Steps of the half-tag path shared by the kernel and tests/sim.  r: w/stride/n/nw set.  Returns false when the read
-// must go on to the general kernel (nothing has been counted then).
-//   half_begin   the read's view (exception range [e0, e1) of a flagged read -> invalid-base mask), the full-tag words
-//                checked against the mask (a tag over a symbol packed as base 0 is no occurrence), the half sets to find
-DCB_HD bool half_begin(ReadView& r, bool flagged, const ExcList& ex, uint32_t e0, uint32_t* inv0, const uint32_t* vblob,
-                       const uint32_t* jblob, uint32_t& hv, uint32_t& hj, uint32_t& need) {
-    const int nwi = (r.nw + 1) / 2;
+// Set up the read: the invalid-base column of a flagged read (exception entries from e0 on), the hand-over words checked
+// against it (a tag over a symbol packed as base 0 is no occurrence), which half sets have to be found.
+// false: pass the read on (several full-tag candidates that cannot be told apart here, or a read too long).
+DCB_HD bool half_begin(ReadView& r, const uint32_t*& inv2, bool flagged, const ExcList& ex, uint32_t e0, uint32_t* inv2col,
+                       const DcbTag* vtags, const DcbTag* jtags, uint32_t& hv, uint32_t& hj, uint32_t& need) {
     r.inv = nullptr; r.exc_pos = ex.pos; r.exc_kind = ex.kind; r.e0 = r.e1 = 0; r.mirror = 0;
     r.cand = nullptr; r.cand_kq = 0; r.hits = nullptr; r.n_hits = 0;
+    inv2 = nullptr;
+    need = 0;
     if (flagged) {
         uint32_t e1 = e0;
         bool any = false;
-        for (int k = 0; k < nwi; k++) inv0[k * r.stride] = 0;
+        for (int k = 0; k < r.nw; k++) inv2col[k * r.stride] = 0;
         for (; e1 < ex.n && ex.read[e1] == ex.read[e0]; e1++) {
             if (ex.kind[e1] == 3) continue;  // a real base in this frame
             const uint32_t p = ex.pos[e1];
-            inv0[(p >> 5) * r.stride] |= 1u << (p & 31);
+            inv2col[(p >> 4) * r.stride] |= 1u << (2 * (p & 15));
             any = true;
         }
         r.e0 = (int)e0; r.e1 = (int)e1;
-        if (any) r.inv = inv0;
+        if (any) inv2 = inv2col;
     }
-    if (hv == DCB_HIT_MULTI || hj == DCB_HIT_MULTI) return false;
-    if (r.inv) {
-        const DcbGene& gv = *reinterpret_cast<const DcbGene*>(vblob);
-        const DcbGene& gj = *reinterpret_cast<const DcbGene*>(jblob);
-        if (hv) { const int P = (int)(hv & 0xFFFFu), L = gene_tag(vblob, gv, (int)((hv >> 16) & 0x7FFFu)).len; if (rd_inv_any(r, P, P + L)) hv = 0u; }
-        if (hj) { const int P = (int)(hj & 0xFFFFu), L = gene_tag(jblob, gj, (int)((hj >> 16) & 0x7FFFu)).len; if (rd_inv_any(r, P, P + L)) hj = 0u; }
+    if (hv == DCB_HIT_MULTI || hj == DCB_HIT_MULTI || r.n > DCB_HALF_MAX_READ) return false;
+    if (inv2) {
+        const ReadView ri = half_inv_view(r, inv2);
+        for (int g = 0; g < 2; g++) {
+            uint32_t& h = g ? hj : hv;
+            if (!h) continue;
+            const int P = (int)(h & 0xFFFFu), L = (g ? jtags : vtags)[(h >> 16) & 0x7FFFu].len;
+            uint32_t ilo, ihi;
+            rd_win32(ri, P, ilo, ihi);
+            if ((ilo & mask2(L)) | (L > 16 ? (ihi & mask2(L - 16)) : 0u)) h = 0u;
+        }
     }
     need = (hv ? 0u : 0x00FFu) | (hj ? 0u : 0xFF00u);
     return true;
 }
-//   half_finish  full-tag occurrences + the n half occurrences collected in hits0 -> sorted hit list -> dcr()
-DCB_HD bool half_finish(ReadView& r, const HalfIdxView& hx, uint32_t hv, uint32_t hj, uint32_t* hits0, int cap, int n,
-                        const uint32_t* vblob, const uint32_t* jblob, const DcrParams& prm, dcb_result& out, dcb_cnt_t* C) {
-    if (hv) { if (n < cap) hits0[n * r.stride] = (hv & 0xFFFFu) | ((uint32_t)hx.fullkw[(hv >> 16) & 0x7FFFu] << 16); n++; }
-    if (hj) { if (n < cap) hits0[n * r.stride] = (hj & 0xFFFFu) | ((uint32_t)hx.fullkw[hx.n_v + ((hj >> 16) & 0x7FFFu)] << 16) | (3u << 24); n++; }
+// vanalysis / janalysis over the sorted candidates of one gene, from entry `i` on (decombine.py:273-394, 397-531).
+// Returns 1 assigned (out filled), 0 not assigned (the failure counter is pending), -1 pass the read on.
+template <bool IS_V, bool PADDED>
+DCB_HD int half_analyse(const ReadView& r, const uint32_t* inv2, const HalfView& hx, const DcbTag* tags, const uint32_t* cand,
+                        int n, int& i, int end_of_v, VJ& out, uint32_t& pend) {
+    const uint32_t gene = IS_V ? 0u : 1u;
+    if (i >= n || DCB_HC_GENE(cand[i * r.stride]) != gene) {
+        pend |= 1u << (IS_V ? DCB_C_no_vtags_found : DCB_C_no_j_assigned);                  // :393 / :530
+        return 0;
+    }
+    const uint32_t kind0 = DCB_HC_KIND(cand[i * r.stride]);
+    const int split = IS_V ? hx.v_split : hx.j_split;
+    const ReadView ri = half_inv_view(r, inv2);
+    int got = 0;
+    for (; i < n; i++) {
+        const uint32_t e = cand[i * r.stride];
+        if (DCB_HC_GENE(e) != gene) break;
+        if (got || DCB_HC_KIND(e) != kind0 || DCB_HC_GUARDFAIL(e)) continue;                // half2 only when half1 never hit (:339 / :473)
+        const int kk = (int)DCB_HC_TAG(e), kwlen = (int)DCB_HC_KWLEN(e);
+        const int P = (int)DCB_HC_END(e) - kwlen;                                           // start of the keyword occurrence
+        const int s0 = kind0 == 2u ? P - split : P;                                         // start of the tag
+        const DcbTag& t = tags[kk];
+        if (kind0) {
+            uint32_t lo, hi;
+            rd_win32x<PADDED>(r, s0, lo, hi);
+            uint32_t xlo = lo ^ t.bits_lo, xhi = hi ^ t.bits_hi;
+            if (inv2) {
+                uint32_t ilo, ihi;
+                rd_win32x<PADDED>(ri, s0, ilo, ihi);
+                xlo |= ilo; xhi |= ihi;
+            }
+            xlo &= t.mask_lo; xhi &= t.mask_hi;
+            if (DCB_POPC((xlo | (xlo >> 1)) & 0x55555555u) + DCB_POPC((xhi | (xhi >> 1)) & 0x55555555u) > 1) continue;   // lev.hamming <= 1
+            pend |= 1u << (IS_V ? (kind0 == 1u ? DCB_C_verr2 : DCB_C_verr1) : (kind0 == 1u ? DCB_C_jerr2 : DCB_C_jerr1));  // :318 :370 :445 :504
+        }
+        const DcbTagFin tf = tag_fin(tags, kk);
+        if (IS_V) {
+            if (!fast_v_deletions<PADDED>(r, tf, s0 + tf.jump - 1, out.pos, out.dels, inv2 ? &ri : nullptr)) return -1;
+            out.seqpos = s0;
+        } else {
+            if (!fast_j_deletions<PADDED>(r, tf, s0 - tf.jump, end_of_v, out.pos, out.dels, inv2 ? &ri : nullptr)) return -1;
+            out.seqpos = kind0 == 1u ? P + 2 * split : s0 + (int)t.len;                     // :450-454 (half1), :411 / :511
+        }
+        out.idx = kk;
+        got = 1;
+    }
+    if (!got)   // :334 / :389 / :469 / :526 -- the J half2 failure bumps foundv2notv1 in the reference; preserved
+        pend |= 1u << (IS_V ? (kind0 == 1u ? DCB_C_foundv1notv2 : DCB_C_foundv2notv1) : (kind0 == 1u ? DCB_C_foundj1notj2 : DCB_C_foundv2notv1));
+    return got;
+}
+// The candidates are complete (n of them, at most cap kept): add the full-tag occurrences, run dcr() (decombine.py:534-585).
+// false: pass the read on to the general kernel (pend is then void).
+template <bool PADDED>
+DCB_HD bool half_run(const ReadView& r, const uint32_t* inv2, const HalfView& hx, const DcbTag* vtags, const DcbTag* jtags,
+                     uint32_t hv, uint32_t hj, uint32_t* cand, int cap, int n, const DcrParams& prm, dcb_result& out, uint32_t& pend) {
+    if (hv) { const int t = (int)((hv >> 16) & 0x7FFFu), P = (int)(hv & 0xFFFFu), L = vtags[t].len; half_insert(cand, r.stride, cap, n, DCB_HC_MAKE(0, 0, P + L, L, t, 0)); }
+    if (hj) { const int t = (int)((hj >> 16) & 0x7FFFu), P = (int)(hj & 0xFFFFu), L = jtags[t].len; half_insert(cand, r.stride, cap, n, DCB_HC_MAKE(1, 0, P + L, L, t, 0)); }
     if (n > cap) return false;
-    half_sort_hits(hits0, r.stride, n, vblob, jblob);
-    r.hits = hits0; r.n_hits = n;
-    dcb_result o;
-    o.status = 0; o.frame = 0; o.v = o.j = 0; o.vdel = o.jdel = 0;
-    o.ins_start = o.ins_end = o.v_seq_start = o.j_seq_end = 0;
-    if (dcr_general(r, vblob, jblob, prm, o, C)) out = o;
+    VJ v, j;
+    int i = 0;
+    const int gv = half_analyse<true, PADDED>(r, inv2, hx, vtags, cand, n, i, 0, v, pend);
+    if (gv < 0) return false;
+    if (gv == 0) return true;                                                              // :542-545
+    const int gj = half_analyse<false, PADDED>(r, inv2, hx, jtags, cand, n, i, v.pos + 1, j, pend);
+    if (gj < 0) return false;
+    if (gj == 0) { pend |= 1u << DCB_C_VJ_assignment_failed; return true; }                // :583-585
+    const DcbTagFin vt = tag_fin(vtags, v.idx), jt = tag_fin(jtags, j.idx);
+    const int c = dcr_finish(r, vt.jump, vt.len, jt.jump, jt.len, v, j, prm, out);
+    if (c >= 0) pend |= 1u << c;
     return true;
 }
-// The whole path on one thread (tests/sim; the kernel probes from registers and confirms in one flat loop).
-DCB_HD bool dcr_half_read(ReadView r, bool flagged, const ExcList& ex, uint32_t e0, uint32_t hv, uint32_t hj, uint32_t* inv0,
-                          uint32_t* hits0, int cap, const uint32_t* vblob, const uint32_t* jblob, const uint32_t* hb,
+DCB_HD void half_commit(uint32_t pend, dcb_cnt_t* C) {
+    for (; pend; pend &= pend - 1) DCB_COUNT(C, DCB_FFS(pend) - 1);
+}
+// The whole path on one thread (tests/sim; the kernel probes from registers).  false: pass the read on, nothing counted.
+DCB_HD bool dcr_half_read(ReadView r, bool flagged, const ExcList& ex, uint32_t e0, uint32_t hv, uint32_t hj, uint32_t* inv2col,
+                          uint32_t* cand, int cap, const uint32_t* vcore, const uint32_t* jcore, const uint32_t* hb,
                           const DcrParams& prm, dcb_result& out, dcb_cnt_t* C) {
-    uint32_t need;
-    if (!half_begin(r, flagged, ex, e0, inv0, vblob, jblob, hv, hj, need)) return false;
-    const HalfIdxView hx = half_idx_view(hb);
+    const DcbTag* vtags = gene_tags(vcore);
+    const DcbTag* jtags = gene_tags(jcore);
+    const uint32_t* inv2;
+    uint32_t need, pend = 0;
+    if (!half_begin(r, inv2, flagged, ex, e0, inv2col, vtags, jtags, hv, hj, need)) return false;
+    const HalfView hx = half_view(hb);
     int n = 0;
+    bool bail = false;
     if (need)
         for (int p = 0; p + DCB_HALF_Q <= r.n; p += DCB_HALF_STRIDE) {
             uint32_t e = hx.t[rd_win16(r, p) & mask2(DCB_HALF_Q)] & need;
             for (; e; e &= e - 1) {
                 const int b = DCB_FFS(e) - 1;
-                half_confirm(r, hx, vblob, jblob, b >> 2, p - (b & 3), hits0, cap, n);
+                half_expand<false>(r, inv2, hx, vtags, jtags, b >> 2, p - (b & 3), cand, cap, n, bail);
             }
         }
-    return half_finish(r, hx, hv, hj, hits0, cap, n, vblob, jblob, prm, out, C);
+    if (bail) return false;
+    dcb_result o;
+    o.status = 0; o.frame = 0; o.v = o.j = 0; o.vdel = o.jdel = 0;
+    o.ins_start = o.ins_end = o.v_seq_start = o.j_seq_end = 0;
+    if (!half_run<false>(r, inv2, hx, vtags, jtags, hv, hj, cand, cap, n, prm, o, pend)) return false;
+    out = o;
+    half_commit(pend, C);
+    return true;
 }
 
 // Both steps on one thread (tests/sim; the kernel regroups in between).

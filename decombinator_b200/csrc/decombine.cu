@@ -624,12 +624,13 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
 // half-tag kernel: the reads the flat exact-tag kernel queued (compacted, so warps are dense), one thread per read.
 // Almost all of them lack ONE full tag because of a substitution or an N in it.  The flat kernel left what it found in
 // the read's result slot; here the half keywords of the missing gene(s) are found through the sampled half-tag index
-// (DcbHalfIndex: a direct-indexed 16-bit entry per 7-mer, probed at every 4th base from registers), every occurrence is
-// confirmed and listed in findall order, and analyse_general runs on that list -- the same analysis code as the general
-// kernel, without its per-base candidate marks, six-set hit list and block-wide regrouping.  A read it cannot take
-// (several full-tag candidates in a read with non-ACGT symbols, more than DCB_HALF_CAP occurrences) goes on to the
-// general kernel through a second queue, uncounted.
-// Tables: 0 = V general blob, 1 = J general blob, 2 = half-tag index.
+// (DcbHalfIndex: a direct-indexed 16-bit entry per 7-mer, probed at every 4th base from registers), every occurrence
+// is confirmed in one warp-voted loop and expanded into (tag, start) candidates kept in the reference's order, and the
+// candidates are tried in turn: Hamming <= 1, counter, bit-parallel deletion walk, the four filters (dcr_core.cuh,
+// "Half-tag path").  Counters stay pending in a register until the read is decided; a read outside the interior case
+// (several full-tag candidates in a read with non-ACGT symbols, a tag window or a deletion walk that leaves the read or
+// the 32-base window, more than DCB_HALF_CAP candidates) goes on to the general kernel through a second queue, uncounted.
+// Tables: 0 = V tag records, 1 = J tag records, 2 = half-tag index.
 // ------------------------------------------------------------------------------------------------
 #define DCB_HALF_CAP 8
 template <int NW, int T>
@@ -637,21 +638,27 @@ __global__ void __launch_bounds__(T, 1)
 dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict__ results,
                    unsigned long long* __restrict__ counters, const uint32_t* __restrict__ queue,
                    const uint32_t* __restrict__ queue_count, uint32_t* __restrict__ queue2, uint32_t* __restrict__ queue2_count) {
-    constexpr int NWI = (NW + 1) / 2;
+    constexpr int ROWS = NW + 3;                                    // a zero row in front of the read's words, two behind
     constexpr int NPOS = (16 * NW - DCB_HALF_Q) / DCB_HALF_STRIDE + 1;
     constexpr int NM = (NPOS + 31) / 32;                            // candidate mask words
+    static_assert(NM <= 3, "three candidate mask words");
     extern __shared__ __align__(16) uint32_t smem[];
-    SmemLayout L = carve(smem, tb, (size_t)(NW + NWI + DCB_HALF_CAP) * T);
-    uint32_t* s_rd = L.cols;                      // [NW][T]
-    uint32_t* s_inv = s_rd + (size_t)NW * T;      // [NWI][T]
-    uint32_t* s_hits = s_inv + (size_t)NWI * T;   // [DCB_HALF_CAP][T]
-    stage_tables(L, tb);
-    const uint32_t* vblob = L.t[0];
-    const uint32_t* jblob = L.t[1];
-    const HalfIdxView hx = half_idx_view(L.t[2]);
-    const uint32_t t7 = smem_u32(hx.t);
-
     const int tid = threadIdx.x;
+    SmemLayout L = carve(smem, tb, (size_t)(2 * ROWS + DCB_HALF_CAP) * T);
+    uint32_t* s_rd = L.cols;                      // [ROWS][T]
+    uint32_t* s_inv = s_rd + (size_t)ROWS * T;    // [ROWS][T] invalid-base column, 01 per non-ACGT symbol
+    uint32_t* s_cand = s_inv + (size_t)ROWS * T;  // [DCB_HALF_CAP][T]
+    s_rd[tid] = 0u; s_rd[(NW + 1) * T + tid] = 0u; s_rd[(NW + 2) * T + tid] = 0u;
+    s_inv[tid] = 0u; s_inv[(NW + 1) * T + tid] = 0u; s_inv[(NW + 2) * T + tid] = 0u;
+    stage_tables(L, tb);
+    const DcbTag* vtags = gene_tags(L.t[0]);
+    const DcbTag* jtags = gene_tags(L.t[1]);
+    const HalfView hx = half_view(L.t[2]);
+    const uint32_t t7 = smem_u32(hx.t);
+    uint32_t* col = s_rd + T + tid;               // word k of this thread's read at col[k * T]
+    uint32_t* icol = s_inv + T + tid;
+    uint32_t* cand = s_cand + tid;
+
     const uint32_t n_items = *queue_count;
     const uint32_t n_tiles = (n_items + T - 1) / T;
     ExcList ex;
@@ -660,7 +667,6 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
         const uint32_t item = tile * T + tid;
         const bool live = item < n_items;
         const uint32_t ri = live ? __ldg(queue + item) : b.first;
-        bool pass_on = false;
         uint32_t w[NW];
         {
             const uint4* src = reinterpret_cast<const uint4*>(b.words + (size_t)ri * NW);
@@ -670,64 +676,84 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
                 w[4 * k + 0] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
             }
 #pragma unroll
-            for (int k = 0; k < NW; k++) s_rd[k * T + tid] = w[k];
+            for (int k = 0; k < NW; k++) col[k * T] = w[k];
         }
+        const uint4 hand = *reinterpret_cast<const uint4*>(results + ri);
+        uint32_t hv = hand.x, hj = hand.y, need = 0;
+        ReadView r;
+        r.w = col; r.stride = T; r.nw = NW;
+        r.n = b.uniform_len ? (int)b.uniform_len : (int)__ldg(b.lens + ri);
+        const uint32_t* inv2 = nullptr;
+        bool act = live;                          // still being decided here; !act && live: passed on
         if (live) {
-            const uint4 hand = *reinterpret_cast<const uint4*>(results + ri);
-            uint32_t hv = hand.x, hj = hand.y, need = 0;
-            ReadView r;
-            r.w = s_rd + tid; r.stride = T; r.nw = NW;
-            r.n = b.uniform_len ? (int)b.uniform_len : (int)__ldg(b.lens + ri);
             const bool flagged = b.n_exc && ((__ldg(b.flags + (ri >> 5)) >> (ri & 31)) & 1u);
             uint32_t e0 = 0;
             if (flagged) {
                 e0 = __ldg(b.exc_index + (ri >> 5));
                 while (__ldg(b.exc_read + e0) < ri) e0++;
             }
-            if (!half_begin(r, flagged, ex, e0, s_inv + tid, vblob, jblob, hv, hj, need)) {
-                pass_on = true;
+            act = half_begin(r, inv2, flagged, ex, e0, icol, vtags, jtags, hv, hj, need);
+        }
+        if (!act) need = 0;
+        // probe: bit i of the candidate mask <=> the 7-mer at base 4 i occurs, at an offset < 4, in a half keyword of a
+        // gene that is still missing
+        uint32_t cm[NM];
+#pragma unroll
+        for (int m = 0; m < NM; m++) cm[m] = 0u;
+        if (__any_sync(0xFFFFFFFFu, need != 0u)) {
+#pragma unroll
+            for (int i = 0; i < NPOS; i++) {
+                const int a = i >> 2, sh = (i & 3) * 8;
+                const uint32_t win = sh <= 16 ? (w[a] >> sh) : __funnelshift_r(w[a], a + 1 < NW ? w[a + 1] : 0u, sh);
+                uint32_t e;
+                asm("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(t7 + ((win & 0x3FFFu) << 1)));
+                cm[i >> 5] |= ((e & need) ? 1u : 0u) << (i & 31);
+            }
+            const int nvalid = r.n >= DCB_HALF_Q ? (r.n - DCB_HALF_Q) / DCB_HALF_STRIDE + 1 : 0;   // probes inside the read
+#pragma unroll
+            for (int m = 0; m < NM; m++) {
+                const int keep = nvalid - 32 * m;
+                if (keep < 32) cm[m] &= keep > 0 ? ((1u << keep) - 1u) : 0u;
+            }
+        }
+        // confirm: ONE warp-voted loop over (candidate, set, offset) triples, so the lanes stay in one instruction stream
+        int n = 0;
+        bool bail = false;
+        {
+            uint32_t e = 0;
+            int p = 0;
+            for (;;) {
+                if (e == 0u) {
+                    int i = -1;
+                    if (cm[0]) { i = __ffs(cm[0]) - 1; cm[0] &= cm[0] - 1u; }
+                    else if (NM > 1 && cm[NM > 1 ? 1 : 0]) { i = 32 + __ffs(cm[NM > 1 ? 1 : 0]) - 1; cm[NM > 1 ? 1 : 0] &= cm[NM > 1 ? 1 : 0] - 1u; }
+                    else if (NM > 2 && cm[NM > 2 ? 2 : 0]) { i = 64 + __ffs(cm[NM > 2 ? 2 : 0]) - 1; cm[NM > 2 ? 2 : 0] &= cm[NM > 2 ? 2 : 0] - 1u; }
+                    if (i >= 0) {
+                        p = DCB_HALF_STRIDE * i;
+                        const uint32_t* c0 = col + (p >> 4) * T;
+                        const uint32_t win = __funnelshift_r(c0[0], c0[T], (p & 15) * 2);
+                        e = hx.t[win & 0x3FFFu] & need;
+                    }
+                }
+                if (!__any_sync(0xFFFFFFFFu, e != 0u)) break;
+                if (e) {
+                    const int bit = __ffs(e) - 1;
+                    e &= e - 1u;
+                    half_expand<true>(r, inv2, hx, vtags, jtags, bit >> 2, p - (bit & 3), cand, DCB_HALF_CAP, n, bail);
+                }
+            }
+        }
+        // decide: the candidates in the reference's order
+        bool pass_on = live && !act;
+        if (act) {
+            dcb_result out;
+            *reinterpret_cast<uint4*>(&out) = make_uint4(0, 0, 0, 0);
+            uint32_t pend = 0;
+            if (!bail && half_run<true>(r, inv2, hx, vtags, jtags, hv, hj, cand, DCB_HALF_CAP, n, prm, out, pend)) {
+                store_result(results + ri, out);
+                half_commit(pend, L.cnt);
             } else {
-                // probe: bit i of the candidate mask <=> the 7-mer at base 4 i occurs, at an offset < 4, in a half keyword
-                // of a gene that is still missing
-                uint32_t cm[NM];
-#pragma unroll
-                for (int m = 0; m < NM; m++) cm[m] = 0u;
-                if (need) {
-#pragma unroll
-                    for (int i = 0; i < NPOS; i++) {
-                        const int a = i >> 2, sh = (i & 3) * 8;
-                        const uint32_t win = sh <= 16 ? (w[a] >> sh) : __funnelshift_r(w[a], a + 1 < NW ? w[a + 1] : 0u, sh);
-                        uint32_t e;
-                        asm("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(t7 + ((win & 0x3FFFu) << 1)));
-                        cm[i >> 5] |= ((e & need) ? 1u : 0u) << (i & 31);
-                    }
-                    const int nvalid = r.n >= DCB_HALF_Q ? (r.n - DCB_HALF_Q) / DCB_HALF_STRIDE + 1 : 0;   // probes inside the read
-#pragma unroll
-                    for (int m = 0; m < NM; m++) {
-                        const int keep = nvalid - 32 * m;
-                        if (keep < 32) cm[m] &= keep > 0 ? ((1u << keep) - 1u) : 0u;
-                    }
-                }
-                // confirm: every (candidate, set, offset) -> the keywords with that prefix, compared as a whole
-                int n = 0;
-#pragma unroll
-                for (int m = 0; m < NM; m++) {
-                    uint32_t c = cm[m];
-                    while (c) {
-                        const int i = 32 * m + __ffs(c) - 1;
-                        c &= c - 1;
-                        const int p = DCB_HALF_STRIDE * i;
-                        uint32_t e = hx.t[rd_win16(r, p) & 0x3FFFu] & need;
-                        for (; e; e &= e - 1) {
-                            const int bit = __ffs(e) - 1;
-                            half_confirm(r, hx, vblob, jblob, bit >> 2, p - (bit & 3), s_hits + tid, DCB_HALF_CAP, n);
-                        }
-                    }
-                }
-                dcb_result out;
-                *reinterpret_cast<uint4*>(&out) = make_uint4(0, 0, 0, 0);
-                if (half_finish(r, hx, hv, hj, s_hits + tid, DCB_HALF_CAP, n, vblob, jblob, prm, out, L.cnt)) store_result(results + ri, out);
-                else pass_on = true;
+                pass_on = true;
             }
         }
         defer_reads(pass_on, ri, queue2, queue2_count);
@@ -1177,7 +1203,7 @@ static int prepare_batch(dcb_ctx* c, const dcb_packed* P) {
     if (qfn && c->d_half && !c->params.both_frames && c->params.force_general == 0) {
         halftag_fn hf = pick_half((int)sw);
         c->half_threads = kHalfThreads;
-        c->half_smem = ((size_t)c->vgen_words + c->jgen_words + c->half_words + (sw + nwi + DCB_HALF_CAP) * kHalfThreads) * 4 + tail;
+        c->half_smem = ((size_t)c->vcore_words + c->jcore_words + c->half_words + (2 * (sw + 3) + DCB_HALF_CAP) * kHalfThreads) * 4 + tail;
         int occ_h = 0;
         if (hf && c->half_smem <= kMaxSmem) {
             CUDA_TRY(cudaFuncSetAttribute(hf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->half_smem));
@@ -1258,12 +1284,12 @@ static int launch_range(dcb_ctx* c, cudaStream_t s, uint32_t first, uint32_t cou
         if (timed && (rc = timing_end(c))) return rc;
     }
     Tables4 tg;
-    tg.g[0] = c->d_vgen; tg.words[0] = c->vgen_words; tg.g[1] = c->d_jgen; tg.words[1] = c->jgen_words;
     tg.g[3] = nullptr; tg.words[3] = 0;
     if (c->half_fn && c->q_fn) {   // the queued reads through the half-tag kernel; what it passes on is the general kernel's queue
         if (timed && (rc = timing_begin(c, 2))) return rc;
         uint32_t* qcount2 = c->d_queue_count + kMaxChunks + slot;
         uint32_t* queue2 = (uint32_t*)c->queue2.p + first;
+        tg.g[0] = c->d_vcore; tg.words[0] = c->vcore_words; tg.g[1] = c->d_jcore; tg.words[1] = c->jcore_words;
         tg.g[2] = c->d_half; tg.words[2] = c->half_words;
         const uint32_t tiles_h = (count + c->half_threads - 1) / c->half_threads;
         const int grid_h = (int)std::max<uint32_t>(1, std::min<uint32_t>(tiles_h, (uint32_t)c->half_grid));
@@ -1274,6 +1300,7 @@ static int launch_range(dcb_ctx* c, cudaStream_t s, uint32_t first, uint32_t cou
         queue = queue2; qcount = qcount2;
     }
     if (timed && (rc = timing_begin(c, 1))) return rc;
+    tg.g[0] = c->d_vgen; tg.words[0] = c->vgen_words; tg.g[1] = c->d_jgen; tg.words[1] = c->jgen_words;
     tg.g[2] = c->d_sfilt; tg.words[2] = c->sfilt_words;
     dcb_general_kernel<<<grid_g, c->general_threads, c->general_smem, s>>>(
         b, tg, prm, c->params.both_frames, (dcb_result*)c->results.p, c->d_counters,

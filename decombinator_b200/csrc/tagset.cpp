@@ -90,7 +90,7 @@ bool build_cuckoo(Cuckoo& ck, const std::vector<std::pair<uint32_t, uint32_t>>& 
 }
 
 // One keyword set -> bitmap + hash + DcbKw array + tag list (general kernel).
-void build_kwset(Blob& b, DcbKwSet& ks, const std::vector<std::string>& list, std::map<std::string, int>* index_of = nullptr) {
+void build_kwset(Blob& b, DcbKwSet& ks, const std::vector<std::string>& list) {
     std::vector<std::string> kws;
     std::vector<std::vector<int>> members;
     std::map<std::string, int> seen;
@@ -148,7 +148,6 @@ void build_kwset(Blob& b, DcbKwSet& ks, const std::vector<std::string>& list, st
         kw.tags_off = (uint8_t)tl;
         for (int t : members[ents[i].id]) taglist[tl++] = (uint8_t)t;
         std::memcpy(&b.w[ks.kw_off + 4 * i], &kw, sizeof(kw));
-        if (index_of) (*index_of)[s] = (int)i;
         b.w[ks.bitmap_off + (ents[i].key >> 5)] |= 1u << (ents[i].key & 31);
         if (i == 0 || ents[i].key != ents[i - 1].key) {
             size_t cnt = 1;
@@ -431,39 +430,60 @@ bool dcb_build_half_index(const dcb_tagset* v, const dcb_tagset* j, std::vector<
     std::memset(&hx, 0, sizeof(hx));
     hx.q = DCB_HALF_Q; hx.stride = DCB_HALF_STRIDE; hx.kmin = hx.q + hx.stride - 1;
     hx.n_v = v->n_tags; hx.n_tags = v->n_tags + j->n_tags;
-    if (hx.n_tags > 255) return false;
-    struct Kw { std::string s; int set, idx; };
-    std::vector<Kw> kws;
+    hx.v_split = v->split; hx.j_split = j->split;
+    struct Kw { std::string s; int set; std::vector<int> tags; };
+    std::vector<Kw> kws;                                            // distinct keywords per set, in order of first use
     for (int gi = 0; gi < 2; gi++) {
         const dcb_tagset* ts = gi ? j : v;
-        for (int half = 1; half <= 2; half++)
-            for (auto& kv : ts->kw_index[half]) {
-                if ((int)kv.first.size() < hx.kmin || kv.first.size() > 32) return false;
-                kws.push_back({kv.first, 2 * gi + (half - 1), kv.second});
+        for (int half = 0; half < 2; half++) {
+            std::map<std::string, size_t> seen;
+            for (int t = 0; t < ts->n_tags; t++) {
+                const std::string h = half ? ts->tags[t].substr(ts->split) : ts->tags[t].substr(0, ts->split);
+                if ((int)h.size() < hx.kmin || h.size() > 31 || ts->tags[t].size() > 31) return false;
+                auto it = seen.find(h);
+                if (it == seen.end()) { seen[h] = kws.size(); kws.push_back({h, 2 * gi + half, {t}}); }
+                else kws[it->second].tags.push_back(t);             // ascending tag index
             }
+        }
     }
-    if (kws.empty() || kws.size() > 250) return false;
+    if (kws.empty() || kws.size() > 255) return false;
     Blob b;
     b.reserve((sizeof(DcbHalfIndex) + 3) / 4);
     b.align4();
     hx.t_off = b.reserve(((size_t)1 << (2 * hx.q)) / 2);
     uint16_t* t16 = reinterpret_cast<uint16_t*>(&b.w[hx.t_off]);
-    std::map<uint32_t, std::vector<int>> by_prefix;                 // set << 28 | kmin-prefix -> keyword indices of that set
-    for (auto& k : kws) {
+    std::map<uint32_t, std::vector<int>> by_prefix;                 // set << 28 | kmin-prefix -> keyword record numbers
+    std::vector<uint8_t> tag_ids;
+    std::vector<DcbHalfKw> recs(kws.size());
+    for (size_t i = 0; i < kws.size(); i++) {
+        const Kw& k = kws[i];
         uint32_t lo, hi;
         for (int o = 0; o < hx.stride; o++) {
             if (!pack64(k.s, o, hx.q, lo, hi)) return false;
             t16[lo] |= (uint16_t)(1u << (4 * k.set + o));
         }
         pack64(k.s, 0, hx.kmin, lo, hi);
-        by_prefix[((uint32_t)k.set << 28) | lo].push_back(k.idx);
+        by_prefix[((uint32_t)k.set << 28) | lo].push_back((int)i);
+        DcbHalfKw& r = recs[i];
+        std::memset(&r, 0, sizeof(r));
+        pack64(k.s, 0, k.s.size(), r.bits_lo, r.bits_hi);
+        const dcb_tagset* ts = k.set >= 2 ? j : v;
+        r.len = (uint8_t)k.s.size();
+        r.first_len = (uint8_t)ts->tags[k.tags[0]].size();          // len(seqs[halfN_seqs.index(keyword)])
+        r.n_tags = (uint8_t)k.tags.size();
+        r.set = (uint8_t)k.set;
+        if (tag_ids.size() + k.tags.size() > 65535) return false;
+        r.tags_off = (uint16_t)tag_ids.size();
+        for (int t : k.tags) tag_ids.push_back((uint8_t)t);
     }
-    std::vector<uint8_t> list;
+    std::vector<uint8_t> ids;
     std::vector<std::pair<uint32_t, uint32_t>> items;
     for (auto& kv : by_prefix) {
-        if (kv.second.size() > 255) return false;
-        items.emplace_back(kv.first, (uint32_t)list.size() | ((uint32_t)kv.second.size() << 8));
-        for (int i : kv.second) list.push_back((uint8_t)i);
+        if (kv.second.size() > 255 || ids.size() > 255) return false;
+        // longest keyword first: the order acora reports keywords that END together in is irrelevant here (they start
+        // together), the hit list is sorted by (end, length) afterwards
+        items.emplace_back(kv.first, (uint32_t)ids.size() | ((uint32_t)kv.second.size() << 8));
+        for (int i : kv.second) ids.push_back((uint8_t)i);
     }
     Cuckoo ck;
     if (!build_cuckoo(ck, items)) return false;
@@ -475,19 +495,14 @@ bool dcb_build_half_index(const dcb_tagset* v, const dcb_tagset* j, std::vector<
         b.w[hx.h_off + 2 * i] = ck.used[i] ? ck.key[i] : DCB_HALF_FREE;
         b.w[hx.h_off + 2 * i + 1] = ck.used[i] ? ck.val[i] : 0u;
     }
-    hx.list_off = b.reserve((list.size() + 3) / 4 + 1);
-    std::memcpy(&b.w[hx.list_off], list.data(), list.size());
-    hx.fullkw_off = b.reserve(((size_t)hx.n_tags + 3) / 4 + 1);
-    uint8_t* fk = reinterpret_cast<uint8_t*>(&b.w[hx.fullkw_off]);
-    for (int gi = 0; gi < 2; gi++) {
-        const dcb_tagset* ts = gi ? j : v;
-        for (int t = 0; t < ts->n_tags; t++) {
-            auto it = ts->kw_index[0].find(ts->tags[t]);
-            if (it == ts->kw_index[0].end()) return false;
-            // a full keyword shared by several tags resolves to the first of them (list.index), as kw.first_tag does
-            fk[(gi ? v->n_tags : 0) + t] = (uint8_t)it->second;
-        }
-    }
+    hx.ids_off = b.reserve((ids.size() + 3) / 4 + 1);
+    std::memcpy(&b.w[hx.ids_off], ids.data(), ids.size());
+    b.align4();
+    hx.n_kw = (int32_t)recs.size();
+    hx.kw_off = b.reserve(4 * recs.size());
+    std::memcpy(&b.w[hx.kw_off], recs.data(), sizeof(DcbHalfKw) * recs.size());
+    hx.tags_off = b.reserve((tag_ids.size() + 3) / 4 + 1);
+    std::memcpy(&b.w[hx.tags_off], tag_ids.data(), tag_ids.size());
     b.align4();
     hx.n_words = (int32_t)b.w.size();
     std::memcpy(&b.w[0], &hx, sizeof(hx));
@@ -551,9 +566,9 @@ dcb_tagset* dcb_tagset_build(const char* const* tags, const int32_t* jumps, cons
                 if (full[k2].compare(0, lmin, full[i], 0, lmin) == 0) { t.next_same_prefix = (uint8_t)k2; break; }
         }
         if (which == 0) {
-            build_kwset(b, g.full, full, &ts->kw_index[0]);
-            build_kwset(b, g.half1, h1, &ts->kw_index[1]);
-            build_kwset(b, g.half2, h2, &ts->kw_index[2]);
+            build_kwset(b, g.full, full);
+            build_kwset(b, g.half1, h1);
+            build_kwset(b, g.half2, h2);
             g.full.set_id = is_v ? 0 : 3; g.half1.set_id = is_v ? 1 : 4; g.half2.set_id = is_v ? 2 : 5;
             for (int i = 0; i < n; i++) {
                 size_t nw = (reg[i].size() + 15) / 16;

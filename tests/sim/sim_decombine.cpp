@@ -17,7 +17,7 @@ extern "C" int sim_decombine(const dcb_packed* P, const uint32_t* vgen, const ui
     DcrParams prm;
     prm.allow_ns = allow_ns; prm.lenthreshold = lenthreshold;
     const int nw = (int)P->slot_words, nwi = (nw + 1) / 2;
-    std::vector<uint32_t> inv0(nwi + 1), inv1(nwi + 1), rd1(nw + 1), cand(nwi + 1), hits(DCB_HITS_CAP);
+    std::vector<uint32_t> inv0(nwi + 1), inv1(nwi + 1), rd1(nw + 1), cand(nwi + 1), hits(DCB_HITS_CAP), inv2(nw + 1);
     dcb_cnt_t cnt[DCB_NCOUNTERS];
     std::memset(cnt, 0, sizeof(cnt));
     ExcList ex;
@@ -53,7 +53,7 @@ extern "C" int sim_decombine(const dcb_packed* P, const uint32_t* vgen, const ui
             deferred++;
             std::memset(&o, 0, sizeof(o));
             const uint32_t e0 = flagged ? exc_lower_bound(ex, (uint32_t)ri) : 0u;
-            if (dcr_half_read(r, flagged, ex, e0, hand[0], hand[1], inv0.data(), hits.data(), DCB_HITS_CAP, vgen, jgen, half, prm, o, cnt))
+            if (dcr_half_read(r, flagged, ex, e0, hand[0], hand[1], inv2.data(), hits.data(), 8, vcore, jcore, half, prm, o, cnt))
                 action = FAST_DONE;
             else deferred--;
         }

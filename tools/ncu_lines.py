@@ -1,6 +1,9 @@
 import re,csv,collections,subprocess,sys
+"""Per-source-line attribution of one kernel of an ncu capture:  ncu_lines.py REPORT.ncu-rep [TOP] [KERNEL-SUBSTRING] [CUBIN-BASENAME]"""
 rep=sys.argv[1]
-subprocess.run("cd /tmp/cub && rm -f *.cubin && cuobjdump -xelf all /root/repo/decombinator_b200/libdcb.so >/dev/null 2>&1 && nvdisasm --print-line-info decombine.sm_100a.cubin 2>&1 | awk '/\\.text\\._Z18dcb_general_kernel/{f=1} /\\.text\\./{ if (f && !/dcb_general_kernel/) exit } f' > gen_lines.txt",shell=True)
+kern=sys.argv[3] if len(sys.argv)>3 else "dcb_general_kernel"
+cubin=sys.argv[4] if len(sys.argv)>4 else "decombine"
+subprocess.run("mkdir -p /tmp/cub && cd /tmp/cub && rm -f *.cubin && cuobjdump -xelf all /root/repo/decombinator_b200/libdcb.so >/dev/null 2>&1 && nvdisasm --print-line-info %s.sm_100a.cubin 2>&1 | awk '/\\.text\\..*%s/{f=1} /\\.text\\./{ if (f && !/%s/) exit } f' > gen_lines.txt" % (cubin, kern, kern),shell=True)
 cur=None; byaddr={}
 for l in open('/tmp/cub/gen_lines.txt'):
     m=re.search(r'//## File "([^"]+)", line (\d+)',l)
