@@ -1099,24 +1099,37 @@ DCB_HD HalfView half_view(const uint32_t* hb) {
     return v;
 }
 // A candidate: gene << 31 | kind << 29 (0 full tag, 1 half1, 2 half2) | end of the keyword occurrence << 19 |
-// (31 - keyword length) << 14 | tag << 6 | guard failed << 5.  Ascending integer order = V before J, full tag, then
-// half1 hits by (end, longest first) with their tags ascending, then half2 hits likewise: the reference's order.
+// (31 - keyword length) << 14 | tag << 6 | dead << 5 (length guard or Hamming <= 1 failed: such a candidate still
+// says that its half keyword DID occur).  Ascending integer order = V before J, full tag, then half1 hits by
+// (end, longest first) with their tags ascending, then half2 hits likewise: the reference's order.
 #define DCB_HC_GENE(e) ((e) >> 31)
 #define DCB_HC_KIND(e) (((e) >> 29) & 3u)
 #define DCB_HC_END(e) (((e) >> 19) & 1023u)
 #define DCB_HC_KWLEN(e) (31u - (((e) >> 14) & 31u))
 #define DCB_HC_TAG(e) (((e) >> 6) & 255u)
-#define DCB_HC_GUARDFAIL(e) (((e) >> 5) & 1u)
-#define DCB_HC_MAKE(gene, kind, end, kwlen, tag, gf) \
-    (((uint32_t)(gene) << 31) | ((uint32_t)(kind) << 29) | ((uint32_t)(end) << 19) | ((31u - (uint32_t)(kwlen)) << 14) | ((uint32_t)(tag) << 6) | ((uint32_t)(gf) << 5))
+#define DCB_HC_DEAD(e) (((e) >> 5) & 1u)
+#define DCB_HC_MAKE(gene, kind, end, kwlen, tag, dead) \
+    (((uint32_t)(gene) << 31) | ((uint32_t)(kind) << 29) | ((uint32_t)(end) << 19) | ((31u - (uint32_t)(kwlen)) << 14) | ((uint32_t)(tag) << 6) | ((uint32_t)(dead) << 5))
 #define DCB_HALF_MAX_READ 1008     // `end` has 10 bits
-DCB_HD void half_insert(uint32_t* cand, int stride, int cap, int& n, uint32_t e) {
-    if (n < cap) {
-        int k = n;
+#define DCB_HALF_BAIL 0x10000u     // added to a read's candidate count: pass the read on
+// Candidates are appended in any order (in the kernel by whichever lane confirmed the occurrence: the count is bumped
+// atomically) and sorted once they are complete.
+#if defined(__CUDA_ARCH__)
+#define DCB_SLOT_TAKE(p, k) atomicAdd((p), (k))
+#else
+#define DCB_SLOT_TAKE(p, k) ((*(p) += (k)) - (k))
+#endif
+DCB_HD void half_append(uint32_t* cand, int stride, int cap, uint32_t* n, uint32_t e) {
+    const uint32_t k = DCB_SLOT_TAKE(n, 1u);
+    if (k < (uint32_t)cap) cand[k * stride] = e;
+}
+DCB_HD void half_sort(uint32_t* cand, int stride, int n) {
+    for (int i = 1; i < n; i++) {
+        const uint32_t e = cand[i * stride];
+        int k = i;
         while (k > 0 && cand[(k - 1) * stride] > e) { cand[k * stride] = cand[(k - 1) * stride]; k--; }
         cand[k * stride] = e;
     }
-    n++;
 }
 // The view of the invalid-base column: same geometry as the read.
 DCB_HD ReadView half_inv_view(const ReadView& r, const uint32_t* inv2) {
@@ -1125,11 +1138,12 @@ DCB_HD ReadView half_inv_view(const ReadView& r, const uint32_t* inv2) {
     return ri;
 }
 // One probe hit: a keyword of `set` may start at P.  Its kmin-prefix is looked up; every keyword with that prefix is
-// compared with the read as a whole and an occurrence expanded into one candidate per tag that has this half.
-// bail: a candidate whose tag window is not inside the read (the reference's slices then wrap or truncate).
+// compared with the read as a whole and an occurrence expanded into one candidate per tag that has this half, with
+// the reference's length guard (decombine.py:302-307) and lev.hamming(tag, window) <= 1 (:309) already evaluated.
+// A candidate whose tag window is not inside the read (the reference's slices then wrap or truncate) passes the read on.
 template <bool PADDED>
 DCB_HD void half_expand(const ReadView& r, const uint32_t* inv2, const HalfView& hx, const DcbTag* vtags, const DcbTag* jtags,
-                        int set, int P, uint32_t* cand, int cap, int& n, bool& bail) {
+                        int set, int P, uint32_t* cand, int cap, uint32_t* n) {
     if (P < 0) return;
     constexpr int KMIN = DCB_HALF_Q + DCB_HALF_STRIDE - 1;
     uint32_t lo, hi;
@@ -1143,24 +1157,31 @@ DCB_HD void half_expand(const ReadView& r, const uint32_t* inv2, const HalfView&
     const int gene = set >> 1, half2 = set & 1;
     const DcbTag* tags = gene ? jtags : vtags;
     const int split = gene ? hx.j_split : hx.v_split;
+    const ReadView ri = half_inv_view(r, inv2);
+    uint32_t ilo = 0, ihi = 0;
+    if (inv2) rd_win32x<PADDED>(ri, P, ilo, ihi);
     for (int i = 0; i < cnt; i++) {
         const DcbHalfKw k = hx.kw[hx.ids[first + i]];
         const int len = k.len;
         if (P + len > r.n) continue;
-        uint32_t xlo = lo ^ k.bits_lo, xhi = hi ^ k.bits_hi;
-        if (inv2) {
-            uint32_t ilo, ihi;
-            rd_win32x<PADDED>(half_inv_view(r, inv2), P, ilo, ihi);
-            xlo |= ilo; xhi |= ihi;                                    // an occurrence needs valid bases
-        }
+        const uint32_t xlo = (lo ^ k.bits_lo) | ilo, xhi = (hi ^ k.bits_hi) | ihi;      // an occurrence needs valid bases
         if ((xlo & mask2(len)) | (len > 16 ? (xhi & mask2(len - 16)) : 0u)) continue;
         const int s0 = half2 ? P - split : P;                          // where the whole tag would start (decombine.py:311, 361)
+        uint32_t tlo = lo, thi = hi, tilo = ilo, tihi = ihi;           // the 32 bases from s0 on
+        if (half2 && s0 >= 0) {
+            rd_win32x<PADDED>(r, s0, tlo, thi);
+            if (inv2) rd_win32x<PADDED>(ri, s0, tilo, tihi);
+        }
         for (int ti = 0; ti < (int)k.n_tags; ti++) {
             const int kk = hx.tags[k.tags_off + ti];
-            const int tlen = tags[kk].len;
+            const DcbTag& t = tags[kk];
+            const int tlen = t.len;
             const int span = tlen > (int)k.first_len ? tlen : (int)k.first_len;
-            if (s0 < 0 || s0 + span > r.n) bail = true;
-            half_insert(cand, r.stride, cap, n, DCB_HC_MAKE(gene, 1 + half2, P + len, len, kk, tlen != (int)k.first_len));
+            if (s0 < 0 || s0 + span > r.n) { (void)DCB_SLOT_TAKE(n, DCB_HALF_BAIL); continue; }
+            const uint32_t dlo = ((tlo ^ t.bits_lo) | tilo) & t.mask_lo, dhi = ((thi ^ t.bits_hi) | tihi) & t.mask_hi;
+            const bool dead = tlen != (int)k.first_len ||
+                              DCB_POPC((dlo | (dlo >> 1)) & 0x55555555u) + DCB_POPC((dhi | (dhi >> 1)) & 0x55555555u) > 1;
+            half_append(cand, r.stride, cap, n, DCB_HC_MAKE(gene, 1 + half2, P + len, len, kk, dead));
         }
     }
 }
@@ -1201,81 +1222,89 @@ DCB_HD bool half_begin(ReadView& r, const uint32_t*& inv2, bool flagged, const E
     need = (hv ? 0u : 0x00FFu) | (hj ? 0u : 0xFF00u);
     return true;
 }
-// vanalysis / janalysis over the sorted candidates of one gene, from entry `i` on (decombine.py:273-394, 397-531).
-// Returns 1 assigned (out filled), 0 not assigned (the failure counter is pending), -1 pass the read on.
-template <bool IS_V, bool PADDED>
-DCB_HD int half_analyse(const ReadView& r, const uint32_t* inv2, const HalfView& hx, const DcbTag* tags, const uint32_t* cand,
-                        int n, int& i, int end_of_v, VJ& out, uint32_t& pend) {
+// vanalysis / janalysis over the sorted candidates of one gene, from entry `i` on (decombine.py:273-394, 397-531): the
+// candidate the reference would accept -- the full tag, else the first half1 candidate that passed the guard and
+// Hamming <= 1, half2 candidates only when half1 never hit.  Returns its entry, or 0 with the failure counter pending.
+// i is left at the first entry of the next gene.
+template <bool IS_V>
+DCB_HD uint32_t half_select(const uint32_t* cand, int stride, int n, int& i, uint32_t& pend) {
     const uint32_t gene = IS_V ? 0u : 1u;
-    if (i >= n || DCB_HC_GENE(cand[i * r.stride]) != gene) {
+    if (i >= n || DCB_HC_GENE(cand[i * stride]) != gene) {
         pend |= 1u << (IS_V ? DCB_C_no_vtags_found : DCB_C_no_j_assigned);                  // :393 / :530
-        return 0;
+        return 0u;
     }
-    const uint32_t kind0 = DCB_HC_KIND(cand[i * r.stride]);
-    const int split = IS_V ? hx.v_split : hx.j_split;
-    const ReadView ri = half_inv_view(r, inv2);
-    int got = 0;
+    const uint32_t kind0 = DCB_HC_KIND(cand[i * stride]);
+    uint32_t pick = 0u;
     for (; i < n; i++) {
-        const uint32_t e = cand[i * r.stride];
+        const uint32_t e = cand[i * stride];
         if (DCB_HC_GENE(e) != gene) break;
-        if (got || DCB_HC_KIND(e) != kind0 || DCB_HC_GUARDFAIL(e)) continue;                // half2 only when half1 never hit (:339 / :473)
-        const int kk = (int)DCB_HC_TAG(e), kwlen = (int)DCB_HC_KWLEN(e);
-        const int P = (int)DCB_HC_END(e) - kwlen;                                           // start of the keyword occurrence
-        const int s0 = kind0 == 2u ? P - split : P;                                         // start of the tag
-        const DcbTag& t = tags[kk];
-        if (kind0) {
-            uint32_t lo, hi;
-            rd_win32x<PADDED>(r, s0, lo, hi);
-            uint32_t xlo = lo ^ t.bits_lo, xhi = hi ^ t.bits_hi;
-            if (inv2) {
-                uint32_t ilo, ihi;
-                rd_win32x<PADDED>(ri, s0, ilo, ihi);
-                xlo |= ilo; xhi |= ihi;
-            }
-            xlo &= t.mask_lo; xhi &= t.mask_hi;
-            if (DCB_POPC((xlo | (xlo >> 1)) & 0x55555555u) + DCB_POPC((xhi | (xhi >> 1)) & 0x55555555u) > 1) continue;   // lev.hamming <= 1
-            pend |= 1u << (IS_V ? (kind0 == 1u ? DCB_C_verr2 : DCB_C_verr1) : (kind0 == 1u ? DCB_C_jerr2 : DCB_C_jerr1));  // :318 :370 :445 :504
-        }
-        const DcbTagFin tf = tag_fin(tags, kk);
-        if (IS_V) {
-            if (!fast_v_deletions<PADDED>(r, tf, s0 + tf.jump - 1, out.pos, out.dels, inv2 ? &ri : nullptr)) return -1;
-            out.seqpos = s0;
-        } else {
-            if (!fast_j_deletions<PADDED>(r, tf, s0 - tf.jump, end_of_v, out.pos, out.dels, inv2 ? &ri : nullptr)) return -1;
-            out.seqpos = kind0 == 1u ? P + 2 * split : s0 + (int)t.len;                     // :450-454 (half1), :411 / :511
-        }
-        out.idx = kk;
-        got = 1;
+        if (!pick && DCB_HC_KIND(e) == kind0 && !DCB_HC_DEAD(e)) pick = e;                  // half2 only when half1 never hit (:339 / :473)
     }
-    if (!got)   // :334 / :389 / :469 / :526 -- the J half2 failure bumps foundv2notv1 in the reference; preserved
+    if (!pick)  // :334 / :389 / :469 / :526 -- the J half2 failure bumps foundv2notv1 in the reference; preserved
         pend |= 1u << (IS_V ? (kind0 == 1u ? DCB_C_foundv1notv2 : DCB_C_foundv2notv1) : (kind0 == 1u ? DCB_C_foundj1notj2 : DCB_C_foundv2notv1));
-    return got;
+    else if (kind0)
+        pend |= 1u << (IS_V ? (kind0 == 1u ? DCB_C_verr2 : DCB_C_verr1) : (kind0 == 1u ? DCB_C_jerr2 : DCB_C_jerr1));  // :318 :370 :445 :504
+    return pick;
 }
-// The candidates are complete (n of them, at most cap kept): add the full-tag occurrences, run dcr() (decombine.py:534-585).
-// false: pass the read on to the general kernel (pend is then void).
+// The deletion walk of the picked candidate (interior case).  false: pass the read on.
+template <bool IS_V, bool PADDED>
+DCB_HD bool half_walk(const ReadView& r, const uint32_t* inv2, const HalfView& hx, const DcbTag* tags, uint32_t e, int end_of_v, VJ& out) {
+    const uint32_t kind = DCB_HC_KIND(e);
+    const int split = IS_V ? hx.v_split : hx.j_split;
+    const int kk = (int)DCB_HC_TAG(e), kwlen = (int)DCB_HC_KWLEN(e);
+    const int P = (int)DCB_HC_END(e) - kwlen;                                               // start of the keyword occurrence
+    const int s0 = kind == 2u ? P - split : P;                                              // start of the tag
+    const DcbTagFin tf = tag_fin(tags, kk);
+    const ReadView ri = half_inv_view(r, inv2);
+    out.idx = kk;
+    if (IS_V) {
+        out.seqpos = s0;
+        return fast_v_deletions<PADDED>(r, tf, s0 + tf.jump - 1, out.pos, out.dels, inv2 ? &ri : nullptr) != 0;
+    }
+    out.seqpos = kind == 1u ? P + 2 * split : s0 + (int)tf.len;                             // :450-454 (half1), :411 / :511
+    return fast_j_deletions<PADDED>(r, tf, s0 - tf.jump, end_of_v, out.pos, out.dels, inv2 ? &ri : nullptr) != 0;
+}
+// The candidates are complete (n of them appended; more than cap, or DCB_HALF_BAIL added: pass the read on): add the
+// full-tag occurrences, sort, run dcr() (decombine.py:534-585).  false: pass the read on to the general kernel (pend is
+// then void).  Written as a sequence of short predicated steps so that the lanes of a warp walk it together.
 template <bool PADDED>
 DCB_HD bool half_run(const ReadView& r, const uint32_t* inv2, const HalfView& hx, const DcbTag* vtags, const DcbTag* jtags,
-                     uint32_t hv, uint32_t hj, uint32_t* cand, int cap, int n, const DcrParams& prm, dcb_result& out, uint32_t& pend) {
-    if (hv) { const int t = (int)((hv >> 16) & 0x7FFFu), P = (int)(hv & 0xFFFFu), L = vtags[t].len; half_insert(cand, r.stride, cap, n, DCB_HC_MAKE(0, 0, P + L, L, t, 0)); }
-    if (hj) { const int t = (int)((hj >> 16) & 0x7FFFu), P = (int)(hj & 0xFFFFu), L = jtags[t].len; half_insert(cand, r.stride, cap, n, DCB_HC_MAKE(1, 0, P + L, L, t, 0)); }
-    if (n > cap) return false;
+                     uint32_t hv, uint32_t hj, uint32_t* cand, int cap, uint32_t n, const DcrParams& prm, dcb_result& out, uint32_t& pend) {
+    if (n > (uint32_t)cap) return false;
+    for (int g = 0; g < 2; g++) {                                                           // the full-tag occurrences handed over
+        const uint32_t h = g ? hj : hv;
+        if (!h) continue;
+        const int t = (int)((h >> 16) & 0x7FFFu), P = (int)(h & 0xFFFFu), L = (g ? jtags : vtags)[t].len;
+        if (n < (uint32_t)cap) cand[n * r.stride] = DCB_HC_MAKE(g, 0, P + L, L, t, 0);
+        n++;
+    }
+    if (n > (uint32_t)cap) return false;
+    half_sort(cand, r.stride, (int)n);
     VJ v, j;
+    v.idx = v.pos = v.dels = v.seqpos = 0;
+    j = v;
     int i = 0;
-    const int gv = half_analyse<true, PADDED>(r, inv2, hx, vtags, cand, n, i, 0, v, pend);
-    if (gv < 0) return false;
-    if (gv == 0) return true;                                                              // :542-545
-    const int gj = half_analyse<false, PADDED>(r, inv2, hx, jtags, cand, n, i, v.pos + 1, j, pend);
-    if (gj < 0) return false;
-    if (gj == 0) { pend |= 1u << DCB_C_VJ_assignment_failed; return true; }                // :583-585
-    const DcbTagFin vt = tag_fin(vtags, v.idx), jt = tag_fin(jtags, j.idx);
-    const int c = dcr_finish(r, vt.jump, vt.len, jt.jump, jt.len, v, j, prm, out);
-    if (c >= 0) pend |= 1u << c;
-    return true;
+    bool ok = true;
+    const uint32_t ev = half_select<true>(cand, r.stride, (int)n, i, pend);
+    if (ev) ok = half_walk<true, PADDED>(r, inv2, hx, vtags, ev, 0, v);
+    uint32_t ej = 0u;
+    if (ev && ok) {                                                                         // :542-548
+        ej = half_select<false>(cand, r.stride, (int)n, i, pend);
+        if (!ej) pend |= 1u << DCB_C_VJ_assignment_failed;                                  // :583-585
+    }
+    if (ej) ok = half_walk<false, PADDED>(r, inv2, hx, jtags, ej, v.pos + 1, j);
+    if (ej && ok) {
+        const DcbTagFin vt = tag_fin(vtags, v.idx), jt = tag_fin(jtags, j.idx);
+        const int c = dcr_finish(r, vt.jump, vt.len, jt.jump, jt.len, v, j, prm, out);
+        if (c >= 0) pend |= 1u << c;
+    }
+    return ok;
 }
 DCB_HD void half_commit(uint32_t pend, dcb_cnt_t* C) {
     for (; pend; pend &= pend - 1) DCB_COUNT(C, DCB_FFS(pend) - 1);
 }
-// The whole path on one thread (tests/sim; the kernel probes from registers).  false: pass the read on, nothing counted.
+// The whole path on one thread (tests/sim; the kernel probes from registers and pools the confirmations of a warp).
+// false: pass the read on, nothing counted.
 DCB_HD bool dcr_half_read(ReadView r, bool flagged, const ExcList& ex, uint32_t e0, uint32_t hv, uint32_t hj, uint32_t* inv2col,
                           uint32_t* cand, int cap, const uint32_t* vcore, const uint32_t* jcore, const uint32_t* hb,
                           const DcrParams& prm, dcb_result& out, dcb_cnt_t* C) {
@@ -1285,17 +1314,15 @@ DCB_HD bool dcr_half_read(ReadView r, bool flagged, const ExcList& ex, uint32_t 
     uint32_t need, pend = 0;
     if (!half_begin(r, inv2, flagged, ex, e0, inv2col, vtags, jtags, hv, hj, need)) return false;
     const HalfView hx = half_view(hb);
-    int n = 0;
-    bool bail = false;
+    uint32_t n = 0;
     if (need)
         for (int p = 0; p + DCB_HALF_Q <= r.n; p += DCB_HALF_STRIDE) {
             uint32_t e = hx.t[rd_win16(r, p) & mask2(DCB_HALF_Q)] & need;
             for (; e; e &= e - 1) {
                 const int b = DCB_FFS(e) - 1;
-                half_expand<false>(r, inv2, hx, vtags, jtags, b >> 2, p - (b & 3), cand, cap, n, bail);
+                half_expand<false>(r, inv2, hx, vtags, jtags, b >> 2, p - (b & 3), cand, cap, &n);
             }
         }
-    if (bail) return false;
     dcb_result o;
     o.status = 0; o.frame = 0; o.v = o.j = 0; o.vdel = o.jdel = 0;
     o.ins_start = o.ins_end = o.v_seq_start = o.j_seq_end = 0;

@@ -633,6 +633,7 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
 // Tables: 0 = V tag records, 1 = J tag records, 2 = half-tag index.
 // ------------------------------------------------------------------------------------------------
 #define DCB_HALF_CAP 8
+#define DCB_HALF_WCAP 192       // probe hits of one warp's 32 reads that are confirmed here; reads beyond pass on
 template <int NW, int T>
 __global__ void __launch_bounds__(T, 1)
 dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict__ results,
@@ -640,14 +641,19 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
                    const uint32_t* __restrict__ queue_count, uint32_t* __restrict__ queue2, uint32_t* __restrict__ queue2_count) {
     constexpr int ROWS = NW + 3;                                    // a zero row in front of the read's words, two behind
     constexpr int NPOS = (16 * NW - DCB_HALF_Q) / DCB_HALF_STRIDE + 1;
-    constexpr int NM = (NPOS + 31) / 32;                            // candidate mask words
-    static_assert(NM <= 3, "three candidate mask words");
+    constexpr int NM = (NPOS + 31) / 32;                            // probe-hit mask words
+    static_assert(NM <= 3 && NPOS <= 255, "three mask words, probe index in 8 bits");
+    const uint32_t n_items = *queue_count;
+    const uint32_t n_tiles = (n_items + T - 1) / T;
+    if (blockIdx.x >= n_tiles) return;                              // nothing queued for this block: do not even stage the tables
     extern __shared__ __align__(16) uint32_t smem[];
-    const int tid = threadIdx.x;
-    SmemLayout L = carve(smem, tb, (size_t)(2 * ROWS + DCB_HALF_CAP) * T);
+    const int tid = threadIdx.x, lane = tid & 31, wbase = tid - lane;
+    SmemLayout L = carve(smem, tb, (size_t)(2 * ROWS + DCB_HALF_CAP + 1) * T + (size_t)(T / 32) * (DCB_HALF_WCAP / 2));
     uint32_t* s_rd = L.cols;                      // [ROWS][T]
     uint32_t* s_inv = s_rd + (size_t)ROWS * T;    // [ROWS][T] invalid-base column, 01 per non-ACGT symbol
     uint32_t* s_cand = s_inv + (size_t)ROWS * T;  // [DCB_HALF_CAP][T]
+    uint32_t* s_n = s_cand + (size_t)DCB_HALF_CAP * T;   // [T] candidates appended per read
+    uint16_t* s_work = reinterpret_cast<uint16_t*>(s_n + T) + (size_t)(tid >> 5) * DCB_HALF_WCAP;   // this warp's probe hits: lane << 8 | probe
     s_rd[tid] = 0u; s_rd[(NW + 1) * T + tid] = 0u; s_rd[(NW + 2) * T + tid] = 0u;
     s_inv[tid] = 0u; s_inv[(NW + 1) * T + tid] = 0u; s_inv[(NW + 2) * T + tid] = 0u;
     stage_tables(L, tb);
@@ -657,10 +663,7 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
     const uint32_t t7 = smem_u32(hx.t);
     uint32_t* col = s_rd + T + tid;               // word k of this thread's read at col[k * T]
     uint32_t* icol = s_inv + T + tid;
-    uint32_t* cand = s_cand + tid;
 
-    const uint32_t n_items = *queue_count;
-    const uint32_t n_tiles = (n_items + T - 1) / T;
     ExcList ex;
     ex.read = b.exc_read; ex.pos = b.exc_pos; ex.kind = b.exc_kind; ex.n = b.n_exc;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -684,7 +687,7 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
         r.w = col; r.stride = T; r.nw = NW;
         r.n = b.uniform_len ? (int)b.uniform_len : (int)__ldg(b.lens + ri);
         const uint32_t* inv2 = nullptr;
-        bool act = live;                          // still being decided here; !act && live: passed on
+        bool act = live;                          // still being decided here; live && !act: passed on
         if (live) {
             const bool flagged = b.n_exc && ((__ldg(b.flags + (ri >> 5)) >> (ri & 31)) & 1u);
             uint32_t e0 = 0;
@@ -695,8 +698,9 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
             act = half_begin(r, inv2, flagged, ex, e0, icol, vtags, jtags, hv, hj, need);
         }
         if (!act) need = 0;
-        // probe: bit i of the candidate mask <=> the 7-mer at base 4 i occurs, at an offset < 4, in a half keyword of a
-        // gene that is still missing
+        s_n[tid] = 0u;
+        // 1. probe: bit i of the mask <=> the 7-mer at base 4 i occurs, at an offset < 4, in a half keyword of a gene that
+        //    is still missing
         uint32_t cm[NM];
 #pragma unroll
         for (int m = 0; m < NM; m++) cm[m] = 0u;
@@ -716,40 +720,56 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
                 if (keep < 32) cm[m] &= keep > 0 ? ((1u << keep) - 1u) : 0u;
             }
         }
-        // confirm: ONE warp-voted loop over (candidate, set, offset) triples, so the lanes stay in one instruction stream
-        int n = 0;
-        bool bail = false;
-        {
-            uint32_t e = 0;
-            int p = 0;
-            for (;;) {
-                if (e == 0u) {
-                    int i = -1;
-                    if (cm[0]) { i = __ffs(cm[0]) - 1; cm[0] &= cm[0] - 1u; }
-                    else if (NM > 1 && cm[NM > 1 ? 1 : 0]) { i = 32 + __ffs(cm[NM > 1 ? 1 : 0]) - 1; cm[NM > 1 ? 1 : 0] &= cm[NM > 1 ? 1 : 0] - 1u; }
-                    else if (NM > 2 && cm[NM > 2 ? 2 : 0]) { i = 64 + __ffs(cm[NM > 2 ? 2 : 0]) - 1; cm[NM > 2 ? 2 : 0] &= cm[NM > 2 ? 2 : 0] - 1u; }
-                    if (i >= 0) {
-                        p = DCB_HALF_STRIDE * i;
-                        const uint32_t* c0 = col + (p >> 4) * T;
-                        const uint32_t win = __funnelshift_r(c0[0], c0[T], (p & 15) * 2);
-                        e = hx.t[win & 0x3FFFu] & need;
-                    }
-                }
-                if (!__any_sync(0xFFFFFFFFu, e != 0u)) break;
-                if (e) {
+        // 2. pool the probe hits of the warp's 32 reads in one list, so that confirming them keeps all lanes busy whatever
+        //    their distribution over the reads (measured before: 6 of 32 lanes active when every lane confirmed its own)
+        int mine = 0;
+#pragma unroll
+        for (int m = 0; m < NM; m++) mine += __popc(cm[m]);
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        int at = incl - mine;
+        const bool fits = incl <= DCB_HALF_WCAP;
+        const int n_work = __reduce_max_sync(0xFFFFFFFFu, fits ? incl : 0);
+        if (mine && !fits) act = false;
+        if (fits) {
+#pragma unroll
+            for (int m = 0; m < NM; m++)
+                for (uint32_t c = cm[m]; c; c &= c - 1u) s_work[at++] = (uint16_t)((lane << 8) | (32 * m + __ffs(c) - 1));
+        }
+        __syncwarp();
+        // 3. confirm: lane k takes hit k of the list -- another lane's read as a rule -- and appends the candidates it
+        //    expands to that read's list
+        for (int k0 = 0; k0 < n_work; k0 += 32) {
+            const bool has = k0 + lane < n_work;
+            const uint32_t it = has ? s_work[k0 + lane] : (uint32_t)(lane << 8);
+            const int src = (int)(it >> 8), p = DCB_HALF_STRIDE * (int)(it & 255u);
+            const uint32_t need_s = __shfl_sync(0xFFFFFFFFu, need, src);
+            const int n_s = __shfl_sync(0xFFFFFFFFu, r.n, src);
+            const int flg_s = __shfl_sync(0xFFFFFFFFu, inv2 != nullptr ? 1 : 0, src);
+            if (has) {
+                ReadView rs;
+                rs.w = s_rd + T + wbase + src; rs.stride = T; rs.nw = NW; rs.n = n_s;
+                const uint32_t* c0 = rs.w + (p >> 4) * T;
+                const uint32_t win = __funnelshift_r(c0[0], c0[T], (p & 15) * 2);
+                for (uint32_t e = hx.t[win & 0x3FFFu] & need_s; e; e &= e - 1u) {
                     const int bit = __ffs(e) - 1;
-                    e &= e - 1u;
-                    half_expand<true>(r, inv2, hx, vtags, jtags, bit >> 2, p - (bit & 3), cand, DCB_HALF_CAP, n, bail);
+                    half_expand<true>(rs, flg_s ? s_inv + T + wbase + src : nullptr, hx, vtags, jtags, bit >> 2, p - (bit & 3),
+                                      s_cand + wbase + src, DCB_HALF_CAP, s_n + wbase + src);
                 }
             }
         }
-        // decide: the candidates in the reference's order
+        __syncwarp();
+        // 4. decide: the candidates in the reference's order
         bool pass_on = live && !act;
         if (act) {
             dcb_result out;
             *reinterpret_cast<uint4*>(&out) = make_uint4(0, 0, 0, 0);
             uint32_t pend = 0;
-            if (!bail && half_run<true>(r, inv2, hx, vtags, jtags, hv, hj, cand, DCB_HALF_CAP, n, prm, out, pend)) {
+            if (half_run<true>(r, inv2, hx, vtags, jtags, hv, hj, s_cand + tid, DCB_HALF_CAP, s_n[tid], prm, out, pend)) {
                 store_result(results + ri, out);
                 half_commit(pend, L.cnt);
             } else {
@@ -757,6 +777,7 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
             }
         }
         defer_reads(pass_on, ri, queue2, queue2_count);
+        __syncwarp();
     }
     flush_counters(L.cnt, counters);
 }
@@ -770,6 +791,7 @@ dcb_general_kernel(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_r
                    const uint32_t* __restrict__ queue_count) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int T = blockDim.x;
+    if (blockIdx.x >= ((queue ? *queue_count : b.n_reads) + T - 1) / T) return;   // nothing for this block: do not even stage the tables
     const int nw = (int)b.slot_words, nwi = (nw + 1) / 2;
     SmemLayout L = carve(smem, tb, (size_t)(nw + nwi) * T * (both_frames ? 2 : 1) + (size_t)(nwi + DCB_HITS_CAP + 6) * T + 20);
     uint32_t* s_rd = L.cols;                      // [nw][T]
@@ -1203,7 +1225,8 @@ static int prepare_batch(dcb_ctx* c, const dcb_packed* P) {
     if (qfn && c->d_half && !c->params.both_frames && c->params.force_general == 0) {
         halftag_fn hf = pick_half((int)sw);
         c->half_threads = kHalfThreads;
-        c->half_smem = ((size_t)c->vcore_words + c->jcore_words + c->half_words + (2 * (sw + 3) + DCB_HALF_CAP) * kHalfThreads) * 4 + tail;
+        c->half_smem = ((size_t)c->vcore_words + c->jcore_words + c->half_words + (2 * (sw + 3) + DCB_HALF_CAP + 1) * kHalfThreads +
+                        (kHalfThreads / 32) * (DCB_HALF_WCAP / 2)) * 4 + tail;
         int occ_h = 0;
         if (hf && c->half_smem <= kMaxSmem) {
             CUDA_TRY(cudaFuncSetAttribute(hf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->half_smem));
