@@ -1138,12 +1138,9 @@ DCB_HD ReadView half_inv_view(const ReadView& r, const uint32_t* inv2) {
     return ri;
 }
 // One probe hit: a keyword of `set` may start at P.  Its kmin-prefix is looked up; every keyword with that prefix is
-// compared with the read as a whole and an occurrence expanded into one candidate per tag that has this half, with
-// the reference's length guard (decombine.py:302-307) and lev.hamming(tag, window) <= 1 (:309) already evaluated.
-// A candidate whose tag window is not inside the read (the reference's slices then wrap or truncate) passes the read on.
-template <bool PADDED>
-DCB_HD void half_expand(const ReadView& r, const uint32_t* inv2, const HalfView& hx, const DcbTag* vtags, const DcbTag* jtags,
-                        int set, int P, uint32_t* cand, int cap, uint32_t* n) {
+// compared with the read as a whole.  sink(keyword record number, number of tags that have this half) per occurrence.
+template <bool PADDED, class Sink>
+DCB_HD void half_lookup(const ReadView& r, const uint32_t* inv2, const HalfView& hx, int set, int P, Sink& sink) {
     if (P < 0) return;
     constexpr int KMIN = DCB_HALF_Q + DCB_HALF_STRIDE - 1;
     uint32_t lo, hi;
@@ -1154,36 +1151,43 @@ DCB_HD void half_expand(const ReadView& r, const uint32_t* inv2, const HalfView&
     if (k1 != key && k2 != key) return;
     const uint32_t meta = hx.h[2 * (k1 == key ? s1 : s2) + 1];
     const int first = (int)(meta & 255u), cnt = (int)(meta >> 8);
-    const int gene = set >> 1, half2 = set & 1;
-    const DcbTag* tags = gene ? jtags : vtags;
-    const int split = gene ? hx.j_split : hx.v_split;
-    const ReadView ri = half_inv_view(r, inv2);
     uint32_t ilo = 0, ihi = 0;
-    if (inv2) rd_win32x<PADDED>(ri, P, ilo, ihi);
+    if (inv2) rd_win32x<PADDED>(half_inv_view(r, inv2), P, ilo, ihi);
     for (int i = 0; i < cnt; i++) {
-        const DcbHalfKw k = hx.kw[hx.ids[first + i]];
+        const int id = hx.ids[first + i];
+        const DcbHalfKw k = hx.kw[id];
         const int len = k.len;
         if (P + len > r.n) continue;
         const uint32_t xlo = (lo ^ k.bits_lo) | ilo, xhi = (hi ^ k.bits_hi) | ihi;      // an occurrence needs valid bases
         if ((xlo & mask2(len)) | (len > 16 ? (xhi & mask2(len - 16)) : 0u)) continue;
-        const int s0 = half2 ? P - split : P;                          // where the whole tag would start (decombine.py:311, 361)
-        uint32_t tlo = lo, thi = hi, tilo = ilo, tihi = ihi;           // the 32 bases from s0 on
-        if (half2 && s0 >= 0) {
-            rd_win32x<PADDED>(r, s0, tlo, thi);
-            if (inv2) rd_win32x<PADDED>(ri, s0, tilo, tihi);
-        }
-        for (int ti = 0; ti < (int)k.n_tags; ti++) {
-            const int kk = hx.tags[k.tags_off + ti];
-            const DcbTag& t = tags[kk];
-            const int tlen = t.len;
-            const int span = tlen > (int)k.first_len ? tlen : (int)k.first_len;
-            if (s0 < 0 || s0 + span > r.n) { (void)DCB_SLOT_TAKE(n, DCB_HALF_BAIL); continue; }
-            const uint32_t dlo = ((tlo ^ t.bits_lo) | tilo) & t.mask_lo, dhi = ((thi ^ t.bits_hi) | tihi) & t.mask_hi;
-            const bool dead = tlen != (int)k.first_len ||
-                              DCB_POPC((dlo | (dlo >> 1)) & 0x55555555u) + DCB_POPC((dhi | (dhi >> 1)) & 0x55555555u) > 1;
-            half_append(cand, r.stride, cap, n, DCB_HC_MAKE(gene, 1 + half2, P + len, len, kk, dead));
-        }
+        sink(id, (int)k.n_tags);
     }
+}
+// One (occurrence, tag) pair: keyword record `id` occurs at P, `ti` counts the tags that have this half.  Appends the
+// candidate with the reference's length guard (decombine.py:302-307) and lev.hamming(tag, window) <= 1 (:309) already
+// evaluated.  A tag window that is not inside the read (the reference's slices then wrap or truncate) passes the read on.
+template <bool PADDED>
+DCB_HD void half_candidate(const ReadView& r, const uint32_t* inv2, const HalfView& hx, const DcbTag* vtags, const DcbTag* jtags,
+                           int id, int ti, int P, uint32_t* cand, int cap, uint32_t* n) {
+    const DcbHalfKw k = hx.kw[id];
+    const int gene = k.set >> 1, half2 = k.set & 1;
+    const int s0 = half2 ? P - (gene ? hx.j_split : hx.v_split) : P;   // where the whole tag would start (decombine.py:311, 361)
+    const int kk = hx.tags[k.tags_off + ti];
+    const DcbTag& t = (gene ? jtags : vtags)[kk];
+    const int tlen = t.len;
+    const int span = tlen > (int)k.first_len ? tlen : (int)k.first_len;
+    if (s0 < 0 || s0 + span > r.n) { (void)DCB_SLOT_TAKE(n, DCB_HALF_BAIL); return; }
+    uint32_t lo, hi;
+    rd_win32x<PADDED>(r, s0, lo, hi);
+    lo ^= t.bits_lo; hi ^= t.bits_hi;
+    if (inv2) {
+        uint32_t ilo, ihi;
+        rd_win32x<PADDED>(half_inv_view(r, inv2), s0, ilo, ihi);
+        lo |= ilo; hi |= ihi;
+    }
+    lo &= t.mask_lo; hi &= t.mask_hi;
+    const bool dead = tlen != (int)k.first_len || DCB_POPC((lo | (lo >> 1)) & 0x55555555u) + DCB_POPC((hi | (hi >> 1)) & 0x55555555u) > 1;
+    half_append(cand, r.stride, cap, n, DCB_HC_MAKE(gene, 1 + half2, P + (int)k.len, k.len, kk, dead));
 }
 // Set up the read: the invalid-base column of a flagged read (exception entries from e0 on), the hand-over words checked
 // against it (a tag over a symbol packed as base 0 is no occurrence), which half sets have to be found.
@@ -1315,12 +1319,20 @@ DCB_HD bool dcr_half_read(ReadView r, bool flagged, const ExcList& ex, uint32_t 
     if (!half_begin(r, inv2, flagged, ex, e0, inv2col, vtags, jtags, hv, hj, need)) return false;
     const HalfView hx = half_view(hb);
     uint32_t n = 0;
+    struct Sink {
+        const ReadView& r; const uint32_t* inv2; const HalfView& hx; const DcbTag* vtags; const DcbTag* jtags;
+        uint32_t* cand; int cap; uint32_t* n; int P;
+        DCB_HD void operator()(int id, int n_tags) {
+            for (int ti = 0; ti < n_tags; ti++) half_candidate<false>(r, inv2, hx, vtags, jtags, id, ti, P, cand, cap, n);
+        }
+    } sink{r, inv2, hx, vtags, jtags, cand, cap, &n, 0};
     if (need)
         for (int p = 0; p + DCB_HALF_Q <= r.n; p += DCB_HALF_STRIDE) {
             uint32_t e = hx.t[rd_win16(r, p) & mask2(DCB_HALF_Q)] & need;
             for (; e; e &= e - 1) {
                 const int b = DCB_FFS(e) - 1;
-                half_expand<false>(r, inv2, hx, vtags, jtags, b >> 2, p - (b & 3), cand, cap, &n);
+                sink.P = p - (b & 3);
+                half_lookup<false>(r, inv2, hx, b >> 2, sink.P, sink);
             }
         }
     dcb_result o;

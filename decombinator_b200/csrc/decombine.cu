@@ -634,6 +634,7 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
 // ------------------------------------------------------------------------------------------------
 #define DCB_HALF_CAP 8
 #define DCB_HALF_WCAP 192       // probe hits of one warp's 32 reads that are confirmed here; reads beyond pass on
+#define DCB_HALF_WCAP2 126      // (occurrence, tag) pairs of one warp's 32 reads
 template <int NW, int T>
 __global__ void __launch_bounds__(T, 1)
 dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict__ results,
@@ -648,12 +649,14 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
     if (blockIdx.x >= n_tiles) return;                              // nothing queued for this block: do not even stage the tables
     extern __shared__ __align__(16) uint32_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, wbase = tid - lane;
-    SmemLayout L = carve(smem, tb, (size_t)(2 * ROWS + DCB_HALF_CAP + 1) * T + (size_t)(T / 32) * (DCB_HALF_WCAP / 2));
+    SmemLayout L = carve(smem, tb, (size_t)(2 * ROWS + DCB_HALF_CAP + 1) * T + (size_t)(T / 32) * (DCB_HALF_WCAP / 2 + DCB_HALF_WCAP2 + 2));
     uint32_t* s_rd = L.cols;                      // [ROWS][T]
     uint32_t* s_inv = s_rd + (size_t)ROWS * T;    // [ROWS][T] invalid-base column, 01 per non-ACGT symbol
     uint32_t* s_cand = s_inv + (size_t)ROWS * T;  // [DCB_HALF_CAP][T]
     uint32_t* s_n = s_cand + (size_t)DCB_HALF_CAP * T;   // [T] candidates appended per read
     uint16_t* s_work = reinterpret_cast<uint16_t*>(s_n + T) + (size_t)(tid >> 5) * DCB_HALF_WCAP;   // this warp's probe hits: lane << 8 | probe
+    uint32_t* s_work2 = s_n + T + (size_t)(T / 32) * (DCB_HALF_WCAP / 2) + (size_t)(tid >> 5) * (DCB_HALF_WCAP2 + 2);   // (occurrence, tag) pairs:
+    uint32_t* s_n2 = s_work2 + DCB_HALF_WCAP2;                                                       // lane | P << 5 | keyword << 15 | tag index << 23
     s_rd[tid] = 0u; s_rd[(NW + 1) * T + tid] = 0u; s_rd[(NW + 2) * T + tid] = 0u;
     s_inv[tid] = 0u; s_inv[(NW + 1) * T + tid] = 0u; s_inv[(NW + 2) * T + tid] = 0u;
     stage_tables(L, tb);
@@ -741,8 +744,11 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
                 for (uint32_t c = cm[m]; c; c &= c - 1u) s_work[at++] = (uint16_t)((lane << 8) | (32 * m + __ffs(c) - 1));
         }
         __syncwarp();
-        // 3. confirm: lane k takes hit k of the list -- another lane's read as a rule -- and appends the candidates it
-        //    expands to that read's list
+        // 3. confirm, in two flat stages with all lanes busy in each:
+        //    a. lane k takes probe hit k of the list -- another lane's read as a rule --, looks the keyword prefix up and
+        //       compares the keyword; an occurrence puts one item per tag that has this half on the warp's second list
+        if (lane == 0) *s_n2 = 0u;
+        __syncwarp();
         for (int k0 = 0; k0 < n_work; k0 += 32) {
             const bool has = k0 + lane < n_work;
             const uint32_t it = has ? s_work[k0 + lane] : (uint32_t)(lane << 8);
@@ -755,11 +761,36 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
                 rs.w = s_rd + T + wbase + src; rs.stride = T; rs.nw = NW; rs.n = n_s;
                 const uint32_t* c0 = rs.w + (p >> 4) * T;
                 const uint32_t win = __funnelshift_r(c0[0], c0[T], (p & 15) * 2);
+                struct Sink {
+                    uint32_t* list; uint32_t* n2; uint32_t* n_src; uint32_t base;
+                    __device__ __forceinline__ void operator()(int id, int n_tags) {
+                        const uint32_t at = atomicAdd(n2, (uint32_t)n_tags);
+                        if (at + n_tags > DCB_HALF_WCAP2) { atomicAdd(n_src, DCB_HALF_BAIL); return; }   // list full: pass the read on
+                        for (int ti = 0; ti < n_tags; ti++) list[at + ti] = base | ((uint32_t)id << 15) | ((uint32_t)ti << 23);
+                    }
+                } sink{s_work2, s_n2, s_n + wbase + src, 0u};
                 for (uint32_t e = hx.t[win & 0x3FFFu] & need_s; e; e &= e - 1u) {
-                    const int bit = __ffs(e) - 1;
-                    half_expand<true>(rs, flg_s ? s_inv + T + wbase + src : nullptr, hx, vtags, jtags, bit >> 2, p - (bit & 3),
-                                      s_cand + wbase + src, DCB_HALF_CAP, s_n + wbase + src);
+                    const int bit = __ffs(e) - 1, P = p - (bit & 3);
+                    sink.base = (uint32_t)src | ((uint32_t)(P < 0 ? 0 : P) << 5);
+                    half_lookup<true>(rs, flg_s ? s_inv + T + wbase + src : nullptr, hx, bit >> 2, P, sink);
                 }
+            }
+        }
+        __syncwarp();
+        //    b. lane k takes item k of the second list: one (occurrence, tag) pair -> length guard, Hamming <= 1, the
+        //       candidate appended to its read's list
+        const int n_work2 = (int)min(*s_n2, (uint32_t)DCB_HALF_WCAP2);
+        for (int k0 = 0; k0 < n_work2; k0 += 32) {
+            const bool has = k0 + lane < n_work2;
+            const uint32_t it = has ? s_work2[k0 + lane] : (uint32_t)lane;
+            const int src = (int)(it & 31u);
+            const int n_s = __shfl_sync(0xFFFFFFFFu, r.n, src);
+            const int flg_s = __shfl_sync(0xFFFFFFFFu, inv2 != nullptr ? 1 : 0, src);
+            if (has) {
+                ReadView rs;
+                rs.w = s_rd + T + wbase + src; rs.stride = T; rs.nw = NW; rs.n = n_s;
+                half_candidate<true>(rs, flg_s ? s_inv + T + wbase + src : nullptr, hx, vtags, jtags, (int)((it >> 15) & 255u),
+                                     (int)(it >> 23), (int)((it >> 5) & 1023u), s_cand + wbase + src, DCB_HALF_CAP, s_n + wbase + src);
             }
         }
         __syncwarp();
@@ -1226,7 +1257,7 @@ static int prepare_batch(dcb_ctx* c, const dcb_packed* P) {
         halftag_fn hf = pick_half((int)sw);
         c->half_threads = kHalfThreads;
         c->half_smem = ((size_t)c->vcore_words + c->jcore_words + c->half_words + (2 * (sw + 3) + DCB_HALF_CAP + 1) * kHalfThreads +
-                        (kHalfThreads / 32) * (DCB_HALF_WCAP / 2)) * 4 + tail;
+                        (kHalfThreads / 32) * (DCB_HALF_WCAP / 2 + DCB_HALF_WCAP2 + 2)) * 4 + tail;
         int occ_h = 0;
         if (hf && c->half_smem <= kMaxSmem) {
             CUDA_TRY(cudaFuncSetAttribute(hf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->half_smem));
