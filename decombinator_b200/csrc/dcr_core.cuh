@@ -862,35 +862,6 @@ struct HitWords {
         jh.code -= (uint32_t)n_v << 16;          // meaningful only when jh.count == 1
     }
 };
-// The whole search for one read, serially (tests/sim and nothing else: the kernel spreads this work over a warp).
-DCB_HD void q_find(const ReadView& r, const uint32_t* ib, FullHit& vh, FullHit& jh) {
-    const DcbSeedIndex& hd = *reinterpret_cast<const DcbSeedIndex*>(ib);
-    const QIdxView ix = q_idx_view(ib, ib + hd.qtab_off);
-    const uint8_t* filt = reinterpret_cast<const uint8_t*>(ib + hd.bfilter_off);
-    HitWords hw;
-    hw.v = 0; hw.j = 0; hw.n_v = ix.n_v;
-    for (int p = 0; p + ix.q <= r.n; p += ix.stride) {
-        const uint32_t win = rd_win16(r, p);
-        if (!filt[DCB_FSLOT(win, hd.fmul, hd.fbits)]) continue;
-        uint32_t wlo, whi;
-        rd_win32(r, p - ix.wlead, wlo, whi);
-        for (uint32_t offs = q_offsets(ix, DCB_FUNNEL_R(wlo, whi, 2 * ix.wlead)); offs; offs &= offs - 1)
-            q_check_offset<false>(r, ix, p, DCB_FFS(offs) - 1, wlo, whi, hw);
-    }
-    hw.decode(vh, jh);
-}
-
-// Outcome of the fast path for one read.
-enum { FAST_DONE = 0, FAST_DEFER = 1 };
-
-// dcr() for the common case: read without exceptions, exactly one full V tag and one full J tag whose
-// deletion walks stay in the interior.  Anything else is deferred UNCOUNTED to the general kernel,
-// except the two outcomes that are final by themselves (multiple V / multiple J matches).
-// When both_frames is set a failed first frame must be retried, so every non-success defers.
-// Reads with non-ACGT symbols (packed as base 0, which can fake an 'A'): the exact-tag search can only find too many
-// occurrences, never too few, so its outcome stands whenever it found exactly one V and one J tag and no symbol lies in
-// anything the reference looks at for this read -- the two tags, the two deletion windows, the inter-tag span.  xp names
-// the read's entries of the sparse exception list; anything else about such a read is deferred.
 struct ExcProbe {
     const uint32_t* read; const uint16_t* pos; const uint8_t* kind;
     const uint32_t* index;      // index[k] = first entry whose read is >= 32 k; the list ends with read = 0xFFFFFFFF
@@ -907,12 +878,51 @@ DCB_HD bool exc_in_span(const ExcProbe& x, int lo, int hi) {
     return false;
 }
 
+// The same for a read with non-ACGT symbols (packed as base 0, which can fake an 'A'): an occurrence that covers such a
+// symbol is no occurrence.  With the fakes dropped here the hit words are exact for these reads too.
+struct HitWordsX {
+    HitWords hw;
+    const ExcProbe* xp;        // null: the read has no such symbols
+    const DcbUTag* utag;
+    DCB_HD void operator()(uint32_t ctag, int P) {
+        if (xp && exc_in_span(*xp, P, P + (int)(utag[ctag].mask_hi_len >> 24))) return;
+        hw(ctag, P);
+    }
+};
+// The whole search for one read, serially (tests/sim and nothing else: the kernel spreads this work over a warp).
+DCB_HD void q_find(const ReadView& r, const uint32_t* ib, FullHit& vh, FullHit& jh, const ExcProbe* xp = nullptr) {
+    const DcbSeedIndex& hd = *reinterpret_cast<const DcbSeedIndex*>(ib);
+    const QIdxView ix = q_idx_view(ib, ib + hd.qtab_off);
+    const uint8_t* filt = reinterpret_cast<const uint8_t*>(ib + hd.bfilter_off);
+    HitWordsX hw;
+    hw.hw.v = 0; hw.hw.j = 0; hw.hw.n_v = ix.n_v; hw.xp = xp; hw.utag = ix.utag;
+    for (int p = 0; p + ix.q <= r.n; p += ix.stride) {
+        const uint32_t win = rd_win16(r, p);
+        if (!filt[DCB_FSLOT(win, hd.fmul, hd.fbits)]) continue;
+        uint32_t wlo, whi;
+        rd_win32(r, p - ix.wlead, wlo, whi);
+        for (uint32_t offs = q_offsets(ix, DCB_FUNNEL_R(wlo, whi, 2 * ix.wlead)); offs; offs &= offs - 1)
+            q_check_offset<false>(r, ix, p, DCB_FFS(offs) - 1, wlo, whi, hw);
+    }
+    hw.hw.decode(vh, jh);
+}
+
+// Outcome of the fast path for one read.
+enum { FAST_DONE = 0, FAST_DEFER = 1 };
+
+// dcr() for the common case: read without exceptions, exactly one full V tag and one full J tag whose
+// deletion walks stay in the interior.  Anything else is deferred UNCOUNTED to the general kernel,
+// except the two outcomes that are final by themselves (multiple V / multiple J matches).
+// When both_frames is set a failed first frame must be retried, so every non-success defers.
+// Reads with non-ACGT symbols (packed as base 0, which can fake an 'A'): the exact-tag search drops every occurrence that
+// covers such a symbol (HitWordsX), so its hit words are exact, and its outcome stands whenever no symbol lies in anything
+// else the reference looks at for this read -- the two deletion windows, the inter-tag span.  xp names the read's entries of
+// the sparse exception list; anything else about such a read is deferred.
 template <bool PADDED>
 DCB_HD int dcr_fast_from_hits(const ReadView& r, const DcbTag* vtags, const DcbTag* jtags, const FullHit& vh,
                               const FullHit& jh, const DcrParams& prm, int both_frames, dcb_result& out,
                               dcb_cnt_t* C, const bool use_xp = false, const ExcProbe xp = ExcProbe()) {
     if (vh.count == 0) return FAST_DEFER;
-    if (use_xp && (vh.count > 1 || jh.count != 1)) return FAST_DEFER;      // an occurrence may be a fake
     if (vh.count > 1) {
         if (both_frames) return FAST_DEFER;
         DCB_COUNT(C, DCB_C_multiple_v_matches);
@@ -922,6 +932,10 @@ DCB_HD int dcr_fast_from_hits(const ReadView& r, const DcbTag* vtags, const DcbT
     VJ v, j;
     v.idx = fullhit_tag(vh); v.seqpos = fullhit_pos(vh);
     if (!fast_v_deletions<PADDED>(r, vt, v.seqpos + vt.jump - 1, v.pos, v.dels)) return FAST_DEFER;
+    if (use_xp) {   // a symbol in the V deletion window: the walk above compared a fake base
+        const int f0 = v.seqpos + vt.jump;
+        if (exc_in_span(xp, f0 - 32, f0)) return FAST_DEFER;
+    }
     if (jh.count == 0) return FAST_DEFER;
     if (jh.count > 1) {
         if (both_frames) return FAST_DEFER;
@@ -981,7 +995,7 @@ DCB_HD int dcr_exact_read(const ReadView& r, bool flagged, const uint32_t* vcore
     vh.count = 0; vh.code = 0;
     jh.count = 0; jh.code = 0;
     if (use_q) {          // the flat kernel's tables (union index only)
-        q_find(r, vidx, vh, jh);
+        q_find(r, vidx, vh, jh, xp);
     } else if (!jidx) {
         fast_find(r, vidx, vh, jh, true);
     } else {
@@ -1273,7 +1287,9 @@ DCB_HD bool half_walk(const ReadView& r, const uint32_t* inv2, const HalfView& h
 // then void).  Written as a sequence of short predicated steps so that the lanes of a warp walk it together.
 template <bool PADDED>
 DCB_HD bool half_run(const ReadView& r, const uint32_t* inv2, const HalfView& hx, const DcbTag* vtags, const DcbTag* jtags,
-                     uint32_t hv, uint32_t hj, uint32_t* cand, int cap, uint32_t n, const DcrParams& prm, dcb_result& out, uint32_t& pend) {
+                     uint32_t hv, uint32_t hj, uint32_t* cand, int cap, uint32_t n, const DcrParams& prm, dcb_result& out, uint32_t& pend,
+                     int* why = nullptr) {
+    if (why) *why = n >= DCB_HALF_BAIL ? 2 : 3;
     if (n > (uint32_t)cap) return false;
     for (int g = 0; g < 2; g++) {                                                           // the full-tag occurrences handed over
         const uint32_t h = g ? hj : hv;
@@ -1291,12 +1307,14 @@ DCB_HD bool half_run(const ReadView& r, const uint32_t* inv2, const HalfView& hx
     bool ok = true;
     const uint32_t ev = half_select<true>(cand, r.stride, (int)n, i, pend);
     if (ev) ok = half_walk<true, PADDED>(r, inv2, hx, vtags, ev, 0, v);
+    if (why) *why = 4;
     uint32_t ej = 0u;
     if (ev && ok) {                                                                         // :542-548
         ej = half_select<false>(cand, r.stride, (int)n, i, pend);
         if (!ej) pend |= 1u << DCB_C_VJ_assignment_failed;                                  // :583-585
     }
     if (ej) ok = half_walk<false, PADDED>(r, inv2, hx, jtags, ej, v.pos + 1, j);
+    if (why && ej) *why = 5;
     if (ej && ok) {
         const DcbTagFin vt = tag_fin(vtags, v.idx), jt = tag_fin(jtags, j.idx);
         const int c = dcr_finish(r, vt.jump, vt.len, jt.jump, jt.len, v, j, prm, out);
@@ -1311,11 +1329,12 @@ DCB_HD void half_commit(uint32_t pend, dcb_cnt_t* C) {
 // false: pass the read on, nothing counted.
 DCB_HD bool dcr_half_read(ReadView r, bool flagged, const ExcList& ex, uint32_t e0, uint32_t hv, uint32_t hj, uint32_t* inv2col,
                           uint32_t* cand, int cap, const uint32_t* vcore, const uint32_t* jcore, const uint32_t* hb,
-                          const DcrParams& prm, dcb_result& out, dcb_cnt_t* C) {
+                          const DcrParams& prm, dcb_result& out, dcb_cnt_t* C, int* why = nullptr) {
     const DcbTag* vtags = gene_tags(vcore);
     const DcbTag* jtags = gene_tags(jcore);
     const uint32_t* inv2;
     uint32_t need, pend = 0;
+    if (why) *why = 1;
     if (!half_begin(r, inv2, flagged, ex, e0, inv2col, vtags, jtags, hv, hj, need)) return false;
     const HalfView hx = half_view(hb);
     uint32_t n = 0;
@@ -1338,7 +1357,7 @@ DCB_HD bool dcr_half_read(ReadView r, bool flagged, const ExcList& ex, uint32_t 
     dcb_result o;
     o.status = 0; o.frame = 0; o.v = o.j = 0; o.vdel = o.jdel = 0;
     o.ins_start = o.ins_end = o.v_seq_start = o.j_seq_end = 0;
-    if (!half_run<false>(r, inv2, hx, vtags, jtags, hv, hj, cand, cap, n, prm, o, pend)) return false;
+    if (!half_run<false>(r, inv2, hx, vtags, jtags, hv, hj, cand, cap, n, prm, o, pend, why)) return false;
     out = o;
     half_commit(pend, C);
     return true;

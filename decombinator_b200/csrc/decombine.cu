@@ -570,8 +570,12 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
 #endif
 
         // 2. confirm, one (hit, offset) candidate per trip
-        HitWords hw;
+        ExcProbe xp;
+        xp.read = b.exc_read; xp.pos = b.exc_pos; xp.kind = b.exc_kind; xp.index = b.exc_index; xp.ri = ri;
+        HitWordsX hwx;                                               // EXC: occurrences over a non-ACGT symbol are dropped
+        HitWords& hw = hwx.hw;
         hw.v = 0; hw.j = 0; hw.n_v = ix.n_v;
+        hwx.xp = (EXC && flagged) ? &xp : nullptr; hwx.utag = ix.utag;
         uint32_t offs = 0, wlo = 0, whi = 0;
         int p = 0;
         for (;;) {
@@ -593,15 +597,14 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
             if (offs) {
                 const int o = 31 - __clz(offs);
                 offs ^= 1u << o;
-                q_check_offset<true>(r, ix, p, o, wlo, whi, hw);
+                if (EXC) q_check_offset<true>(r, ix, p, o, wlo, whi, hwx);
+                else q_check_offset<true>(r, ix, p, o, wlo, whi, hw);
                 if (hw.v == DCB_HIT_MULTI) { h = 0u; hb = 0u; offs = 0u; }   // final whatever else is found (decombine.py:278-280)
             }
         }
         FullHit vh, jh;
         hw.decode(vh, jh);
         if (EXC) {
-            ExcProbe xp;
-            xp.read = b.exc_read; xp.pos = b.exc_pos; xp.kind = b.exc_kind; xp.index = b.exc_index; xp.ri = ri;
             if (scan) action = dcr_fast_from_hits<true>(r, vtags, jtags, vh, jh, prm, both_frames, out, s_cnt, flagged, xp);
         } else {
             if (scan) action = dcr_fast_from_hits<true>(r, vtags, jtags, vh, jh, prm, both_frames, out, s_cnt);
@@ -632,7 +635,7 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
 // the 32-base window, more than DCB_HALF_CAP candidates) goes on to the general kernel through a second queue, uncounted.
 // Tables: 0 = V tag records, 1 = J tag records, 2 = half-tag index.
 // ------------------------------------------------------------------------------------------------
-#define DCB_HALF_CAP 8
+#define DCB_HALF_CAP 12
 #define DCB_HALF_WCAP 192       // probe hits of one warp's 32 reads that are confirmed here; reads beyond pass on
 #define DCB_HALF_WCAP2 126      // (occurrence, tag) pairs of one warp's 32 reads
 template <int NW, int T>
@@ -1019,13 +1022,13 @@ static int q_rows(int nw) {   // must match the kernel's ROWS
 }
 
 typedef void (*halftag_fn)(BatchDev, Tables4, DcrParams, dcb_result*, unsigned long long*, const uint32_t*, const uint32_t*, uint32_t*, uint32_t*);
-static constexpr int kHalfThreads = 768;
-static halftag_fn pick_half(int nw) {
+// block width per slot size: as wide as the read / invalid-base / candidate columns leave room for beside the tables
+static halftag_fn pick_half(int nw, int* threads) {
     switch (nw) {
-        case 8:  return dcb_halftag_kernel<8, kHalfThreads>;
-        case 12: return dcb_halftag_kernel<12, kHalfThreads>;
-        case 16: return dcb_halftag_kernel<16, kHalfThreads>;
-        case 20: return dcb_halftag_kernel<20, kHalfThreads>;
+        case 8:  *threads = 768; return dcb_halftag_kernel<8, 768>;
+        case 12: *threads = 768; return dcb_halftag_kernel<12, 768>;
+        case 16: *threads = 768; return dcb_halftag_kernel<16, 768>;
+        case 20: *threads = 640; return dcb_halftag_kernel<20, 640>;
         default: return nullptr;
     }
 }
@@ -1254,14 +1257,15 @@ static int prepare_batch(dcb_ctx* c, const dcb_packed* P) {
     // half-tag kernel: between the flat kernel and the general kernel, for chains with a half-tag index (one frame only)
     c->half_fn = nullptr;
     if (qfn && c->d_half && !c->params.both_frames && c->params.force_general == 0) {
-        halftag_fn hf = pick_half((int)sw);
-        c->half_threads = kHalfThreads;
-        c->half_smem = ((size_t)c->vcore_words + c->jcore_words + c->half_words + (2 * (sw + 3) + DCB_HALF_CAP + 1) * kHalfThreads +
-                        (kHalfThreads / 32) * (DCB_HALF_WCAP / 2 + DCB_HALF_WCAP2 + 2)) * 4 + tail;
+        int ht = 0;
+        halftag_fn hf = pick_half((int)sw, &ht);
+        c->half_threads = ht;
+        c->half_smem = ((size_t)c->vcore_words + c->jcore_words + c->half_words + (2 * (sw + 3) + DCB_HALF_CAP + 1) * ht +
+                        (ht / 32) * (DCB_HALF_WCAP / 2 + DCB_HALF_WCAP2 + 2)) * 4 + tail;
         int occ_h = 0;
         if (hf && c->half_smem <= kMaxSmem) {
             CUDA_TRY(cudaFuncSetAttribute(hf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->half_smem));
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_h, hf, kHalfThreads, c->half_smem));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_h, hf, ht, c->half_smem));
             if (occ_h >= 1) { c->half_fn = (void*)hf; c->half_grid = c->n_sms * occ_h; }
         }
     }

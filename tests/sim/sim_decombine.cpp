@@ -8,6 +8,9 @@
 #include <cstring>
 #include <vector>
 
+// why the half-tag path passed reads on (diagnostics): 1 several full-tag candidates / read too long, 2 tag window outside the
+// read, 3 too many candidates, 4 V deletion walk not interior, 5 J deletion walk not interior
+extern "C" { uint64_t sim_half_pass_reasons[8] = {0}; }
 // vidx: the V seed index, or the union index of both genes when jidx is null
 extern "C" int sim_decombine(const dcb_packed* P, const uint32_t* vgen, const uint32_t* jgen, const uint32_t* vcore,
                              const uint32_t* jcore, const uint32_t* vidx, const uint32_t* jidx, int both_frames,
@@ -53,9 +56,10 @@ extern "C" int sim_decombine(const dcb_packed* P, const uint32_t* vgen, const ui
             deferred++;
             std::memset(&o, 0, sizeof(o));
             const uint32_t e0 = flagged ? exc_lower_bound(ex, (uint32_t)ri) : 0u;
-            if (dcr_half_read(r, flagged, ex, e0, hand[0], hand[1], inv2.data(), hits.data(), 8, vcore, jcore, half, prm, o, cnt))
+            int why = 0;
+            if (dcr_half_read(r, flagged, ex, e0, hand[0], hand[1], inv2.data(), hits.data(), 12, vcore, jcore, half, prm, o, cnt, &why))
                 action = FAST_DONE;
-            else deferred--;
+            else { deferred--; if (why >= 0 && why < 8) sim_half_pass_reasons[why]++; }
         }
         if (action == FAST_DEFER) {
             deferred++; deferred2++;
