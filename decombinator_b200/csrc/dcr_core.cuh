@@ -879,14 +879,32 @@ DCB_HD bool exc_in_span(const ExcProbe& x, int lo, int hi) {
 }
 
 // The same for a read with non-ACGT symbols (packed as base 0, which can fake an 'A'): an occurrence that covers such a
-// symbol is no occurrence.  With the fakes dropped here the hit words are exact for these reads too.
+// symbol is no occurrence.  The exception list is only consulted when it matters -- when a SECOND distinct occurrence
+// turns up (is one of the two a fake?) and once at the end for the single occurrence kept (finish) -- so the common
+// path through the confirmation loop is the plain one.  After finish() the hit words are exact for these reads too.
 struct HitWordsX {
     HitWords hw;
     const ExcProbe* xp;        // null: the read has no such symbols
     const DcbUTag* utag;
+    DCB_HD bool fake(uint32_t c) const {                             // c: DCB_HIT_ONE | ctag << 16 | position
+        const int P = (int)(c & 0xFFFFu);
+        return exc_in_span(*xp, P, P + (int)(utag[(c >> 16) & 0x7FFFu].mask_hi_len >> 24));
+    }
     DCB_HD void operator()(uint32_t ctag, int P) {
-        if (xp && exc_in_span(*xp, P, P + (int)(utag[ctag].mask_hi_len >> 24))) return;
+        if (xp) {
+            const uint32_t c = DCB_HIT_ONE | (ctag << 16) | (uint32_t)P;
+            uint32_t& cur = (int)ctag >= hw.n_v ? hw.j : hw.v;
+            if (cur != 0u && cur != c && cur != DCB_HIT_MULTI) {     // a second occurrence: drop whichever is a fake
+                if (fake(c)) return;
+                if (fake(cur)) { cur = c; return; }
+            }
+        }
         hw(ctag, P);
+    }
+    DCB_HD void finish() {
+        if (!xp) return;
+        if (hw.v != 0u && hw.v != DCB_HIT_MULTI && fake(hw.v)) hw.v = 0u;
+        if (hw.j != 0u && hw.j != DCB_HIT_MULTI && fake(hw.j)) hw.j = 0u;
     }
 };
 // The whole search for one read, serially (tests/sim and nothing else: the kernel spreads this work over a warp).
@@ -904,6 +922,7 @@ DCB_HD void q_find(const ReadView& r, const uint32_t* ib, FullHit& vh, FullHit& 
         for (uint32_t offs = q_offsets(ix, DCB_FUNNEL_R(wlo, whi, 2 * ix.wlead)); offs; offs &= offs - 1)
             q_check_offset<false>(r, ix, p, DCB_FFS(offs) - 1, wlo, whi, hw);
     }
+    hw.finish();
     hw.hw.decode(vh, jh);
 }
 

@@ -602,6 +602,7 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
                 if (hw.v == DCB_HIT_MULTI) { h = 0u; hb = 0u; offs = 0u; }   // final whatever else is found (decombine.py:278-280)
             }
         }
+        if (EXC) hwx.finish();
         FullHit vh, jh;
         hw.decode(vh, jh);
         if (EXC) {
