@@ -862,22 +862,45 @@ struct HitWords {
         jh.code -= (uint32_t)n_v << 16;          // meaningful only when jh.count == 1
     }
 };
+// The non-ACGT symbols of ONE read, in registers: up to four positions (16 bits each, 0xFFFF = none), fetched once per
+// read (the kernel does it warp-wide: the 32 lanes of a warp own 32 consecutive reads, i.e. one run of the sorted list).
+// A read with more of them is not searched by the exact-tag kernel (over: it goes to the general kernel).
 struct ExcProbe {
-    const uint32_t* read; const uint16_t* pos; const uint8_t* kind;
-    const uint32_t* index;      // index[k] = first entry whose read is >= 32 k; the list ends with read = 0xFFFFFFFF
-    uint32_t ri;
+    uint32_t p01, p23;
+    uint32_t e0;                // the read's first entry in the exception list
+    bool over;
 };
-DCB_HD bool exc_in_span(const ExcProbe& x, int lo, int hi) {
-    uint32_t e = x.index[x.ri >> 5];
-    while (x.read[e] < x.ri) e++;
-    for (; x.read[e] == x.ri; e++) {
-        if (x.kind[e] == 3) continue;               // a real base in this frame
-        const int p = (int)x.pos[e];
-        if (p >= lo && p < hi) return true;
-    }
-    return false;
+DCB_HD ExcProbe exc_probe_none() {
+    ExcProbe x;
+    x.p01 = x.p23 = 0xFFFFFFFFu; x.e0 = 0; x.over = false;
+    return x;
 }
-
+DCB_HD void exc_probe_add(ExcProbe& x, int slot, uint32_t pos) {   // slot 0..3
+    const uint32_t sh = (slot & 1) * 16, m = 0xFFFFu << sh;
+    uint32_t& w = slot < 2 ? x.p01 : x.p23;
+    w = (w & ~m) | (pos << sh);
+}
+// The read's entries from the sorted list (tests/sim, and the shape the kernel's warp-wide fetch reproduces):
+// index[k] = first entry whose read is >= 32 k; the list ends with read = 0xFFFFFFFF.  Entries of kind 3 are real bases
+// in this frame.
+DCB_HD ExcProbe exc_probe_load(const uint32_t* read, const uint16_t* pos, const uint8_t* kind, const uint32_t* index, uint32_t ri) {
+    ExcProbe x = exc_probe_none();
+    uint32_t e = index[ri >> 5];
+    while (read[e] < ri) e++;
+    x.e0 = e;
+    int n = 0;
+    for (; read[e] == ri; e++) {
+        if (kind[e] == 3) continue;
+        if (n < 4) exc_probe_add(x, n, pos[e]);
+        n++;
+    }
+    x.over = n > 4;
+    return x;
+}
+DCB_HD bool exc_in_span(const ExcProbe& x, int lo, int hi) {
+    const int a = (int)(x.p01 & 0xFFFFu), b = (int)(x.p01 >> 16), c = (int)(x.p23 & 0xFFFFu), d = (int)(x.p23 >> 16);
+    return (a >= lo && a < hi) || (b >= lo && b < hi) || (c >= lo && c < hi) || (d >= lo && d < hi);
+}
 // The same for a read with non-ACGT symbols (packed as base 0, which can fake an 'A'): an occurrence that covers such a
 // symbol is no occurrence.  The exception list is only consulted when it matters -- when a SECOND distinct occurrence
 // turns up (is one of the two a fake?) and once at the end for the single occurrence kept (finish) -- so the common
@@ -940,7 +963,7 @@ enum { FAST_DONE = 0, FAST_DEFER = 1 };
 template <bool PADDED>
 DCB_HD int dcr_fast_from_hits(const ReadView& r, const DcbTag* vtags, const DcbTag* jtags, const FullHit& vh,
                               const FullHit& jh, const DcrParams& prm, int both_frames, dcb_result& out,
-                              dcb_cnt_t* C, const bool use_xp = false, const ExcProbe xp = ExcProbe()) {
+                              dcb_cnt_t* C, const bool use_xp = false, const ExcProbe xp = exc_probe_none()) {
     if (vh.count == 0) return FAST_DEFER;
     if (vh.count > 1) {
         if (both_frames) return FAST_DEFER;
@@ -1008,7 +1031,7 @@ DCB_HD int dcr_exact_read(const ReadView& r, bool flagged, const uint32_t* vcore
                           dcb_result& out, dcb_cnt_t* C, bool use_q = false, const ExcProbe* xp = nullptr,
                           uint32_t* hand = nullptr) {
     if (hand) { hand[0] = DCB_HIT_MULTI; hand[1] = DCB_HIT_MULTI; }   // "not searched": the half-tag path passes such a read on
-    if (flagged && !xp) return FAST_DEFER;
+    if (flagged && (!xp || xp->over)) return FAST_DEFER;
     if (!flagged) xp = nullptr;
     FullHit vh, jh;
     vh.count = 0; vh.code = 0;
@@ -1023,7 +1046,7 @@ DCB_HD int dcr_exact_read(const ReadView& r, bool flagged, const uint32_t* vcore
     }
     if (hand) { hand[0] = half_word_of(vh); hand[1] = half_word_of(jh); }
     return dcr_fast_from_hits<false>(r, gene_tags(vcore), gene_tags(jcore), vh, jh, prm, both_frames, out, C, xp != nullptr,
-                                     xp ? *xp : ExcProbe());
+                                     xp ? *xp : exc_probe_none());
 }
 
 // General kernel body for one read: r has w/stride/n/nw set; inv0, rd1, inv1 are this thread's scratch

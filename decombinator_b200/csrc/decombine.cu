@@ -481,6 +481,7 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
     uint32_t* s_qtab = s_head + qt.head_words;
     dcb_cnt_t* s_cnt = s_qtab + qt.qtab_words;
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_cnt + ((DCB_NCOUNTERS + 3) & ~3));
+    uint32_t* s_x = reinterpret_cast<uint32_t*>(bar + 2);            // [T] EXC only: where each read's exception entries sit in its warp's run
 
     s_rd[tid] = 0u;
     for (int k = 0; k < TRAIL; k++) s_rd[(1 + NW + k) * T + tid] = 0u;
@@ -522,7 +523,37 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
         }
         // EXC: the batch has reads with non-ACGT symbols (its own instantiation, so that the clean path carries none of it)
         const bool flagged = live && b.n_exc && ((__ldg(b.flags + (ri >> 5)) >> (ri & 31)) & 1u);
-        const bool scan = EXC ? live : (live && !flagged);   // EXC: reads with non-ACGT symbols too, see ExcProbe
+        ExcProbe xp = exc_probe_none();
+        if (EXC) {
+            // The warp's 32 reads are 32 consecutive read indices (b.first and T are multiples of 32): their non-ACGT symbols
+            // are ONE run of the sorted exception list.  Lane k fetches entry k of the run; every read's entries (a short
+            // sub-run) then come to its lane by shuffle -- no per-read scans of the list in global memory.
+            const int lane = tid & 31;
+            const uint32_t g = ri >> 5;
+            const bool wlive = tile * T + (tid & ~31) < b.n_reads;          // the warp has a live lane: g is a group of the batch
+            const uint32_t eb = wlive ? __ldg(b.exc_index + g) : 0u, ee = wlive ? __ldg(b.exc_index + g + 1) : 0u;
+            const uint32_t k = eb + lane;
+            const bool have = k < ee;
+            const uint32_t rd = have ? __ldg(b.exc_read + k) : 0u;
+            const uint32_t ps = have ? (uint32_t)__ldg(b.exc_pos + k) : 0u, kd = have ? (uint32_t)__ldg(b.exc_kind + k) : 3u;
+            const uint32_t same = __match_any_sync(0xFFFFFFFFu, have ? (rd & 31u) : 32u + lane);   // the lanes holding one read's entries
+            s_x[tid] = 0u;
+            __syncwarp();
+            if (have && lane == __ffs(same) - 1) s_x[(tid & ~31) + (rd & 31u)] = (uint32_t)lane | ((uint32_t)__popc(same) << 8);
+            __syncwarp();
+            const uint32_t info = s_x[tid];
+            const int first = (int)(info & 255u), cnt = (int)(info >> 8);
+            int nx = 0;
+#pragma unroll
+            for (int s2 = 0; s2 < 4; s2++) {
+                const uint32_t p2 = __shfl_sync(0xFFFFFFFFu, ps, (first + s2) & 31), k2 = __shfl_sync(0xFFFFFFFFu, kd, (first + s2) & 31);
+                if (s2 < cnt && k2 != 3u) { exc_probe_add(xp, nx, p2); nx++; }
+            }
+            xp.e0 = eb + (uint32_t)first;
+            // more than four symbols, or a run that does not fit in the 32 entries fetched: not searched here
+            xp.over = flagged && (cnt > 4 || cnt == 0 || (ee - eb > 32u && first + cnt >= 32));
+        }
+        const bool scan = EXC ? (live && !xp.over) : (live && !flagged);   // EXC: reads with non-ACGT symbols too, see ExcProbe
         ReadView r;
         r.w = col; r.inv = nullptr; r.stride = T;
         r.n = b.uniform_len ? (int)b.uniform_len : (live ? (int)__ldg(b.lens + ri) : 0);
@@ -570,8 +601,6 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
 #endif
 
         // 2. confirm, one (hit, offset) candidate per trip
-        ExcProbe xp;
-        xp.read = b.exc_read; xp.pos = b.exc_pos; xp.kind = b.exc_kind; xp.index = b.exc_index; xp.ri = ri;
         HitWordsX hwx;                                               // EXC: occurrences over a non-ACGT symbol are dropped
         HitWords& hw = hwx.hw;
         hw.v = 0; hw.j = 0; hw.n_v = ix.n_v;
@@ -617,7 +646,8 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
             // hand-over to dcb_halftag_kernel in the read's (still unused) result slot: what the search found, one word
             // per gene with the tag numbered inside its gene; "several" for a read that was not searched
             const bool one_j = hw.j != 0u && hw.j != DCB_HIT_MULTI;
-            const uint4 hand = make_uint4(scan ? hw.v : DCB_HIT_MULTI, scan ? (one_j ? hw.j - ((uint32_t)ix.n_v << 16) : hw.j) : DCB_HIT_MULTI, 0u, 0u);
+            const uint4 hand = make_uint4(scan ? hw.v : DCB_HIT_MULTI, scan ? (one_j ? hw.j - ((uint32_t)ix.n_v << 16) : hw.j) : DCB_HIT_MULTI,
+                                          xp.e0, 0u);
             *reinterpret_cast<uint4*>(results + ri) = hand;
         }
     }
@@ -697,11 +727,7 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
         bool act = live;                          // still being decided here; live && !act: passed on
         if (live) {
             const bool flagged = b.n_exc && ((__ldg(b.flags + (ri >> 5)) >> (ri & 31)) & 1u);
-            uint32_t e0 = 0;
-            if (flagged) {
-                e0 = __ldg(b.exc_index + (ri >> 5));
-                while (__ldg(b.exc_read + e0) < ri) e0++;
-            }
+            const uint32_t e0 = hand.z;           // the read's first entry in the exception list, from the exact-tag kernel
             act = half_begin(r, inv2, flagged, ex, e0, icol, vtags, jtags, hv, hj, need);
         }
         if (!act) need = 0;
@@ -1207,7 +1233,7 @@ static int prepare_batch(dcb_ctx* c, const dcb_packed* P) {
         qfn = pick_q((int)sw, c->uqq, c->uqs, c->lminv, P->n_exc != 0);
     if (qfn) {
         c->exact_smem = ((size_t)1 << DCB_FBITS) + ((size_t)q_rows((int)sw) * kQThreads +
-                         c->vcore_words + c->jcore_words + c->uhead + c->uqtab_words) * 4 + tail;
+                         c->vcore_words + c->jcore_words + c->uhead + c->uqtab_words) * 4 + tail + (P->n_exc ? kQThreads * 4 : 0);
         if (c->exact_smem > kMaxSmem) qfn = nullptr;
     }
     c->q_fn = (void*)qfn;

@@ -46,8 +46,7 @@ extern "C" int sim_decombine(const dcb_packed* P, const uint32_t* vgen, const ui
         dcb_result o;
         std::memset(&o, 0, sizeof(o));
         int action = FAST_DEFER;
-        ExcProbe xp;
-        xp.read = xread.data(); xp.pos = P->exc_pos; xp.kind = P->exc_kind; xp.index = xindex.data(); xp.ri = (uint32_t)ri;
+        const ExcProbe xp = flagged ? exc_probe_load(xread.data(), P->exc_pos, P->exc_kind, xindex.data(), (uint32_t)ri) : exc_probe_none();
         uint32_t hand[2] = {DCB_HIT_MULTI, DCB_HIT_MULTI};
         if (mode == 0 || mode == 2)
             action = dcr_exact_read(r, flagged, vcore, jcore, vidx, jidx, prm, both_frames, o, cnt, mode == 2,
@@ -55,7 +54,7 @@ extern "C" int sim_decombine(const dcb_packed* P, const uint32_t* vgen, const ui
         if (action == FAST_DEFER && half && !both_frames) {   // the half-tag path (dcb_halftag_kernel)
             deferred++;
             std::memset(&o, 0, sizeof(o));
-            const uint32_t e0 = flagged ? exc_lower_bound(ex, (uint32_t)ri) : 0u;
+            const uint32_t e0 = xp.e0;   // handed over by the exact-tag kernel
             int why = 0;
             if (dcr_half_read(r, flagged, ex, e0, hand[0], hand[1], inv2.data(), hits.data(), 12, vcore, jcore, half, prm, o, cnt, &why))
                 action = FAST_DONE;
@@ -100,14 +99,13 @@ extern "C" int sim_defer_classes(const dcb_packed* P, const uint32_t* vcore, con
         r.n = P->uniform_len ? (int)P->uniform_len : (int)P->lens[ri];
         r.nw = (int)P->slot_words;
         const bool flagged = P->n_exc && ((P->flags[ri >> 5] >> (ri & 31)) & 1u);
-        ExcProbe xp;
-        xp.read = xread.data(); xp.pos = P->exc_pos; xp.kind = P->exc_kind; xp.index = xindex.data(); xp.ri = (uint32_t)ri;
+        const ExcProbe xp = flagged ? exc_probe_load(xread.data(), P->exc_pos, P->exc_kind, xindex.data(), (uint32_t)ri) : exc_probe_none();
         FullHit vh, jh;
-        q_find(r, uidx, vh, jh);
+        q_find(r, uidx, vh, jh, flagged ? &xp : nullptr);
         dcb_result o;
         std::memset(&o, 0, sizeof(o));
         const int action = dcr_fast_from_hits<false>(r, gene_tags(vcore), gene_tags(jcore), vh, jh, prm, both_frames, o, cnt,
-                                                     flagged, flagged ? xp : ExcProbe());
+                                                     flagged, xp);
         uint8_t c = 0;
         if (action == FAST_DEFER) {
             if (vh.count == 0) c |= 1;
