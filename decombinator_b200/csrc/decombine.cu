@@ -636,6 +636,7 @@ dcb_exact_kernel_flat(BatchDev b, QTables qt, DcrParams prm, int both_frames, dc
         hw.decode(vh, jh);
         if (EXC) {
             if (scan) action = dcr_fast_from_hits<true>(r, vtags, jtags, vh, jh, prm, both_frames, out, s_cnt, flagged, xp);
+            else if (live) action = FAST_DEFER;
         } else {
             if (scan) action = dcr_fast_from_hits<true>(r, vtags, jtags, vh, jh, prm, both_frames, out, s_cnt);
             else if (live) action = FAST_DEFER;
