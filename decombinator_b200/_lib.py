@@ -92,6 +92,9 @@ def lib():
     L.dcb_ctx_destroy.argtypes = [vp]
     L.dcb_ctx_set_stream.argtypes = [vp, vp]
     L.dcb_decombine_batch.argtypes = [vp, ctypes.POINTER(CPacked), vp, vp]
+    L.dcb_decombine_ascii.argtypes = [vp, vp, vp, vp, u64, u32, i32, vp, vp]
+    L.dcb_pack_device.argtypes = [vp, vp, vp, vp, u64, u32, i32, ctypes.POINTER(ctypes.POINTER(CPacked))]
+    L.dcb_pack_device_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     L.dcb_pinned_alloc.restype = vp
     L.dcb_pinned_alloc.argtypes = [ctypes.c_size_t]
     L.dcb_pinned_free.argtypes = [vp]
@@ -229,6 +232,15 @@ class Packed:
     @property
     def max_len(self):
         return int(self._p.contents.max_len)
+
+    def arrays(self):
+        """Every array of the batch as numpy copies (words, lens, flags, exc_read, exc_pos, exc_kind)."""
+        c, n, ne = self._p.contents, self.n_reads, self.n_exc
+
+        def arr(ptr, count):
+            return np.ctypeslib.as_array(ptr, shape=(max(1, count),))[:count].copy()
+        return {"words": arr(c.words, n * self.slot_words), "lens": arr(c.lens, n), "flags": arr(c.flags, (n + 31) // 32),
+                "exc_read": arr(c.exc_read, ne), "exc_pos": arr(c.exc_pos, ne), "exc_kind": arr(c.exc_kind, ne)}
 
     def words(self):
         c = self._p.contents
@@ -396,6 +408,41 @@ class Context:
             counters = np.zeros(NCOUNTERS, dtype=np.uint64)
         _check(lib().dcb_decombine_batch(self._h, packed.c, res.ctypes.data, counters.ctypes.data), "dcb_decombine_batch")
         return res, counters
+
+    @staticmethod
+    def _ascii_args(buf, off, length, uniform_len):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8) if not (isinstance(buf, np.ndarray) and buf.dtype == np.uint8 and buf.flags.c_contiguous) else buf
+        n = len(length) if length is not None else (len(off) if off is not None else (len(buf) // uniform_len if uniform_len else 0))
+        off = None if off is None else np.ascontiguousarray(off, dtype=np.uint64)
+        length = None if (length is None or uniform_len) else np.ascontiguousarray(length, dtype=np.uint32)
+        return buf, off, length, n
+
+    def decombine_ascii(self, buf, off, length, revcomp, uniform_len=0, counters=None, pinned=False):
+        """dcb_decombine_ascii: ASCII reads in host memory in (read i = buf[off[i] : off[i] + length[i]]; off None = contiguous
+        reads of uniform_len), result records in host memory out; the reads are packed on the device."""
+        buf, off, length, n = self._ascii_args(buf, off, length, uniform_len)
+        res = self._pinned_results(n) if pinned else np.zeros(n, dtype=RESULT_DTYPE)
+        if counters is None:
+            counters = np.zeros(NCOUNTERS, dtype=np.uint64)
+        _check(lib().dcb_decombine_ascii(self._h, buf.ctypes.data if len(buf) else None, off.ctypes.data if off is not None else None,
+                                         length.ctypes.data if length is not None else None, n, int(uniform_len), int(bool(revcomp)),
+                                         res.ctypes.data, counters.ctypes.data), "dcb_decombine_ascii")
+        self._n = n
+        return res, counters
+
+    def pack_device(self, buf, off, length, revcomp, uniform_len=0) -> Packed:
+        """dcb_pack_device: the device packer's output as a host Packed (tests compare it with pack_arrays)."""
+        buf, off, length, n = self._ascii_args(buf, off, length, uniform_len)
+        out = ctypes.POINTER(CPacked)()
+        _check(lib().dcb_pack_device(self._h, buf.ctypes.data if len(buf) else None, off.ctypes.data if off is not None else None,
+                                     length.ctypes.data if length is not None else None, n, int(uniform_len), int(bool(revcomp)),
+                                     ctypes.byref(out)), "dcb_pack_device")
+        return Packed(out)
+
+    def pack_device_ms(self):
+        ms = ctypes.c_double()
+        _check(lib().dcb_pack_device_ms(self._h, ctypes.byref(ms)), "dcb_pack_device_ms")
+        return ms.value
 
     def upload(self, packed: Packed):
         _check(lib().dcb_upload(self._h, packed.c), "dcb_upload")

@@ -24,6 +24,8 @@ bool dcb_build_seed_index(const std::vector<std::string>* gene_v, const std::vec
 // Sampled half-tag index over both genes of a chain (DcbHalfIndex); false when a half keyword is too short for it.
 bool dcb_build_half_index(const dcb_tagset* v, const dcb_tagset* j, std::vector<uint32_t>& out);
 
+extern "C" int dcb_packed_alloc(uint64_t n, uint32_t slot_words, uint32_t n_exc, dcb_packed** out);
+
 #if defined(__GNUC__)
 __attribute__((format(printf, 1, 2)))
 #endif

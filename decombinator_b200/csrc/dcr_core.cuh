@@ -1012,11 +1012,12 @@ struct ExcList {
     const uint32_t* read;   // sorted read indices
     const uint16_t* pos;
     const uint8_t* kind;    // 1 'N', 2 other, 3 valid in the packed frame but not in its reverse complement
-    uint32_t n;
+    uint32_t n;             // end of the range that can hold a read's entries (the kernels: the end of its 32-read group's run)
+    uint32_t lo = 0;        // start of that range
 };
 
 DCB_HD uint32_t exc_lower_bound(const ExcList& ex, uint32_t key) {
-    uint32_t lo = 0, hi = ex.n;
+    uint32_t lo = ex.lo, hi = ex.n;
     while (lo < hi) {
         uint32_t mid = (lo + hi) >> 1;
         if (ex.read[mid] < key) lo = mid + 1; else hi = mid;

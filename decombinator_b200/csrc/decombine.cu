@@ -729,7 +729,9 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
         if (live) {
             const bool flagged = b.n_exc && ((__ldg(b.flags + (ri >> 5)) >> (ri & 31)) & 1u);
             const uint32_t e0 = hand.z;           // the read's first entry in the exception list, from the exact-tag kernel
-            act = half_begin(r, inv2, flagged, ex, e0, icol, vtags, jtags, hv, hj, need);
+            ExcList exr = ex;
+            if (flagged) exr.n = __ldg(b.exc_index + (ri >> 5) + 1);   // its entries end inside its 32-read group's run
+            act = half_begin(r, inv2, flagged, exr, e0, icol, vtags, jtags, hv, hj, need);
         }
         if (!act) need = 0;
         s_n[tid] = 0u;
@@ -898,7 +900,9 @@ dcb_general_kernel(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_r
             r.n = b.uniform_len ? (int)b.uniform_len : (int)__ldg(b.lens + ri);
             r.nw = nw;
             const bool flagged = b.n_exc && ((__ldg(b.flags + (ri >> 5)) >> (ri & 31)) & 1u);
-            cls = dcr_general_prepare(r, ri, flagged, ex, s_inv + tid, vblob, jblob, sfilt, s_cand + tid, s_hits + tid);
+            ExcList exr = ex;                          // the read's entries lie inside its 32-read group's run of the list
+            if (flagged) { exr.lo = __ldg(b.exc_index + (ri >> 5)); exr.n = __ldg(b.exc_index + (ri >> 5) + 1); }
+            cls = dcr_general_prepare(r, ri, flagged, exr, s_inv + tid, vblob, jblob, sfilt, s_cand + tid, s_hits + tid);
             uint32_t* m = s_meta + tid;                    // what step 2 needs to rebuild the view of this column
             m[0] = ri; m[T] = (uint32_t)r.n; m[2 * T] = (uint32_t)r.e0; m[3 * T] = (uint32_t)r.e1;
             m[4 * T] = (uint32_t)r.n_hits | (r.hits ? 0x100u : 0u) | (r.inv ? 0x200u : 0u) | (r.cand ? 0x400u : 0u) |
@@ -935,6 +939,8 @@ dcb_general_kernel(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_r
     }
     flush_counters(L.cnt, counters);
 }
+
+#include "pack_device.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // context
@@ -983,6 +989,12 @@ struct dcb_ctx {
     int half_grid = 0, half_threads = 0;
     size_t half_smem = 0;
     DevBuf queue2;                 // reads the half-tag kernel passes on to the general kernel
+    // device-side packing (dcb_decombine_ascii / dcb_pack_device): text and per-read offsets / lengths of the chunk in
+    // flight on each of the two streams, exception counts per 32-read group, the running total of the exception list
+    DevBuf text[2], roff[2], rlen[2], group_count;
+    uint32_t* d_exc_total = nullptr;
+    cudaEvent_t ev_scan[2] = {nullptr, nullptr};
+    double pack_ms = 0;            // device time of the pack kernels of the last dcb_pack_device call (CUDA events)
     int vgen_words = 0, jgen_words = 0, vcore_words = 0, jcore_words = 0, vidx_words = 0, jidx_words = 0, uidx_words = 0;
     DevBuf words, lens, flags, exc_read, exc_pos, exc_kind, exc_index, results, queue;
     std::vector<uint32_t> h_exc_index;   // host copy of exc_index while its upload is in flight
@@ -1170,6 +1182,9 @@ dcb_ctx* dcb_ctx_create(int device, const dcb_tagset* v, const dcb_tagset* j, co
     // queue counters and reference counters in ONE block: a step clears both with one memset
     if (cudaMalloc((void**)&c->d_queue_count, kZeroBlockBytes) != cudaSuccess) return fail("cudaMalloc");
     c->d_counters = reinterpret_cast<unsigned long long*>(c->d_queue_count + 2 * kMaxChunks);
+    if (cudaMalloc((void**)&c->d_exc_total, 16) != cudaSuccess) return fail("cudaMalloc");
+    for (int i = 0; i < 2; i++)
+        if (cudaEventCreateWithFlags(&c->ev_scan[i], cudaEventDisableTiming) != cudaSuccess) return fail("cudaEventCreate");
     return c;
 }
 
@@ -1186,6 +1201,9 @@ void dcb_ctx_destroy(dcb_ctx* c) {
     cudaFree(c->d_queue_count);   // d_counters lives in the same block
     c->words.release(); c->lens.release(); c->flags.release(); c->exc_read.release(); c->exc_pos.release(); c->exc_index.release();
     c->exc_kind.release(); c->results.release(); c->queue.release(); c->queue2.release();
+    for (int i = 0; i < 2; i++) { c->text[i].release(); c->roff[i].release(); c->rlen[i].release(); if (c->ev_scan[i]) cudaEventDestroy(c->ev_scan[i]); }
+    c->group_count.release();
+    cudaFree(c->d_exc_total);
     delete c;
 }
 
@@ -1196,14 +1214,14 @@ int dcb_ctx_set_stream(dcb_ctx* c, void* cuda_stream) {
 }
 
 // Size the device buffers for batch P, point the BatchDev at them and pick the launch geometry.  No copies.
-static int prepare_batch(dcb_ctx* c, const dcb_packed* P) {
+static int prepare_batch(dcb_ctx* c, const dcb_packed* P, size_t exc_cap = 0) {
     if (P->n_reads >= 0xFFFFFFFFull) { dcb_set_error("batch too large"); return DCB_EINVAL; }
     const size_t n = P->n_reads, sw = P->slot_words;
     if (sw == 0 || sw % 4) { dcb_set_error("slot_words must be a positive multiple of 4"); return DCB_EINVAL; }
     int rc;
     if ((rc = c->words.ensure(n * sw * 4 + 16)) || (rc = c->lens.ensure(n * 2 + 16)) ||
-        (rc = c->flags.ensure(((n + 31) / 32) * 4 + 16)) || (rc = c->exc_read.ensure((size_t)P->n_exc * 4 + 16)) ||
-        (rc = c->exc_pos.ensure((size_t)P->n_exc * 2 + 16)) || (rc = c->exc_kind.ensure((size_t)P->n_exc + 16)) ||
+        (rc = c->flags.ensure(((n + 31) / 32) * 4 + 16)) || (rc = c->exc_read.ensure(std::max<size_t>(P->n_exc, exc_cap) * 4 + 16)) ||
+        (rc = c->exc_pos.ensure(std::max<size_t>(P->n_exc, exc_cap) * 2 + 16)) || (rc = c->exc_kind.ensure(std::max<size_t>(P->n_exc, exc_cap) + 16)) ||
         (rc = c->exc_index.ensure(((n + 31) / 32 + 2) * 4 + 16)) ||
         (rc = c->results.ensure(n * sizeof(dcb_result) + 16)) || (rc = c->queue.ensure(n * 4 + 16)) ||
         (rc = c->queue2.ensure(n * 4 + 16)))
@@ -1468,6 +1486,185 @@ int dcb_decombine_batch(dcb_ctx* c, const dcb_packed* P, dcb_result* out, uint64
     CUDA_TRY(cudaStreamWaitEvent(st[0], c->ev_done, 0));
     c->ran = true;
     return read_counters(c, st[0], counters);
+}
+
+// ---- ASCII in: pack on the device ----------------------------------------------------------------------------
+// Geometry of an ASCII batch: what dcb_pack_reads derives on the host (slot width from the longest read).
+static int ascii_geometry(const uint32_t* len, uint64_t n, uint32_t uniform_len, dcb_packed* G) {
+    std::memset(G, 0, sizeof(*G));
+    uint32_t max_len = uniform_len, min_len = uniform_len;
+    if (!uniform_len && n) {
+        if (!len) { dcb_set_error("read lengths missing"); return DCB_EINVAL; }
+        max_len = 0; min_len = 0xFFFFFFFFu;
+        for (uint64_t i = 0; i < n; i++) { max_len = std::max(max_len, len[i]); min_len = std::min(min_len, len[i]); }
+    }
+    if (max_len > DCB_MAX_READ_LEN) {
+        dcb_set_error("read of %u nt exceeds the supported maximum of %d", max_len, DCB_MAX_READ_LEN);
+        return DCB_EUNSUPPORTED;
+    }
+    G->n_reads = n; G->max_len = max_len;
+    G->slot_words = std::max<uint32_t>(4u, ((max_len + 63) / 64) * 4);
+    G->uniform_len = (n && min_len == max_len) ? max_len : 0;
+    G->n_exc = 1;                       // unknown until packed: the kernels take the path that honours the exception list
+    return DCB_OK;
+}
+
+// Pack reads [first, first + count) on stream s (buffers of parity `par`): text bytes and offsets / lengths up, the pack
+// kernel, the scan that continues the exception index from the chunks before (ordered across the two streams by
+// events), the exception entries.  The packed data lands in the context's batch buffers at the reads' global positions.
+static int pack_chunk(dcb_ctx* c, cudaStream_t s, int par, const char* ascii, const uint64_t* off, const uint32_t* len,
+                      uint32_t uniform_len, int revcomp, uint32_t first, uint32_t count, size_t exc_cap, int chunk_no) {
+    if (!count) return DCB_OK;
+    const uint32_t L = uniform_len;
+    const bool contiguous = off == nullptr;
+    const uint64_t lo = contiguous ? (uint64_t)first * L : off[first];
+    uint64_t hi = lo;
+    if (contiguous) hi = (uint64_t)(first + count) * L;
+    else for (uint32_t i = first; i < first + count; i++) hi = std::max<uint64_t>(hi, off[i] + (len ? len[i] : L));
+    if (!contiguous) for (uint32_t i = first; i < first + count; i++) if (off[i] < lo) { dcb_set_error("read offsets must not decrease inside a batch"); return DCB_EINVAL; }
+    int rc;
+    if ((rc = c->text[par].ensure(hi - lo + 64))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->text[par].p, ascii + lo, hi - lo, cudaMemcpyHostToDevice, s));
+    PackSrc src;
+    src.text = (const unsigned char*)c->text[par].p; src.text_lo = lo; src.stride = L; src.uniform_len = len ? 0u : L;
+    src.first = first; src.count = count; src.off = nullptr; src.len = nullptr;
+    if (!contiguous) {
+        if ((rc = c->roff[par].ensure((size_t)count * 8 + 16))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c->roff[par].p, off + first, (size_t)count * 8, cudaMemcpyHostToDevice, s));
+        src.off = (const uint64_t*)c->roff[par].p;
+    }
+    if (len) {
+        if ((rc = c->rlen[par].ensure((size_t)count * 4 + 16))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c->rlen[par].p, len + first, (size_t)count * 4, cudaMemcpyHostToDevice, s));
+        src.len = (const uint32_t*)c->rlen[par].p;
+    }
+    const uint32_t groups = (count + 31) / 32, blocks = (groups + 7) / 8;
+    const uint32_t sw = c->batch.slot_words;
+    dcb_pack_kernel<<<blocks, 256, 0, s>>>(src, revcomp, sw, (uint32_t*)c->words.p, (uint16_t*)c->lens.p, (uint32_t*)c->flags.p,
+                                           (uint32_t*)c->group_count.p);
+    CUDA_TRY(cudaGetLastError());
+    if (chunk_no > 0) CUDA_TRY(cudaStreamWaitEvent(s, c->ev_scan[(chunk_no - 1) & 1], 0));   // the list continues where the chunk before ends
+    dcb_pack_scan_kernel<<<1, 1024, 0, s>>>((const uint32_t*)c->group_count.p, first >> 5, groups, (uint32_t*)c->exc_index.p, c->d_exc_total);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(c->ev_scan[chunk_no & 1], s));
+    dcb_pack_exc_kernel<<<blocks, 256, 0, s>>>(src, revcomp, sw, (const uint32_t*)c->flags.p, (const uint32_t*)c->exc_index.p, (uint32_t)exc_cap,
+                                               (uint32_t*)c->exc_read.p, (uint16_t*)c->exc_pos.p, (uint8_t*)c->exc_kind.p);
+    CUDA_TRY(cudaGetLastError());
+    return DCB_OK;
+}
+
+static size_t exc_capacity(uint64_t n) { return (size_t)std::min<uint64_t>(0xFFFFFFF0ull, 2 * n + (1u << 20)); }
+
+static int ascii_begin(dcb_ctx* c, const char* ascii, const uint64_t* off, const uint32_t* len, uint64_t n, uint32_t uniform_len,
+                       size_t* exc_cap) {
+    if (!c || (n && !ascii)) { dcb_set_error("null argument"); return DCB_EINVAL; }
+    if (!off && !uniform_len && n) { dcb_set_error("contiguous reads (off == NULL) need uniform_len"); return DCB_EINVAL; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    dcb_packed G;
+    int rc;
+    if ((rc = ascii_geometry(uniform_len ? nullptr : len, n, uniform_len, &G))) return rc;
+    *exc_cap = exc_capacity(n);
+    if ((rc = prepare_batch(c, &G, *exc_cap))) return rc;
+    if ((rc = c->group_count.ensure(((n + 31) / 32 + 2) * 4))) return rc;
+    CUDA_TRY(cudaMemsetAsync(c->d_exc_total, 0, 16, c->stream));
+    return DCB_OK;
+}
+
+// The exception list of a device-packed batch is complete: its length, against the capacity it was given.
+static int ascii_finish(dcb_ctx* c, size_t exc_cap, uint32_t* n_exc) {
+    uint32_t total = 0;
+    CUDA_TRY(cudaMemcpy(&total, c->d_exc_total, 4, cudaMemcpyDeviceToHost));
+    if (total > exc_cap) {
+        dcb_set_error("device packing: %u non-ACGT symbols exceed the list capacity %zu (pack on the host with dcb_pack_reads)", total, exc_cap);
+        return DCB_EUNSUPPORTED;
+    }
+    c->batch.n_exc = total;
+    if (n_exc) *n_exc = total;
+    return DCB_OK;
+}
+
+int dcb_decombine_ascii(dcb_ctx* c, const char* ascii, const uint64_t* off, const uint32_t* len, uint64_t n, uint32_t uniform_len,
+                        int revcomp, dcb_result* out, uint64_t* counters) {
+    size_t exc_cap = 0;
+    int rc;
+    if ((rc = ascii_begin(c, ascii, off, len, n, uniform_len, &exc_cap))) return rc;
+    const uint32_t* lens = uniform_len ? nullptr : len;
+    cudaStream_t st[2] = {c->stream, c->stream2};
+    CUDA_TRY(cudaMemsetAsync(c->d_queue_count, 0, kZeroBlockBytes, st[0]));
+    CUDA_TRY(cudaEventRecord(c->ev_ready, st[0]));
+    CUDA_TRY(cudaStreamWaitEvent(st[1], c->ev_ready, 0));
+    uint32_t chunk = std::max<uint32_t>(kChunkReads, (uint32_t)((n + kMaxChunks - 1) / kMaxChunks));
+    chunk = (chunk + 1023u) & ~1023u;
+    int k = 0;
+    for (uint64_t first = 0; first < n; first += chunk, k++) {
+        const uint32_t count = (uint32_t)std::min<uint64_t>(chunk, n - first);
+        cudaStream_t s = st[k & 1];
+        if ((rc = pack_chunk(c, s, k & 1, ascii, off, lens, uniform_len, revcomp, (uint32_t)first, count, exc_cap, k))) return rc;
+        if ((rc = launch_range(c, s, (uint32_t)first, count, k, false))) return rc;
+        if (out)
+            CUDA_TRY(cudaMemcpyAsync(out + first, (dcb_result*)c->results.p + first, (size_t)count * sizeof(dcb_result),
+                                     cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(cudaEventRecord(c->ev_done, st[1]));
+    CUDA_TRY(cudaStreamWaitEvent(st[0], c->ev_done, 0));
+    c->ran = true;
+    if ((rc = read_counters(c, st[0], counters))) return rc;
+    return ascii_finish(c, exc_cap, nullptr);
+}
+
+// The device packer alone, its output copied back into a host dcb_packed (tests: bit-identical to dcb_pack_reads;
+// tools: the pack kernels' device time through dcb_pack_device_ms).
+int dcb_pack_device(dcb_ctx* c, const char* ascii, const uint64_t* off, const uint32_t* len, uint64_t n, uint32_t uniform_len,
+                    int revcomp, dcb_packed** out) {
+    if (!out) { dcb_set_error("dcb_pack_device: null argument"); return DCB_EINVAL; }
+    size_t exc_cap = 0;
+    int rc;
+    if ((rc = ascii_begin(c, ascii, off, len, n, uniform_len, &exc_cap))) return rc;
+    const uint32_t* lens = uniform_len ? nullptr : len;
+    cudaStream_t st[2] = {c->stream, c->stream2};
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaEventRecord(c->ev_ready, st[0]));
+    CUDA_TRY(cudaStreamWaitEvent(st[1], c->ev_ready, 0));
+    const uint32_t chunk = kChunkReads;
+    int k = 0;
+    CUDA_TRY(cudaEventRecord(e0, st[0]));
+    for (uint64_t first = 0; first < n; first += chunk, k++)
+        if ((rc = pack_chunk(c, st[k & 1], k & 1, ascii, off, lens, uniform_len, revcomp, (uint32_t)first,
+                             (uint32_t)std::min<uint64_t>(chunk, n - first), exc_cap, k))) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev_done, st[1]));
+    CUDA_TRY(cudaStreamWaitEvent(st[0], c->ev_done, 0));
+    CUDA_TRY(cudaEventRecord(e1, st[0]));
+    CUDA_TRY(cudaStreamSynchronize(st[0]));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    c->pack_ms = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    uint32_t n_exc = 0;
+    if ((rc = ascii_finish(c, exc_cap, &n_exc))) return rc;
+    // a host dcb_packed of the same shape (no reads packed on the host: n = 0 buffers would be too small, so pack a
+    // batch of empty reads of the right count is not possible either) -- allocate through the host packer's owner
+    dcb_packed* P = nullptr;
+    if ((rc = dcb_packed_alloc(n, c->batch.slot_words, n_exc, &P))) return rc;
+    P->uniform_len = c->batch.uniform_len; P->max_len = 0;
+    if (n) {
+        CUDA_TRY(cudaMemcpy(P->words, c->words.p, (size_t)n * c->batch.slot_words * 4, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(P->lens, c->lens.p, (size_t)n * 2, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(P->flags, c->flags.p, ((size_t)n + 31) / 32 * 4, cudaMemcpyDeviceToHost));
+        for (uint64_t i = 0; i < n; i++) P->max_len = std::max<uint32_t>(P->max_len, P->lens[i]);
+    }
+    if (n_exc) {
+        CUDA_TRY(cudaMemcpy(P->exc_read, c->exc_read.p, (size_t)n_exc * 4, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(P->exc_pos, c->exc_pos.p, (size_t)n_exc * 2, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(P->exc_kind, c->exc_kind.p, (size_t)n_exc, cudaMemcpyDeviceToHost));
+    }
+    *out = P;
+    return DCB_OK;
+}
+int dcb_pack_device_ms(dcb_ctx* c, double* ms) {
+    if (!c || !ms) return DCB_EINVAL;
+    *ms = c->pack_ms;
+    return DCB_OK;
 }
 
 void* dcb_pinned_alloc(size_t bytes) {

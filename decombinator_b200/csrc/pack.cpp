@@ -160,6 +160,31 @@ int dcb_pack_reads(const char* ascii, const uint64_t* off, const uint32_t* len, 
     return DCB_OK;
 }
 
+// An empty dcb_packed of the given shape (the device packer's output is copied into it); free with dcb_packed_free.
+int dcb_packed_alloc(uint64_t n, uint32_t slot_words, uint32_t n_exc, dcb_packed** out) {
+    Owner* o = new Owner();
+    int dev_count = 0;
+    o->pinned = cudaGetDeviceCount(&dev_count) == cudaSuccess && dev_count > 0;
+    if (!o->pinned) (void)cudaGetLastError();
+    dcb_packed* P = new dcb_packed();
+    std::memset(P, 0, sizeof(*P));
+    P->owner = o;
+    P->n_reads = n; P->slot_words = slot_words; P->n_exc = n_exc;
+    P->words = (uint32_t*)host_alloc(o, n * slot_words * 4);
+    P->lens = (uint16_t*)host_alloc(o, n * 2);
+    P->flags = (uint32_t*)host_alloc(o, ((n + 31) / 32) * 4);
+    P->exc_read = (uint32_t*)host_alloc(o, ((size_t)n_exc + 1) * 4);
+    P->exc_pos = (uint16_t*)host_alloc(o, ((size_t)n_exc + 1) * 2);
+    P->exc_kind = (uint8_t*)host_alloc(o, (size_t)n_exc + 1);
+    if (!P->words || !P->lens || !P->flags || !P->exc_read || !P->exc_pos || !P->exc_kind) {
+        dcb_packed_free(P);
+        dcb_set_error("dcb_packed_alloc: out of memory");
+        return DCB_ENOMEM;
+    }
+    *out = P;
+    return DCB_OK;
+}
+
 void dcb_packed_free(dcb_packed* P) {
     if (!P) return;
     Owner* o = (Owner*)P->owner;

@@ -209,6 +209,20 @@ int dcb_ctx_set_stream(dcb_ctx*, void* cuda_stream);
  * counters[DCB_NCOUNTERS].  Synchronous on return. */
 int dcb_decombine_batch(dcb_ctx*, const dcb_packed* reads, dcb_result* out, uint64_t* counters);
 
+/* The same from ASCII: replaces the string handling in front of dcr() -- `vdj = record1[1]` (decombine.py:965-977) and,
+ * when revcomp != 0, revcomp(vdj) (decombine.py:182-184, 1000) -- AND the hot loop, in one call.  The text is streamed
+ * to HBM in chunks and packed there (csrc/pack_device.cuh: bit-identical to dcb_pack_reads); no packed copy is made on
+ * the host.  Read i is ascii[off[i] .. off[i] + len[i]); offsets must not decrease inside the batch (FASTQ order).
+ * off == NULL: the reads are contiguous, read i at i * uniform_len.  uniform_len != 0: every read has that length and
+ * len is ignored.  With page-locked text (dcb_pinned_alloc) the step is bound by the host->device copy of the text. */
+int dcb_decombine_ascii(dcb_ctx*, const char* ascii, const uint64_t* off, const uint32_t* len, uint64_t n, uint32_t uniform_len,
+                        int revcomp, dcb_result* out, uint64_t* counters);
+/* The device packer alone: its output copied back into a host dcb_packed (free with dcb_packed_free); tests compare it
+ * with dcb_pack_reads.  dcb_pack_device_ms: device time (CUDA events) of the last call, copies of the text included. */
+int dcb_pack_device(dcb_ctx*, const char* ascii, const uint64_t* off, const uint32_t* len, uint64_t n, uint32_t uniform_len,
+                    int revcomp, dcb_packed** out);
+int dcb_pack_device_ms(dcb_ctx*, double* ms);
+
 /* Page-locked host memory for result records (so that the device->host copies of dcb_decombine_batch run
  * asynchronously, overlapped with the uploads); NULL when no GPU is usable. */
 void* dcb_pinned_alloc(size_t bytes);

@@ -1,0 +1,120 @@
+"""Device-side packing (csrc/pack_device.cuh) against the host packer dcb_pack_reads: bit-identical slot words, lengths,
+flag words and exception list (decombine.py:182-184 revcomp through Bio.Seq's table, :965-977 slicing), and
+dcb_decombine_ascii against dcb_decombine_batch on the host-packed batch.  GPU, through the C ABI."""
+import numpy as np
+import pytest
+
+from decombinator_b200 import _lib, tags
+from helpers import synth_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(info=None, **kw):
+    info = info or tags.load("human", "extended", "b")
+    vt, jt = info.tables()
+    return _lib.Context(vt, jt, device=0, **kw)
+
+
+def _same(a: "_lib.Packed", b: "_lib.Packed", what):
+    assert (a.n_reads, a.slot_words, a.n_exc, a.uniform_len, a.max_len) == (b.n_reads, b.slot_words, b.n_exc, b.uniform_len, b.max_len), what
+    xa, xb = a.arrays(), b.arrays()
+    for k in xa:
+        assert np.array_equal(xa[k], xb[k]), "%s: %s differs at %s" % (what, k, np.nonzero(xa[k] != xb[k])[0][:8])
+
+
+def _concat(reads):
+    bufs = [r.encode("latin-1") for r in reads]
+    length = np.array([len(b) for b in bufs], dtype=np.uint32)
+    off = np.zeros(len(bufs), dtype=np.uint64)
+    if len(bufs) > 1:
+        off[1:] = np.cumsum(length[:-1], dtype=np.uint64)
+    return np.frombuffer(b"".join(bufs) + b"\0" * 8, dtype=np.uint8).copy(), off, length
+
+
+SYMBOLS = "ACGTNacgtnUuRYKMSWBDHVrykm-.*X"
+
+
+def _fuzzed_reads(n, seed, max_len=330):
+    """Ragged reads over ACGT with sprinkled N / IUPAC / lower-case / U / junk symbols, empty and one-base reads included."""
+    rng = np.random.default_rng(seed)
+    reads = []
+    for i in range(n):
+        L = int(rng.integers(0, max_len + 1)) if i % 7 else int(rng.choice([0, 1, 7, 8, 9, 15, 16, 17, 63, 64, 65, 255, 256, 257, max_len]))
+        s = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, L)].copy()
+        if i % 3 == 0 and L:
+            k = int(rng.integers(1, 6))
+            pos = rng.integers(0, L, k)
+            s[pos] = np.frombuffer(SYMBOLS.encode(), dtype=np.uint8)[rng.integers(0, len(SYMBOLS), k)]
+        if i % 41 == 0:
+            s[:] = ord("N")
+        reads.append(s.tobytes().decode("latin-1"))
+    return reads
+
+
+@pytest.mark.parametrize("revcomp", [True, False])
+def test_device_pack_equals_host_pack_ragged(revcomp):
+    ctx = _ctx()
+    for n, seed, max_len in ((1, 1, 40), (31, 2, 100), (33, 3, 330), (5000, 4, 330), (3000, 5, 1000), (70, 6, 4000)):
+        reads = _fuzzed_reads(n, seed, max_len)
+        buf, off, length = _concat(reads)
+        host = _lib.pack_arrays(buf, off, length, revcomp)
+        dev = ctx.pack_device(buf, off, length, revcomp)
+        _same(dev, host, "ragged n=%d revcomp=%s" % (n, revcomp))
+        for i in (0, n // 2, n - 1):
+            assert dev.unpack(i) == host.unpack(i)
+        host.free(); dev.free()
+    ctx.close()
+
+
+def test_device_pack_equals_host_pack_uniform_chunks():
+    """3.3 M uniform reads (four chunks on two streams: the exception list continues across chunks), contiguous layout."""
+    info = tags.load("human", "extended", "b")
+    n, L = 3_300_000, 250
+    r1, off, ln = synth_batch(info, n, L, 0.01, 0.002, 0.02, seed=9)
+    r1[np.arange(0, n * L, 997)] = ord("n")          # lower case: kind 2
+    r1[np.arange(5, n * L, 4999)] = ord("U")         # kind 3 on the reverse strand
+    ctx = _ctx(info)
+    for revcomp in (True, False):
+        host = _lib.pack_arrays(r1, off, ln, revcomp)
+        dev = ctx.pack_device(r1, None, None, revcomp, uniform_len=L)
+        _same(dev, host, "uniform contiguous revcomp=%s" % revcomp)
+        dev2 = ctx.pack_device(r1, off, ln, revcomp)
+        _same(dev2, host, "uniform with offsets revcomp=%s" % revcomp)
+        host.free(); dev.free(); dev2.free()
+    ctx.close()
+
+
+@pytest.mark.parametrize("chain,both", [("b", False), ("a", False), ("b", True)])
+def test_decombine_ascii_equals_decombine_batch(chain, both):
+    info = tags.load("human", "extended", chain)
+    n, L = 2_200_000, 250
+    r1, off, ln = synth_batch(info, n, L, 0.01, 0.001, 0.05, seed=20260003)
+    ctx = _ctx(info, both_frames=both)
+    packed = _lib.pack_arrays(r1, off, ln, True)
+    want, wcnt = ctx.decombine(packed)
+    got, cnt = ctx.decombine_ascii(r1, None, None, True, uniform_len=L)
+    assert np.array_equal(got, want) and np.array_equal(cnt, wcnt)
+    got2, cnt2 = ctx.decombine_ascii(r1, off, ln, True)
+    assert np.array_equal(got2, want) and np.array_equal(cnt2, wcnt)
+    packed.free(); ctx.close()
+
+
+def test_decombine_ascii_ragged_and_empty():
+    info = tags.load("human", "extended", "b")
+    r1, off, ln = synth_batch(info, 4000, 250, 0.01, 0.001, 0.05, seed=5)
+    reads = [bytes(r1[i * 250:(i + 1) * 250]).decode() for i in range(4000)]
+    rng = np.random.default_rng(1)
+    ragged = [r[sorted(rng.integers(0, 251, size=2))[0]:] if i % 3 else r for i, r in enumerate(reads)] + ["", "A", "N" * 250, "acgt" * 30]
+    buf, off, length = _concat(ragged)
+    for kw in ({}, {"both_frames": True}, {"allow_ns": True}):
+        ctx = _ctx(info, **kw)
+        packed = _lib.pack_arrays(buf, off, length, True)
+        want, wcnt = ctx.decombine(packed)
+        got, cnt = ctx.decombine_ascii(buf, off, length, True)
+        assert np.array_equal(got, want) and np.array_equal(cnt, wcnt), kw
+        packed.free(); ctx.close()
+    ctx = _ctx(info)
+    got, cnt = ctx.decombine_ascii(np.zeros(8, dtype=np.uint8), np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=np.uint32), True)
+    assert len(got) == 0 and not cnt.any()
+    ctx.close()
