@@ -351,6 +351,31 @@ def count_ranges_with(buf, off, length, symbol, n_threads=None):
     return int(lib().dcb_count_ranges_with(buf.ctypes.data, off.ctypes.data, length.ctypes.data, len(off), ord(symbol), nt))
 
 
+class PinnedBytes:
+    """A page-locked uint8 buffer (dcb_pinned_alloc) as a numpy array `.a`; host->device copies from it run at link speed."""
+
+    def __init__(self, src):
+        src = np.ascontiguousarray(src, dtype=np.uint8).reshape(-1)
+        self._n = len(src)
+        self._p = lib().dcb_pinned_alloc(self._n + 64)
+        if not self._p:
+            raise DcbError("dcb_pinned_alloc: " + lib().dcb_last_error().decode())
+        self.a = np.frombuffer((ctypes.c_uint8 * (self._n + 64)).from_address(self._p), dtype=np.uint8, count=self._n)
+        self.a[:] = src
+
+    def free(self):
+        if self._p:
+            self.a = None
+            lib().dcb_pinned_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 def pack_arrays(buf, off, length, revcomp, n_threads=None) -> Packed:
     """dcb_pack_reads over reads stored in one uint8 buffer (off: uint64 offsets, length: uint32)."""
     buf = np.ascontiguousarray(buf, dtype=np.uint8)

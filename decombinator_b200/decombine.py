@@ -125,9 +125,17 @@ def decombine_batch(batch: fastq.ReadBatch, inputargs):
     """GPU pass over every V(D)J read of the batch -> dcb_result array (one record per read)."""
     pack_rc, both = _orientation_plan(inputargs["orientation"])
     ctx = _context(inputargs, both)
-    packed = _lib.pack_arrays(batch.buf, batch.off, batch.len, revcomp=pack_rc)
-    res, dev_counts = ctx.decombine(packed)
-    packed.free()
+    off = np.ascontiguousarray(batch.off, dtype=np.uint64)
+    try:
+        if len(off) > 1 and bool(np.any(off[1:] < off[:-1])):
+            raise _lib.DcbError("reads are not in text order")
+        # the text goes to the GPU as it is and is 2-bit packed there (dcb_decombine_ascii): no packed copy on the host
+        res, dev_counts = ctx.decombine_ascii(batch.buf, off, batch.len, pack_rc)
+    except _lib.DcbError:
+        # reads out of text order, or more non-ACGT symbols than the device-side list holds: pack on the host threads
+        packed = _lib.pack_arrays(batch.buf, off, batch.len, revcomp=pack_rc)
+        res, dev_counts = ctx.decombine(packed)
+        packed.free()
     _add_device_counters(dev_counts)
     return res
 
@@ -188,8 +196,15 @@ def decombinator(inputargs: dict) -> list:
     print("Decombining FASTQ data...")
 
     outdata = []
+    _t = [time()]
+
+    def _lap(what):   # DCB_TIMING=1: where the wall time of the stage goes
+        if os.environ.get("DCB_TIMING"):
+            _t.append(time())
+            print("\t[timing] %-28s %.3f s" % (what, _t[-1] - _t[-2]))
     if inputargs["nobarcoding"] == False:  # noqa: E712
         batch = fastq.load_pairs(inputargs, opener)
+        _lap("FASTQ text -> record index")
         if inputargs.get("shard"):   # multi-GPU run (parallel.py): this rank analyses one contiguous shard of the reads
             from .parallel import shard_bounds
             batch = batch.shard(*shard_bounds(len(batch), *inputargs["shard"]))
@@ -202,7 +217,9 @@ def decombinator(inputargs: dict) -> list:
         if inputargs["dontcount"] == False:  # noqa: E712
             for k in range(100000, n + 1, 100000):
                 print("\t read", k)
+        _lap("barcode N count")
         res = decombine_batch(batch, inputargs) if n else np.zeros(0, dtype=_lib.RESULT_DTYPE)
+        _lap("text -> GPU -> records")
         pack_rc, _ = _orientation_plan(inputargs["orientation"])
         hits = np.nonzero(res["status"])[0]
         counts["vj_count"] += int(len(hits))
@@ -243,6 +260,7 @@ def decombinator(inputargs: dict) -> list:
             print("Non-barcoding option selected, but default output file extension (n12) detected. "
                   "Automatically changing to 'nbc'.")
 
+        _lap("row assembly")
     counts["end_time"] = time()
     timetaken = counts["end_time"] - counts["start_time"]
 
