@@ -300,10 +300,36 @@ def format_rows(res, packed_revcomp, columns, sep, n_threads=None):
     nt = n_threads or min(32, os.cpu_count() or 1)
     _check(lib().dcb_format_rows(res.ctypes.data, len(res), int(bool(packed_revcomp)), *cols, sep.encode("ascii"), nt,
                                  ctypes.byref(out), ctypes.byref(nbytes), ctypes.byref(nrows)), "dcb_format_rows")
-    try:
-        return ctypes.string_at(out.value, nbytes.value), int(nrows.value)
-    finally:
-        lib().dcb_buffer_free(out)
+    return NativeText(out.value, nbytes.value), int(nrows.value)
+
+
+class NativeText:
+    """A text buffer malloc'ed by the library (dcb_format_rows), handed on WITHOUT a copy: `.a` is a uint8 array over it,
+    bytes(obj) / obj.tobytes() copy, the buffer is freed with the object."""
+
+    def __init__(self, ptr, nbytes):
+        self._p, self._n = ptr, int(nbytes)
+        self.a = np.frombuffer((ctypes.c_uint8 * max(1, self._n)).from_address(ptr), dtype=np.uint8, count=self._n)
+
+    def __len__(self):
+        return self._n
+
+    def tobytes(self):
+        return self.a.tobytes()
+
+    __bytes__ = tobytes
+
+    def decode(self, *a):
+        return self.tobytes().decode(*a)
+
+    def __del__(self):
+        try:
+            if self._p:
+                self.a = None
+                lib().dcb_buffer_free(self._p)
+                self._p = None
+        except Exception:
+            pass
 
 
 class CFastqIndex(ctypes.Structure):
@@ -330,14 +356,34 @@ def fastq_index(data, n_threads=None):
             return None
         n = int(ix.n_records)
         res = {}
+        owner = _FastqIndexOwner(out)      # the arrays are views of the index's own memory: it lives as long as any of them
+        out = None
         for name, ctype, dt in (("name_off", ctypes.c_uint64, np.uint64), ("name_len", ctypes.c_uint32, np.uint32),
                                 ("seq_off", ctypes.c_uint64, np.uint64), ("seq_len", ctypes.c_uint32, np.uint32),
                                 ("qual_off", ctypes.c_uint64, np.uint64), ("qual_len", ctypes.c_uint32, np.uint32)):
-            res[name] = np.ctypeslib.as_array(getattr(ix, name), shape=(n,)).astype(dt, copy=True) if n else np.zeros(0, dt)
+            if not n:
+                res[name] = np.zeros(0, dt)
+                continue
+            carr = (ctype * n).from_address(ctypes.addressof(getattr(ix, name).contents))
+            carr._owner = owner
+            res[name] = np.frombuffer(carr, dtype=dt, count=n)
         return res
     finally:
         if out:
             lib().dcb_fastq_index_free(out)
+
+
+class _FastqIndexOwner:
+    def __init__(self, ptr):
+        self._p = ptr
+
+    def __del__(self):
+        try:
+            if self._p:
+                lib().dcb_fastq_index_free(self._p)
+                self._p = None
+        except Exception:
+            pass
 
 
 def count_ranges_with(buf, off, length, symbol, n_threads=None):

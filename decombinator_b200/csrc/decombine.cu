@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 // ------------------------------------------------------------------------------------------------
@@ -994,6 +995,11 @@ struct dcb_ctx {
     DevBuf text[2], roff[2], rlen[2], group_count;
     uint32_t* d_exc_total = nullptr;
     cudaEvent_t ev_scan[2] = {nullptr, nullptr};
+    // page-locked staging for text that arrives in pageable memory (a memory-mapped FASTQ file): host threads copy the
+    // chunk in, the copy engine takes it from there at link speed while the threads fill the other buffer
+    char* stage[2] = {nullptr, nullptr};
+    size_t stage_cap[2] = {0, 0};
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
     double pack_ms = 0;            // device time of the pack kernels of the last dcb_pack_device call (CUDA events)
     int vgen_words = 0, jgen_words = 0, vcore_words = 0, jcore_words = 0, vidx_words = 0, jidx_words = 0, uidx_words = 0;
     DevBuf words, lens, flags, exc_read, exc_pos, exc_kind, exc_index, results, queue;
@@ -1184,7 +1190,8 @@ dcb_ctx* dcb_ctx_create(int device, const dcb_tagset* v, const dcb_tagset* j, co
     c->d_counters = reinterpret_cast<unsigned long long*>(c->d_queue_count + 2 * kMaxChunks);
     if (cudaMalloc((void**)&c->d_exc_total, 16) != cudaSuccess) return fail("cudaMalloc");
     for (int i = 0; i < 2; i++)
-        if (cudaEventCreateWithFlags(&c->ev_scan[i], cudaEventDisableTiming) != cudaSuccess) return fail("cudaEventCreate");
+        if (cudaEventCreateWithFlags(&c->ev_scan[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_stage[i], cudaEventDisableTiming) != cudaSuccess) return fail("cudaEventCreate");
     return c;
 }
 
@@ -1201,7 +1208,12 @@ void dcb_ctx_destroy(dcb_ctx* c) {
     cudaFree(c->d_queue_count);   // d_counters lives in the same block
     c->words.release(); c->lens.release(); c->flags.release(); c->exc_read.release(); c->exc_pos.release(); c->exc_index.release();
     c->exc_kind.release(); c->results.release(); c->queue.release(); c->queue2.release();
-    for (int i = 0; i < 2; i++) { c->text[i].release(); c->roff[i].release(); c->rlen[i].release(); if (c->ev_scan[i]) cudaEventDestroy(c->ev_scan[i]); }
+    for (int i = 0; i < 2; i++) {
+        c->text[i].release(); c->roff[i].release(); c->rlen[i].release();
+        if (c->ev_scan[i]) cudaEventDestroy(c->ev_scan[i]);
+        if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]);
+        if (c->stage[i]) cudaFreeHost(c->stage[i]);
+    }
     c->group_count.release();
     cudaFree(c->d_exc_total);
     delete c;
@@ -1512,8 +1524,19 @@ static int ascii_geometry(const uint32_t* len, uint64_t n, uint32_t uniform_len,
 // Pack reads [first, first + count) on stream s (buffers of parity `par`): text bytes and offsets / lengths up, the pack
 // kernel, the scan that continues the exception index from the chunks before (ordered across the two streams by
 // events), the exception entries.  The packed data lands in the context's batch buffers at the reads' global positions.
+static void parallel_copy(char* dst, const char* src, size_t bytes, int n_threads) {
+    if (bytes < (1u << 22) || n_threads <= 1) { std::memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; t++) {
+        const size_t a = bytes * t / n_threads, b = bytes * (t + 1) / n_threads;
+        th.emplace_back([=] { std::memcpy(dst + a, src + a, b - a); });
+    }
+    for (auto& x : th) x.join();
+}
+
 static int pack_chunk(dcb_ctx* c, cudaStream_t s, int par, const char* ascii, const uint64_t* off, const uint32_t* len,
-                      uint32_t uniform_len, int revcomp, uint32_t first, uint32_t count, size_t exc_cap, int chunk_no) {
+                      uint32_t uniform_len, int revcomp, uint32_t first, uint32_t count, size_t exc_cap, int chunk_no,
+                      bool staged = false) {
     if (!count) return DCB_OK;
     const uint32_t L = uniform_len;
     const bool contiguous = off == nullptr;
@@ -1524,7 +1547,22 @@ static int pack_chunk(dcb_ctx* c, cudaStream_t s, int par, const char* ascii, co
     if (!contiguous) for (uint32_t i = first; i < first + count; i++) if (off[i] < lo) { dcb_set_error("read offsets must not decrease inside a batch"); return DCB_EINVAL; }
     int rc;
     if ((rc = c->text[par].ensure(hi - lo + 64))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(c->text[par].p, ascii + lo, hi - lo, cudaMemcpyHostToDevice, s));
+    const char* from = ascii + lo;
+    if (staged) {
+        CUDA_TRY(cudaEventSynchronize(c->ev_stage[par]));                      // the copy engine is done with this buffer
+        if (c->stage_cap[par] < hi - lo) {
+            if (c->stage[par]) cudaFreeHost(c->stage[par]);
+            c->stage[par] = nullptr; c->stage_cap[par] = 0;
+            const size_t want = (hi - lo) + (hi - lo) / 8 + 4096;
+            CUDA_TRY(cudaHostAlloc((void**)&c->stage[par], want, cudaHostAllocDefault));
+            c->stage_cap[par] = want;
+        }
+        const unsigned hw = std::thread::hardware_concurrency();
+        parallel_copy(c->stage[par], from, hi - lo, (int)std::min<unsigned>(16u, hw ? hw : 4u));
+        from = c->stage[par];
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->text[par].p, from, hi - lo, cudaMemcpyHostToDevice, s));
+    if (staged) CUDA_TRY(cudaEventRecord(c->ev_stage[par], s));
     PackSrc src;
     src.text = (const unsigned char*)c->text[par].p; src.text_lo = lo; src.stride = L; src.uniform_len = len ? 0u : L;
     src.first = first; src.count = count; src.off = nullptr; src.len = nullptr;
@@ -1593,13 +1631,20 @@ int dcb_decombine_ascii(dcb_ctx* c, const char* ascii, const uint64_t* off, cons
     CUDA_TRY(cudaMemsetAsync(c->d_queue_count, 0, kZeroBlockBytes, st[0]));
     CUDA_TRY(cudaEventRecord(c->ev_ready, st[0]));
     CUDA_TRY(cudaStreamWaitEvent(st[1], c->ev_ready, 0));
-    uint32_t chunk = std::max<uint32_t>(kChunkReads, (uint32_t)((n + kMaxChunks - 1) / kMaxChunks));
+    // text in pageable memory (a memory-mapped file): smaller chunks through page-locked staging buffers
+    bool staged = false;
+    if (n) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, ascii) != cudaSuccess) { (void)cudaGetLastError(); staged = true; }
+        else staged = attr.type == cudaMemoryTypeUnregistered;
+    }
+    uint32_t chunk = std::max<uint32_t>(staged ? kChunkReads / 4 : kChunkReads, (uint32_t)((n + kMaxChunks - 1) / kMaxChunks));
     chunk = (chunk + 1023u) & ~1023u;
     int k = 0;
     for (uint64_t first = 0; first < n; first += chunk, k++) {
         const uint32_t count = (uint32_t)std::min<uint64_t>(chunk, n - first);
         cudaStream_t s = st[k & 1];
-        if ((rc = pack_chunk(c, s, k & 1, ascii, off, lens, uniform_len, revcomp, (uint32_t)first, count, exc_cap, k))) return rc;
+        if ((rc = pack_chunk(c, s, k & 1, ascii, off, lens, uniform_len, revcomp, (uint32_t)first, count, exc_cap, k, staged))) return rc;
         if ((rc = launch_range(c, s, (uint32_t)first, count, k, false))) return rc;
         if (out)
             CUDA_TRY(cudaMemcpyAsync(out + first, (dcb_result*)c->results.p + first, (size_t)count * sizeof(dcb_result),

@@ -118,7 +118,7 @@ class RowsText:
         return self.n_rows
 
     def rows(self):
-        return [line.split(", ") for line in self.text.decode("ascii").split("\n")[:-1]]
+        return [line.split(", ") for line in bytes(self.text).decode("ascii").split("\n")[:-1]]
 
 
 def decombine_batch(batch: fastq.ReadBatch, inputargs):
@@ -237,7 +237,7 @@ def decombinator(inputargs: dict) -> list:
                 hits = ()
             elif not any(c.buf.find(sep.encode()) != -1 for c in {id(c.buf): c for c in cols if c is not None}.values()):
                 blob, nrows = _lib.format_rows(res, pack_rc, cols, sep)
-                outdata = [line.split(sep) for line in blob.decode("ascii").split("\n")[:-1]]
+                outdata = [line.split(sep) for line in blob.tobytes().decode("ascii").split("\n")[:-1]]
                 assert len(outdata) == nrows == len(hits)
                 hits = ()
         for i in hits:
@@ -260,7 +260,7 @@ def decombinator(inputargs: dict) -> list:
             print("Non-barcoding option selected, but default output file extension (n12) detected. "
                   "Automatically changing to 'nbc'.")
 
-        _lap("row assembly")
+    _lap("row assembly")
     counts["end_time"] = time()
     timetaken = counts["end_time"] - counts["start_time"]
 

@@ -132,7 +132,7 @@ def write_out_intermediate(data: list, inputargs: dict, suffix: str):
     outfilename = intermediate_filename(inputargs, suffix)
     if hasattr(data, "text"):     # decombine.RowsText: the rows already formatted natively (dcb_format_rows)
         with open(outfilename, "wb") as outfile:
-            outfile.write(data.text)
+            outfile.write(memoryview(data.text.a) if hasattr(data.text, "a") else data.text)
     else:
         with open(outfilename, "w") as outfile:
             outfile.writelines(", ".join(map(str, line)) + "\n" for line in data)

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--reads", type=int, default=2_000_000)
     ap.add_argument("--python-fastq", action="store_true", help="use the general (Python) parser instead of the native index")
     ap.add_argument("--rows-as-text", action="store_true", help="what the `decombine` command does: rows handed over as .n12 text")
+    ap.add_argument("--profile", action="store_true", help="cProfile of the timed decombinator() call")
     ap.add_argument("--pipeline", action="store_true", help="decombine + collapse (pipeline.run) on reads with repeated UMIs")
     args = ap.parse_args()
     from decombinator_b200 import _lib, decombine, fastq, io, tags
@@ -68,9 +69,16 @@ def main():
     t_ingest = time.perf_counter() - t0
     decombine.decombinator(dict(ia))          # first run: CUDA context, tables, page-locked buffers
     os.environ["DCB_TIMING"] = "1"
+    if args.profile:
+        import cProfile, pstats
+        pr = cProfile.Profile()
+        pr.enable()
     t0 = time.perf_counter()
     rows = decombine.decombinator(ia)
     t_total = time.perf_counter() - t0
+    if args.profile:
+        pr.disable()
+        pstats.Stats(pr).sort_stats("cumulative").print_stats(22)
     print(json.dumps({"reads": n, "parser": "python" if args.python_fastq else "native", "rows_as_text": bool(args.rows_as_text), "fastq_write_s": round(t_write, 2),
                       "ingest_only_s": round(t_ingest, 3), "decombinator_s": round(t_total, 2), "rows": len(rows),
                       "reads_per_s": round(n / t_total), "ingest_reads_per_s": round(n / t_ingest)}))
