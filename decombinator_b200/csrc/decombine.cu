@@ -1524,16 +1524,6 @@ static int ascii_geometry(const uint32_t* len, uint64_t n, uint32_t uniform_len,
 // Pack reads [first, first + count) on stream s (buffers of parity `par`): text bytes and offsets / lengths up, the pack
 // kernel, the scan that continues the exception index from the chunks before (ordered across the two streams by
 // events), the exception entries.  The packed data lands in the context's batch buffers at the reads' global positions.
-static void parallel_copy(char* dst, const char* src, size_t bytes, int n_threads) {
-    if (bytes < (1u << 22) || n_threads <= 1) { std::memcpy(dst, src, bytes); return; }
-    std::vector<std::thread> th;
-    for (int t = 0; t < n_threads; t++) {
-        const size_t a = bytes * t / n_threads, b = bytes * (t + 1) / n_threads;
-        th.emplace_back([=] { std::memcpy(dst + a, src + a, b - a); });
-    }
-    for (auto& x : th) x.join();
-}
-
 static int pack_chunk(dcb_ctx* c, cudaStream_t s, int par, const char* ascii, const uint64_t* off, const uint32_t* len,
                       uint32_t uniform_len, int revcomp, uint32_t first, uint32_t count, size_t exc_cap, int chunk_no,
                       bool staged = false) {
@@ -1546,30 +1536,62 @@ static int pack_chunk(dcb_ctx* c, cudaStream_t s, int par, const char* ascii, co
     else for (uint32_t i = first; i < first + count; i++) hi = std::max<uint64_t>(hi, off[i] + (len ? len[i] : L));
     if (!contiguous) for (uint32_t i = first; i < first + count; i++) if (off[i] < lo) { dcb_set_error("read offsets must not decrease inside a batch"); return DCB_EINVAL; }
     int rc;
-    if ((rc = c->text[par].ensure(hi - lo + 64))) return rc;
-    const char* from = ascii + lo;
+    PackSrc src;
+    src.stride = L; src.uniform_len = len ? 0u : L;
+    src.first = first; src.count = count; src.off = nullptr; src.len = nullptr;
     if (staged) {
+        // Pageable text: host threads GATHER the chunk's reads (the sequence lines only, not the headers and qualities
+        // between them) into a page-locked buffer, back to back; the copy engine takes it from there at link speed while
+        // the threads fill the other buffer.  Layout of the buffer: [local offsets (only when lengths vary)][text].
         CUDA_TRY(cudaEventSynchronize(c->ev_stage[par]));                      // the copy engine is done with this buffer
-        if (c->stage_cap[par] < hi - lo) {
+        const bool vary = len != nullptr;
+        uint64_t total = 0;
+        if (vary) for (uint32_t i = first; i < first + count; i++) total += len[i];
+        else total = (uint64_t)count * L;
+        const size_t head = vary ? (((size_t)count * 8 + 255) & ~(size_t)255) : 0;
+        if (c->stage_cap[par] < head + total + 64) {
             if (c->stage[par]) cudaFreeHost(c->stage[par]);
             c->stage[par] = nullptr; c->stage_cap[par] = 0;
-            const size_t want = (hi - lo) + (hi - lo) / 8 + 4096;
+            const size_t want = head + total + (head + total) / 8 + 4096;
             CUDA_TRY(cudaHostAlloc((void**)&c->stage[par], want, cudaHostAllocDefault));
             c->stage_cap[par] = want;
         }
+        uint64_t* loc = reinterpret_cast<uint64_t*>(c->stage[par]);
+        char* dst = c->stage[par] + head;
+        if (vary) { uint64_t at = 0; for (uint32_t i = 0; i < count; i++) { loc[i] = at; at += len[first + i]; } }
         const unsigned hw = std::thread::hardware_concurrency();
-        parallel_copy(c->stage[par], from, hi - lo, (int)std::min<unsigned>(16u, hw ? hw : 4u));
-        from = c->stage[par];
-    }
-    CUDA_TRY(cudaMemcpyAsync(c->text[par].p, from, hi - lo, cudaMemcpyHostToDevice, s));
-    if (staged) CUDA_TRY(cudaEventRecord(c->ev_stage[par], s));
-    PackSrc src;
-    src.text = (const unsigned char*)c->text[par].p; src.text_lo = lo; src.stride = L; src.uniform_len = len ? 0u : L;
-    src.first = first; src.count = count; src.off = nullptr; src.len = nullptr;
-    if (!contiguous) {
-        if ((rc = c->roff[par].ensure((size_t)count * 8 + 16))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(c->roff[par].p, off + first, (size_t)count * 8, cudaMemcpyHostToDevice, s));
-        src.off = (const uint64_t*)c->roff[par].p;
+        const int nt = count < 8192 ? 1 : (int)std::min<unsigned>(16u, hw ? hw : 4u);
+        auto work = [&](uint32_t a, uint32_t b) {
+            for (uint32_t i = a; i < b; i++) {
+                const uint32_t Li = vary ? len[first + i] : L;
+                std::memcpy(dst + (vary ? loc[i] : (uint64_t)i * L), ascii + (contiguous ? (uint64_t)(first + i) * L : off[first + i]), Li);
+            }
+        };
+        if (nt == 1) work(0, count);
+        else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nt; t++) th.emplace_back(work, (uint32_t)((uint64_t)count * t / nt), (uint32_t)((uint64_t)count * (t + 1) / nt));
+            for (auto& x : th) x.join();
+        }
+        if ((rc = c->text[par].ensure(total + 64))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c->text[par].p, dst, total, cudaMemcpyHostToDevice, s));
+        src.text = (const unsigned char*)c->text[par].p;
+        src.text_lo = vary ? 0 : (uint64_t)first * L;                          // read i of the chunk at i * L (uniform) or loc[i]
+        if (vary) {
+            if ((rc = c->roff[par].ensure((size_t)count * 8 + 16))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(c->roff[par].p, loc, (size_t)count * 8, cudaMemcpyHostToDevice, s));
+            src.off = (const uint64_t*)c->roff[par].p;
+        }
+        CUDA_TRY(cudaEventRecord(c->ev_stage[par], s));
+    } else {
+        if ((rc = c->text[par].ensure(hi - lo + 64))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c->text[par].p, ascii + lo, hi - lo, cudaMemcpyHostToDevice, s));
+        src.text = (const unsigned char*)c->text[par].p; src.text_lo = lo;
+        if (!contiguous) {
+            if ((rc = c->roff[par].ensure((size_t)count * 8 + 16))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(c->roff[par].p, off + first, (size_t)count * 8, cudaMemcpyHostToDevice, s));
+            src.off = (const uint64_t*)c->roff[par].p;
+        }
     }
     if (len) {
         if ((rc = c->rlen[par].ensure((size_t)count * 4 + 16))) return rc;

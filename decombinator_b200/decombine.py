@@ -50,8 +50,6 @@ def import_tcr_info(inputargs):
     chain = _info.chain
     if _info.chain_detected:
         counts["chain_detected"] = 1
-    for c in _ctx_cache.values():
-        c.close()
     _ctx_cache = {}
     g = globals()
     for name in ("v_seqs", "j_seqs", "half1_v_seqs", "half2_v_seqs", "half1_j_seqs", "half2_j_seqs", "jump_to_end_v",
@@ -60,13 +58,25 @@ def import_tcr_info(inputargs):
     return _info
 
 
+_ctx_store = {}   # (tag set, device, both_frames, allowNs, lenthreshold) -> _lib.Context, kept across runs of one process
+
+
 def _context(inputargs, both_frames):
     key = (bool(both_frames), bool(inputargs["allowNs"]), int(inputargs["lenthreshold"]))
     ctx = _ctx_cache.get(key)
     if ctx is None:
-        vt, jt = _info.tables()
         device = int(os.environ.get("LOCAL_RANK", inputargs.get("device", 0) or 0))
-        ctx = _lib.Context(vt, jt, device=device, both_frames=key[0], allow_ns=key[1], lenthreshold=key[2])
+        # the device tables depend on nothing but the tag set: a second run with the same set (the pipeline's next stage,
+        # the next file of a batch job) reuses the context with its device buffers and page-locked staging
+        tagkey = (tuple(_info.v_seqs), tuple(_info.j_seqs), tuple(_info.jump_to_end_v), tuple(_info.jump_to_start_j),
+                  _info.v_half_split, _info.j_half_split, hash(tuple(_info.v_regions)), hash(tuple(_info.j_regions)), device) + key
+        ctx = _ctx_store.get(tagkey)
+        if ctx is None:
+            if len(_ctx_store) >= 4:          # a handful of chains at most stay resident
+                _ctx_store.pop(next(iter(_ctx_store))).close()
+            vt, jt = _info.tables()
+            ctx = _lib.Context(vt, jt, device=device, both_frames=key[0], allow_ns=key[1], lenthreshold=key[2])
+            _ctx_store[tagkey] = ctx
         _ctx_cache[key] = ctx
     return ctx
 

@@ -152,6 +152,8 @@ class ReadBatch:
 
 def _clip(off, length, start, stop=None):
     """(offset, length) of s[start:stop] for every record s = (off, length); start, stop >= 0."""
+    if start == 0 and stop is not None:          # a prefix (the barcode and its quality): one pass
+        return off, np.minimum(length, np.uint32(stop)).astype(np.uint32, copy=False)
     n = length.astype(np.int64)
     a = np.minimum(n, start)
     b = n if stop is None else np.minimum(n, stop)
