@@ -83,16 +83,16 @@ def cpu_reference_run(r1, off, ln, threads, steps=1, warmup=0):
     return len(off) * steps / dt, dt / steps, int(res["ok"].sum())
 
 
-def run_cfg2(args, rank, world, local_rank, host_threads, stream, barrier):
-    """BASELINE configs[2] in the same run: ONE mixed file (even reads alpha molecules, odd reads beta), human extended tag
-    sets, 1 % substitutions + 0.1 % N per base, analysed once per chain (-c a, then -c b) as the reference's example does.
-    Batch resident in HBM, K passes of all three kernels per chain, CUDA events, max over ranks."""
+def run_mixed(args, rank, world, local_rank, host_threads, stream, barrier, species, tagset, chains, seed, sub, nrate, label):
+    """One mixed file (read i is a molecule of chain i % len(chains)) analysed once per chain, as the reference's example
+    runs `-c a` and `-c b` on the same FASTQ.  Batch resident in HBM, K passes of all kernels per chain, CUDA events on
+    the launching stream, max over ranks."""
     import torch
     import torch.distributed as dist
     from decombinator_b200 import _lib, tags
-    ia, ib = tags.load("human", "extended", "a"), tags.load("human", "extended", "b")
-    n, seed = args.reads, 20260003
-    syn = _lib.Synth([(ia.v_regions, ia.j_regions), (ib.v_regions, ib.j_regions)], seed, READ_LEN, 0, 0.01, 0.001, 0.0)
+    infos = [tags.load(species, tagset, c) for c in chains]
+    n = args.reads
+    syn = _lib.Synth([(i.v_regions, i.j_regions) for i in infos], seed, READ_LEN, 0, sub, nrate, 0.0)
     r1, _ = syn.reads(rank * n, n, n_threads=host_threads)
     off = np.arange(n, dtype=np.uint64) * READ_LEN
     ln = np.full(n, READ_LEN, dtype=np.uint32)
@@ -105,11 +105,9 @@ def run_cfg2(args, rank, world, local_rank, host_threads, stream, barrier):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    out = {"workload": "synthetic 250-nt reads, one mixed file (even reads human alpha, odd reads human beta), extended tag sets, "
-                       "1 %% substitutions + 0.1 %% N per base, analysed once per chain (BASELINE configs[2] shape, %d reads per GPU)" % n,
-           "seed": seed, "steps": steps, "chains": {}}
+    out = {"workload": label % n, "seed": seed, "steps": steps, "chains": {}}
     total_ms = 0.0
-    for chain, info in (("a", ia), ("b", ib)):
+    for chain, info in zip(chains, infos):
         vt, jt = info.tables()
         ctx = _lib.Context(vt, jt, device=local_rank)
         ctx.set_stream(stream.cuda_stream)
@@ -147,9 +145,24 @@ def run_cfg2(args, rank, world, local_rank, host_threads, stream, barrier):
         ctx.close()
     packed.free()
     out["value"] = world * n / (total_ms / 1e3)
-    out["unit"] = "reads of the file/s, both chains analysed"
+    out["unit"] = "reads of the file/s, all chains analysed"
     out["ms_per_file_pass"] = total_ms
     return out
+
+
+def run_cfg2(args, rank, world, local_rank, host_threads, stream, barrier):
+    """BASELINE configs[2]: human alpha / beta, extended tag sets, 1 % substitutions + 0.1 % N per base."""
+    return run_mixed(args, rank, world, local_rank, host_threads, stream, barrier, "human", "extended", ("a", "b"), 20260003, 0.01, 0.001,
+                     "synthetic 250-nt reads, one mixed file (even reads human alpha, odd reads human beta), extended tag sets, "
+                     "1 %% substitutions + 0.1 %% N per base, analysed once per chain (BASELINE configs[2] shape, %d reads per GPU)")
+
+
+def run_cfg4(args, rank, world, local_rank, host_threads, stream, barrier):
+    """BASELINE configs[4]: mouse gamma / delta, original tag sets (12-nt J tags: the bit-filter exact kernel), 0.5 % substitutions."""
+    return run_mixed(args, rank, world, local_rank, host_threads, stream, barrier, "mouse", "original", ("g", "d"), 20260005, 0.005, 0.0,
+                     "synthetic 250-nt reads, one mixed file (even reads mouse gamma, odd reads mouse delta), original tag sets, "
+                     "0.5 %% substitutions per base, analysed once per chain (BASELINE configs[4] shape, %d reads per GPU; the named "
+                     "500 M reads on 8 GPUs are 6.25 such shards per GPU)")
 
 
 class ClockSampler:
@@ -320,11 +333,12 @@ def main():
     exact_name, h2d_bytes = ctx.exact_kernel_name(), packed.h2d_bytes()
 
     n_general = ctx.last_general()
-    cfg2 = None
+    cfg2 = cfg4 = None
     if not args.no_workloads:
         ctx.close(); ctx = None
         packed.free()
         cfg2 = run_cfg2(args, rank, world, local_rank, host_threads, stream, barrier)
+        cfg4 = run_cfg4(args, rank, world, local_rank, host_threads, stream, barrier)
         packed = None
 
     if world > 1:
@@ -379,7 +393,7 @@ def main():
             "clocks": clocks,
         }
         if cfg2:
-            line["workloads"] = {"cfg2": cfg2}
+            line["workloads"] = {"cfg2": cfg2, "cfg4": cfg4}
         if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only
             threads = os.cpu_count() or 1
             sample = args.cpu_sample or min(n, 2_000_000 if threads < 16 else 10_000_000)
