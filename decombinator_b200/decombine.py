@@ -169,38 +169,95 @@ def _open_summary(inputargs, summaryname, logpath, date, samplenam):
     raise RuntimeError("no free summary file name")
 
 
+def sample_name(inputargs):
+    samplenam = str(inputargs["infile"].split(".")[0])
+    if os.sep in samplenam:
+        samplenam = samplenam.split(os.sep)[-1]
+    return samplenam
+
+
+def summary_location(inputargs, samplenam, date):
+    """Logs/ directory (created) and the first-choice summary name (decombine.py:897-910)."""
+    logpath = inputargs["outpath"] + f"Logs{os.sep}"
+    if not os.path.exists(logpath):
+        os.makedirs(logpath, exist_ok=True)
+    return logpath, _summary_path(inputargs, logpath, date, samplenam)
+
+
+def check_fastq(inputargs, opener, summaryname, logpath, date, samplenam):
+    """The input check at the top of decombinator() (decombine.py:131-179, 912-918): fewer than four lines -> stub summary and
+    ValueError.  Multi-GPU runs call it on rank 0 and broadcast the outcome (parallel.decombinator_shard)."""
+    if summaryname is None:
+        raise UnboundLocalError("cannot access local variable 'summaryname'")  # as the reference (-s without -dk)
+    if not fastq.fastq_sanity(inputargs["infile"], opener):
+        # stub summary for an empty input (decombine.py:131-161)
+        inout_name = "_".join(f"{samplenam}".split("_")[:-1]) + f"_{chainnams[chain]}"
+        summstr = "OutputFile," + inout_name + "\nNumberReadsInput," + "0"
+        summaryname, fh = _open_summary(inputargs, summaryname, logpath, date, samplenam)
+        print(summstr, file=fh)
+        fh.close()
+        sort_permissions(summaryname)
+        raise ValueError(
+            "There are fewer than four lines in this file, and thus it is not a valid FASTQ file. Please check input and try again."
+        )
+
+
+def write_summary(inputargs, summaryname, logpath, date, samplenam, timetaken):
+    """The Decombinator summary CSV from the module's `counts` (decombine.py:1081-1200).  Multi-GPU runs call this on rank 0
+    AFTER the per-rank counters have been summed (parallel.decombinator_shard), so the file reports the whole job."""
+    summaryname, summaryfile = _open_summary(inputargs, summaryname, logpath, date, samplenam)
+    inout_name = "_".join(f"{samplenam}".split("_")[:-1]) + f"_{chainnams[chain]}"
+    summstr = ("Property,Value\nDirectory," + os.getcwd() + "\nInputFile," + inout_name + "\nOutputFile," + inout_name
+               + "\nDateFinished," + date + "\nTimeFinished," + strftime("%H:%M:%S") + "\nTimeTaken(Seconds),"
+               + str(round(timetaken, 2)) + "\n\nInputArguments:,\n")
+    for s in ["species", "chain", "extension", "tags", "dontgzip", "allowNs", "orientation", "lenthreshold", "bc_read",
+              "bclength"]:
+        summstr = summstr + s + "," + str(inputargs[s]) + "\n"
+    counts["pc_decombined"] = counts["vj_count"] / counts["read_count"]
+    sections = [
+        ("\nNumberReadsInput,", "read_count"), ("\nNumberReadsDecombined,", "vj_count"),
+    ]
+    for label, key in sections:
+        summstr += label + str(counts[key])
+    summstr += "\nPercentReadsDecombined," + str(round(counts["pc_decombined"], 3))
+    summstr += "\n\nReadsAssignedUsingHalfTags:,"
+    for label, key in (("V1error", "verr1"), ("V2error", "verr2"), ("J1error", "jerr1"), ("J2error", "jerr2")):
+        summstr += "\n" + label + "," + str(counts[key])
+    summstr += "\n\nReadsFilteredOut:,"
+    for label, key in (("AmbiguousBaseCall(DCR)", "dcrfilter_intertagN"),
+                       ("AmbiguousBaseCall(Barcode)", "dcrfilter_barcodeN"),
+                       ("OverlongInterTagSeq", "dcrfilter_toolong_intertag"),
+                       ("ImpossibleDeletions", "dcrfilter_imposs_deletion"),
+                       ("OverlappingTagBoundaries", "dcrfilter_tag_overlap")):
+        summstr += "\n" + label + "," + str(counts[key])
+    summstr += "\n\nReadsFailedAssignment:,"
+    for label, key in (("MultipleVtagMatches", "multiple_v_matches"), ("VTagAtEndRead", "v_del_failed_tag_at_end"),
+                       ("VDeletionsUndetermined", "v_del_failed"), ("FoundV1HalfTagNotV2", "foundv1notv2"),
+                       ("FoundV2HalfTagNotV1", "foundv2notv1"), ("NoVDetected", "no_vtags_found"),
+                       ("MultipleJTagMatches", "multiple_j_matches"), ("JDeletionsUndermined", "j_del_failed"),
+                       ("FoundJ1HalfTagNotJ2", "foundj1notj2"), ("FoundJ2HalfTagNotJ1", "foundj2notj1"),
+                       ("NoJDetected", "no_j_assigned")):
+        summstr += "\n" + label + "," + str(counts[key])
+    print(summstr, file=summaryfile)
+    summaryfile.close()
+    sort_permissions(summaryname)
+
+
 def decombinator(inputargs: dict) -> list:
     """Function wrapper for decombinator (decombine.py:881-1202)."""
     print("Running Decombinator version", __version__)
     opener = opener_check(inputargs)
     import_tcr_info(inputargs)
 
-    samplenam = str(inputargs["infile"].split(".")[0])
-    if os.sep in samplenam:
-        samplenam = samplenam.split(os.sep)[-1]
+    samplenam = sample_name(inputargs)
 
     summaryname = logpath = None
     date = strftime("%Y_%m_%d")
     if inputargs["suppresssummary"] == False:  # noqa: E712
-        logpath = inputargs["outpath"] + f"Logs{os.sep}"
-        if not os.path.exists(logpath):
-            os.makedirs(logpath)
-        summaryname = _summary_path(inputargs, logpath, date, samplenam)
+        logpath, summaryname = summary_location(inputargs, samplenam, date)
 
     if inputargs["dontcheck"] == False:  # noqa: E712
-        if summaryname is None:
-            raise UnboundLocalError("cannot access local variable 'summaryname'")  # as the reference (-s without -dk)
-        if not fastq.fastq_sanity(inputargs["infile"], opener):
-            # stub summary for an empty input (decombine.py:131-161)
-            inout_name = "_".join(f"{samplenam}".split("_")[:-1]) + f"_{chainnams[chain]}"
-            summstr = "OutputFile," + inout_name + "\nNumberReadsInput," + "0"
-            summaryname, fh = _open_summary(inputargs, summaryname, logpath, date, samplenam)
-            print(summstr, file=fh)
-            fh.close()
-            sort_permissions(summaryname)
-            raise ValueError(
-                "There are fewer than four lines in this file, and thus it is not a valid FASTQ file. Please check input and try again."
-            )
+        check_fastq(inputargs, opener, summaryname, logpath, date, samplenam)
 
     counts["start_time"] = time()
     print("Decombining FASTQ data...")
@@ -280,42 +337,7 @@ def decombinator(inputargs: dict) -> list:
     print("Took", str(round(timetaken, 2)), "seconds")
 
     if inputargs["suppresssummary"] == False:  # noqa: E712
-        summaryname, summaryfile = _open_summary(inputargs, summaryname, logpath, date, samplenam)
-        inout_name = "_".join(f"{samplenam}".split("_")[:-1]) + f"_{chainnams[chain]}"
-        summstr = ("Property,Value\nDirectory," + os.getcwd() + "\nInputFile," + inout_name + "\nOutputFile," + inout_name
-                   + "\nDateFinished," + date + "\nTimeFinished," + strftime("%H:%M:%S") + "\nTimeTaken(Seconds),"
-                   + str(round(timetaken, 2)) + "\n\nInputArguments:,\n")
-        for s in ["species", "chain", "extension", "tags", "dontgzip", "allowNs", "orientation", "lenthreshold", "bc_read",
-                  "bclength"]:
-            summstr = summstr + s + "," + str(inputargs[s]) + "\n"
-        counts["pc_decombined"] = counts["vj_count"] / counts["read_count"]
-        sections = [
-            ("\nNumberReadsInput,", "read_count"), ("\nNumberReadsDecombined,", "vj_count"),
-        ]
-        for label, key in sections:
-            summstr += label + str(counts[key])
-        summstr += "\nPercentReadsDecombined," + str(round(counts["pc_decombined"], 3))
-        summstr += "\n\nReadsAssignedUsingHalfTags:,"
-        for label, key in (("V1error", "verr1"), ("V2error", "verr2"), ("J1error", "jerr1"), ("J2error", "jerr2")):
-            summstr += "\n" + label + "," + str(counts[key])
-        summstr += "\n\nReadsFilteredOut:,"
-        for label, key in (("AmbiguousBaseCall(DCR)", "dcrfilter_intertagN"),
-                           ("AmbiguousBaseCall(Barcode)", "dcrfilter_barcodeN"),
-                           ("OverlongInterTagSeq", "dcrfilter_toolong_intertag"),
-                           ("ImpossibleDeletions", "dcrfilter_imposs_deletion"),
-                           ("OverlappingTagBoundaries", "dcrfilter_tag_overlap")):
-            summstr += "\n" + label + "," + str(counts[key])
-        summstr += "\n\nReadsFailedAssignment:,"
-        for label, key in (("MultipleVtagMatches", "multiple_v_matches"), ("VTagAtEndRead", "v_del_failed_tag_at_end"),
-                           ("VDeletionsUndetermined", "v_del_failed"), ("FoundV1HalfTagNotV2", "foundv1notv2"),
-                           ("FoundV2HalfTagNotV1", "foundv2notv1"), ("NoVDetected", "no_vtags_found"),
-                           ("MultipleJTagMatches", "multiple_j_matches"), ("JDeletionsUndermined", "j_del_failed"),
-                           ("FoundJ1HalfTagNotJ2", "foundj1notj2"), ("FoundJ2HalfTagNotJ1", "foundj2notj1"),
-                           ("NoJDetected", "no_j_assigned")):
-            summstr += "\n" + label + "," + str(counts[key])
-        print(summstr, file=summaryfile)
-        summaryfile.close()
-        sort_permissions(summaryname)
+        write_summary(inputargs, summaryname, logpath, date, samplenam, timetaken)
 
     return outdata
 

@@ -103,21 +103,44 @@ def decombinator_shard(inputargs):
     """This rank's part of ``decombinator(inputargs)``: -> (rows of its shard, global row index of the first one).
     ``decombine.counts`` ends up holding the whole-job totals on every rank."""
     rank, world = _rank_world()
-    args = dict(inputargs)
-    if world > 1:
-        args["shard"] = (rank, world)
-        if rank:   # rank 0 checks the FASTQ and writes the summary
-            args["suppresssummary"] = True
-            args["dontcheck"] = True
-    rows = D.decombinator(args)
     if world == 1:
-        return rows, 0
+        return D.decombinator(dict(inputargs)), 0
+    args = dict(inputargs)
+    args["shard"] = (rank, world)
+    # No rank writes the summary from inside decombinator(): its counters cover one shard.  Rank 0 writes it below from
+    # the summed counters.  The FASTQ check runs on rank 0 and its verdict is broadcast, so that a bad input makes EVERY
+    # rank raise instead of leaving the others waiting in the next collective.
+    args["suppresssummary"] = True
+    args["dontcheck"] = True
+    want_summary = inputargs["suppresssummary"] == False  # noqa: E712
+    t0 = time.time()
+    verdict = [None]
+    if rank == 0 and inputargs["dontcheck"] == False:  # noqa: E712
+        try:
+            from time import strftime
+            D.import_tcr_info(dict(inputargs))                      # sets the chain the stub summary is named after
+            samplenam, date = D.sample_name(inputargs), strftime("%Y_%m_%d")
+            logpath = summaryname = None
+            if want_summary:
+                logpath, summaryname = D.summary_location(inputargs, samplenam, date)
+            D.check_fastq(inputargs, D.opener_check(inputargs), summaryname, logpath, date, samplenam)
+        except BaseException as exc:  # noqa: BLE001 -- re-raised on every rank
+            verdict[0] = exc
+    dist.broadcast_object_list(verdict, src=0)
+    if verdict[0] is not None:
+        raise verdict[0]
+    rows = D.decombinator(args)
     sizes = [None] * world
     dist.all_gather_object(sizes, len(rows))
     skip = ("start_time", "end_time", "pc_decombined", "chain_detected")
     total = _sum_counters({k: v for k, v in D.counts.items() if k not in skip})
     for k, v in total.items():
         D.counts[k] = v
+    if rank == 0 and want_summary:
+        from time import strftime
+        samplenam, date = D.sample_name(inputargs), strftime("%Y_%m_%d")
+        logpath, summaryname = D.summary_location(inputargs, samplenam, date)
+        D.write_summary(inputargs, summaryname, logpath, date, samplenam, time.time() - t0)
     return rows, sum(sizes[:rank])
 
 
@@ -156,7 +179,11 @@ def collapsinator_sharded(inputargs, data=None, first_index=0, n_total=None):
     if from_file:
         import gzip
         opener = gzip.open if inputargs["infile"].endswith(".gz") else open
-        if rank == 0 and not inputargs["dontcheckinput"] and not C.check_dcr_file(inputargs["infile"], opener):
+        verdict = [True]
+        if rank == 0 and not inputargs["dontcheckinput"]:
+            verdict[0] = bool(C.check_dcr_file(inputargs["infile"], opener))
+        dist.broadcast_object_list(verdict, src=0)           # every rank stops on a bad file, none is left in a collective
+        if not verdict[0]:
             raise SystemExit("Please check that file contains suitable Decombinator output for collapsing.")
         with opener(inputargs["infile"], "rt") as fh:
             lines = fh.readlines()

@@ -102,7 +102,11 @@ def fuzz(reads, info, rng):
             v = rng.choice(info.v_regions); j = rng.choice(info.j_regions)
             mol = v[:len(v) - rng.randrange(0, 45)] + j[rng.randrange(0, 30):] + "".join(rng.choice("ACGT") for _ in range(rng.randrange(0, 30)))
             out.append(mol.translate(comp)[::-1])
-        elif op == 11:   # J before V (tag-overlap / inter-tag-length filters)
+        elif op == 11:   # J before V.  (This cannot reach dcrfilter_tag_overlap or, with a positive threshold,
+            # dcrfilter_toolong_intertag -- nothing can: once vdel <= jump_v - len(vtag) and jdel <= jump_j have passed
+            # (dcrfilter_imposs_deletion is checked first, decombine.py:561-565), end_of_v >= v_seq_start + len(vtag) and the
+            # J walk only accepts positions >= end_of_v with pos <= jump_j, so the J tag starts at or behind the V tag's end:
+            # v_seq_start + len(vtag) <= j_seq_end < j_seq_end + len(jtag).  Both filters are dead code)
             v = rng.choice(info.v_regions); j = rng.choice(info.j_regions)
             mol = j + "".join(rng.choice("ACGT") for _ in range(rng.randrange(0, 20))) + v + \
                   "".join(rng.choice("ACGT") for _ in range(rng.randrange(12, 40)))
@@ -235,13 +239,25 @@ def main():
                                               tags=tagset, orientation=orient, bclength=bl, **extra)
             rows = ref["decombine"].decombinator(args)
             counts = {k: int(v) for k, v in ref["decombine"].counts.items() if k not in ("start_time", "end_time")}
+            # the same run once more with the summary switched on: the text of Logs/..._Decombinator_Summary.csv, with the
+            # values of the four lines that depend on where and when it ran replaced (so the fixture regenerates identically)
+            sargs = dict(args, suppresssummary=False, dontcheck=False)
+            ref["decombine"].decombinator(sargs)
+            logs = sorted(os.listdir("Logs"))
+            assert len(logs) == fi + 1, logs
+            newest = max((os.path.join("Logs", n) for n in logs), key=os.path.getmtime)
+            with open(newest) as fh:
+                summary = fh.read()
+            summary = "\n".join(ln.split(",")[0] + ",<run>" if ln.split(",")[0] in ("Directory", "DateFinished", "TimeFinished", "TimeTaken(Seconds)")
+                                else ln for ln in summary.split("\n"))
+            summary_name = os.path.basename(newest).split("_", 3)[3]        # without the date prefix YYYY_MM_DD_
             with open(f1) as fh:
                 t1 = fh.read()
             with open(f1.replace("1.f", "2.f")) as fh:
                 t2 = fh.read()
             print("file run", fi, species, tagset, chain, orient, bc_read, "rows", len(rows))
             runs.append({"args": {k: v for k, v in args.items() if k != "tagfastadir"}, "fastq1": t1, "fastq2": t2,
-                         "rows": rows, "counts": counts})
+                         "rows": rows, "counts": counts, "summary": summary, "summary_name": summary_name})
     finally:
         os.chdir(cwd)
     out = os.path.join(ROOT, "tests", "golden", "decombinator_runs.json.gz")

@@ -62,6 +62,17 @@ def test_recorded_reference_runs(decombinator_runs, tmp_path):
             assert rows == run["rows"], (ri, mode)
             got = {k: int(v) for k, v in decombine.counts.items() if k not in ("start_time", "end_time")}
             assert got == run["counts"], (ri, mode, got, run["counts"])
+        # the summary CSV, byte for byte (the values of the four lines that depend on where / when it ran are masked in
+        # the recording, decombine.py:1081-1200), and its file name behind the date prefix
+        logdir = tmp_path / "Logs"
+        before = set(os.listdir(logdir)) if logdir.exists() else set()
+        decombine.decombinator(dict(a, suppresssummary=False, dontcheck=False, outpath=str(tmp_path) + os.sep))
+        new = sorted(set(os.listdir(logdir)) - before)
+        assert len(new) == 1 and new[0].split("_", 3)[3] == run["summary_name"], (ri, new)
+        text = (logdir / new[0]).read_text()
+        masked = "\n".join(ln.split(",")[0] + ",<run>" if ln.split(",")[0] in ("Directory", "DateFinished", "TimeFinished", "TimeTaken(Seconds)")
+                           else ln for ln in text.split("\n"))
+        assert masked == run["summary"], (ri, masked, run["summary"])
 
 
 @gpu
@@ -112,8 +123,10 @@ def _sharded_worker(rank, world, port, tmp, out_path):
     import torch.distributed as dist
     from decombinator_b200 import collapse as C, decombine as D, parallel
     parallel.init_from_env("gloo")
-    args = _args(os.path.join(tmp, "TINY_1.fq"), "b", tmp, suppresssummary=True, dontcheck=True, oligo="M13", command="pipeline")
+    # the summary is switched ON: rank 0 must write it from the counters summed over both ranks (and run the input check)
+    args = _args(os.path.join(tmp, "TINY_1.fq"), "b", os.path.join(tmp, "two"), oligo="M13", command="pipeline")
     mine, first = parallel.decombinator_shard(args)     # every rank keeps its own shard for the collapse all-to-all
+    args["suppresssummary"] = True                      # (the collapse summary is not under test here)
     rows = parallel.gather_rows(mine)
     freq = parallel.collapsinator_sharded(args, data=mine, first_index=first)
     if rank == 0:
@@ -135,8 +148,19 @@ def test_two_rank_pipeline_equals_golden(golden_dir, tmp_path):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     out_path = str(tmp_path / "out.json")
+    (tmp_path / "two").mkdir()
     mp.spawn(_sharded_worker, args=(2, port, str(tmp_path), out_path), nprocs=2, join=True)
     got = json.load(open(out_path))
+    # the two-rank summary CSV equals the single-process one (all counters are whole-job totals), time lines aside
+    (tmp_path / "one").mkdir()
+    decombine.decombinator(_args(str(tmp_path / "TINY_1.fq"), "b", tmp_path / "one"))
+
+    def summary(d):
+        logs = os.listdir(tmp_path / d / "Logs")
+        assert len(logs) == 1, logs
+        return [ln for ln in (tmp_path / d / "Logs" / logs[0]).read_text().split("\n")
+                if ln.split(",")[0] not in ("TimeFinished", "TimeTaken(Seconds)")]
+    assert summary("two") == summary("one") and "NumberReadsInput,106" in summary("two")
     want_n12 = open(os.path.join(golden_dir, "dcr_TINY_1_beta.n12")).read()
     assert "".join(", ".join(map(str, r)) + "\n" for r in got["rows"]) == want_n12
     assert got["vj"] == 48
