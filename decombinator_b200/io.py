@@ -143,3 +143,21 @@ def write_out_intermediate(data: list, inputargs: dict, suffix: str):
         os.unlink(outfilename)
         outfilename += ".gz"
     sort_permissions(outfilename)
+
+
+def write_out_translated(data, inputargs: dict):
+    """AIRR ``.tsv`` writer: ``DataFrame.to_csv(sep="\\t", index=False)``, gzip unless -dz (io.py:516-548)."""
+    chainnams = {"a": "alpha", "b": "beta", "g": "gamma", "d": "delta"}
+    filename_id = os.path.basename(inputargs["infile"]).split(".")[0]
+    if inputargs["command"] in ["collapse", "translate"]:
+        outfilename = inputargs["outpath"] + f"{filename_id}" + ".tsv"
+    else:
+        outfilename = inputargs["outpath"] + inputargs["prefix"] + f"{filename_id}" + f"_{chainnams[inputargs['chain'].lower()]}" + ".tsv"
+    data.to_csv(f"{outfilename}", sep="\t", index=False)
+    if not inputargs["dontgzip"]:
+        print("Compressing pipeline output file to", outfilename + ".gz")
+        with open(outfilename) as infile, gzip.open(outfilename + ".gz", "wt") as outfile:
+            outfile.writelines(infile)
+        os.unlink(outfilename)
+        outfilename += ".gz"
+    sort_permissions(outfilename)

@@ -1,18 +1,13 @@
-"""Entry point: ``decombinator {decombine|pipeline|collapse|translate}`` (reference pipeline.py:10-53).
+"""Entry point: ``decombinator {decombine|pipeline|collapse|translate}`` (reference pipeline.py:10-53): decombine ->
+``.n12`` -> collapse -> ``.freq`` -> translate -> AIRR ``.tsv``, stages chained in memory.
 
 Under ``torchrun`` (WORLD_SIZE > 1) the same commands run one process per GPU: reads are sharded over the ranks for
 ``decombine``, rows are repartitioned by barcode hash for ``collapse`` (parallel.py); rank 0 writes the files."""
 import os
-import sys
+from datetime import datetime
 
 from .decombine import decombinator
-from .io import cli_args, write_out_intermediate
-
-
-def _translate_out_of_scope():
-    print("decombinator_b200: the 'translate' stage is outside this build (DESIGN.md section 7: it runs on the collapsed, "
-          "tiny output); run the reference's `decombinator translate` on the .freq file written here.")
-    sys.exit(2)
+from .io import cli_args, write_out_intermediate, write_out_translated
 
 
 def _world():
@@ -20,9 +15,12 @@ def _world():
 
 
 def run(args=None, cli_args=None):
-    """Decombine -> .n12 -> collapse -> .freq, stages chained in memory (reference pipeline.py:10-38)."""
+    """Decombine -> .n12 -> collapse -> .freq -> translate -> .tsv, stages chained in memory (reference pipeline.py:10-38).
+    Returns the translated DataFrame (the reference returns nothing; its tests read the files)."""
+    start = datetime.now()
     inputargs = cli_args if cli_args else args
     from .collapse import collapsinator
+    from .translate import cdr3translator
     if _world() > 1:
         from . import parallel
         rank, _ = parallel.init_from_env()
@@ -35,6 +33,13 @@ def run(args=None, cli_args=None):
         if rank == 0 and not inputargs["dontsave"]:
             write_out_intermediate(data, inputargs, ".freq")
         print("Collapsinator complete...")
+        if rank != 0:
+            return data
+        data = cdr3translator(data=data, inputargs=inputargs)     # the collapsed rows are few: rank 0 translates them
+        print("CDR3translator complete...")
+        if not inputargs["dontsave"]:
+            write_out_translated(data, inputargs)
+        print(f"Pipeline complete in {datetime.now() - start}")
         return data
     data = decombinator(inputargs)
     if not inputargs["dontsave"]:
@@ -44,6 +49,11 @@ def run(args=None, cli_args=None):
     if not inputargs["dontsave"]:
         write_out_intermediate(data, inputargs, ".freq")
     print("Collapsinator complete...")
+    data = cdr3translator(data=data, inputargs=inputargs)
+    print("CDR3translator complete...")
+    if not inputargs["dontsave"]:
+        write_out_translated(data, inputargs)
+    print(f"Pipeline complete in {datetime.now() - start}")
     return data
 
 
@@ -69,7 +79,9 @@ def main():
         if rank == 0:
             write_out_intermediate(data, inputargs, ".freq")
     elif inputargs["command"] == "translate":
-        _translate_out_of_scope()
+        from .translate import cdr3translator
+        if rank == 0:                                   # host-only stage over the collapsed rows: one process does it
+            write_out_translated(cdr3translator(inputargs=inputargs), inputargs)
     else:
         run(cli_args=inputargs)
 

@@ -194,9 +194,16 @@ def test_cli_commands_write_the_golden_files(golden_dir, tmp_path, chain, name, 
     pipeline.main()
     assert gzip.open(out2 / ("dcr_TINY_1_%s.n12.gz" % name), "rb").read() == want_n12
     monkeypatch.setattr(sys, "argv", ["decombinator", "pipeline"] + base + ["-dz", "-ol", "M13", "-op", str(out3) + os.sep])
-    try:
-        pipeline.main()
-    except SystemExit as e:           # the translate stage is outside this build: decombine + collapse ran before it
-        assert e.code in (0, 2, None)
+    pipeline.main()
     assert (out3 / ("dcr_TINY_1_%s.n12" % name)).read_bytes() == want_n12
     assert (out3 / ("dcr_TINY_1_%s.freq" % name)).read_bytes() == want_freq
+    # ... and the AIRR .tsv of the translate stage (reference tests/test_pipeline.py:39-60)
+    assert (out3 / ("dcr_TINY_1_%s.tsv" % name)).read_bytes() == open(os.path.join(golden_dir, "dcr_TINY_1_%s.tsv" % name), "rb").read()
+    assert len(os.listdir(out3 / "Logs")) == 3       # one summary per stage
+    # `decombinator translate` on the .freq just written (reference tests/test_subparsers.py:78-100)
+    out4 = tmp_path / "o4"
+    out4.mkdir()
+    monkeypatch.setattr(sys, "argv", ["decombinator", "translate", "-in", str(out3 / ("dcr_TINY_1_%s.freq" % name)), "-c", chain, "-dz",
+                                      "-op", str(out4) + os.sep])
+    pipeline.main()
+    assert (out4 / ("dcr_TINY_1_%s.tsv" % name)).read_bytes() == open(os.path.join(golden_dir, "dcr_TINY_1_%s.tsv" % name), "rb").read()

@@ -58,7 +58,7 @@ def main():
         out = pipeline.run(dict(ia))
         t_pipe = time.perf_counter() - t0
         print(json.dumps({"reads": n, "decombinator_s": round(t_dec, 2), "pipeline_s": round(t_pipe, 2), "rows": len(rows),
-                          "collapsed": len(out), "pipeline_reads_per_s": round(n / t_pipe)}))
+                          "translated": len(out), "pipeline_reads_per_s": round(n / t_pipe)}))
         return
     # warm-up: tables, context, CUDA
     small = dict(ia)
