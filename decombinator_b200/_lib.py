@@ -116,6 +116,8 @@ def lib():
     L.dcb_umi_pairs.argtypes = [vp, vp, u32, i32, vp, u64, ctypes.POINTER(u64)]
     L.dcb_lev_leq.argtypes = [vp, vp, vp, vp, u32, vp, vp, u64, ctypes.c_double, vp]
     L.dcb_dist_last_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
+    L.dcb_dist_last_method.argtypes = [vp]
+    L.dcb_dist_last_method.restype = ctypes.c_char_p
     L.dcb_synth_create.restype = vp
     L.dcb_synth_create.argtypes = [ctypes.POINTER(CSynthParams), i32, ctypes.POINTER(cpp), ctypes.POINTER(ctypes.c_int),
                                    ctypes.POINTER(cpp), ctypes.POINTER(ctypes.c_int)]
@@ -695,6 +697,9 @@ class Dist:
         ms = ctypes.c_double()
         _check(lib().dcb_dist_last_ms(self._h, ctypes.byref(ms)), "dcb_dist_last_ms")
         return ms.value
+
+    def last_method(self):
+        return lib().dcb_dist_last_method(self._h).decode()
 
     def close(self):
         if self._h:

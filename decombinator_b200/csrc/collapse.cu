@@ -7,18 +7,27 @@
 //   dcb_lev_leq    batch of are_seqs_equivalent(seq1, seq2, frac) verdicts (collapse.py:355-360):
 //                  polyleven.levenshtein(a, b) <= len(shorter) * frac, compared in double like the reference.
 //
-// Both are integer-pipe bound (no tensor cores: nothing is a dense contraction).  The pair search is a tiled
-// all-pairs sweep -- tile of 256 UMIs staged in shared memory and broadcast to 256 threads that each keep one
-// UMI's match masks in registers -- with a pigeonhole prefilter in front of the bit-parallel verifier, a
-// warp-aggregated append of the surviving pairs and a device radix sort of the 64-bit (row << 32 | col) keys.
+// Both are integer-pipe bound (no tensor cores: nothing is a dense contraction).  The pair search has two forms:
+//   * deletion neighbourhoods (what symdel does), for max_edits <= 2 and more than a few thousand UMIs: every UMI
+//     emits its variants with up to max_edits symbols deleted (79 for a 12-symbol UMI), the (variant, UMI) entries
+//     are radix-sorted by variant, and two UMIs within max_edits edits necessarily share a variant -- so only the
+//     pairs inside a run of equal variants are verified (Hamming first, then the bit-parallel Levenshtein), appended
+//     with a warp-aggregated atomic, sorted and made unique.  2 M random 12-mers: 158 M entries, ~8 G verifications,
+//     instead of the 2 x 10^12 of an all-pairs sweep;
+//   * a tiled all-pairs sweep for small lists (and max_edits > 2) -- tile of 256 UMIs staged in shared memory and
+//     broadcast to 256 threads that each keep one UMI's match masks in registers -- with a pigeonhole prefilter in
+//     front of the verifier.
+// The output of both is the device radix sort of the 64-bit (row << 32 | col) keys.
 #include "dcb_internal.h"
 #include "lev_core.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #define CUDA_TRY(expr)                                                                          \
@@ -83,6 +92,98 @@ dcb_umi_pairs_kernel(const uint64_t* __restrict__ codes, uint32_t n, int k, uint
     }
 }
 
+// ---- deletion neighbourhoods ------------------------------------------------------------------------------------
+// variants of a UMI of L symbols with up to d <= 2 deletions: 1 + L (+ L (L - 1) / 2)
+__host__ __device__ __forceinline__ uint32_t umi_n_variants(int L, int d) {
+    return 1u + (d >= 1 ? (uint32_t)L : 0u) + (d >= 2 ? (uint32_t)(L * (L - 1) / 2) : 0u);
+}
+__device__ __forceinline__ uint64_t umi_delete(uint64_t c, int p) {        // symbol p removed, length - 1
+    const uint64_t body = c & ((1ull << 58) - 1ull);
+    const uint64_t low = body & ((1ull << (3 * p)) - 1ull);
+    const uint64_t high = (body >> (3 * (p + 1))) << (3 * p);
+    return (low | high) | ((uint64_t)(umi_len(c) - 1) << 58);
+}
+// entry t of UMI i: variant t in the order (none), (p), (p < q)
+__global__ void __launch_bounds__(256)
+dcb_umi_variants_kernel(const uint64_t* __restrict__ codes, const uint64_t* __restrict__ first, uint32_t n, int d,
+                        uint64_t* __restrict__ keys, uint32_t* __restrict__ ids) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t c = codes[i];
+    const int L = umi_len(c);
+    uint64_t at = first[i];
+    keys[at] = c; ids[at] = i; at++;
+    if (d >= 1)
+        for (int p = 0; p < L; p++) {
+            const uint64_t c1 = umi_delete(c, p);
+            keys[at] = c1; ids[at] = i; at++;
+            if (d >= 2)
+                for (int q = p; q < L - 1; q++) {      // second deletion at or behind p in the shortened code: original p < q + 1
+                    keys[at] = umi_delete(c1, q); ids[at] = i; at++;
+                }
+        }
+}
+// Entry e looks at the entries behind it in its run of equal variants: every pair of UMIs of a run is a candidate.
+__global__ void __launch_bounds__(256)
+dcb_umi_runs_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ ids, uint64_t n_entries,
+                    const uint64_t* __restrict__ codes, int k, unsigned long long* __restrict__ out, unsigned long long cap,
+                    unsigned long long* __restrict__ count) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = e < n_entries;
+    const uint64_t key = live ? keys[e] : 0ull;
+    const uint32_t ia = live ? ids[e] : 0u;
+    const uint64_t ca = live ? codes[ia] : 0ull;
+    const int lane = threadIdx.x & 31;
+    UmiPattern pat;
+    bool have_pat = false;
+    uint64_t f = e + 1;
+    bool more = live && f < n_entries && keys[f] == key;
+    while (__any_sync(0xFFFFFFFFu, more)) {
+        bool hit = false;
+        uint32_t ib = 0;
+        if (more) {
+            ib = ids[f];
+            if (ib != ia) {
+                const uint64_t cb = codes[ib];
+                if (umi_len(ca) == umi_len(cb)) {          // Hamming distance <= k settles it at once
+                    const uint64_t x = (ca ^ cb) & ((1ull << 58) - 1ull);
+                    hit = __popcll((x | (x >> 1) | (x >> 2)) & 0x0249249249249249ull) <= k;
+                }
+                if (!hit && umi_may_be_within(ca, cb, k)) {
+                    if (!have_pat) { umi_pattern(ca, pat); have_pat = true; }
+                    hit = umi_distance(pat, cb) <= k;
+                }
+            }
+            f++;
+            more = f < n_entries && keys[f] == key;
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (hit) {
+                const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
+                if (slot < cap) out[slot] = ia < ib ? (((unsigned long long)ia << 32) | ib) : (((unsigned long long)ib << 32) | ia);
+            }
+        }
+    }
+}
+
+// device memory that is released on every way out of a function
+struct DevMem {
+    void* p = nullptr;
+    ~DevMem() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { if (p) { cudaFree(p); p = nullptr; } return cudaMalloc(&p, bytes ? bytes : 16); }
+    template <class T> T* as() { return static_cast<T*>(p); }
+    void* release() { void* q = p; p = nullptr; return q; }
+};
+struct Events {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+};
+
 // one thread per pair; the shorter sequence is the pattern
 template <int W>
 __device__ __forceinline__ int lev_pair(const uint8_t* pa, int la, const uint8_t* pb, int lb) {
@@ -93,11 +194,18 @@ __device__ __forceinline__ int lev_pair(const uint8_t* pa, int la, const uint8_t
 
 __global__ void __launch_bounds__(128)
 dcb_lev_leq_kernel(const uint8_t* __restrict__ sym, const uint64_t* __restrict__ off, const uint32_t* __restrict__ len,
-                   const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, unsigned long long n_pairs, double frac,
-                   uint8_t* __restrict__ verdict) {
+                   const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, unsigned long long n_pairs, uint32_t n_seqs,
+                   double frac, uint8_t* __restrict__ verdict, uint32_t* __restrict__ flag) {
     const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_pairs) return;
     uint32_t ia = a[t], ib = b[t];
+    if (ia >= n_seqs || ib >= n_seqs) { flag[0] = 1u; flag[1] = (uint32_t)t; verdict[t] = 0; return; }
+    {   // symbol codes are three bits wide
+        uint32_t any = 0;
+        for (uint32_t k = 0; k < len[ia]; k++) any |= sym[off[ia] + k];
+        for (uint32_t k = 0; k < len[ib]; k++) any |= sym[off[ib] + k];
+        if (any > 7u) { flag[2] = 1u; flag[3] = (uint32_t)t; verdict[t] = 0; return; }
+    }
     int la = (int)len[ia], lb = (int)len[ib];
     if (la > lb) { const uint32_t x = ia; ia = ib; ib = x; const int y = la; la = lb; lb = y; }
     const uint8_t* pa = sym + off[ia];
@@ -112,12 +220,28 @@ dcb_lev_leq_kernel(const uint8_t* __restrict__ sym, const uint64_t* __restrict__
     verdict[t] = ((double)d <= (double)la * frac) ? 1 : 0;
 }
 
+struct GrowBuf {            // grow-only device buffer kept between calls (dcb_lev_leq is called once per grouping round)
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 4 + 4096;
+        const cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
 struct dcb_dist {
     int device = 0;
     cudaStream_t stream = nullptr;
     unsigned long long* d_keys = nullptr;      // sorted pair keys of the last dcb_umi_pairs
     unsigned long long n_keys = 0;
     double last_ms = 0.0;
+    GrowBuf sym, off, len, a, b, ver, flag;   // dcb_lev_leq
+    const char* last_method = "";
 };
 
 extern "C" {
@@ -148,6 +272,7 @@ void dcb_dist_destroy(dcb_dist* d) {
     cudaSetDevice(d->device);
     if (d->stream) { cudaStreamSynchronize(d->stream); cudaStreamDestroy(d->stream); }
     cudaFree(d->d_keys);
+    d->sym.release(); d->off.release(); d->len.release(); d->a.release(); d->b.release(); d->ver.release(); d->flag.release();
     delete d;
 }
 
@@ -163,50 +288,109 @@ int dcb_umi_pairs(dcb_dist* d, const uint64_t* codes, uint32_t n, int max_edits,
         cudaFree(d->d_keys); d->d_keys = nullptr; d->n_keys = 0;
         *n_pairs = 0;
         if (n < 2) return DCB_OK;
-        uint64_t* d_codes = nullptr;
-        unsigned long long* d_count = nullptr;
-        unsigned long long* d_raw = nullptr;
-        CUDA_TRY(cudaMalloc((void**)&d_codes, (size_t)n * 8));
-        CUDA_TRY(cudaMalloc((void**)&d_count, 8));
-        CUDA_TRY(cudaMemcpyAsync(d_codes, codes, (size_t)n * 8, cudaMemcpyHostToDevice, s));
-        const uint32_t n_tiles = (n + kPairTile - 1) / kPairTile;
-        const unsigned long long n_blocks = (unsigned long long)n_tiles * (n_tiles + 1) / 2;
-        if (n_blocks > 0x7FFFFFFFull) { cudaFree(d_codes); cudaFree(d_count); dcb_set_error("dcb_umi_pairs: too many UMIs for one launch (%u)", n); return DCB_EUNSUPPORTED; }
-        unsigned long long capacity = std::max<unsigned long long>(1ull << 20, 8ull * n);
+        DevMem d_codes, d_count, d_raw;
+        Events ev;
+        CUDA_TRY(d_codes.alloc((size_t)n * 8));
+        CUDA_TRY(d_count.alloc(8));
+        CUDA_TRY(cudaMemcpyAsync(d_codes.p, codes, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaEventCreate(&ev.a)); CUDA_TRY(cudaEventCreate(&ev.b));
         unsigned long long found = 0;
-        cudaEvent_t e0, e1;
-        CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
-        for (int attempt = 0; attempt < 2; attempt++) {
-            CUDA_TRY(cudaMalloc((void**)&d_raw, capacity * 8));
-            CUDA_TRY(cudaMemsetAsync(d_count, 0, 8, s));
-            CUDA_TRY(cudaEventRecord(e0, s));
-            dcb_umi_pairs_kernel<<<(unsigned)n_blocks, kPairTile, 0, s>>>(d_codes, n, max_edits, n_tiles, d_raw, capacity, d_count);
+        // which form: deletion neighbourhoods for long lists (DCB_UMI_SYMDEL_MIN overrides the switch-over, for tests)
+        uint32_t symdel_min = 4096;
+        if (const char* e = std::getenv("DCB_UMI_SYMDEL_MIN")) symdel_min = (uint32_t)std::strtoul(e, nullptr, 10);
+        const bool symdel = max_edits >= 1 && max_edits <= 2 && n >= symdel_min;
+        d->last_method = symdel ? "deletion neighbourhoods" : "all pairs";
+        if (symdel) {
+            std::vector<uint64_t> first((size_t)n + 1);
+            uint64_t total = 0;
+            for (uint32_t i = 0; i < n; i++) { first[i] = total; total += umi_n_variants((int)(codes[i] >> 58), max_edits); }
+            first[n] = total;
+            DevMem d_first, k_in, k_out, v_in, v_out, d_tmp;
+            CUDA_TRY(d_first.alloc(((size_t)n + 1) * 8));
+            CUDA_TRY(k_in.alloc(total * 8)); CUDA_TRY(k_out.alloc(total * 8));
+            CUDA_TRY(v_in.alloc(total * 4)); CUDA_TRY(v_out.alloc(total * 4));
+            CUDA_TRY(cudaMemcpyAsync(d_first.p, first.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaEventRecord(ev.a, s));
+            dcb_umi_variants_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_codes.as<uint64_t>(), d_first.as<uint64_t>(), n, max_edits,
+                                                                    k_in.as<uint64_t>(), v_in.as<uint32_t>());
             CUDA_TRY(cudaGetLastError());
-            CUDA_TRY(cudaEventRecord(e1, s));
-            CUDA_TRY(cudaMemcpyAsync(&found, d_count, 8, cudaMemcpyDeviceToHost, s));
-            CUDA_TRY(cudaStreamSynchronize(s));
-            if (found <= capacity) break;
-            cudaFree(d_raw); d_raw = nullptr;      // the list did not fit: size it exactly and sweep again
-            capacity = found;
+            size_t tmp_bytes = 0;
+            CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in.as<uint64_t>(), k_out.as<uint64_t>(), v_in.as<uint32_t>(),
+                                                     v_out.as<uint32_t>(), (size_t)total, 0, 64, s));
+            CUDA_TRY(d_tmp.alloc(tmp_bytes));
+            CUDA_TRY(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, k_in.as<uint64_t>(), k_out.as<uint64_t>(), v_in.as<uint32_t>(),
+                                                     v_out.as<uint32_t>(), (size_t)total, 0, 64, s));
+            unsigned long long capacity = std::max<unsigned long long>(1ull << 22, 64ull * n);
+            for (int attempt = 0; attempt < 2; attempt++) {
+                CUDA_TRY(d_raw.alloc(capacity * 8));
+                CUDA_TRY(cudaMemsetAsync(d_count.p, 0, 8, s));
+                dcb_umi_runs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(k_out.as<uint64_t>(), v_out.as<uint32_t>(), total,
+                                                                                   d_codes.as<uint64_t>(), max_edits,
+                                                                                   d_raw.as<unsigned long long>(), capacity,
+                                                                                   d_count.as<unsigned long long>());
+                CUDA_TRY(cudaGetLastError());
+                CUDA_TRY(cudaMemcpyAsync(&found, d_count.p, 8, cudaMemcpyDeviceToHost, s));
+                CUDA_TRY(cudaStreamSynchronize(s));
+                if (found <= capacity) break;
+                capacity = found;                  // the list did not fit: size it exactly and walk the runs again
+            }
+            // a pair turns up once per variant its two UMIs share: sort, then keep one of each
+            if (found) {
+                DevMem d_sorted, d_uniq, d_nsel, d_tmp2;
+                CUDA_TRY(d_sorted.alloc(found * 8));
+                size_t tb = 0;
+                CUDA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, tb, d_raw.as<unsigned long long>(), d_sorted.as<unsigned long long>(), (size_t)found, 0, 64, s));
+                CUDA_TRY(d_tmp2.alloc(tb));
+                CUDA_TRY(cub::DeviceRadixSort::SortKeys(d_tmp2.p, tb, d_raw.as<unsigned long long>(), d_sorted.as<unsigned long long>(), (size_t)found, 0, 64, s));
+                CUDA_TRY(d_uniq.alloc(found * 8));
+                CUDA_TRY(d_nsel.alloc(8));
+                size_t tb2 = 0;
+                CUDA_TRY(cub::DeviceSelect::Unique(nullptr, tb2, d_sorted.as<unsigned long long>(), d_uniq.as<unsigned long long>(), d_nsel.as<unsigned long long>(), (size_t)found, s));
+                if (tb2 > tb) CUDA_TRY(d_tmp2.alloc(tb2));
+                CUDA_TRY(cub::DeviceSelect::Unique(d_tmp2.p, tb2, d_sorted.as<unsigned long long>(), d_uniq.as<unsigned long long>(), d_nsel.as<unsigned long long>(), (size_t)found, s));
+                CUDA_TRY(cudaEventRecord(ev.b, s));
+                unsigned long long nu = 0;
+                CUDA_TRY(cudaMemcpyAsync(&nu, d_nsel.p, 8, cudaMemcpyDeviceToHost, s));
+                CUDA_TRY(cudaStreamSynchronize(s));
+                d->d_keys = (unsigned long long*)d_uniq.release();
+                found = nu;
+            } else {
+                CUDA_TRY(cudaEventRecord(ev.b, s));
+                CUDA_TRY(cudaStreamSynchronize(s));
+            }
+        } else {
+            const uint32_t n_tiles = (n + kPairTile - 1) / kPairTile;
+            const unsigned long long n_blocks = (unsigned long long)n_tiles * (n_tiles + 1) / 2;
+            if (n_blocks > 0x7FFFFFFFull) { dcb_set_error("dcb_umi_pairs: too many UMIs for an all-pairs sweep (%u)", n); return DCB_EUNSUPPORTED; }
+            unsigned long long capacity = std::max<unsigned long long>(1ull << 20, 8ull * n);
+            for (int attempt = 0; attempt < 2; attempt++) {
+                CUDA_TRY(d_raw.alloc(capacity * 8));
+                CUDA_TRY(cudaMemsetAsync(d_count.p, 0, 8, s));
+                CUDA_TRY(cudaEventRecord(ev.a, s));
+                dcb_umi_pairs_kernel<<<(unsigned)n_blocks, kPairTile, 0, s>>>(d_codes.as<uint64_t>(), n, max_edits, n_tiles,
+                                                                              d_raw.as<unsigned long long>(), capacity,
+                                                                              d_count.as<unsigned long long>());
+                CUDA_TRY(cudaGetLastError());
+                CUDA_TRY(cudaEventRecord(ev.b, s));
+                CUDA_TRY(cudaMemcpyAsync(&found, d_count.p, 8, cudaMemcpyDeviceToHost, s));
+                CUDA_TRY(cudaStreamSynchronize(s));
+                if (found <= capacity) break;
+                capacity = found;      // the list did not fit: size it exactly and sweep again
+            }
+            if (found) {
+                DevMem d_sorted, d_tmp;
+                CUDA_TRY(d_sorted.alloc(found * 8));
+                size_t tmp_bytes = 0;
+                CUDA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_raw.as<unsigned long long>(), d_sorted.as<unsigned long long>(), (size_t)found, 0, 64, s));
+                CUDA_TRY(d_tmp.alloc(tmp_bytes));
+                CUDA_TRY(cub::DeviceRadixSort::SortKeys(d_tmp.p, tmp_bytes, d_raw.as<unsigned long long>(), d_sorted.as<unsigned long long>(), (size_t)found, 0, 64, s));
+                CUDA_TRY(cudaStreamSynchronize(s));
+                d->d_keys = (unsigned long long*)d_sorted.release();
+            }
         }
         float ms = 0.f;
-        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventElapsedTime(&ms, ev.a, ev.b);
         d->last_ms = ms;
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
-        cudaFree(d_codes); cudaFree(d_count);
-        if (found) {
-            unsigned long long* d_sorted = nullptr;
-            CUDA_TRY(cudaMalloc((void**)&d_sorted, found * 8));
-            size_t tmp_bytes = 0;
-            CUDA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_raw, d_sorted, (size_t)found, 0, 64, s));
-            void* d_tmp = nullptr;
-            CUDA_TRY(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 16));
-            CUDA_TRY(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_raw, d_sorted, (size_t)found, 0, 64, s));
-            CUDA_TRY(cudaStreamSynchronize(s));
-            cudaFree(d_tmp);
-            d->d_keys = d_sorted;
-        }
-        cudaFree(d_raw);
         d->n_keys = found;
     }
     *n_pairs = d->n_keys;
@@ -231,43 +415,38 @@ int dcb_lev_leq(dcb_dist* d, const uint8_t* symbols, const uint64_t* off, const 
         if (len[i] > 512) { dcb_set_error("dcb_lev_leq: sequence %u has %u symbols (limit 512)", i, len[i]); return DCB_EUNSUPPORTED; }
         total = std::max<uint64_t>(total, off[i] + len[i]);
     }
-    for (uint64_t t = 0; t < total; t++)
-        if (symbols[t] > 7) { dcb_set_error("dcb_lev_leq: symbol code %u at %llu (codes are 0..7)", symbols[t], (unsigned long long)t); return DCB_EINVAL; }
-    for (uint64_t t = 0; t < n_pairs; t++)
-        if (a[t] >= n_seqs || b[t] >= n_seqs) { dcb_set_error("dcb_lev_leq: pair %llu names a sequence out of range", (unsigned long long)t); return DCB_EINVAL; }
-    uint8_t *d_sym = nullptr, *d_ver = nullptr;
-    uint64_t* d_off = nullptr;
-    uint32_t *d_len = nullptr, *d_a = nullptr, *d_b = nullptr;
-    CUDA_TRY(cudaMalloc((void**)&d_sym, total + 16));
-    CUDA_TRY(cudaMalloc((void**)&d_off, (size_t)n_seqs * 8));
-    CUDA_TRY(cudaMalloc((void**)&d_len, (size_t)n_seqs * 4));
-    CUDA_TRY(cudaMalloc((void**)&d_a, n_pairs * 4));
-    CUDA_TRY(cudaMalloc((void**)&d_b, n_pairs * 4));
-    CUDA_TRY(cudaMalloc((void**)&d_ver, n_pairs));
-    CUDA_TRY(cudaMemcpyAsync(d_sym, symbols, total, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(d_off, off, (size_t)n_seqs * 8, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(d_len, len, (size_t)n_seqs * 4, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(d_a, a, n_pairs * 4, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(d_b, b, n_pairs * 4, cudaMemcpyHostToDevice, s));
+    // buffers are kept between calls (the grouping of read_in_data calls this once per round); symbol codes and pair
+    // indices are checked by the kernel itself (a flag comes back), not by host loops over every symbol and pair
+    CUDA_TRY(d->sym.ensure(total + 16)); CUDA_TRY(d->off.ensure((size_t)n_seqs * 8)); CUDA_TRY(d->len.ensure((size_t)n_seqs * 4));
+    CUDA_TRY(d->a.ensure(n_pairs * 4)); CUDA_TRY(d->b.ensure(n_pairs * 4)); CUDA_TRY(d->ver.ensure(n_pairs)); CUDA_TRY(d->flag.ensure(16));
+    CUDA_TRY(cudaMemsetAsync(d->flag.p, 0, 16, s));
+    CUDA_TRY(cudaMemcpyAsync(d->sym.p, symbols, total, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d->off.p, off, (size_t)n_seqs * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d->len.p, len, (size_t)n_seqs * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d->a.p, a, n_pairs * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d->b.p, b, n_pairs * 4, cudaMemcpyHostToDevice, s));
     const unsigned long long blocks = (n_pairs + 127) / 128;
-    cudaEvent_t e0, e1;
-    CUDA_TRY(cudaEventCreate(&e0));
-    CUDA_TRY(cudaEventCreate(&e1));
-    CUDA_TRY(cudaEventRecord(e0, s));
-    dcb_lev_leq_kernel<<<(unsigned)blocks, 128, 0, s>>>(d_sym, d_off, d_len, d_a, d_b, n_pairs, frac, d_ver);
+    Events ev;
+    CUDA_TRY(cudaEventCreate(&ev.a));
+    CUDA_TRY(cudaEventCreate(&ev.b));
+    CUDA_TRY(cudaEventRecord(ev.a, s));
+    dcb_lev_leq_kernel<<<(unsigned)blocks, 128, 0, s>>>((const uint8_t*)d->sym.p, (const uint64_t*)d->off.p, (const uint32_t*)d->len.p,
+                                                        (const uint32_t*)d->a.p, (const uint32_t*)d->b.p, n_pairs, n_seqs, frac,
+                                                        (uint8_t*)d->ver.p, (uint32_t*)d->flag.p);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(e1, s));
-    CUDA_TRY(cudaMemcpyAsync(verdict, d_ver, n_pairs, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaEventRecord(ev.b, s));
+    uint32_t flag[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpyAsync(verdict, d->ver.p, n_pairs, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(flag, d->flag.p, 16, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
-    {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) d->last_ms = ms;   // kernel time of this call (dcb_dist_last_ms)
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
-    }
-    cudaFree(d_sym); cudaFree(d_off); cudaFree(d_len); cudaFree(d_a); cudaFree(d_b); cudaFree(d_ver);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) d->last_ms = ms;   // kernel time of this call (dcb_dist_last_ms)
+    if (flag[0]) { dcb_set_error("dcb_lev_leq: pair %u names a sequence out of range", flag[1]); return DCB_EINVAL; }
+    if (flag[2]) { dcb_set_error("dcb_lev_leq: a symbol code above 7 in a sequence of pair %u (codes are 0..7)", flag[3]); return DCB_EINVAL; }
     return DCB_OK;
 }
+
+const char* dcb_dist_last_method(const dcb_dist* d) { return d ? d->last_method : ""; }
 
 int dcb_dist_last_ms(dcb_dist* d, double* ms) {
     if (!d || !ms) return DCB_EINVAL;

@@ -279,8 +279,13 @@ int dcb_umi_pairs(dcb_dist*, const uint64_t* codes, uint32_t n, int max_edits, u
  * alphabet), sequence i at symbols[off[i] .. off[i] + len[i]), len <= 512. */
 int dcb_lev_leq(dcb_dist*, const uint8_t* symbols, const uint64_t* off, const uint32_t* len, uint32_t n_seqs,
                 const uint32_t* a, const uint32_t* b, uint64_t n_pairs, double frac, uint8_t* verdict);
-/* Device time of the pair-search kernel of the last dcb_umi_pairs (CUDA events). */
+/* Device time of the last dcb_umi_pairs (pair search, incl. its sorts on the deletion-neighbourhood path) or
+   dcb_lev_leq kernel (CUDA events). */
 int dcb_dist_last_ms(dcb_dist*, double* ms);
+/* How the last dcb_umi_pairs searched: "deletion neighbourhoods" (max_edits <= 2 and a long list: what symdel does,
+   collapse.py:735-740) or "all pairs" (short lists, max_edits > 2).  The environment variable DCB_UMI_SYMDEL_MIN moves
+   the switch-over (default 4096 UMIs). */
+const char* dcb_dist_last_method(const dcb_dist*);
 
 /* ---------------------------------------------------------------------------------------------
  * Synthetic workload generator: deterministic in (seed, read index).

@@ -96,10 +96,89 @@ def test_umi_pairs_vs_oracle(dist, n, alphabet, length, k):
     assert np.all(np.diff(key) > 0)   # sorted row-major, no duplicates
 
 
-def test_umi_pairs_matches_recorded_runs(dist, collapse_cases):
-    for case in collapse_cases["cases"]:
-        row, col = dist.umi_pairs(_lib.encode_umis(case["umis"]), case["args"]["bcthreshold"])
-        assert [[int(i), int(j)] for i, j in zip(row, col)] == case["pairs"]
+def test_umi_pairs_matches_recorded_runs(dist, collapse_cases, monkeypatch):
+    """The pair lists symdel returned inside the unmodified reference (collapse.py:735-742), through both forms of the
+    search: all pairs, and deletion neighbourhoods forced for these short lists."""
+    for force in ("1000000000", "0"):
+        monkeypatch.setenv("DCB_UMI_SYMDEL_MIN", force)
+        for case in collapse_cases["cases"]:
+            k = case["args"]["bcthreshold"]
+            row, col = dist.umi_pairs(_lib.encode_umis(case["umis"]), k)
+            assert [[int(i), int(j)] for i, j in zip(row, col)] == case["pairs"]
+            if len(case["umis"]) > 1:
+                assert dist.last_method() == ("deletion neighbourhoods" if force == "0" and 1 <= k <= 2 else "all pairs")
+
+
+@pytest.mark.parametrize("n,alphabet,length,k", [(3000, "ACGT", 6, 2), (3000, "AC", 12, 2), (2500, "ACGTNSL", 12, 1), (2000, "ACG", 17, 2),
+                                                  (4000, "ACGT", 8, 1), (40000, "ACGT", 12, 2)])
+def test_umi_pairs_deletion_neighbourhoods_equal_all_pairs(dist, monkeypatch, n, alphabet, length, k):
+    """Both forms on the same lists (mixed lengths, the padded-barcode alphabet, dense and sparse): identical output."""
+    rng = random.Random(1000 * n + k)
+    seen, umis = set(), []
+    while len(umis) < n:
+        L = length if rng.random() < 0.8 else max(1, length - rng.randrange(0, 3))
+        u = "".join(rng.choice(alphabet) for _ in range(L))
+        if u not in seen or rng.random() < 0.02:        # a few duplicates too (distance 0)
+            seen.add(u); umis.append(u)
+    codes = _lib.encode_umis(umis)
+    monkeypatch.setenv("DCB_UMI_SYMDEL_MIN", "1000000000")
+    r0, c0 = dist.umi_pairs(codes, k)
+    assert dist.last_method() == "all pairs"
+    monkeypatch.setenv("DCB_UMI_SYMDEL_MIN", "0")
+    r1, c1 = dist.umi_pairs(codes, k)
+    assert dist.last_method() == "deletion neighbourhoods"
+    assert len(r0) > 0 and np.array_equal(r0, r1) and np.array_equal(c0, c1)
+
+
+def test_umi_pairs_two_million(dist):
+    """BASELINE configs[3] scale: 2 M distinct random 12-nt UMIs, two edits -- ~10^8 pairs.  Every sampled pair is real,
+    planted neighbours (substitution, deletion + insertion, two substitutions) are all found, the list is sorted and unique."""
+    rng = np.random.default_rng(20260004)
+    n = 2_000_000
+    vals = np.unique(rng.integers(0, 4 ** 12, size=int(n * 1.1), dtype=np.uint64))[:n]
+    rng.shuffle(vals)
+    sym = np.stack([(vals >> np.uint64(2 * k)) & np.uint64(3) for k in range(12)], axis=1)
+    codes = np.full(n, 12 << 58, dtype=np.uint64)
+    for k in range(12):
+        codes |= sym[:, k] << np.uint64(3 * k)
+    row, col = dist.umi_pairs(codes, 2)
+    assert dist.last_method() == "deletion neighbourhoods"
+    assert len(row) > 10 * n and np.all(row < col)
+    key = row.astype(np.uint64) * np.uint64(1 << 32) + col.astype(np.uint64)
+    assert np.all(key[1:] > key[:-1])
+    letters = np.array(list("ACGT"))
+
+    def s(i):
+        return "".join(letters[sym[i].astype(int)])
+    for t in rng.integers(0, len(row), size=300):
+        assert CO.levenshtein(s(int(row[t])), s(int(col[t]))) <= 2
+    # exhaustive for a few UMIs: their neighbours by brute force over the whole list
+    where = {int(v): i for i, v in enumerate(vals.tolist())}
+    for i in rng.integers(0, n, size=3):
+        a = s(int(i))
+        want = set()
+        # every string within two edits of a that is in the list (generate by two rounds of single edits)
+        def edits(x):
+            out = set()
+            for p in range(len(x) + 1):
+                for ch in "ACGT":
+                    out.add(x[:p] + ch + x[p:])
+                if p < len(x):
+                    out.add(x[:p] + x[p + 1:])
+                    for ch in "ACGT":
+                        out.add(x[:p] + ch + x[p + 1:])
+            return out
+        near = set()
+        for y in edits(a):
+            near |= edits(y)
+        for y in near:
+            if len(y) == 12 and y != a:
+                v = sum("ACGT".index(ch) << (2 * k) for k, ch in enumerate(y))
+                if v in where:
+                    want.add(where[v])
+        lo, hi = np.searchsorted(row, i), np.searchsorted(row, i, side="right")
+        got = set(col[lo:hi].tolist()) | set(row[col == i].tolist())
+        assert got == want, (int(i), len(got), len(want))
 
 
 def test_umi_pairs_large_properties(dist):
