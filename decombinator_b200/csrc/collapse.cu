@@ -123,53 +123,114 @@ dcb_umi_variants_kernel(const uint64_t* __restrict__ codes, const uint64_t* __re
                 }
         }
 }
-// Entry e looks at the entries behind it in its run of equal variants: every pair of UMIs of a run is a candidate.
+// Do two UMIs of EQUAL length share a variant with one deletion each (a - p == b - q)?  Then they agree on a prefix of
+// p symbols and a suffix behind q, and between the two one is the other shifted by a symbol.  The longest common prefix
+// and suffix give the smallest window that has to match under the shift.
+__device__ __forceinline__ bool umi_share_one_deletion(uint64_t a, uint64_t b) {
+    const int L = umi_len(a);
+    const uint64_t body = (1ull << (3 * L)) - 1ull;
+    const uint64_t x = (a ^ b) & body;
+    if (!x) return true;
+    const int pre = (__ffsll((long long)x) - 1) / 3;                 // symbols before the first difference
+    const int suf = (__clzll((long long)x) - (64 - 3 * L)) / 3;      // symbols behind the last difference
+    const int q = L - 1 - suf;                                       // last differing symbol
+    if (q <= pre) return true;                                       // one substitution: delete it in both
+    // a - pre == b - q  <=>  a[pre+1 .. q] == b[pre .. q-1];   or the mirror image
+    const uint64_t win = ((1ull << (3 * (q - pre))) - 1ull) << (3 * pre);
+    return ((((a >> 3) ^ b) & win) == 0ull) || ((((b >> 3) ^ a) & win) == 0ull);
+}
+// Block B owns entries [256 B, 256 B + 256) of the sorted (variant, UMI) list; thread t owns one entry and tests it
+// against the entries BEHIND it in its run of equal variants.  The partners are staged tile by tile in shared memory
+// (variant, UMI, code: the code gathered once per entry instead of once per pair), so the inner loop reads shared
+// memory only.  A pair within max_edits edits is emitted from the run of a two-deletion variant only when the two UMIs
+// share no one-deletion variant (they are then emitted from that run): without this rule a pair one substitution apart
+// would be emitted 12 times for 12-symbol UMIs and the output would be 15 times the number of distinct pairs.
 __global__ void __launch_bounds__(256)
 dcb_umi_runs_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ ids, uint64_t n_entries,
                     const uint64_t* __restrict__ codes, int k, unsigned long long* __restrict__ out, unsigned long long cap,
                     unsigned long long* __restrict__ count) {
-    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = e < n_entries;
-    const uint64_t key = live ? keys[e] : 0ull;
+    __shared__ uint64_t s_key[256], s_code[256];
+    __shared__ uint32_t s_id[256];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint64_t e = (uint64_t)blockIdx.x * 256 + tid;
+    bool live = e < n_entries;
+    const uint64_t key = live ? keys[e] : ~0ull;
     const uint32_t ia = live ? ids[e] : 0u;
     const uint64_t ca = live ? codes[ia] : 0ull;
-    const int lane = threadIdx.x & 31;
+    // Deleting either symbol of a repeat gives the same variant, so a UMI can be listed several times under one
+    // variant.  The entries were generated in UMI order and the radix sort is stable: such copies are neighbours, and
+    // every copy but the first is skipped, as owner and as partner.
+    live = live && !(e > 0 && keys[e - 1] == key && ids[e - 1] == ia);
+    const bool two_del = live && umi_len(key) + 2 == umi_len(ca);
     UmiPattern pat;
     bool have_pat = false;
-    uint64_t f = e + 1;
-    bool more = live && f < n_entries && keys[f] == key;
-    while (__any_sync(0xFFFFFFFFu, more)) {
-        bool hit = false;
-        uint32_t ib = 0;
-        if (more) {
-            ib = ids[f];
-            if (ib != ia) {
-                const uint64_t cb = codes[ib];
-                if (umi_len(ca) == umi_len(cb)) {          // Hamming distance <= k settles it at once
-                    const uint64_t x = (ca ^ cb) & ((1ull << 58) - 1ull);
-                    hit = __popcll((x | (x >> 1) | (x >> 2)) & 0x0249249249249249ull) <= k;
-                }
-                if (!hit && umi_may_be_within(ca, cb, k)) {
-                    if (!have_pat) { umi_pattern(ca, pat); have_pat = true; }
-                    hit = umi_distance(pat, cb) <= k;
-                }
-            }
-            f++;
-            more = f < n_entries && keys[f] == key;
+    for (uint64_t tile = blockIdx.x; tile * 256 < n_entries; tile++) {
+        const uint64_t base = tile * 256;
+        __syncthreads();
+        {
+            const uint64_t f = base + tid;
+            const bool in = f < n_entries;
+            const uint64_t kf = in ? keys[f] : ~0ull - 1ull;
+            const uint32_t id = in ? ids[f] : 0u;
+            const bool copy = in && f > 0 && keys[f - 1] == kf && ids[f - 1] == id;
+            s_key[tid] = kf;
+            s_id[tid] = copy ? 0xFFFFFFFFu : id;             // a repeated listing of the UMI in front of it: no partner
+            s_code[tid] = in ? codes[id] : 0ull;
         }
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
-        if (m) {
-            const int leader = __ffs(m) - 1;
-            unsigned long long base = 0;
-            if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(m));
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (hit) {
-                const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
-                if (slot < cap) out[slot] = ia < ib ? (((unsigned long long)ia << 32) | ib) : (((unsigned long long)ib << 32) | ia);
+        __syncthreads();
+        const bool need = live && (tile == blockIdx.x || s_key[0] == key);      // sorted: my run reaches this tile or it does not
+        if (!__syncthreads_or(need)) break;
+        int j = tile == blockIdx.x ? tid + 1 : 0;
+        bool more = need && j < 256 && s_key[j] == key;
+        while (__any_sync(0xFFFFFFFFu, more)) {
+            bool hit = false;
+            uint32_t ib = 0;
+            if (more) {
+                ib = s_id[j];
+                const uint64_t cb = s_code[j];
+                if (ib != ia && ib != 0xFFFFFFFFu) {
+                    const bool same_len = umi_len(ca) == umi_len(cb);
+                    if (same_len) {          // Hamming distance <= k settles it at once
+                        const uint64_t x = (ca ^ cb) & ((1ull << 58) - 1ull);
+                        hit = __popcll((x | (x >> 1) | (x >> 2)) & 0x0249249249249249ull) <= k;
+                    }
+                    if (!hit && umi_may_be_within(ca, cb, k)) {
+                        if (!have_pat) { umi_pattern(ca, pat); have_pat = true; }
+                        hit = umi_distance(pat, cb) <= k;
+                    }
+                    if (hit && two_del && same_len && umi_share_one_deletion(ca, cb)) hit = false;   // emitted from that run
+                }
+                j++;
+                more = j < 256 && s_key[j] == key;
+            }
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                unsigned long long at = 0;
+                if (lane == leader) at = atomicAdd(count, (unsigned long long)__popc(m));
+                at = __shfl_sync(0xFFFFFFFFu, at, leader);
+                if (hit) {
+                    const unsigned long long slot = at + __popc(m & ((1u << lane) - 1u));
+                    if (slot < cap) out[slot] = ia < ib ? (((unsigned long long)ia << 32) | ib) : (((unsigned long long)ib << 32) | ia);
+                }
             }
         }
     }
 }
+
+// DCB_UMI_TRACE=1: phase times of the pair search on stderr (tuning aid; synchronises the stream at every mark)
+struct PhaseTrace {
+    bool on; cudaStream_t s; cudaEvent_t last = nullptr;
+    PhaseTrace(cudaStream_t st) : on(std::getenv("DCB_UMI_TRACE") != nullptr), s(st) { if (on) { cudaEventCreate(&last); cudaEventRecord(last, s); } }
+    ~PhaseTrace() { if (last) cudaEventDestroy(last); }
+    void mark(const char* what, double count = 0) {
+        if (!on) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); cudaEventSynchronize(e);
+        float ms = 0.f; cudaEventElapsedTime(&ms, last, e);
+        std::fprintf(stderr, "[umi_pairs] %-28s %9.3f ms  %.4g\n", what, ms, count);
+        cudaEventDestroy(last); last = e;
+    }
+};
 
 // device memory that is released on every way out of a function
 struct DevMem {
@@ -311,16 +372,19 @@ int dcb_umi_pairs(dcb_dist* d, const uint64_t* codes, uint32_t n, int max_edits,
             CUDA_TRY(v_in.alloc(total * 4)); CUDA_TRY(v_out.alloc(total * 4));
             CUDA_TRY(cudaMemcpyAsync(d_first.p, first.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, s));
             CUDA_TRY(cudaEventRecord(ev.a, s));
+            PhaseTrace tr(s);
             dcb_umi_variants_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_codes.as<uint64_t>(), d_first.as<uint64_t>(), n, max_edits,
                                                                     k_in.as<uint64_t>(), v_in.as<uint32_t>());
             CUDA_TRY(cudaGetLastError());
+            tr.mark("variants", (double)total);
             size_t tmp_bytes = 0;
             CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in.as<uint64_t>(), k_out.as<uint64_t>(), v_in.as<uint32_t>(),
                                                      v_out.as<uint32_t>(), (size_t)total, 0, 64, s));
             CUDA_TRY(d_tmp.alloc(tmp_bytes));
             CUDA_TRY(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, k_in.as<uint64_t>(), k_out.as<uint64_t>(), v_in.as<uint32_t>(),
                                                      v_out.as<uint32_t>(), (size_t)total, 0, 64, s));
-            unsigned long long capacity = std::max<unsigned long long>(1ull << 22, 64ull * n);
+            tr.mark("sort entries", (double)total);
+            unsigned long long capacity = std::max<unsigned long long>(1ull << 22, 96ull * n);
             for (int attempt = 0; attempt < 2; attempt++) {
                 CUDA_TRY(d_raw.alloc(capacity * 8));
                 CUDA_TRY(cudaMemsetAsync(d_count.p, 0, 8, s));
@@ -331,6 +395,7 @@ int dcb_umi_pairs(dcb_dist* d, const uint64_t* codes, uint32_t n, int max_edits,
                 CUDA_TRY(cudaGetLastError());
                 CUDA_TRY(cudaMemcpyAsync(&found, d_count.p, 8, cudaMemcpyDeviceToHost, s));
                 CUDA_TRY(cudaStreamSynchronize(s));
+                tr.mark("verify runs", (double)found);
                 if (found <= capacity) break;
                 capacity = found;                  // the list did not fit: size it exactly and walk the runs again
             }
@@ -348,6 +413,7 @@ int dcb_umi_pairs(dcb_dist* d, const uint64_t* codes, uint32_t n, int max_edits,
                 CUDA_TRY(cub::DeviceSelect::Unique(nullptr, tb2, d_sorted.as<unsigned long long>(), d_uniq.as<unsigned long long>(), d_nsel.as<unsigned long long>(), (size_t)found, s));
                 if (tb2 > tb) CUDA_TRY(d_tmp2.alloc(tb2));
                 CUDA_TRY(cub::DeviceSelect::Unique(d_tmp2.p, tb2, d_sorted.as<unsigned long long>(), d_uniq.as<unsigned long long>(), d_nsel.as<unsigned long long>(), (size_t)found, s));
+                tr.mark("sort + unique pairs", (double)found);
                 CUDA_TRY(cudaEventRecord(ev.b, s));
                 unsigned long long nu = 0;
                 CUDA_TRY(cudaMemcpyAsync(&nu, d_nsel.p, 8, cudaMemcpyDeviceToHost, s));
