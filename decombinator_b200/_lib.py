@@ -44,6 +44,15 @@ class CParams(ctypes.Structure):
                 ("force_general", ctypes.c_int32)]
 
 
+class CBcParams(ctypes.Structure):
+    _fields_ = [("oligo", ctypes.c_int32), ("allow_ns", ctypes.c_int32), ("min_q", ctypes.c_int32), ("max_below", ctypes.c_int32),
+                ("avg_q", ctypes.c_double)]
+
+
+BC_OK, BC_FAIL_N, BC_FAIL_NOSPACER, BC_FAIL_NOT2, BC_FAIL_N1SHORT, BC_FAIL_N1LONG, BC_FAIL_N2END, BC_FAIL_QUALITY, BC_HOST = 0, 1, 2, 3, 4, 5, 6, 7, 255
+OLIGOS_ON_DEVICE = {"m13": 0, "i8": 1}
+
+
 class CSynthParams(ctypes.Structure):
     _fields_ = [("seed", ctypes.c_uint64), ("read_len", ctypes.c_uint32), ("read2_len", ctypes.c_uint32),
                 ("sub_rate", ctypes.c_uint32), ("n_rate", ctypes.c_uint32), ("junk_rate", ctypes.c_uint32),
@@ -115,6 +124,7 @@ def lib():
     L.dcb_dist_destroy.argtypes = [vp]
     L.dcb_umi_pairs.argtypes = [vp, vp, u32, i32, vp, u64, ctypes.POINTER(u64)]
     L.dcb_lev_leq.argtypes = [vp, vp, vp, vp, u32, vp, vp, u64, ctypes.c_double, vp]
+    L.dcb_barcodes.argtypes = [vp, vp, vp, vp, vp, vp, vp, u64, ctypes.POINTER(CBcParams), vp, vp, vp]
     L.dcb_dist_last_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     L.dcb_dist_last_method.argtypes = [vp]
     L.dcb_dist_last_method.restype = ctypes.c_char_p
@@ -692,6 +702,30 @@ class Dist:
         _check(lib().dcb_lev_leq(self._h, symbols.ctypes.data, off.ctypes.data, length.ctypes.data, len(length),
                                  a.ctypes.data, b.ctypes.data, len(a), float(frac), out.ctypes.data), "dcb_lev_leq")
         return out.astype(bool)
+
+    def barcodes(self, bcs, quals, oligo, allow_ns, min_q, max_below, avg_q):
+        """dcb_barcodes over lists of barcode-region strings and their quality strings.
+        -> (status uint8, n1len uint8, code uint64) arrays; status BC_HOST rows are for the reference's fuzzy spacer search."""
+        n = len(bcs)
+        status, n1, code = np.full(n, BC_HOST, dtype=np.uint8), np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.uint64)
+        if n == 0:
+            return status, n1, code
+        try:
+            bbuf = np.frombuffer("".join(bcs).encode("ascii") + b"\0", dtype=np.uint8)
+            qbuf = np.frombuffer("".join(quals).encode("ascii") + b"\0", dtype=np.uint8)
+        except UnicodeEncodeError:
+            return status, n1, code                      # non-ASCII text: every row takes the host path
+        bl = np.fromiter((len(x) for x in bcs), dtype=np.uint32, count=n)
+        ql = np.fromiter((len(x) for x in quals), dtype=np.uint32, count=n)
+        bo = np.zeros(n, dtype=np.uint64)
+        qo = np.zeros(n, dtype=np.uint64)
+        if n > 1:
+            np.cumsum(bl[:-1], dtype=np.uint64, out=bo[1:])
+            np.cumsum(ql[:-1], dtype=np.uint64, out=qo[1:])
+        prm = CBcParams(int(oligo), int(bool(allow_ns)), int(min_q), int(max_below), float(avg_q))
+        _check(lib().dcb_barcodes(self._h, bbuf.ctypes.data, bo.ctypes.data, bl.ctypes.data, qbuf.ctypes.data, qo.ctypes.data,
+                                  ql.ctypes.data, n, ctypes.byref(prm), status.ctypes.data, n1.ctypes.data, code.ctypes.data), "dcb_barcodes")
+        return status, n1, code
 
     def last_ms(self):
         ms = ctypes.c_double()

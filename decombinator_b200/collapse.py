@@ -357,29 +357,69 @@ class _BarcodeMachine:
         return None
 
 
+_BC_SYMBOLS = np.frombuffer(b"ACGTNSL?", dtype=np.uint8)
+
+
+def _device_barcodes(rows, inputargs, qp):
+    """dcb_barcodes over the barcode regions of all rows at once: -> (status, n1len, barcode strings) or None when this
+    oligo / option has no device path.  Rows whose spacers are not found exactly come back with status BC_HOST."""
+    name = inputargs["oligo"].lower()
+    if name not in _lib.OLIGOS_ON_DEVICE or inputargs["sampling_analysis"] or not rows:
+        return None
+    status, n1, code = _gpu().barcodes([r[8] for r in rows], [r[9] for r in rows], _lib.OLIGOS_ON_DEVICE[name],
+                                       inputargs["allowNs"] != False, qp[0], qp[1], qp[2])  # noqa: E712
+    sym = (code[:, None] >> (np.uint64(3) * np.arange(12, dtype=np.uint64))[None, :]) & np.uint64(7)
+    text = _BC_SYMBOLS[sym.astype(np.intp)].tobytes().decode("ascii")          # 12 characters per row, back to back
+    # the reference's counters for the rows decided on the device (collapse.py:241-278, 388-422, 546-553)
+    st = np.bincount(status, minlength=256)
+    for key, k in (("getbarcode_fail_N", st[_lib.BC_FAIL_N]), ("getbarcode_fail_nospacerfound", st[_lib.BC_FAIL_NOSPACER]),
+                   ("getbarcode_fail_not2spacersfound", st[_lib.BC_FAIL_NOT2]), ("getbarcode_fail_n1tooshort", st[_lib.BC_FAIL_N1SHORT]),
+                   ("getbarcode_fail_n1toolong", st[_lib.BC_FAIL_N1LONG]), ("getbarcode_fail_n2pastend", st[_lib.BC_FAIL_N2END]),
+                   ("readdata_fail_no_bclocs", int(st[_lib.BC_FAIL_N:_lib.BC_FAIL_N2END + 1].sum())),
+                   ("readdata_fail_low_barcode_quality", st[_lib.BC_FAIL_QUALITY])):
+        if k:
+            counts[key] += int(k)
+    placed = (status == _lib.BC_OK) | (status == _lib.BC_FAIL_QUALITY)         # both spacers found exactly, N1 / N2 in range
+    for key, k in (("getbarcode_pass_exactmatch", placed.sum()), ("getbarcode_pass_other", (placed & (n1 == 6)).sum()),
+                   ("readdata_short_barcode", (placed & (n1 < 6)).sum()), ("readdata_long_barcode", (placed & (n1 > 6)).sum())):
+        if k:
+            counts[key] += int(k)
+    return status, text
+
+
 def _filter_rows(data, inputargs, barcode_quality_parameters, dont_count, from_file, first_index=0):
     """The per-row part of read_in_data (collapse.py:523-593): barcode location, quality and length filters.
+
+    The barcode of every row is located, assembled and quality-checked by ONE kernel launch (dcb_barcodes: exact spacer
+    search); only the rows it hands back -- spacers not found exactly, so the reference's fuzzy regular expressions
+    decide -- go through get_barcode_positions / set_barcode / check_umi_quality on the host.
 
     -> ([(global row index, barcode, seq, dcretc), ...] for the rows that survive, Counter of str(dcr), rows seen).
     Rows are independent here, so a multi-GPU run calls this on each rank's shard (parallel.py)."""
     t0 = time.time()
+    rows = [line.rstrip("\n").split(", ") for line in data] if from_file else (data if isinstance(data, list) else list(data))
+    dev = _device_barcodes(rows, inputargs, barcode_quality_parameters)
     kept = []
     input_dcr_counts = coll.Counter()
     lcount = -1
-    for lcount, line in enumerate(data):
-        if from_file:
-            line = line.rstrip("\n").split(", ")
+    for lcount, line in enumerate(rows):
         if lcount % 50000 == 0 and lcount != 0 and not dont_count:
             print("   Read in", lcount, "lines... ", round(time.time() - t0, 2), "seconds")
         counts["readdata_input_dcrs"] += 1
-        bc_locs = get_barcode_positions(line[8], inputargs, counts)
-        if not bc_locs:
-            counts["readdata_fail_no_bclocs"] += 1
-            continue
-        barcode, barcode_qualstring = set_barcode(line, bc_locs, inputargs)
-        if check_umi_quality(barcode_qualstring, barcode_quality_parameters):
-            counts["readdata_fail_low_barcode_quality"] += 1
-            continue
+        st = dev[0][lcount] if dev is not None else _lib.BC_HOST
+        if st == _lib.BC_HOST:
+            bc_locs = get_barcode_positions(line[8], inputargs, counts)
+            if not bc_locs:
+                counts["readdata_fail_no_bclocs"] += 1
+                continue
+            barcode, barcode_qualstring = set_barcode(line, bc_locs, inputargs)
+            if check_umi_quality(barcode_qualstring, barcode_quality_parameters):
+                counts["readdata_fail_low_barcode_quality"] += 1
+                continue
+        elif st != _lib.BC_OK:
+            continue                                  # rejected on the device, counted in _device_barcodes
+        else:
+            barcode, barcode_qualstring = dev[1][12 * lcount:12 * lcount + 12], None
         dcr = line[:5]
         input_dcr_counts[str(dcr)] += 1
         seq = line[6]

@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #define CUDA_TRY(expr)                                                                          \
@@ -281,6 +282,81 @@ dcb_lev_leq_kernel(const uint8_t* __restrict__ sym, const uint64_t* __restrict__
     verdict[t] = ((double)d <= (double)la * frac) ? 1 : 0;
 }
 
+// ---- barcode extraction ------------------------------------------------------------------------
+// One thread per decombined row: the barcode region (R2[:bclength], field 8 of an .n12 row) and its quality string.
+// What collapse.py does per row before any grouping, for the two-spacer oligos (M13, I8):
+//   get_barcode_positions (collapse.py:367-479): an 'N' anywhere rejects the row (unless -N); spacer 1 is searched in
+//     bc[0 : 10 + len(spacer1)] and must be found exactly once, spacer 2 in bc[len(spacer1):] and must be found exactly once
+//     (regex.findall: leftmost, non-overlapping); N1 lies between the spacers, N2 is the six bases behind spacer 2; N1 of
+//     <= 3 or >= 9 bases and an N2 that runs past the end reject the row;
+//   set_barcode (:281-326): N1 + N2, a short N1 padded with 'S' (quality '?'), a long one cut to five bases + 'L';
+//   check_umi_quality (:340-352): more than `max_below` bases under `min_q`, or a mean under `avg_q`, rejects the row.
+// Only the EXACT spacer search is done here.  The reference escalates to fuzzy regular expressions ({1s<=2}, then
+// {2i+2d+1s<=2}) when an exact search finds nothing: such rows (a few percent) come back as DCB_BC_HOST and the host
+// runs the reference's own search on them; so do rows with symbols outside ACGTN or a quality string of another length.
+__device__ __forceinline__ int bc_find(const unsigned char* s, int from, int to, const char* pat, int plen) {   // first match in [from, to)
+    for (int p = from; p + plen <= to; p++) {
+        int k = 0;
+        while (k < plen && s[p + k] == (unsigned char)pat[k]) k++;
+        if (k == plen) return p;
+    }
+    return -1;
+}
+__device__ __forceinline__ int bc_count(const unsigned char* s, int from, int to, const char* pat, int plen, int& first) {
+    int n = 0;
+    first = -1;
+    for (int p = bc_find(s, from, to, pat, plen); p >= 0; p = bc_find(s, p + plen, to, pat, plen)) { if (!n) first = p; n++; }
+    return n;
+}
+struct BcParams { char sp1[32], sp2[32]; int len1, len2, allow_ns, min_q, max_below; double avg_q; };
+
+__global__ void __launch_bounds__(128)
+dcb_barcodes_kernel(const unsigned char* __restrict__ bc, const unsigned char* __restrict__ qual, const uint64_t* __restrict__ bc_off,
+                    const uint32_t* __restrict__ bc_len, const uint64_t* __restrict__ q_off, const uint32_t* __restrict__ q_len,
+                    uint64_t n, BcParams P, uint8_t* __restrict__ status, uint8_t* __restrict__ n1len, uint64_t* __restrict__ code) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned char* s = bc + bc_off[i];
+    const unsigned char* q = qual + q_off[i];
+    const int L = (int)bc_len[i];
+    status[i] = DCB_BC_HOST; n1len[i] = 0; code[i] = 0;
+    if (L > 250 || (int)q_len[i] != L) return;
+    bool has_n = false, odd = false;
+    for (int p = 0; p < L; p++) {
+        const unsigned char c = s[p];
+        has_n |= c == 'N';
+        odd |= !(c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'N');
+    }
+    if (has_n && !P.allow_ns) { status[i] = DCB_BC_FAIL_N; return; }                        // collapse.py:388-392
+    if (odd) return;
+    int w0, w1;
+    const int hi = L < 10 + P.len1 ? L : 10 + P.len1;
+    const int c1 = bc_count(s, 0, hi, P.sp1, P.len1, w0);                                   // :405-413
+    if (c1 == 0) return;                                                                    // the fuzzy searches decide
+    if (c1 != 1) { status[i] = DCB_BC_FAIL_NOSPACER; return; }
+    const int c2 = bc_count(s, P.len1, L, P.sp2, P.len2, w1);                               // :417-422
+    if (c2 == 0) return;
+    if (c2 != 1) { status[i] = DCB_BC_FAIL_NOT2; return; }
+    const int b1s = w0 + P.len1, b1e = w1, b2s = w1 + P.len2, b2e = b2s + 6, n1 = b1e - b1s;
+    if (n1 <= 3) { status[i] = DCB_BC_FAIL_N1SHORT; return; }                               // :241-254
+    if (n1 >= 9) { status[i] = DCB_BC_FAIL_N1LONG; return; }
+    if (b2e > L) { status[i] = DCB_BC_FAIL_N2END; return; }
+    n1len[i] = (uint8_t)n1;
+    // the 12 symbols (A C G T N S L = 0..6) and their qualities; a long N1 has no pad quality (11 values)
+    uint64_t cd = 12ull << 58;
+    int qsum = 0, qn = 0, below = 0, k = 0;
+    auto sym = [](unsigned char c) -> uint64_t { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 4; };
+    auto addq = [&](int v) { qsum += v; qn++; below += v < P.min_q; };
+    const int take1 = n1 > 6 ? 5 : n1;
+    for (int p = 0; p < take1; p++, k++) { cd |= sym(s[b1s + p]) << (3 * k); addq((int)q[b1s + p] - 33); }
+    if (n1 < 6) for (int p = n1; p < 6; p++, k++) { cd |= 5ull << (3 * k); addq('?' - 33); }   // 'S', quality '?'
+    if (n1 > 6) { cd |= 6ull << (3 * k); k++; }                                               // 'L'; "?" * (6 - n1) is empty
+    for (int p = 0; p < 6; p++, k++) { cd |= sym(s[b2s + p]) << (3 * k); addq((int)q[b2s + p] - 33); }
+    code[i] = cd;
+    const bool bad_q = below > P.max_below || (double)qsum / (double)qn < P.avg_q;            // :350-352
+    status[i] = bad_q ? DCB_BC_FAIL_QUALITY : DCB_BC_OK;
+}
+
 struct GrowBuf {            // grow-only device buffer kept between calls (dcb_lev_leq is called once per grouping round)
     void* p = nullptr;
     size_t cap = 0;
@@ -509,6 +585,54 @@ int dcb_lev_leq(dcb_dist* d, const uint8_t* symbols, const uint64_t* off, const 
     if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) d->last_ms = ms;   // kernel time of this call (dcb_dist_last_ms)
     if (flag[0]) { dcb_set_error("dcb_lev_leq: pair %u names a sequence out of range", flag[1]); return DCB_EINVAL; }
     if (flag[2]) { dcb_set_error("dcb_lev_leq: a symbol code above 7 in a sequence of pair %u (codes are 0..7)", flag[3]); return DCB_EINVAL; }
+    return DCB_OK;
+}
+
+int dcb_barcodes(dcb_dist* d, const char* bc_text, const uint64_t* bc_off, const uint32_t* bc_len, const char* q_text,
+                 const uint64_t* q_off, const uint32_t* q_len, uint64_t n, const dcb_bc_params* prm, uint8_t* status,
+                 uint8_t* n1len, uint64_t* code) {
+    if (!d || !prm || (n && (!bc_text || !bc_off || !bc_len || !q_text || !q_off || !q_len || !status || !n1len || !code))) {
+        dcb_set_error("dcb_barcodes: null argument");
+        return DCB_EINVAL;
+    }
+    if (n == 0) return DCB_OK;
+    BcParams P;
+    std::memset(&P, 0, sizeof(P));
+    const char *sp1, *sp2;
+    if (prm->oligo == DCB_OLIGO_M13) { sp1 = "GTCGTGACTGGGAAAACCCTGG"; sp2 = "GTCGTGAT"; }     // collapse.py:176-177
+    else if (prm->oligo == DCB_OLIGO_I8) { sp1 = "GTCGTGAT"; sp2 = "GTCGTGAT"; }
+    else { dcb_set_error("dcb_barcodes: oligo %d has no device path (M13 and I8 do)", prm->oligo); return DCB_EUNSUPPORTED; }
+    P.len1 = (int)std::strlen(sp1); P.len2 = (int)std::strlen(sp2);
+    std::memcpy(P.sp1, sp1, P.len1); std::memcpy(P.sp2, sp2, P.len2);
+    P.allow_ns = prm->allow_ns; P.min_q = prm->min_q; P.max_below = prm->max_below; P.avg_q = prm->avg_q;
+    CUDA_TRY(cudaSetDevice(d->device));
+    cudaStream_t s = d->stream;
+    uint64_t bc_bytes = 0, q_bytes = 0;
+    for (uint64_t i = 0; i < n; i++) { bc_bytes = std::max<uint64_t>(bc_bytes, bc_off[i] + bc_len[i]); q_bytes = std::max<uint64_t>(q_bytes, q_off[i] + q_len[i]); }
+    DevMem dbc, dq, dbo, dbl, dqo, dql, dst, dn1, dcd;
+    CUDA_TRY(dbc.alloc(bc_bytes + 16)); CUDA_TRY(dq.alloc(q_bytes + 16));
+    CUDA_TRY(dbo.alloc(n * 8)); CUDA_TRY(dbl.alloc(n * 4)); CUDA_TRY(dqo.alloc(n * 8)); CUDA_TRY(dql.alloc(n * 4));
+    CUDA_TRY(dst.alloc(n)); CUDA_TRY(dn1.alloc(n)); CUDA_TRY(dcd.alloc(n * 8));
+    CUDA_TRY(cudaMemcpyAsync(dbc.p, bc_text, bc_bytes, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(dq.p, q_text, q_bytes, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(dbo.p, bc_off, n * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(dbl.p, bc_len, n * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(dqo.p, q_off, n * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(dql.p, q_len, n * 4, cudaMemcpyHostToDevice, s));
+    Events ev;
+    CUDA_TRY(cudaEventCreate(&ev.a)); CUDA_TRY(cudaEventCreate(&ev.b));
+    CUDA_TRY(cudaEventRecord(ev.a, s));
+    dcb_barcodes_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(dbc.as<unsigned char>(), dq.as<unsigned char>(), dbo.as<uint64_t>(),
+                                                                   dbl.as<uint32_t>(), dqo.as<uint64_t>(), dql.as<uint32_t>(), n, P,
+                                                                   dst.as<uint8_t>(), dn1.as<uint8_t>(), dcd.as<uint64_t>());
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ev.b, s));
+    CUDA_TRY(cudaMemcpyAsync(status, dst.p, n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(n1len, dn1.p, n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(code, dcd.p, n * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) d->last_ms = ms;
     return DCB_OK;
 }
 

@@ -279,6 +279,30 @@ int dcb_umi_pairs(dcb_dist*, const uint64_t* codes, uint32_t n, int max_edits, u
  * alphabet), sequence i at symbols[off[i] .. off[i] + len[i]), len <= 512. */
 int dcb_lev_leq(dcb_dist*, const uint8_t* symbols, const uint64_t* off, const uint32_t* len, uint32_t n_seqs,
                 const uint32_t* a, const uint32_t* b, uint64_t n_pairs, double frac, uint8_t* verdict);
+/* Barcode extraction of the collapse step, per decombined row: replaces, for the two-spacer oligos M13 and I8 and rows whose
+ * spacers are found EXACTLY, get_barcode_positions (collapse.py:367-479), set_barcode (:281-326) and check_umi_quality
+ * (:340-352).  bc / q: the barcode region of the row (field 8 of an .n12 row) and its quality string (field 9), as
+ * (offset, length) into two text buffers.  Per row:
+ *   status  DCB_BC_OK, the failure the reference would count (DCB_BC_FAIL_*), or DCB_BC_HOST: an exact spacer search found
+ *           nothing, so the reference's fuzzy regular-expression searches decide (or the row has a symbol outside ACGTN / a
+ *           quality string of another length): the caller runs the reference's own code on these rows;
+ *   n1len   length of N1 (4..8) once the spacers are placed (also for DCB_BC_FAIL_QUALITY): 6 = plain, < 6 padded with 'S',
+ *           > 6 cut to five bases + 'L' (the readdata_short_barcode / readdata_long_barcode counters);
+ *   code    the 12-symbol barcode as dcb_umi_pairs takes it: 3 bits per symbol, A C G T N S L = 0..6, length in bits [58, 64). */
+enum { DCB_BC_OK = 0, DCB_BC_FAIL_N = 1, DCB_BC_FAIL_NOSPACER = 2, DCB_BC_FAIL_NOT2 = 3, DCB_BC_FAIL_N1SHORT = 4, DCB_BC_FAIL_N1LONG = 5,
+       DCB_BC_FAIL_N2END = 6, DCB_BC_FAIL_QUALITY = 7, DCB_BC_HOST = 255 };
+enum { DCB_OLIGO_M13 = 0, DCB_OLIGO_I8 = 1 };
+typedef struct dcb_bc_params {
+    int32_t oligo;       /* DCB_OLIGO_* (inputargs["oligo"]) */
+    int32_t allow_ns;    /* inputargs["allowNs"] */
+    int32_t min_q;       /* inputargs["minbcQ"] */
+    int32_t max_below;   /* inputargs["bcQbelowmin"] */
+    double avg_q;        /* inputargs["avgQthreshold"] */
+} dcb_bc_params;
+int dcb_barcodes(dcb_dist*, const char* bc_text, const uint64_t* bc_off, const uint32_t* bc_len, const char* q_text,
+                 const uint64_t* q_off, const uint32_t* q_len, uint64_t n, const dcb_bc_params* prm, uint8_t* status,
+                 uint8_t* n1len, uint64_t* code);
+
 /* Device time of the last dcb_umi_pairs (pair search, incl. its sorts on the deletion-neighbourhood path) or
    dcb_lev_leq kernel (CUDA events). */
 int dcb_dist_last_ms(dcb_dist*, double* ms);

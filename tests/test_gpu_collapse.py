@@ -1,6 +1,7 @@
 """Parity tests of the collapse distance kernels (csrc/collapse.cu) through the C ABI: dcb_umi_pairs and dcb_lev_leq
 against the oracle and against fixtures recorded from the unmodified reference; the collapse stage end to end with the
 distances on the GPU against the recorded runs and the reference's golden .freq files.  Bit-exact everywhere."""
+import collections as coll
 import gzip
 import json
 import os
@@ -220,3 +221,78 @@ def test_collapse_reproduces_golden_freq(golden_dir, tmp_path, chain, name):
 
 def test_reference_unit_answers_on_gpu():
     collapse_checks.check_reference_unit_answers()
+
+
+def _host_barcode(bc, q, args, qp):
+    """What collapse.py does for one row on the host (the reference's code path): -> (status, n1len, barcode)."""
+    c = coll.Counter()
+    saved = collapse.counts
+    collapse.counts = coll.Counter()
+    try:
+        locs = collapse.get_barcode_positions(bc, args, c)
+        if not locs:
+            for key, st in (("getbarcode_fail_N", _lib.BC_FAIL_N), ("getbarcode_fail_nospacerfound", _lib.BC_FAIL_NOSPACER),
+                            ("getbarcode_fail_not2spacersfound", _lib.BC_FAIL_NOT2), ("getbarcode_fail_n1tooshort", _lib.BC_FAIL_N1SHORT),
+                            ("getbarcode_fail_n1toolong", _lib.BC_FAIL_N1LONG), ("getbarcode_fail_n2pastend", _lib.BC_FAIL_N2END)):
+                if c[key]:
+                    return st, 0, None, c
+            raise AssertionError(c)
+        fields = [None] * 8 + [bc, q]
+        barcode, bq = collapse.set_barcode(fields, locs, args)
+        bad = collapse.check_umi_quality(bq, qp)
+        return (_lib.BC_FAIL_QUALITY if bad else _lib.BC_OK), locs[1] - locs[0], barcode, c
+    finally:
+        collapse.counts = saved
+
+
+@pytest.mark.parametrize("oligo", ["M13", "I8"])
+@pytest.mark.parametrize("allow_ns", [False, True])
+def test_barcode_kernel_equals_the_host_path(dist, oligo, allow_ns):
+    """dcb_barcodes row by row against get_barcode_positions + set_barcode + check_umi_quality (collapse.py:281-479): every
+    row the kernel decides must carry the host path's verdict, N1 length and barcode; rows it hands back (BC_HOST) are
+    exactly those whose spacers are not found by an exact search (or that hold odd symbols)."""
+    rng = random.Random(7 if oligo == "M13" else 8)
+    sp1, sp2 = ("GTCGTGACTGGGAAAACCCTGG", "GTCGTGAT") if oligo == "M13" else ("GTCGTGAT", "GTCGTGAT")
+    bcs, quals = [], []
+    for i in range(6000):
+        n1 = rng.choice((6, 6, 6, 6, 5, 4, 7, 8, 3, 9, 2, 10))
+        s = "".join(rng.choice("ACGT") for _ in range(rng.choice((0, 0, 0, 1, 2)))) + sp1 + "".join(rng.choice("ACGT") for _ in range(n1)) + sp2 + \
+            "".join(rng.choice("ACGT") for _ in range(rng.choice((6, 6, 6, 8, 5, 3))))
+        s = list(s)
+        r = rng.random()
+        if r < 0.15:                       # substitutions: some fall into a spacer (fuzzy search on the host), some into N1 / N2
+            for _ in range(rng.randrange(1, 3)):
+                s[rng.randrange(len(s))] = rng.choice("ACGTN")
+        elif r < 0.2 and s:
+            del s[rng.randrange(len(s))]
+        elif r < 0.25:
+            s.insert(rng.randrange(len(s) + 1), rng.choice("ACGT"))
+        elif r < 0.27:
+            s[rng.randrange(len(s))] = rng.choice("acgtRY")
+        elif r < 0.3:                      # a second copy of a spacer
+            s += list(sp2)
+        s = "".join(s)[:rng.choice((42, 42, 42, 60, 30))]
+        q = "".join(rng.choice("IIIIIIIIIIFFF:5,#!") for _ in range(len(s)))
+        if i % 50 == 0:
+            q = q[:-1]                     # a quality string of another length: host
+        bcs.append(s); quals.append(q)
+    bcs += ["", "A", sp1, sp1 + "ACGTAC" + sp2, sp1 + "ACGTAC" + sp2 + "ACGTA"]
+    quals += ["", "I", "I" * len(sp1), "I" * (len(sp1) + 14), "I" * (len(sp1) + 19)]
+    args = {"oligo": oligo, "allowNs": allow_ns, "sampling_analysis": False}
+    for qp in ([20, 1, 30], [30, 0, 35.5], [2, 5, 0]):
+        status, n1, code = dist.barcodes(bcs, quals, _lib.OLIGOS_ON_DEVICE[oligo.lower()], allow_ns, *qp)
+        decided = 0
+        for i, (bc, q) in enumerate(zip(bcs, quals)):
+            if status[i] == _lib.BC_HOST:
+                # handed back: no exact hit of one of the spacers in its window, odd symbols, or a ragged quality string
+                lo_hi = bc[:10 + len(sp1)]
+                assert (sp1 not in lo_hi) or (sp2 not in bc[len(sp1):]) or set(bc) - set("ACGTN") or len(q) != len(bc), (i, bc)
+                continue
+            decided += 1
+            st, hn1, barcode, _ = _host_barcode(bc, q, args, qp)
+            assert status[i] == st, (i, bc, q, status[i], st)
+            if st in (_lib.BC_OK, _lib.BC_FAIL_QUALITY):
+                assert n1[i] == hn1
+                got = "".join("ACGTNSL"[(int(code[i]) >> (3 * k)) & 7] for k in range(int(code[i]) >> 58))
+                assert got == barcode, (i, bc, got, barcode)
+        assert decided > 0.6 * len(bcs)
