@@ -364,8 +364,8 @@ def _device_barcodes(rows, inputargs, qp):
     """dcb_barcodes over the barcode regions of all rows at once: -> (status, n1len, barcode strings) or None when this
     oligo / option has no device path.  Rows whose spacers are not found exactly come back with status BC_HOST."""
     name = inputargs["oligo"].lower()
-    if name not in _lib.OLIGOS_ON_DEVICE or inputargs["sampling_analysis"] or not rows:
-        return None
+    if name not in _lib.OLIGOS_ON_DEVICE or inputargs["sampling_analysis"] or not rows or "allowNs" not in inputargs:
+        return None      # (without the allowNs key the reference fails on the first barcode that holds an N: host path)
     status, n1, code = _gpu().barcodes([r[8] for r in rows], [r[9] for r in rows], _lib.OLIGOS_ON_DEVICE[name],
                                        inputargs["allowNs"] != False, qp[0], qp[1], qp[2])  # noqa: E712
     sym = (code[:, None] >> (np.uint64(3) * np.arange(12, dtype=np.uint64))[None, :]) & np.uint64(7)
