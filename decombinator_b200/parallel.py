@@ -86,6 +86,122 @@ def all_to_all_bytes(chunks):
     return out
 
 
+# ---------------------------------------------------------------------------------------------------------
+# The collapse exchange: 64-byte records (SURVEY.md 8(d)), one NCCL all-to-all straight from device buffers.
+#   u64 global row index | u64 barcode (12 symbols x 3 bits over ACGTNSL, length in the top bits: what dcb_umi_pairs takes)
+#   u8 v, u8 j, u16 vdel, u16 jdel | u8 inter-tag length, u8 insert offset in it, u8 insert length, u8 flags
+#   33 B inter-tag sequence, 2 bits per base (<= 132 nt; -ln defaults to 130) | 5 B padding
+# The barcode was located and quality-filtered on the source rank, so the 42-nt barcode region, the quality strings and
+# the read id do not travel (they are only needed again for -wc / sampling analysis, which use the pickled rows below).
+# ---------------------------------------------------------------------------------------------------------
+RECORD = np.dtype([("idx", "<u8"), ("code", "<u8"), ("v", "u1"), ("j", "u1"), ("vdel", "<u2"), ("jdel", "<u2"), ("seq_len", "u1"),
+                   ("ins_off", "u1"), ("ins_len", "u1"), ("flags", "u1"), ("seq", "u1", (33,)), ("pad", "u1", (5,))])
+assert RECORD.itemsize == 64
+_SYM = {c: i for i, c in enumerate("ACGTNSL")}
+_B2 = {"A": 0, "C": 1, "G": 2, "T": 3}
+_PACK4 = {a + b + c + d: _B2[a] | (_B2[b] << 2) | (_B2[c] << 4) | (_B2[d] << 6) for a in "ACGT" for b in "ACGT" for c in "ACGT" for d in "ACGT"}
+_UNPACK4 = ["".join("ACGT"[(v >> (2 * k)) & 3] for k in range(4)) for v in range(256)]
+
+
+def encode_records(kept):
+    """[(global row index, barcode, inter-tag seq, dcretc), ...] -> RECORD array, or None when a row does not fit the record
+    (a symbol outside ACGT in the inter-tag sequence, more than 132 nt, a field out of range): the caller then falls back
+    to pickled rows."""
+    import ast
+    out = np.zeros(len(kept), dtype=RECORD)
+    try:
+        for t, (idx, barcode, seq, dcretc) in enumerate(kept):
+            v, j, vdel, jdel, ins = ast.literal_eval(dcretc.split("|", 1)[0])
+            off = seq.find(ins)
+            n = len(seq)
+            if n > 132 or off < 0 or len(barcode) > 19:
+                return None
+            code = len(barcode) << 58
+            for k, ch in enumerate(barcode):
+                code |= _SYM[ch] << (3 * k)
+            r = out[t]
+            r["idx"], r["code"], r["v"], r["j"], r["vdel"], r["jdel"] = idx, code, int(v), int(j), int(vdel), int(jdel)
+            r["seq_len"], r["ins_off"], r["ins_len"] = n, off, len(ins)
+            padded = seq + "A" * (-n % 4)
+            r["seq"][:len(padded) // 4] = [_PACK4[padded[k:k + 4]] for k in range(0, len(padded), 4)]
+    except (KeyError, ValueError, OverflowError, SyntaxError):
+        return None
+    return out
+
+
+def decode_records(rec):
+    """RECORD array -> the (global row index, barcode, inter-tag seq, dcretc) tuples the grouping takes; the dcretc of a
+    decoded row is ``str(dcr)|seq||`` (quality string and read id did not travel)."""
+    rows = []
+    for r in rec:
+        code, n = int(r["code"]), int(r["seq_len"])
+        barcode = "".join("ACGTNSL"[(code >> (3 * k)) & 7] for k in range(code >> 58))
+        seq = "".join(_UNPACK4[b] for b in r["seq"][:(n + 3) // 4].tolist())[:n]
+        ins = seq[int(r["ins_off"]):int(r["ins_off"]) + int(r["ins_len"])]
+        dcr = [str(int(r["v"])), str(int(r["j"])), str(int(r["vdel"])), str(int(r["jdel"])), ins]
+        rows.append((int(r["idx"]), barcode, seq, "|".join([str(dcr), seq, "", ""])))
+    return rows
+
+
+def record_owner(codes, world):
+    """Destination rank of every record: a multiplicative hash of the barcode code (the same on every rank)."""
+    h = (np.asarray(codes, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(40)
+    return (h % np.uint64(world)).astype(np.int64)
+
+
+_last_exchange = {}
+
+
+def exchange_records(rec):
+    """All-to-all of RECORD rows keyed by the barcode hash: every rank gets the records whose barcode it owns.  The send
+    buffer (records ordered by destination) and the receive buffer are DEVICE tensors under NCCL -- the collective moves
+    them GPU to GPU over NVLink --, CPU tensors under gloo.  Two collectives: the counts, then the payload."""
+    rank, world = _rank_world()
+    if world == 1:
+        return rec
+    dev = _comm_device()
+    owner = record_owner(rec["code"], world)
+    order = np.argsort(owner, kind="stable")
+    send_counts = np.bincount(owner, minlength=world).astype(np.int64)
+    send = torch.from_numpy(np.ascontiguousarray(rec[order]).view(np.uint8).reshape(-1, 64).copy()).to(dev)
+    sc = torch.from_numpy(send_counts).to(dev)
+    rc = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(rc, sc)
+    recv_counts = rc.tolist()
+    recv = torch.empty((int(sum(recv_counts)), 64), dtype=torch.uint8, device=dev)
+    timed = dev.type == "cuda"
+    if timed:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=send_counts.tolist())
+    if timed:
+        e1.record()
+        torch.cuda.synchronize()
+        _last_exchange.update(ms=e0.elapsed_time(e1), sent_bytes=int(send.numel()), received_bytes=int(recv.numel()))
+    return np.ascontiguousarray(recv.cpu().numpy()).view(RECORD).reshape(-1)
+
+
+def all_gather_codes(codes):
+    """Every rank's UMI codes (uint64) concatenated in rank order, on every rank: one all_gather of the counts and one of
+    the padded payload (device tensors under NCCL)."""
+    rank, world = _rank_world()
+    codes = np.ascontiguousarray(codes, dtype=np.uint64)
+    if world == 1:
+        return codes, [len(codes)]
+    dev = _comm_device()
+    n = torch.tensor([len(codes)], dtype=torch.int64, device=dev)
+    sizes = [torch.empty(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(x.item()) for x in sizes]
+    width = max(max(sizes), 1)
+    mine = torch.zeros(width, dtype=torch.int64, device=dev)
+    mine[:len(codes)] = torch.from_numpy(codes.view(np.int64)).to(dev)
+    parts = [torch.empty(width, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    flat = np.concatenate([p[:k].cpu().numpy() for p, k in zip(parts, sizes)]).view(np.uint64)
+    return flat, sizes
+
+
 def _sum_counters(local):
     """Counter summed over ranks (every rank gets the total)."""
     rank, world = _rank_world()
@@ -191,12 +307,22 @@ def collapsinator_sharded(inputargs, data=None, first_index=0, n_total=None):
         data, first_index = lines[lo:hi], lo
     # 1. per-row filters on the source rank
     kept, dcr_counts, _ = C._filter_rows(data, inputargs, qp, True, from_file, first_index=first_index)
-    # 2. ONE all-to-all keyed by hash(exact barcode)
-    outbox = [[] for _ in range(world)]
-    for item in kept:
-        outbox[barcode_owner(item[1], world)].append(item)
-    inbox = all_to_all_bytes([pickle.dumps(x, protocol=4) for x in outbox])
-    mine = [item for blob in inbox for item in pickle.loads(blob)]
+    # 2. ONE all-to-all keyed by hash(exact barcode): 64-byte records from device buffers.  Rows that do not fit a record
+    #    (and runs that need the quality strings / read ids again: -wc, sampling analysis) travel as pickled rows instead;
+    #    the ranks agree on the form first.
+    rec = None if (inputargs["writeclusters"] or inputargs["sampling_analysis"]) else encode_records(kept)
+    flag = torch.tensor([0 if rec is None else 1], dtype=torch.int64, device=_comm_device())
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    _last_exchange.clear()
+    _last_exchange["form"] = "records" if int(flag.item()) else "pickled rows"
+    if int(flag.item()):
+        mine = decode_records(exchange_records(rec))
+    else:
+        outbox = [[] for _ in range(world)]
+        for item in kept:
+            outbox[barcode_owner(item[1], world)].append(item)
+        inbox = all_to_all_bytes([pickle.dumps(x, protocol=4) for x in outbox])
+        mine = [item for blob in inbox for item in pickle.loads(blob)]
     mine.sort(key=lambda item: item[0])                      # global input order within every barcode
     # 3. group this rank's barcodes (Levenshtein verdicts on this rank's GPU)
     machines = C._group_rows(mine, frac)

@@ -37,6 +37,24 @@ def _worker(rank, world, port, case_index, out_path):
     assert got == [("%d->%d;" % (s, rank)).encode() * (rank + 1) for s in range(world)], got
     lo, hi = parallel.shard_bounds(len(rows), rank, world)
     out = parallel.collapsinator_sharded(dict(case["args"]), data=rows[lo:hi], first_index=lo)
+    assert parallel._last_exchange["form"] == "records"          # 64-byte records, not pickled rows
+    # the UMI-code all-gather: every rank ends up with every rank's codes, in rank order
+    import numpy as np
+    codes, sizes = parallel.all_gather_codes(np.arange(3 + 2 * rank, dtype=np.uint64) + np.uint64(100 * rank))
+    assert sizes == [3 + 2 * r for r in range(world)]
+    assert codes.tolist() == [100 * r + k for r in range(world) for k in range(3 + 2 * r)]
+    # with -wc the rows travel pickled (quality strings and read ids are needed again), same result
+    if case_index == 0:
+        args_wc = dict(case["args"], writeclusters=True, chain="b")
+        cwd = os.getcwd()
+        os.chdir(os.path.dirname(out_path))
+        try:
+            out_wc = parallel.collapsinator_sharded(args_wc, data=rows[lo:hi], first_index=lo)
+        finally:
+            os.chdir(cwd)
+        assert parallel._last_exchange["form"] == "pickled rows"
+        if rank == 0:
+            assert out_wc == out
     if rank == 0:
         with open(out_path, "w") as fh:
             json.dump({"freq": out, "counts": {k: v for k, v in collapse.counts.items() if isinstance(v, int)}}, fh)
