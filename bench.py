@@ -165,6 +165,105 @@ def run_cfg4(args, rank, world, local_rank, host_threads, stream, barrier):
                      "500 M reads on 8 GPUs are 6.25 such shards per GPU)")
 
 
+def run_cfg3(args, rank, world, local_rank, host_threads, stream, barrier):
+    """BASELINE configs[3] in the same run: decombine + the device steps of collapse on reads with UMI barcodes (human beta,
+    0.5 % substitutions in R1 and in the 42-nt barcode region, every molecule ~50 copies): the decombine kernels, the
+    barcode-extraction kernel, the barcode-hash all-to-all of 64-byte records between the GPUs (NCCL, device tensors;
+    N > 1 only) and the UMI neighbour search over the gathered unique barcodes.  The order-dependent grouping that follows
+    is host code (collapse.py) and is not part of this block."""
+    import torch
+    import torch.distributed as dist
+    from decombinator_b200 import _lib, parallel, tags
+    info = tags.load("human", "extended", "b")
+    n, seed = args.reads, 20260004
+    pool = max(1000, n * world // 50)
+    syn = _lib.Synth([(info.v_regions, info.j_regions)], seed, READ_LEN, 62, 0.005, 0.0, 0.0, umi_pool=pool, sub_rate2=0.005)
+    r1, r2 = syn.reads(rank * n, n, want_r2=True, n_threads=host_threads)
+    off = np.arange(n, dtype=np.uint64) * READ_LEN
+    ln = np.full(n, READ_LEN, dtype=np.uint32)
+    packed = _lib.pack_arrays(r1, off, ln, revcomp=True, n_threads=host_threads)
+    del r1
+    steps = max(1, min(args.steps, 20))
+    vt, jt = info.tables()
+    ctx = _lib.Context(vt, jt, device=local_rank)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.upload(packed)
+    with torch.cuda.stream(stream):
+        for _ in range(5):
+            ctx.run_resident()
+        torch.cuda.synchronize()
+        res, _ = ctx.download()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(steps):
+            ctx.run_resident()
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    queued, general = ctx.last_deferred() / n, ctx.last_general() / n
+    ctx.close(); packed.free()
+    out = {"workload": "synthetic 250-nt reads with UMI barcodes (M13 oligo, 42-nt barcode region in R2), human beta, 0.5 %% substitutions in R1 "
+                       "and in the barcode region, %d molecules x ~50 copies (BASELINE configs[3] shape, %d reads per GPU)" % (pool, n),
+           "seed": seed,
+           "decombine": {"value": world * n * steps / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / steps,
+                         "decombined_fraction": float(res["status"].mean()), "queued_by_exact_kernel": queued,
+                         "deferred_to_general_kernel": general}}
+    # barcode extraction of the decombined rows (exact-spacer fast path + quality filter on the device)
+    hits = np.nonzero(res["status"])[0]
+    d = _lib.Dist(local_rank)
+    qbuf = np.full(62, ord("I"), dtype=np.uint8)
+    bo = hits.astype(np.uint64) * np.uint64(62)
+    bl = np.full(len(hits), 42, dtype=np.uint32)
+    qo = np.zeros(len(hits), dtype=np.uint64)
+    st, n1, code = d.barcodes_arrays(r2, bo, bl, qbuf, qo, bl, 0, False, 20, 1, 30)
+    bc_ms = d.last_ms()
+    ok = st == _lib.BC_OK
+    out["barcodes"] = {"rows": int(len(hits)), "device_ms": bc_ms, "rows_per_s": len(hits) / (bc_ms / 1e3),
+                       "decided_on_device": float((st != _lib.BC_HOST).mean()), "passed": float(ok.mean()),
+                       "algorithmic_GBps": len(hits) * (84 + 10) / (bc_ms / 1e3) / 1e9}
+    # the 64-byte records of the surviving rows, exchanged by barcode hash
+    rec = np.zeros(int(ok.sum()), dtype=parallel.RECORD)
+    rec["idx"] = (rank * n + hits[ok]).astype(np.uint64)
+    rec["code"] = code[ok]
+    for f in ("v", "j", "vdel", "jdel"):
+        rec[f] = res[f][hits[ok]]
+    ex = {"records_per_gpu": int(len(rec)), "bytes_per_record": 64}
+    if world > 1:
+        mine = parallel.exchange_records(rec)                      # warm-up of the same call (NCCL channels)
+        reps, tot = 5, 0.0
+        for _ in range(reps):
+            mine = parallel.exchange_records(rec)
+            tot += parallel._last_exchange["ms"]
+        t = torch.tensor([tot / reps, float(parallel._last_exchange["sent_bytes"])], device="cuda", dtype=torch.float64)
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        a2a_ms, total_bytes = float(tmax[0]), float(tsum[1])
+        off_rank = total_bytes * (world - 1) / world
+        ex.update({"all_to_all_ms": a2a_ms, "bytes_sent_all_gpus": total_bytes,
+                   "GBps_per_gpu_off_rank": off_rank / world / (a2a_ms / 1e3) / 1e9, "bound_GBps_per_gpu": 770.0,
+                   "frac_of_bound": off_rank / world / (a2a_ms / 1e3) / 1e9 / 770.0,
+                   "how": "torch.distributed.all_to_all_single on device tensors (NCCL), CUDA events, max over ranks"})
+    else:
+        mine = rec
+        ex["note"] = "one GPU: no exchange"
+    out["exchange"] = ex
+    # UMI neighbour search over the unique barcodes of the whole job (all-gather of the codes, search on every rank's GPU;
+    # rank 0's time is reported)
+    uniq = np.unique(mine["code"])
+    codes, sizes = parallel.all_gather_codes(uniq)
+    d.umi_pairs(codes[:1000], 2)
+    row, _ = d.umi_pairs(codes, 2)
+    out["umi_pairs"] = {"unique_umis": int(len(codes)), "pairs": int(len(row)), "device_ms": d.last_ms(), "method": d.last_method(),
+                        "max_edits": 2}
+    d.close()
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -333,12 +432,13 @@ def main():
     exact_name, h2d_bytes = ctx.exact_kernel_name(), packed.h2d_bytes()
 
     n_general = ctx.last_general()
-    cfg2 = cfg4 = None
+    cfg2 = cfg3 = cfg4 = None
     if not args.no_workloads:
         ctx.close(); ctx = None
         packed.free()
         cfg2 = run_cfg2(args, rank, world, local_rank, host_threads, stream, barrier)
         cfg4 = run_cfg4(args, rank, world, local_rank, host_threads, stream, barrier)
+        cfg3 = run_cfg3(args, rank, world, local_rank, host_threads, stream, barrier)
         packed = None
 
     if world > 1:
@@ -393,7 +493,7 @@ def main():
             "clocks": clocks,
         }
         if cfg2:
-            line["workloads"] = {"cfg2": cfg2, "cfg4": cfg4}
+            line["workloads"] = {"cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4}
         if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only
             threads = os.cpu_count() or 1
             sample = args.cpu_sample or min(n, 2_000_000 if threads < 16 else 10_000_000)

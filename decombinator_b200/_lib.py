@@ -707,14 +707,13 @@ class Dist:
         """dcb_barcodes over lists of barcode-region strings and their quality strings.
         -> (status uint8, n1len uint8, code uint64) arrays; status BC_HOST rows are for the reference's fuzzy spacer search."""
         n = len(bcs)
-        status, n1, code = np.full(n, BC_HOST, dtype=np.uint8), np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.uint64)
         if n == 0:
-            return status, n1, code
+            return np.zeros(0, dtype=np.uint8), np.zeros(0, dtype=np.uint8), np.zeros(0, dtype=np.uint64)
         try:
             bbuf = np.frombuffer("".join(bcs).encode("ascii") + b"\0", dtype=np.uint8)
             qbuf = np.frombuffer("".join(quals).encode("ascii") + b"\0", dtype=np.uint8)
-        except UnicodeEncodeError:
-            return status, n1, code                      # non-ASCII text: every row takes the host path
+        except UnicodeEncodeError:                       # non-ASCII text: every row takes the host path
+            return np.full(n, BC_HOST, dtype=np.uint8), np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.uint64)
         bl = np.fromiter((len(x) for x in bcs), dtype=np.uint32, count=n)
         ql = np.fromiter((len(x) for x in quals), dtype=np.uint32, count=n)
         bo = np.zeros(n, dtype=np.uint64)
@@ -722,6 +721,16 @@ class Dist:
         if n > 1:
             np.cumsum(bl[:-1], dtype=np.uint64, out=bo[1:])
             np.cumsum(ql[:-1], dtype=np.uint64, out=qo[1:])
+        return self.barcodes_arrays(bbuf, bo, bl, qbuf, qo, ql, oligo, allow_ns, min_q, max_below, avg_q)
+
+    def barcodes_arrays(self, bbuf, bo, bl, qbuf, qo, ql, oligo, allow_ns, min_q, max_below, avg_q):
+        """dcb_barcodes over (offset, length) columns into two uint8 text buffers."""
+        n = len(bo)
+        status, n1, code = np.full(n, BC_HOST, dtype=np.uint8), np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.uint64)
+        if n == 0:
+            return status, n1, code
+        bo, qo = np.ascontiguousarray(bo, dtype=np.uint64), np.ascontiguousarray(qo, dtype=np.uint64)
+        bl, ql = np.ascontiguousarray(bl, dtype=np.uint32), np.ascontiguousarray(ql, dtype=np.uint32)
         prm = CBcParams(int(oligo), int(bool(allow_ns)), int(min_q), int(max_below), float(avg_q))
         _check(lib().dcb_barcodes(self._h, bbuf.ctypes.data, bo.ctypes.data, bl.ctypes.data, qbuf.ctypes.data, qo.ctypes.data,
                                   ql.ctypes.data, n, ctypes.byref(prm), status.ctypes.data, n1.ctypes.data, code.ctypes.data), "dcb_barcodes")
