@@ -401,13 +401,22 @@ def _filter_rows(data, inputargs, barcode_quality_parameters, dont_count, from_f
     dev = _device_barcodes(rows, inputargs, barcode_quality_parameters)
     kept = []
     input_dcr_counts = coll.Counter()
-    lcount = -1
+    n_rows = len(rows)
+    counts["readdata_input_dcrs"] += n_rows
+    status = dev[0].tolist() if dev is not None else None
+    text = dev[1] if dev is not None else None
+    lenthreshold, sampling = inputargs["lenthreshold"], inputargs["sampling_analysis"]
+    n_long = n_ok = 0
+    HOST, OK = _lib.BC_HOST, _lib.BC_OK
     for lcount, line in enumerate(rows):
         if lcount % 50000 == 0 and lcount != 0 and not dont_count:
             print("   Read in", lcount, "lines... ", round(time.time() - t0, 2), "seconds")
-        counts["readdata_input_dcrs"] += 1
-        st = dev[0][lcount] if dev is not None else _lib.BC_HOST
-        if st == _lib.BC_HOST:
+        st = status[lcount] if status is not None else HOST
+        if st == OK:
+            barcode, barcode_qualstring = text[12 * lcount:12 * lcount + 12], None
+        elif st != HOST:
+            continue                                  # rejected on the device, counted in _device_barcodes
+        else:
             bc_locs = get_barcode_positions(line[8], inputargs, counts)
             if not bc_locs:
                 counts["readdata_fail_no_bclocs"] += 1
@@ -416,22 +425,23 @@ def _filter_rows(data, inputargs, barcode_quality_parameters, dont_count, from_f
             if check_umi_quality(barcode_qualstring, barcode_quality_parameters):
                 counts["readdata_fail_low_barcode_quality"] += 1
                 continue
-        elif st != _lib.BC_OK:
-            continue                                  # rejected on the device, counted in _device_barcodes
-        else:
-            barcode, barcode_qualstring = dev[1][12 * lcount:12 * lcount + 12], None
-        dcr = line[:5]
-        input_dcr_counts[str(dcr)] += 1
+        dcr = str(line[:5])
+        input_dcr_counts[dcr] += 1
         seq = line[6]
-        if len(seq) > inputargs["lenthreshold"]:
-            counts["readdata_fail_overlong_intertag_seq"] += 1
+        if len(seq) > lenthreshold:
+            n_long += 1
             continue
-        counts["readdata_success"] += 1
-        parts = [str(dcr), seq, line[7], line[5]]
-        if inputargs["sampling_analysis"]:
-            parts += [barcode, barcode_qualstring, line[8], line[10]]
-        kept.append((first_index + lcount, barcode, seq, "|".join(parts)))
-    return kept, input_dcr_counts, lcount + 1
+        n_ok += 1
+        if sampling:
+            dcretc = "|".join([dcr, seq, line[7], line[5], barcode, barcode_qualstring, line[8], line[10]])
+        else:
+            dcretc = "|".join((dcr, seq, line[7], line[5]))
+        kept.append((first_index + lcount, barcode, seq, dcretc))
+    if n_long:
+        counts["readdata_fail_overlong_intertag_seq"] += n_long
+    if n_ok:
+        counts["readdata_success"] += n_ok
+    return kept, input_dcr_counts, n_rows
 
 
 def _group_rows(kept, lev_threshold_fraction):

@@ -54,9 +54,16 @@ def main():
         t0 = time.perf_counter()
         rows = decombine.decombinator(dict(ia))
         t_dec = time.perf_counter() - t0
+        if args.profile:
+            import cProfile, pstats
+            pr = cProfile.Profile()
+            pr.enable()
         t0 = time.perf_counter()
         out = pipeline.run(dict(ia))
         t_pipe = time.perf_counter() - t0
+        if args.profile:
+            pr.disable()
+            pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
         print(json.dumps({"reads": n, "decombinator_s": round(t_dec, 2), "pipeline_s": round(t_pipe, 2), "rows": len(rows),
                           "translated": len(out), "pipeline_reads_per_s": round(n / t_pipe)}))
         return
