@@ -1194,21 +1194,26 @@ DCB_HD ReadView half_inv_view(const ReadView& r, const uint32_t* inv2) {
     ri.w = inv2;
     return ri;
 }
-// One probe hit: a keyword of `set` may start at P.  Its kmin-prefix is looked up; every keyword with that prefix is
-// compared with the read as a whole.  sink(keyword record number, number of tags that have this half) per occurrence.
-template <bool PADDED, class Sink>
-DCB_HD void half_lookup(const ReadView& r, const uint32_t* inv2, const HalfView& hx, int set, int P, Sink& sink) {
-    if (P < 0) return;
+// One probe hit: a keyword of `set` may start at P.  half_prefix looks its kmin-prefix up: 0 when no keyword of the set
+// starts like that, else the keyword list (position | count << 8).  half_keywords then compares every keyword of the list
+// with the read as a whole: sink(keyword record number, number of tags that have this half) per occurrence.
+template <bool PADDED>
+DCB_HD uint32_t half_prefix(const ReadView& r, const HalfView& hx, int set, int P) {
+    if (P < 0) return 0u;
     constexpr int KMIN = DCB_HALF_Q + DCB_HALF_STRIDE - 1;
     uint32_t lo, hi;
     rd_win32x<PADDED>(r, P, lo, hi);
     const uint32_t key = ((uint32_t)set << 28) | (lo & mask2(KMIN));
     const uint32_t s1 = (key * hx.c1) >> hx.hshift, s2 = (key * hx.c2) >> hx.hshift;
     const uint32_t k1 = hx.h[2 * s1], k2 = hx.h[2 * s2];
-    if (k1 != key && k2 != key) return;
-    const uint32_t meta = hx.h[2 * (k1 == key ? s1 : s2) + 1];
-    const int first = (int)(meta & 255u), cnt = (int)(meta >> 8);
-    uint32_t ilo = 0, ihi = 0;
+    if (k1 != key && k2 != key) return 0u;
+    return hx.h[2 * (k1 == key ? s1 : s2) + 1] | 0x80000000u;
+}
+template <bool PADDED, class Sink>
+DCB_HD void half_keywords(const ReadView& r, const uint32_t* inv2, const HalfView& hx, uint32_t meta, int P, Sink& sink) {
+    const int first = (int)(meta & 255u), cnt = (int)((meta >> 8) & 255u);
+    uint32_t lo, hi, ilo = 0, ihi = 0;
+    rd_win32x<PADDED>(r, P, lo, hi);
     if (inv2) rd_win32x<PADDED>(half_inv_view(r, inv2), P, ilo, ihi);
     for (int i = 0; i < cnt; i++) {
         const int id = hx.ids[first + i];
@@ -1219,6 +1224,11 @@ DCB_HD void half_lookup(const ReadView& r, const uint32_t* inv2, const HalfView&
         if ((xlo & mask2(len)) | (len > 16 ? (xhi & mask2(len - 16)) : 0u)) continue;
         sink(id, (int)k.n_tags);
     }
+}
+template <bool PADDED, class Sink>
+DCB_HD void half_lookup(const ReadView& r, const uint32_t* inv2, const HalfView& hx, int set, int P, Sink& sink) {
+    const uint32_t meta = half_prefix<PADDED>(r, hx, set, P);
+    if (meta) half_keywords<PADDED>(r, inv2, hx, meta, P, sink);
 }
 // One (occurrence, tag) pair: keyword record `id` occurs at P, `ti` counts the tags that have this half.  Appends the
 // candidate with the reference's length guard (decombine.py:302-307) and lev.hamming(tag, window) <= 1 (:309) already

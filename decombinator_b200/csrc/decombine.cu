@@ -685,14 +685,15 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
     if (blockIdx.x >= n_tiles) return;                              // nothing queued for this block: do not even stage the tables
     extern __shared__ __align__(16) uint32_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, wbase = tid - lane;
-    SmemLayout L = carve(smem, tb, (size_t)(2 * ROWS + DCB_HALF_CAP + 1) * T + (size_t)(T / 32) * (DCB_HALF_WCAP / 2 + DCB_HALF_WCAP2 + 2));
+    SmemLayout L = carve(smem, tb, (size_t)(2 * ROWS + DCB_HALF_CAP + 1) * T + (size_t)(T / 32) * (DCB_HALF_WCAP / 2 + 2 * DCB_HALF_WCAP2 + 2));
     uint32_t* s_rd = L.cols;                      // [ROWS][T]
     uint32_t* s_inv = s_rd + (size_t)ROWS * T;    // [ROWS][T] invalid-base column, 01 per non-ACGT symbol
     uint32_t* s_cand = s_inv + (size_t)ROWS * T;  // [DCB_HALF_CAP][T]
     uint32_t* s_n = s_cand + (size_t)DCB_HALF_CAP * T;   // [T] candidates appended per read
     uint16_t* s_work = reinterpret_cast<uint16_t*>(s_n + T) + (size_t)(tid >> 5) * DCB_HALF_WCAP;   // this warp's probe hits: lane << 8 | probe
-    uint32_t* s_work2 = s_n + T + (size_t)(T / 32) * (DCB_HALF_WCAP / 2) + (size_t)(tid >> 5) * (DCB_HALF_WCAP2 + 2);   // (occurrence, tag) pairs:
-    uint32_t* s_n2 = s_work2 + DCB_HALF_WCAP2;                                                       // lane | P << 5 | keyword << 15 | tag index << 23
+    uint32_t* s_work2 = s_n + T + (size_t)(T / 32) * (DCB_HALF_WCAP / 2) + (size_t)(tid >> 5) * (2 * DCB_HALF_WCAP2 + 2);   // prefix hits: lane | P << 5 | set << 15
+    uint32_t* s_work3 = s_work2 + DCB_HALF_WCAP2;             // (occurrence, tag) pairs: lane | P << 5 | keyword << 15 | tag index << 23
+    uint32_t* s_n2 = s_work3 + DCB_HALF_WCAP2;                // lengths of the two lists
     s_rd[tid] = 0u; s_rd[(NW + 1) * T + tid] = 0u; s_rd[(NW + 2) * T + tid] = 0u;
     s_inv[tid] = 0u; s_inv[(NW + 1) * T + tid] = 0u; s_inv[(NW + 2) * T + tid] = 0u;
     stage_tables(L, tb);
@@ -778,10 +779,10 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
                 for (uint32_t c = cm[m]; c; c &= c - 1u) s_work[at++] = (uint16_t)((lane << 8) | (32 * m + __ffs(c) - 1));
         }
         __syncwarp();
-        // 3. confirm, in two flat stages with all lanes busy in each:
-        //    a. lane k takes probe hit k of the list -- another lane's read as a rule --, looks the keyword prefix up and
-        //       compares the keyword; an occurrence puts one item per tag that has this half on the warp's second list
-        if (lane == 0) *s_n2 = 0u;
+        // 3. confirm, in three flat stages with all lanes busy in each:
+        //    a. lane k takes probe hit k of the list -- another lane's read as a rule -- and looks the keyword prefix of
+        //       every (set, offset) the probe entry names up; a prefix that exists goes on the warp's second list
+        if (lane == 0) { s_n2[0] = 0u; s_n2[1] = 0u; }
         __syncwarp();
         for (int k0 = 0; k0 < n_work; k0 += 32) {
             const bool has = k0 + lane < n_work;
@@ -789,34 +790,52 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
             const int src = (int)(it >> 8), p = DCB_HALF_STRIDE * (int)(it & 255u);
             const uint32_t need_s = __shfl_sync(0xFFFFFFFFu, need, src);
             const int n_s = __shfl_sync(0xFFFFFFFFu, r.n, src);
-            const int flg_s = __shfl_sync(0xFFFFFFFFu, inv2 != nullptr ? 1 : 0, src);
             if (has) {
                 ReadView rs;
                 rs.w = s_rd + T + wbase + src; rs.stride = T; rs.nw = NW; rs.n = n_s;
                 const uint32_t* c0 = rs.w + (p >> 4) * T;
                 const uint32_t win = __funnelshift_r(c0[0], c0[T], (p & 15) * 2);
+                for (uint32_t e = hx.t[win & 0x3FFFu] & need_s; e; e &= e - 1u) {
+                    const int bit = __ffs(e) - 1, P = p - (bit & 3);
+                    if (half_prefix<true>(rs, hx, bit >> 2, P)) {
+                        const uint32_t at = atomicAdd(s_n2, 1u);
+                        if (at < DCB_HALF_WCAP2) s_work2[at] = (uint32_t)src | ((uint32_t)P << 5) | ((uint32_t)(bit >> 2) << 15);
+                        else atomicAdd(s_n + wbase + src, DCB_HALF_BAIL);                          // list full: pass the read on
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        //    a'. lane k takes prefix hit k: the keywords with that prefix are compared with the read as a whole; an occurrence
+        //       puts one item per tag that has this half on the third list
+        const int n_pre = (int)min(s_n2[0], (uint32_t)DCB_HALF_WCAP2);
+        for (int k0 = 0; k0 < n_pre; k0 += 32) {
+            const bool has = k0 + lane < n_pre;
+            const uint32_t it = has ? s_work2[k0 + lane] : (uint32_t)lane;
+            const int src = (int)(it & 31u), P = (int)((it >> 5) & 1023u), set = (int)((it >> 15) & 3u);
+            const int n_s = __shfl_sync(0xFFFFFFFFu, r.n, src);
+            const int flg_s = __shfl_sync(0xFFFFFFFFu, inv2 != nullptr ? 1 : 0, src);
+            if (has) {
+                ReadView rs;
+                rs.w = s_rd + T + wbase + src; rs.stride = T; rs.nw = NW; rs.n = n_s;
                 struct Sink {
-                    uint32_t* list; uint32_t* n2; uint32_t* n_src; uint32_t base;
+                    uint32_t* list; uint32_t* n3; uint32_t* n_src; uint32_t base;
                     __device__ __forceinline__ void operator()(int id, int n_tags) {
-                        const uint32_t at = atomicAdd(n2, (uint32_t)n_tags);
+                        const uint32_t at = atomicAdd(n3, (uint32_t)n_tags);
                         if (at + n_tags > DCB_HALF_WCAP2) { atomicAdd(n_src, DCB_HALF_BAIL); return; }   // list full: pass the read on
                         for (int ti = 0; ti < n_tags; ti++) list[at + ti] = base | ((uint32_t)id << 15) | ((uint32_t)ti << 23);
                     }
-                } sink{s_work2, s_n2, s_n + wbase + src, 0u};
-                for (uint32_t e = hx.t[win & 0x3FFFu] & need_s; e; e &= e - 1u) {
-                    const int bit = __ffs(e) - 1, P = p - (bit & 3);
-                    sink.base = (uint32_t)src | ((uint32_t)(P < 0 ? 0 : P) << 5);
-                    half_lookup<true>(rs, flg_s ? s_inv + T + wbase + src : nullptr, hx, bit >> 2, P, sink);
-                }
+                } sink{s_work3, s_n2 + 1, s_n + wbase + src, (uint32_t)src | ((uint32_t)P << 5)};
+                half_keywords<true>(rs, flg_s ? s_inv + T + wbase + src : nullptr, hx, half_prefix<true>(rs, hx, set, P), P, sink);
             }
         }
         __syncwarp();
         //    b. lane k takes item k of the second list: one (occurrence, tag) pair -> length guard, Hamming <= 1, the
         //       candidate appended to its read's list
-        const int n_work2 = (int)min(*s_n2, (uint32_t)DCB_HALF_WCAP2);
+        const int n_work2 = (int)min(s_n2[1], (uint32_t)DCB_HALF_WCAP2);
         for (int k0 = 0; k0 < n_work2; k0 += 32) {
             const bool has = k0 + lane < n_work2;
-            const uint32_t it = has ? s_work2[k0 + lane] : (uint32_t)lane;
+            const uint32_t it = has ? s_work3[k0 + lane] : (uint32_t)lane;
             const int src = (int)(it & 31u);
             const int n_s = __shfl_sync(0xFFFFFFFFu, r.n, src);
             const int flg_s = __shfl_sync(0xFFFFFFFFu, inv2 != nullptr ? 1 : 0, src);
@@ -1319,7 +1338,7 @@ static int prepare_batch(dcb_ctx* c, const dcb_packed* P, size_t exc_cap = 0) {
         halftag_fn hf = pick_half((int)sw, &ht);
         c->half_threads = ht;
         c->half_smem = ((size_t)c->vcore_words + c->jcore_words + c->half_words + (2 * (sw + 3) + DCB_HALF_CAP + 1) * ht +
-                        (ht / 32) * (DCB_HALF_WCAP / 2 + DCB_HALF_WCAP2 + 2)) * 4 + tail;
+                        (ht / 32) * (DCB_HALF_WCAP / 2 + 2 * DCB_HALF_WCAP2 + 2)) * 4 + tail;
         int occ_h = 0;
         if (hf && c->half_smem <= kMaxSmem) {
             CUDA_TRY(cudaFuncSetAttribute(hf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->half_smem));
