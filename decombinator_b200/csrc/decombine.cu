@@ -1092,8 +1092,8 @@ static halftag_fn pick_half(int nw, int* threads) {
     switch (nw) {
         case 8:  *threads = 768; return dcb_halftag_kernel<8, 768>;
         case 12: *threads = 768; return dcb_halftag_kernel<12, 768>;
-        case 16: *threads = 768; return dcb_halftag_kernel<16, 768>;
-        case 20: *threads = 640; return dcb_halftag_kernel<20, 640>;
+        case 16: *threads = 736; return dcb_halftag_kernel<16, 736>;
+        case 20: *threads = 608; return dcb_halftag_kernel<20, 608>;
         default: return nullptr;
     }
 }
