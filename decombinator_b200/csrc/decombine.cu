@@ -706,35 +706,22 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
 
     ExcList ex;
     ex.read = b.exc_read; ex.pos = b.exc_pos; ex.kind = b.exc_kind; ex.n = b.n_exc;
-    // The queue is an indirection (queue -> read index -> packed words, hand-over words): two dependent trips to global
-    // memory per read.  They are taken out of the tile's critical path by loading ahead: the read index two tiles ahead,
-    // the words and hand-over words one tile ahead (in registers), while the current tile is analysed.
-    auto queue_at = [&](uint32_t t) -> uint32_t {
-        const uint32_t it = t * T + tid;
-        return (t < n_tiles && it < n_items) ? __ldg(queue + it) : b.first;
-    };
-    auto load_read = [&](uint32_t ri, uint4 (&v)[NW / 4], uint4& hand) {
-        const uint4* src = reinterpret_cast<const uint4*>(b.words + (size_t)ri * NW);
-#pragma unroll
-        for (int k = 0; k < NW / 4; k++) v[k] = ldg_stream(src + k);
-        hand = __ldg(reinterpret_cast<const uint4*>(results + ri));
-    };
-    uint32_t ri_next = queue_at(blockIdx.x), ri_next2 = queue_at(blockIdx.x + gridDim.x);
-    uint4 v_next[NW / 4], hand_next;
-    load_read(ri_next, v_next, hand_next);
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t item = tile * T + tid;
         const bool live = item < n_items;
-        const uint32_t ri = ri_next;
+        const uint32_t ri = live ? __ldg(queue + item) : b.first;
         uint32_t w[NW];
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(b.words + (size_t)ri * NW);
 #pragma unroll
-        for (int k = 0; k < NW / 4; k++) { w[4 * k + 0] = v_next[k].x; w[4 * k + 1] = v_next[k].y; w[4 * k + 2] = v_next[k].z; w[4 * k + 3] = v_next[k].w; }
-        const uint4 hand = hand_next;
-        ri_next = ri_next2;
-        ri_next2 = queue_at(tile + 2 * gridDim.x);
-        load_read(ri_next, v_next, hand_next);            // in flight while this tile is analysed
+            for (int k = 0; k < NW / 4; k++) {
+                const uint4 v = ldg_stream(src + k);
+                w[4 * k + 0] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+            }
 #pragma unroll
-        for (int k = 0; k < NW; k++) col[k * T] = w[k];
+            for (int k = 0; k < NW; k++) col[k * T] = w[k];
+        }
+        const uint4 hand = *reinterpret_cast<const uint4*>(results + ri);
         uint32_t hv = hand.x, hj = hand.y, need = 0;
         ReadView r;
         r.w = col; r.stride = T; r.nw = NW;
