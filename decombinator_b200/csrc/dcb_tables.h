@@ -215,7 +215,8 @@ struct DcbSuffixFilter {
 //     of the set that start with this prefix (almost always one), as a run of `ids`, each naming a DcbHalfKw record:
 //     the whole keyword to compare with the read, the length of the FIRST tag that has this half (the reference's
 //     length guard, decombine.py:302-307) and the tags that share it, ascending.
-// Built only for chains whose half keywords all have >= 10 bases (every `extended` set).
+// Built for chains whose V half keywords all have >= 10 bases (every shipped set: the V split is 10); the J sets are
+// left out (j_ok = 0) when a J half is shorter (the 6-base halves of the `original` J sets).
 struct alignas(16) DcbHalfKw {
     uint32_t bits_lo, bits_hi;   // packed keyword
     uint8_t len, first_len, n_tags, set;
@@ -232,7 +233,9 @@ struct DcbHalfIndex {
     int32_t kw_off, n_kw;        // DcbHalfKw[n_kw]
     int32_t tags_off;            // uint8 tag ids
     int32_t n_words;
-    int32_t pad[3];
+    int32_t j_ok;                // 0: the J half keywords are too short for the index (6-base halves of the `original` J sets): only the
+                                 // V side is searched; a read whose V is assigned but whose J tag is missing goes on to the general kernel
+    int32_t pad[2];
 };
 #define DCB_HALF_Q 7
 #define DCB_HALF_STRIDE 4

@@ -770,6 +770,7 @@ DCB_HD void fast_find(const ReadView& r, const uint32_t* ib, FullHit& vh, FullHi
 // ------------------------------------------------------------------------------------------------
 #define DCB_HIT_ONE 0x80000000u
 #define DCB_HIT_MULTI 0xFFFFFFFFu
+#define DCB_HIT_UNKNOWN 0xFFFFFFFEu     // hand-over only: the gene was not searched (J, when the read has no single full V tag)
 // add an occurrence (or merge the state another lane collected) into a hit word
 DCB_HD uint32_t hit_merge(uint32_t cur, uint32_t c) {
     return cur == 0u ? c : ((c == 0u || c == cur) ? cur : DCB_HIT_MULTI);
@@ -1045,7 +1046,7 @@ DCB_HD int dcr_exact_read(const ReadView& r, bool flagged, const uint32_t* vcore
         fast_find(r, vidx, vh, jh, true);
         if (vh.count == 1) fast_find(r, jidx, vh, jh, false);
     }
-    if (hand) { hand[0] = half_word_of(vh); hand[1] = half_word_of(jh); }
+    if (hand) { hand[0] = half_word_of(vh); hand[1] = (!use_q && jidx && vh.count != 1) ? DCB_HIT_UNKNOWN : half_word_of(jh); }
     return dcr_fast_from_hits<false>(r, gene_tags(vcore), gene_tags(jcore), vh, jh, prm, both_frames, out, C, xp != nullptr,
                                      xp ? *xp : exc_probe_none());
 }
@@ -1142,7 +1143,7 @@ struct HalfView {
     const DcbHalfKw* kw;
     const uint8_t* tags;
     uint32_t c1, c2;
-    int hshift, v_split, j_split;
+    int hshift, v_split, j_split, j_ok;
 };
 DCB_HD HalfView half_view(const uint32_t* hb) {
     const DcbHalfIndex& hx = *reinterpret_cast<const DcbHalfIndex*>(hb);
@@ -1152,7 +1153,7 @@ DCB_HD HalfView half_view(const uint32_t* hb) {
     v.ids = reinterpret_cast<const uint8_t*>(hb + hx.ids_off);
     v.kw = reinterpret_cast<const DcbHalfKw*>(hb + hx.kw_off);
     v.tags = reinterpret_cast<const uint8_t*>(hb + hx.tags_off);
-    v.c1 = hx.c1; v.c2 = hx.c2; v.hshift = hx.hshift; v.v_split = hx.v_split; v.j_split = hx.j_split;
+    v.c1 = hx.c1; v.c2 = hx.c2; v.hshift = hx.hshift; v.v_split = hx.v_split; v.j_split = hx.j_split; v.j_ok = hx.j_ok;
     return v;
 }
 // A candidate: gene << 31 | kind << 29 (0 full tag, 1 half1, 2 half2) | end of the keyword occurrence << 19 |
@@ -1260,11 +1261,12 @@ DCB_HD void half_candidate(const ReadView& r, const uint32_t* inv2, const HalfVi
 // against it (a tag over a symbol packed as base 0 is no occurrence), which half sets have to be found.
 // false: pass the read on (several full-tag candidates that cannot be told apart here, or a read too long).
 DCB_HD bool half_begin(ReadView& r, const uint32_t*& inv2, bool flagged, const ExcList& ex, uint32_t e0, uint32_t* inv2col,
-                       const DcbTag* vtags, const DcbTag* jtags, uint32_t& hv, uint32_t& hj, uint32_t& need) {
+                       const DcbTag* vtags, const DcbTag* jtags, uint32_t& hv, uint32_t& hj, uint32_t& need, bool j_ok = true) {
     r.inv = nullptr; r.exc_pos = ex.pos; r.exc_kind = ex.kind; r.e0 = r.e1 = 0; r.mirror = 0;
     r.cand = nullptr; r.cand_kq = 0; r.hits = nullptr; r.n_hits = 0;
     inv2 = nullptr;
     need = 0;
+    if (hv == DCB_HIT_MULTI || hj == DCB_HIT_MULTI || r.n > DCB_HALF_MAX_READ) return false;
     if (flagged) {
         uint32_t e1 = e0;
         bool any = false;
@@ -1278,19 +1280,18 @@ DCB_HD bool half_begin(ReadView& r, const uint32_t*& inv2, bool flagged, const E
         r.e0 = (int)e0; r.e1 = (int)e1;
         if (any) inv2 = inv2col;
     }
-    if (hv == DCB_HIT_MULTI || hj == DCB_HIT_MULTI || r.n > DCB_HALF_MAX_READ) return false;
     if (inv2) {
         const ReadView ri = half_inv_view(r, inv2);
         for (int g = 0; g < 2; g++) {
             uint32_t& h = g ? hj : hv;
-            if (!h) continue;
+            if (!h || h == DCB_HIT_UNKNOWN) continue;
             const int P = (int)(h & 0xFFFFu), L = (g ? jtags : vtags)[(h >> 16) & 0x7FFFu].len;
             uint32_t ilo, ihi;
             rd_win32(ri, P, ilo, ihi);
             if ((ilo & mask2(L)) | (L > 16 ? (ihi & mask2(L - 16)) : 0u)) h = 0u;
         }
     }
-    need = (hv ? 0u : 0x00FFu) | (hj ? 0u : 0xFF00u);
+    need = (hv ? 0u : 0x00FFu) | ((hj || !j_ok) ? 0u : 0xFF00u);
     return true;
 }
 // vanalysis / janalysis over the sorted candidates of one gene, from entry `i` on (decombine.py:273-394, 397-531): the
@@ -1346,7 +1347,7 @@ DCB_HD bool half_run(const ReadView& r, const uint32_t* inv2, const HalfView& hx
     if (n > (uint32_t)cap) return false;
     for (int g = 0; g < 2; g++) {                                                           // the full-tag occurrences handed over
         const uint32_t h = g ? hj : hv;
-        if (!h) continue;
+        if (!h || h == DCB_HIT_UNKNOWN) continue;
         const int t = (int)((h >> 16) & 0x7FFFu), P = (int)(h & 0xFFFFu), L = (g ? jtags : vtags)[t].len;
         if (n < (uint32_t)cap) cand[n * r.stride] = DCB_HC_MAKE(g, 0, P + L, L, t, 0);
         n++;
@@ -1361,6 +1362,9 @@ DCB_HD bool half_run(const ReadView& r, const uint32_t* inv2, const HalfView& hx
     const uint32_t ev = half_select<true>(cand, r.stride, (int)n, i, pend);
     if (ev) ok = half_walk<true, PADDED>(r, inv2, hx, vtags, ev, 0, v);
     if (why) *why = 4;
+    // V is assigned: now J.  A J gene that was not searched for full tags, or whose half tags this index does not hold
+    // while the full tag is missing, is the general kernel's business.
+    if (ev && ok && (hj == DCB_HIT_UNKNOWN || (hj == 0u && !hx.j_ok))) return false;
     uint32_t ej = 0u;
     if (ev && ok) {                                                                         // :542-548
         ej = half_select<false>(cand, r.stride, (int)n, i, pend);
@@ -1388,8 +1392,8 @@ DCB_HD bool dcr_half_read(ReadView r, bool flagged, const ExcList& ex, uint32_t 
     const uint32_t* inv2;
     uint32_t need, pend = 0;
     if (why) *why = 1;
-    if (!half_begin(r, inv2, flagged, ex, e0, inv2col, vtags, jtags, hv, hj, need)) return false;
     const HalfView hx = half_view(hb);
+    if (!half_begin(r, inv2, flagged, ex, e0, inv2col, vtags, jtags, hv, hj, need, hx.j_ok != 0)) return false;
     uint32_t n = 0;
     struct Sink {
         const ReadView& r; const uint32_t* inv2; const HalfView& hx; const DcbTag* vtags; const DcbTag* jtags;

@@ -230,7 +230,9 @@ dcb_exact_kernel(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_res
             r.n = b.uniform_len ? (int)b.uniform_len : (int)__ldg(b.lens + ri);
             r.nw = (int)b.slot_words;
             r.exc_pos = nullptr; r.exc_kind = nullptr; r.e0 = r.e1 = 0; r.mirror = 0; r.cand = nullptr; r.cand_kq = 0; r.hits = nullptr; r.n_hits = 0;
-            action = dcr_exact_read(r, flagged, L.t[0], L.t[1], L.t[2], L.t[3], prm, both_frames, out, L.cnt);
+            uint32_t hand[2];
+            action = dcr_exact_read(r, flagged, L.t[0], L.t[1], L.t[2], L.t[3], prm, both_frames, out, L.cnt, false, nullptr, hand);
+            if (action == FAST_DEFER) *reinterpret_cast<uint4*>(results + ri) = make_uint4(hand[0], hand[1], 0u, 0u);   // for dcb_halftag_kernel
         }
         defer_reads(live && action == FAST_DEFER, ri, queue, queue_count);
         if (live && action == FAST_DONE) store_result(results + ri, out);
@@ -412,6 +414,11 @@ dcb_exact_kernel_spec(BatchDev b, Tables4 tb, SpecBlooms bl, DcrParams prm, int 
         else if (live) action = FAST_DEFER;
         defer_reads(live && action == FAST_DEFER, ri, queue, queue_count);
         if (live && action == FAST_DONE) store_result(results + ri, out);
+        else if (live) {
+            // hand-over to dcb_halftag_kernel: what the search found; J was only searched for reads with one full V tag
+            const uint32_t hj = (!UNION && vh.count != 1) ? DCB_HIT_UNKNOWN : half_word_of(jh);
+            *reinterpret_cast<uint4*>(results + ri) = scan ? make_uint4(half_word_of(vh), hj, 0u, 0u) : make_uint4(DCB_HIT_MULTI, DCB_HIT_MULTI, 0u, 0u);
+        }
     }
     flush_counters(L.cnt, counters);
 }
@@ -733,7 +740,7 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
             const uint32_t e0 = hand.z;           // the read's first entry in the exception list, from the exact-tag kernel
             ExcList exr = ex;
             if (flagged) exr.n = __ldg(b.exc_index + (ri >> 5) + 1);   // its entries end inside its 32-read group's run
-            act = half_begin(r, inv2, flagged, exr, e0, icol, vtags, jtags, hv, hj, need);
+            act = half_begin(r, inv2, flagged, exr, e0, icol, vtags, jtags, hv, hj, need, hx.j_ok != 0);
         }
         if (!act) need = 0;
         s_n[tid] = 0u;
@@ -1333,7 +1340,7 @@ static int prepare_batch(dcb_ctx* c, const dcb_packed* P, size_t exc_cap = 0) {
     }
     // half-tag kernel: between the flat kernel and the general kernel, for chains with a half-tag index (one frame only)
     c->half_fn = nullptr;
-    if (qfn && c->d_half && !c->params.both_frames && c->params.force_general == 0) {
+    if (c->d_half && !c->params.both_frames && c->params.force_general == 0) {
         int ht = 0;
         halftag_fn hf = pick_half((int)sw, &ht);
         c->half_threads = ht;
@@ -1420,7 +1427,7 @@ static int launch_range(dcb_ctx* c, cudaStream_t s, uint32_t first, uint32_t cou
     }
     Tables4 tg;
     tg.g[3] = nullptr; tg.words[3] = 0;
-    if (c->half_fn && c->q_fn) {   // the queued reads through the half-tag kernel; what it passes on is the general kernel's queue
+    if (c->half_fn) {   // the queued reads through the half-tag kernel; what it passes on is the general kernel's queue
         if (timed && (rc = timing_begin(c, 2))) return rc;
         uint32_t* qcount2 = c->d_queue_count + kMaxChunks + slot;
         uint32_t* queue2 = (uint32_t*)c->queue2.p + first;
@@ -1796,10 +1803,10 @@ int dcb_last_deferred(dcb_ctx* c, uint64_t* n) {
 int dcb_last_general(dcb_ctx* c, uint64_t* n) {
     if (!c || !n || !c->ran) return DCB_EINVAL;
     if (c->params.force_general == 1) { *n = c->batch.n_reads; return DCB_OK; }
-    return sum_queue_counts(c, (c->half_fn && c->q_fn) ? 1 : 0, n);
+    return sum_queue_counts(c, c->half_fn ? 1 : 0, n);
 }
 const char* dcb_halftag_kernel_name(const dcb_ctx* c) {
-    return (c && c->have_batch && c->half_fn && c->q_fn) ? "dcb_halftag_kernel" : "";
+    return (c && c->have_batch && c->half_fn) ? "dcb_halftag_kernel" : "";
 }
 
 }  // extern "C"

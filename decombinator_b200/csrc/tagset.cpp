@@ -433,8 +433,12 @@ bool dcb_build_half_index(const dcb_tagset* v, const dcb_tagset* j, std::vector<
     hx.v_split = v->split; hx.j_split = j->split;
     struct Kw { std::string s; int set; std::vector<int> tags; };
     std::vector<Kw> kws;                                            // distinct keywords per set, in order of first use
+    hx.j_ok = 1;
+    for (int t = 0; t < j->n_tags; t++)
+        if (j->split < hx.kmin || (int)j->tags[t].size() - j->split < hx.kmin) hx.j_ok = 0;
     for (int gi = 0; gi < 2; gi++) {
         const dcb_tagset* ts = gi ? j : v;
+        if (gi == 1 && !hx.j_ok) break;                             // J halves too short: the V side only
         for (int half = 0; half < 2; half++) {
             std::map<std::string, size_t> seen;
             for (int t = 0; t < ts->n_tags; t++) {

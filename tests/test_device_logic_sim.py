@@ -101,12 +101,36 @@ def test_sim_half_tag_path_matches_oracle(chain, L, sub, nrate):
     packed.free()
 
 
-def test_half_index_only_for_long_half_tags():
-    """The sampled index needs half tags of >= 10 bases: every `extended` chain has one, chains with a 6-base J split none."""
-    for sp, ts, ch, want in (("human", "extended", "a", True), ("human", "extended", "b", True), ("human", "original", "a", False),
-                             ("human", "original", "b", False), ("mouse", "original", "g", False)):
+def test_half_index_covers_j_only_with_long_half_tags():
+    """The sampled index needs half tags of >= 10 bases: every chain has one for its V side (the V split is 10); the J
+    side is in it only for the `extended` sets (a 6-base J split leaves it out: j_ok = 0)."""
+    for sp, ts, ch, j_ok in (("human", "extended", "a", 1), ("human", "extended", "b", 1), ("human", "original", "a", 0),
+                             ("human", "original", "b", 0), ("mouse", "original", "g", 0), ("mouse", "original", "d", 0)):
         vt, jt = tags.load(sp, ts, ch).tables()
-        assert (_lib.half_index(vt, jt) is not None) == want
+        hx = _lib.half_index(vt, jt)
+        assert hx is not None
+        assert int(hx[17]) == j_ok, (sp, ts, ch, hx[:20])       # DcbHalfIndex.j_ok
+
+
+@pytest.mark.parametrize("species,tagset,chain,L,sub,nrate", [("mouse", "original", "g", 250, 0.005, 0.0), ("mouse", "original", "d", 250, 0.005, 0.001),
+                                                              ("human", "original", "b", 250, 0.01, 0.001), ("human", "original", "a", 150, 0.01, 0.0)])
+def test_sim_half_tag_path_v_side_only(species, tagset, chain, L, sub, nrate):
+    """Chains with a 6-base J split: the half-tag path decides the reads whose V fails or whose J tag is whole, and passes
+    the rest on; mixed with reads of another chain (no V tag at all), as in a file analysed once per chain."""
+    info = tags.load(species, tagset, chain)
+    other = tags.load(species, tagset, {"g": "d", "d": "g", "a": "b", "b": "a"}[chain])
+    vt, jt = info.tables()
+    n = 30000
+    r1, off, ln = synth_batch(info, n, L, sub, nrate, 0.02, seed=31, sets=[(info.v_regions, info.j_regions), (other.v_regions, other.j_regions)])
+    orc = O.Oracle(O.TagSet(species, tagset, chain))
+    want = orc.decombine_arrays(r1, off, ln, "reverse", nthreads=4)
+    packed = _lib.pack_arrays(r1, off, ln, revcomp=True)
+    use_q = _lib.union_index(vt, jt) is not None
+    res, cnt, nd, nd2 = simlib.sim_decombine(packed, vt, jt, use_q=use_q, use_half=True, want_deferred2=True)
+    assert_records_equal(res, want, "reverse")
+    assert np.array_equal(cnt, orc.counts)
+    assert nd > 0.5 * n and nd2 < 0.5 * nd           # most of what the exact search queues is decided without the general path
+    packed.free()
 
 
 def sweep_reads(info, L, seed=5):
