@@ -83,6 +83,18 @@ def cpu_reference_run(r1, off, ln, threads, steps=1, warmup=0):
     return len(off) * steps / dt, dt / steps, int(res["ok"].sum())
 
 
+def reference_timing():
+    """The unmodified reference (pure Python + stand-ins for its absent wheels, compiled Aho-Corasick behind `acora`) on one
+    core: measured by oracle/time_reference.py in the build container -- /root/reference does not exist on the GPU box --
+    and committed under profiles/."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_reference_cpu_timing.json")))
+        return {"value": t["value"], "unit": UNIT, "cores": 1, "kind": "reference", "cpu": t["cpu"], "where": t["where"],
+                "sample": t["workload"], "source": "profiles/r02_reference_cpu_timing.json (oracle/time_reference.py)"}
+    except Exception:
+        return None
+
+
 def run_mixed(args, rank, world, local_rank, host_threads, stream, barrier, species, tagset, chains, seed, sub, nrate, label):
     """One mixed file (read i is a molecule of chain i % len(chains)) analysed once per chain, as the reference's example
     runs `-c a` and `-c b` on the same FASTQ.  Batch resident in HBM, K passes of all kernels per chain, CUDA events on
@@ -334,20 +346,29 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        # Nothing of the product is on this path: reads come from libdcbsynth.so (the generator alone), the timed call is the
+        # oracle's C port (oracle/liboracle.so) on all host threads.  The reference itself is pure Python with native deps that
+        # cannot be installed offline; its own speed (with stand-ins) is quoted from profiles/r02_reference_cpu_timing.json.
         threads = os.cpu_count() or 1
-        n = min(args.reads, 4_000_000)
+        n = args.reads
         r1, off, ln = make_reads(info, 0, n, threads, args.sub_rate, args.n_rate)
-        rps, sec, _ = cpu_reference_run(r1, off, ln, threads, steps=max(1, args.steps), warmup=min(1, args.warmup))
+        rps, sec, _ = cpu_reference_run(r1, off, ln, threads, steps=1, warmup=1)        # warm pass, then the size of a step
+        steps = max(1, args.steps)
+        # a step is a bounded sample of the workload: the whole run (K steps + W warm-ups) stays under about two minutes
+        sample = int(min(n, max(100_000, rps * 100.0 / (steps + max(1, args.warmup)))))
+        rps, sec, _ = cpu_reference_run(r1[:sample * READ_LEN], off[:sample], ln[:sample], threads, steps=steps, warmup=max(1, args.warmup))
         line = {"impl": "reference", "metric": METRIC, "value": rps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": rps, "unit": UNIT, "cores": threads, "kind": "port",
-                                 "sample": "first %d reads of the workload per step, ASCII in host memory, C port of the "
-                                           "reference's dcr() incl. revcomp, pthreads" % n},
+                                 "sample": "first %d reads of the workload per step (of %d), ASCII in host memory, C port of the "
+                                           "reference's dcr() incl. revcomp, pthreads, after %d warm-up passes" % (sample, n, max(1, args.warmup))},
+                "cpu_baseline_reference": reference_timing(),
                 "e2e": {"value": rps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "note": "the reference is pure Python with un-installable native deps (acora, Levenshtein, biopython); "
                         "this arm times the oracle's C restatement of the same algorithm, which is pinned against "
-                        "fixtures recorded from the unmodified reference"}
+                        "fixtures recorded from the unmodified reference; cpu_baseline_reference is the unmodified reference "
+                        "itself, timed in the build container"}
         print(json.dumps(line), file=_JSON_OUT, flush=True)
         return
 
@@ -428,6 +449,18 @@ def main():
             res_a, cnt_a = ctx.decombine_ascii(text.a, None, None, True, uniform_len=READ_LEN, pinned=True)
         e_ms = (time.perf_counter() - e0) * 1e3
         assert np.array_equal(res_a, res0) and np.array_equal(cnt_a, cnt0)
+        # ---- the ceiling e2e runs against: page-locked host -> device copies of the same text, all ranks at once --------
+        dev_buf = torch.empty(len(text.a), dtype=torch.uint8, device="cuda")
+        host_t = torch.from_numpy(text.a)          # a view of the page-locked buffer
+        for _ in range(2):
+            dev_buf.copy_(host_t, non_blocking=True)
+        barrier()
+        c0 = time.perf_counter()
+        for _ in range(5):
+            dev_buf.copy_(host_t, non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_gbps = 5 * len(text.a) / (time.perf_counter() - c0) / 1e9
+        del dev_buf, host_t
         text.free()
     exact_name, h2d_bytes = ctx.exact_kernel_name(), packed.h2d_bytes()
 
@@ -445,6 +478,9 @@ def main():
         t = torch.tensor([ms_total, e_ms, ep_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, e_ms, ep_ms = float(t[0]), float(t[1]), float(t[2])
+        t = torch.tensor([h2d_gbps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        h2d_gbps = float(t[0])
         ok = torch.tensor([int(res0["status"].sum())], device="cuda", dtype=torch.int64)
         dist.all_reduce(ok)
         decombined = int(ok[0])
@@ -485,7 +521,11 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(n * READ_LEN),
                     "d2h_bytes_per_step": int(n * 16 + 8 * _lib.NCOUNTERS), "steps": e2e_steps,
                     "call": "dcb_decombine_ascii: ASCII reads in page-locked host memory in (the reference arm's input), packed on "
-                            "the device, result records in host memory out"},
+                            "the device, result records in host memory out",
+                    "h2d_ceiling": {"GBps_per_gpu": h2d_gbps, "GBps_all_gpus": h2d_gbps * world,
+                                    "how": "torch copy_ of the same page-locked text to the device, all ranks at once, slowest rank",
+                                    "reads_per_s_at_ceiling": h2d_gbps * 1e9 / READ_LEN * world,
+                                    "e2e_frac_of_ceiling": e2e / (h2d_gbps * 1e9 / READ_LEN * world)}},
             "e2e_packed": {"value": world * n * e2e_steps / (ep_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                            "d2h_bytes_per_step": int(n * 16 + 8 * _lib.NCOUNTERS), "steps": e2e_steps,
                            "call": "dcb_decombine_batch: reads 2-bit packed on the host beforehand (outside the timed region)"},
@@ -497,9 +537,10 @@ def main():
         if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only
             threads = os.cpu_count() or 1
             sample = args.cpu_sample or min(n, 2_000_000 if threads < 16 else 10_000_000)
-            rps, sec, _ = cpu_reference_run(r1[:sample * READ_LEN], off[:sample], ln[:sample], threads)
+            rps, sec, _ = cpu_reference_run(r1[:sample * READ_LEN], off[:sample], ln[:sample], threads, steps=2, warmup=1)
             line["cpu_baseline"] = {"value": rps, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "first %d reads of rank 0's shard, one pass, %.1f s" % (sample, sec)}
+                                    "sample": "first %d reads of rank 0's shard, mean of two passes after a warm-up pass, %.1f s each" % (sample, sec)}
+            line["cpu_baseline_reference"] = reference_timing()
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()

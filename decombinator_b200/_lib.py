@@ -585,13 +585,32 @@ class Context:
             pass
 
 
+_synth = None
+
+
+def synth_lib():
+    """libdcbsynth.so: the synthetic read generator in a library of its own, so that a process which only generates reads
+    (bench.py --impl reference) never maps libdcb.so."""
+    global _synth
+    if _synth is None:
+        L = ctypes.CDLL(_build.build_synth())
+        cpp = ctypes.POINTER(ctypes.c_char_p)
+        L.dcb_synth_create.restype = ctypes.c_void_p
+        L.dcb_synth_create.argtypes = [ctypes.POINTER(CSynthParams), ctypes.c_int, ctypes.POINTER(cpp), ctypes.POINTER(ctypes.c_int),
+                                       ctypes.POINTER(cpp), ctypes.POINTER(ctypes.c_int)]
+        L.dcb_synth_destroy.argtypes = [ctypes.c_void_p]
+        L.dcb_synth_reads.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        _synth = L
+    return _synth
+
+
 class Synth:
     """dcb_synth: deterministic synthetic read generator."""
 
     def __init__(self, gene_sets, seed, read_len, read2_len=0, sub_rate=0.0, n_rate=0.0, junk_rate=0.0, umi_pool=0,
                  sub_rate2=0.0):
         """gene_sets: list of (v_regions, j_regions); read i is drawn from set i % len(gene_sets)."""
-        L = lib()
+        L = synth_lib()
         self.read_len, self.read2_len = int(read_len), int(read2_len)
 
         def prob(x):
@@ -614,14 +633,14 @@ class Synth:
         r1 = np.empty(n * self.read_len, dtype=np.uint8)
         r2 = np.empty(n * self.read2_len, dtype=np.uint8) if (want_r2 and self.read2_len) else None
         nt = n_threads or min(32, os.cpu_count() or 1)
-        _check(lib().dcb_synth_reads(self._h, int(first), int(n), r1.ctypes.data,
-                                     r2.ctypes.data if r2 is not None else None, nt), "dcb_synth_reads")
+        if synth_lib().dcb_synth_reads(self._h, int(first), int(n), r1.ctypes.data, r2.ctypes.data if r2 is not None else None, nt) != 0:
+            raise DcbError("dcb_synth_reads failed")
         return r1, r2
 
     def __del__(self):
         try:
             if self._h:
-                lib().dcb_synth_destroy(self._h)
+                synth_lib().dcb_synth_destroy(self._h)
                 self._h = None
         except Exception:
             pass

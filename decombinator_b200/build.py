@@ -11,6 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdcb.so")
+SYNTH_LIB = os.path.join(HERE, "libdcbsynth.so")   # the synthetic read generator alone (bench.py's reference arm maps only this + oracle/)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 SOURCES = ["decombine.cu", "collapse.cu", "tagset.cpp", "pack.cpp", "fastq.cpp", "synth.cpp", "error.cpp"]
@@ -44,7 +45,21 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libdcb.so")
     with open(os.path.join(HERE, "build.log"), "w") as fh:
         fh.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+    build_synth(force=True)
     return LIB
+
+
+def build_synth(force=False):
+    """libdcbsynth.so: csrc/synth.cpp alone (plain C++, no CUDA)."""
+    src = [os.path.join(CSRC, "synth.cpp"), os.path.join(CSRC, "error.cpp")]
+    if not force and os.path.exists(SYNTH_LIB) and all(os.path.getmtime(x) <= os.path.getmtime(SYNTH_LIB) for x in src):
+        return SYNTH_LIB
+    cmd = ["g++", "-O3", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(os.path.dirname(HERE), "include"), "-o", SYNTH_LIB] + src + ["-lpthread"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building libdcbsynth.so")
+    return SYNTH_LIB
 
 
 if __name__ == "__main__":
