@@ -370,7 +370,12 @@ def _device_barcodes(rows, inputargs, qp):
                                        inputargs["allowNs"] != False, qp[0], qp[1], qp[2])  # noqa: E712
     sym = (code[:, None] >> (np.uint64(3) * np.arange(12, dtype=np.uint64))[None, :]) & np.uint64(7)
     text = _BC_SYMBOLS[sym.astype(np.intp)].tobytes().decode("ascii")          # 12 characters per row, back to back
-    # the reference's counters for the rows decided on the device (collapse.py:241-278, 388-422, 546-553)
+    _count_device_barcodes(status, n1)
+    return status, text
+
+
+def _count_device_barcodes(status, n1):
+    """The reference's counters for the rows decided on the device (collapse.py:241-278, 388-422, 546-553)."""
     st = np.bincount(status, minlength=256)
     for key, k in (("getbarcode_fail_N", st[_lib.BC_FAIL_N]), ("getbarcode_fail_nospacerfound", st[_lib.BC_FAIL_NOSPACER]),
                    ("getbarcode_fail_not2spacersfound", st[_lib.BC_FAIL_NOT2]), ("getbarcode_fail_n1tooshort", st[_lib.BC_FAIL_N1SHORT]),
@@ -384,7 +389,30 @@ def _device_barcodes(rows, inputargs, qp):
                    ("readdata_short_barcode", (placed & (n1 < 6)).sum()), ("readdata_long_barcode", (placed & (n1 > 6)).sum())):
         if k:
             counts[key] += int(k)
-    return status, text
+
+
+def _filter_columns(data, inputargs, barcode_quality_parameters, first_index=0):
+    """_filter_rows for the columnar hand-over of `pipeline` (decombine.RowsColumns): the barcode regions and their
+    qualities go to the device as (offset, length) columns into the FASTQ text -- no Python string per row -- and rows
+    are only materialised for the reads the barcode kernel lets through or hands back.  Same results, same counters.
+    None when this run has no device path for the barcodes (the caller then takes the rows)."""
+    name = inputargs["oligo"].lower()
+    if name not in _lib.OLIGOS_ON_DEVICE or inputargs["sampling_analysis"] or "allowNs" not in inputargs or len(data) == 0:
+        return None
+    ids, vdj, qual, bc, bcq, _ = data.columns
+    hits = data.hits
+    bbuf = np.frombuffer(bc.buf, dtype=np.uint8)
+    qbuf = np.frombuffer(bcq.buf, dtype=np.uint8)
+    status, n1, code = _gpu().barcodes_arrays(bbuf, np.asarray(bc.off)[hits], np.asarray(bc.len)[hits], qbuf, np.asarray(bcq.off)[hits],
+                                              np.asarray(bcq.len)[hits], _lib.OLIGOS_ON_DEVICE[name], inputargs["allowNs"] != False,  # noqa: E712
+                                              *barcode_quality_parameters)
+    _count_device_barcodes(status, n1)
+    keep = (status == _lib.BC_OK) | (status == _lib.BC_HOST)
+    rows = data.subset_rows(keep)                       # only these become Python rows
+    sym = (code[keep][:, None] >> (np.uint64(3) * np.arange(12, dtype=np.uint64))[None, :]) & np.uint64(7)
+    text = _BC_SYMBOLS[sym.astype(np.intp)].tobytes().decode("ascii")
+    where = np.nonzero(keep)[0]
+    return rows, status[keep].tolist(), text, (first_index + where).tolist(), int(len(status))
 
 
 def _filter_rows(data, inputargs, barcode_quality_parameters, dont_count, from_file, first_index=0):
@@ -397,14 +425,19 @@ def _filter_rows(data, inputargs, barcode_quality_parameters, dont_count, from_f
     -> ([(global row index, barcode, seq, dcretc), ...] for the rows that survive, Counter of str(dcr), rows seen).
     Rows are independent here, so a multi-GPU run calls this on each rank's shard (parallel.py)."""
     t0 = time.time()
-    rows = [line.rstrip("\n").split(", ") for line in data] if from_file else (data if isinstance(data, list) else list(data))
-    dev = _device_barcodes(rows, inputargs, barcode_quality_parameters)
+    columnar = _filter_columns(data, inputargs, barcode_quality_parameters, first_index) if hasattr(data, "subset_rows") else None
+    index = None
+    if columnar is not None:
+        rows, status, text, index, n_rows = columnar
+    else:
+        rows = [line.rstrip("\n").split(", ") for line in data] if from_file else (data if isinstance(data, list) else list(data))
+        dev = _device_barcodes(rows, inputargs, barcode_quality_parameters)
+        n_rows = len(rows)
+        status = dev[0].tolist() if dev is not None else None
+        text = dev[1] if dev is not None else None
     kept = []
     input_dcr_counts = coll.Counter()
-    n_rows = len(rows)
     counts["readdata_input_dcrs"] += n_rows
-    status = dev[0].tolist() if dev is not None else None
-    text = dev[1] if dev is not None else None
     lenthreshold, sampling = inputargs["lenthreshold"], inputargs["sampling_analysis"]
     n_long = n_ok = 0
     HOST, OK = _lib.BC_HOST, _lib.BC_OK
@@ -436,7 +469,7 @@ def _filter_rows(data, inputargs, barcode_quality_parameters, dont_count, from_f
             dcretc = "|".join([dcr, seq, line[7], line[5], barcode, barcode_qualstring, line[8], line[10]])
         else:
             dcretc = "|".join((dcr, seq, line[7], line[5]))
-        kept.append((first_index + lcount, barcode, seq, dcretc))
+        kept.append((index[lcount] if index is not None else first_index + lcount, barcode, seq, dcretc))
     if n_long:
         counts["readdata_fail_overlong_intertag_seq"] += n_long
     if n_ok:

@@ -131,6 +131,48 @@ class RowsText:
         return [line.split(", ") for line in bytes(self.text).decode("ascii").split("\n")[:-1]]
 
 
+class RowsColumns:
+    """The rows of a run kept COLUMNAR: the result records of the kernels plus the FASTQ text columns they index.  This is
+    what `pipeline` hands from decombine to collapse instead of a list of ten Python strings per read: collapse locates the
+    barcodes straight from the text columns on the device and only builds strings for the rows that survive its filters.
+
+    Anything that wants the reference's ``list[list[str]]`` still gets it: len(), iteration, indexing and ``rows()``
+    materialise the rows (through dcb_format_rows), ``text`` is the .n12 text for the writer."""
+
+    def __init__(self, res, hits, columns, pack_rc):
+        self.res, self.hits, self.columns, self.pack_rc = res, hits, columns, pack_rc
+        self._rows = self._text = None
+
+    def __len__(self):
+        return int(len(self.hits))
+
+    @property
+    def text(self):
+        if self._text is None:
+            self._text = _lib.format_rows(self.res, self.pack_rc, self.columns, ", ")[0]
+        return self._text
+
+    def subset_rows(self, keep):
+        """list[list[str]] of the hits selected by the boolean mask `keep` (over the hits), in order."""
+        res = self.res
+        if not bool(np.all(keep)):
+            res = res.copy()
+            res["status"][self.hits[~np.asarray(keep, dtype=bool)]] = 0
+        blob, _ = _lib.format_rows(res, self.pack_rc, self.columns, "\x1f")
+        return [line.split("\x1f") for line in blob.tobytes().decode("ascii").split("\n")[:-1]]
+
+    def rows(self):
+        if self._rows is None:
+            self._rows = self.subset_rows(np.ones(len(self.hits), dtype=bool))
+        return self._rows
+
+    def __iter__(self):
+        return iter(self.rows())
+
+    def __getitem__(self, i):
+        return self.rows()[i]
+
+
 def decombine_batch(batch: fastq.ReadBatch, inputargs):
     """GPU pass over every V(D)J read of the batch -> dcb_result array (one record per read)."""
     pack_rc, both = _orientation_plan(inputargs["orientation"])
@@ -296,7 +338,11 @@ def decombinator(inputargs: dict) -> list:
             # field separator cannot occur in the data, and split here at C speed
             sep = "\x1f"
             cols = (batch.ids, batch.vdj, batch.vdjqual, batch.bc, batch.bcq, batch.v_tail if sampling else None)
-            if inputargs.get("rows_as_text"):
+            if inputargs.get("rows_as_columns") and not any(c.buf.find(sep.encode()) != -1 for c in {id(c.buf): c for c in cols if c is not None}.values()):
+                # `pipeline`: the next stage takes the columns themselves
+                outdata = RowsColumns(res, hits, cols, pack_rc)
+                hits = ()
+            elif inputargs.get("rows_as_text"):
                 # the `decombine` command only writes the rows: with the .n12 separator the buffer IS the file's text
                 blob, nrows = _lib.format_rows(res, pack_rc, cols, ", ")
                 assert nrows == len(hits)

@@ -41,6 +41,7 @@ def run(args=None, cli_args=None):
             write_out_translated(data, inputargs)
         print(f"Pipeline complete in {datetime.now() - start}")
         return data
+    inputargs["rows_as_columns"] = True          # the rows stay columnar between the stages (decombine.RowsColumns)
     data = decombinator(inputargs)
     if not inputargs["dontsave"]:
         write_out_intermediate(data, inputargs, ".n12")

@@ -207,3 +207,42 @@ def test_cli_commands_write_the_golden_files(golden_dir, tmp_path, chain, name, 
                                       "-op", str(out4) + os.sep])
     pipeline.main()
     assert (out4 / ("dcr_TINY_1_%s.tsv" % name)).read_bytes() == open(os.path.join(golden_dir, "dcr_TINY_1_%s.tsv" % name), "rb").read()
+
+
+@gpu
+def test_columnar_hand_over_equals_row_hand_over(tmp_path):
+    """`pipeline` hands decombine.RowsColumns to collapse (barcodes located on the device straight from the FASTQ text
+    columns, strings only for surviving rows); the result, the counters and the .n12 text must equal the hand-over of
+    list[list[str]] rows -- on reads with repeated UMIs, substitutions in the barcode region (fuzzy spacers: host path),
+    low-quality barcodes and N."""
+    import collections as coll
+    import numpy as np
+    from decombinator_b200 import _lib, collapse, tags
+    info = tags.load("human", "extended", "b")
+    n, L = 30000, 250
+    syn = _lib.Synth([(info.v_regions, info.j_regions)], 77, L, 62, 0.005, 0.0005, 0.02, umi_pool=1500, sub_rate2=0.01)
+    r1, r2 = syn.reads(0, n, want_r2=True)
+    rng = np.random.default_rng(3)
+    q2 = np.full((n, 62), ord("I"), dtype=np.uint8)
+    low = rng.random(n) < 0.05
+    q2[low, 22:28] = ord("#")
+    for path, arr, ln, q in ((tmp_path / "s_1.fq", r1, L, None), (tmp_path / "s_2.fq", r2, 62, q2)):
+        a = arr.reshape(n, ln)
+        with open(path, "wb") as fh:
+            fh.write(b"".join(b"@SYN:%d 1:N:0\n%s\n+\n%s\n" % (i, a[i].tobytes(), (q[i].tobytes() if q is not None else b"I" * ln))
+                              for i in range(n)))
+    base = _args(str(tmp_path / "s_1.fq"), "b", tmp_path, suppresssummary=True, dontcheck=True, oligo="M13", command="pipeline")
+    out, cnts, texts = {}, {}, {}
+    for mode in ("rows", "columns"):
+        a = dict(base)
+        if mode == "columns":
+            a["rows_as_columns"] = True
+        data = decombine.decombinator(a)
+        assert isinstance(data, decombine.RowsColumns) == (mode == "columns")
+        texts[mode] = bytes(data.text) if mode == "columns" else "".join(", ".join(r) + "\n" for r in data).encode()
+        out[mode] = collapse.collapsinator(dict(a), data=data)
+        cnts[mode] = {k: v for k, v in collapse.counts.items() if "time" not in k}
+    assert texts["rows"] == texts["columns"]
+    assert out["rows"] == out["columns"] and len(out["rows"]) > 500
+    assert cnts["rows"] == cnts["columns"]
+    assert cnts["rows"]["getbarcode_pass_regexmatch"] > 0 and cnts["rows"]["readdata_fail_low_barcode_quality"] > 0
