@@ -123,6 +123,7 @@ def lib():
     L.dcb_dist_create.argtypes = [i32]
     L.dcb_dist_destroy.argtypes = [vp]
     L.dcb_umi_pairs.argtypes = [vp, vp, u32, i32, vp, u64, ctypes.POINTER(u64)]
+    L.dcb_umi_pairs_part.argtypes = [vp, vp, u32, i32, u32, u32, vp, u64, ctypes.POINTER(u64)]
     L.dcb_lev_leq.argtypes = [vp, vp, vp, vp, u32, vp, vp, u64, ctypes.c_double, vp]
     L.dcb_barcodes.argtypes = [vp, vp, vp, vp, vp, vp, vp, u64, ctypes.POINTER(CBcParams), vp, vp, vp]
     L.dcb_dist_last_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
@@ -676,6 +677,23 @@ def encode_umis(umis):
     return out
 
 
+def encode_umis_fixed(umis):
+    """encode_umis with the FIXED alphabet A C G T N S L = 0..6 (what dcb_barcodes emits): the same code for the same UMI on
+    every rank of a multi-GPU run, whatever symbols a rank happens to hold."""
+    table = {c: i for i, c in enumerate(_BASE_ALPHABET)}
+    out = np.zeros(len(umis), dtype=np.uint64)
+    for i, u in enumerate(umis):
+        if len(u) > UMI_MAX_LEN:
+            raise DcbError("UMI %r is longer than %d symbols" % (u, UMI_MAX_LEN))
+        v = len(u) << 58
+        for k, ch in enumerate(u):
+            if ch not in table:
+                raise DcbError("UMI %r holds a symbol outside %s" % (u, _BASE_ALPHABET))
+            v |= table[ch] << (3 * k)
+        out[i] = v
+    return out
+
+
 def encode_seqs(seqs):
     """list[str] -> (symbols uint8, off uint64, len uint32) for dcb_lev_leq."""
     codes = _alphabet(seqs)
@@ -699,12 +717,13 @@ class Dist:
         if not self._h:
             raise DcbError("dcb_dist_create: " + L.dcb_last_error().decode())
 
-    def umi_pairs(self, codes, max_edits):
-        """-> (row, col) int64 arrays: every pair row < col within max_edits, ascending (row, col)."""
+    def umi_pairs(self, codes, max_edits, part=0, n_parts=1):
+        """-> (row, col) int64 arrays: every pair row < col within max_edits, ascending (row, col).  n_parts > 1: this
+        GPU's share of a search split over n_parts GPUs (the union of the shares is the whole list)."""
         codes = np.ascontiguousarray(codes, dtype=np.uint64)
         n = ctypes.c_uint64()
-        _check(lib().dcb_umi_pairs(self._h, codes.ctypes.data, len(codes), int(max_edits), None, 0, ctypes.byref(n)),
-               "dcb_umi_pairs")
+        _check(lib().dcb_umi_pairs_part(self._h, codes.ctypes.data, len(codes), int(max_edits), int(part), int(n_parts), None, 0,
+                                        ctypes.byref(n)), "dcb_umi_pairs")
         keys = np.zeros(n.value, dtype=np.uint64)
         if n.value:
             _check(lib().dcb_umi_pairs(self._h, None, 0, 0, keys.ctypes.data, n.value, ctypes.byref(n)), "dcb_umi_pairs")

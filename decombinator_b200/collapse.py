@@ -652,12 +652,13 @@ def write_clusters(clusters, inputargs):
                 fh.write(name + "|" + dcretc + "\n")
 
 
-def cluster_UMIs(barcode_dcretc, inputargs, barcode_threshold, lev_threshold_fraction, dont_count):
-    """Merge groups with neighbouring barcodes and equivalent proto-sequences (collapse.py:851-894)."""
+def cluster_UMIs(barcode_dcretc, inputargs, barcode_threshold, lev_threshold_fraction, dont_count, find_pairs=None):
+    """Merge groups with neighbouring barcodes and equivalent proto-sequences (collapse.py:851-894).
+    find_pairs: how to search the UMI pairs (default make_merge_groups on this GPU; parallel.py splits it over the ranks)."""
     print("Clustering barcode groups...")
     num_initial_groups, barcode_dcretc_list, umi_protoseq_tuple = create_clustering_objs(barcode_dcretc)
     t0 = time.time()
-    matches = make_merge_groups(umi_protoseq_tuple, barcode_threshold, dont_count)
+    matches = (find_pairs or make_merge_groups)(umi_protoseq_tuple, barcode_threshold, dont_count)
     print("  ", "comparing TCR sequences of similar UMIs...")
     clusters = make_clusters(matches, barcode_dcretc_list, lev_threshold_fraction)
     print("  ", num_initial_groups, "groups merged into", len(clusters), "clusters")
@@ -667,9 +668,10 @@ def cluster_UMIs(barcode_dcretc, inputargs, barcode_threshold, lev_threshold_fra
     return clusters
 
 
-def _count_clusters(barcode_dcretc, inputargs, barcode_distance_threshold, lev_threshold_fraction, dont_count, outpath, file_id):
+def _count_clusters(barcode_dcretc, inputargs, barcode_distance_threshold, lev_threshold_fraction, dont_count, outpath, file_id,
+                    find_pairs=None):
     """cluster -> count (collapse.py:919-976), from the initial groups on."""
-    clusters = cluster_UMIs(barcode_dcretc, inputargs, barcode_distance_threshold, lev_threshold_fraction, dont_count)
+    clusters = cluster_UMIs(barcode_dcretc, inputargs, barcode_distance_threshold, lev_threshold_fraction, dont_count, find_pairs)
 
     print("Collapsing clusters...")
     t0 = time.time()

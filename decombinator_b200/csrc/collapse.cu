@@ -45,8 +45,10 @@ static constexpr int kPairTile = 256;
 // grid.x enumerates the tile pairs (bi <= bj) of the upper triangle
 __global__ void __launch_bounds__(kPairTile)
 dcb_umi_pairs_kernel(const uint64_t* __restrict__ codes, uint32_t n, int k, uint32_t n_tiles,
-                     unsigned long long* __restrict__ keys, unsigned long long cap, unsigned long long* __restrict__ count) {
+                     unsigned long long* __restrict__ keys, unsigned long long cap, unsigned long long* __restrict__ count,
+                     uint32_t part, uint32_t n_parts) {
     __shared__ uint64_t s_j[kPairTile];
+    if (blockIdx.x % n_parts != part) return;            // a multi-GPU search: every GPU takes its share of the tile pairs
     // decode the linear block index into (bi, bj), bi <= bj: row bi of the triangle starts at bi*n_tiles - bi*(bi-1)/2
     unsigned long long lin = blockIdx.x;
     uint32_t bi = 0;
@@ -149,7 +151,7 @@ __device__ __forceinline__ bool umi_share_one_deletion(uint64_t a, uint64_t b) {
 __global__ void __launch_bounds__(256)
 dcb_umi_runs_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ ids, uint64_t n_entries,
                     const uint64_t* __restrict__ codes, int k, unsigned long long* __restrict__ out, unsigned long long cap,
-                    unsigned long long* __restrict__ count) {
+                    unsigned long long* __restrict__ count, uint32_t part, uint32_t n_parts) {
     __shared__ uint64_t s_key[256], s_code[256];
     __shared__ uint32_t s_id[256];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -162,6 +164,8 @@ dcb_umi_runs_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restric
     // variant.  The entries were generated in UMI order and the radix sort is stable: such copies are neighbours, and
     // every copy but the first is skipped, as owner and as partner.
     live = live && !(e > 0 && keys[e - 1] == key && ids[e - 1] == ia);
+    // a multi-GPU search: the runs are dealt out by a hash of their variant (the verification is where the time goes)
+    live = live && (n_parts == 1 || (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 40) % n_parts == part);
     const bool two_del = live && umi_len(key) + 2 == umi_len(ca);
     UmiPattern pat;
     bool have_pat = false;
@@ -415,7 +419,13 @@ void dcb_dist_destroy(dcb_dist* d) {
 
 int dcb_umi_pairs(dcb_dist* d, const uint64_t* codes, uint32_t n, int max_edits, uint64_t* keys, uint64_t cap,
                   uint64_t* n_pairs) {
+    return dcb_umi_pairs_part(d, codes, n, max_edits, 0, 1, keys, cap, n_pairs);
+}
+
+int dcb_umi_pairs_part(dcb_dist* d, const uint64_t* codes, uint32_t n, int max_edits, uint32_t part, uint32_t n_parts,
+                       uint64_t* keys, uint64_t cap, uint64_t* n_pairs) {
     if (!d || !n_pairs) { dcb_set_error("dcb_umi_pairs: null argument"); return DCB_EINVAL; }
+    if (n_parts == 0 || part >= n_parts) { dcb_set_error("dcb_umi_pairs_part: part %u of %u", part, n_parts); return DCB_EINVAL; }
     CUDA_TRY(cudaSetDevice(d->device));
     cudaStream_t s = d->stream;
     if (codes) {   // compute (and cache) the sorted pair list
@@ -467,7 +477,7 @@ int dcb_umi_pairs(dcb_dist* d, const uint64_t* codes, uint32_t n, int max_edits,
                 dcb_umi_runs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(k_out.as<uint64_t>(), v_out.as<uint32_t>(), total,
                                                                                    d_codes.as<uint64_t>(), max_edits,
                                                                                    d_raw.as<unsigned long long>(), capacity,
-                                                                                   d_count.as<unsigned long long>());
+                                                                                   d_count.as<unsigned long long>(), part, n_parts);
                 CUDA_TRY(cudaGetLastError());
                 CUDA_TRY(cudaMemcpyAsync(&found, d_count.p, 8, cudaMemcpyDeviceToHost, s));
                 CUDA_TRY(cudaStreamSynchronize(s));
@@ -511,7 +521,7 @@ int dcb_umi_pairs(dcb_dist* d, const uint64_t* codes, uint32_t n, int max_edits,
                 CUDA_TRY(cudaEventRecord(ev.a, s));
                 dcb_umi_pairs_kernel<<<(unsigned)n_blocks, kPairTile, 0, s>>>(d_codes.as<uint64_t>(), n, max_edits, n_tiles,
                                                                               d_raw.as<unsigned long long>(), capacity,
-                                                                              d_count.as<unsigned long long>());
+                                                                              d_count.as<unsigned long long>(), part, n_parts);
                 CUDA_TRY(cudaGetLastError());
                 CUDA_TRY(cudaEventRecord(ev.b, s));
                 CUDA_TRY(cudaMemcpyAsync(&found, d_count.p, 8, cudaMemcpyDeviceToHost, s));

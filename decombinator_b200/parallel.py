@@ -22,6 +22,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import _lib
 from . import collapse as C
 from . import decombine as D
 
@@ -332,6 +333,26 @@ def collapsinator_sharded(inputargs, data=None, first_index=0, n_total=None):
     parts = [None] * world if rank == 0 else None
     dist.gather_object(local, parts, dst=0)
     totals = _sum_counters({k: v for k, v in C.counts.items() if k != "start_time"})
+    # 3b. the UMI neighbour search over ALL groups, split over the GPUs: an all-gather of the barcode codes (rank order), every
+    #     rank verifies its share of the deletion-variant runs on its own GPU, the shares are gathered on rank 0
+    #     (barcodes with symbols outside ACGTNSL -- IUPAC codes from the host's fuzzy path -- have no rank-independent code:
+    #     rank 0 then searches alone, as a 1-GPU run does)
+    try:
+        local_codes, codable = _lib.encode_umis_fixed([g[1] for g in groups]), 1
+    except _lib.DcbError:
+        local_codes, codable = np.zeros(0, dtype=np.uint64), 0
+    flag = torch.tensor([codable], dtype=torch.int64, device=_comm_device())
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    split_search = bool(int(flag.item()))
+    shares = None
+    if split_search:
+        all_codes, sizes = all_gather_codes(local_codes)
+        if len(all_codes) > 1:
+            row, col = C._gpu().umi_pairs(all_codes, inputargs["bcthreshold"], part=rank, n_parts=world)
+        else:
+            row = col = np.zeros(0, dtype=np.int64)
+        shares = [None] * world if rank == 0 else None
+        dist.gather_object((row, col), shares, dst=0)
     if rank != 0:
         return []
     # 4. rank 0: the reference's dict order back from the ticks, then clustering and counting as in a 1-GPU run
@@ -340,10 +361,29 @@ def collapsinator_sharded(inputargs, data=None, first_index=0, n_total=None):
     all_dcr = coll.Counter()
     for p in parts:
         all_dcr.update(p["dcr_counts"])
-    barcode_dcretc = C._groups_to_dict([g for p in parts for g in p["groups"]], all_dcr,
-                                       sum(p["dropped"] for p in parts), sum(p["dead"] for p in parts))
+    gathered = [g for p in parts for g in p["groups"]]            # rank order = the order of the gathered codes
+    barcode_dcretc = C._groups_to_dict(gathered, all_dcr, sum(p["dropped"] for p in parts), sum(p["dead"] for p in parts))
+
+    def find_pairs(umi_protoseq_tuple, barcode_threshold, dont_count):
+        """The pairs of the split search, renumbered from the gathered (rank) order to the dict's order and sorted row-major."""
+        n_groups = len(gathered)
+        if n_groups == 0:
+            raise ValueError("No UMIs to cluster, check .n12 file for errors")
+        order = sorted(range(n_groups), key=lambda g: gathered[g][0])           # dict order = ascending tick (stable)
+        pos = np.empty(n_groups, dtype=np.int64)
+        pos[np.asarray(order, dtype=np.int64)] = np.arange(n_groups, dtype=np.int64)
+        r = np.concatenate([np.asarray(x[0], dtype=np.int64) for x in shares])
+        c = np.concatenate([np.asarray(x[1], dtype=np.int64) for x in shares])
+        a, b = pos[r], pos[c]
+        key = np.unique(np.minimum(a, b) * np.int64(n_groups) + np.maximum(a, b))
+        print("Clustering UMIs...")
+        print("  ", n_groups, "unique UMIs")
+        print("  ", len(key), "UMIs within edit distance of", barcode_threshold)
+        return C._PairList(key // n_groups, key % n_groups)
+
     file_id = inputargs["infile"].split("/")[-1].split(".")[0]
-    out_data, _, sizes = C._count_clusters(barcode_dcretc, inputargs, inputargs["bcthreshold"], frac, True, "", file_id)
+    out_data, _, sizes = C._count_clusters(barcode_dcretc, inputargs, inputargs["bcthreshold"], frac, True, "", file_id,
+                                           find_pairs if split_search else None)
     C.counts["end_time"] = time.time()
     C.counts["time_taken_total_s"] = C.counts["end_time"] - C.counts["start_time"]
     if inputargs["suppresssummary"] == False:  # noqa: E712

@@ -272,6 +272,11 @@ void dcb_dist_destroy(dcb_dist*);
  * (DCB_ENOMEM when cap is too small).  Typical use: one call with keys == NULL to size, one with codes == NULL. */
 int dcb_umi_pairs(dcb_dist*, const uint64_t* codes, uint32_t n, int max_edits, uint64_t* keys, uint64_t cap,
                   uint64_t* n_pairs);
+/* One GPU's share of the same search when n_parts GPUs hold the same list (an all-gather of the UMI codes): part p verifies
+ * the runs of equal deletion variants whose variant hashes to p (the tile pairs numbered p modulo n_parts on the all-pairs
+ * path).  The union of the parts' lists is the list of dcb_umi_pairs; a pair can be in more than one part. */
+int dcb_umi_pairs_part(dcb_dist*, const uint64_t* codes, uint32_t n, int max_edits, uint32_t part, uint32_t n_parts,
+                       uint64_t* keys, uint64_t cap, uint64_t* n_pairs);
 
 /* Batch of are_seqs_equivalent(seq1, seq2, lev_threshold_fraction) (collapse.py:355-360; called at :601, :778):
  *     verdict[t] = polyleven.levenshtein(A, B) <= len(shorter of A, B) * frac        (compared in double)

@@ -56,12 +56,15 @@ class OracleDist:
 
     ALPHABET = "ACGTNSL"
 
-    def umi_pairs(self, codes, max_edits):
+    def umi_pairs(self, codes, max_edits, part=0, n_parts=1):
+        """(a share of a split search: the pairs whose row is `part` modulo n_parts -- any split whose union is whole)"""
         umis = []
         for c in np.asarray(codes, dtype=np.uint64).tolist():
             n = c >> 58
             umis.append("".join(chr(ord("a") + ((c >> (3 * k)) & 7)) for k in range(n)))
-        return umi_pairs(umis, max_edits)
+        row, col = umi_pairs(umis, max_edits)
+        mine = row % n_parts == part
+        return row[mine], col[mine]
 
     def lev_leq(self, symbols, off, length, a, b, frac):
         seqs = [bytes(symbols[int(o):int(o) + int(l)]) for o, l in zip(off, length)]

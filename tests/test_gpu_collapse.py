@@ -131,6 +131,25 @@ def test_umi_pairs_deletion_neighbourhoods_equal_all_pairs(dist, monkeypatch, n,
     assert (len(r0) > 0 or alphabet == "ACGTNSL") and np.array_equal(r0, r1) and np.array_equal(c0, c1)
 
 
+@pytest.mark.parametrize("force", ["0", "1000000000"])
+def test_umi_pairs_split_over_parts(dist, monkeypatch, force):
+    """dcb_umi_pairs_part: the union of the shares of a search split over 1, 2, 3 and 8 GPUs is the whole list (both forms)."""
+    monkeypatch.setenv("DCB_UMI_SYMDEL_MIN", force)
+    rng = random.Random(99)
+    umis = list({"".join(rng.choice("ACGT") for _ in range(rng.choice((8, 8, 8, 7)))) for _ in range(9000)})
+    codes = _lib.encode_umis(umis)
+    row, col = dist.umi_pairs(codes, 2)
+    whole = row * (1 << 32) + col
+    assert len(whole) > 1000
+    for n_parts in (2, 3, 8):
+        got = []
+        for part in range(n_parts):
+            r, c = dist.umi_pairs(codes, 2, part=part, n_parts=n_parts)
+            assert len(r) < len(row)
+            got.append(r * (1 << 32) + c)
+        assert np.array_equal(np.unique(np.concatenate(got)), whole)
+
+
 def test_umi_pairs_two_million(dist):
     """BASELINE configs[3] scale: 2 M distinct random 12-nt UMIs, two edits -- ~10^8 pairs.  Every sampled pair is real,
     planted neighbours (substitution, deletion + insertion, two substitutions) are all found, the list is sorted and unique."""
