@@ -125,6 +125,7 @@ def lib():
     L.dcb_umi_pairs.argtypes = [vp, vp, u32, i32, vp, u64, ctypes.POINTER(u64)]
     L.dcb_umi_pairs_part.argtypes = [vp, vp, u32, i32, u32, u32, vp, u64, ctypes.POINTER(u64)]
     L.dcb_lev_leq.argtypes = [vp, vp, vp, vp, u32, vp, vp, u64, ctypes.c_double, vp]
+    L.dcb_lev_leq_bytes.argtypes = [vp, vp, vp, vp, u32, vp, vp, u64, ctypes.c_double, vp]
     L.dcb_barcodes.argtypes = [vp, vp, vp, vp, vp, vp, vp, u64, ctypes.POINTER(CBcParams), vp, vp, vp]
     L.dcb_dist_last_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     L.dcb_dist_last_method.argtypes = [vp]
@@ -695,11 +696,15 @@ def encode_umis_fixed(umis):
 
 
 def encode_seqs(seqs):
-    """list[str] -> (symbols uint8, off uint64, len uint32) for dcb_lev_leq."""
-    codes = _alphabet(seqs)
-    table = np.zeros(256, dtype=np.uint8)
-    for ch, v in codes.items():
-        table[ord(ch)] = v
+    """list[str] -> (symbols uint8, off uint64, len uint32) for dcb_lev_leq: codes 0..7 when the batch has at most eight
+    distinct characters (the usual case), else the characters themselves (Dist.lev_leq then calls dcb_lev_leq_bytes)."""
+    present = set("".join(seqs))
+    table = np.arange(256, dtype=np.uint8)
+    if len(present) <= 8:
+        for ch, v in _alphabet(seqs).items():
+            table[ord(ch)] = v
+    elif any(ord(ch) > 255 for ch in present):
+        raise DcbError("sequence symbols outside latin-1")
     length = np.array([len(x) for x in seqs], dtype=np.uint32)
     off = np.zeros(len(seqs), dtype=np.uint64)
     if len(seqs) > 1:
@@ -737,7 +742,8 @@ class Dist:
         off = np.ascontiguousarray(off, dtype=np.uint64)
         length = np.ascontiguousarray(length, dtype=np.uint32)
         out = np.zeros(len(a), dtype=np.uint8)
-        _check(lib().dcb_lev_leq(self._h, symbols.ctypes.data, off.ctypes.data, length.ctypes.data, len(length),
+        wide = len(symbols) and int(symbols.max()) > 7
+        _check((lib().dcb_lev_leq_bytes if wide else lib().dcb_lev_leq)(self._h, symbols.ctypes.data, off.ctypes.data, length.ctypes.data, len(length),
                                  a.ctypes.data, b.ctypes.data, len(a), float(frac), out.ctypes.data), "dcb_lev_leq")
         return out.astype(bool)
 

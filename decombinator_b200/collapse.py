@@ -37,6 +37,7 @@ from . import __version__, _lib
 
 counts = coll.Counter()
 _dist = None
+MAX_SEQ_LEN = 512        # dcb_lev_leq (include/dcb.h); the reference's default -ln is 130
 
 # spacer sequences per ligation oligo (collapse.py:172-190), first spacer then (if any) second
 _OLIGOS = {
@@ -793,6 +794,9 @@ def collapsinator(inputargs: dict, data: list = None) -> list:
     barcode_quality_parameters = [inputargs["minbcQ"], inputargs["bcQbelowmin"], inputargs["avgQthreshold"]]
     lev_threshold_fraction = inputargs["percentlevdist"] / 100
     barcode_distance_threshold = inputargs["bcthreshold"]
+    if inputargs["lenthreshold"] > MAX_SEQ_LEN:      # said before any work is done, not in the middle of the grouping
+        raise ValueError("-ln %d: the sequence comparisons of this build take inter-tag sequences of up to %d bases"
+                         % (inputargs["lenthreshold"], MAX_SEQ_LEN))
     if inputargs["command"] == "collapse":
         data = inputargs["infile"]
     file_id = inputargs["infile"].split("/")[-1].split(".")[0]

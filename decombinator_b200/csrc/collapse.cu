@@ -250,14 +250,15 @@ struct Events {
     ~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
 };
 
-// one thread per pair; the shorter sequence is the pattern
-template <int W>
+// one thread per pair; the shorter sequence is the pattern.  NP: code bits per symbol (3: codes 0..7; 8: any byte)
+template <int W, int NP>
 __device__ __forceinline__ int lev_pair(const uint8_t* pa, int la, const uint8_t* pb, int lb) {
-    SeqPattern<W> pat;
-    seq_pattern<W>(pa, la, pat);
-    return seq_distance<W>(pat, pb, lb);
+    SeqPattern<W, NP> pat;
+    seq_pattern<W, NP>(pa, la, pat);
+    return seq_distance<W, NP>(pat, pb, lb);
 }
 
+template <int NP>
 __global__ void __launch_bounds__(128)
 dcb_lev_leq_kernel(const uint8_t* __restrict__ sym, const uint64_t* __restrict__ off, const uint32_t* __restrict__ len,
                    const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, unsigned long long n_pairs, uint32_t n_seqs,
@@ -266,22 +267,22 @@ dcb_lev_leq_kernel(const uint8_t* __restrict__ sym, const uint64_t* __restrict__
     if (t >= n_pairs) return;
     uint32_t ia = a[t], ib = b[t];
     if (ia >= n_seqs || ib >= n_seqs) { flag[0] = 1u; flag[1] = (uint32_t)t; verdict[t] = 0; return; }
-    {   // symbol codes are three bits wide
+    if (NP < 8) {   // symbol codes are NP bits wide
         uint32_t any = 0;
         for (uint32_t k = 0; k < len[ia]; k++) any |= sym[off[ia] + k];
         for (uint32_t k = 0; k < len[ib]; k++) any |= sym[off[ib] + k];
-        if (any > 7u) { flag[2] = 1u; flag[3] = (uint32_t)t; verdict[t] = 0; return; }
+        if (any >> NP) { flag[2] = 1u; flag[3] = (uint32_t)t; verdict[t] = 0; return; }
     }
     int la = (int)len[ia], lb = (int)len[ib];
     if (la > lb) { const uint32_t x = ia; ia = ib; ib = x; const int y = la; la = lb; lb = y; }
     const uint8_t* pa = sym + off[ia];
     const uint8_t* pb = sym + off[ib];
     int d;
-    if (la <= 64) d = lev_pair<1>(pa, la, pb, lb);
-    else if (la <= 128) d = lev_pair<2>(pa, la, pb, lb);
-    else if (la <= 192) d = lev_pair<3>(pa, la, pb, lb);
-    else if (la <= 256) d = lev_pair<4>(pa, la, pb, lb);
-    else d = lev_pair<8>(pa, la, pb, lb);
+    if (la <= 64) d = lev_pair<1, NP>(pa, la, pb, lb);
+    else if (la <= 128) d = lev_pair<2, NP>(pa, la, pb, lb);
+    else if (la <= 192) d = lev_pair<3, NP>(pa, la, pb, lb);
+    else if (la <= 256) d = lev_pair<4, NP>(pa, la, pb, lb);
+    else d = lev_pair<8, NP>(pa, la, pb, lb);
     // threshold = len(min(seq1, seq2, key=len)) * lev_threshold_fraction ; return distance <= threshold  (collapse.py:359-360)
     verdict[t] = ((double)d <= (double)la * frac) ? 1 : 0;
 }
@@ -556,8 +557,20 @@ int dcb_umi_pairs_part(dcb_dist* d, const uint64_t* codes, uint32_t n, int max_e
     return DCB_OK;
 }
 
+static int lev_leq_impl(dcb_dist* d, const uint8_t* symbols, const uint64_t* off, const uint32_t* len, uint32_t n_seqs,
+                        const uint32_t* a, const uint32_t* b, uint64_t n_pairs, double frac, uint8_t* verdict, bool bytes);
+
 int dcb_lev_leq(dcb_dist* d, const uint8_t* symbols, const uint64_t* off, const uint32_t* len, uint32_t n_seqs,
                 const uint32_t* a, const uint32_t* b, uint64_t n_pairs, double frac, uint8_t* verdict) {
+    return lev_leq_impl(d, symbols, off, len, n_seqs, a, b, n_pairs, frac, verdict, false);
+}
+int dcb_lev_leq_bytes(dcb_dist* d, const uint8_t* symbols, const uint64_t* off, const uint32_t* len, uint32_t n_seqs,
+                      const uint32_t* a, const uint32_t* b, uint64_t n_pairs, double frac, uint8_t* verdict) {
+    return lev_leq_impl(d, symbols, off, len, n_seqs, a, b, n_pairs, frac, verdict, true);
+}
+
+static int lev_leq_impl(dcb_dist* d, const uint8_t* symbols, const uint64_t* off, const uint32_t* len, uint32_t n_seqs,
+                        const uint32_t* a, const uint32_t* b, uint64_t n_pairs, double frac, uint8_t* verdict, bool bytes) {
     if (!d || (n_pairs && (!symbols || !off || !len || !a || !b || !verdict))) { dcb_set_error("dcb_lev_leq: null argument"); return DCB_EINVAL; }
     if (n_pairs == 0) return DCB_OK;
     CUDA_TRY(cudaSetDevice(d->device));
@@ -582,9 +595,14 @@ int dcb_lev_leq(dcb_dist* d, const uint8_t* symbols, const uint64_t* off, const 
     CUDA_TRY(cudaEventCreate(&ev.a));
     CUDA_TRY(cudaEventCreate(&ev.b));
     CUDA_TRY(cudaEventRecord(ev.a, s));
-    dcb_lev_leq_kernel<<<(unsigned)blocks, 128, 0, s>>>((const uint8_t*)d->sym.p, (const uint64_t*)d->off.p, (const uint32_t*)d->len.p,
-                                                        (const uint32_t*)d->a.p, (const uint32_t*)d->b.p, n_pairs, n_seqs, frac,
-                                                        (uint8_t*)d->ver.p, (uint32_t*)d->flag.p);
+    if (bytes)
+        dcb_lev_leq_kernel<8><<<(unsigned)blocks, 128, 0, s>>>((const uint8_t*)d->sym.p, (const uint64_t*)d->off.p, (const uint32_t*)d->len.p,
+                                                               (const uint32_t*)d->a.p, (const uint32_t*)d->b.p, n_pairs, n_seqs, frac,
+                                                               (uint8_t*)d->ver.p, (uint32_t*)d->flag.p);
+    else
+        dcb_lev_leq_kernel<3><<<(unsigned)blocks, 128, 0, s>>>((const uint8_t*)d->sym.p, (const uint64_t*)d->off.p, (const uint32_t*)d->len.p,
+                                                               (const uint32_t*)d->a.p, (const uint32_t*)d->b.p, n_pairs, n_seqs, frac,
+                                                               (uint8_t*)d->ver.p, (uint32_t*)d->flag.p);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ev.b, s));
     uint32_t flag[4] = {0, 0, 0, 0};

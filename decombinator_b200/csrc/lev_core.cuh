@@ -99,36 +99,43 @@ LEV_HD bool umi_may_be_within(uint64_t a, uint64_t b, int k) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Sequences of small codes (one byte per symbol, values 0..7), pattern up to 64*W symbols.
-// The pattern is kept as three bit planes per word instead of one match mask per symbol, so that the whole
-// state stays in registers: eq(c) = the positions whose three code bits all agree with c.
+// Sequences of small codes (one byte per symbol), pattern up to 64*W symbols.
+// The pattern is kept as NP bit planes per word instead of one match mask per symbol, so that the whole
+// state stays in registers: eq(c) = the positions whose NP code bits all agree with c.  NP = 3 for codes 0..7
+// (the usual case: A C G T N and a few more), NP = 8 for arbitrary bytes (lower case, the whole IUPAC alphabet).
 // ------------------------------------------------------------------------------------------------
-template <int W>
+template <int W, int NP = 3>
 struct SeqPattern {
-    uint64_t p0[W], p1[W], p2[W], valid[W];
+    uint64_t p[NP][W], valid[W];
     int len;
 };
 
-template <int W>
-LEV_HD void seq_pattern(const uint8_t* s, int m, SeqPattern<W>& p) {
+template <int W, int NP>
+LEV_HD void seq_pattern(const uint8_t* s, int m, SeqPattern<W, NP>& p) {
     p.len = m;
     LEV_UNROLL
     for (int w = 0; w < W; w++) {
-        uint64_t a = 0, b = 0, c = 0, v = 0;
+        uint64_t pl[NP], v = 0;
+        LEV_UNROLL
+        for (int b = 0; b < NP; b++) pl[b] = 0;
         for (int k = 0; k < 64; k++) {
             const int i = 64 * w + k;
             if (i < m) {
                 const uint64_t x = s[i];
-                a |= (x & 1ull) << k; b |= ((x >> 1) & 1ull) << k; c |= ((x >> 2) & 1ull) << k; v |= 1ull << k;
+                LEV_UNROLL
+                for (int b = 0; b < NP; b++) pl[b] |= ((x >> b) & 1ull) << k;
+                v |= 1ull << k;
             }
         }
-        p.p0[w] = a; p.p1[w] = b; p.p2[w] = c; p.valid[w] = v;
+        LEV_UNROLL
+        for (int b = 0; b < NP; b++) p.p[b][w] = pl[b];
+        p.valid[w] = v;
     }
 }
 
 // Levenshtein(pattern, text[0:n])
-template <int W>
-LEV_HD int seq_distance(const SeqPattern<W>& p, const uint8_t* text, int n) {
+template <int W, int NP>
+LEV_HD int seq_distance(const SeqPattern<W, NP>& p, const uint8_t* text, int n) {
     const int m = p.len;
     if (m == 0) return n;
     uint64_t vp[W], vn[W];
@@ -139,12 +146,16 @@ LEV_HD int seq_distance(const SeqPattern<W>& p, const uint8_t* text, int n) {
     int score = m;
     for (int j = 0; j < n; j++) {
         const uint64_t x = text[j];
-        const uint64_t m0 = (x & 1ull) ? ~0ull : 0ull, m1 = (x & 2ull) ? ~0ull : 0ull, m2 = (x & 4ull) ? ~0ull : 0ull;
+        uint64_t mk[NP];
+        LEV_UNROLL
+        for (int b = 0; b < NP; b++) mk[b] = ((x >> b) & 1ull) ? ~0ull : 0ull;
         uint64_t hp_carry = 1ull, hn_carry = 0ull;
     LEV_UNROLL
         for (int w = 0; w < W; w++) {
             if (w > lw) break;
-            const uint64_t eq = ~(p.p0[w] ^ m0) & ~(p.p1[w] ^ m1) & ~(p.p2[w] ^ m2) & p.valid[w];
+            uint64_t eq = p.valid[w];
+            LEV_UNROLL
+            for (int b = 0; b < NP; b++) eq &= ~(p.p[b][w] ^ mk[b]);
             const uint64_t xx = eq | hn_carry;
             const uint64_t d0 = ((((xx | vn[w]) & vp[w]) + vp[w]) ^ vp[w]) | xx | vn[w];
             uint64_t hp = vn[w] | ~(d0 | vp[w]);

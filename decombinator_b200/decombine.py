@@ -178,14 +178,36 @@ def decombine_batch(batch: fastq.ReadBatch, inputargs):
     pack_rc, both = _orientation_plan(inputargs["orientation"])
     ctx = _context(inputargs, both)
     off = np.ascontiguousarray(batch.off, dtype=np.uint64)
+    lens = np.asarray(batch.len)
+    if len(lens) and int(lens.max()) > MAX_READ_LEN:
+        raise ValueError("read %d has %d bases; this build analyses reads of up to %d bases (DCB_MAX_READ_LEN)"
+                         % (int(lens.argmax()), int(lens.max()), MAX_READ_LEN))
+    # A read slot is as wide as the longest read of a batch, and the fastest kernels take slots of up to 320 bases: a few
+    # long reads in a file of short ones are analysed as a batch of their own instead of widening every slot.
+    if len(lens) and int(lens.max()) > FAST_READ_LEN and float((lens <= FAST_READ_LEN).mean()) >= 0.5:
+        res = np.zeros(len(lens), dtype=_lib.RESULT_DTYPE)
+        for part in (np.nonzero(lens <= FAST_READ_LEN)[0], np.nonzero(lens > FAST_READ_LEN)[0]):
+            sub = fastq.ReadBatch()
+            sub.buf, sub.off, sub.len = batch.buf, off[part], np.ascontiguousarray(lens[part], dtype=np.uint32)
+            res[part] = _decombine_columns(ctx, sub.buf, sub.off, sub.len, pack_rc)
+        return res
+    return _decombine_columns(ctx, batch.buf, off, batch.len, pack_rc)
+
+
+MAX_READ_LEN = 4096      # DCB_MAX_READ_LEN of csrc/dcb_tables.h
+FAST_READ_LEN = 320      # widest slot of the flat exact-tag kernel and the half-tag kernel (20 words)
+
+
+def _decombine_columns(ctx, buf, off, length, pack_rc):
+    """(offset, length) columns into a text buffer -> dcb_result array; counters added to `counts`."""
     try:
         if len(off) > 1 and bool(np.any(off[1:] < off[:-1])):
             raise _lib.DcbError("reads are not in text order")
         # the text goes to the GPU as it is and is 2-bit packed there (dcb_decombine_ascii): no packed copy on the host
-        res, dev_counts = ctx.decombine_ascii(batch.buf, off, batch.len, pack_rc)
+        res, dev_counts = ctx.decombine_ascii(buf, off, length, pack_rc)
     except _lib.DcbError:
         # reads out of text order, or more non-ACGT symbols than the device-side list holds: pack on the host threads
-        packed = _lib.pack_arrays(batch.buf, off, batch.len, revcomp=pack_rc)
+        packed = _lib.pack_arrays(buf, off, length, revcomp=pack_rc)
         res, dev_counts = ctx.decombine(packed)
         packed.free()
     _add_device_counters(dev_counts)

@@ -284,6 +284,10 @@ int dcb_umi_pairs_part(dcb_dist*, const uint64_t* codes, uint32_t n, int max_edi
  * alphabet), sequence i at symbols[off[i] .. off[i] + len[i]), len <= 512. */
 int dcb_lev_leq(dcb_dist*, const uint8_t* symbols, const uint64_t* off, const uint32_t* len, uint32_t n_seqs,
                 const uint32_t* a, const uint32_t* b, uint64_t n_pairs, double frac, uint8_t* verdict);
+/* The same over arbitrary byte symbols (a batch with more than eight distinct characters: lower case, the whole IUPAC
+ * alphabet); the pattern then takes eight bit planes instead of three. */
+int dcb_lev_leq_bytes(dcb_dist*, const uint8_t* symbols, const uint64_t* off, const uint32_t* len, uint32_t n_seqs,
+                      const uint32_t* a, const uint32_t* b, uint64_t n_pairs, double frac, uint8_t* verdict);
 /* Barcode extraction of the collapse step, per decombined row: replaces, for the two-spacer oligos M13 and I8 and rows whose
  * spacers are found EXACTLY, get_barcode_positions (collapse.py:367-479), set_barcode (:281-326) and check_umi_quality
  * (:340-352).  bc / q: the barcode region of the row (field 8 of an .n12 row) and its quality string (field 9), as

@@ -78,4 +78,5 @@ def lev_sim():
         _lev.sim_umi_distance.argtypes = [ctypes.c_uint64, ctypes.c_uint64]
         _lev.sim_umi_may_be_within.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int]
         _lev.sim_seq_distance.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        _lev.sim_seq_distance_bytes.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
     return _lev

@@ -71,6 +71,33 @@ def test_device_levenshtein_code_matches_oracle(collapse_cases):
                 assert sim.sim_umi_may_be_within(ca, cb, k) == 1, (a, b, k)
 
 
+def test_device_levenshtein_code_on_arbitrary_bytes():
+    """The eight-bit-plane form (batches with more than eight distinct characters: lower case, IUPAC) against the oracle."""
+    sim = simlib.lev_sim()
+    rng = random.Random(5)
+    alphabet = "ACGTNRYKMSWBDHVacgtn"
+    for _ in range(400):
+        L = rng.choice((1, 20, 64, 65, 130, 200, 300))
+        a = "".join(rng.choice(alphabet) for _ in range(L))
+        b = list(a)
+        for _ in range(rng.randrange(0, 12)):
+            op = rng.randrange(3)
+            if op == 0 and b:
+                b[rng.randrange(len(b))] = rng.choice(alphabet)
+            elif op == 1 and b:
+                del b[rng.randrange(len(b))]
+            else:
+                b.insert(rng.randrange(len(b) + 1), rng.choice(alphabet))
+        b = "".join(b)
+        x = np.frombuffer(a.encode(), dtype=np.uint8).copy()
+        y = np.frombuffer(b.encode(), dtype=np.uint8).copy()
+        assert sim.sim_seq_distance_bytes(x.ctypes.data, len(a), y.ctypes.data, len(b)) == CO.levenshtein(a, b)
+    sym, off, ln = _lib.encode_seqs(["ACGTNRYKMSWacgt", "ACGT"])          # more than eight symbols: the characters themselves
+    assert sym.max() > 7 and bytes(sym[:4]) == b"ACGT"
+    sym, off, ln = _lib.encode_seqs(["ACGTN", "ACGT"])
+    assert sym.max() <= 7
+
+
 def test_host_logic_matches_reference_runs(collapse_cases, oracle_distances):
     for case in collapse_cases["cases"]:
         collapse_checks.check_case(case)

@@ -246,3 +246,36 @@ def test_columnar_hand_over_equals_row_hand_over(tmp_path):
     assert out["rows"] == out["columns"] and len(out["rows"]) > 500
     assert cnts["rows"] == cnts["columns"]
     assert cnts["rows"]["getbarcode_pass_regexmatch"] > 0 and cnts["rows"]["readdata_fail_low_barcode_quality"] > 0
+
+
+@gpu
+def test_a_few_long_reads_do_not_widen_every_slot(tmp_path):
+    """A file of 250-nt reads with a handful of 600..3000-nt ones: same rows as the oracle; the short reads still go through
+    the flat exact-tag kernel (the long ones are analysed as a batch of their own)."""
+    import numpy as np
+    import decombine_oracle as O
+    from decombinator_b200 import _lib, tags
+    info = tags.load("human", "extended", "b")
+    n, L = 3000, 250
+    syn = _lib.Synth([(info.v_regions, info.j_regions)], 5, L, 62, 0.01, 0.001, 0.02)
+    r1, r2 = syn.reads(0, n, want_r2=True)
+    reads = [bytes(r1[i * L:(i + 1) * L]).decode() for i in range(n)]
+    rng = np.random.default_rng(2)
+    for i in (7, 500, 501, 2999):
+        reads[i] = "".join("ACGT"[k] for k in rng.integers(0, 4, int(rng.integers(600, 3000)))) + reads[i]
+    with open(tmp_path / "m_1.fq", "w") as f1, open(tmp_path / "m_2.fq", "w") as f2:
+        for i, r in enumerate(reads):
+            f1.write("@R%d\n%s\n+\n%s\n" % (i, r, "I" * len(r)))
+            f2.write("@R%d\n%s\n+\n%s\n" % (i, bytes(r2[i * 62:(i + 1) * 62]).decode(), "I" * 62))
+    args = _args(str(tmp_path / "m_1.fq"), "b", tmp_path, suppresssummary=True, dontcheck=True)
+    rows = decombine.decombinator(args)
+    orc = O.Oracle(O.TagSet("human", "extended", "b"))
+    want = orc.decombine_reads(reads, "reverse")
+    assert len(rows) == int(want["ok"].sum())
+    assert [int(r[5][1:]) for r in rows] == np.nonzero(want["ok"])[0].tolist()
+    assert decombine._ctx_cache and list(decombine._ctx_cache.values())[0].exact_kernel_name() in ("dcb_exact_kernel", "dcb_exact_kernel_spec", "dcb_exact_kernel_flat")
+    with open(tmp_path / "m_1.fq", "a") as f1, open(tmp_path / "m_2.fq", "a") as f2:
+        f1.write("@RX\n%s\n+\n%s\n" % ("A" * 5000, "I" * 5000))
+        f2.write("@RX\n%s\n+\n%s\n" % ("A" * 62, "I" * 62))
+    with pytest.raises(ValueError, match="4096"):
+        decombine.decombinator(args)

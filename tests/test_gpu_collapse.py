@@ -73,6 +73,27 @@ def test_lev_leq_random_pairs_vs_oracle(dist):
         assert got.tolist() == want
 
 
+def test_lev_leq_on_more_than_eight_symbols(dist):
+    """Lower case and IUPAC symbols in the inter-tag sequences (the reference compares whatever characters it is given):
+    the batch goes through dcb_lev_leq_bytes."""
+    rng = random.Random(21)
+    alphabet = "ACGTNRYKMSWBDHVacgtn"
+    seqs = []
+    for _ in range(500):
+        L = rng.choice((20, 64, 65, 100, 130, 257))
+        a = [rng.choice(alphabet) for _ in range(L)]
+        b = list(a)
+        for _ in range(rng.randrange(0, 14)):
+            b[rng.randrange(len(b))] = rng.choice(alphabet)
+        seqs += ["".join(a), "".join(b)]
+    sym, off, ln = _lib.encode_seqs(seqs)
+    assert sym.max() > 7
+    a = np.arange(0, len(seqs), 2, dtype=np.uint32)
+    got = dist.lev_leq(sym, off, ln, a, a + 1, 0.1)
+    assert got.tolist() == [CO.seqs_equivalent(seqs[i], seqs[i + 1], 0.1) for i in a]
+    assert collapse.are_seqs_equivalent("ACGTNRYKMSWacgt", "ACGTNRYKMSWacgA", 0.1) is True
+
+
 def test_lev_leq_rejects_bad_input(dist):
     sym, off, ln = _lib.encode_seqs(["A" * 513, "ACGT"])
     with pytest.raises(_lib.DcbError):
