@@ -876,13 +876,27 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
 // ------------------------------------------------------------------------------------------------
 // general kernel (queued reads, or every read when queue == nullptr)
 // ------------------------------------------------------------------------------------------------
+#ifndef DCB_GENERAL_MIN_SPREAD
+#define DCB_GENERAL_MIN_SPREAD 4
+#endif
 __global__ void __launch_bounds__(kGeneralThreads, DCB_GENERAL_BLOCKS)
 dcb_general_kernel(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_result* __restrict__ results,
                    unsigned long long* __restrict__ counters, const uint32_t* __restrict__ queue,
                    const uint32_t* __restrict__ queue_count) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int T = blockDim.x;
-    if (blockIdx.x >= ((queue ? *queue_count : b.n_reads) + T - 1) / T) return;   // nothing for this block: do not even stage the tables
+    // A short queue is spread thinly: S reads per warp (lanes 0 .. S-1), so that all of it runs in one wave of warps and a
+    // warp serialises S divergent paths instead of 32 -- the reads that get here are the odd ones, each on a path of its
+    // own, and a tile's latency is its slowest warp's (measured on configs[2]: 9 k reads took 0.16 ms at 32 per warp).
+    const uint32_t n_items = queue ? *queue_count : b.n_reads;
+    uint32_t S = 32;
+    {
+        const uint64_t warps = (uint64_t)gridDim.x * (uint32_t)(T >> 5);
+        while (S > DCB_GENERAL_MIN_SPREAD && (uint64_t)n_items <= warps * (S >> 1)) S >>= 1;
+    }
+    const uint32_t per_tile = (uint32_t)(T >> 5) * S;
+    const uint32_t n_tiles = (n_items + per_tile - 1) / per_tile;
+    if (blockIdx.x >= n_tiles) return;   // nothing for this block: do not even stage the tables
     const int nw = (int)b.slot_words, nwi = (nw + 1) / 2;
     SmemLayout L = carve(smem, tb, (size_t)(nw + nwi) * T * (both_frames ? 2 : 1) + (size_t)(nwi + DCB_HITS_CAP + 6) * T + 20);
     uint32_t* s_rd = L.cols;                      // [nw][T]
@@ -900,14 +914,14 @@ dcb_general_kernel(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_r
     const uint32_t* sfilt = tb.words[2] ? L.t[2] : nullptr;      // union suffix filter
 
     const int tid = threadIdx.x;
-    const uint32_t n_items = queue ? *queue_count : b.n_reads;
-    const uint32_t n_tiles = (n_items + T - 1) / T;
+    const uint32_t slot = (uint32_t)(tid >> 5) * S + (uint32_t)(tid & 31);   // this thread's place among the tile's reads
+    const bool placed = (uint32_t)(tid & 31) < S;
     ExcList ex;
     ex.read = b.exc_read; ex.pos = b.exc_pos; ex.kind = b.exc_kind; ex.n = b.n_exc;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         // ---- step 1: thread t prepares the read in column t (marks, invalid-base mask, hit list) and classifies it
-        const uint32_t item = tile * T + tid;
-        const bool live = item < n_items;
+        const uint32_t item = tile * per_tile + slot;
+        const bool live = placed && item < n_items;
         int cls = 16;                                      // dead column (past the end of the queue)
         __syncthreads();                                   // the previous tile is done with the columns and s_cls
         if (tid < 18) s_cls[tid] = 0u;
@@ -947,8 +961,8 @@ dcb_general_kernel(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_r
         s_perm[s_cls[cls] + rank] = (uint16_t)tid;
         __syncthreads();
         // ---- step 2: thread t analyses column s_perm[t] (dead columns sort last)
-        const int col = s_perm[tid];
-        if ((uint32_t)tid < s_cls[16]) {                   // live columns: classes 0..15
+        const int col = s_perm[placed ? slot : 0];
+        if (placed && slot < s_cls[16]) {                  // live columns: classes 0..15
             const uint32_t* m = s_meta + col;
             const uint32_t ri = m[0], fl = m[4 * T];
             ReadView r;
