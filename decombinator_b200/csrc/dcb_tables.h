@@ -235,8 +235,11 @@ struct DcbHalfIndex {
     int32_t n_words;
     int32_t j_ok;                // 0: the J half keywords are too short for the index (6-base halves of the `original` J sets): only the
                                  // V side is searched; a read whose V is assigned but whose J tag is missing goes on to the general kernel
-    int32_t pad[2];
+    int32_t j_short;             // j_ok == 0 and every J half has at least DCB_HALF_JQ bases: jt_off is a direct table over the first
+    int32_t jt_off;              // DCB_HALF_JQ bases of the J half keywords, uint16[4^JQ] of (first | count << 8) into ids; a read whose
+                                 // V is assigned and whose J is missing is probed with it at every base
 };
+#define DCB_HALF_JQ 6
 #define DCB_HALF_Q 7
 #define DCB_HALF_STRIDE 4
 #define DCB_HALF_FREE 0xFFFFFFFFu

@@ -1142,8 +1142,9 @@ struct HalfView {
     const uint8_t* ids;
     const DcbHalfKw* kw;
     const uint8_t* tags;
+    const uint16_t* jt;        // j_short: direct table over the first DCB_HALF_JQ bases of the J half keywords
     uint32_t c1, c2;
-    int hshift, v_split, j_split, j_ok;
+    int hshift, v_split, j_split, j_ok, j_short;
 };
 DCB_HD HalfView half_view(const uint32_t* hb) {
     const DcbHalfIndex& hx = *reinterpret_cast<const DcbHalfIndex*>(hb);
@@ -1153,11 +1154,14 @@ DCB_HD HalfView half_view(const uint32_t* hb) {
     v.ids = reinterpret_cast<const uint8_t*>(hb + hx.ids_off);
     v.kw = reinterpret_cast<const DcbHalfKw*>(hb + hx.kw_off);
     v.tags = reinterpret_cast<const uint8_t*>(hb + hx.tags_off);
+    v.jt = hx.j_short ? reinterpret_cast<const uint16_t*>(hb + hx.jt_off) : nullptr;
     v.c1 = hx.c1; v.c2 = hx.c2; v.hshift = hx.hshift; v.v_split = hx.v_split; v.j_split = hx.j_split; v.j_ok = hx.j_ok;
+    v.j_short = hx.j_short;
     return v;
 }
 // A candidate: gene << 31 | kind << 29 (0 full tag, 1 half1, 2 half2) | end of the keyword occurrence << 19 |
-// (31 - keyword length) << 14 | tag << 6 | dead << 5 (length guard or Hamming <= 1 failed: such a candidate still
+// (31 - keyword length) << 14 | tag << 6.  Only (occurrence, tag) pairs that pass the length guard and Hamming <= 1 become
+// candidates; an occurrence that yields none is remembered as a DCB_HALF_SEEN bit of the read's candidate word (it still
 // says that its half keyword DID occur).  Ascending integer order = V before J, full tag, then half1 hits by
 // (end, longest first) with their tags ascending, then half2 hits likewise: the reference's order.
 #define DCB_HC_GENE(e) ((e) >> 31)
@@ -1169,16 +1173,23 @@ DCB_HD HalfView half_view(const uint32_t* hb) {
 #define DCB_HC_MAKE(gene, kind, end, kwlen, tag, dead) \
     (((uint32_t)(gene) << 31) | ((uint32_t)(kind) << 29) | ((uint32_t)(end) << 19) | ((31u - (uint32_t)(kwlen)) << 14) | ((uint32_t)(tag) << 6) | ((uint32_t)(dead) << 5))
 #define DCB_HALF_MAX_READ 1008     // `end` has 10 bits
-#define DCB_HALF_BAIL 0x10000u     // added to a read's candidate count: pass the read on
+// A read's candidate word: the number of candidates appended (12 bits) | which half keyword sets occurred WITHOUT
+// yielding a candidate (length guard or Hamming <= 1 failed for every tag: DCB_HALF_SEEN, one bit per gene and half) |
+// DCB_HALF_BAIL added any number of times: pass the read on.
+#define DCB_HALF_COUNT(n) ((n) & 0xFFFu)
+#define DCB_HALF_SEEN(gene, half2) (0x1000u << (2 * (gene) + (half2)))
+#define DCB_HALF_BAIL 0x10000u
 // Candidates are appended in any order (in the kernel by whichever lane confirmed the occurrence: the count is bumped
 // atomically) and sorted once they are complete.
 #if defined(__CUDA_ARCH__)
 #define DCB_SLOT_TAKE(p, k) atomicAdd((p), (k))
+#define DCB_SLOT_OR(p, k) atomicOr((p), (k))
 #else
 #define DCB_SLOT_TAKE(p, k) ((*(p) += (k)) - (k))
+#define DCB_SLOT_OR(p, k) (*(p) |= (k))
 #endif
 DCB_HD void half_append(uint32_t* cand, int stride, int cap, uint32_t* n, uint32_t e) {
-    const uint32_t k = DCB_SLOT_TAKE(n, 1u);
+    const uint32_t k = DCB_HALF_COUNT(DCB_SLOT_TAKE(n, 1u));
     if (k < (uint32_t)cap) cand[k * stride] = e;
 }
 DCB_HD void half_sort(uint32_t* cand, int stride, int n) {
@@ -1244,6 +1255,12 @@ DCB_HD void half_candidate(const ReadView& r, const uint32_t* inv2, const HalfVi
     const DcbTag& t = (gene ? jtags : vtags)[kk];
     const int tlen = t.len;
     const int span = tlen > (int)k.first_len ? tlen : (int)k.first_len;
+    if (s0 >= 0 && s0 + span > r.n && tlen == (int)k.first_len) {
+        // the tag window runs past the end of the read: the reference's slice comes out short, the length guard fails
+        // (:302-307) -- the keyword still DID occur
+        (void)DCB_SLOT_OR(n, DCB_HALF_SEEN(gene, half2));
+        return;
+    }
     if (s0 < 0 || s0 + span > r.n) { (void)DCB_SLOT_TAKE(n, DCB_HALF_BAIL); return; }
     uint32_t lo, hi;
     rd_win32x<PADDED>(r, s0, lo, hi);
@@ -1255,7 +1272,61 @@ DCB_HD void half_candidate(const ReadView& r, const uint32_t* inv2, const HalfVi
     }
     lo &= t.mask_lo; hi &= t.mask_hi;
     const bool dead = tlen != (int)k.first_len || DCB_POPC((lo | (lo >> 1)) & 0x55555555u) + DCB_POPC((hi | (hi >> 1)) & 0x55555555u) > 1;
-    half_append(cand, r.stride, cap, n, DCB_HC_MAKE(gene, 1 + half2, P + (int)k.len, k.len, kk, dead));
+    // a tag that fails still says that its half keyword DID occur (half2 is only tried when half1 never hit)
+    if (dead) (void)DCB_SLOT_OR(n, DCB_HALF_SEEN(gene, half2));
+    else half_append(cand, r.stride, cap, n, DCB_HC_MAKE(gene, 1 + half2, P + (int)k.len, k.len, kk, 0));
+}
+// J half keywords below the sampled index's kmin (j_short: the 6-base halves of the 12-nt J tags) are found with a direct
+// table over their first DCB_HALF_JQ bases, probed at EVERY base -- only in reads that need it: V assigned (a full V tag
+// or a half-tag candidate that passed), J missing.  When the exact-tag kernel did not search J at all (full: it only
+// does for reads with one full V tag), the full J tags are found here too: an occurrence starts with its first half.
+// half_jshort_ok: does the read need the scan?  cand / n: the candidates so far (V side).
+DCB_HD bool half_jshort_ok(const HalfView& hx, uint32_t hv, uint32_t hj, const uint32_t* cand, int stride, int cap, uint32_t n) {
+    if (!hx.j_short || !(hj == 0u || hj == DCB_HIT_UNKNOWN) || n >= DCB_HALF_BAIL || DCB_HALF_COUNT(n) > (uint32_t)cap) return false;
+    if (hv != 0u) return true;
+    for (uint32_t i = 0; i < DCB_HALF_COUNT(n); i++) {
+        const uint32_t e = cand[i * stride];
+        if (DCB_HC_GENE(e) == 0u) return true;
+    }
+    return false;          // no V: janalysis is never reached (decombine.py:542-545)
+}
+// A full J tag starts with its first half: (occurrence of a half1 keyword at P, tag ti of that keyword) -> the whole tag
+// compared, an occurrence appended as a candidate of kind 0.
+template <bool PADDED>
+DCB_HD void half_jfull_candidate(const ReadView& r, const uint32_t* inv2, const HalfView& hx, const DcbTag* jtags, int id, int ti, int P,
+                                 uint32_t* cand, int cap, uint32_t* n) {
+    const DcbHalfKw k = hx.kw[id];
+    if (k.set != 2) return;
+    const int kk = hx.tags[k.tags_off + ti];
+    const DcbTag& t = jtags[kk];
+    if (P + (int)t.len > r.n) return;
+    uint32_t lo, hi;
+    rd_win32x<PADDED>(r, P, lo, hi);
+    lo ^= t.bits_lo; hi ^= t.bits_hi;
+    if (inv2) {
+        uint32_t ilo, ihi;
+        rd_win32x<PADDED>(half_inv_view(r, inv2), P, ilo, ihi);
+        lo |= ilo; hi |= ihi;
+    }
+    if (!((lo & t.mask_lo) | (hi & t.mask_hi))) half_append(cand, r.stride, cap, n, DCB_HC_MAKE(1, 0, P + (int)t.len, t.len, kk, 0));
+}
+// One base of the scan, serially (tests/sim; the kernel pools the 6-mer hits of a warp): `six` = the DCB_HALF_JQ bases at P.
+template <bool PADDED>
+DCB_HD void half_jshort_at(const ReadView& r, const uint32_t* inv2, const HalfView& hx, const DcbTag* vtags, const DcbTag* jtags,
+                           uint32_t six, int P, bool full, uint32_t* cand, int cap, uint32_t* n) {
+    const uint32_t meta = hx.jt[six];
+    if (!meta) return;
+    struct Sink {
+        const ReadView& r; const uint32_t* inv2; const HalfView& hx; const DcbTag* vtags; const DcbTag* jtags;
+        int P; bool full; uint32_t* cand; int cap; uint32_t* n;
+        DCB_HD void operator()(int id, int n_tags) {
+            for (int ti = 0; ti < n_tags; ti++) {
+                half_candidate<PADDED>(r, inv2, hx, vtags, jtags, id, ti, P, cand, cap, n);
+                if (full) half_jfull_candidate<PADDED>(r, inv2, hx, jtags, id, ti, P, cand, cap, n);
+            }
+        }
+    } sink{r, inv2, hx, vtags, jtags, P, full, cand, cap, n};
+    half_keywords<PADDED>(r, inv2, hx, meta, P, sink);
 }
 // Set up the read: the invalid-base column of a flagged read (exception entries from e0 on), the hand-over words checked
 // against it (a tag over a symbol packed as base 0 is no occurrence), which half sets have to be found.
@@ -1299,18 +1370,27 @@ DCB_HD bool half_begin(ReadView& r, const uint32_t*& inv2, bool flagged, const E
 // Hamming <= 1, half2 candidates only when half1 never hit.  Returns its entry, or 0 with the failure counter pending.
 // i is left at the first entry of the next gene.
 template <bool IS_V>
-DCB_HD uint32_t half_select(const uint32_t* cand, int stride, int n, int& i, uint32_t& pend) {
+DCB_HD uint32_t half_select(const uint32_t* cand, int stride, int n, int& i, uint32_t& pend, uint32_t seen) {
     const uint32_t gene = IS_V ? 0u : 1u;
-    if (i >= n || DCB_HC_GENE(cand[i * stride]) != gene) {
+    // the first keyword set that hit: full tags, else half1, else half2 -- by a candidate or by an occurrence that yielded none
+    const uint32_t kind_seen = (seen & DCB_HALF_SEEN(gene, 0)) ? 1u : ((seen & DCB_HALF_SEEN(gene, 1)) ? 2u : 3u);
+    const uint32_t kind_cand = (i < n && DCB_HC_GENE(cand[i * stride]) == gene) ? DCB_HC_KIND(cand[i * stride]) : 3u;
+    const uint32_t kind0 = kind_cand < kind_seen ? kind_cand : kind_seen;
+    if (kind0 == 3u) {
         pend |= 1u << (IS_V ? DCB_C_no_vtags_found : DCB_C_no_j_assigned);                  // :393 / :530
         return 0u;
     }
-    const uint32_t kind0 = DCB_HC_KIND(cand[i * stride]);
     uint32_t pick = 0u;
+    int n_full = 0;
     for (; i < n; i++) {
         const uint32_t e = cand[i * stride];
         if (DCB_HC_GENE(e) != gene) break;
-        if (!pick && DCB_HC_KIND(e) == kind0 && !DCB_HC_DEAD(e)) pick = e;                  // half2 only when half1 never hit (:339 / :473)
+        if (!pick && DCB_HC_KIND(e) == kind0) pick = e;                                     // half2 only when half1 never hit (:339 / :473)
+        n_full += DCB_HC_KIND(e) == 0u ? 1 : 0;
+    }
+    if (n_full > 1) {          // several occurrences of full tags (only the J scan of half_jshort_at lists them one by one): :278 / :402
+        pend |= 1u << (IS_V ? DCB_C_multiple_v_matches : DCB_C_multiple_j_matches);
+        return 0u;
     }
     if (!pick)  // :334 / :389 / :469 / :526 -- the J half2 failure bumps foundv2notv1 in the reference; preserved
         pend |= 1u << (IS_V ? (kind0 == 1u ? DCB_C_foundv1notv2 : DCB_C_foundv2notv1) : (kind0 == 1u ? DCB_C_foundj1notj2 : DCB_C_foundv2notv1));
@@ -1344,6 +1424,9 @@ DCB_HD bool half_run(const ReadView& r, const uint32_t* inv2, const HalfView& hx
                      uint32_t hv, uint32_t hj, uint32_t* cand, int cap, uint32_t n, const DcrParams& prm, dcb_result& out, uint32_t& pend,
                      int* why = nullptr) {
     if (why) *why = n >= DCB_HALF_BAIL ? 2 : 3;
+    const uint32_t seen = n;
+    if (n >= DCB_HALF_BAIL) return false;
+    n = DCB_HALF_COUNT(n);
     if (n > (uint32_t)cap) return false;
     for (int g = 0; g < 2; g++) {                                                           // the full-tag occurrences handed over
         const uint32_t h = g ? hj : hv;
@@ -1359,15 +1442,15 @@ DCB_HD bool half_run(const ReadView& r, const uint32_t* inv2, const HalfView& hx
     j = v;
     int i = 0;
     bool ok = true;
-    const uint32_t ev = half_select<true>(cand, r.stride, (int)n, i, pend);
+    const uint32_t ev = half_select<true>(cand, r.stride, (int)n, i, pend, seen);
     if (ev) ok = half_walk<true, PADDED>(r, inv2, hx, vtags, ev, 0, v);
     if (why) *why = 4;
     // V is assigned: now J.  A J gene that was not searched for full tags, or whose half tags this index does not hold
     // while the full tag is missing, is the general kernel's business.
-    if (ev && ok && (hj == DCB_HIT_UNKNOWN || (hj == 0u && !hx.j_ok))) return false;
+    if (ev && ok && !hx.j_short && (hj == DCB_HIT_UNKNOWN || (hj == 0u && !hx.j_ok))) return false;
     uint32_t ej = 0u;
     if (ev && ok) {                                                                         // :542-548
-        ej = half_select<false>(cand, r.stride, (int)n, i, pend);
+        ej = half_select<false>(cand, r.stride, (int)n, i, pend, seen);
         if (!ej) pend |= 1u << DCB_C_VJ_assignment_failed;                                  // :583-585
     }
     if (ej) ok = half_walk<false, PADDED>(r, inv2, hx, jtags, ej, v.pos + 1, j);
@@ -1411,6 +1494,9 @@ DCB_HD bool dcr_half_read(ReadView r, bool flagged, const ExcList& ex, uint32_t 
                 half_lookup<false>(r, inv2, hx, b >> 2, sink.P, sink);
             }
         }
+    if (half_jshort_ok(hx, hv, hj, cand, r.stride, cap, n))
+        for (int p = 0; p + DCB_HALF_JQ <= r.n; p++)
+            half_jshort_at<false>(r, inv2, hx, vtags, jtags, rd_win16(r, p) & mask2(DCB_HALF_JQ), p, hj == DCB_HIT_UNKNOWN, cand, cap, &n);
     dcb_result o;
     o.status = 0; o.frame = 0; o.v = o.j = 0; o.vdel = o.jdel = 0;
     o.ins_start = o.ins_end = o.v_seq_start = o.j_seq_end = 0;

@@ -813,47 +813,104 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
             }
         }
         __syncwarp();
-        //    a'. lane k takes prefix hit k: the keywords with that prefix are compared with the read as a whole; an occurrence
-        //       puts one item per tag that has this half on the third list
-        const int n_pre = (int)min(s_n2[0], (uint32_t)DCB_HALF_WCAP2);
-        for (int k0 = 0; k0 < n_pre; k0 += 32) {
-            const bool has = k0 + lane < n_pre;
-            const uint32_t it = has ? s_work2[k0 + lane] : (uint32_t)lane;
-            const int src = (int)(it & 31u), P = (int)((it >> 5) & 1023u), set = (int)((it >> 15) & 3u);
-            const int n_s = __shfl_sync(0xFFFFFFFFu, r.n, src);
-            const int flg_s = __shfl_sync(0xFFFFFFFFu, inv2 != nullptr ? 1 : 0, src);
-            if (has) {
-                ReadView rs;
-                rs.w = s_rd + T + wbase + src; rs.stride = T; rs.nw = NW; rs.n = n_s;
-                struct Sink {
-                    uint32_t* list; uint32_t* n3; uint32_t* n_src; uint32_t base;
-                    __device__ __forceinline__ void operator()(int id, int n_tags) {
-                        const uint32_t at = atomicAdd(n3, (uint32_t)n_tags);
-                        if (at + n_tags > DCB_HALF_WCAP2) { atomicAdd(n_src, DCB_HALF_BAIL); return; }   // list full: pass the read on
-                        for (int ti = 0; ti < n_tags; ti++) list[at + ti] = base | ((uint32_t)id << 15) | ((uint32_t)ti << 23);
+        //    Round 0: the prefix hits of the sampled index.  Rounds 1, 2, ..., only for chains whose J halves are below the sampled
+        //    index (j_short: 12-nt J tags): a read whose V is assigned and whose J is missing is probed with the 6-mer table at
+        //    every base, the warp's lanes taking 8 bases each; the occurrences go on the (empty again) second list and through
+        //    the same two stages, a few reads per round.  Where the exact-tag kernel did not search J, the full J tags are
+        //    compared as well.
+        uint32_t mw = 0;                                        // reads of this warp still to be scanned (rounds 1, 2, ...)
+        for (int round = 0;; round++) {
+            if (round >= 1) {
+                if (round == 1) {
+                    if (!hx.j_short) break;
+                    mw = __ballot_sync(0xFFFFFFFFu, act && half_jshort_ok(hx, hv, hj, s_cand + tid, T, DCB_HALF_CAP, s_n[tid]));
+                }
+                if (!mw) break;
+                if (lane == 0) { s_n2[0] = 0u; s_n2[1] = 0u; }
+                __syncwarp();
+                while (mw) {                                    // as many reads per round as the lists take comfortably
+                    const int src = __ffs(mw) - 1;
+                    mw &= mw - 1u;
+                    const int n_s = __shfl_sync(0xFFFFFFFFu, r.n, src);
+                    const uint32_t full_s = __shfl_sync(0xFFFFFFFFu, hj == DCB_HIT_UNKNOWN ? 1u : 0u, src);
+                    const uint32_t* cs = s_rd + T + wbase + src;
+                    for (int base = 0; base + DCB_HALF_JQ <= n_s; base += 256) {
+                        const int p0 = base + 8 * lane;
+                        uint32_t found = 0;                     // bit k: a J half keyword may start at p0 + k
+                        if (p0 + DCB_HALF_JQ <= n_s) {
+                            const uint32_t* c0 = cs + (p0 >> 4) * T;
+                            const uint64_t w64 = (((uint64_t)c0[T] << 32) | c0[0]) >> ((p0 & 15) * 2);
+#pragma unroll
+                            for (int k = 0; k < 8; k++)
+                                found |= (hx.jt[(uint32_t)(w64 >> (2 * k)) & 0xFFFu] != 0 && p0 + k + DCB_HALF_JQ <= n_s ? 1u : 0u) << k;
+                        }
+                        for (; found; found &= found - 1u) {
+                            const uint32_t at = atomicAdd(s_n2, 1u);
+                            if (at < DCB_HALF_WCAP2) s_work2[at] = (uint32_t)src | ((uint32_t)(p0 + __ffs(found) - 1) << 5) | (1u << 17) | (full_s << 18);
+                            else atomicAdd(s_n + wbase + src, DCB_HALF_BAIL);               // list full: pass the read on
+                        }
                     }
-                } sink{s_work3, s_n2 + 1, s_n + wbase + src, (uint32_t)src | ((uint32_t)P << 5)};
-                half_keywords<true>(rs, flg_s ? s_inv + T + wbase + src : nullptr, hx, half_prefix<true>(rs, hx, set, P), P, sink);
+                    __syncwarp();
+                    if (s_n2[0] >= DCB_HALF_WCAP2 / 3) break;
+                }
             }
-        }
-        __syncwarp();
-        //    b. lane k takes item k of the second list: one (occurrence, tag) pair -> length guard, Hamming <= 1, the
-        //       candidate appended to its read's list
-        const int n_work2 = (int)min(s_n2[1], (uint32_t)DCB_HALF_WCAP2);
-        for (int k0 = 0; k0 < n_work2; k0 += 32) {
-            const bool has = k0 + lane < n_work2;
-            const uint32_t it = has ? s_work3[k0 + lane] : (uint32_t)lane;
-            const int src = (int)(it & 31u);
-            const int n_s = __shfl_sync(0xFFFFFFFFu, r.n, src);
-            const int flg_s = __shfl_sync(0xFFFFFFFFu, inv2 != nullptr ? 1 : 0, src);
-            if (has) {
-                ReadView rs;
-                rs.w = s_rd + T + wbase + src; rs.stride = T; rs.nw = NW; rs.n = n_s;
-                half_candidate<true>(rs, flg_s ? s_inv + T + wbase + src : nullptr, hx, vtags, jtags, (int)((it >> 15) & 255u),
-                                     (int)(it >> 23), (int)((it >> 5) & 1023u), s_cand + wbase + src, DCB_HALF_CAP, s_n + wbase + src);
+            //    a'. lane k takes prefix hit k: the keywords with that prefix are compared with the read as a whole; an occurrence
+            //       puts one item per tag that has this half on the third list
+            const int n_pre = (int)min(s_n2[0], (uint32_t)DCB_HALF_WCAP2);
+            for (int k0 = 0; k0 < n_pre; k0 += 32) {
+                const bool has = k0 + lane < n_pre;
+                const uint32_t it = has ? s_work2[k0 + lane] : (uint32_t)lane;
+                const int src = (int)(it & 31u), P = (int)((it >> 5) & 1023u), set = (int)((it >> 15) & 3u);
+                const int n_s = __shfl_sync(0xFFFFFFFFu, r.n, src);
+                const int flg_s = __shfl_sync(0xFFFFFFFFu, inv2 != nullptr ? 1 : 0, src);
+                if (has) {
+                    ReadView rs;
+                    rs.w = s_rd + T + wbase + src; rs.stride = T; rs.nw = NW; rs.n = n_s;
+                    struct Sink {
+                        uint32_t* list; uint32_t* n3; uint32_t* n_src; uint32_t base;
+                        __device__ __forceinline__ void operator()(int id, int n_tags) {
+                            const uint32_t at = atomicAdd(n3, (uint32_t)n_tags);
+                            if (at + n_tags > DCB_HALF_WCAP2) {             // list full: pass the read on; what was reserved is void
+                                atomicAdd(n_src, DCB_HALF_BAIL);
+                                for (uint32_t q = at; q < DCB_HALF_WCAP2; q++) list[q] = 0xFFFFFFFFu;
+                                return;
+                            }
+                            for (int ti = 0; ti < n_tags; ti++) list[at + ti] = base | ((uint32_t)id << 15) | ((uint32_t)ti << 23);
+                        }
+                    } sink{s_work3, s_n2 + 1, s_n + wbase + src, (uint32_t)src | ((uint32_t)P << 5) | (((it >> 18) & 1u) << 27)};
+                    uint32_t meta;
+                    if ((it >> 17) & 1u) {                          // a 6-mer hit of the J scan
+                        uint32_t lo, hi;
+                        rd_win32x<true>(rs, P, lo, hi);
+                        meta = hx.jt[lo & 0xFFFu];
+                    } else {
+                        meta = half_prefix<true>(rs, hx, set, P);
+                    }
+                    half_keywords<true>(rs, flg_s ? s_inv + T + wbase + src : nullptr, hx, meta, P, sink);
+                }
             }
+            __syncwarp();
+            //    b. lane k takes item k of the third list: one (occurrence, tag) pair -> length guard, Hamming <= 1, the
+            //       candidate appended to its read's list
+            const int n_work2 = (int)min(s_n2[1], (uint32_t)DCB_HALF_WCAP2);
+            for (int k0 = 0; k0 < n_work2; k0 += 32) {
+                uint32_t it = k0 + lane < n_work2 ? s_work3[k0 + lane] : 0xFFFFFFFFu;
+                const bool has = it != 0xFFFFFFFFu;
+                if (!has) it = (uint32_t)lane;
+                const int src = (int)(it & 31u);
+                const int n_s = __shfl_sync(0xFFFFFFFFu, r.n, src);
+                const int flg_s = __shfl_sync(0xFFFFFFFFu, inv2 != nullptr ? 1 : 0, src);
+                if (has) {
+                    ReadView rs;
+                    rs.w = s_rd + T + wbase + src; rs.stride = T; rs.nw = NW; rs.n = n_s;
+                    const uint32_t* inv_s = flg_s ? s_inv + T + wbase + src : nullptr;
+                    const int id = (int)((it >> 15) & 255u), ti = (int)((it >> 23) & 15u), P = (int)((it >> 5) & 1023u);
+                    half_candidate<true>(rs, inv_s, hx, vtags, jtags, id, ti, P, s_cand + wbase + src, DCB_HALF_CAP, s_n + wbase + src);
+                    if ((it >> 27) & 1u) half_jfull_candidate<true>(rs, inv_s, hx, jtags, id, ti, P, s_cand + wbase + src, DCB_HALF_CAP, s_n + wbase + src);
+                }
+            }
+            __syncwarp();
         }
-        __syncwarp();
         // 4. decide: the candidates in the reference's order
         bool pass_on = live && !act;
         if (act) {
@@ -1109,14 +1166,22 @@ static int q_rows(int nw) {   // must match the kernel's ROWS
 
 typedef void (*halftag_fn)(BatchDev, Tables4, DcrParams, dcb_result*, unsigned long long*, const uint32_t*, const uint32_t*, uint32_t*, uint32_t*);
 // block width per slot size: as wide as the read / invalid-base / candidate columns leave room for beside the tables
-static halftag_fn pick_half(int nw, int* threads) {
-    switch (nw) {
-        case 8:  *threads = 768; return dcb_halftag_kernel<8, 768>;
-        case 12: *threads = 768; return dcb_halftag_kernel<12, 768>;
-        case 16: *threads = 736; return dcb_halftag_kernel<16, 736>;
-        case 20: *threads = 608; return dcb_halftag_kernel<20, 608>;
+static halftag_fn pick_half(int nw, int attempt, int* threads) {
+    // widest first; the later attempts are for tag sets whose tables leave less room
+#define DCB_HALF_PICK(NW_, T_) { *threads = T_; return dcb_halftag_kernel<NW_, T_>; }
+    switch (nw * 4 + attempt) {
+        case 32: DCB_HALF_PICK(8, 768)
+        case 33: DCB_HALF_PICK(8, 640)
+        case 48: DCB_HALF_PICK(12, 768)
+        case 49: DCB_HALF_PICK(12, 640)
+        case 64: DCB_HALF_PICK(16, 736)
+        case 65: DCB_HALF_PICK(16, 672)
+        case 66: DCB_HALF_PICK(16, 608)
+        case 80: DCB_HALF_PICK(20, 608)
+        case 81: DCB_HALF_PICK(20, 544)
         default: return nullptr;
     }
+#undef DCB_HALF_PICK
 }
 
 // rows of shared memory per read column in the specialised kernel (must match the kernel's ROWS)
@@ -1355,16 +1420,17 @@ static int prepare_batch(dcb_ctx* c, const dcb_packed* P, size_t exc_cap = 0) {
     // half-tag kernel: between the flat kernel and the general kernel, for chains with a half-tag index (one frame only)
     c->half_fn = nullptr;
     if (c->d_half && !c->params.both_frames && c->params.force_general == 0) {
-        int ht = 0;
-        halftag_fn hf = pick_half((int)sw, &ht);
-        c->half_threads = ht;
-        c->half_smem = ((size_t)c->vcore_words + c->jcore_words + c->half_words + (2 * (sw + 3) + DCB_HALF_CAP + 1) * ht +
-                        (ht / 32) * (DCB_HALF_WCAP / 2 + 2 * DCB_HALF_WCAP2 + 2)) * 4 + tail;
-        int occ_h = 0;
-        if (hf && c->half_smem <= kMaxSmem) {
-            CUDA_TRY(cudaFuncSetAttribute(hf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->half_smem));
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_h, hf, ht, c->half_smem));
-            if (occ_h >= 1) { c->half_fn = (void*)hf; c->half_grid = c->n_sms * occ_h; }
+        for (int attempt = 0; attempt < 4 && !c->half_fn; attempt++) {
+            int ht = 0;
+            halftag_fn hf = pick_half((int)sw, attempt, &ht);
+            if (!hf) break;
+            const size_t smem = ((size_t)c->vcore_words + c->jcore_words + c->half_words + (2 * (sw + 3) + DCB_HALF_CAP + 1) * ht +
+                                 (ht / 32) * (DCB_HALF_WCAP / 2 + 2 * DCB_HALF_WCAP2 + 2)) * 4 + tail;
+            if (smem > kMaxSmem) continue;
+            int occ_h = 0;
+            CUDA_TRY(cudaFuncSetAttribute(hf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_h, hf, ht, smem));
+            if (occ_h >= 1) { c->half_fn = (void*)hf; c->half_grid = c->n_sms * occ_h; c->half_threads = ht; c->half_smem = smem; }
         }
     }
     if (occ_e < 1 || occ_g < 1) { dcb_set_error("kernel does not fit on an SM"); return DCB_EUNSUPPORTED; }

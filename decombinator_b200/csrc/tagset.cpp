@@ -436,14 +436,20 @@ bool dcb_build_half_index(const dcb_tagset* v, const dcb_tagset* j, std::vector<
     hx.j_ok = 1;
     for (int t = 0; t < j->n_tags; t++)
         if (j->split < hx.kmin || (int)j->tags[t].size() - j->split < hx.kmin) hx.j_ok = 0;
+    // J halves below kmin (the 6-base halves of the 12-nt J tags) are not in the sampled index; when they have at least
+    // DCB_HALF_JQ bases they get a table of their own, probed at EVERY base of the reads that need it (j_short)
+    hx.j_short = hx.j_ok ? 0 : 1;
+    for (int t = 0; t < j->n_tags; t++)
+        if (j->split < DCB_HALF_JQ || (int)j->tags[t].size() - j->split < DCB_HALF_JQ) hx.j_short = 0;
     for (int gi = 0; gi < 2; gi++) {
         const dcb_tagset* ts = gi ? j : v;
-        if (gi == 1 && !hx.j_ok) break;                             // J halves too short: the V side only
+        if (gi == 1 && !hx.j_ok && !hx.j_short) break;              // J halves too short: the V side only
+        const int kmin = (gi == 1 && !hx.j_ok) ? DCB_HALF_JQ : hx.kmin;
         for (int half = 0; half < 2; half++) {
             std::map<std::string, size_t> seen;
             for (int t = 0; t < ts->n_tags; t++) {
                 const std::string h = half ? ts->tags[t].substr(ts->split) : ts->tags[t].substr(0, ts->split);
-                if ((int)h.size() < hx.kmin || h.size() > 31 || ts->tags[t].size() > 31) return false;
+                if ((int)h.size() < kmin || h.size() > 31 || ts->tags[t].size() > 31) return false;
                 auto it = seen.find(h);
                 if (it == seen.end()) { seen[h] = kws.size(); kws.push_back({h, 2 * gi + half, {t}}); }
                 else kws[it->second].tags.push_back(t);             // ascending tag index
@@ -457,23 +463,31 @@ bool dcb_build_half_index(const dcb_tagset* v, const dcb_tagset* j, std::vector<
     hx.t_off = b.reserve(((size_t)1 << (2 * hx.q)) / 2);
     uint16_t* t16 = reinterpret_cast<uint16_t*>(&b.w[hx.t_off]);
     std::map<uint32_t, std::vector<int>> by_prefix;                 // set << 28 | kmin-prefix -> keyword record numbers
+    std::map<uint32_t, std::vector<int>> by_six;                    // j_short: first DCB_HALF_JQ bases -> J keyword record numbers (both halves)
     std::vector<uint8_t> tag_ids;
     std::vector<DcbHalfKw> recs(kws.size());
     for (size_t i = 0; i < kws.size(); i++) {
         const Kw& k = kws[i];
         uint32_t lo, hi;
-        for (int o = 0; o < hx.stride; o++) {
-            if (!pack64(k.s, o, hx.q, lo, hi)) return false;
-            t16[lo] |= (uint16_t)(1u << (4 * k.set + o));
+        if (k.set >= 2 && hx.j_short) {
+            if (!pack64(k.s, 0, DCB_HALF_JQ, lo, hi)) return false;
+            by_six[lo].push_back((int)i);
+        } else {
+            for (int o = 0; o < hx.stride; o++) {
+                if (!pack64(k.s, o, hx.q, lo, hi)) return false;
+                t16[lo] |= (uint16_t)(1u << (4 * k.set + o));
+            }
+            pack64(k.s, 0, hx.kmin, lo, hi);
+            by_prefix[((uint32_t)k.set << 28) | lo].push_back((int)i);
         }
-        pack64(k.s, 0, hx.kmin, lo, hi);
-        by_prefix[((uint32_t)k.set << 28) | lo].push_back((int)i);
+        if (!pack64(k.s, 0, k.s.size(), lo, hi)) return false;
         DcbHalfKw& r = recs[i];
         std::memset(&r, 0, sizeof(r));
         pack64(k.s, 0, k.s.size(), r.bits_lo, r.bits_hi);
         const dcb_tagset* ts = k.set >= 2 ? j : v;
         r.len = (uint8_t)k.s.size();
         r.first_len = (uint8_t)ts->tags[k.tags[0]].size();          // len(seqs[halfN_seqs.index(keyword)])
+        if (k.tags.size() > 15) return false;                       // the kernel's work items count them in four bits
         r.n_tags = (uint8_t)k.tags.size();
         r.set = (uint8_t)k.set;
         if (tag_ids.size() + k.tags.size() > 65535) return false;
@@ -488,6 +502,15 @@ bool dcb_build_half_index(const dcb_tagset* v, const dcb_tagset* j, std::vector<
         // together), the hit list is sorted by (end, length) afterwards
         items.emplace_back(kv.first, (uint32_t)ids.size() | ((uint32_t)kv.second.size() << 8));
         for (int i : kv.second) ids.push_back((uint8_t)i);
+    }
+    std::vector<uint16_t> jt;
+    if (hx.j_short) {
+        jt.assign((size_t)1 << (2 * DCB_HALF_JQ), 0);
+        for (auto& kv : by_six) {
+            if (kv.second.size() > 255 || ids.size() > 255) return false;
+            jt[kv.first] = (uint16_t)(ids.size() | (kv.second.size() << 8));     // same layout as a prefix-table value
+            for (int i : kv.second) ids.push_back((uint8_t)i);
+        }
     }
     Cuckoo ck;
     if (!build_cuckoo(ck, items)) return false;
@@ -507,6 +530,10 @@ bool dcb_build_half_index(const dcb_tagset* v, const dcb_tagset* j, std::vector<
     std::memcpy(&b.w[hx.kw_off], recs.data(), sizeof(DcbHalfKw) * recs.size());
     hx.tags_off = b.reserve((tag_ids.size() + 3) / 4 + 1);
     std::memcpy(&b.w[hx.tags_off], tag_ids.data(), tag_ids.size());
+    if (hx.j_short) {
+        hx.jt_off = b.reserve(jt.size() / 2);
+        std::memcpy(&b.w[hx.jt_off], jt.data(), 2 * jt.size());
+    }
     b.align4();
     hx.n_words = (int32_t)b.w.size();
     std::memcpy(&b.w[0], &hx, sizeof(hx));

@@ -81,6 +81,31 @@ def test_cuda_matches_oracle_on_synthetic(species, tagset, chain, orientation, L
     packed.free()
 
 
+ALL_CHAINS = [(sp, ts, ch) for sp in ("human", "mouse") for ts in ("original", "extended") for ch in "abgd"]
+
+
+@pytest.mark.parametrize("species,tagset,chain", ALL_CHAINS)
+def test_halftag_kernel_serves_every_shipped_chain(species, tagset, chain):
+    """Every shipped tag set / chain, 250-nt reads with 1 % substitutions: the half-tag kernel is picked (its tables and
+    columns fit an SM for each of them), it takes most of what the exact-tag kernel queues -- for the 12-nt J tags through
+    the 6-mer scan, dcr_core.cuh half_jshort_at -- and the records and counters are the oracle's."""
+    info = tags.load(species, tagset, chain)
+    n = 40000
+    r1, off, ln = synth_batch(info, n, 250, 0.01, 0.0, 0.02, seed=20260006)
+    orc = O.Oracle(O.TagSet(species, tagset, chain))
+    want = orc.decombine_arrays(r1, off, ln, "reverse", nthreads=os.cpu_count() or 4)
+    packed = _lib.pack_arrays(r1, off, ln, revcomp=True)
+    ctx = _ctx(info)
+    res, cnt = ctx.decombine(packed)
+    assert_records_equal(res, want, "reverse", "%s %s %s" % (species, tagset, chain))
+    assert np.array_equal(cnt, orc.counts), dict(zip(O.COUNTER_NAMES, zip(cnt, orc.counts)))
+    assert ctx.halftag_kernel_name() == "dcb_halftag_kernel"
+    assert ctx.last_deferred() > 0.05 * n and ctx.last_general() <= 0.35 * ctx.last_deferred(), (ctx.last_deferred(), ctx.last_general())
+    res2, cnt2 = ctx.decombine(packed)                 # work lists filled by atomics: the order must not matter
+    assert np.array_equal(res2, res) and np.array_equal(cnt2, cnt)
+    packed.free(); ctx.close()
+
+
 def test_mixed_alpha_beta_stream_config3():
     """BASELINE configs[2]: one mixed file (even reads alpha, odd reads beta) analysed once per chain."""
     ia, ib = tags.load("human", "extended", "a"), tags.load("human", "extended", "b")
