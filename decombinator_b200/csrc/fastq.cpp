@@ -12,9 +12,15 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <chrono>
+#include <sys/mman.h>
+#include <cstdio>
 #include <cstring>
 #include <thread>
 #include <vector>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 namespace {
 
@@ -29,6 +35,25 @@ void parallel_for(int n_threads, uint64_t n, F f) {
 
 }  // namespace
 
+#if defined(__x86_64__)
+namespace {
+const bool kAvx2 = __builtin_cpu_supports("avx2");
+// Line starts of text[i .. b) in steps of 32 bytes (i is left at the first byte not looked at); returns non-zero when a
+// '\r' or a non-ASCII byte was seen.
+__attribute__((target("avx2"))) unsigned char scan_lines_avx2(const unsigned char* p, uint64_t& i, uint64_t b, std::vector<uint64_t>& v) {
+    const __m256i nl = _mm256_set1_epi8('\n'), cr = _mm256_set1_epi8('\r');
+    __m256i acc = _mm256_setzero_si256();
+    for (; i + 32 <= b; i += 32) {
+        const __m256i x = _mm256_loadu_si256((const __m256i*)(p + i));
+        acc = _mm256_or_si256(acc, _mm256_or_si256(x, _mm256_cmpeq_epi8(x, cr)));
+        for (uint32_t m = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(x, nl)); m; m &= m - 1u)
+            v.push_back(i + (uint64_t)__builtin_ctz(m) + 1);
+    }
+    return _mm256_movemask_epi8(acc) != 0 ? 1 : 0;
+}
+}  // namespace
+#endif
+
 extern "C" {
 
 int dcb_fastq_index_build(const char* text, uint64_t n_bytes, int n_threads, dcb_fastq_index** out) {
@@ -41,37 +66,49 @@ int dcb_fastq_index_build(const char* text, uint64_t n_bytes, int n_threads, dcb
     ix->strict = 0;
     if (n_bytes == 0 || text[n_bytes - 1] != '\n') return DCB_OK;          // empty, or the last line is not terminated
 
-    // pass 1: newlines per chunk; '\r' or a non-ASCII byte anywhere ends the strict path
-    std::vector<uint64_t> nl(n_threads + 1, 0);
+    const auto T0 = std::chrono::steady_clock::now();
+    // pass 1 (the only one over the whole text): every thread lists the line starts of its chunk and checks its bytes --
+    // a '\r' or a non-ASCII byte anywhere ends the strict path
+    std::vector<std::vector<uint64_t>> found(n_threads);
     std::vector<int> bad(n_threads, 0);
-    parallel_for(n_threads, n_bytes, [&](int t, uint64_t a, uint64_t b) {
-        uint64_t c = 0;
-        unsigned char any = 0;
+    const int nt1 = (n_bytes < 4096) ? 1 : n_threads;
+    parallel_for(nt1, n_bytes, [&](int t, uint64_t a, uint64_t b) {
+        std::vector<uint64_t>& v = found[t];
+        v.reserve((size_t)((b - a) / 48 + 16));
         const unsigned char* p = (const unsigned char*)text;
-        for (uint64_t i = a; i < b; i++) { c += p[i] == '\n'; any |= (unsigned char)((p[i] & 0x80) | (p[i] == '\r' ? 0x80 : 0)); }
-        nl[t + 1] = c; bad[t] = any != 0;
+        unsigned char any = 0;
+        uint64_t i = a;
+#if defined(__x86_64__)
+        if (kAvx2) { any = scan_lines_avx2(p, i, b, v); }
+#endif
+        for (; i < b; i++) {
+            const unsigned char ch = p[i];
+            any |= (unsigned char)((ch & 0x80) | (ch == '\r' ? 0x80 : 0));
+            if (ch == '\n') v.push_back(i + 1);
+        }
+        bad[t] = any != 0;
     });
-    for (int t = 0; t < n_threads; t++) { if (bad[t]) return DCB_OK; nl[t + 1] += nl[t]; }
+    const auto T1 = std::chrono::steady_clock::now();
+    std::vector<uint64_t> nl(n_threads + 1, 0);
+    for (int t = 0; t < n_threads; t++) { if (bad[t]) return DCB_OK; nl[t + 1] = nl[t] + found[t].size(); }
     const uint64_t n_lines = nl[n_threads];
     if (n_lines == 0 || n_lines % 4 != 0) return DCB_OK;
     const uint64_t n = n_lines / 4;
     if (n >= 0xFFFFFFFFull) return DCB_OK;
 
-    // pass 2: where every line starts (line k + 1 starts behind the k-th newline)
+    // where every line starts (line k + 1 starts behind the k-th newline): the threads' lists, end to end
     uint64_t* start = (uint64_t*)std::malloc(sizeof(uint64_t) * (n_lines + 1));
     if (!start) { dcb_set_error("dcb_fastq_index_build: out of memory"); return DCB_ENOMEM; }
     start[0] = 0;
-    parallel_for(n_threads, n_bytes, [&](int t, uint64_t a, uint64_t b) {
-        uint64_t k = nl[t];
-        const char* p = text + a;
-        const char* end = text + b;
-        while (p < end) {
-            const char* q = (const char*)std::memchr(p, '\n', (size_t)(end - p));
-            if (!q) break;
-            start[++k] = (uint64_t)(q - text) + 1;
-            p = q + 1;
-        }
-    });
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; t++)
+            if (!found[t].empty())
+                th.emplace_back([&, t] { std::memcpy(start + 1 + nl[t], found[t].data(), sizeof(uint64_t) * found[t].size()); });
+        for (auto& x : th) x.join();
+    }
+    found.clear();
+    const auto T2 = std::chrono::steady_clock::now();
 
     // pass 3: the records
     ix->name_off = (uint64_t*)std::malloc(sizeof(uint64_t) * n); ix->name_len = (uint32_t*)std::malloc(sizeof(uint32_t) * n);
@@ -98,6 +135,11 @@ int dcb_fastq_index_build(const char* text, uint64_t n_bytes, int n_threads, dcb
         }
     });
     std::free(start);
+    if (std::getenv("DCB_TIMING")) {
+        const auto T3 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "\t[timing] fastq index: scan %.3f s, line starts %.3f s, records %.3f s (%d threads)\n", std::chrono::duration<double>(T1 - T0).count(),
+                     std::chrono::duration<double>(T2 - T1).count(), std::chrono::duration<double>(T3 - T2).count(), n_threads);
+    }
     for (int t = 0; t < n_threads; t++) if (irregular[t]) return DCB_OK;
     ix->n_records = n;
     ix->strict = 1;
@@ -149,6 +191,44 @@ struct Comp {
 };
 const Comp kComp;
 
+// dst[k] = src[n - 1 - k] for k in [a, b): a reversed slice, 16 bytes at a time where the CPU has SSSE3
+#if defined(__x86_64__)
+#define DCB_HAVE_SSSE3_PATH 1
+const bool kSsse3 = __builtin_cpu_supports("ssse3");
+__attribute__((target("ssse3"))) inline void rev_copy_ssse3(char* dst, const char* src, int64_t n, int64_t a, int64_t b) {
+    const __m128i flip = _mm_set_epi8(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
+    int64_t k = a;
+    for (; k + 16 <= b; k += 16)         // dst[k .. k+16) = reversed src[n-16-k .. n-k)
+        _mm_storeu_si128((__m128i*)(dst + (k - a)), _mm_shuffle_epi8(_mm_loadu_si128((const __m128i*)(src + n - 16 - k)), flip));
+    for (; k < b; k++) dst[k - a] = src[n - 1 - k];
+}
+// The same with the complement of A C G T N; false (nothing usable written) when another symbol turns up: the caller
+// then takes the table (Bio.Seq's whole IUPAC alphabet, lower case).
+__attribute__((target("ssse3"))) inline bool revcomp_copy_ssse3(char* dst, const unsigned char* src, int64_t n, int64_t a, int64_t b) {
+    const __m128i flip = _mm_set_epi8(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
+    // by low nibble: 'A' 0x41 -> 1, 'C' 0x43 -> 3, 'T' 0x54 -> 4, 'G' 0x47 -> 7, 'N' 0x4E -> 14
+    const __m128i comp = _mm_setr_epi8(0, 'T', 0, 'G', 'A', 0, 0, 'C', 0, 0, 0, 0, 0, 0, 'N', 0);
+    const __m128i self = _mm_setr_epi8(-1, 'A', -1, 'C', 'T', -1, -1, 'G', -1, -1, -1, -1, -1, -1, 'N', -1);
+    const __m128i low = _mm_set1_epi8(0x0F);
+    int64_t k = a;
+    int ok = 0xFFFF;
+    for (; k + 16 <= b; k += 16) {
+        const __m128i v = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i*)(src + n - 16 - k)), flip);
+        const __m128i nib = _mm_and_si128(v, low);
+        ok &= _mm_movemask_epi8(_mm_cmpeq_epi8(_mm_shuffle_epi8(self, nib), v));
+        _mm_storeu_si128((__m128i*)(dst + (k - a)), _mm_shuffle_epi8(comp, nib));
+    }
+    if (ok != 0xFFFF) return false;
+    for (; k < b; k++) {
+        const unsigned char ch = src[n - 1 - k];
+        char o;
+        switch (ch) { case 'A': o = 'T'; break; case 'C': o = 'G'; break; case 'G': o = 'C'; break; case 'T': o = 'A'; break; case 'N': o = 'N'; break; default: return false; }
+        dst[k - a] = o;
+    }
+    return true;
+}
+#endif
+
 inline void clip(int64_t len, int64_t& a, int64_t& b) {          // Python s[a:b] for a, b >= 0
     if (a > len) a = len;
     if (b > len) b = len;
@@ -185,15 +265,24 @@ inline size_t row_emit(const RowCtx& c, uint64_t i, char* dst) {
     const unsigned char* s = (const unsigned char*)c.vdj->text + c.vdj->off[i];
     const char* q = c.qual->text + c.qual->off[i];
     auto seq = [&](int64_t a, int64_t b) {                       // oriented[a:b]
-        if (rev) for (int64_t k = a; k < b; k++) *p++ = (char)kComp.t[s[n - 1 - k]];
-        else { std::memcpy(p, s + a, (size_t)(b - a)); p += b - a; }
+        if (rev) {
+#ifdef DCB_HAVE_SSSE3_PATH
+            if (kSsse3 && b - a >= 16 && revcomp_copy_ssse3(p, s, n, a, b)) { p += b - a; return; }
+#endif
+            for (int64_t k = a; k < b; k++) *p++ = (char)kComp.t[s[n - 1 - k]];
+        } else { std::memcpy(p, s + a, (size_t)(b - a)); p += b - a; }
     };
     p = put_dec(p, r.v); sep(); p = put_dec(p, r.j); sep(); p = put_dec(p, r.vdel); sep(); p = put_dec(p, r.jdel); sep();
     seq(ia, ib); sep();
     raw(c.ids); sep();
     seq(sa, sb); sep();
-    if (rev) for (int64_t k = qa; k < qb; k++) *p++ = q[nq - 1 - k];
-    else { std::memcpy(p, q + qa, (size_t)(qb - qa)); p += qb - qa; }
+    if (rev) {
+#ifdef DCB_HAVE_SSSE3_PATH
+        if (kSsse3) { rev_copy_ssse3(p, q, nq, qa, qb); p += qb - qa; }
+        else
+#endif
+        for (int64_t k = qa; k < qb; k++) *p++ = q[nq - 1 - k];
+    } else { std::memcpy(p, q + qa, (size_t)(qb - qa)); p += qb - qa; }
     sep();
     raw(c.bc); sep();
     raw(c.bcq);
@@ -215,6 +304,7 @@ int dcb_format_rows(const dcb_result* res, uint64_t n, int packed_revcomp, const
     }
     if (n_threads < 1) n_threads = 1;
     if (n_threads > 64) n_threads = 64;
+    const auto T0 = std::chrono::steady_clock::now();
     RowCtx c;
     c.res = res; c.packed_rc = packed_revcomp; c.ids = ids; c.vdj = vdj; c.qual = vdjqual; c.bc = bc; c.bcq = bcq; c.tail = v_tail;
     c.sep = sep; c.sep_len = std::strlen(sep);
@@ -234,7 +324,17 @@ int dcb_format_rows(const dcb_result* res, uint64_t n, int packed_revcomp, const
         for (auto& x : th) x.join();
     }
     for (int t = 0; t < nt; t++) { bytes[t + 1] += bytes[t]; rows[t + 1] += rows[t]; }
-    char* buf = (char*)std::malloc(bytes[nt] + 1);
+    const auto T1 = std::chrono::steady_clock::now();
+    // a large buffer is first touched here: huge pages (where the system hands them out) cut the page faults 512-fold
+    char* buf = nullptr;
+    if (bytes[nt] >= ((size_t)8 << 20) && !std::getenv("DCB_NO_HUGE")) {
+        const size_t huge = (size_t)2 << 20, want = (bytes[nt] + 1 + huge - 1) / huge * huge;
+        buf = (char*)std::aligned_alloc(huge, want);
+#ifdef MADV_HUGEPAGE
+        if (buf) madvise(buf, want, MADV_HUGEPAGE);
+#endif
+    }
+    if (!buf) buf = (char*)std::malloc(bytes[nt] + 1);
     if (!buf) { dcb_set_error("dcb_format_rows: out of memory"); return DCB_ENOMEM; }
     {
         std::vector<std::thread> th;
@@ -248,6 +348,11 @@ int dcb_format_rows(const dcb_result* res, uint64_t n, int packed_revcomp, const
         for (auto& x : th) x.join();
     }
     buf[bytes[nt]] = 0;
+    if (std::getenv("DCB_TIMING")) {
+        const auto T2 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "\t[timing] format_rows: sizes %.3f s, emit %.3f s (%.2f GB)\n", std::chrono::duration<double>(T1 - T0).count(),
+                     std::chrono::duration<double>(T2 - T1).count(), bytes[nt] / 1e9);
+    }
     *out = buf; *out_bytes = bytes[nt]; *n_rows = rows[nt];
     return DCB_OK;
 }
