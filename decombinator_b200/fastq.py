@@ -181,15 +181,20 @@ def load_pairs_native(inputargs, opener):
     if not isinstance(bclength, int) or bclength < 0 or inputargs["bc_read"] not in ("R1", "R2"):
         return None
     data1 = _file_bytes(inputargs["infile"], opener)
-    ix1 = _lib.fastq_index(data1)
-    if ix1 is None:
-        return None
     sampling = inputargs.get("sampling_analysis")
     batch = ReadBatch()
     if inputargs["bc_read"] == "R2":
+        # both files are indexed side by side (the native call releases the GIL): the line-start and record passes of one
+        # overlap the text scan of the other
+        import threading
         data2 = _file_bytes(inputargs["infile"].replace("1.f", "2.f"), opener)
-        ix2 = _lib.fastq_index(data2)
-        if ix2 is None:
+        box = {}
+        th = threading.Thread(target=lambda: box.__setitem__("ix2", _lib.fastq_index(data2)))
+        th.start()
+        ix1 = _lib.fastq_index(data1)
+        th.join()
+        ix2 = box.get("ix2")
+        if ix1 is None or ix2 is None:
             return None
         n = min(len(ix1["seq_off"]), len(ix2["seq_off"]))            # zip() stops at the shorter file
         one = {k: v[:n] for k, v in ix1.items()}
@@ -201,6 +206,9 @@ def load_pairs_native(inputargs, opener):
         batch.bcq = TextColumn(data2, *_clip(two["qual_off"], two["qual_len"], 0, bclength))
         batch.v_tail = TextColumn(data2, *_clip(two["seq_off"], two["seq_len"], bclength, bclength + 31)) if sampling else []
     else:
+        ix1 = _lib.fastq_index(data1)
+        if ix1 is None:
+            return None
         # the reference zips the generator with itself: records 2k and 2k+1 are consumed together, the second only
         # feeds the sampling column
         n = len(ix1["seq_off"]) // 2
