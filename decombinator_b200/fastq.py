@@ -180,20 +180,30 @@ def load_pairs_native(inputargs, opener):
     bclength = inputargs["bclength"]
     if not isinstance(bclength, int) or bclength < 0 or inputargs["bc_read"] not in ("R1", "R2"):
         return None
-    data1 = _file_bytes(inputargs["infile"], opener)
     sampling = inputargs.get("sampling_analysis")
     batch = ReadBatch()
     if inputargs["bc_read"] == "R2":
-        # both files are indexed side by side (the native call releases the GIL): the line-start and record passes of one
-        # overlap the text scan of the other
+        # both files are read (for .gz: decompressed -- zlib releases the GIL, and that is most of the wall time of a run on
+        # compressed input) and indexed side by side: the line-start and record passes of one overlap the text scan of the other
         import threading
-        data2 = _file_bytes(inputargs["infile"].replace("1.f", "2.f"), opener)
         box = {}
-        th = threading.Thread(target=lambda: box.__setitem__("ix2", _lib.fastq_index(data2)))
+
+        def second():
+            try:
+                box["data2"] = _file_bytes(inputargs["infile"].replace("1.f", "2.f"), opener)
+                box["ix2"] = _lib.fastq_index(box["data2"])
+            except BaseException as e:      # raised again in the calling thread
+                box["error"] = e
+        th = threading.Thread(target=second)
         th.start()
-        ix1 = _lib.fastq_index(data1)
-        th.join()
-        ix2 = box.get("ix2")
+        try:
+            data1 = _file_bytes(inputargs["infile"], opener)
+            ix1 = _lib.fastq_index(data1)
+        finally:
+            th.join()
+        if "error" in box:
+            raise box["error"]
+        data2, ix2 = box["data2"], box.get("ix2")
         if ix1 is None or ix2 is None:
             return None
         n = min(len(ix1["seq_off"]), len(ix2["seq_off"]))            # zip() stops at the shorter file
@@ -206,6 +216,7 @@ def load_pairs_native(inputargs, opener):
         batch.bcq = TextColumn(data2, *_clip(two["qual_off"], two["qual_len"], 0, bclength))
         batch.v_tail = TextColumn(data2, *_clip(two["seq_off"], two["seq_len"], bclength, bclength + 31)) if sampling else []
     else:
+        data1 = _file_bytes(inputargs["infile"], opener)
         ix1 = _lib.fastq_index(data1)
         if ix1 is None:
             return None
