@@ -449,6 +449,17 @@ def main():
             res_a, cnt_a = ctx.decombine_ascii(text.a, None, None, True, uniform_len=READ_LEN, pinned=True)
         e_ms = (time.perf_counter() - e0) * 1e3
         assert np.array_equal(res_a, res0) and np.array_equal(cnt_a, cnt0)
+        host_chunks, device_chunks = ctx.last_pack_shares()
+        # the same with every chunk packed by the device (the whole text crosses the link): what the ceiling below bounds
+        os.environ["DCB_HOST_SHARE"] = "0"
+        ctx.decombine_ascii(text.a, None, None, True, uniform_len=READ_LEN, pinned=True)
+        barrier()
+        e0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            res_d, cnt_d = ctx.decombine_ascii(text.a, None, None, True, uniform_len=READ_LEN, pinned=True)
+        ed_ms = (time.perf_counter() - e0) * 1e3
+        del os.environ["DCB_HOST_SHARE"]
+        assert np.array_equal(res_d, res0) and np.array_equal(cnt_d, cnt0)
         # ---- the ceiling e2e runs against: page-locked host -> device copies of the same text, all ranks at once --------
         dev_buf = torch.empty(len(text.a), dtype=torch.uint8, device="cuda")
         host_t = torch.from_numpy(text.a)          # a view of the page-locked buffer
@@ -475,9 +486,9 @@ def main():
         packed = None
 
     if world > 1:
-        t = torch.tensor([ms_total, e_ms, ep_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms_total, e_ms, ep_ms, ed_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e_ms, ep_ms = float(t[0]), float(t[1]), float(t[2])
+        ms_total, e_ms, ep_ms, ed_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
         t = torch.tensor([h2d_gbps], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         h2d_gbps = float(t[0])
@@ -490,6 +501,7 @@ def main():
     if rank == 0:
         value = world * n * args.steps / (ms_total / 1e3)
         e2e = world * n * e2e_steps / (e_ms / 1e3)
+        e2e_dev = world * n * e2e_steps / (ed_ms / 1e3)
         bytes_per_read = (READ_LEN + 3) // 4 + 16
         exact_ms = kms[0] / max(1, klaunch[0])
         general_ms = kms[1] / max(1, klaunch[1])
@@ -518,10 +530,16 @@ def main():
                          "traffic": traffic, "traffic_source": "profiles/traffic.json (one ncu --set full capture of this kernel, per read) x reads",
                          "kernel": exact_name, "bytes_per_read": bytes_per_read,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650"},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(n * READ_LEN),
+            "e2e": {"value": e2e, "unit": UNIT,
+                    "h2d_bytes_per_step": int(n * (READ_LEN * device_chunks + packed.slot_words * 4 * host_chunks) / max(1, host_chunks + device_chunks)),
                     "d2h_bytes_per_step": int(n * 16 + 8 * _lib.NCOUNTERS), "steps": e2e_steps,
-                    "call": "dcb_decombine_ascii: ASCII reads in page-locked host memory in (the reference arm's input), packed on "
-                            "the device, result records in host memory out",
+                    "call": "dcb_decombine_ascii: ASCII reads in page-locked host memory in (the reference arm's input), result records in "
+                            "host memory out; chunks of clean reads are packed by the device (the text crosses the link) or, while the "
+                            "copy engine is busy, by the host threads (a quarter of the bytes crosses) -- one rank per host only",
+                    "chunks_packed_by": {"host_threads": host_chunks, "device": device_chunks, "rank": 0},
+                    "device_packed_only": {"value": e2e_dev, "unit": UNIT, "h2d_bytes_per_step": int(n * READ_LEN),
+                                           "how": "DCB_HOST_SHARE=0: the whole text crosses the link",
+                                           "frac_of_h2d_ceiling": e2e_dev / (h2d_gbps * 1e9 / READ_LEN * world)},
                     "h2d_ceiling": {"GBps_per_gpu": h2d_gbps, "GBps_all_gpus": h2d_gbps * world,
                                     "how": "torch copy_ of the same page-locked text to the device, all ranks at once, slowest rank",
                                     "reads_per_s_at_ceiling": h2d_gbps * 1e9 / READ_LEN * world,

@@ -95,6 +95,9 @@ def lib():
     L.dcb_buffer_free.restype = None
     L.dcb_pack_reads.argtypes = [vp, vp, vp, u64, i32, i32, ctypes.POINTER(ctypes.POINTER(CPacked))]
     L.dcb_packed_free.argtypes = [ctypes.POINTER(CPacked)]
+    L.dcb_pack_words.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32,
+                                 ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    L.dcb_pack_words.restype = ctypes.c_int
     L.dcb_unpack_read.argtypes = [ctypes.POINTER(CPacked), u64, ctypes.c_char_p, u32]
     L.dcb_ctx_create.restype = vp
     L.dcb_ctx_create.argtypes = [i32, vp, vp, ctypes.POINTER(CParams)]
@@ -104,6 +107,8 @@ def lib():
     L.dcb_decombine_ascii.argtypes = [vp, vp, vp, vp, u64, u32, i32, vp, vp]
     L.dcb_pack_device.argtypes = [vp, vp, vp, vp, u64, u32, i32, ctypes.POINTER(ctypes.POINTER(CPacked))]
     L.dcb_pack_device_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
+    L.dcb_last_pack_shares.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]
+    L.dcb_last_pack_shares.restype = ctypes.c_int
     L.dcb_pinned_alloc.restype = vp
     L.dcb_pinned_alloc.argtypes = [ctypes.c_size_t]
     L.dcb_pinned_free.argtypes = [vp]
@@ -317,6 +322,25 @@ def format_rows(res, packed_revcomp, columns, sep, n_threads=None):
     return NativeText(out.value, nbytes.value), int(nrows.value)
 
 
+def pack_words(buf, off, length, revcomp, slot_words, uniform_len=0, first=0, count=None, n_threads=None, out=None):
+    """dcb_pack_words: reads of nothing but A / C / G / T packed by the host threads into a uint32 array of
+    count * slot_words words.  -> (words, clean); clean False: another symbol turned up, the words are void."""
+    buf = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf
+    if off is not None:
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+    if length is not None:
+        length = np.ascontiguousarray(length, dtype=np.uint32)
+    n = len(off) if off is not None else (len(buf) // uniform_len if uniform_len else 0)
+    count = n - first if count is None else count
+    words = out if out is not None else np.empty(count * slot_words, dtype=np.uint32)
+    clean = ctypes.c_int(0)
+    _check(lib().dcb_pack_words(buf.ctypes.data, off.ctypes.data if off is not None else None,
+                                length.ctypes.data if length is not None else None, int(first), int(count), int(uniform_len),
+                                int(bool(revcomp)), int(slot_words), words.ctypes.data,
+                                n_threads or min(32, os.cpu_count() or 1), ctypes.byref(clean)), "dcb_pack_words")
+    return words, bool(clean.value)
+
+
 class NativeText:
     """A text buffer malloc'ed by the library (dcb_format_rows), handed on WITHOUT a copy: `.a` is a uint8 array over it,
     bytes(obj) / obj.tobytes() copy, the buffer is freed with the object."""
@@ -501,6 +525,12 @@ class Context:
         off = None if off is None else np.ascontiguousarray(off, dtype=np.uint64)
         length = None if (length is None or uniform_len) else np.ascontiguousarray(length, dtype=np.uint32)
         return buf, off, length, n
+
+    def last_pack_shares(self):
+        """(chunks packed by the host threads, chunks packed by the device) of the last decombine_ascii call."""
+        a, b = ctypes.c_uint32(0), ctypes.c_uint32(0)
+        _check(lib().dcb_last_pack_shares(self._h, ctypes.byref(a), ctypes.byref(b)), "dcb_last_pack_shares")
+        return int(a.value), int(b.value)
 
     def decombine_ascii(self, buf, off, length, revcomp, uniform_len=0, counters=None, pinned=False):
         """dcb_decombine_ascii: ASCII reads in host memory in (read i = buf[off[i] : off[i] + length[i]]; off None = contiguous

@@ -25,6 +25,8 @@ bool dcb_build_seed_index(const std::vector<std::string>* gene_v, const std::vec
 bool dcb_build_half_index(const dcb_tagset* v, const dcb_tagset* j, std::vector<uint32_t>& out);
 
 extern "C" int dcb_packed_alloc(uint64_t n, uint32_t slot_words, uint32_t n_exc, dcb_packed** out);
+extern "C" int dcb_pack_words(const char* ascii, const uint64_t* off, const uint32_t* len, uint64_t first, uint64_t count, uint32_t uniform_len,
+                              int revcomp, uint32_t slot_words, uint32_t* words, int n_threads, int* clean);
 
 #if defined(__GNUC__)
 __attribute__((format(printf, 1, 2)))

@@ -1097,6 +1097,13 @@ struct dcb_ctx {
     char* stage[2] = {nullptr, nullptr};
     size_t stage_cap[2] = {0, 0};
     cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+    // the host's share of dcb_decombine_ascii: chunks of clean reads packed by the host threads (dcb_pack_words) into
+    // page-locked buffers while the copy engine is busy with the text of a chunk the device packs
+    uint32_t* hwords[2] = {nullptr, nullptr};
+    size_t hwords_cap[2] = {0, 0};
+    cudaEvent_t ev_hw[2] = {nullptr, nullptr}, ev_acopy = nullptr;
+    bool acopy_pending = false;
+    uint32_t host_chunks = 0, device_chunks = 0;   // of the last dcb_decombine_ascii call
     double pack_ms = 0;            // device time of the pack kernels of the last dcb_pack_device call (CUDA events)
     int vgen_words = 0, jgen_words = 0, vcore_words = 0, jcore_words = 0, vidx_words = 0, jidx_words = 0, uidx_words = 0;
     DevBuf words, lens, flags, exc_read, exc_pos, exc_kind, exc_index, results, queue;
@@ -1296,7 +1303,9 @@ dcb_ctx* dcb_ctx_create(int device, const dcb_tagset* v, const dcb_tagset* j, co
     if (cudaMalloc((void**)&c->d_exc_total, 16) != cudaSuccess) return fail("cudaMalloc");
     for (int i = 0; i < 2; i++)
         if (cudaEventCreateWithFlags(&c->ev_scan[i], cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&c->ev_stage[i], cudaEventDisableTiming) != cudaSuccess) return fail("cudaEventCreate");
+            cudaEventCreateWithFlags(&c->ev_stage[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_hw[i], cudaEventDisableTiming) != cudaSuccess) return fail("cudaEventCreate");
+    if (cudaEventCreateWithFlags(&c->ev_acopy, cudaEventDisableTiming) != cudaSuccess) return fail("cudaEventCreate");
     return c;
 }
 
@@ -1318,7 +1327,10 @@ void dcb_ctx_destroy(dcb_ctx* c) {
         if (c->ev_scan[i]) cudaEventDestroy(c->ev_scan[i]);
         if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]);
         if (c->stage[i]) cudaFreeHost(c->stage[i]);
+        if (c->ev_hw[i]) cudaEventDestroy(c->ev_hw[i]);
+        if (c->hwords[i]) cudaFreeHost(c->hwords[i]);
     }
+    if (c->ev_acopy) cudaEventDestroy(c->ev_acopy);
     c->group_count.release();
     cudaFree(c->d_exc_total);
     delete c;
@@ -1630,6 +1642,56 @@ static int ascii_geometry(const uint32_t* len, uint64_t n, uint32_t uniform_len,
 // Pack reads [first, first + count) on stream s (buffers of parity `par`): text bytes and offsets / lengths up, the pack
 // kernel, the scan that continues the exception index from the chunks before (ordered across the two streams by
 // events), the exception entries.  The packed data lands in the context's batch buffers at the reads' global positions.
+// Host threads this process may use for packing / gathering: all of them, or its part when several ranks share the host
+// (torchrun sets LOCAL_WORLD_SIZE).
+static int local_world() {
+    const char* e = std::getenv("LOCAL_WORLD_SIZE");
+    const int w = e ? std::atoi(e) : 1;
+    return w < 1 ? 1 : w;
+}
+static int host_threads() {
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int t = (int)(hw ? hw : 4u) / local_world();
+    return std::max(1, std::min(32, t));
+}
+
+// The host's share: the chunk's reads packed by the host threads into a page-locked buffer and copied to their slots --
+// a quarter of the text's bytes over the link.  Only for chunks of nothing but A / C / G / T (no exception list to merge:
+// the chunk's groups take part in the running exception index with a count of zero).  1: done, 0: not clean (the caller
+// lets the device pack the chunk), < 0: error.
+static int pack_chunk_host(dcb_ctx* c, cudaStream_t s, int par, const char* ascii, const uint64_t* off, const uint32_t* len,
+                           uint32_t uniform_len, int revcomp, uint32_t first, uint32_t count, int chunk_no) {
+    const uint32_t sw = c->batch.slot_words;
+    const size_t wbytes = (size_t)count * sw * 4, lbytes = len ? (((size_t)count * 2 + 255) & ~(size_t)255) : 0;
+    if (cudaEventSynchronize(c->ev_hw[par]) != cudaSuccess) { dcb_set_error("cudaEventSynchronize failed"); return DCB_ENOGPU; }
+    if (c->hwords_cap[par] < wbytes + lbytes) {
+        if (c->hwords[par]) cudaFreeHost(c->hwords[par]);
+        c->hwords[par] = nullptr; c->hwords_cap[par] = 0;
+        const size_t want = wbytes + lbytes + (wbytes + lbytes) / 8 + 4096;
+        if (cudaHostAlloc((void**)&c->hwords[par], want, cudaHostAllocDefault) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+        c->hwords_cap[par] = want;
+    }
+    int clean = 0;
+    int rc = dcb_pack_words(ascii, off, len, first, count, uniform_len, revcomp, sw, c->hwords[par], host_threads(), &clean);
+    if (rc) return rc;
+    if (!clean) return 0;
+    CUDA_TRY(cudaMemcpyAsync((uint32_t*)c->words.p + (size_t)first * sw, c->hwords[par], wbytes, cudaMemcpyHostToDevice, s));
+    if (len) {
+        uint16_t* hl = reinterpret_cast<uint16_t*>(reinterpret_cast<char*>(c->hwords[par]) + wbytes);
+        for (uint32_t i = 0; i < count; i++) hl[i] = (uint16_t)len[first + i];
+        CUDA_TRY(cudaMemcpyAsync((uint16_t*)c->lens.p + first, hl, (size_t)count * 2, cudaMemcpyHostToDevice, s));
+    }
+    CUDA_TRY(cudaEventRecord(c->ev_hw[par], s));
+    const uint32_t groups = (count + 31) / 32;
+    CUDA_TRY(cudaMemsetAsync((uint32_t*)c->flags.p + (first >> 5), 0, (size_t)groups * 4, s));
+    CUDA_TRY(cudaMemsetAsync((uint32_t*)c->group_count.p + (first >> 5), 0, (size_t)groups * 4, s));
+    if (chunk_no > 0) CUDA_TRY(cudaStreamWaitEvent(s, c->ev_scan[(chunk_no - 1) & 1], 0));
+    dcb_pack_scan_kernel<<<1, 1024, 0, s>>>((const uint32_t*)c->group_count.p, first >> 5, groups, (uint32_t*)c->exc_index.p, c->d_exc_total);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(c->ev_scan[chunk_no & 1], s));
+    return 1;
+}
+
 static int pack_chunk(dcb_ctx* c, cudaStream_t s, int par, const char* ascii, const uint64_t* off, const uint32_t* len,
                       uint32_t uniform_len, int revcomp, uint32_t first, uint32_t count, size_t exc_cap, int chunk_no,
                       bool staged = false) {
@@ -1665,8 +1727,7 @@ static int pack_chunk(dcb_ctx* c, cudaStream_t s, int par, const char* ascii, co
         uint64_t* loc = reinterpret_cast<uint64_t*>(c->stage[par]);
         char* dst = c->stage[par] + head;
         if (vary) { uint64_t at = 0; for (uint32_t i = 0; i < count; i++) { loc[i] = at; at += len[first + i]; } }
-        const unsigned hw = std::thread::hardware_concurrency();
-        const int nt = count < 8192 ? 1 : (int)std::min<unsigned>(16u, hw ? hw : 4u);
+        const int nt = count < 8192 ? 1 : std::min(16, host_threads());
         auto work = [&](uint32_t a, uint32_t b) {
             for (uint32_t i = a; i < b; i++) {
                 const uint32_t Li = vary ? len[first + i] : L;
@@ -1692,6 +1753,8 @@ static int pack_chunk(dcb_ctx* c, cudaStream_t s, int par, const char* ascii, co
     } else {
         if ((rc = c->text[par].ensure(hi - lo + 64))) return rc;
         CUDA_TRY(cudaMemcpyAsync(c->text[par].p, ascii + lo, hi - lo, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaEventRecord(c->ev_acopy, s));
+        c->acopy_pending = true;
         src.text = (const unsigned char*)c->text[par].p; src.text_lo = lo;
         if (!contiguous) {
             if ((rc = c->roff[par].ensure((size_t)count * 8 + 16))) return rc;
@@ -1768,11 +1831,41 @@ int dcb_decombine_ascii(dcb_ctx* c, const char* ascii, const uint64_t* off, cons
     }
     uint32_t chunk = std::max<uint32_t>(staged ? kChunkReads / 4 : kChunkReads, (uint32_t)((n + kMaxChunks - 1) / kMaxChunks));
     chunk = (chunk + 1023u) & ~1023u;
+    // Who packs a chunk: the device (the text goes over the link, 4 bytes per packed byte) or the host threads.  Text in
+    // pageable memory would have to be gathered into page-locked staging by the host threads anyway: they pack it instead.
+    // Page-locked text: the host packs a chunk whenever the copy engine is still busy with the text of the last chunk given
+    // to the device, so the two shares balance themselves -- when this process has the host to itself: with several ranks on
+    // one host (LOCAL_WORLD_SIZE > 1) the link is shared too and the host threads are few, so the device packs.
+    // DCB_HOST_SHARE=0 / 1 / 2 / 3: never / when the copy engine is busy / always / pageable text only (tests, measurements).
+    int host_share = local_world() == 1 ? 1 : 3;
+    if (const char* e = std::getenv("DCB_HOST_SHARE")) host_share = std::atoi(e);
+    c->host_chunks = c->device_chunks = 0;
+    c->acopy_pending = false;
+    bool host_ok = host_share != 0;
     int k = 0;
     for (uint64_t first = 0; first < n; first += chunk, k++) {
         const uint32_t count = (uint32_t)std::min<uint64_t>(chunk, n - first);
         cudaStream_t s = st[k & 1];
-        if ((rc = pack_chunk(c, s, k & 1, ascii, off, lens, uniform_len, revcomp, (uint32_t)first, count, exc_cap, k, staged))) return rc;
+        bool by_host = false;
+        if (host_ok) {
+            bool want = staged || host_share == 2;
+            if (!want && host_share == 1 && c->acopy_pending) {
+                const cudaError_t q = cudaEventQuery(c->ev_acopy);
+                if (q == cudaErrorNotReady) want = true;
+                else if (q != cudaSuccess) { dcb_set_error("cudaEventQuery failed: %s", cudaGetErrorString(q)); return DCB_ENOGPU; }
+            }
+            if (want) {
+                rc = pack_chunk_host(c, s, k & 1, ascii, off, lens, uniform_len, revcomp, (uint32_t)first, count, k);
+                if (rc < 0) return rc;
+                by_host = rc == 1;
+                if (!by_host) host_ok = false;          // symbols beyond A / C / G / T (or no AVX2): the device packs the rest
+            }
+        }
+        if (by_host) c->host_chunks++;
+        else {
+            if ((rc = pack_chunk(c, s, k & 1, ascii, off, lens, uniform_len, revcomp, (uint32_t)first, count, exc_cap, k, staged))) return rc;
+            c->device_chunks++;
+        }
         if ((rc = launch_range(c, s, (uint32_t)first, count, k, false))) return rc;
         if (out)
             CUDA_TRY(cudaMemcpyAsync(out + first, (dcb_result*)c->results.p + first, (size_t)count * sizeof(dcb_result),
@@ -1885,6 +1978,12 @@ int dcb_last_general(dcb_ctx* c, uint64_t* n) {
     if (c->params.force_general == 1) { *n = c->batch.n_reads; return DCB_OK; }
     return sum_queue_counts(c, c->half_fn ? 1 : 0, n);
 }
+int dcb_last_pack_shares(dcb_ctx* c, uint32_t* host_chunks, uint32_t* device_chunks) {
+    if (!c || !host_chunks || !device_chunks) { dcb_set_error("dcb_last_pack_shares: null argument"); return DCB_EINVAL; }
+    *host_chunks = c->host_chunks; *device_chunks = c->device_chunks;
+    return DCB_OK;
+}
+
 const char* dcb_halftag_kernel_name(const dcb_ctx* c) {
     return (c && c->have_batch && c->half_fn) ? "dcb_halftag_kernel" : "";
 }

@@ -14,6 +14,9 @@
 #include <cstring>
 #include <thread>
 #include <vector>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 namespace {
 
@@ -49,6 +52,77 @@ void* host_alloc(Owner* o, size_t bytes) {
 }
 
 struct Exc { uint32_t read; uint16_t pos; uint8_t kind; };
+
+#if defined(__x86_64__)
+const bool kAvx2 = __builtin_cpu_supports("avx2");
+// 32 bases -> 64 packed bits.  v: the 32 symbols in output order (already reversed for the reverse strand).  `bad` collects
+// the symbols that are not A / C / G / T (upper case; everything else is the byte loop's business).
+__attribute__((target("avx2"))) inline uint64_t pack32_avx2(__m256i v, bool comp, __m256i& bad) {
+    // by low nibble: 'A' 0x41 -> 1, 'C' 0x43 -> 3, 'T' 0x54 -> 4, 'G' 0x47 -> 7
+    const __m256i self = _mm256_setr_epi8(-1, 'A', -1, 'C', 'T', -1, -1, 'G', -1, -1, -1, -1, -1, -1, -1, -1,
+                                          -1, 'A', -1, 'C', 'T', -1, -1, 'G', -1, -1, -1, -1, -1, -1, -1, -1);
+    const __m256i low = _mm256_set1_epi8(0x0F), three = _mm256_set1_epi8(3);
+    const __m256i nib = _mm256_and_si256(v, low);
+    // an ASCII symbol whose low nibble names one of the four and that IS that one; bytes >= 0x80 shuffle to 0 and differ
+    bad = _mm256_or_si256(bad, _mm256_xor_si256(_mm256_cmpeq_epi8(_mm256_shuffle_epi8(self, nib), v), _mm256_set1_epi8(-1)));
+    // code = ((c >> 1) ^ (c >> 2)) & 3 maps A, C, G, T -> 0, 1, 2, 3 (16-bit shifts: the bits that cross a byte are masked off)
+    __m256i c = _mm256_and_si256(_mm256_xor_si256(_mm256_srli_epi16(v, 1), _mm256_srli_epi16(v, 2)), three);
+    if (comp) c = _mm256_xor_si256(c, three);
+    // four codes per byte: pairs (b0 + 4 b1) as 16-bit lanes, then pairs of those (w0 + 16 w1) as 32-bit lanes
+    const __m256i p16 = _mm256_maddubs_epi16(c, _mm256_set1_epi16(0x0401));
+    const __m256i p32 = _mm256_madd_epi16(p16, _mm256_set1_epi32(0x00100001));
+    // the low byte of every 32-bit lane, four per 128-bit half
+    const __m256i pick = _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+                                          0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+    const __m256i q = _mm256_shuffle_epi8(p32, pick);
+    return (uint64_t)(uint32_t)_mm256_extract_epi32(q, 0) | ((uint64_t)(uint32_t)_mm256_extract_epi32(q, 4) << 32);
+}
+// One read of A / C / G / T into its slot (all sw words written).  false: another symbol turned up (the slot's content is
+// then void and the caller packs the read with the byte loop).
+__attribute__((target("avx2"))) inline bool pack_read_avx2(const unsigned char* s, uint32_t L, bool revcomp, uint32_t* w, size_t sw) {
+    const __m256i flip = _mm256_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
+    __m256i bad = _mm256_setzero_si256();
+    uint32_t i = 0;
+    for (; i + 32 <= L; i += 32) {
+        __m256i v;
+        if (revcomp) {   // output bases i .. i+31 are the input bytes L-32-i .. L-1-i backwards
+            v = _mm256_loadu_si256((const __m256i*)(s + (L - 32 - i)));
+            v = _mm256_permute4x64_epi64(_mm256_shuffle_epi8(v, flip), 0x4E);
+        } else {
+            v = _mm256_loadu_si256((const __m256i*)(s + i));
+        }
+        const uint64_t bits = pack32_avx2(v, revcomp, bad);
+        std::memcpy(w + (i >> 4), &bits, 8);
+    }
+    if (i < L && L >= 32) {
+        // the last, partial block: the 32 symbols that END the output (they overlap the block before, whose bits are the
+        // same, so they are OR-ed in), shifted to their place
+        __m256i v;
+        if (revcomp) v = _mm256_permute4x64_epi64(_mm256_shuffle_epi8(_mm256_loadu_si256((const __m256i*)s), flip), 0x4E);
+        else v = _mm256_loadu_si256((const __m256i*)(s + (L - 32)));
+        const uint64_t bits = pack32_avx2(v, revcomp, bad);
+        const uint32_t b0 = L - 32, u = b0 >> 5, sh = 2 * (b0 & 31);
+        uint64_t lo;
+        std::memcpy(&lo, w + 2 * u, 8);
+        lo |= bits << sh;
+        std::memcpy(w + 2 * u, &lo, 8);
+        if (sh) { const uint64_t hi = bits >> (64 - sh); std::memcpy(w + 2 * u + 2, &hi, 8); }
+        i = 32 * (u + (sh ? 2 : 1));
+    } else if (i < L) {  // a read of fewer than 32 symbols: through a buffer padded with 'A' (code 0; 'T' on the reverse strand, 3 ^ 3)
+        alignas(32) unsigned char tmp[32];
+        const uint32_t rem = L - i;
+        std::memset(tmp, revcomp ? 'T' : 'A', 32);
+        if (revcomp) for (uint32_t k = 0; k < rem; k++) tmp[k] = s[rem - 1 - k];
+        else std::memcpy(tmp, s + i, rem);
+        const uint64_t bits = pack32_avx2(_mm256_load_si256((const __m256i*)tmp), revcomp, bad);
+        if ((i >> 4) + 1 < sw) std::memcpy(w + (i >> 4), &bits, 8);
+        else { const uint32_t lo = (uint32_t)bits; std::memcpy(w + (i >> 4), &lo, 4); }
+        i += 32;
+    }
+    for (size_t k = (size_t)(i >> 4); k < sw; k++) w[k] = 0;
+    return _mm256_testz_si256(bad, bad) != 0;
+}
+#endif
 
 }  // namespace
 
@@ -97,6 +171,9 @@ int dcb_pack_reads(const char* ascii, const uint64_t* off, const uint32_t* len, 
             bool flagged = false;
             uint32_t acc = 0;
             uint32_t i = 0;
+#if defined(__x86_64__)
+            if (kAvx2 && pack_read_avx2(s, L, revcomp != 0, w, sw)) continue;     // nothing but A / C / G / T: done
+#endif
             // eight bases at a time while they are all A/C/G/T (SWAR): code = ((c >> 1) ^ (c >> 2)) & 3 maps
             // A,C,G,T -> 0,1,2,3; the reverse complement reads the bytes from the end (byte swap) and flips the code.
             // Any other symbol in a group hands the rest of the read to the byte loop below.
@@ -157,6 +234,44 @@ int dcb_pack_reads(const char* ascii, const uint64_t* off, const uint32_t* len, 
     for (auto& e : excs)
         for (auto& x : e) { P->exc_read[k] = x.read; P->exc_pos[k] = x.pos; P->exc_kind[k] = x.kind; k++; }
     *out = P;
+    return DCB_OK;
+}
+
+// Reads of nothing but A / C / G / T, packed into the caller's buffer (count * slot_words words; page-locked when it is the
+// staging buffer of dcb_decombine_ascii).  *clean = 0 when another symbol turned up or the CPU has no AVX2: the buffer's
+// content is then void and the caller takes another path (the device packer, dcb_pack_reads).
+int dcb_pack_words(const char* ascii, const uint64_t* off, const uint32_t* len, uint64_t first, uint64_t count, uint32_t uniform_len,
+                   int revcomp, uint32_t slot_words, uint32_t* words, int n_threads, int* clean) {
+    if (!clean || (count && (!ascii || !words)) || (!off && !uniform_len) || (!len && !uniform_len)) {
+        dcb_set_error("dcb_pack_words: null argument");
+        return DCB_EINVAL;
+    }
+    *clean = 0;
+#if defined(__x86_64__)
+    if (!kAvx2) return DCB_OK;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 64) n_threads = 64;
+    if (count < 4096) n_threads = 1;
+    std::vector<int> dirty(n_threads, 0);
+    auto work = [&](int t) {
+        const uint64_t lo = count * (uint64_t)t / n_threads, hi = count * (uint64_t)(t + 1) / n_threads;
+        for (uint64_t i = lo; i < hi; i++) {
+            const uint64_t r = first + i;
+            const uint32_t L = uniform_len ? uniform_len : len[r];
+            const unsigned char* s = (const unsigned char*)ascii + (off ? off[r] : r * (uint64_t)uniform_len);
+            if ((L + 15) / 16 > slot_words || !pack_read_avx2(s, L, revcomp != 0, words + i * slot_words, slot_words)) { dirty[t] = 1; return; }
+        }
+    };
+    if (n_threads == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; t++) th.emplace_back(work, t);
+        for (auto& t : th) t.join();
+    }
+    int any = 0;
+    for (int d : dirty) any |= d;
+    *clean = !any;
+#endif
     return DCB_OK;
 }
 

@@ -127,6 +127,11 @@ typedef struct dcb_packed {
 int dcb_pack_reads(const char* ascii, const uint64_t* off, const uint32_t* len, uint64_t n, int revcomp,
                    int n_threads, dcb_packed** out);
 void dcb_packed_free(dcb_packed*);
+/* The host's share of dcb_decombine_ascii: reads [first, first + count) of nothing but A / C / G / T packed (AVX2, n_threads
+ * host threads) into the caller's buffer of count * slot_words words, in the layout of dcb_packed.words.  *clean = 0 when
+ * another symbol turned up (or the CPU has no AVX2): the buffer is then void.  off == NULL: contiguous reads of uniform_len. */
+int dcb_pack_words(const char* ascii, const uint64_t* off, const uint32_t* len, uint64_t first, uint64_t count, uint32_t uniform_len,
+                   int revcomp, uint32_t slot_words, uint32_t* words, int n_threads, int* clean);
 /* ---------------------------------------------------------------------------------------------
  * FASTQ ingest (host): the record index of a FASTQ text held in memory.  Replaces the reference's
  * parser readfq (decombine.py:228-265) for files in the strict layout (four lines per record, '\n'
@@ -214,7 +219,8 @@ int dcb_decombine_batch(dcb_ctx*, const dcb_packed* reads, dcb_result* out, uint
  * to HBM in chunks and packed there (csrc/pack_device.cuh: bit-identical to dcb_pack_reads); no packed copy is made on
  * the host.  Read i is ascii[off[i] .. off[i] + len[i]); offsets must not decrease inside the batch (FASTQ order).
  * off == NULL: the reads are contiguous, read i at i * uniform_len.  uniform_len != 0: every read has that length and
- * len is ignored.  With page-locked text (dcb_pinned_alloc) the step is bound by the host->device copy of the text. */
+ * len is ignored.  Chunks of nothing but A / C / G / T are shared between the device packer and the host threads
+ * (dcb_pack_words), whichever is free; reads with other symbols are packed by the device. */
 int dcb_decombine_ascii(dcb_ctx*, const char* ascii, const uint64_t* off, const uint32_t* len, uint64_t n, uint32_t uniform_len,
                         int revcomp, dcb_result* out, uint64_t* counters);
 /* The device packer alone: its output copied back into a host dcb_packed (free with dcb_packed_free); tests compare it
@@ -222,6 +228,10 @@ int dcb_decombine_ascii(dcb_ctx*, const char* ascii, const uint64_t* off, const 
 int dcb_pack_device(dcb_ctx*, const char* ascii, const uint64_t* off, const uint32_t* len, uint64_t n, uint32_t uniform_len,
                     int revcomp, dcb_packed** out);
 int dcb_pack_device_ms(dcb_ctx*, double* ms);
+/* How the chunks of the last dcb_decombine_ascii call were packed: by the host threads (clean reads, dcb_pack_words: a
+ * quarter of the text's bytes cross the link) or by the device (the text itself crosses the link).  The environment
+ * variable DCB_HOST_SHARE = 0 / 2 forces never / always (default: the host packs while the copy engine is busy). */
+int dcb_last_pack_shares(dcb_ctx*, uint32_t* host_chunks, uint32_t* device_chunks);
 
 /* Page-locked host memory for result records (so that the device->host copies of dcb_decombine_batch run
  * asynchronously, overlapped with the uploads); NULL when no GPU is usable. */

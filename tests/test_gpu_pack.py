@@ -118,3 +118,44 @@ def test_decombine_ascii_ragged_and_empty():
     got, cnt = ctx.decombine_ascii(np.zeros(8, dtype=np.uint8), np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=np.uint32), True)
     assert len(got) == 0 and not cnt.any()
     ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("share", ["0", "1", "2", "3"])
+def test_decombine_ascii_host_share_changes_nothing(share, monkeypatch):
+    """dcb_decombine_ascii shares the chunks of clean reads between the device packer and the host threads
+    (DCB_HOST_SHARE: 0 never, 1 while the copy engine is busy, 2 always, 3 pageable text only): the records and counters
+    are those of the host-packed batch whichever packs; a chunk with another symbol goes back to the device."""
+    monkeypatch.setenv("DCB_HOST_SHARE", share)
+    info = tags.load("human", "extended", "b")
+    vt, jt = info.tables()
+    ctx = _lib.Context(vt, jt, device=0)
+    n, L = 2_300_000, 250                                   # three chunks of the page-locked path
+    syn = _lib.Synth([(info.v_regions, info.j_regions)], 20260007, L, 0, 0.0, 0.0, 0.0)
+    r1, _ = syn.reads(0, n)
+    off = np.arange(n, dtype=np.uint64) * L
+    ln = np.full(n, L, dtype=np.uint32)
+    packed = _lib.pack_arrays(r1, off, ln, revcomp=True)
+    want, wcnt = ctx.decombine(packed)
+    packed.free()
+    text = _lib.PinnedBytes(r1)
+    for buf in (text.a, r1):                                # page-locked and pageable text
+        got, cnt = ctx.decombine_ascii(buf, None, None, True, uniform_len=L)
+        assert np.array_equal(got, want) and np.array_equal(cnt, wcnt)
+        host, dev = ctx.last_pack_shares()
+        assert host + dev >= 3
+        if share == "0":
+            assert host == 0
+        if share == "2":
+            assert dev == 0
+    text.free()
+    # ragged reads, and an N in the second chunk: from there on the device packs
+    r2, off2, ln2 = synth_batch(info, 1_200_000, 250, 0.0, 0.0, 0.0, seed=5)
+    r2 = r2.copy()
+    r2[int(off2[1_100_000]) + 17] = ord("N")
+    packed = _lib.pack_arrays(r2, off2, ln2, revcomp=True)
+    want, wcnt = ctx.decombine(packed)
+    packed.free()
+    got, cnt = ctx.decombine_ascii(r2, off2, ln2, True)
+    assert np.array_equal(got, want) and np.array_equal(cnt, wcnt)
+    ctx.close()
