@@ -1829,7 +1829,7 @@ int dcb_decombine_ascii(dcb_ctx* c, const char* ascii, const uint64_t* off, cons
         if (cudaPointerGetAttributes(&attr, ascii) != cudaSuccess) { (void)cudaGetLastError(); staged = true; }
         else staged = attr.type == cudaMemoryTypeUnregistered;
     }
-    uint32_t chunk = std::max<uint32_t>(staged ? kChunkReads / 4 : kChunkReads, (uint32_t)((n + kMaxChunks - 1) / kMaxChunks));
+    uint32_t chunk = std::max<uint32_t>(staged ? kChunkReads / 2 : kChunkReads, (uint32_t)((n + kMaxChunks - 1) / kMaxChunks));
     chunk = (chunk + 1023u) & ~1023u;
     // Who packs a chunk: the device (the text goes over the link, 4 bytes per packed byte) or the host threads.  Text in
     // pageable memory would have to be gathered into page-locked staging by the host threads anyway: they pack it instead.

@@ -189,22 +189,33 @@ def decombine_batch(batch: fastq.ReadBatch, inputargs):
         for part in (np.nonzero(lens <= FAST_READ_LEN)[0], np.nonzero(lens > FAST_READ_LEN)[0]):
             sub = fastq.ReadBatch()
             sub.buf, sub.off, sub.len = batch.buf, off[part], np.ascontiguousarray(lens[part], dtype=np.uint32)
-            res[part] = _decombine_columns(ctx, sub.buf, sub.off, sub.len, pack_rc)
+            res[part] = _decombine_columns(ctx, sub.buf, sub.off, sub.len, pack_rc, True)
         return res
-    return _decombine_columns(ctx, batch.buf, off, batch.len, pack_rc)
+    # the `decombine` command formats the rows and lets go of the records: it may read them where the device wrote them
+    return _decombine_columns(ctx, batch.buf, off, batch.len, pack_rc, bool(inputargs.get("rows_as_text")))
 
 
 MAX_READ_LEN = 4096      # DCB_MAX_READ_LEN of csrc/dcb_tables.h
 FAST_READ_LEN = 320      # widest slot of the flat exact-tag kernel and the half-tag kernel (20 words)
 
 
-def _decombine_columns(ctx, buf, off, length, pack_rc):
-    """(offset, length) columns into a text buffer -> dcb_result array; counters added to `counts`."""
+def _decombine_columns(ctx, buf, off, length, pack_rc, transient=False):
+    """(offset, length) columns into a text buffer -> dcb_result array; counters added to `counts`.
+
+    The records arrive in a page-locked buffer of the context (copies into pageable memory would stall the chunk loop);
+    transient: the caller is done with them before the context is used again, so the view itself is returned."""
     try:
+        t0 = time()
         if len(off) > 1 and bool(np.any(off[1:] < off[:-1])):
             raise _lib.DcbError("reads are not in text order")
-        # the text goes to the GPU as it is and is 2-bit packed there (dcb_decombine_ascii): no packed copy on the host
-        res, dev_counts = ctx.decombine_ascii(buf, off, length, pack_rc)
+        t1 = time()
+        # the text goes to the GPU as it is, or 2-bit packed by the host threads (dcb_decombine_ascii shares the chunks)
+        res, dev_counts = ctx.decombine_ascii(buf, off, length, pack_rc, pinned=True)
+        if not transient:
+            res = res.copy()
+        if os.environ.get("DCB_TIMING"):
+            print("\t[timing]   order check %.3f s, dcb_decombine_ascii %.3f s (chunks packed by host threads / device: %s)"
+                  % (t1 - t0, time() - t1, ctx.last_pack_shares()))
     except _lib.DcbError:
         # reads out of text order, or more non-ACGT symbols than the device-side list holds: pack on the host threads
         packed = _lib.pack_arrays(buf, off, length, revcomp=pack_rc)
