@@ -473,7 +473,7 @@ def main():
         h2d_gbps = 5 * len(text.a) / (time.perf_counter() - c0) / 1e9
         del dev_buf, host_t
         text.free()
-    exact_name, h2d_bytes = ctx.exact_kernel_name(), packed.h2d_bytes()
+    exact_name, h2d_bytes, slot_bytes = ctx.exact_kernel_name(), packed.h2d_bytes(), packed.slot_words * 4
 
     n_general = ctx.last_general()
     cfg2 = cfg3 = cfg4 = None
@@ -531,7 +531,7 @@ def main():
                          "kernel": exact_name, "bytes_per_read": bytes_per_read,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650"},
             "e2e": {"value": e2e, "unit": UNIT,
-                    "h2d_bytes_per_step": int(n * (READ_LEN * device_chunks + packed.slot_words * 4 * host_chunks) / max(1, host_chunks + device_chunks)),
+                    "h2d_bytes_per_step": int(n * (READ_LEN * device_chunks + slot_bytes * host_chunks) / max(1, host_chunks + device_chunks)),
                     "d2h_bytes_per_step": int(n * 16 + 8 * _lib.NCOUNTERS), "steps": e2e_steps,
                     "call": "dcb_decombine_ascii: ASCII reads in page-locked host memory in (the reference arm's input), result records in "
                             "host memory out; chunks of clean reads are packed by the device (the text crosses the link) or, while the "

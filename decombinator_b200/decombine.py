@@ -363,7 +363,9 @@ def decombinator(inputargs: dict) -> list:
         res = decombine_batch(batch, inputargs) if n else np.zeros(0, dtype=_lib.RESULT_DTYPE)
         _lap("text -> GPU -> records")
         pack_rc, _ = _orientation_plan(inputargs["orientation"])
-        hits = np.nonzero(res["status"])[0]
+        text_only = bool(inputargs.get("rows_as_text")) and isinstance(batch.vdj, fastq.TextColumn) and not inputargs.get("rows_as_columns")
+        # (the `decombine` command needs the number of hits, not their indices: the formatter walks the records itself)
+        hits = range(int(np.count_nonzero(res["status"]))) if text_only else np.nonzero(res["status"])[0]
         counts["vj_count"] += int(len(hits))
         sampling = inputargs.get("sampling_analysis")
         if isinstance(batch.vdj, fastq.TextColumn) and len(hits):
