@@ -35,24 +35,41 @@ void parallel_for(int n_threads, uint64_t n, F f) {
 
 }  // namespace
 
-#if defined(__x86_64__)
 namespace {
+// A line of the text as the scan records it: where it starts (48 bits) | its first byte << 48 | the offset of its first
+// SPACE << 56 (255: none within the first 255 bytes) -- all the record pass needs, so that it never touches the text again.
+inline uint64_t line_entry(const unsigned char* p, uint64_t pos, uint64_t n_bytes) {
+    return pos | ((uint64_t)(pos < n_bytes ? p[pos] : 0) << 48) | (255ull << 56);
+}
+inline void line_space(std::vector<uint64_t>& v, uint64_t at) {          // a space at `at`: the first of the current line?
+    if (v.empty()) return;                                               // in a line that started in the chunk before
+    uint64_t& e = v.back();
+    if ((e >> 56) != 255) return;
+    const uint64_t k = at - (e & 0xFFFFFFFFFFFFull);
+    if (k < 255) e = (e & ~(255ull << 56)) | (k << 56);
+}
+#if defined(__x86_64__)
 const bool kAvx2 = __builtin_cpu_supports("avx2");
-// Line starts of text[i .. b) in steps of 32 bytes (i is left at the first byte not looked at); returns non-zero when a
+// Lines of text[i .. b) in steps of 32 bytes (i is left at the first byte not looked at); returns non-zero when a
 // '\r' or a non-ASCII byte was seen.
-__attribute__((target("avx2"))) unsigned char scan_lines_avx2(const unsigned char* p, uint64_t& i, uint64_t b, std::vector<uint64_t>& v) {
-    const __m256i nl = _mm256_set1_epi8('\n'), cr = _mm256_set1_epi8('\r');
+__attribute__((target("avx2"))) unsigned char scan_lines_avx2(const unsigned char* p, uint64_t& i, uint64_t b, uint64_t n_bytes, std::vector<uint64_t>& v) {
+    const __m256i nl = _mm256_set1_epi8('\n'), cr = _mm256_set1_epi8('\r'), sp = _mm256_set1_epi8(' ');
     __m256i acc = _mm256_setzero_si256();
     for (; i + 32 <= b; i += 32) {
         const __m256i x = _mm256_loadu_si256((const __m256i*)(p + i));
         acc = _mm256_or_si256(acc, _mm256_or_si256(x, _mm256_cmpeq_epi8(x, cr)));
-        for (uint32_t m = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(x, nl)); m; m &= m - 1u)
-            v.push_back(i + (uint64_t)__builtin_ctz(m) + 1);
+        const uint32_t m_nl = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(x, nl));
+        const uint32_t m_sp = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(x, sp));
+        for (uint32_t m = m_nl | m_sp; m; m &= m - 1u) {
+            const uint32_t k = (uint32_t)__builtin_ctz(m);
+            if ((m_nl >> k) & 1u) v.push_back(line_entry(p, i + k + 1, n_bytes));
+            else line_space(v, i + k);
+        }
     }
     return _mm256_movemask_epi8(acc) != 0 ? 1 : 0;
 }
-}  // namespace
 #endif
+}  // namespace
 
 extern "C" {
 
@@ -78,20 +95,27 @@ int dcb_fastq_index_build(const char* text, uint64_t n_bytes, int n_threads, dcb
         const unsigned char* p = (const unsigned char*)text;
         unsigned char any = 0;
         uint64_t i = a;
+        if (a == 0) v.push_back(line_entry(p, 0, n_bytes));                  // the first line starts the text
 #if defined(__x86_64__)
-        if (kAvx2) { any = scan_lines_avx2(p, i, b, v); }
+        if (kAvx2) { any = scan_lines_avx2(p, i, b, n_bytes, v); }
 #endif
         for (; i < b; i++) {
             const unsigned char ch = p[i];
             any |= (unsigned char)((ch & 0x80) | (ch == '\r' ? 0x80 : 0));
-            if (ch == '\n') v.push_back(i + 1);
+            if (ch == '\n') v.push_back(line_entry(p, i + 1, n_bytes));
+            else if (ch == ' ') line_space(v, i);
         }
+        // the first space of the chunk's last line may lie in the next chunk
+        if (!v.empty() && (v.back() >> 56) == 255)
+            for (uint64_t k = b; k < n_bytes && p[k] != '\n' && k - (v.back() & 0xFFFFFFFFFFFFull) < 255; k++)
+                if (p[k] == ' ') { line_space(v, k); break; }
         bad[t] = any != 0;
     });
     const auto T1 = std::chrono::steady_clock::now();
     std::vector<uint64_t> nl(n_threads + 1, 0);
     for (int t = 0; t < n_threads; t++) { if (bad[t]) return DCB_OK; nl[t + 1] = nl[t] + found[t].size(); }
-    const uint64_t n_lines = nl[n_threads];
+    const uint64_t n_lines = nl[n_threads] - 1;                             // entries: every line start + the end of the text
+    if (n_bytes >= (1ull << 48)) return DCB_OK;
     if (n_lines == 0 || n_lines % 4 != 0) return DCB_OK;
     const uint64_t n = n_lines / 4;
     if (n >= 0xFFFFFFFFull) return DCB_OK;
@@ -99,12 +123,11 @@ int dcb_fastq_index_build(const char* text, uint64_t n_bytes, int n_threads, dcb
     // where every line starts (line k + 1 starts behind the k-th newline): the threads' lists, end to end
     uint64_t* start = (uint64_t*)std::malloc(sizeof(uint64_t) * (n_lines + 1));
     if (!start) { dcb_set_error("dcb_fastq_index_build: out of memory"); return DCB_ENOMEM; }
-    start[0] = 0;
     {
         std::vector<std::thread> th;
         for (int t = 0; t < n_threads; t++)
             if (!found[t].empty())
-                th.emplace_back([&, t] { std::memcpy(start + 1 + nl[t], found[t].data(), sizeof(uint64_t) * found[t].size()); });
+                th.emplace_back([&, t] { std::memcpy(start + nl[t], found[t].data(), sizeof(uint64_t) * found[t].size()); });
         for (auto& x : th) x.join();
     }
     found.clear();
@@ -122,14 +145,23 @@ int dcb_fastq_index_build(const char* text, uint64_t n_bytes, int n_threads, dcb
     std::vector<int> irregular(n_threads, 0);
     parallel_for(n_threads, n, [&](int t, uint64_t a, uint64_t b) {
         for (uint64_t r = a; r < b; r++) {
-            const uint64_t h = start[4 * r], s = start[4 * r + 1], p = start[4 * r + 2], q = start[4 * r + 3], e = start[4 * r + 4];
+            const uint64_t M = 0xFFFFFFFFFFFFull;
+            const uint64_t eh = start[4 * r], es = start[4 * r + 1], ep = start[4 * r + 2];
+            const uint64_t h = eh & M, s = es & M, p = ep & M, q = start[4 * r + 3] & M, e = start[4 * r + 4] & M;
             const uint64_t hl = s - h - 1, sl = p - s - 1, ql = e - q - 1;            // line lengths without the '\n'
-            if (text[h] != '@' || text[p] != '+') { irregular[t] = 1; return; }
-            if (sl > 0 && (text[s] == '@' || text[s] == '+' || text[s] == '>')) { irregular[t] = 1; return; }   // a marker to readfq
+            const unsigned char ch = (unsigned char)(eh >> 48), cs = (unsigned char)(es >> 48), cp = (unsigned char)(ep >> 48);
+            if (ch != '@' || cp != '+') { irregular[t] = 1; return; }
+            if (sl > 0 && (cs == '@' || cs == '+' || cs == '>')) { irregular[t] = 1; return; }   // a marker to readfq
             if (ql < sl || sl > 0xFFFFFFu || ql > 0xFFFFFFu) { irregular[t] = 1; return; }     // multi-line quality / absurd
-            const char* sp = (const char*)std::memchr(text + h + 1, ' ', (size_t)(hl - 1 + (hl == 0)));
+            uint64_t name_len = hl == 0 ? 0 : hl - 1;                                 // up to the first space behind the '@'
+            const uint64_t k = eh >> 56;
+            if (k != 255) { if (k >= 1 && k <= hl) name_len = k - 1; }
+            else if (hl > 255) {
+                const char* sp = (const char*)std::memchr(text + h + 255, ' ', (size_t)(hl - 255));
+                if (sp) name_len = (uint64_t)(sp - (text + h + 1));
+            }
             ix->name_off[r] = h + 1;
-            ix->name_len[r] = hl == 0 ? 0u : (uint32_t)(sp ? (uint64_t)(sp - (text + h + 1)) : hl - 1);
+            ix->name_len[r] = (uint32_t)name_len;
             ix->seq_off[r] = s; ix->seq_len[r] = (uint32_t)sl;
             ix->qual_off[r] = q; ix->qual_len[r] = (uint32_t)ql;
         }
