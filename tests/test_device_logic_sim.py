@@ -117,7 +117,8 @@ def test_half_index_covers_j_only_with_long_half_tags():
 
 @pytest.mark.parametrize("species,tagset,chain,L,sub,nrate", [("mouse", "original", "g", 250, 0.005, 0.0), ("mouse", "original", "d", 250, 0.005, 0.001),
                                                               ("human", "original", "b", 250, 0.01, 0.001), ("human", "original", "a", 150, 0.01, 0.0),
-                                                              ("mouse", "extended", "a", 250, 0.01, 0.0), ("human", "extended", "d", 200, 0.02, 0.0)])
+                                                              ("mouse", "extended", "a", 250, 0.01, 0.0), ("human", "extended", "d", 200, 0.02, 0.0),
+                                                              ("human", "original", "a", 250, 0.01, 0.002)])   # flat kernel + N: the scan sees the invalid-base column
 def test_sim_half_tag_path_short_j_halves(species, tagset, chain, L, sub, nrate):
     """Chains with a 6-base J split (12-nt J tags): their J halves -- and, behind an exact-tag kernel that only searches J
     in reads with one full V tag, the full J tags -- are found with the 6-mer table at every base of the reads whose V is

@@ -52,6 +52,7 @@ def test_cuda_matches_reference_fixtures(dcr_cases, force_general):
     ("mouse", "original", "g", "reverse", 250, 0.005, 0.0, 0.02),    # configs[4] shape
     ("mouse", "original", "d", "both", 250, 0.005, 0.001, 0.02),
     ("mouse", "original", "a", "reverse", 250, 0.01, 0.001, 0.02),
+    ("human", "original", "a", "reverse", 250, 0.01, 0.002, 0.02),   # flat kernel + N + 6-base J halves: the J scan over the invalid-base column
 ])
 def test_cuda_matches_oracle_on_synthetic(species, tagset, chain, orientation, L, sub, nrate, junk):
     info = tags.load(species, tagset, chain)
