@@ -1032,7 +1032,10 @@ DCB_HD int dcr_exact_read(const ReadView& r, bool flagged, const uint32_t* vcore
                           const uint32_t* vidx, const uint32_t* jidx, const DcrParams& prm, int both_frames,
                           dcb_result& out, dcb_cnt_t* C, bool use_q = false, const ExcProbe* xp = nullptr,
                           uint32_t* hand = nullptr) {
-    if (hand) { hand[0] = DCB_HIT_MULTI; hand[1] = DCB_HIT_MULTI; }   // "not searched": the half-tag path passes such a read on
+    // a read with non-ACGT symbols is not searched here unless the caller handed its symbols over (the flat kernel, up to
+    // four of them): behind the bit-filter kernels the half-tag path searches both genes itself ("unknown"); a read the flat
+    // kernel skips is passed on by the half-tag path ("several")
+    if (hand) { hand[0] = hand[1] = use_q ? DCB_HIT_MULTI : DCB_HIT_UNKNOWN; }
     if (flagged && (!xp || xp->over)) return FAST_DEFER;
     if (!flagged) xp = nullptr;
     FullHit vh, jh;
@@ -1283,22 +1286,25 @@ DCB_HD void half_candidate(const ReadView& r, const uint32_t* inv2, const HalfVi
 // half_jshort_ok: does the read need the scan?  cand / n: the candidates so far (V side).
 DCB_HD bool half_jshort_ok(const HalfView& hx, uint32_t hv, uint32_t hj, const uint32_t* cand, int stride, int cap, uint32_t n) {
     if (!hx.j_short || !(hj == 0u || hj == DCB_HIT_UNKNOWN) || n >= DCB_HALF_BAIL || DCB_HALF_COUNT(n) > (uint32_t)cap) return false;
-    if (hv != 0u) return true;
+    if (hv != 0u && hv != DCB_HIT_UNKNOWN) return true;
     for (uint32_t i = 0; i < DCB_HALF_COUNT(n); i++) {
         const uint32_t e = cand[i * stride];
         if (DCB_HC_GENE(e) == 0u) return true;
     }
     return false;          // no V: janalysis is never reached (decombine.py:542-545)
 }
-// A full J tag starts with its first half: (occurrence of a half1 keyword at P, tag ti of that keyword) -> the whole tag
-// compared, an occurrence appended as a candidate of kind 0.
+// A full tag starts with its first half: (occurrence of a half1 keyword at P, tag ti of that keyword) -> the whole tag
+// compared, an occurrence appended as a candidate of kind 0.  fu: the genes whose full tags the exact-tag kernel did not
+// search (bit 0 V, bit 1 J).
+#define DCB_FU_OF(hv, hj) (((hv) == DCB_HIT_UNKNOWN ? 1u : 0u) | ((hj) == DCB_HIT_UNKNOWN ? 2u : 0u))
 template <bool PADDED>
-DCB_HD void half_jfull_candidate(const ReadView& r, const uint32_t* inv2, const HalfView& hx, const DcbTag* jtags, int id, int ti, int P,
-                                 uint32_t* cand, int cap, uint32_t* n) {
+DCB_HD void half_full_candidate(const ReadView& r, const uint32_t* inv2, const HalfView& hx, const DcbTag* vtags, const DcbTag* jtags,
+                                int id, int ti, int P, uint32_t fu, uint32_t* cand, int cap, uint32_t* n) {
     const DcbHalfKw k = hx.kw[id];
-    if (k.set != 2) return;
+    if ((k.set & 1) || !((fu >> (k.set >> 1)) & 1u)) return;
+    const int gene = k.set >> 1;
     const int kk = hx.tags[k.tags_off + ti];
-    const DcbTag& t = jtags[kk];
+    const DcbTag& t = (gene ? jtags : vtags)[kk];
     if (P + (int)t.len > r.n) return;
     uint32_t lo, hi;
     rd_win32x<PADDED>(r, P, lo, hi);
@@ -1308,7 +1314,7 @@ DCB_HD void half_jfull_candidate(const ReadView& r, const uint32_t* inv2, const 
         rd_win32x<PADDED>(half_inv_view(r, inv2), P, ilo, ihi);
         lo |= ilo; hi |= ihi;
     }
-    if (!((lo & t.mask_lo) | (hi & t.mask_hi))) half_append(cand, r.stride, cap, n, DCB_HC_MAKE(1, 0, P + (int)t.len, t.len, kk, 0));
+    if (!((lo & t.mask_lo) | (hi & t.mask_hi))) half_append(cand, r.stride, cap, n, DCB_HC_MAKE(gene, 0, P + (int)t.len, t.len, kk, 0));
 }
 // One base of the scan, serially (tests/sim; the kernel pools the 6-mer hits of a warp): `six` = the DCB_HALF_JQ bases at P.
 template <bool PADDED>
@@ -1322,7 +1328,7 @@ DCB_HD void half_jshort_at(const ReadView& r, const uint32_t* inv2, const HalfVi
         DCB_HD void operator()(int id, int n_tags) {
             for (int ti = 0; ti < n_tags; ti++) {
                 half_candidate<PADDED>(r, inv2, hx, vtags, jtags, id, ti, P, cand, cap, n);
-                if (full) half_jfull_candidate<PADDED>(r, inv2, hx, jtags, id, ti, P, cand, cap, n);
+                if (full) half_full_candidate<PADDED>(r, inv2, hx, vtags, jtags, id, ti, P, 2u, cand, cap, n);
             }
         }
     } sink{r, inv2, hx, vtags, jtags, P, full, cand, cap, n};
@@ -1362,7 +1368,7 @@ DCB_HD bool half_begin(ReadView& r, const uint32_t*& inv2, bool flagged, const E
             if ((ilo & mask2(L)) | (L > 16 ? (ihi & mask2(L - 16)) : 0u)) h = 0u;
         }
     }
-    need = (hv ? 0u : 0x00FFu) | ((hj || !j_ok) ? 0u : 0xFF00u);
+    need = ((hv && hv != DCB_HIT_UNKNOWN) ? 0u : 0x00FFu) | (((hj && hj != DCB_HIT_UNKNOWN) || !j_ok) ? 0u : 0xFF00u);
     return true;
 }
 // vanalysis / janalysis over the sorted candidates of one gene, from entry `i` on (decombine.py:273-394, 397-531): the
@@ -1447,7 +1453,7 @@ DCB_HD bool half_run(const ReadView& r, const uint32_t* inv2, const HalfView& hx
     if (why) *why = 4;
     // V is assigned: now J.  A J gene that was not searched for full tags, or whose half tags this index does not hold
     // while the full tag is missing, is the general kernel's business.
-    if (ev && ok && !hx.j_short && (hj == DCB_HIT_UNKNOWN || (hj == 0u && !hx.j_ok))) return false;
+    if (ev && ok && !hx.j_short && !hx.j_ok && (hj == DCB_HIT_UNKNOWN || hj == 0u)) return false;
     uint32_t ej = 0u;
     if (ev && ok) {                                                                         // :542-548
         ej = half_select<false>(cand, r.stride, (int)n, i, pend, seen);
@@ -1481,10 +1487,14 @@ DCB_HD bool dcr_half_read(ReadView r, bool flagged, const ExcList& ex, uint32_t 
     struct Sink {
         const ReadView& r; const uint32_t* inv2; const HalfView& hx; const DcbTag* vtags; const DcbTag* jtags;
         uint32_t* cand; int cap; uint32_t* n; int P;
+        uint32_t fu;
         DCB_HD void operator()(int id, int n_tags) {
-            for (int ti = 0; ti < n_tags; ti++) half_candidate<false>(r, inv2, hx, vtags, jtags, id, ti, P, cand, cap, n);
+            for (int ti = 0; ti < n_tags; ti++) {
+                half_candidate<false>(r, inv2, hx, vtags, jtags, id, ti, P, cand, cap, n);
+                if (fu) half_full_candidate<false>(r, inv2, hx, vtags, jtags, id, ti, P, fu, cand, cap, n);
+            }
         }
-    } sink{r, inv2, hx, vtags, jtags, cand, cap, &n, 0};
+    } sink{r, inv2, hx, vtags, jtags, cand, cap, &n, 0, DCB_FU_OF(hv, hj)};
     if (need)
         for (int p = 0; p + DCB_HALF_Q <= r.n; p += DCB_HALF_STRIDE) {
             uint32_t e = hx.t[rd_win16(r, p) & mask2(DCB_HALF_Q)] & need;

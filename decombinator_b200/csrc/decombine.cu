@@ -181,6 +181,13 @@ __device__ __forceinline__ void flush_counters(const dcb_cnt_t* s_cnt, unsigned 
         atomicAdd(counters + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
 }
 
+// The first entry of read ri (which has some) in the sorted exception list: inside its 32-read group's run.
+__device__ __forceinline__ uint32_t exc_first_entry(const BatchDev& b, uint32_t ri) {
+    uint32_t e = __ldg(b.exc_index + (ri >> 5));
+    while (__ldg(b.exc_read + e) < ri) e++;
+    return e;
+}
+
 // Append the reads of this warp that must go to the general kernel: one atomic per warp.
 __device__ __forceinline__ void defer_reads(bool defer, uint32_t ri, uint32_t* queue, uint32_t* queue_count) {
     const unsigned m = __ballot_sync(0xFFFFFFFFu, defer);
@@ -232,7 +239,8 @@ dcb_exact_kernel(BatchDev b, Tables4 tb, DcrParams prm, int both_frames, dcb_res
             r.exc_pos = nullptr; r.exc_kind = nullptr; r.e0 = r.e1 = 0; r.mirror = 0; r.cand = nullptr; r.cand_kq = 0; r.hits = nullptr; r.n_hits = 0;
             uint32_t hand[2];
             action = dcr_exact_read(r, flagged, L.t[0], L.t[1], L.t[2], L.t[3], prm, both_frames, out, L.cnt, false, nullptr, hand);
-            if (action == FAST_DEFER) *reinterpret_cast<uint4*>(results + ri) = make_uint4(hand[0], hand[1], 0u, 0u);   // for dcb_halftag_kernel
+            if (action == FAST_DEFER)   // for dcb_halftag_kernel
+                *reinterpret_cast<uint4*>(results + ri) = make_uint4(hand[0], hand[1], flagged ? exc_first_entry(b, ri) : 0u, 0u);
         }
         defer_reads(live && action == FAST_DEFER, ri, queue, queue_count);
         if (live && action == FAST_DONE) store_result(results + ri, out);
@@ -417,7 +425,9 @@ dcb_exact_kernel_spec(BatchDev b, Tables4 tb, SpecBlooms bl, DcrParams prm, int 
         else if (live) {
             // hand-over to dcb_halftag_kernel: what the search found; J was only searched for reads with one full V tag
             const uint32_t hj = (!UNION && vh.count != 1) ? DCB_HIT_UNKNOWN : half_word_of(jh);
-            *reinterpret_cast<uint4*>(results + ri) = scan ? make_uint4(half_word_of(vh), hj, 0u, 0u) : make_uint4(DCB_HIT_MULTI, DCB_HIT_MULTI, 0u, 0u);
+            // (a read with non-ACGT symbols is not searched here: both genes "unknown", the half-tag kernel searches them itself)
+            *reinterpret_cast<uint4*>(results + ri) = scan ? make_uint4(half_word_of(vh), hj, 0u, 0u)
+                                                           : make_uint4(DCB_HIT_UNKNOWN, DCB_HIT_UNKNOWN, flagged ? exc_first_entry(b, ri) : 0u, 0u);
         }
     }
     flush_counters(L.cnt, counters);
@@ -832,7 +842,6 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
                     const int src = __ffs(mw) - 1;
                     mw &= mw - 1u;
                     const int n_s = __shfl_sync(0xFFFFFFFFu, r.n, src);
-                    const uint32_t full_s = __shfl_sync(0xFFFFFFFFu, hj == DCB_HIT_UNKNOWN ? 1u : 0u, src);
                     const uint32_t* cs = s_rd + T + wbase + src;
                     for (int base = 0; base + DCB_HALF_JQ <= n_s; base += 256) {
                         const int p0 = base + 8 * lane;
@@ -846,7 +855,7 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
                         }
                         for (; found; found &= found - 1u) {
                             const uint32_t at = atomicAdd(s_n2, 1u);
-                            if (at < DCB_HALF_WCAP2) s_work2[at] = (uint32_t)src | ((uint32_t)(p0 + __ffs(found) - 1) << 5) | (1u << 17) | (full_s << 18);
+                            if (at < DCB_HALF_WCAP2) s_work2[at] = (uint32_t)src | ((uint32_t)(p0 + __ffs(found) - 1) << 5) | (1u << 17);
                             else atomicAdd(s_n + wbase + src, DCB_HALF_BAIL);               // list full: pass the read on
                         }
                     }
@@ -863,6 +872,7 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
                 const int src = (int)(it & 31u), P = (int)((it >> 5) & 1023u), set = (int)((it >> 15) & 3u);
                 const int n_s = __shfl_sync(0xFFFFFFFFu, r.n, src);
                 const int flg_s = __shfl_sync(0xFFFFFFFFu, inv2 != nullptr ? 1 : 0, src);
+                const uint32_t fu_s = __shfl_sync(0xFFFFFFFFu, DCB_FU_OF(hv, hj), src);   // genes whose full tags are not searched yet
                 if (has) {
                     ReadView rs;
                     rs.w = s_rd + T + wbase + src; rs.stride = T; rs.nw = NW; rs.n = n_s;
@@ -877,7 +887,7 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
                             }
                             for (int ti = 0; ti < n_tags; ti++) list[at + ti] = base | ((uint32_t)id << 15) | ((uint32_t)ti << 23);
                         }
-                    } sink{s_work3, s_n2 + 1, s_n + wbase + src, (uint32_t)src | ((uint32_t)P << 5) | (((it >> 18) & 1u) << 27)};
+                    } sink{s_work3, s_n2 + 1, s_n + wbase + src, (uint32_t)src | ((uint32_t)P << 5) | (fu_s << 27)};
                     uint32_t meta;
                     if ((it >> 17) & 1u) {                          // a 6-mer hit of the J scan
                         uint32_t lo, hi;
@@ -906,7 +916,8 @@ dcb_halftag_kernel(BatchDev b, Tables4 tb, DcrParams prm, dcb_result* __restrict
                     const uint32_t* inv_s = flg_s ? s_inv + T + wbase + src : nullptr;
                     const int id = (int)((it >> 15) & 255u), ti = (int)((it >> 23) & 15u), P = (int)((it >> 5) & 1023u);
                     half_candidate<true>(rs, inv_s, hx, vtags, jtags, id, ti, P, s_cand + wbase + src, DCB_HALF_CAP, s_n + wbase + src);
-                    if ((it >> 27) & 1u) half_jfull_candidate<true>(rs, inv_s, hx, jtags, id, ti, P, s_cand + wbase + src, DCB_HALF_CAP, s_n + wbase + src);
+                    if ((it >> 27) & 3u)
+                        half_full_candidate<true>(rs, inv_s, hx, vtags, jtags, id, ti, P, (it >> 27) & 3u, s_cand + wbase + src, DCB_HALF_CAP, s_n + wbase + src);
                 }
             }
             __syncwarp();

@@ -136,11 +136,12 @@ def test_sim_half_tag_path_short_j_halves(species, tagset, chain, L, sub, nrate)
     assert_records_equal(res, want, "reverse")
     assert np.array_equal(cnt, orc.counts)
     assert nd > 0.5 * n
-    if nrate == 0.0 and L >= 200:
-        assert nd2 < 0.05 * n, (nd, nd2)             # next to nothing is left for the general path
+    if L >= 200:
+        # next to nothing is left for the general path -- reads with non-ACGT symbols included: behind the bit-filter exact
+        # kernels (which do not search them) both genes are handed over "unknown" and the half-tag path compares the full tags
+        assert nd2 < 0.05 * n, (nd, nd2)
     else:
-        # reads with non-ACGT symbols are not searched by the bit-filter exact kernels and go on unseen; short reads cut tags off
-        assert nd2 < 0.5 * nd
+        assert nd2 < 0.5 * nd                        # short reads cut tags off
     packed.free()
 
 
