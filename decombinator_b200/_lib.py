@@ -93,6 +93,9 @@ def lib():
                                   ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(u64), ctypes.POINTER(u64)]
     L.dcb_buffer_free.argtypes = [ctypes.c_void_p]
     L.dcb_buffer_free.restype = None
+    L.dcb_format_collapse_rows.argtypes = [vp, u64, i32] + [ctypes.POINTER(CColumn)] * 3 + [i32, ctypes.POINTER(ctypes.c_void_p),
+                                           ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
+    L.dcb_format_collapse_rows.restype = ctypes.c_int
     L.dcb_pack_reads.argtypes = [vp, vp, vp, u64, i32, i32, ctypes.POINTER(ctypes.POINTER(CPacked))]
     L.dcb_packed_free.argtypes = [ctypes.POINTER(CPacked)]
     L.dcb_pack_words.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32,
@@ -339,6 +342,25 @@ def pack_words(buf, off, length, revcomp, slot_words, uniform_len=0, first=0, co
                                 int(bool(revcomp)), int(slot_words), words.ctypes.data,
                                 n_threads or min(32, os.cpu_count() or 1), ctypes.byref(clean)), "dcb_pack_words")
     return words, bool(clean.value)
+
+
+def format_collapse_rows(res, packed_revcomp, columns, n_threads=None):
+    """dcb_format_collapse_rows: three lines per decombined read -- tcrseq, str(row[:5]) and the "|"-joined
+    (str(row[:5]), tcrseq, tcrQ, read id) collapse files its rows under.  columns: (ids, vdj, vdjqual, ...).
+    -> (NativeText, number of rows)"""
+    keep, cols = [], []
+    for col in columns[:3]:
+        buf = np.frombuffer(col.buf, dtype=np.uint8)
+        off = np.ascontiguousarray(col.off, dtype=np.uint64)
+        ln = np.ascontiguousarray(col.len, dtype=np.uint32)
+        keep.append((buf, off, ln))
+        cols.append(ctypes.pointer(CColumn(buf.ctypes.data, off.ctypes.data, ln.ctypes.data)))
+    res = np.ascontiguousarray(res)
+    out, nbytes, nrows = ctypes.c_void_p(), ctypes.c_uint64(), ctypes.c_uint64()
+    nt = n_threads or min(32, os.cpu_count() or 1)
+    _check(lib().dcb_format_collapse_rows(res.ctypes.data, len(res), int(bool(packed_revcomp)), *cols, nt,
+                                          ctypes.byref(out), ctypes.byref(nbytes), ctypes.byref(nrows)), "dcb_format_collapse_rows")
+    return NativeText(out.value, nbytes.value), int(nrows.value)
 
 
 class NativeText:

@@ -25,7 +25,10 @@ There is no CPU implementation of the distances here: without libdcb.so and a GP
 import ast
 import collections as coll
 import gzip
+import itertools
+import operator
 import os
+import re
 import sys
 import time
 from statistics import median
@@ -408,12 +411,15 @@ def _filter_columns(data, inputargs, barcode_quality_parameters, first_index=0):
                                               np.asarray(bcq.len)[hits], _lib.OLIGOS_ON_DEVICE[name], inputargs["allowNs"] != False,  # noqa: E712
                                               *barcode_quality_parameters)
     _count_device_barcodes(status, n1)
-    keep = (status == _lib.BC_OK) | (status == _lib.BC_HOST)
-    rows = data.subset_rows(keep)                       # only these become Python rows
-    sym = (code[keep][:, None] >> (np.uint64(3) * np.arange(12, dtype=np.uint64))[None, :]) & np.uint64(7)
+    ok, host = status == _lib.BC_OK, status == _lib.BC_HOST
+    # rows whose barcode the kernel assembled: no Python row at all, the three strings collapse files them under come from
+    # dcb_format_collapse_rows; rows it hands back (fuzzy spacer search) become Python rows as before
+    seqs, dcrs, etcs = data.collapse_lines(ok)
+    sym = (code[ok][:, None] >> (np.uint64(3) * np.arange(12, dtype=np.uint64))[None, :]) & np.uint64(7)
     text = _BC_SYMBOLS[sym.astype(np.intp)].tobytes().decode("ascii")
-    where = np.nonzero(keep)[0]
-    return rows, status[keep].tolist(), text, (first_index + where).tolist(), int(len(status))
+    fast = (seqs, dcrs, etcs, re.findall("." * 12, text), (first_index + np.nonzero(ok)[0]).tolist())
+    rows = data.subset_rows(host) if bool(host.any()) else []
+    return rows, (first_index + np.nonzero(host)[0]).tolist(), fast, int(len(status))
 
 
 def _filter_rows(data, inputargs, barcode_quality_parameters, dont_count, from_file, first_index=0):
@@ -427,9 +433,10 @@ def _filter_rows(data, inputargs, barcode_quality_parameters, dont_count, from_f
     Rows are independent here, so a multi-GPU run calls this on each rank's shard (parallel.py)."""
     t0 = time.time()
     columnar = _filter_columns(data, inputargs, barcode_quality_parameters, first_index) if hasattr(data, "subset_rows") else None
-    index = None
+    index = fast = None
     if columnar is not None:
-        rows, status, text, index, n_rows = columnar
+        rows, index, fast, n_rows = columnar
+        status = text = None                           # the rows left are the ones the kernel handed back
     else:
         rows = [line.rstrip("\n").split(", ") for line in data] if from_file else (data if isinstance(data, list) else list(data))
         dev = _device_barcodes(rows, inputargs, barcode_quality_parameters)
@@ -471,6 +478,18 @@ def _filter_rows(data, inputargs, barcode_quality_parameters, dont_count, from_f
         else:
             dcretc = "|".join((dcr, seq, line[7], line[5]))
         kept.append((index[lcount] if index is not None else first_index + lcount, barcode, seq, dcretc))
+    if fast is not None and fast[0]:
+        seqs, dcrs, etcs, barcodes, idx = fast
+        input_dcr_counts.update(dcrs)
+        short = (np.fromiter(map(len, seqs), dtype=np.int64, count=len(seqs)) <= lenthreshold).tolist()
+        part = list(itertools.compress(zip(idx, barcodes, seqs, etcs), short))
+        n_long += len(seqs) - len(part)
+        n_ok += len(part)
+        if kept:                                       # both lists are in input order: one merge
+            kept = part + kept
+            kept.sort(key=operator.itemgetter(0))
+        else:
+            kept = part
     if n_long:
         counts["readdata_fail_overlong_intertag_seq"] += n_long
     if n_ok:

@@ -277,6 +277,8 @@ struct RowCtx {
     const dcb_result* res; int packed_rc;
     const dcb_column *ids, *vdj, *qual, *bc, *bcq, *tail;
     const char* sep; size_t sep_len;
+    int mode;        // 0: the row, fields joined by sep; 1: what collapse builds per row, three lines: tcrseq, str(row[:5]),
+                     //    "|".join((str(row[:5]), tcrseq, tcrQ, read id)) (collapse.py:560-590)
 };
 
 // length of the row of read i (it decombined), or its bytes when dst != nullptr
@@ -287,6 +289,42 @@ inline size_t row_emit(const RowCtx& c, uint64_t i, char* dst) {
     int64_t ia = r.ins_start, ib = r.ins_end, sa = r.v_seq_start, sb = r.j_seq_end, qa = r.v_seq_start, qb = r.j_seq_end;
     clip(n, ia, ib); clip(n, sa, sb); clip(nq, qa, qb);
     const size_t fixed = (size_t)dec_len(r.v) + dec_len(r.j) + dec_len(r.vdel) + dec_len(r.jdel);
+    if (c.mode == 1) {
+        const size_t dcr = fixed + (size_t)(ib - ia) + 20, sq = (size_t)(sb - sa);     // ['v', 'j', 'vdel', 'jdel', 'insert']
+        const size_t total = sq + 1 + dcr + 1 + dcr + 1 + sq + 1 + (size_t)(qb - qa) + 1 + c.ids->len[i] + 1;
+        if (!dst) return total;
+        char* p = dst;
+        const unsigned char* s = (const unsigned char*)c.vdj->text + c.vdj->off[i];
+        const char* q = c.qual->text + c.qual->off[i];
+        auto seq = [&](int64_t a, int64_t b) {
+            if (rev) {
+#ifdef DCB_HAVE_SSSE3_PATH
+                if (kSsse3 && b - a >= 16 && revcomp_copy_ssse3(p, s, n, a, b)) { p += b - a; return; }
+#endif
+                for (int64_t k = a; k < b; k++) *p++ = (char)kComp.t[s[n - 1 - k]];
+            } else { std::memcpy(p, s + a, (size_t)(b - a)); p += b - a; }
+        };
+        auto lit = [&](const char* t, size_t l) { std::memcpy(p, t, l); p += l; };
+        char* const seq_at = p;
+        seq(sa, sb); *p++ = '\n';
+        char* const dcr_at = p;
+        lit("['", 2); p = put_dec(p, r.v); lit("', '", 4); p = put_dec(p, r.j); lit("', '", 4); p = put_dec(p, r.vdel); lit("', '", 4);
+        p = put_dec(p, r.jdel); lit("', '", 4); seq(ia, ib); lit("']", 2);
+        *p++ = '\n';
+        std::memcpy(p, dcr_at, dcr); p += dcr; *p++ = '|';
+        std::memcpy(p, seq_at, sq); p += sq; *p++ = '|';
+        if (rev) {
+#ifdef DCB_HAVE_SSSE3_PATH
+            if (kSsse3) { rev_copy_ssse3(p, q, nq, qa, qb); p += qb - qa; }
+            else
+#endif
+            for (int64_t k = qa; k < qb; k++) *p++ = q[nq - 1 - k];
+        } else { std::memcpy(p, q + qa, (size_t)(qb - qa)); p += qb - qa; }
+        *p++ = '|';
+        std::memcpy(p, c.ids->text + c.ids->off[i], c.ids->len[i]); p += c.ids->len[i];
+        *p++ = '\n';
+        return (size_t)(p - dst);
+    }
     const int nf = c.tail ? 11 : 10;
     const size_t total = fixed + (size_t)(ib - ia) + c.ids->len[i] + (size_t)(sb - sa) + (size_t)(qb - qa) + c.bc->len[i] +
                          c.bcq->len[i] + (c.tail ? c.tail->len[i] : 0) + (size_t)(nf - 1) * c.sep_len + 1;
@@ -327,6 +365,8 @@ inline size_t row_emit(const RowCtx& c, uint64_t i, char* dst) {
 
 extern "C" {
 
+static int format_impl(const RowCtx& c, const dcb_result* res, uint64_t n, int n_threads, char** out, uint64_t* out_bytes, uint64_t* n_rows);
+
 int dcb_format_rows(const dcb_result* res, uint64_t n, int packed_revcomp, const dcb_column* ids, const dcb_column* vdj,
                     const dcb_column* vdjqual, const dcb_column* bc, const dcb_column* bcq, const dcb_column* v_tail,
                     const char* sep, int n_threads, char** out, uint64_t* out_bytes, uint64_t* n_rows) {
@@ -334,12 +374,28 @@ int dcb_format_rows(const dcb_result* res, uint64_t n, int packed_revcomp, const
         dcb_set_error("dcb_format_rows: null argument");
         return DCB_EINVAL;
     }
+    RowCtx c;
+    c.res = res; c.packed_rc = packed_revcomp; c.ids = ids; c.vdj = vdj; c.qual = vdjqual; c.bc = bc; c.bcq = bcq; c.tail = v_tail;
+    c.sep = sep; c.sep_len = std::strlen(sep); c.mode = 0;
+    return format_impl(c, res, n, n_threads, out, out_bytes, n_rows);
+}
+
+int dcb_format_collapse_rows(const dcb_result* res, uint64_t n, int packed_revcomp, const dcb_column* ids, const dcb_column* vdj,
+                             const dcb_column* vdjqual, int n_threads, char** out, uint64_t* out_bytes, uint64_t* n_rows) {
+    if (!out || !out_bytes || !n_rows || (n && (!res || !ids || !vdj || !vdjqual))) {
+        dcb_set_error("dcb_format_collapse_rows: null argument");
+        return DCB_EINVAL;
+    }
+    RowCtx c;
+    c.res = res; c.packed_rc = packed_revcomp; c.ids = ids; c.vdj = vdj; c.qual = vdjqual; c.bc = nullptr; c.bcq = nullptr; c.tail = nullptr;
+    c.sep = ""; c.sep_len = 0; c.mode = 1;
+    return format_impl(c, res, n, n_threads, out, out_bytes, n_rows);
+}
+
+static int format_impl(const RowCtx& c, const dcb_result* res, uint64_t n, int n_threads, char** out, uint64_t* out_bytes, uint64_t* n_rows) {
     if (n_threads < 1) n_threads = 1;
     if (n_threads > 64) n_threads = 64;
     const auto T0 = std::chrono::steady_clock::now();
-    RowCtx c;
-    c.res = res; c.packed_rc = packed_revcomp; c.ids = ids; c.vdj = vdj; c.qual = vdjqual; c.bc = bc; c.bcq = bcq; c.tail = v_tail;
-    c.sep = sep; c.sep_len = std::strlen(sep);
     // contiguous read ranges per thread: sizes, then bytes, rows staying in read order
     std::vector<uint64_t> bytes(n_threads + 1, 0), rows(n_threads + 1, 0);
     const int nt = (n < 4096) ? 1 : n_threads;

@@ -161,6 +161,17 @@ class RowsColumns:
         blob, _ = _lib.format_rows(res, self.pack_rc, self.columns, "\x1f")
         return [line.split("\x1f") for line in blob.tobytes().decode("ascii").split("\n")[:-1]]
 
+    def collapse_lines(self, keep):
+        """For the hits selected by `keep`, in order: (tcrseq, str(row[:5]), "|".join((str(row[:5]), tcrseq, tcrQ, id))) as
+        three parallel lists of str -- what collapse files a row under, built by dcb_format_collapse_rows."""
+        res = self.res
+        if not bool(np.all(keep)):
+            res = res.copy()
+            res["status"][self.hits[~np.asarray(keep, dtype=bool)]] = 0
+        blob, n = _lib.format_collapse_rows(res, self.pack_rc, self.columns)
+        lines = blob.tobytes().decode("ascii").split("\n")
+        return lines[0:3 * n:3], lines[1:3 * n:3], lines[2:3 * n:3]
+
     def rows(self):
         if self._rows is None:
             self._rows = self.subset_rows(np.ones(len(self.hits), dtype=bool))

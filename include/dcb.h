@@ -184,6 +184,10 @@ typedef struct dcb_column { const char* text; const uint64_t* off; const uint32_
 int dcb_format_rows(const dcb_result* res, uint64_t n, int packed_revcomp, const dcb_column* ids, const dcb_column* vdj,
                     const dcb_column* vdjqual, const dcb_column* bc, const dcb_column* bcq, const dcb_column* v_tail,
                     const char* sep, int n_threads, char** out, uint64_t* out_bytes, uint64_t* n_rows);
+/* What collapse builds per decombined row before it groups them (collapse.py:560-590), for all rows at once: three lines
+ * per row -- tcrseq; str(row[:5]), i.e. "['v', 'j', 'vdel', 'jdel', 'insert']"; and "|".join((that, tcrseq, tcrQ, read id)). */
+int dcb_format_collapse_rows(const dcb_result* res, uint64_t n, int packed_revcomp, const dcb_column* ids, const dcb_column* vdj,
+                             const dcb_column* vdjqual, int n_threads, char** out, uint64_t* out_bytes, uint64_t* n_rows);
 void dcb_buffer_free(char*);
 
 
