@@ -688,6 +688,16 @@ def cluster_UMIs(barcode_dcretc, inputargs, barcode_threshold, lev_threshold_fra
     return clusters
 
 
+def _parse_dcr(dcr):
+    """ast.literal_eval of str([v, j, vdel, jdel, insert]) -- five plain strings -- without compiling an expression per
+    DCR (a second of a million-read run); anything that does not look like that goes through literal_eval."""
+    if dcr.startswith("['") and dcr.endswith("']") and '"' not in dcr and "\\" not in dcr:
+        parts = dcr[2:-2].split("', '")
+        if len(parts) == 5 and not any("'" in x for x in parts):
+            return parts
+    return ast.literal_eval(dcr)
+
+
 def _count_clusters(barcode_dcretc, inputargs, barcode_distance_threshold, lev_threshold_fraction, dont_count, outpath, file_id,
                     find_pairs=None):
     """cluster -> count (collapse.py:919-976), from the initial groups on."""
@@ -713,7 +723,7 @@ def _count_clusters(barcode_dcretc, inputargs, barcode_distance_threshold, lev_t
     for dcr, dcr_count in collapsed.items():
         av_clus_size = round(sum(cluster_sizes[dcr]) / dcr_count)   # Python's round: half to even
         average_cluster_size_counter[av_clus_size] += 1
-        out_data.append(ast.literal_eval(dcr) + [dcr_count, av_clus_size])
+        out_data.append(_parse_dcr(dcr) + [dcr_count, av_clus_size])
 
     if inputargs["barcodeduplication"] == True:  # noqa: E712
         outfile = outpath + file_id + "_barcode_duplication.txt"
