@@ -216,17 +216,14 @@ def _decombine_columns(ctx, buf, off, length, pack_rc, transient=False):
     The records arrive in a page-locked buffer of the context (copies into pageable memory would stall the chunk loop);
     transient: the caller is done with them before the context is used again, so the view itself is returned."""
     try:
-        t0 = time()
-        if len(off) > 1 and bool(np.any(off[1:] < off[:-1])):
-            raise _lib.DcbError("reads are not in text order")
         t1 = time()
-        # the text goes to the GPU as it is, or 2-bit packed by the host threads (dcb_decombine_ascii shares the chunks)
+        # the text goes to the GPU as it is, or 2-bit packed by the host threads (dcb_decombine_ascii shares the chunks; it
+        # refuses offsets that run backwards inside a chunk)
         res, dev_counts = ctx.decombine_ascii(buf, off, length, pack_rc, pinned=True)
         if not transient:
             res = res.copy()
         if os.environ.get("DCB_TIMING"):
-            print("\t[timing]   order check %.3f s, dcb_decombine_ascii %.3f s (chunks packed by host threads / device: %s)"
-                  % (t1 - t0, time() - t1, ctx.last_pack_shares()))
+            print("\t[timing]   dcb_decombine_ascii %.3f s (chunks packed by host threads / device: %s)" % (time() - t1, ctx.last_pack_shares()))
     except _lib.DcbError:
         # reads out of text order, or more non-ACGT symbols than the device-side list holds: pack on the host threads
         packed = _lib.pack_arrays(buf, off, length, revcomp=pack_rc)
@@ -362,17 +359,27 @@ def decombinator(inputargs: dict) -> list:
             from .parallel import shard_bounds
             batch = batch.shard(*shard_bounds(len(batch), *inputargs["shard"]))
         n = len(batch)
+        bc_n = None
         if inputargs["allowNs"] == False:  # noqa: E712
-            counts["dcrfilter_barcodeN"] += fastq.count_containing(batch.bc, "N")
-            if counts["dcrfilter_barcodeN"] == 0:
-                del counts["dcrfilter_barcodeN"]
+            # barcodes with an N are counted beside the GPU pass (another file's text, the native scan releases the GIL)
+            import threading
+            box = []
+            bc_n = threading.Thread(target=lambda: box.append(fastq.count_containing(batch.bc, "N")))
+            bc_n.start()
         counts["read_count"] += n
         if inputargs["dontcount"] == False:  # noqa: E712
             for k in range(100000, n + 1, 100000):
                 print("\t read", k)
-        _lap("barcode N count")
-        res = decombine_batch(batch, inputargs) if n else np.zeros(0, dtype=_lib.RESULT_DTYPE)
-        _lap("text -> GPU -> records")
+        try:
+            res = decombine_batch(batch, inputargs) if n else np.zeros(0, dtype=_lib.RESULT_DTYPE)
+        finally:
+            if bc_n is not None:
+                bc_n.join()
+        if bc_n is not None:
+            counts["dcrfilter_barcodeN"] += box[0] if box else fastq.count_containing(batch.bc, "N")
+            if counts["dcrfilter_barcodeN"] == 0:
+                del counts["dcrfilter_barcodeN"]
+        _lap("text -> GPU -> records (+ barcode N count)")
         pack_rc, _ = _orientation_plan(inputargs["orientation"])
         text_only = bool(inputargs.get("rows_as_text")) and isinstance(batch.vdj, fastq.TextColumn) and not inputargs.get("rows_as_columns")
         # (the `decombine` command needs the number of hits, not their indices: the formatter walks the records itself)
