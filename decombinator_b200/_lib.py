@@ -96,6 +96,10 @@ def lib():
     L.dcb_format_collapse_rows.argtypes = [vp, u64, i32] + [ctypes.POINTER(CColumn)] * 3 + [i32, ctypes.POINTER(ctypes.c_void_p),
                                            ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
     L.dcb_format_collapse_rows.restype = ctypes.c_int
+    L.dcb_n12_index.argtypes = [vp, u64, i32, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(u64)]
+    L.dcb_n12_index.restype = ctypes.c_int
+    L.dcb_n12_collapse_rows.argtypes = [vp, vp, vp, u64, vp, i32, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(u64), ctypes.POINTER(u64)]
+    L.dcb_n12_collapse_rows.restype = ctypes.c_int
     L.dcb_pack_reads.argtypes = [vp, vp, vp, u64, i32, i32, ctypes.POINTER(ctypes.POINTER(CPacked))]
     L.dcb_packed_free.argtypes = [ctypes.POINTER(CPacked)]
     L.dcb_pack_words.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32,
@@ -360,6 +364,36 @@ def format_collapse_rows(res, packed_revcomp, columns, n_threads=None):
     nt = n_threads or min(32, os.cpu_count() or 1)
     _check(lib().dcb_format_collapse_rows(res.ctypes.data, len(res), int(bool(packed_revcomp)), *cols, nt,
                                           ctypes.byref(out), ctypes.byref(nbytes), ctypes.byref(nrows)), "dcb_format_collapse_rows")
+    return NativeText(out.value, nbytes.value), int(nrows.value)
+
+
+def n12_index(text, n_threads=None):
+    """dcb_n12_index: (off, len) arrays of shape (rows, 10) over an .n12 text (uint8 array), or None when the text is not ten
+    ", "-joined fields per row."""
+    off, ln, n = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_uint64(0)
+    _check(lib().dcb_n12_index(text.ctypes.data, len(text), n_threads or min(32, os.cpu_count() or 1), ctypes.byref(off), ctypes.byref(ln),
+                               ctypes.byref(n)), "dcb_n12_index")
+    if n.value == 0:
+        return None
+    try:
+        o = np.ctypeslib.as_array(ctypes.cast(off, ctypes.POINTER(ctypes.c_uint64)), shape=(n.value * 10,)).reshape(n.value, 10).copy()
+        l = np.ctypeslib.as_array(ctypes.cast(ln, ctypes.POINTER(ctypes.c_uint32)), shape=(n.value * 10,)).reshape(n.value, 10).copy()
+    finally:
+        lib().dcb_buffer_free(off)
+        lib().dcb_buffer_free(ln)
+    return o, l
+
+
+def n12_collapse_rows(text, off, ln, keep, n_threads=None):
+    """dcb_n12_collapse_rows -> (NativeText, rows) or None when a field cannot be written the way str() writes it."""
+    off, ln = np.ascontiguousarray(off, dtype=np.uint64), np.ascontiguousarray(ln, dtype=np.uint32)
+    keep = np.ascontiguousarray(keep, dtype=np.uint8)
+    out, nbytes, nrows = ctypes.c_void_p(), ctypes.c_uint64(), ctypes.c_uint64()
+    _check(lib().dcb_n12_collapse_rows(text.ctypes.data, off.ctypes.data, ln.ctypes.data, len(off), keep.ctypes.data,
+                                       n_threads or min(32, os.cpu_count() or 1), ctypes.byref(out), ctypes.byref(nbytes),
+                                       ctypes.byref(nrows)), "dcb_n12_collapse_rows")
+    if nrows.value == 0xFFFFFFFFFFFFFFFF:
+        return None
     return NativeText(out.value, nbytes.value), int(nrows.value)
 
 

@@ -395,6 +395,52 @@ def _count_device_barcodes(status, n1):
             counts[key] += int(k)
 
 
+class N12Columns:
+    """The rows of an .n12 FILE kept columnar (the `collapse` command's input, collapse.py:523-530): the text as one uint8
+    array plus the (offset, length) of the ten fields of every row (dcb_n12_index).  Same protocol as
+    decombine.RowsColumns: the barcode regions go to the device as columns into the text, the three strings collapse
+    files a row under come from dcb_n12_collapse_rows, Python rows are only made for the rows the kernel hands back."""
+
+    def __init__(self, text, off, ln):
+        self.text, self.off, self.len = text, off, ln
+
+    @classmethod
+    def from_file(cls, path, opener):
+        """None when the file is not plain ten-field ", "-joined ASCII rows ending in a newline (the caller then reads
+        it line by line as the reference does)."""
+        with opener(path, "rb") as handle:
+            raw = handle.read()
+        text = np.frombuffer(raw, dtype=np.uint8)
+        if len(text) == 0 or bool((text >= 128).any()):
+            return None
+        index = _lib.n12_index(text)
+        return None if index is None else cls(text, index[0], index[1])
+
+    def __len__(self):
+        return int(len(self.off))
+
+    def barcode_columns(self):
+        return (self.text, self.off[:, 8], self.len[:, 8], self.text, self.off[:, 9], self.len[:, 9])
+
+    def subset_rows(self, keep):
+        t, off, ln = self.text, self.off, self.len
+        out = []
+        for i in np.nonzero(keep)[0].tolist():
+            a, b = int(off[i, 0]), int(off[i, 9]) + int(ln[i, 9])
+            out.append(t[a:b].tobytes().decode("ascii").split(", "))
+        return out
+
+    def collapse_lines(self, keep):
+        got = _lib.n12_collapse_rows(self.text, self.off, self.len, keep)
+        if got is None:                                  # a quote or a backslash in a field: str() decides how it is written
+            rows = self.subset_rows(keep)
+            dcrs = [str(r[:5]) for r in rows]
+            return [r[6] for r in rows], dcrs, ["|".join((d, r[6], r[7], r[5])) for d, r in zip(dcrs, rows)]
+        blob, n = got
+        lines = blob.tobytes().decode("ascii").split("\n")
+        return lines[0:3 * n:3], lines[1:3 * n:3], lines[2:3 * n:3]
+
+
 def _filter_columns(data, inputargs, barcode_quality_parameters, first_index=0):
     """_filter_rows for the columnar hand-over of `pipeline` (decombine.RowsColumns): the barcode regions and their
     qualities go to the device as (offset, length) columns into the FASTQ text -- no Python string per row -- and rows
@@ -403,12 +449,7 @@ def _filter_columns(data, inputargs, barcode_quality_parameters, first_index=0):
     name = inputargs["oligo"].lower()
     if name not in _lib.OLIGOS_ON_DEVICE or inputargs["sampling_analysis"] or "allowNs" not in inputargs or len(data) == 0:
         return None
-    ids, vdj, qual, bc, bcq, _ = data.columns
-    hits = data.hits
-    bbuf = np.frombuffer(bc.buf, dtype=np.uint8)
-    qbuf = np.frombuffer(bcq.buf, dtype=np.uint8)
-    status, n1, code = _gpu().barcodes_arrays(bbuf, np.asarray(bc.off)[hits], np.asarray(bc.len)[hits], qbuf, np.asarray(bcq.off)[hits],
-                                              np.asarray(bcq.len)[hits], _lib.OLIGOS_ON_DEVICE[name], inputargs["allowNs"] != False,  # noqa: E712
+    status, n1, code = _gpu().barcodes_arrays(*data.barcode_columns(), _lib.OLIGOS_ON_DEVICE[name], inputargs["allowNs"] != False,  # noqa: E712
                                               *barcode_quality_parameters)
     _count_device_barcodes(status, n1)
     ok, host = status == _lib.BC_OK, status == _lib.BC_HOST
@@ -549,13 +590,16 @@ def read_in_data(data, inputargs, barcode_quality_parameters, lev_threshold_frac
                 print("Please check that file contains suitable Decombinator output for collapsing.")
                 print("Alternatively, disable the input file sanity check by changing the 'dontcheckinput' flag, i.e. '-di True'")
                 sys.exit()
-        data = opener(data, "rt")
+        columns = None
+        if inputargs["oligo"].lower() in _lib.OLIGOS_ON_DEVICE and not inputargs["sampling_analysis"] and "allowNs" in inputargs:
+            columns = N12Columns.from_file(data, opener)
+        data = columns if columns is not None and len(columns) else opener(data, "rt")
     if not data:
         raise ValueError("No reads found in input file. Check .n12 and log files for errors.")
 
     print("Reading data in...")
     t0 = time.time()
-    from_file = inputargs["command"] == "collapse"
+    from_file = inputargs["command"] == "collapse" and not isinstance(data, N12Columns)
     kept, input_dcr_counts, n_lines = _filter_rows(data, inputargs, barcode_quality_parameters, dont_count, from_file)
     if from_file:
         data.close()

@@ -69,6 +69,13 @@ __attribute__((target("avx2"))) unsigned char scan_lines_avx2(const unsigned cha
     return _mm256_movemask_epi8(acc) != 0 ? 1 : 0;
 }
 #endif
+template <class F>
+void run_threads(int nt, F f) {          // f(t) for t in [0, nt), each on a thread of its own
+    if (nt <= 1) { f(0); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back([=] { f(t); });
+    for (auto& x : th) x.join();
+}
 }  // namespace
 
 extern "C" {
@@ -446,5 +453,127 @@ static int format_impl(const RowCtx& c, const dcb_result* res, uint64_t n, int n
 }
 
 void dcb_buffer_free(char* p) { std::free(p); }
+
+// ------------------------------------------------------------------------------------------------
+// .n12 text (the `collapse` command's input, written by write_out_intermediate, io.py:480-513): where the ten fields
+// of every row are, and the strings collapse files a row under, built from those fields.
+// ------------------------------------------------------------------------------------------------
+/* Index of an .n12 text: rows of exactly ten fields joined by ", ", every row ended by '\n'.  off / len: n_rows x 10,
+ * row-major, malloc'ed (free with dcb_buffer_free).  *n_rows = 0 with DCB_OK when the text is not of that shape (a row
+ * with another number of fields, a missing final newline, a '\r'): the caller splits the lines itself. */
+int dcb_n12_index(const char* text, uint64_t n_bytes, int n_threads, uint64_t** off_out, uint32_t** len_out, uint64_t* n_rows) {
+    if (!off_out || !len_out || !n_rows || (n_bytes && !text)) { dcb_set_error("dcb_n12_index: null argument"); return DCB_EINVAL; }
+    *off_out = nullptr; *len_out = nullptr; *n_rows = 0;
+    if (n_bytes == 0 || text[n_bytes - 1] != '\n') return DCB_OK;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 64) n_threads = 64;
+    if (n_bytes < 65536) n_threads = 1;
+    // thread t owns the rows that START in its byte range; a range begins at the first row start at or behind its nominal start
+    std::vector<uint64_t> cut(n_threads + 1, n_bytes);
+    cut[0] = 0;
+    for (int t = 1; t < n_threads; t++) {
+        uint64_t p = n_bytes * (uint64_t)t / n_threads;
+        const char* q = (const char*)std::memchr(text + p, '\n', (size_t)(n_bytes - p));
+        cut[t] = q ? (uint64_t)(q - text) + 1 : n_bytes;
+    }
+    std::vector<std::vector<uint64_t>> offs(n_threads);
+    std::vector<std::vector<uint32_t>> lens(n_threads);
+    std::vector<int> bad(n_threads, 0);
+    run_threads(n_threads, [&](int t) {
+        {
+            std::vector<uint64_t>& o = offs[t];
+            std::vector<uint32_t>& l = lens[t];
+            uint64_t p = cut[t];
+            const uint64_t end = cut[t + 1];
+            o.reserve((size_t)((end - p) / 400 + 16) * 10); l.reserve((size_t)((end - p) / 400 + 16) * 10);
+            while (p < end) {
+                const char* nl = (const char*)std::memchr(text + p, '\n', (size_t)(n_bytes - p));
+                const uint64_t e = (uint64_t)(nl - text);                       // the text ends with '\n': nl is never null
+                int nf = 0;
+                uint64_t f = p;
+                for (uint64_t i = p; i + 1 < e && nf < 11; i++)
+                    if (text[i] == ',' && text[i + 1] == ' ') { if (nf < 10) { o.push_back(f); l.push_back((uint32_t)(i - f)); } nf++; f = i + 2; i++; }
+                if (nf != 9 || e - f > 0xFFFFFFFFull || std::memchr(text + p, '\r', (size_t)(e - p))) { bad[t] = 1; return; }
+                o.push_back(f); l.push_back((uint32_t)(e - f));
+                p = e + 1;
+            }
+        }
+    });
+    uint64_t total = 0;
+    for (int t = 0; t < n_threads; t++) { if (bad[t]) return DCB_OK; total += offs[t].size(); }
+    if (total == 0 || total % 10) return DCB_OK;
+    uint64_t* O = (uint64_t*)std::malloc(sizeof(uint64_t) * total);
+    uint32_t* Ln = (uint32_t*)std::malloc(sizeof(uint32_t) * total);
+    if (!O || !Ln) { std::free(O); std::free(Ln); dcb_set_error("dcb_n12_index: out of memory"); return DCB_ENOMEM; }
+    uint64_t at = 0;
+    for (int t = 0; t < n_threads; t++) {
+        if (!offs[t].empty()) {
+            std::memcpy(O + at, offs[t].data(), sizeof(uint64_t) * offs[t].size());
+            std::memcpy(Ln + at, lens[t].data(), sizeof(uint32_t) * lens[t].size());
+        }
+        at += offs[t].size();
+    }
+    *off_out = O; *len_out = Ln; *n_rows = total / 10;
+    return DCB_OK;
+}
+
+/* The same three lines per row as dcb_format_collapse_rows, for the rows of an .n12 text selected by keep[i] != 0:
+ * tcrseq (field 6); "['f0', 'f1', 'f2', 'f3', 'f4']" (str(row[:5]) -- fields with a quote or a backslash cannot be
+ * written that way: *n_rows = UINT64_MAX, the caller builds the strings itself); that + "|" + field 6 + "|" + field 7 + "|" + field 5. */
+int dcb_n12_collapse_rows(const char* text, const uint64_t* off, const uint32_t* len, uint64_t n, const uint8_t* keep, int n_threads,
+                          char** out, uint64_t* out_bytes, uint64_t* n_rows) {
+    if (!out || !out_bytes || !n_rows || (n && (!text || !off || !len || !keep))) { dcb_set_error("dcb_n12_collapse_rows: null argument"); return DCB_EINVAL; }
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 64) n_threads = 64;
+    const int nt = n < 4096 ? 1 : n_threads;
+    std::vector<uint64_t> bytes(nt + 1, 0), rows(nt + 1, 0);
+    std::vector<int> odd(nt, 0);
+    auto range = [&](int t, uint64_t& a, uint64_t& b) { a = n * (uint64_t)t / nt; b = n * (uint64_t)(t + 1) / nt; };
+    auto dcr_len = [&](uint64_t i) { size_t s = 20; for (int k = 0; k < 5; k++) s += len[10 * i + k]; return s; };
+    run_threads(nt, [&](int t) {
+        {
+            uint64_t a, b, sz = 0, nr = 0;
+            range(t, a, b);
+            for (uint64_t i = a; i < b; i++) {
+                if (!keep[i]) continue;
+                for (int k = 0; k < 5; k++) {
+                    const char* f = text + off[10 * i + k];
+                    for (uint32_t c = 0; c < len[10 * i + k]; c++) if (f[c] == '\'' || f[c] == '\\' || f[c] == '\n' || (unsigned char)f[c] < 32) odd[t] = 1;
+                }
+                const size_t d = dcr_len(i), sq = len[10 * i + 6];
+                sz += sq + 1 + d + 1 + d + 1 + sq + 1 + len[10 * i + 7] + 1 + len[10 * i + 5] + 1;
+                nr++;
+            }
+            bytes[t + 1] = sz; rows[t + 1] = nr;
+        }
+    });
+    for (int t = 0; t < nt; t++) { if (odd[t]) { *out = nullptr; *out_bytes = 0; *n_rows = ~0ull; return DCB_OK; } bytes[t + 1] += bytes[t]; rows[t + 1] += rows[t]; }
+    char* buf = (char*)std::malloc(bytes[nt] + 1);
+    if (!buf) { dcb_set_error("dcb_n12_collapse_rows: out of memory"); return DCB_ENOMEM; }
+    run_threads(nt, [&](int t) {
+        {
+            uint64_t a, b;
+            range(t, a, b);
+            char* p = buf + bytes[t];
+            for (uint64_t i = a; i < b; i++) {
+                if (!keep[i]) continue;
+                auto field = [&](int k) { std::memcpy(p, text + off[10 * i + k], len[10 * i + k]); p += len[10 * i + k]; };
+                auto lit = [&](const char* s, size_t l) { std::memcpy(p, s, l); p += l; };
+                field(6); *p++ = '\n';
+                char* const dcr_at = p;
+                lit("['", 2);
+                for (int k = 0; k < 5; k++) { field(k); if (k < 4) lit("', '", 4); }
+                lit("']", 2);
+                const size_t d = (size_t)(p - dcr_at);
+                *p++ = '\n';
+                std::memcpy(p, dcr_at, d); p += d; *p++ = '|';
+                field(6); *p++ = '|'; field(7); *p++ = '|'; field(5); *p++ = '\n';
+            }
+        }
+    });
+    buf[bytes[nt]] = 0;
+    *out = buf; *out_bytes = bytes[nt]; *n_rows = rows[nt];
+    return DCB_OK;
+}
 
 }  // extern "C"

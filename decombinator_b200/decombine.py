@@ -152,6 +152,13 @@ class RowsColumns:
             self._text = _lib.format_rows(self.res, self.pack_rc, self.columns, ", ")[0]
         return self._text
 
+    def barcode_columns(self):
+        """(text, offsets, lengths) of the barcode regions and of their qualities, one entry per hit (dcb_barcodes' input)."""
+        _, _, _, bc, bcq, _ = self.columns
+        hits = self.hits
+        return (np.frombuffer(bc.buf, dtype=np.uint8), np.asarray(bc.off)[hits], np.asarray(bc.len)[hits],
+                np.frombuffer(bcq.buf, dtype=np.uint8), np.asarray(bcq.off)[hits], np.asarray(bcq.len)[hits])
+
     def subset_rows(self, keep):
         """list[list[str]] of the hits selected by the boolean mask `keep` (over the hits), in order."""
         res = self.res

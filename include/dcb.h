@@ -188,6 +188,14 @@ int dcb_format_rows(const dcb_result* res, uint64_t n, int packed_revcomp, const
  * per row -- tcrseq; str(row[:5]), i.e. "['v', 'j', 'vdel', 'jdel', 'insert']"; and "|".join((that, tcrseq, tcrQ, read id)). */
 int dcb_format_collapse_rows(const dcb_result* res, uint64_t n, int packed_revcomp, const dcb_column* ids, const dcb_column* vdj,
                              const dcb_column* vdjqual, int n_threads, char** out, uint64_t* out_bytes, uint64_t* n_rows);
+/* The `collapse` command's input: index of an .n12 text (ten fields per row joined by ", ", as write_out_intermediate
+ * writes them, io.py:480-513) -- off / len are n_rows x 10, row-major, malloc'ed (dcb_buffer_free); *n_rows = 0 when the
+ * text is not of that shape (the caller then splits the lines as the reference does, collapse.py:523-530) -- and the
+ * three lines of dcb_format_collapse_rows built from the fields of the rows with keep[i] != 0 (*n_rows = UINT64_MAX:
+ * a field holds a quote or a backslash, str() would write it differently; the caller builds the strings itself). */
+int dcb_n12_index(const char* text, uint64_t n_bytes, int n_threads, uint64_t** off, uint32_t** len, uint64_t* n_rows);
+int dcb_n12_collapse_rows(const char* text, const uint64_t* off, const uint32_t* len, uint64_t n, const uint8_t* keep, int n_threads,
+                          char** out, uint64_t* out_bytes, uint64_t* n_rows);
 void dcb_buffer_free(char*);
 
 

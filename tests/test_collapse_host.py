@@ -133,6 +133,41 @@ def test_barcode_positions_known_answers():
         assert collapse.findFirstSpacer({"spcr1": spacer}, seq, lo, hi) == [spacer]
 
 
+def test_n12_index_and_collapse_lines_equal_the_split_lines(golden_dir, tmp_path):
+    """dcb_n12_index / dcb_n12_collapse_rows (host code) against the reference's own parsing of an .n12 file
+    (collapse.py:523-530: line.rstrip("\\n").split(", "); :565-590: str(row[:5]), "|".join(...))."""
+    for name in ("alpha", "beta"):
+        raw = open(os.path.join(golden_dir, "dcr_TINY_1_%s.n12" % name), "rb").read()
+        rows = [line.rstrip("\n").split(", ") for line in raw.decode().splitlines(True)]
+        cols = collapse.N12Columns.from_file(os.path.join(golden_dir, "dcr_TINY_1_%s.n12" % name), open)
+        assert len(cols) == len(rows)
+        keep = np.arange(len(rows)) % 3 != 1
+        assert cols.subset_rows(keep) == [r for r, k in zip(rows, keep) if k]
+        seqs, dcrs, etcs = cols.collapse_lines(keep)
+        want = [r for r, k in zip(rows, keep) if k]
+        assert seqs == [r[6] for r in want] and dcrs == [str(r[:5]) for r in want]
+        assert etcs == ["|".join((str(r[:5]), r[6], r[7], r[5])) for r in want]
+        # many rows: every thread's share, cut at row starts
+        big = raw * 400
+        text = np.frombuffer(big, dtype=np.uint8)
+        off, ln = _lib.n12_index(text, n_threads=7)
+        assert len(off) == 400 * len(rows)
+        flat = [big[int(o):int(o) + int(l)].decode() for o, l in zip(off[-len(rows):].ravel(), ln[-len(rows):].ravel())]
+        assert flat == [f for r in rows for f in r]
+    # texts the index declines (the caller then reads the lines as the reference does)
+    one = b"1, 2, 3, 4, ACGT, id, ACGT, IIII, ACGT, IIII\n"
+    assert _lib.n12_index(np.frombuffer(one[:-1], dtype=np.uint8)) is None                       # no final newline
+    assert _lib.n12_index(np.frombuffer(one + b"1, 2, 3\n", dtype=np.uint8)) is None              # a short row
+    assert _lib.n12_index(np.frombuffer(one.replace(b"\n", b"\r\n"), dtype=np.uint8)) is None    # carriage returns
+    quoted = one.replace(b"ACGT, id", b"AC'T, id")
+    off, ln = _lib.n12_index(np.frombuffer(quoted, dtype=np.uint8))
+    assert _lib.n12_collapse_rows(np.frombuffer(quoted, dtype=np.uint8), off, ln, np.ones(1, dtype=bool)) is None
+    p = tmp_path / "q.n12"
+    p.write_bytes(quoted)
+    seqs, dcrs, etcs = collapse.N12Columns.from_file(str(p), open).collapse_lines(np.ones(1, dtype=bool))
+    assert dcrs == [str(["1", "2", "3", "4", "AC'T"])]
+
+
 def test_empty_n12_raises(tmp_path):
     p = tmp_path / "empty.n12"
     p.write_text("")
