@@ -26,12 +26,16 @@ import refenv  # noqa: E402
 from decombinator_b200 import _lib, tags as dtags  # noqa: E402
 
 
-def make_rows(ref, species, tagset, chain, n, pool, L, sub1, sub2, seed, oligo):
+def make_rows(ref, species, tagset, chain, n, pool, L, sub1, sub2, seed, oligo, r2_layout=None, n1_at=22):
+    """r2_layout(read 2 as the generator wrote it: M13 spacer, N6, I8 spacer, N6, ...) -> read 2 of another oligo design
+    (make_golden_collapse_oligos.py); n1_at: where that design's first random hexamer starts."""
     info = dtags.load(species, tagset, chain)
     syn = _lib.Synth([(info.v_regions, info.j_regions)], seed, L, L, sub1, 0.0, 0.02, umi_pool=pool, sub_rate2=sub2)
     r1, r2 = syn.reads(0, n, want_r2=True)
     a = [bytes(r1[i * L:(i + 1) * L]).decode() for i in range(n)]
     b = [bytes(r2[i * L:(i + 1) * L]).decode() for i in range(n)]
+    if r2_layout is not None:
+        b = [r2_layout(x) for x in b]
     rng = random.Random(seed)
     order = list(range(n))
     rng.shuffle(order)
@@ -43,13 +47,13 @@ def make_rows(ref, species, tagset, chain, n, pool, L, sub1, sub2, seed, oligo):
         q = ["I"] * L
         r = rng.random()
         if r < 0.03:
-            b[i] = b[i][:24] + b[i][25:] + "A"          # N1 of 5 bases
+            b[i] = b[i][:n1_at + 2] + b[i][n1_at + 3:] + "A"          # N1 of 5 bases
         elif r < 0.06:
-            b[i] = b[i][:24] + "C" + b[i][24:-1]        # N1 of 7 bases
+            b[i] = b[i][:n1_at + 2] + "C" + b[i][n1_at + 2:-1]        # N1 of 7 bases
         elif r < 0.08:
-            b[i] = b[i][:30] + "N" + b[i][31:]
+            b[i] = b[i][:n1_at + 8] + "N" + b[i][n1_at + 9:]
         elif r < 0.12:
-            for k in rng.sample(range(22, 42), 3):
+            for k in rng.sample(range(n1_at, n1_at + 20), 3):
                 q[k] = "#"
         elif r < 0.15 and i > 10:
             b[i] = b[rng.randrange(0, i)]               # barcode collision with an unrelated molecule
@@ -69,6 +73,36 @@ def make_rows(ref, species, tagset, chain, n, pool, L, sub1, sub2, seed, oligo):
     return rows, args
 
 
+def record_case(C, rows, args, extra, label):
+    """One recorded run of the reference's collapse stage over `rows`: every intermediate and the .freq rows."""
+    args = dict(args)
+    args.update(extra)
+    # the stages separately (what the reference's own unit tests call) ...
+    C.counts = coll.Counter()
+    qp = [args["minbcQ"], args["bcQbelowmin"], args["avgQthreshold"]]
+    frac = args["percentlevdist"] / 100
+    groups = C.read_in_data([list(r) for r in rows], args, qp, frac, True, open)
+    read_counts = {k: v for k, v in sorted(C.counts.items()) if not k.startswith("time_") and isinstance(v, int)}
+    group_keys = list(groups.keys())
+    group_sizes = [len(v) for v in groups.values()]
+    _, blist, umi_proto = C.create_clustering_objs(groups)
+    matches = C.make_merge_groups(umi_proto, args["bcthreshold"], True)
+    pairs = [[int(i), int(j)] for i, j in zip(matches.row, matches.col)]
+    protos = [k.split("|")[2] for k in group_keys]
+    verdicts = [bool(C.are_seqs_equivalent(protos[i], protos[j], frac)) for i, j in pairs]
+    clusters = C.make_clusters(matches, blist, frac)
+    cluster_keys = list(clusters.keys())
+    cluster_sizes = [len(v) for v in clusters.values()]
+    # ... and the whole stage
+    out = C.collapsinator(dict(args), data=[list(r) for r in rows])
+    print("case", *label, "rows", len(rows), "groups", len(group_keys), "pairs", len(pairs),
+          "merged", sum(verdicts), "clusters", len(cluster_keys), "out", len(out))
+    return {"args": {k: v for k, v in args.items() if k != "tagfastadir"}, "rows": rows,
+            "group_keys": group_keys, "group_sizes": group_sizes, "umis": [u for u, _ in umi_proto],
+            "pairs": pairs, "verdicts": verdicts, "cluster_keys": cluster_keys, "cluster_sizes": cluster_sizes,
+            "freq": out, "counts_read_in_data": read_counts}
+
+
 def main():
     ref = refenv.load()
     C = ref["collapse"]
@@ -86,31 +120,7 @@ def main():
         ]
         for ci, (species, tagset, chain, n, pool, L, sub1, sub2, extra) in enumerate(spec):
             rows, args = make_rows(ref, species, tagset, chain, n, pool, L, sub1, sub2, 20260300 + ci, "M13")
-            args = dict(args)
-            args.update(extra)
-            # the stages separately (what the reference's own unit tests call) ...
-            C.counts = coll.Counter()
-            qp = [args["minbcQ"], args["bcQbelowmin"], args["avgQthreshold"]]
-            frac = args["percentlevdist"] / 100
-            groups = C.read_in_data([list(r) for r in rows], args, qp, frac, True, open)
-            group_keys = list(groups.keys())
-            group_sizes = [len(v) for v in groups.values()]
-            _, blist, umi_proto = C.create_clustering_objs(groups)
-            matches = C.make_merge_groups(umi_proto, args["bcthreshold"], True)
-            pairs = [[int(i), int(j)] for i, j in zip(matches.row, matches.col)]
-            protos = [k.split("|")[2] for k in group_keys]
-            verdicts = [bool(C.are_seqs_equivalent(protos[i], protos[j], frac)) for i, j in pairs]
-            clusters = C.make_clusters(matches, blist, frac)
-            cluster_keys = list(clusters.keys())
-            cluster_sizes = [len(v) for v in clusters.values()]
-            # ... and the whole stage
-            out = C.collapsinator(dict(args), data=[list(r) for r in rows])
-            print("case", ci, species, tagset, chain, "rows", len(rows), "groups", len(group_keys), "pairs", len(pairs),
-                  "merged", sum(verdicts), "clusters", len(cluster_keys), "out", len(out))
-            cases.append({"args": {k: v for k, v in args.items() if k != "tagfastadir"}, "rows": rows,
-                          "group_keys": group_keys, "group_sizes": group_sizes, "umis": [u for u, _ in umi_proto],
-                          "pairs": pairs, "verdicts": verdicts, "cluster_keys": cluster_keys, "cluster_sizes": cluster_sizes,
-                          "freq": out})
+            cases.append(record_case(C, rows, args, extra, (ci, species, tagset, chain)))
     finally:
         os.chdir(cwd)
     # distance known answers: random sequence pairs with the stand-in polyleven (checked against the reference's

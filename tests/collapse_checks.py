@@ -14,6 +14,9 @@ def check_case(case):
     qp = [args["minbcQ"], args["bcQbelowmin"], args["avgQthreshold"]]
     frac = args["percentlevdist"] / 100
     groups = collapse.read_in_data([list(r) for r in rows], args, qp, frac, True, open)
+    if "counts_read_in_data" in case:                 # the reference's counters after read_in_data (barcode location, filters)
+        got = {k: v for k, v in sorted(collapse.counts.items()) if not k.startswith("time_") and isinstance(v, int)}
+        assert got == case["counts_read_in_data"]
     assert list(groups.keys()) == case["group_keys"]
     assert [len(v) for v in groups.values()] == case["group_sizes"]
     _, blist, umi_proto = collapse.create_clustering_objs(groups)

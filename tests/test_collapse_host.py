@@ -98,6 +98,20 @@ def test_device_levenshtein_code_on_arbitrary_bytes():
     assert sym.max() <= 7
 
 
+@pytest.fixture(scope="module")
+def oligo_cases(golden_dir):
+    """Runs of the unmodified reference for the oligo designs beside M13 (oracle/make_golden_collapse_oligos.py)."""
+    with gzip.open(os.path.join(golden_dir, "collapse_cases_oligos.json.gz"), "rt") as fh:
+        return json.load(fh)
+
+
+def test_host_logic_matches_reference_runs_other_oligos(oligo_cases, oracle_distances):
+    """I8 (two cases), I8_single, NEBIO, TAKARA: groups, UMI pairs, clusters, .freq rows and the counters of read_in_data."""
+    assert [c["args"]["oligo"] for c in oligo_cases["cases"]] == ["I8", "I8", "I8_single", "NEBIO", "TAKARA"]
+    for case in oligo_cases["cases"]:
+        collapse_checks.check_case(case)
+
+
 def test_host_logic_matches_reference_runs(collapse_cases, oracle_distances):
     for case in collapse_cases["cases"]:
         collapse_checks.check_case(case)
