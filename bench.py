@@ -534,8 +534,9 @@ def main():
                     "h2d_bytes_per_step": int(n * (READ_LEN * device_chunks + slot_bytes * host_chunks) / max(1, host_chunks + device_chunks)),
                     "d2h_bytes_per_step": int(n * 16 + 8 * _lib.NCOUNTERS), "steps": e2e_steps,
                     "call": "dcb_decombine_ascii: ASCII reads in page-locked host memory in (the reference arm's input), result records in "
-                            "host memory out; chunks of clean reads are packed by the device (the text crosses the link) or, while the "
-                            "copy engine is busy, by the host threads (a quarter of the bytes crosses) -- one rank per host only",
+                            "host memory out; the chunks are shared from both ends -- the device packs chunks from the front (their text crosses "
+                            "the link), a worker with the host threads packs chunks of clean reads from the back (AVX-512, a quarter of the "
+                            "bytes crosses) until the two meet -- one rank per host only",
                     "chunks_packed_by": {"host_threads": host_chunks, "device": device_chunks, "rank": 0},
                     "device_packed_only": {"value": e2e_dev, "unit": UNIT, "h2d_bytes_per_step": int(n * READ_LEN),
                                            "how": "DCB_HOST_SHARE=0: the whole text crosses the link",

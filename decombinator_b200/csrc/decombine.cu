@@ -28,6 +28,8 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -1115,6 +1117,14 @@ struct dcb_ctx {
     cudaEvent_t ev_hw[2] = {nullptr, nullptr}, ev_acopy = nullptr;
     bool acopy_pending = false;
     uint32_t host_chunks = 0, device_chunks = 0;   // of the last dcb_decombine_ascii call
+    // two-ended sharing (ascii_two_ended): the device takes the chunks from the front, a host thread packs chunks from the
+    // back into ONE page-locked region (slot i = the i-th chunk from the end) until the two meet
+    char* hstage = nullptr;
+    size_t hstage_cap = 0;
+    cudaEvent_t ev_text[2] = {nullptr, nullptr};   // the text copy of the last device chunk of each parity
+    cudaStream_t stream3 = nullptr;                // the worker's copies of the chunks it packed
+    std::vector<cudaEvent_t> ev_hcopy;             // one per chunk: its packed words have arrived
+    bool text_pending[2] = {false, false};
     double pack_ms = 0;            // device time of the pack kernels of the last dcb_pack_device call (CUDA events)
     int vgen_words = 0, jgen_words = 0, vcore_words = 0, jcore_words = 0, vidx_words = 0, jidx_words = 0, uidx_words = 0;
     DevBuf words, lens, flags, exc_read, exc_pos, exc_kind, exc_index, results, queue;
@@ -1317,6 +1327,8 @@ dcb_ctx* dcb_ctx_create(int device, const dcb_tagset* v, const dcb_tagset* j, co
             cudaEventCreateWithFlags(&c->ev_stage[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->ev_hw[i], cudaEventDisableTiming) != cudaSuccess) return fail("cudaEventCreate");
     if (cudaEventCreateWithFlags(&c->ev_acopy, cudaEventDisableTiming) != cudaSuccess) return fail("cudaEventCreate");
+    for (int i = 0; i < 2; i++)
+        if (cudaEventCreateWithFlags(&c->ev_text[i], cudaEventDisableTiming) != cudaSuccess) return fail("cudaEventCreate");
     return c;
 }
 
@@ -1342,6 +1354,10 @@ void dcb_ctx_destroy(dcb_ctx* c) {
         if (c->hwords[i]) cudaFreeHost(c->hwords[i]);
     }
     if (c->ev_acopy) cudaEventDestroy(c->ev_acopy);
+    for (int i = 0; i < 2; i++) if (c->ev_text[i]) cudaEventDestroy(c->ev_text[i]);
+    if (c->hstage) cudaFreeHost(c->hstage);
+    if (c->stream3) { cudaStreamSynchronize(c->stream3); cudaStreamDestroy(c->stream3); }
+    for (cudaEvent_t e : c->ev_hcopy) cudaEventDestroy(e);
     c->group_count.release();
     cudaFree(c->d_exc_total);
     delete c;
@@ -1666,6 +1682,8 @@ static int host_threads() {
     return std::max(1, std::min(32, t));
 }
 
+static int submit_host_chunk(dcb_ctx* c, cudaStream_t s, const uint32_t* hw, bool with_lens, uint32_t first, uint32_t count, int chunk_no);
+static int copy_host_chunk(dcb_ctx* c, cudaStream_t s, const uint32_t* hw, bool with_lens, uint32_t first, uint32_t count);
 // The host's share: the chunk's reads packed by the host threads into a page-locked buffer and copied to their slots --
 // a quarter of the text's bytes over the link.  Only for chunks of nothing but A / C / G / T (no exception list to merge:
 // the chunk's groups take part in the running exception index with a count of zero).  1: done, 0: not clean (the caller
@@ -1686,13 +1704,28 @@ static int pack_chunk_host(dcb_ctx* c, cudaStream_t s, int par, const char* asci
     int rc = dcb_pack_words(ascii, off, len, first, count, uniform_len, revcomp, sw, c->hwords[par], host_threads(), &clean);
     if (rc) return rc;
     if (!clean) return 0;
-    CUDA_TRY(cudaMemcpyAsync((uint32_t*)c->words.p + (size_t)first * sw, c->hwords[par], wbytes, cudaMemcpyHostToDevice, s));
     if (len) {
         uint16_t* hl = reinterpret_cast<uint16_t*>(reinterpret_cast<char*>(c->hwords[par]) + wbytes);
         for (uint32_t i = 0; i < count; i++) hl[i] = (uint16_t)len[first + i];
-        CUDA_TRY(cudaMemcpyAsync((uint16_t*)c->lens.p + first, hl, (size_t)count * 2, cudaMemcpyHostToDevice, s));
     }
+    if ((rc = submit_host_chunk(c, s, c->hwords[par], len != nullptr, first, count, chunk_no))) return rc;
     CUDA_TRY(cudaEventRecord(c->ev_hw[par], s));
+    return 1;
+}
+
+// A chunk the host threads packed -- words, then (reads of varying length) the 16-bit lengths behind them, in page-locked
+// memory -- copied to its slots; its groups join the running exception index with a count of zero.
+static int copy_host_chunk(dcb_ctx* c, cudaStream_t s, const uint32_t* hw, bool with_lens, uint32_t first, uint32_t count) {
+    const uint32_t sw = c->batch.slot_words;
+    const size_t wbytes = (size_t)count * sw * 4;
+    CUDA_TRY(cudaMemcpyAsync((uint32_t*)c->words.p + (size_t)first * sw, hw, wbytes, cudaMemcpyHostToDevice, s));
+    if (with_lens)
+        CUDA_TRY(cudaMemcpyAsync((uint16_t*)c->lens.p + first, reinterpret_cast<const char*>(hw) + wbytes, (size_t)count * 2, cudaMemcpyHostToDevice, s));
+    return DCB_OK;
+}
+// hw == nullptr: the words (and lengths) are there already (copy_host_chunk on another stream, which s has been made to wait for)
+static int submit_host_chunk(dcb_ctx* c, cudaStream_t s, const uint32_t* hw, bool with_lens, uint32_t first, uint32_t count, int chunk_no) {
+    if (hw) { const int rc = copy_host_chunk(c, s, hw, with_lens, first, count); if (rc) return rc; }
     const uint32_t groups = (count + 31) / 32;
     CUDA_TRY(cudaMemsetAsync((uint32_t*)c->flags.p + (first >> 5), 0, (size_t)groups * 4, s));
     CUDA_TRY(cudaMemsetAsync((uint32_t*)c->group_count.p + (first >> 5), 0, (size_t)groups * 4, s));
@@ -1700,7 +1733,7 @@ static int pack_chunk_host(dcb_ctx* c, cudaStream_t s, int par, const char* asci
     dcb_pack_scan_kernel<<<1, 1024, 0, s>>>((const uint32_t*)c->group_count.p, first >> 5, groups, (uint32_t*)c->exc_index.p, c->d_exc_total);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev_scan[chunk_no & 1], s));
-    return 1;
+    return DCB_OK;
 }
 
 static int pack_chunk(dcb_ctx* c, cudaStream_t s, int par, const char* ascii, const uint64_t* off, const uint32_t* len,
@@ -1766,6 +1799,8 @@ static int pack_chunk(dcb_ctx* c, cudaStream_t s, int par, const char* ascii, co
         CUDA_TRY(cudaMemcpyAsync(c->text[par].p, ascii + lo, hi - lo, cudaMemcpyHostToDevice, s));
         CUDA_TRY(cudaEventRecord(c->ev_acopy, s));
         c->acopy_pending = true;
+        CUDA_TRY(cudaEventRecord(c->ev_text[par], s));
+        c->text_pending[par] = true;
         src.text = (const unsigned char*)c->text[par].p; src.text_lo = lo;
         if (!contiguous) {
             if ((rc = c->roff[par].ensure((size_t)count * 8 + 16))) return rc;
@@ -1823,6 +1858,132 @@ static int ascii_finish(dcb_ctx* c, size_t exc_cap, uint32_t* n_exc) {
     return DCB_OK;
 }
 
+// Page-locked text, this process alone on its host: the chunks are shared from BOTH ENDS.  The calling thread gives the
+// device the chunks from the front (the text crosses the link, dcb_pack_kernel packs it), never more than two text copies
+// queued; meanwhile one worker packs chunks from the back with the host threads (dcb_pack_words) into a page-locked region.
+// Each packed chunk is copied to its slots at once (a quarter of its text's bytes over the link, between the device's text
+// copies); when the two meet, the host's chunks take their place in the exception index and run their kernels, in index
+// order (the index runs on from chunk to chunk).  Neither side waits for the other until then, so the link never idles while a
+// chunk is being packed and the shares settle at whatever the host's memory system allows.  A chunk in which the worker
+// meets a symbol beyond A / C / G / T ends the host's share: the device packs that chunk and the worker claims no more.
+// The region holds at most DCB_HOST_STAGE_MB (default 1024) of packed reads; the worker stops claiming when it is full.
+static int ascii_two_ended(dcb_ctx* c, const char* ascii, const uint64_t* off, const uint32_t* lens, uint64_t n, uint32_t uniform_len,
+                           int revcomp, dcb_result* out, uint32_t chunk, size_t exc_cap) {
+    cudaStream_t st[2] = {c->stream, c->stream2};
+    const int K = (int)((n + chunk - 1) / chunk);
+    const uint32_t sw = c->batch.slot_words;
+    const size_t slot_bytes = (((size_t)chunk * sw * 4 + (lens ? (size_t)chunk * 2 : 0)) + 255) & ~(size_t)255;
+    size_t budget = (size_t)1024 << 20;
+    if (const char* e = std::getenv("DCB_HOST_STAGE_MB")) budget = (size_t)std::max(0, std::atoi(e)) << 20;
+    const int max_host = (int)std::min<size_t>((size_t)(K - 1), budget / slot_bytes);     // chunk 0 is the device's
+    if (max_host > 0 && c->hstage_cap < (size_t)max_host * slot_bytes) {
+        if (c->hstage) cudaFreeHost(c->hstage);
+        c->hstage = nullptr; c->hstage_cap = 0;
+        if (cudaHostAlloc((void**)&c->hstage, (size_t)max_host * slot_bytes, cudaHostAllocDefault) == cudaSuccess) c->hstage_cap = (size_t)max_host * slot_bytes;
+        else (void)cudaGetLastError();
+    }
+    const int host_cap = c->hstage ? std::min<int>(max_host, (int)(c->hstage_cap / slot_bytes)) : 0;
+    auto slot_of = [&](int k) { return reinterpret_cast<uint32_t*>(c->hstage + (size_t)(K - 1 - k) * slot_bytes); };
+    auto first_of = [&](int k) { return (uint64_t)k * chunk; };
+    auto count_of = [&](int k) { return (uint32_t)std::min<uint64_t>(chunk, n - (uint64_t)k * chunk); };
+
+    std::mutex m;
+    int dev_next = 0, host_lo = K;           // device owns [0, dev_next), host owns [host_lo, K); under m
+    bool host_open = host_cap > 0;
+    std::vector<char> dirty(K, 0);           // host chunks the worker could not pack (device packs them)
+    int worker_rc = DCB_OK;
+    if (!c->stream3 && cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking) != cudaSuccess) { dcb_set_error("cudaStreamCreate failed"); return DCB_ENOGPU; }
+    while ((int)c->ev_hcopy.size() < K) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->ev_hcopy.push_back(e);
+    }
+    CUDA_TRY(cudaStreamWaitEvent(c->stream3, c->ev_ready, 0));
+    std::thread worker([&] {
+        const int nt = std::max(1, host_threads() - 1);
+        if (cudaSetDevice(c->device) != cudaSuccess) { std::lock_guard<std::mutex> g(m); worker_rc = DCB_ENOGPU; host_open = false; return; }
+        for (;;) {
+            int k;
+            {
+                std::lock_guard<std::mutex> g(m);
+                if (!host_open || host_lo - 1 < dev_next || K - host_lo >= host_cap) { host_open = false; return; }
+                k = --host_lo;
+            }
+            const uint32_t count = count_of(k);
+            uint32_t* hw = slot_of(k);
+            int clean = 0;
+            const int rc = dcb_pack_words(ascii, off, lens, first_of(k), count, uniform_len, revcomp, sw, hw, nt, &clean);
+            if (rc || !clean) {
+                std::lock_guard<std::mutex> g(m);
+                if (rc) worker_rc = rc;
+                dirty[k] = 1; host_open = false;
+                return;
+            }
+            if (lens) {
+                uint16_t* hl = reinterpret_cast<uint16_t*>(reinterpret_cast<char*>(hw) + (size_t)count * sw * 4);
+                for (uint32_t i = 0; i < count; i++) hl[i] = (uint16_t)lens[first_of(k) + i];
+            }
+            // the packed words go to their slots right away, between the device's text copies: only the chunk's place in
+            // the exception index and its kernels have to wait for the chunks in front of it
+            int crc = copy_host_chunk(c, c->stream3, hw, lens != nullptr, (uint32_t)first_of(k), count);
+            if (!crc && cudaEventRecord(c->ev_hcopy[k], c->stream3) != cudaSuccess) { dcb_set_error("cudaEventRecord failed"); crc = DCB_ENOGPU; }
+            if (crc) {
+                std::lock_guard<std::mutex> g(m);
+                worker_rc = crc; host_open = false;
+                return;
+            }
+        }
+    });
+    struct Joiner {          // an early return: the worker claims nothing more and is waited for
+        std::thread& t; std::mutex& m; bool& open;
+        ~Joiner() { if (t.joinable()) { { std::lock_guard<std::mutex> g(m); open = false; } t.join(); } }
+    } joiner{worker, m, host_open};
+
+    int rc = DCB_OK;
+    auto device_chunk = [&](int k) -> int {
+        cudaStream_t s = st[k & 1];
+        const uint32_t first = (uint32_t)first_of(k), count = count_of(k);
+        int r;
+        if ((r = pack_chunk(c, s, k & 1, ascii, off, lens, uniform_len, revcomp, first, count, exc_cap, k, false))) return r;
+        c->device_chunks++;
+        if ((r = launch_range(c, s, first, count, k, false))) return r;
+        if (out) CUDA_TRY(cudaMemcpyAsync(out + first, (dcb_result*)c->results.p + first, (size_t)count * sizeof(dcb_result), cudaMemcpyDeviceToHost, s));
+        return DCB_OK;
+    };
+    c->text_pending[0] = c->text_pending[1] = false;
+    int k = 0;
+    for (;; k++) {
+        // at most two text copies queued: the one the copy engine works on and the next
+        if (c->text_pending[k & 1]) {
+            for (;;) {
+                const cudaError_t q = cudaEventQuery(c->ev_text[k & 1]);
+                if (q == cudaSuccess) break;
+                if (q != cudaErrorNotReady) { dcb_set_error("cudaEventQuery failed: %s", cudaGetErrorString(q)); return DCB_ENOGPU; }
+                std::this_thread::sleep_for(std::chrono::microseconds(20));
+            }
+        }
+        {
+            std::lock_guard<std::mutex> g(m);
+            if (k >= host_lo) break;
+            dev_next = k + 1;
+        }
+        if ((rc = device_chunk(k))) return rc;
+    }
+    worker.join();
+    if (worker_rc) return worker_rc;
+    for (; k < K; k++) {                    // the host's chunks, in index order
+        if (dirty[k]) { if ((rc = device_chunk(k))) return rc; continue; }
+        cudaStream_t s = st[k & 1];
+        const uint32_t first = (uint32_t)first_of(k), count = count_of(k);
+        CUDA_TRY(cudaStreamWaitEvent(s, c->ev_hcopy[k], 0));
+        if ((rc = submit_host_chunk(c, s, nullptr, lens != nullptr, first, count, k))) return rc;
+        c->host_chunks++;
+        if ((rc = launch_range(c, s, first, count, k, false))) return rc;
+        if (out) CUDA_TRY(cudaMemcpyAsync(out + first, (dcb_result*)c->results.p + first, (size_t)count * sizeof(dcb_result), cudaMemcpyDeviceToHost, s));
+    }
+    return DCB_OK;
+}
+
 int dcb_decombine_ascii(dcb_ctx* c, const char* ascii, const uint64_t* off, const uint32_t* len, uint64_t n, uint32_t uniform_len,
                         int revcomp, dcb_result* out, uint64_t* counters) {
     size_t exc_cap = 0;
@@ -1852,9 +2013,25 @@ int dcb_decombine_ascii(dcb_ctx* c, const char* ascii, const uint64_t* off, cons
     if (const char* e = std::getenv("DCB_HOST_SHARE")) host_share = std::atoi(e);
     c->host_chunks = c->device_chunks = 0;
     c->acopy_pending = false;
-    bool host_ok = host_share != 0;
+    bool host_ok = host_share != 0, shared = false;
     int k = 0;
-    for (uint64_t first = 0; first < n; first += chunk, k++) {
+    const char* two = std::getenv("DCB_TWO_ENDED");          // 0: the round's earlier scheme (the caller's thread packs; measurements)
+    if (host_share == 1 && !staged && n && !(two && two[0] == '0')) {
+        // smaller chunks: the shares are settled chunk by chunk, and the two sides meet inside one
+        uint32_t fine = kChunkReads / 4;
+        if (const char* e = std::getenv("DCB_CHUNK_READS")) fine = (uint32_t)std::max(1024, std::atoi(e));
+        fine = std::max<uint32_t>(fine, (uint32_t)((n + kMaxChunks - 1) / kMaxChunks));
+        fine = (fine + 1023u) & ~1023u;
+        if ((n + fine - 1) / fine >= 4) {
+            if ((rc = ascii_two_ended(c, ascii, off, lens, n, uniform_len, revcomp, out, fine, exc_cap))) {
+                cudaStreamSynchronize(st[0]); cudaStreamSynchronize(st[1]);
+                if (c->stream3) cudaStreamSynchronize(c->stream3);
+                return rc;
+            }
+            shared = true;
+        }
+    }
+    for (uint64_t first = 0; first < n && !shared; first += chunk, k++) {
         const uint32_t count = (uint32_t)std::min<uint64_t>(chunk, n - first);
         cudaStream_t s = st[k & 1];
         bool by_host = false;

@@ -122,6 +122,94 @@ __attribute__((target("avx2"))) inline bool pack_read_avx2(const unsigned char* 
     for (size_t k = (size_t)(i >> 4); k < sw; k++) w[k] = 0;
     return _mm256_testz_si256(bad, bad) != 0;
 }
+// The same with AVX-512 (VBMI for the byte reversal): 64 bases -> 128 packed bits per step.  bad: bit k set <=> symbol k of
+// some block was not A / C / G / T.
+#define DCB_AVX512 __attribute__((target("avx512f,avx512bw,avx512vbmi,avx512vl")))
+const bool kAvx512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vbmi") &&
+                     __builtin_cpu_supports("avx512vl") && !std::getenv("DCB_NO_AVX512");
+// How a packed slot is written: 2 = assembled in a local buffer, then streaming stores (measured on the GPU box with the
+// copy engine reading the same memory: dcb_decombine_ascii with every chunk packed by the host 271 -> 307 M reads/s, shared
+// with the device 345 -> 354); 0 = stored directly, 1 = local buffer and ordinary stores (DCB_PACK_STORE, measurements).
+const int kPackStore = std::getenv("DCB_PACK_STORE") ? std::atoi(std::getenv("DCB_PACK_STORE")) : 2;
+DCB_AVX512 inline __m128i pack64_avx512(__m512i v, bool comp, __mmask64& bad) {
+    const __m512i self = _mm512_broadcast_i32x4(_mm_setr_epi8(-1, 'A', -1, 'C', 'T', -1, -1, 'G', -1, -1, -1, -1, -1, -1, -1, -1));
+    const __m512i three = _mm512_set1_epi8(3);
+    // a symbol whose low nibble names one of the four and that IS that one (bytes >= 0x80 shuffle to 0 and differ)
+    bad |= _mm512_cmpneq_epi8_mask(_mm512_shuffle_epi8(self, _mm512_and_si512(v, _mm512_set1_epi8(0x0F))), v);
+    __m512i c = _mm512_and_si512(_mm512_xor_si512(_mm512_srli_epi16(v, 1), _mm512_srli_epi16(v, 2)), three);
+    if (comp) c = _mm512_xor_si512(c, three);
+    const __m512i p16 = _mm512_maddubs_epi16(c, _mm512_set1_epi16(0x0401));
+    const __m512i p32 = _mm512_madd_epi16(p16, _mm512_set1_epi32(0x00100001));
+    return _mm512_cvtepi32_epi8(p32);                    // the low byte of every 32-bit lane: four bases each
+}
+DCB_AVX512 inline bool pack_read_avx512(const unsigned char* s, uint32_t L, bool revcomp, uint32_t* w, size_t sw) {
+    const __m512i flip = _mm512_set_epi8(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31,
+                                         32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48, 49, 50, 51, 52, 53, 54, 55, 56, 57, 58, 59, 60, 61, 62, 63);
+    __mmask64 bad = 0;
+    uint32_t i = 0;
+    if (kPackStore && sw <= 32 && ((uintptr_t)w & 15) == 0) {
+        // The usual slot (reads of up to 512 bases): assembled in a local buffer and written with streaming stores -- the
+        // slot is not read again by this CPU (the copy engine or the kernels' host takes it from memory), so the lines
+        // need not be fetched before they are overwritten.  The caller fences (pack_fence) before the words are handed on.
+        alignas(64) uint64_t t[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (; i + 64 <= L; i += 64) {
+            __m512i v;
+            if (revcomp) v = _mm512_permutexvar_epi8(flip, _mm512_loadu_si512(s + (L - 64 - i)));
+            else v = _mm512_loadu_si512(s + i);
+            _mm_store_si128((__m128i*)(t + (i >> 5)), pack64_avx512(v, revcomp, bad));
+        }
+        if (i < L) {
+            __m512i v;
+            if (revcomp) v = _mm512_permutexvar_epi8(flip, _mm512_loadu_si512(s));
+            else v = _mm512_loadu_si512(s + (L - 64));
+            alignas(16) uint64_t bits[2];
+            _mm_store_si128((__m128i*)bits, pack64_avx512(v, revcomp, bad));
+            const uint32_t b0 = L - 64, u = b0 >> 5, sh = 2 * (b0 & 31);
+            if (sh == 0) { t[u] = bits[0]; t[u + 1] = bits[1]; }
+            else { t[u] |= bits[0] << sh; t[u + 1] = (bits[0] >> (64 - sh)) | (bits[1] << sh); t[u + 2] = bits[1] >> (64 - sh); }
+        }
+        if (kPackStore == 2 && ((uintptr_t)w & 63) == 0 && (sw & 15) == 0)
+            for (size_t k = 0; k < sw / 16; k++) _mm512_stream_si512((__m512i*)w + k, _mm512_load_si512((const __m512i*)t + k));
+        else
+            for (size_t k = 0; k < sw / 4; k++) _mm_store_si128((__m128i*)w + k, _mm_load_si128((const __m128i*)t + k));
+        return bad == 0;
+    }
+    for (; i + 64 <= L; i += 64) {
+        __m512i v;
+        if (revcomp) v = _mm512_permutexvar_epi8(flip, _mm512_loadu_si512(s + (L - 64 - i)));   // output bases i .. i+63: the input bytes L-64-i .. L-1-i backwards
+        else v = _mm512_loadu_si512(s + i);
+        _mm_storeu_si128((__m128i*)(w + (i >> 4)), pack64_avx512(v, revcomp, bad));
+    }
+    uint32_t next = i >> 4;                                  // first word not written yet
+    if (i < L) {
+        // the last, partial block: the 64 symbols that END the output (they overlap the block before, whose bits are the
+        // same, so they are OR-ed in), shifted to their place
+        __m512i v;
+        if (revcomp) v = _mm512_permutexvar_epi8(flip, _mm512_loadu_si512(s));
+        else v = _mm512_loadu_si512(s + (L - 64));
+        alignas(16) uint64_t bits[2];
+        _mm_store_si128((__m128i*)bits, pack64_avx512(v, revcomp, bad));
+        const uint32_t b0 = L - 64, u = b0 >> 5, sh = 2 * (b0 & 31);
+        if (sh == 0) { std::memcpy(w + 2 * u, bits, 16); next = 2 * (u + 2); }
+        else {
+            uint64_t out[3];
+            std::memcpy(&out[0], w + 2 * u, 8);
+            out[0] |= bits[0] << sh;
+            out[1] = (bits[0] >> (64 - sh)) | (bits[1] << sh);
+            out[2] = bits[1] >> (64 - sh);
+            std::memcpy(w + 2 * u, out, 24);
+            next = 2 * (u + 3);
+        }
+    }
+    for (size_t k = next; k < sw; k++) w[k] = 0;
+    return bad == 0;
+}
+// One read of nothing but A / C / G / T into its slot with the widest unit the CPU has; false: another symbol (or no unit).
+inline void pack_fence() { _mm_sfence(); }               // after a thread's last read: its streaming stores are visible
+inline bool pack_read_simd(const unsigned char* s, uint32_t L, bool revcomp, uint32_t* w, size_t sw) {
+    if (kAvx512 && L >= 64) return pack_read_avx512(s, L, revcomp, w, sw);
+    return kAvx2 && pack_read_avx2(s, L, revcomp, w, sw);
+}
 #endif
 
 }  // namespace
@@ -172,7 +260,7 @@ int dcb_pack_reads(const char* ascii, const uint64_t* off, const uint32_t* len, 
             uint32_t acc = 0;
             uint32_t i = 0;
 #if defined(__x86_64__)
-            if (kAvx2 && pack_read_avx2(s, L, revcomp != 0, w, sw)) continue;     // nothing but A / C / G / T: done
+            if (pack_read_simd(s, L, revcomp != 0, w, sw)) continue;     // nothing but A / C / G / T: done
 #endif
             // eight bases at a time while they are all A/C/G/T (SWAR): code = ((c >> 1) ^ (c >> 2)) & 3 maps
             // A,C,G,T -> 0,1,2,3; the reverse complement reads the bytes from the end (byte swap) and flips the code.
@@ -215,6 +303,9 @@ int dcb_pack_reads(const char* ascii, const uint64_t* off, const uint32_t* len, 
             for (uint32_t k = (L + 15) / 16; k < sw; k++) w[k] = 0;
             if (flagged) P->flags[r >> 5] |= 1u << (r & 31);
         }
+#if defined(__x86_64__)
+        pack_fence();
+#endif
     };
     if (n_threads == 1) work(0);
     else {
@@ -259,8 +350,9 @@ int dcb_pack_words(const char* ascii, const uint64_t* off, const uint32_t* len, 
             const uint64_t r = first + i;
             const uint32_t L = uniform_len ? uniform_len : len[r];
             const unsigned char* s = (const unsigned char*)ascii + (off ? off[r] : r * (uint64_t)uniform_len);
-            if ((L + 15) / 16 > slot_words || !pack_read_avx2(s, L, revcomp != 0, words + i * slot_words, slot_words)) { dirty[t] = 1; return; }
+            if ((L + 15) / 16 > slot_words || !pack_read_simd(s, L, revcomp != 0, words + i * slot_words, slot_words)) { dirty[t] = 1; pack_fence(); return; }
         }
+        pack_fence();
     };
     if (n_threads == 1) work(0);
     else {

@@ -159,3 +159,55 @@ def test_decombine_ascii_host_share_changes_nothing(share, monkeypatch):
     got, cnt = ctx.decombine_ascii(r2, off2, ln2, True)
     assert np.array_equal(got, want) and np.array_equal(cnt, wcnt)
     ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stage_mb", ["1024", "1"])
+def test_decombine_ascii_two_ended_sharing(stage_mb, monkeypatch):
+    """Page-locked text, one rank per host: the device takes chunks from the front while a worker packs chunks from the back
+    (ascii_two_ended).  Small chunks so that a modest batch has many of them; uniform and ragged reads; a batch whose
+    front half is full of Ns (device chunks with exception lists, clean host chunks behind them: the exception index must
+    run on); an N near the end (the worker gives that chunk back and stops); a page-locked region that holds two chunks."""
+    monkeypatch.setenv("DCB_HOST_SHARE", "1")
+    monkeypatch.setenv("DCB_CHUNK_READS", "8192")
+    monkeypatch.setenv("DCB_HOST_STAGE_MB", stage_mb)
+    info = tags.load("human", "extended", "b")
+    ctx = _ctx(info)
+    L = 250
+
+    def check(buf, off, ln, uniform):
+        packed = _lib.pack_arrays(buf, off, ln, revcomp=True)
+        want, wcnt = ctx.decombine(packed)
+        packed.free()
+        text = _lib.PinnedBytes(buf)
+        for _ in range(2):
+            if uniform:
+                got, cnt = ctx.decombine_ascii(text.a, None, None, True, uniform_len=L)
+            else:
+                got, cnt = ctx.decombine_ascii(text.a, off, ln, True)
+            assert np.array_equal(got, want) and np.array_equal(cnt, wcnt)
+        shares = ctx.last_pack_shares()
+        text.free()
+        return shares
+
+    n = 300_000
+    clean, off, ln = synth_batch(info, n, L, 0.01, 0.0, 0.05, seed=11)
+    host, dev = check(clean, off, ln, True)
+    assert host + dev == (n + 8191) // 8192 and host >= 1 and dev >= 1
+    if stage_mb == "1":
+        assert host <= 2
+    # Ns in the front half only
+    dirty, _, _ = synth_batch(info, n, L, 0.01, 0.002, 0.05, seed=12)
+    mixed = np.concatenate([dirty[:n // 2 * L], clean[n // 2 * L:]])
+    host, dev = check(mixed, off, ln, True)
+    assert dev >= n // 2 // 8192
+    # one N in the third chunk from the end
+    late = clean.copy()
+    late[(n - 20_000) * L + 5] = ord("N")
+    check(late, off, ln, True)
+    # ragged reads
+    rng = np.random.default_rng(3)
+    ln2 = rng.integers(0, L + 1, size=n).astype(np.uint32)
+    ln2[::7] = L
+    check(clean, off, ln2, False)
+    ctx.close()
