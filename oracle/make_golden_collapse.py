@@ -23,49 +23,14 @@ sys.path.insert(0, HERE)
 sys.path.insert(0, ROOT)
 
 import refenv  # noqa: E402
+import synth_pairs  # noqa: E402
 from decombinator_b200 import _lib, tags as dtags  # noqa: E402
 
 
 def make_rows(ref, species, tagset, chain, n, pool, L, sub1, sub2, seed, oligo, r2_layout=None, n1_at=22):
     """r2_layout(read 2 as the generator wrote it: M13 spacer, N6, I8 spacer, N6, ...) -> read 2 of another oligo design
     (make_golden_collapse_oligos.py); n1_at: where that design's first random hexamer starts."""
-    info = dtags.load(species, tagset, chain)
-    syn = _lib.Synth([(info.v_regions, info.j_regions)], seed, L, L, sub1, 0.0, 0.02, umi_pool=pool, sub_rate2=sub2)
-    r1, r2 = syn.reads(0, n, want_r2=True)
-    a = [bytes(r1[i * L:(i + 1) * L]).decode() for i in range(n)]
-    b = [bytes(r2[i * L:(i + 1) * L]).decode() for i in range(n)]
-    if r2_layout is not None:
-        b = [r2_layout(x) for x in b]
-    rng = random.Random(seed)
-    order = list(range(n))
-    rng.shuffle(order)
-    a = [a[i] for i in order]
-    b = [b[i] for i in order]
-    # barcode-read edge cases: N1 one base short / long, an N, low quality, a second molecule on a used barcode
-    q2 = []
-    for i in range(n):
-        q = ["I"] * L
-        r = rng.random()
-        if r < 0.03:
-            b[i] = b[i][:n1_at + 2] + b[i][n1_at + 3:] + "A"          # N1 of 5 bases
-        elif r < 0.06:
-            b[i] = b[i][:n1_at + 2] + "C" + b[i][n1_at + 2:-1]        # N1 of 7 bases
-        elif r < 0.08:
-            b[i] = b[i][:n1_at + 8] + "N" + b[i][n1_at + 9:]
-        elif r < 0.12:
-            for k in rng.sample(range(n1_at, n1_at + 20), 3):
-                q[k] = "#"
-        elif r < 0.15 and i > 10:
-            b[i] = b[rng.randrange(0, i)]               # barcode collision with an unrelated molecule
-        q2.append("".join(q))
-    q1 = ["I" * L for _ in range(n)]
-    names = ["SYN:%d" % i for i in range(n)]
-    with open("s_1.fq", "wt") as fh:
-        for nm, s, q in zip(names, a, q1):
-            fh.write("@%s\n%s\n+\n%s\n" % (nm, s, q))
-    with open("s_2.fq", "wt") as fh:
-        for nm, s, q in zip(names, b, q2):
-            fh.write("@%s\n%s\n+\n%s\n" % (nm, s, q))
+    synth_pairs.write_pairs("s_1.fq", "s_2.fq", species, tagset, chain, n, pool, L, sub1, sub2, seed, r2_layout, n1_at)
     args = ref["io"].create_args_dict(infile="s_1.fq", chain=chain, bc_read="R2", dontcount=True, suppresssummary=True,
                                       dontcheck=True, tagfastadir=refenv.REF_TAGDIR, outpath="", species=species, tags=tagset,
                                       oligo=oligo, command="pipeline")
