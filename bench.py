@@ -536,7 +536,7 @@ def main():
                     "call": "dcb_decombine_ascii: ASCII reads in page-locked host memory in (the reference arm's input), result records in "
                             "host memory out; the chunks are shared from both ends -- the device packs chunks from the front (their text crosses "
                             "the link), a worker with the host threads packs chunks of clean reads from the back (AVX-512, a quarter of the "
-                            "bytes crosses) until the two meet -- one rank per host only",
+                            "bytes crosses) until the two meet",
                     "chunks_packed_by": {"host_threads": host_chunks, "device": device_chunks, "rank": 0},
                     "device_packed_only": {"value": e2e_dev, "unit": UNIT, "h2d_bytes_per_step": int(n * READ_LEN),
                                            "how": "DCB_HOST_SHARE=0: the whole text crosses the link",

@@ -2005,11 +2005,11 @@ int dcb_decombine_ascii(dcb_ctx* c, const char* ascii, const uint64_t* off, cons
     chunk = (chunk + 1023u) & ~1023u;
     // Who packs a chunk: the device (the text goes over the link, 4 bytes per packed byte) or the host threads.  Text in
     // pageable memory would have to be gathered into page-locked staging by the host threads anyway: they pack it instead.
-    // Page-locked text: the host packs a chunk whenever the copy engine is still busy with the text of the last chunk given
-    // to the device, so the two shares balance themselves -- when this process has the host to itself: with several ranks on
-    // one host (LOCAL_WORLD_SIZE > 1) the link is shared too and the host threads are few, so the device packs.
+    // Page-locked text: shared from both ends (ascii_two_ended) -- also with several ranks on one host, each with its share
+    // of the host threads (LOCAL_WORLD_SIZE): measured on 2 ranks 407 -> 528 M reads/s, on 8 ranks 655 -> 686 M (there the
+    // host's memory system bounds the copies of all eight links and the packer takes 11 of 39 chunks).
     // DCB_HOST_SHARE=0 / 1 / 2 / 3: never / when the copy engine is busy / always / pageable text only (tests, measurements).
-    int host_share = local_world() == 1 ? 1 : 3;
+    int host_share = 1;
     if (const char* e = std::getenv("DCB_HOST_SHARE")) host_share = std::atoi(e);
     c->host_chunks = c->device_chunks = 0;
     c->acopy_pending = false;
