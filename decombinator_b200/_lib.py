@@ -100,6 +100,16 @@ def lib():
     L.dcb_n12_index.restype = ctypes.c_int
     L.dcb_n12_collapse_rows.argtypes = [vp, vp, vp, u64, vp, i32, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(u64), ctypes.POINTER(u64)]
     L.dcb_n12_collapse_rows.restype = ctypes.c_int
+    pu64 = ctypes.POINTER(u64)
+    L.dcb_group_create.argtypes = [vp, u64, u64, vp, vp, ctypes.POINTER(ctypes.c_void_p)]
+    L.dcb_group_step.argtypes = [vp, pu64]
+    L.dcb_group_pairs.argtypes = [vp, pu64, pu64, vp, vp, vp, vp, vp, ctypes.POINTER(ctypes.c_int)]
+    L.dcb_group_verdicts.argtypes = [vp, vp, u64]
+    L.dcb_group_result.argtypes = [vp, pu64, pu64, pu64, pu64, vp, vp, vp, vp, vp]
+    L.dcb_group_free.argtypes = [vp]
+    L.dcb_group_free.restype = None
+    for f in (L.dcb_group_create, L.dcb_group_step, L.dcb_group_pairs, L.dcb_group_verdicts, L.dcb_group_result):
+        f.restype = ctypes.c_int
     L.dcb_pack_reads.argtypes = [vp, vp, vp, u64, i32, i32, ctypes.POINTER(ctypes.POINTER(CPacked))]
     L.dcb_packed_free.argtypes = [ctypes.POINTER(CPacked)]
     L.dcb_pack_words.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32,
@@ -395,6 +405,61 @@ def n12_collapse_rows(text, off, ln, keep, n_threads=None):
     if nrows.value == 0xFFFFFFFFFFFFFFFF:
         return None
     return NativeText(out.value, nbytes.value), int(nrows.value)
+
+
+class Grouping:
+    """dcb_group: the grouping of collapse's read_in_data over columns (csrc/group.cpp).  seqs: bytes of the rows' inter-tag
+    sequences joined by newlines; code / idx: barcode code and global row index per row.  ``run(verdicts)`` drives the
+    rounds: verdicts(symbols, off, len, a, b) -> bool array is the caller's route to the GPU (Dist.lev_leq)."""
+
+    def __init__(self, seqs, code, idx):
+        self._seqs = seqs                                  # the library reads the text in place
+        self._buf = np.frombuffer(seqs, dtype=np.uint8)
+        self._h = ctypes.c_void_p()
+        code = np.ascontiguousarray(code, dtype=np.uint64)
+        idx = np.ascontiguousarray(idx, dtype=np.uint64)
+        _check(lib().dcb_group_create(self._buf.ctypes.data if len(self._buf) else None, len(self._buf), len(code), code.ctypes.data,
+                                      idx.ctypes.data, ctypes.byref(self._h)), "dcb_group_create")
+
+    def run(self, verdicts):
+        L = lib()
+        n_pairs = ctypes.c_uint64()
+        while True:
+            _check(L.dcb_group_step(self._h, ctypes.byref(n_pairs)), "dcb_group_step")
+            if n_pairs.value == 0:
+                break
+            ns, nsym, coded = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_int()
+            _check(L.dcb_group_pairs(self._h, ctypes.byref(ns), ctypes.byref(nsym), None, None, None, None, None, None), "dcb_group_pairs")
+            sym = np.zeros(max(1, nsym.value), dtype=np.uint8)
+            off, ln = np.zeros(ns.value, dtype=np.uint64), np.zeros(ns.value, dtype=np.uint32)
+            a, b = np.zeros(n_pairs.value, dtype=np.uint32), np.zeros(n_pairs.value, dtype=np.uint32)
+            _check(L.dcb_group_pairs(self._h, ctypes.byref(ns), ctypes.byref(nsym), sym.ctypes.data, off.ctypes.data, ln.ctypes.data,
+                                     a.ctypes.data, b.ctypes.data, ctypes.byref(coded)), "dcb_group_pairs")
+            same = np.ascontiguousarray(verdicts(sym[:nsym.value], off, ln, a, b), dtype=np.uint8)
+            _check(L.dcb_group_verdicts(self._h, same.ctypes.data, len(same)), "dcb_group_verdicts")
+
+    def result(self):
+        """-> (code uint64[g], tick uint64[g], proto_row uint32[g], first uint64[g + 1], rows uint32[members], dropped, dead)"""
+        L = lib()
+        ng, nm, dr, dd = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        args = [ctypes.byref(ng), ctypes.byref(nm), ctypes.byref(dr), ctypes.byref(dd)]
+        _check(L.dcb_group_result(self._h, *args, None, None, None, None, None), "dcb_group_result")
+        code, tick, proto = np.zeros(ng.value, dtype=np.uint64), np.zeros(ng.value, dtype=np.uint64), np.zeros(ng.value, dtype=np.uint32)
+        first, rows = np.zeros(ng.value + 1, dtype=np.uint64), np.zeros(max(1, nm.value), dtype=np.uint32)
+        _check(L.dcb_group_result(self._h, *args, code.ctypes.data, tick.ctypes.data, proto.ctypes.data, first.ctypes.data, rows.ctypes.data),
+               "dcb_group_result")
+        return code, tick, proto, first, rows[:nm.value], int(dr.value), int(dd.value)
+
+    def close(self):
+        if self._h:
+            lib().dcb_group_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class NativeText:

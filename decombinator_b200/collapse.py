@@ -538,11 +538,23 @@ def _filter_rows(data, inputargs, barcode_quality_parameters, dont_count, from_f
     return kept, input_dcr_counts, n_rows
 
 
+_BC_CODE = np.full(256, 255, dtype=np.uint8)
+_BC_CODE[np.frombuffer(b"ACGTNSL", dtype=np.uint8)] = np.arange(7, dtype=np.uint8)
+
+
 def _group_rows(kept, lev_threshold_fraction):
     """Order-dependent grouping by exact barcode (collapse.py:595-682) of rows given in global input order.
 
-    -> list of finished _BarcodeMachine.  Only rows with the SAME barcode interact, so any partition of the barcodes
-    (parallel.py: hash(barcode) % world) can be grouped independently and merged by ``tick`` afterwards."""
+    -> ([(tick, barcode, proto, members), ...] of the surviving groups, rows dropped, barcodes blacklisted).  Only rows with
+    the SAME barcode interact, so any partition of the barcodes (parallel.py: hash(barcode) % world) can be grouped
+    independently and merged by ``tick`` afterwards.
+
+    The rules run in the library over columns (dcb_group, csrc/group.cpp) when every barcode is twelve symbols of ACGTNSL
+    and the sequences are plain ASCII -- the usual case; anything else through the same rules in Python (_BarcodeMachine).
+    Either way each round resolves, in ONE GPU batch, every sequence verdict some barcode waits for."""
+    native = _group_rows_native(kept, lev_threshold_fraction) if len(kept) >= 64 and os.environ.get("DCB_GROUP_NATIVE", "1") != "0" else None
+    if native is not None:
+        return native
     machines = {}
     for idx, barcode, seq, dcretc in kept:
         m = machines.get(barcode)
@@ -563,7 +575,38 @@ def _group_rows(kept, lev_threshold_fraction):
             for key, verdict in zip(keys, _verdicts(keys, lev_threshold_fraction)):
                 cache[key] = verdict
         waiting = blocked
-    return list(machines.values())
+    ms = list(machines.values())
+    return ([(m.tick, m.barcode, m.proto, m.members) for m in ms if m.members is not None], sum(m.dropped for m in ms),
+            sum(1 for m in ms if m.dead))
+
+
+def _group_rows_native(kept, lev_threshold_fraction):
+    """_group_rows through dcb_group; None when the rows are not of the shape it takes."""
+    n = len(kept)
+    idx_l, bc_l, seq_l, etc_l = zip(*kept)
+    try:
+        bcs = "".join(bc_l).encode("ascii")
+        seqs = "\n".join(seq_l).encode("ascii")
+    except UnicodeEncodeError:
+        return None
+    if len(bcs) != 12 * n or len(seqs) != sum(map(len, seq_l)) + n - 1 or b"\n" in bcs:
+        return None
+    sym = _BC_CODE[np.frombuffer(bcs, dtype=np.uint8)].reshape(n, 12)
+    if int(sym.max()) > 6 or any("\n" in s for s in set(seq_l)):
+        return None
+    code = (sym.astype(np.uint64) << (np.uint64(3) * np.arange(12, dtype=np.uint64))[None, :]).sum(axis=1, dtype=np.uint64)
+    g = _lib.Grouping(seqs, code, np.fromiter(idx_l, dtype=np.uint64, count=n))
+    try:
+        g.run(lambda symbols, off, ln, a, b: _gpu().lev_leq(symbols, off, ln, a, b, lev_threshold_fraction))
+        _, tick, proto, first, rows, dropped, dead = g.result()
+    finally:
+        g.close()
+    rows, first, tick = rows.tolist(), first.tolist(), tick.tolist()
+    groups = []
+    for k, p in enumerate(proto.tolist()):
+        members = rows[first[k]:first[k + 1]]
+        groups.append((tick[k], bc_l[members[0]], seq_l[p], [etc_l[r] for r in members]))
+    return groups, dropped, dead
 
 
 def _groups_to_dict(groups, input_dcr_counts, dropped, dead):
@@ -603,9 +646,8 @@ def read_in_data(data, inputargs, barcode_quality_parameters, lev_threshold_frac
     kept, input_dcr_counts, n_lines = _filter_rows(data, inputargs, barcode_quality_parameters, dont_count, from_file)
     if from_file:
         data.close()
-    machines = _group_rows(kept, lev_threshold_fraction)
-    barcode_dcretc = _groups_to_dict([(m.tick, m.barcode, m.proto, m.members) for m in machines if m.members is not None],
-                                     input_dcr_counts, sum(m.dropped for m in machines), sum(1 for m in machines if m.dead))
+    groups, dropped, dead = _group_rows(kept, lev_threshold_fraction)
+    barcode_dcretc = _groups_to_dict(groups, input_dcr_counts, dropped, dead)
     t1 = time.time()
     print("   Read in total of", n_lines, "lines")
     print("  ", counts["readdata_success"], "reads sorted into", len(barcode_dcretc), "initial groups")

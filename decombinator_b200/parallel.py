@@ -326,10 +326,8 @@ def collapsinator_sharded(inputargs, data=None, first_index=0, n_total=None):
         mine = [item for blob in inbox for item in pickle.loads(blob)]
     mine.sort(key=lambda item: item[0])                      # global input order within every barcode
     # 3. group this rank's barcodes (Levenshtein verdicts on this rank's GPU)
-    machines = C._group_rows(mine, frac)
-    groups = [(m.tick, m.barcode, m.proto, m.members) for m in machines if m.members is not None]
-    local = {"groups": groups, "dropped": sum(m.dropped for m in machines), "dead": sum(1 for m in machines if m.dead),
-             "dcr_counts": dict(dcr_counts)}
+    groups, dropped, dead = C._group_rows(mine, frac)
+    local = {"groups": groups, "dropped": dropped, "dead": dead, "dcr_counts": dict(dcr_counts)}
     parts = [None] * world if rank == 0 else None
     dist.gather_object(local, parts, dst=0)
     totals = _sum_counters({k: v for k, v in C.counts.items() if k != "start_time"})

@@ -198,6 +198,24 @@ int dcb_n12_collapse_rows(const char* text, const uint64_t* off, const uint32_t*
                           char** out, uint64_t* out_bytes, uint64_t* n_rows);
 void dcb_buffer_free(char*);
 
+/* The order-dependent grouping of collapse's read_in_data (collapse.py:595-682) over columns instead of a Python loop over
+ * rows: per barcode, rows in input order found / join / kill the barcode's group (rules: csrc/group.cpp).  Host logic; the
+ * sequence comparisons it needs (are_seqs_equivalent, collapse.py:355-360) are the caller's to fetch from the GPU:
+ *   dcb_group_create(seqs joined by '\n', barcode code and global row index per row)
+ *   loop: dcb_group_step -> n_pairs; 0: done.  dcb_group_pairs (sizes with symbols == NULL, then the arrays) is a batch
+ *         for dcb_lev_leq (coded = 1) / dcb_lev_leq_bytes (coded = 0); dcb_group_verdicts feeds the answers back
+ *   dcb_group_result (sizes with rows == NULL, then the arrays): surviving groups in the reference's dict order with
+ *         their barcode code, tick (the row index at which the group took its place), a row holding the proto-sequence, and their member rows (first[g] .. first[g + 1]). */
+typedef struct dcb_group dcb_group;
+int dcb_group_create(const char* seqs, uint64_t seqs_bytes, uint64_t n, const uint64_t* code, const uint64_t* idx, dcb_group** out);
+int dcb_group_step(dcb_group*, uint64_t* n_pairs);
+int dcb_group_pairs(dcb_group*, uint64_t* n_seqs, uint64_t* n_symbols, uint8_t* symbols, uint64_t* off, uint32_t* len, uint32_t* a, uint32_t* b,
+                    int* coded);
+int dcb_group_verdicts(dcb_group*, const uint8_t* same, uint64_t n_pairs);
+int dcb_group_result(dcb_group*, uint64_t* n_groups, uint64_t* n_members, uint64_t* dropped, uint64_t* dead, uint64_t* code, uint64_t* tick,
+                     uint32_t* proto_row, uint64_t* first, uint32_t* rows);
+void dcb_group_free(dcb_group*);
+
 
 typedef struct dcb_params {
     int32_t both_frames;   /* -or both: retry the reverse complement of the packed read when the first try fails

@@ -182,6 +182,47 @@ def test_n12_index_and_collapse_lines_equal_the_split_lines(golden_dir, tmp_path
     assert dcrs == [str(["1", "2", "3", "4", "AC'T"])]
 
 
+def test_native_grouping_equals_the_python_state_machines(oracle_distances, monkeypatch):
+    """dcb_group (csrc/group.cpp) against _BarcodeMachine -- the restatement of collapse.py:595-682 the recorded runs of the
+    reference pin -- on rows with many copies per barcode, variants one or two edits apart (so that proto-sequences change),
+    unrelated sequences on a used barcode (dead barcodes) and S / L / N symbols in barcodes."""
+    rng = random.Random(17)
+    pool = ["".join(rng.choice("ACGT") for _ in range(rng.randrange(60, 90))) for _ in range(40)]
+    barcodes = ["".join(rng.choice("ACGTACGTACGTNSL") for _ in range(12)) for _ in range(150)]
+    home = {b: rng.choice(pool) for b in barcodes}
+    kept = []
+    for i in range(6000):
+        b = rng.choice(barcodes)
+        seq = list(home[b])
+        r = rng.random()
+        if r < 0.35:
+            for _ in range(rng.randrange(1, 3)):
+                seq[rng.randrange(len(seq))] = rng.choice("ACGT")
+        elif r < 0.40:
+            del seq[rng.randrange(len(seq))]
+        elif r < 0.42:
+            seq = list(rng.choice(pool))                       # another molecule on this barcode
+        seq = "".join(seq)
+        kept.append((3 * i + 1, b, seq, "dcr|%s|q|id%d" % (seq, i)))
+    calls = []
+    real = _lib.Grouping.run
+    monkeypatch.setattr(_lib.Grouping, "run", lambda self, v: (calls.append(1), real(self, v))[1])
+    for frac in (0.03, 0.1):
+        native = collapse._group_rows(kept, frac)
+        assert calls, "the library's grouping did not run"
+        monkeypatch.setenv("DCB_GROUP_NATIVE", "0")
+        n_calls = len(calls)
+        python = collapse._group_rows(kept, frac)
+        assert len(calls) == n_calls
+        monkeypatch.delenv("DCB_GROUP_NATIVE")
+        assert sorted(native[0]) == sorted(python[0]) and native[1:] == python[1:]
+        assert [g[0] for g in native[0]] == sorted(g[0] for g in python[0])          # the library hands them over in dict order
+        assert native[2] > 3 and native[1] > native[2]                              # dead barcodes, and rows dropped behind them
+    # rows it does not take: a barcode of another length, a symbol outside ACGTNSL
+    assert collapse._group_rows_native(kept[:100] + [(99999, "ACGT", "ACGT", "x")], 0.1) is None
+    assert collapse._group_rows_native(kept[:100] + [(99999, "ACGTACGTACGR", "ACGT", "x")], 0.1) is None
+
+
 def test_empty_n12_raises(tmp_path):
     p = tmp_path / "empty.n12"
     p.write_text("")
