@@ -589,10 +589,10 @@ def _group_rows_native(kept, lev_threshold_fraction):
         seqs = "\n".join(seq_l).encode("ascii")
     except UnicodeEncodeError:
         return None
-    if len(bcs) != 12 * n or len(seqs) != sum(map(len, seq_l)) + n - 1 or b"\n" in bcs:
+    if len(bcs) != 12 * n or seqs.count(b"\n") != n - 1:          # (a sequence that holds a newline: not the library's shape)
         return None
     sym = _BC_CODE[np.frombuffer(bcs, dtype=np.uint8)].reshape(n, 12)
-    if int(sym.max()) > 6 or any("\n" in s for s in set(seq_l)):
+    if int(sym.max()) > 6 or len(set(map(len, bc_l))) != 1:
         return None
     code = (sym.astype(np.uint64) << (np.uint64(3) * np.arange(12, dtype=np.uint64))[None, :]).sum(axis=1, dtype=np.uint64)
     g = _lib.Grouping(seqs, code, np.fromiter(idx_l, dtype=np.uint64, count=n))
@@ -605,7 +605,8 @@ def _group_rows_native(kept, lev_threshold_fraction):
     groups = []
     for k, p in enumerate(proto.tolist()):
         members = rows[first[k]:first[k + 1]]
-        groups.append((tick[k], bc_l[members[0]], seq_l[p], [etc_l[r] for r in members]))
+        groups.append((tick[k], bc_l[members[0]], seq_l[p],
+                       list(operator.itemgetter(*members)(etc_l)) if len(members) > 1 else [etc_l[members[0]]]))
     return groups, dropped, dead
 
 
