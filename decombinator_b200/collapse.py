@@ -796,7 +796,8 @@ def _count_clusters(barcode_dcretc, inputargs, barcode_distance_threshold, lev_t
     cluster_sizes = coll.defaultdict(list)
     for members in clusters.values():
         # most common DCR of the cluster; ties go to the first one met (Counter.most_common semantics)
-        protodcr = coll.Counter(x.split("|")[0] for x in members).most_common(1)[0][0]
+        dcrs = [x.split("|", 1)[0] for x in members]
+        protodcr = dcrs[0] if dcrs.count(dcrs[0]) == len(dcrs) else coll.Counter(dcrs).most_common(1)[0][0]
         collapsed[protodcr] += 1
         cluster_sizes[protodcr].append(len(members))
     counts["number_output_unique_dcrs"] = len(collapsed)
