@@ -6,6 +6,9 @@ of every line is dropped unconditionally).  ``load_pairs`` materialises the reco
 (decombine.py:950-989) as flat byte buffers that go straight to ``dcb_pack_reads``.
 """
 import gzip
+import os
+import struct
+import zlib
 import itertools
 import mmap
 
@@ -169,8 +172,103 @@ def _file_bytes(path, opener):
                 return mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
         except (ValueError, OSError):      # empty file, or a file system without mmap
             pass
+    if opener is gzip.open:
+        try:
+            return gunzip_file(path)
+        except Exception:                  # a damaged file: the gzip module then raises what the reference's reader raises
+            pass
     with opener(path, "rb") as fh:
         return fh.read()
+
+
+def _bgzf_blocks(raw):
+    """[(first byte of the deflate data, one past its end, uncompressed size), ...] when the file is a chain of BGZF blocks
+    (gzip members whose extra field 'BC' holds the member's size: bgzip, Illumina's converters), else None."""
+    blocks, p, n = [], 0, len(raw)
+    while p < n:
+        if n - p < 18 or raw[p:p + 4] != b"\x1f\x8b\x08\x04":       # FLG = FEXTRA alone, as BGZF writes it
+            return None
+        xlen = struct.unpack_from("<H", raw, p + 10)[0]
+        q, end, bsize = p + 12, p + 12 + xlen, None
+        while q + 4 <= end:
+            si1, si2, slen = raw[q], raw[q + 1], struct.unpack_from("<H", raw, q + 2)[0]
+            if si1 == 66 and si2 == 67 and slen == 2:
+                bsize = struct.unpack_from("<H", raw, q + 4)[0] + 1
+            q += 4 + slen
+        if bsize is None or p + bsize > n or bsize < 12 + xlen + 8:
+            return None
+        isize = struct.unpack_from("<I", raw, p + bsize - 4)[0]
+        if isize:
+            blocks.append((p + 12 + xlen, p + bsize - 8, isize))
+        p += bsize
+    return blocks or None
+
+
+def gunzip_file(path, n_threads=None):
+    """The decompressed bytes of a .gz file in an anonymous memory map (the same kind of object a plain file is read
+    through).  A BGZF file is inflated block by block on all host threads (zlib releases the GIL); any other gzip file --
+    one member or several -- is one deflate stream after the other, inflated in slices straight into the map."""
+    with open(path, "rb") as fh:
+        try:
+            raw = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+        except (ValueError, OSError):
+            raw = fh.read()
+    if len(raw) == 0:
+        return b""
+    blocks = _bgzf_blocks(raw)
+    if blocks:
+        sizes = np.fromiter((b[2] for b in blocks), dtype=np.int64, count=len(blocks))
+        starts = np.concatenate([[0], np.cumsum(sizes)])
+        out = mmap.mmap(-1, int(starts[-1]), flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)
+        view = memoryview(out)
+        nt = n_threads or min(32, os.cpu_count() or 1)
+        per = max(1, min(256, len(blocks) // (4 * nt) or 1))
+
+        def work(lo):
+            d_crc = zlib.crc32
+            for k in range(lo, min(lo + per, len(blocks))):
+                a, b, isize = blocks[k]
+                data = zlib.decompress(raw[a:b], -15, isize)
+                if len(data) != isize or d_crc(data) != struct.unpack_from("<I", raw, b)[0]:
+                    raise zlib.error("BGZF block %d: size or CRC mismatch" % k)
+                view[int(starts[k]):int(starts[k]) + isize] = data
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(nt) as pool:
+            list(pool.map(work, range(0, len(blocks), per)))
+        view.release()
+        return out
+    cap = max(1 << 20, 4 * len(raw))
+    out = mmap.mmap(-1, cap, flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)      # (a shared anonymous map cannot grow)
+    pos, at, step = 0, 0, 1 << 24
+    d = zlib.decompressobj(31)
+    pending = b""
+    while True:
+        if not pending:
+            if at >= len(raw):
+                break
+            pending = raw[at:at + step]
+            at += len(pending)
+        chunk = d.decompress(pending, step)
+        pending = d.unconsumed_tail
+        if pos + len(chunk) > cap:
+            cap = max(cap * 2, pos + len(chunk))
+            out.resize(cap)
+        out[pos:pos + len(chunk)] = chunk
+        pos += len(chunk)
+        if d.eof:                          # the end of a member: another one may follow (gzip files concatenate)
+            rest = d.unused_data + pending
+            while rest[:1] == b"\0":       # zero padding behind the last member, as the gzip module tolerates
+                rest = rest[1:]
+            pending = rest
+            if not pending and at >= len(raw):
+                break
+            d = zlib.decompressobj(31)
+    if not d.eof:
+        raise EOFError("Compressed file ended before the end-of-stream marker was reached")
+    if pos == 0:
+        return b""
+    out.resize(pos)
+    return out
 
 
 def load_pairs_native(inputargs, opener):

@@ -150,3 +150,49 @@ def test_format_rows_matches_the_reference_row_assembly(pack_rc, with_tail):
         want.append(", ".join(row) + "\n")
     assert blob.decode() == "".join(want)
     assert nrows == len(want)
+
+
+def _bgzf(data, block=60000):
+    """A BGZF file (the format bgzip and Illumina's converters write): gzip members of at most 64 KB whose extra field
+    'BC' holds the member's size, closed by an empty member."""
+    import struct
+    import zlib
+    out = []
+    for lo in list(range(0, len(data), block)) + [None]:
+        chunk = b"" if lo is None else data[lo:lo + block]
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = c.compress(chunk) + c.flush()
+        bsize = 12 + 6 + len(body) + 8
+        out.append(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1) + body +
+                   struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+    return b"".join(out)
+
+
+def test_gunzip_file_equals_the_gzip_module(tmp_path):
+    """fastq.gunzip_file: one member, several members, BGZF blocks (inflated in parallel), zero padding, an empty file; a
+    damaged file is left to the gzip module (the reader the reference uses), whose error then surfaces."""
+    import gzip
+    import random
+    from decombinator_b200 import fastq
+    rng = random.Random(3)
+    text = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, bytes(rng.choice(b"ACGT") for _ in range(rng.randrange(40, 200))), b"I" * 50)
+                    for i in range(20000))
+    cases = {"one.gz": gzip.compress(text), "many.gz": b"".join(gzip.compress(text[lo:lo + 300000]) for lo in range(0, len(text), 300000)),
+             "bgzf.gz": _bgzf(text), "padded.gz": gzip.compress(text) + b"\0" * 512, "empty_member.gz": gzip.compress(b"")}
+    for name, blob in cases.items():
+        path = tmp_path / name
+        path.write_bytes(blob)
+        want = gzip.open(path, "rb").read()
+        got = fastq.gunzip_file(str(path))
+        assert bytes(got) == want, name
+        assert bytes(fastq._file_bytes(str(path), gzip.open)) == want, name
+    assert fastq._bgzf_blocks(cases["bgzf.gz"]) is not None and fastq._bgzf_blocks(cases["one.gz"]) is None
+    assert bytes(fastq.gunzip_file(str(tmp_path / "bgzf.gz"), n_threads=3)) == text
+    bad = bytearray(cases["bgzf.gz"])
+    bad[5000] ^= 0x55
+    (tmp_path / "bad.gz").write_bytes(bytes(bad))
+    with pytest.raises(Exception):
+        fastq._file_bytes(str(tmp_path / "bad.gz"), gzip.open)
+    (tmp_path / "cut.gz").write_bytes(cases["one.gz"][:-100])
+    with pytest.raises(EOFError):
+        fastq._file_bytes(str(tmp_path / "cut.gz"), gzip.open)

@@ -22,6 +22,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reads", type=int, default=2_000_000)
     ap.add_argument("--python-fastq", action="store_true", help="use the general (Python) parser instead of the native index")
+    ap.add_argument("--gz", choices=["gzip", "bgzf"], default=None, help="compress the two files first: one gzip stream each, or BGZF blocks")
     ap.add_argument("--rows-as-text", action="store_true", help="what the `decombine` command does: rows handed over as .n12 text")
     ap.add_argument("--profile", action="store_true", help="cProfile of the timed decombinator() call")
     ap.add_argument("--pipeline", action="store_true", help="decombine + collapse (pipeline.run) on reads with repeated UMIs")
@@ -44,6 +45,17 @@ def main():
                 rows = [b"@SYN:%d 1:N:0\n%s\n+\n%s\n" % (i, a[i - lo + lo].tobytes(), b"I" * ln) for i in range(lo, hi)]
                 fh.write(b"".join(rows))
     t_write = time.perf_counter() - t0
+    if args.gz:
+        import subprocess
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        for q in (p1, p2):
+            if args.gz == "gzip":
+                subprocess.run(["gzip", "-kf", q], check=True)
+            else:
+                from test_fastq_native import _bgzf
+                with open(q, "rb") as fh, open(q + ".gz", "wb") as out:
+                    out.write(_bgzf(fh.read()))
+        p1, p2 = p1 + ".gz", p2 + ".gz"
     ia = io.create_args_dict(infile=p1, chain="b", bc_read="R2", suppresssummary=True, dontcheck=True, dontcount=True,
                              outpath="/tmp/e2e/")
     ia["python_fastq"] = args.python_fastq
@@ -71,7 +83,7 @@ def main():
     small = dict(ia)
     decombine.import_tcr_info(small)
     t0 = time.perf_counter()
-    opener = open
+    opener = fastq.opener_check(ia)
     batch = fastq.load_pairs(ia, opener)
     t_ingest = time.perf_counter() - t0
     decombine.decombinator(dict(ia))          # first run: CUDA context, tables, page-locked buffers
