@@ -101,6 +101,8 @@ def lib():
     L.dcb_n12_collapse_rows.argtypes = [vp, vp, vp, u64, vp, i32, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(u64), ctypes.POINTER(u64)]
     L.dcb_n12_collapse_rows.restype = ctypes.c_int
     pu64 = ctypes.POINTER(u64)
+    L.dcb_bgzf_inflate.argtypes = [vp, vp, vp, vp, vp, u64, vp, i32]
+    L.dcb_bgzf_inflate.restype = ctypes.c_int
     L.dcb_group_create.argtypes = [vp, u64, u64, vp, vp, ctypes.POINTER(ctypes.c_void_p)]
     L.dcb_group_step.argtypes = [vp, pu64]
     L.dcb_group_pairs.argtypes = [vp, pu64, pu64, vp, vp, vp, vp, vp, ctypes.POINTER(ctypes.c_int)]
@@ -405,6 +407,14 @@ def n12_collapse_rows(text, off, ln, keep, n_threads=None):
     if nrows.value == 0xFFFFFFFFFFFFFFFF:
         return None
     return NativeText(out.value, nbytes.value), int(nrows.value)
+
+
+def bgzf_inflate(raw, start, end, isize, out_off, out, n_threads=None):
+    """dcb_bgzf_inflate: raw / out are uint8 arrays (views of the compressed file and of the buffer to fill)."""
+    start, end = np.ascontiguousarray(start, dtype=np.uint64), np.ascontiguousarray(end, dtype=np.uint64)
+    isize, out_off = np.ascontiguousarray(isize, dtype=np.uint32), np.ascontiguousarray(out_off, dtype=np.uint64)
+    _check(lib().dcb_bgzf_inflate(raw.ctypes.data, start.ctypes.data, end.ctypes.data, isize.ctypes.data, out_off.ctypes.data, len(start),
+                                  out.ctypes.data, n_threads or min(32, os.cpu_count() or 1)), "dcb_bgzf_inflate")
 
 
 class Grouping:

@@ -10,6 +10,8 @@
 // (the last character of EVERY line is dropped, decombine.py:239-256) only matter there.
 #include "dcb_internal.h"
 
+#include <zlib.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <chrono>
@@ -453,6 +455,38 @@ static int format_impl(const RowCtx& c, const dcb_result* res, uint64_t n, int n
 }
 
 void dcb_buffer_free(char* p) { std::free(p); }
+
+// ------------------------------------------------------------------------------------------------
+// BGZF blocks (gzip members of at most 64 KB that carry their own size: bgzip, Illumina's converters) inflated side by side:
+// block k is raw deflate data raw[start[k], end[k]) of isize[k] bytes, followed by its CRC-32, and goes to out + out_off[k].
+// ------------------------------------------------------------------------------------------------
+int dcb_bgzf_inflate(const unsigned char* raw, const uint64_t* start, const uint64_t* end, const uint32_t* isize, const uint64_t* out_off,
+                     uint64_t n_blocks, unsigned char* out, int n_threads) {
+    if (n_blocks && (!raw || !start || !end || !isize || !out_off || !out)) { dcb_set_error("dcb_bgzf_inflate: null argument"); return DCB_EINVAL; }
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 64) n_threads = 64;
+    if ((uint64_t)n_threads > n_blocks) n_threads = n_blocks ? (int)n_blocks : 1;
+    std::vector<long long> bad(n_threads, -1);
+    run_threads(n_threads, [&](int t) {
+        z_stream z;
+        std::memset(&z, 0, sizeof(z));
+        if (inflateInit2(&z, -15) != Z_OK) { bad[t] = (long long)(n_blocks * (uint64_t)t / n_threads); return; }
+        const uint64_t lo = n_blocks * (uint64_t)t / n_threads, hi = n_blocks * (uint64_t)(t + 1) / n_threads;
+        for (uint64_t k = lo; k < hi; k++) {
+            inflateReset(&z);
+            z.next_in = const_cast<unsigned char*>(raw + start[k]); z.avail_in = (uInt)(end[k] - start[k]);
+            z.next_out = out + out_off[k]; z.avail_out = isize[k];
+            const int rc = inflate(&z, Z_FINISH);
+            uint32_t want;
+            std::memcpy(&want, raw + end[k], 4);
+            if (rc != Z_STREAM_END || z.avail_out != 0 || (uint32_t)crc32(0L, out + out_off[k], isize[k]) != want) { bad[t] = (long long)k; break; }
+        }
+        inflateEnd(&z);
+    });
+    for (int t = 0; t < n_threads; t++)
+        if (bad[t] >= 0) { dcb_set_error("dcb_bgzf_inflate: block %lld does not inflate to its size and CRC", bad[t]); return DCB_EINVAL; }
+    return DCB_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // .n12 text (the `collapse` command's input, written by write_out_intermediate, io.py:480-513): where the ten fields

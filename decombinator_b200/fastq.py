@@ -206,7 +206,7 @@ def _bgzf_blocks(raw):
 
 def gunzip_file(path, n_threads=None):
     """The decompressed bytes of a .gz file in an anonymous memory map (the same kind of object a plain file is read
-    through).  A BGZF file is inflated block by block on all host threads (zlib releases the GIL); any other gzip file --
+    through).  A BGZF file is inflated block by block on all host threads (dcb_bgzf_inflate); any other gzip file --
     one member or several -- is one deflate stream after the other, inflated in slices straight into the map."""
     with open(path, "rb") as fh:
         try:
@@ -217,25 +217,14 @@ def gunzip_file(path, n_threads=None):
         return b""
     blocks = _bgzf_blocks(raw)
     if blocks:
-        sizes = np.fromiter((b[2] for b in blocks), dtype=np.int64, count=len(blocks))
-        starts = np.concatenate([[0], np.cumsum(sizes)])
-        out = mmap.mmap(-1, int(starts[-1]), flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)
-        view = memoryview(out)
-        nt = n_threads or min(32, os.cpu_count() or 1)
-        per = max(1, min(256, len(blocks) // (4 * nt) or 1))
-
-        def work(lo):
-            d_crc = zlib.crc32
-            for k in range(lo, min(lo + per, len(blocks))):
-                a, b, isize = blocks[k]
-                data = zlib.decompress(raw[a:b], -15, isize)
-                if len(data) != isize or d_crc(data) != struct.unpack_from("<I", raw, b)[0]:
-                    raise zlib.error("BGZF block %d: size or CRC mismatch" % k)
-                view[int(starts[k]):int(starts[k]) + isize] = data
-        from concurrent.futures import ThreadPoolExecutor
-        with ThreadPoolExecutor(nt) as pool:
-            list(pool.map(work, range(0, len(blocks), per)))
-        view.release()
+        from . import _lib
+        arr = np.array(blocks, dtype=np.uint64)
+        out_off = np.zeros(len(blocks), dtype=np.uint64)
+        np.cumsum(arr[:-1, 2], out=out_off[1:])
+        total = int(arr[:, 2].sum())
+        out = mmap.mmap(-1, total, flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)
+        _lib.bgzf_inflate(np.frombuffer(raw, dtype=np.uint8), arr[:, 0], arr[:, 1], arr[:, 2], out_off, np.frombuffer(out, dtype=np.uint8),
+                          n_threads)
         return out
     cap = max(1 << 20, 4 * len(raw))
     out = mmap.mmap(-1, cap, flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)      # (a shared anonymous map cannot grow)

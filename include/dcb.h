@@ -197,6 +197,10 @@ int dcb_n12_index(const char* text, uint64_t n_bytes, int n_threads, uint64_t** 
 int dcb_n12_collapse_rows(const char* text, const uint64_t* off, const uint32_t* len, uint64_t n, const uint8_t* keep, int n_threads,
                           char** out, uint64_t* out_bytes, uint64_t* n_rows);
 void dcb_buffer_free(char*);
+/* Compressed FASTQ (the reference reads it through gzip.open, decombine.py:118-123): the blocks of a BGZF file -- raw deflate
+ * data raw[start[k], end[k]) of isize[k] bytes each, its CRC-32 behind it -- inflated side by side into out + out_off[k]. */
+int dcb_bgzf_inflate(const unsigned char* raw, const uint64_t* start, const uint64_t* end, const uint32_t* isize, const uint64_t* out_off,
+                     uint64_t n_blocks, unsigned char* out, int n_threads);
 
 /* The order-dependent grouping of collapse's read_in_data (collapse.py:595-682) over columns instead of a Python loop over
  * rows: per barcode, rows in input order found / join / kill the barcode's group (rules: csrc/group.cpp).  Host logic; the
