@@ -1,8 +1,9 @@
 """Import the UNMODIFIED reference (`/root/reference/src/decombinator`) in the build container.
 
-TEST INFRASTRUCTURE ONLY.  Used by `oracle/make_golden.py` (and by
-`tests/test_oracle_vs_reference.py`, which skips when `/root/reference` is
-absent) to record what the reference itself returns.  The missing third-party
+TEST INFRASTRUCTURE ONLY.  Used by the scripts that record what the reference
+itself returns (`oracle/make_golden.py`, `make_golden_collapse.py`,
+`make_golden_collapse_oligos.py`, `make_golden_pipeline_digest.py`,
+`time_reference.py`); nothing that runs on the GPU box imports it.  The missing third-party
 wheels are replaced by the pure-Python stand-ins in `oracle/standins/`, and
 `importlib.metadata.version("decombinator")` (decombine.py:884) is patched to
 return a string because the reference is not pip-installed.
